@@ -1,0 +1,121 @@
+// plan.h — host-side execution plan of the gate executor (no CUDA dependency).
+//
+// Pipeline:  qcb_op[] (reference vocabulary, qubit 0 = MSB)
+//              -> lower()      Gate[]   (logical index-bit space, bit = n-1-qubit; quirks applied)
+//              -> schedule()   Plan     (stages of fused shared-memory tile sweeps + qubit exchanges)
+//              -> encode       flat 64-bit word stream = the "program" the tile kernel interprets
+//
+// The same word stream is (a) uploaded to the GPU and interpreted by k_tile_stage (kernels.cu),
+// (b) returned by qcb_plan_serialize() so the CPU test-suite can check the scheduler and the encoding
+// against the oracle with the host emulator in tests/emu/ (test infrastructure, not a product path).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/qcb200.h"
+
+namespace qcb {
+
+struct cplx { double re, im; };
+
+// ---- lowered gates (logical bit space) ----
+enum GateKind : int {
+  G_MAT1 = 0,    // dense 2x2 on target bit t0, applied where (idx & cmask) == cmask
+  G_MAT2 = 1,    // dense 4x4 on bits (t1 = more significant basis bit, t0 = less significant)
+  G_SWAPP = 2,   // exchange amplitudes whose bits t0,t1 differ, multiplied by phase m[0]; control cmask
+  G_DMASK = 3,   // diagonal: amp *= m[0] where (idx & dmask) == dval
+  G_DTAB1 = 4,   // diagonal: where (idx & cmask) == cmask: amp *= (bit t0 ? m[1] : m[0])
+  G_DPOP1 = 5,   // diagonal: amp *= m[0] where popcount(idx & dmask) == 1
+  G_REFLECT = 6, // Grover diffusion 2|s><s| - I  (needs the global mean: reduction + affine pass)
+};
+
+struct Gate {
+  int kind = G_MAT1;
+  int t0 = -1, t1 = -1;        // target bits (non-diagonal action); for G_DTAB1 t0 is the table bit
+  uint64_t cmask = 0;          // control bits (all must be 1)
+  uint64_t dmask = 0, dval = 0;
+  cplx m[16] = {};
+  double frac = 1.0;           // fraction of the state a stand-alone application touches
+  int src_op = -1;             // index of the originating qcb_op
+
+  uint64_t target_mask() const;   // bits acted on non-diagonally
+  uint64_t diag_mask() const;     // bits only read (controls, diagonal operands)
+};
+
+// ---- device program encoding ----
+constexpr int OP_WORDS = 16;              // one op slot = 16 x 64-bit words
+constexpr int MAX_TILE_BITS = 13;
+constexpr int MAX_SLOT_BITS = 3;          // register-resident bits per round
+constexpr int MAX_RUNS = 16;
+
+enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_DTAB1 = 4, D_DPOP1 = 5, D_AFFINE = 6 };
+
+// Descriptor words (all uint64) — see encode_stage() for the authoritative writer.
+//   StageDesc  (STAGE_WORDS words):
+//     [0] n_local  [1] m  [2] L  [3] n_rounds  [4] n_runs  [5] ext_hi_base (rank << (n_local-m))
+//     [6] skip_mask [7] skip_val  (tile skipped unless (ext_hi & skip_mask) == skip_val)
+//     [8..8+MAX_TILE_BITS)  physical position of tile bit k (k < m), ascending; first L are 0..L-1
+//     [24..24+MAX_RUNS)     run_start | run_len << 8 : contiguous runs of non-tile positions (ascending)
+//     [40] total words of this stage (desc + rounds + ops)  [41] flags
+//   RoundDesc  (ROUND_WORDS words) x n_rounds, then op slots.
+//     [0] r  [1] n_op_slots  [2] op word offset (from stage start)  [3] n_lane
+//     [4..7)  slot_pos[3] (tile-local, ascending)   [7..10) lane_pos[3]
+//     [10] n_ins  [11..17) ins_pos[6] ascending (slot ∪ lane positions)
+constexpr int STAGE_WORDS = 48;
+constexpr int ROUND_WORDS = 20;
+constexpr uint64_t FLAG_NEEDS_SUM = 1;     // epilogue: accumulate sum of amplitudes (for the next REFLECT)
+
+enum StageKind : int { S_TILE = 0, S_EXCHANGE = 1, S_SUM = 2 };
+
+struct Round {
+  std::vector<int> slot_pos;        // tile-local positions held in registers
+  std::vector<Gate> gates;          // gates with bits already translated to ext space (see Stage)
+};
+
+struct Stage {
+  int kind = S_TILE;
+  // S_TILE
+  int m = 0, L = 0;
+  std::vector<int> tile_pos;        // physical positions of the tile bits, ascending
+  uint64_t skip_mask = 0, skip_val = 0;
+  uint64_t flags = 0;
+  std::vector<Round> rounds;
+  std::vector<int> src_gates;       // indices into the lowered gate list (for tests / stats)
+  double sweep_fraction = 1.0;      // fraction of tiles actually visited
+  // S_EXCHANGE: swap global physical bit gbit with local physical bit lbit
+  int gbit = -1, lbit = -1;
+};
+
+struct Config {
+  int n_total = 0, n_local = 0;
+  int rank = 0, world = 1;
+  int tile_bits = 12, low_bits = 4;
+  int fusion = 1, strict = 1;
+  int max_stage_cost = 0;
+  int threads = 256;
+};
+
+struct Plan {
+  Config cfg;
+  std::vector<Gate> gates;                 // lowered
+  std::vector<Stage> stages;
+  std::vector<int> perm_out;               // logical bit -> physical bit after the plan ran
+  std::vector<uint64_t> words;             // encoded program: [hdr][stage...]
+  std::vector<uint64_t> stage_offsets;     // word offset of each stage in `words`
+  uint64_t n_rounds = 0, n_exchanges = 0;
+  double algorithmic_bytes = 0, unfused_bytes = 0;
+  std::string error;
+};
+
+// qcb_op[] -> Gate[] ; returns QCB_OK or an error code with `err` set.
+int lower_ops(const Config& cfg, const qcb_op* ops, uint64_t n_ops, std::vector<Gate>& out, std::string& err);
+
+// Gate[] -> stages (+ encoded program).  perm_in: logical->physical bit map (identity when empty).
+int schedule(Plan& plan, const std::vector<int>& perm_in);
+
+// Standard 2x2 matrices of the reference (domain/gate.clj:38-283)
+void gate_matrix(int kind, double angle, cplx out[4]);
+
+Config config_from(const qcb_config& c);
+
+}  // namespace qcb

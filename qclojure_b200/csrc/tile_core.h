@@ -1,0 +1,271 @@
+// tile_core.h — the arithmetic core of the fused gate executor, shared verbatim between the CUDA
+// kernel (kernels.cu: k_tile_stage) and the host emulator used by the CPU test-suite (tests/emu/).
+//
+// Data model.  One *stage* sweeps the local state once.  A CTA owns one *tile* of 2^m amplitudes:
+// the m tile bits are the L lowest index bits (a contiguous, coalesced run of 2^L * 16 bytes) plus
+// m-L arbitrary higher bits chosen by the scheduler.  The tile lives in shared memory as interleaved
+// double2, XOR-swizzled so that 16-byte accesses of a quarter-warp fall into 8 distinct bank groups.
+// A stage is a list of *rounds*; in a round every thread keeps 2^r amplitudes (r <= 3 "slot" bits) in
+// registers and interprets the round's op list on them; rounds are separated by __syncthreads().
+//
+// The "ext" index of an amplitude = (rank | tile id | tile-local index): bit positions [0,m) are the
+// tile-local bits, [m, n_local) the tile-id bits, [n_local, n_total) the rank bits.  Control masks and
+// diagonal predicates are expressed in ext space by the scheduler (plan.cpp: to_ext).
+#pragma once
+#include <stdint.h>
+#include <vector_types.h>   // double2 (plain header, usable from g++ as well)
+
+#if defined(__CUDACC__)
+#define QCB_HD __host__ __device__ __forceinline__
+#else
+#define QCB_HD inline
+#endif
+
+namespace qcb {
+
+// must match plan.h
+enum : uint32_t { TD_MAT1 = 0, TD_MAT2 = 1, TD_SWAPP = 2, TD_DMASK = 3, TD_DTAB1 = 4, TD_DPOP1 = 5, TD_AFFINE = 6 };
+constexpr int T_OP_WORDS = 16, T_STAGE_WORDS = 48, T_ROUND_WORDS = 20;
+
+QCB_HD uint32_t swz(uint32_t i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u); }
+
+QCB_HD uint32_t insert_zero(uint32_t v, uint32_t pos) { return ((v >> pos) << (pos + 1)) | (v & ((1u << pos) - 1u)); }
+
+QCB_HD int popc64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(v);
+#else
+  return __builtin_popcountll(v);
+#endif
+}
+
+QCB_HD double as_double(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)u);
+#else
+  double d; __builtin_memcpy(&d, &u, 8); return d;
+#endif
+}
+
+QCB_HD double2 cmul(double2 a, double2 b) { return double2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+// a*b + c*d
+QCB_HD double2 cmul2(double2 a, double2 b, double2 c, double2 d) {
+  return double2{a.x * b.x - a.y * b.y + (c.x * d.x - c.y * d.y), a.x * b.y + a.y * b.x + (c.x * d.y + c.y * d.x)};
+}
+
+struct RoundCtx {
+  uint32_t r, n_slots, n_lane, n_ins;
+  uint32_t slot_pos[3], lane_pos[3], ins_pos[6];
+  const uint64_t* ops;
+};
+
+QCB_HD void decode_round(const uint64_t* stage, uint32_t round_idx, RoundCtx& rc) {
+  const uint64_t* w = stage + T_STAGE_WORDS + (uint64_t)round_idx * T_ROUND_WORDS;
+  rc.r = (uint32_t)w[0]; rc.n_slots = (uint32_t)w[1]; rc.ops = stage + w[2]; rc.n_lane = (uint32_t)w[3];
+  for (int j = 0; j < 3; ++j) { rc.slot_pos[j] = (uint32_t)w[4 + j]; rc.lane_pos[j] = (uint32_t)w[7 + j]; }
+  rc.n_ins = (uint32_t)w[10];
+  for (int j = 0; j < 6; ++j) rc.ins_pos[j] = (uint32_t)w[11 + j];
+}
+
+// group index g in [0, 2^(m-r)) -> tile-local index with all slot bits = 0
+QCB_HD uint32_t group_idx0(const RoundCtx& rc, uint32_t g) {
+  uint32_t lane = g & ((1u << rc.n_lane) - 1u);
+  uint32_t v = g >> rc.n_lane;
+  // fully unrolled with static indices so that RoundCtx stays in registers on the device
+#pragma unroll
+  for (uint32_t k = 0; k < 6; ++k) if (k < rc.n_ins) v = insert_zero(v, rc.ins_pos[k]);
+#pragma unroll
+  for (uint32_t j = 0; j < 3; ++j) if (j < rc.n_lane) v |= ((lane >> j) & 1u) << rc.lane_pos[j];
+  return v;
+}
+
+// ---- op interpreters on 2^R register-resident amplitudes.  `ext0` = ext index with slot bits 0;
+//      off[s] = tile-local offset of slot pattern s.
+template <int R>
+QCB_HD void op_mat1(double2 (&a)[1 << R], uint32_t j, uint64_t cmask, const uint64_t* mw, uint64_t ext0, const uint32_t (&off)[1 << R]) {
+  const double2 m00{as_double(mw[0]), as_double(mw[1])}, m01{as_double(mw[2]), as_double(mw[3])};
+  const double2 m10{as_double(mw[4]), as_double(mw[5])}, m11{as_double(mw[6]), as_double(mw[7])};
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    if ((uint32_t)jj != j) continue;
+#pragma unroll
+    for (int s = 0; s < (1 << R); ++s) {
+      if (s & (1 << jj)) continue;
+      const int s1 = s | (1 << jj);
+      if (((ext0 | off[s]) & cmask) == cmask) {
+        double2 a0 = a[s], a1 = a[s1];
+        a[s] = cmul2(m00, a0, m01, a1);
+        a[s1] = cmul2(m10, a0, m11, a1);
+      }
+    }
+  }
+}
+
+template <int R>
+QCB_HD void op_swapp(double2 (&a)[1 << R], uint32_t j0, uint32_t j1, uint64_t cmask, const uint64_t* mw, uint64_t ext0, const uint32_t (&off)[1 << R]) {
+  const double2 ph{as_double(mw[0]), as_double(mw[1])};
+  const bool unit = (ph.x == 1.0 && ph.y == 0.0);
+#pragma unroll
+  for (int p0 = 0; p0 < R; ++p0) {
+#pragma unroll
+    for (int p1 = p0 + 1; p1 < R; ++p1) {
+      if ((uint32_t)p0 != j0 || (uint32_t)p1 != j1) continue;
+#pragma unroll
+      for (int s = 0; s < (1 << R); ++s) {
+        if (!((s >> p0) & 1) || ((s >> p1) & 1)) continue;     // s: bit p0 = 1, bit p1 = 0
+        const int t = (s ^ (1 << p0)) | (1 << p1);            // partner: bit p0 = 0, bit p1 = 1
+        if (((ext0 | off[s]) & cmask) == cmask) {
+          double2 x = a[s], y = a[t];
+          if (!unit) { x = cmul(ph, x); y = cmul(ph, y); }
+          a[s] = y; a[t] = x;
+        }
+      }
+    }
+  }
+}
+
+template <int R>
+QCB_HD void op_mat2(double2 (&a)[1 << R], uint32_t j0, uint32_t j1, uint64_t cmask, const uint64_t* mw, uint64_t ext0, const uint32_t (&off)[1 << R]) {
+#pragma unroll
+  for (int p0 = 0; p0 < R; ++p0) {
+#pragma unroll
+    for (int p1 = p0 + 1; p1 < R; ++p1) {
+      if ((uint32_t)p0 != j0 || (uint32_t)p1 != j1) continue;
+#pragma unroll
+      for (int s = 0; s < (1 << R); ++s) {
+        if (((s >> p0) & 1) || ((s >> p1) & 1)) continue;
+        if (((ext0 | off[s]) & cmask) != cmask) continue;
+        const int i0 = s, i1 = s | (1 << p0), i2 = s | (1 << p1), i3 = s | (1 << p0) | (1 << p1);
+        const double2 v0 = a[i0], v1 = a[i1], v2 = a[i2], v3 = a[i3];
+        double2 o[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint64_t* row = mw + r * 8;
+          double2 c0{as_double(row[0]), as_double(row[1])}, c1{as_double(row[2]), as_double(row[3])};
+          double2 c2{as_double(row[4]), as_double(row[5])}, c3{as_double(row[6]), as_double(row[7])};
+          double2 t0 = cmul2(c0, v0, c1, v1), t1 = cmul2(c2, v2, c3, v3);
+          o[r] = double2{t0.x + t1.x, t0.y + t1.y};
+        }
+        a[i0] = o[0]; a[i1] = o[1]; a[i2] = o[2]; a[i3] = o[3];
+      }
+    }
+  }
+}
+
+template <int R>
+QCB_HD void apply_ops(double2 (&a)[1 << R], const uint64_t* ops, uint32_t n_slots, uint64_t ext0,
+                      const uint32_t (&off)[1 << R], const double* dev_vals) {
+  for (uint32_t s = 0; s < n_slots;) {
+    const uint64_t* w = ops + (uint64_t)s * T_OP_WORDS;
+    const uint64_t hdr = w[0];
+    const uint32_t kind = (uint32_t)(hdr & 0xff), j0 = (uint32_t)((hdr >> 8) & 0xff), j1 = (uint32_t)((hdr >> 16) & 0xff);
+    const uint32_t ns = (uint32_t)((hdr >> 24) & 0xff);
+    switch (kind) {
+      case TD_MAT1: op_mat1<R>(a, j0, w[1], w + 4, ext0, off); break;
+      case TD_MAT2: op_mat2<R>(a, j0, j1, w[1], w + 4, ext0, off); break;
+      case TD_SWAPP: op_swapp<R>(a, j0, j1, w[1], w + 4, ext0, off); break;
+      case TD_DMASK: {
+        const uint64_t mask = w[1], val = w[2];
+        const double2 ph{as_double(w[4]), as_double(w[5])};
+#pragma unroll
+        for (int k = 0; k < (1 << R); ++k)
+          if (((ext0 | off[k]) & mask) == val) a[k] = cmul(a[k], ph);
+        break;
+      }
+      case TD_DTAB1: {
+        const uint64_t cmask = w[1]; const uint32_t bit = (uint32_t)w[2];
+        const double2 p0{as_double(w[4]), as_double(w[5])}, p1{as_double(w[6]), as_double(w[7])};
+#pragma unroll
+        for (int k = 0; k < (1 << R); ++k) {
+          const uint64_t e = ext0 | off[k];
+          if ((e & cmask) == cmask) a[k] = cmul(a[k], ((e >> bit) & 1) ? p1 : p0);
+        }
+        break;
+      }
+      case TD_DPOP1: {
+        const uint64_t mask = w[1];
+        const double2 ph{as_double(w[4]), as_double(w[5])};
+#pragma unroll
+        for (int k = 0; k < (1 << R); ++k)
+          if (popc64((ext0 | off[k]) & mask) == 1) a[k] = cmul(a[k], ph);
+        break;
+      }
+      case TD_AFFINE: {   // a' = alpha * a + beta, (alpha, beta) produced on the device by a reduction
+        const double* v = dev_vals + 4 * w[2];
+        const double2 al{v[0], v[1]}, be{v[2], v[3]};
+#pragma unroll
+        for (int k = 0; k < (1 << R); ++k) { double2 t = cmul(al, a[k]); a[k] = double2{t.x + be.x, t.y + be.y}; }
+        break;
+      }
+      default: break;
+    }
+    s += (ns ? ns : 1u);
+  }
+}
+
+// One thread's share of a round: groups g = tid, tid+T, ... ; tile = swizzled shared-memory tile.
+template <int R>
+QCB_HD void run_round_thread(double2* tile, const RoundCtx& rc, uint32_t m, uint64_t ext_hi, uint32_t tid, uint32_t nthreads,
+                             const double* dev_vals) {
+  uint32_t off[1 << R];
+#pragma unroll
+  for (int s = 0; s < (1 << R); ++s) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) if ((s >> j) & 1) o |= 1u << rc.slot_pos[j];
+    off[s] = o;
+  }
+  const uint32_t ngroups = 1u << (m - R);
+  for (uint32_t g = tid; g < ngroups; g += nthreads) {
+    const uint32_t idx0 = group_idx0(rc, g);
+    double2 a[1 << R];
+#pragma unroll
+    for (int s = 0; s < (1 << R); ++s) a[s] = tile[swz(idx0 | off[s])];
+    apply_ops<R>(a, rc.ops, rc.n_slots, (ext_hi << m) | idx0, off, dev_vals);
+#pragma unroll
+    for (int s = 0; s < (1 << R); ++s) tile[swz(idx0 | off[s])] = a[s];
+  }
+}
+
+// ---- tile addressing
+struct StageCtx {
+  uint32_t n_local, m, L, n_rounds, n_runs;
+  uint64_t ext_hi_base, skip_mask, skip_val;
+};
+
+QCB_HD void decode_stage(const uint64_t* st, StageCtx& sc) {
+  sc.n_local = (uint32_t)st[0]; sc.m = (uint32_t)st[1]; sc.L = (uint32_t)st[2]; sc.n_rounds = (uint32_t)st[3];
+  sc.n_runs = (uint32_t)st[4]; sc.ext_hi_base = st[5]; sc.skip_mask = st[6]; sc.skip_val = st[7];
+}
+
+// active-tile ordinal -> tile id (deposit into the tile-id bits not fixed by skip_mask, OR the fixed value)
+QCB_HD uint64_t active_to_tile(const StageCtx& sc, uint64_t a) {
+  const uint32_t nb = sc.n_local - sc.m;
+  const uint64_t tmask = (nb >= 64) ? ~0ULL : ((1ULL << nb) - 1ULL);
+  const uint64_t fixed = sc.skip_mask & tmask;
+  if (!fixed) return a;
+  uint64_t t = sc.skip_val & fixed, src = a;
+  for (uint32_t b = 0; b < nb; ++b)
+    if (!((fixed >> b) & 1ULL)) { t |= (src & 1ULL) << b; src >>= 1; }
+  return t;
+}
+
+// tile id -> base amplitude offset (tile bits = 0): scatter the id over the runs of non-tile positions
+QCB_HD uint64_t tile_base(const uint64_t* st, const StageCtx& sc, uint64_t tile) {
+  uint64_t base = 0, t = tile;
+  for (uint32_t k = 0; k < sc.n_runs; ++k) {
+    const uint32_t start = (uint32_t)(st[24 + k] & 0xff), len = (uint32_t)(st[24 + k] >> 8);
+    base |= (t & ((1ULL << len) - 1ULL)) << start;
+    t >>= len;
+  }
+  return base;
+}
+
+// offset contributed by the high tile bits (tile-local bits L..m-1) for hi = local >> L
+QCB_HD uint64_t hi_offset(const uint64_t* st, const StageCtx& sc, uint32_t hi) {
+  uint64_t o = 0;
+  for (uint32_t k = sc.L; k < sc.m; ++k) o |= (uint64_t)((hi >> (k - sc.L)) & 1u) << st[8 + k];
+  return o;
+}
+
+}  // namespace qcb

@@ -1,0 +1,126 @@
+// emu.cpp — HOST EMULATOR of the tile executor.  TEST INFRASTRUCTURE ONLY.
+//
+// It runs the scheduler's encoded program (plan.cpp) with the very same interpreter code the CUDA
+// kernel uses (csrc/tile_core.h), replacing the CTA/thread grid by plain loops: every __syncthreads()
+// boundary of k_tile_stage becomes a loop boundary here.  This lets the CPU test-suite check the
+// scheduler, the ext-index encoding, the swizzle/lane mapping and the op interpreters against the
+// oracle without a GPU.  It is built into tests/emu/libqcbemu.so by the tests themselves; nothing in
+// qclojure_b200/ or libqcb200.so links, loads or falls back to it.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../qclojure_b200/csrc/plan.h"
+#include "../../qclojure_b200/csrc/tile_core.h"
+
+using namespace qcb;
+
+struct Emu {
+  Plan plan;
+  std::string err;
+};
+
+extern "C" {
+
+int emu_create(const qcb_config* cfg, const qcb_op* ops, uint64_t n_ops, const int32_t* perm_in, Emu** out) {
+  Emu* e = new Emu();
+  e->plan.cfg = config_from(*cfg);
+  int rc = lower_ops(e->plan.cfg, ops, n_ops, e->plan.gates, e->err);
+  if (rc == QCB_OK) {
+    std::vector<int> perm;
+    if (perm_in) perm.assign(perm_in, perm_in + cfg->n_qubits);
+    rc = schedule(e->plan, perm);
+    if (rc != QCB_OK) e->err = e->plan.error;
+  }
+  *out = e;
+  return rc;
+}
+
+const char* emu_error(Emu* e) { return e->err.c_str(); }
+void emu_destroy(Emu* e) { delete e; }
+uint64_t emu_num_stages(Emu* e) { return e->plan.stages.size(); }
+int emu_stage_kind(Emu* e, uint64_t i) { return e->plan.stages[i].kind; }
+void emu_stage_exchange(Emu* e, uint64_t i, int* gbit, int* lbit) { *gbit = e->plan.stages[i].gbit; *lbit = e->plan.stages[i].lbit; }
+uint64_t emu_num_rounds(Emu* e) { return e->plan.n_rounds; }
+uint64_t emu_num_gates(Emu* e) { return e->plan.gates.size(); }
+double emu_algorithmic_bytes(Emu* e) { return e->plan.algorithmic_bytes; }
+double emu_unfused_bytes(Emu* e) { return e->plan.unfused_bytes; }
+void emu_perm_out(Emu* e, int32_t* out) { for (size_t b = 0; b < e->plan.perm_out.size(); ++b) out[b] = e->plan.perm_out[b]; }
+uint64_t emu_stage_num_gates(Emu* e, uint64_t i) { return e->plan.stages[i].src_gates.size(); }
+uint64_t emu_stage_num_rounds(Emu* e, uint64_t i) { return e->plan.stages[i].rounds.size(); }
+double emu_stage_fraction(Emu* e, uint64_t i) { return e->plan.stages[i].sweep_fraction; }
+
+// bank-conflict audit of one stage: worst number of distinct 16-byte bank-group collisions in any
+// quarter-warp of any round (1 = conflict free)
+int emu_stage_max_conflict(Emu* e, uint64_t si, int nthreads) {
+  const uint64_t* st = e->plan.words.data() + e->plan.stage_offsets[si] + 2;
+  StageCtx sc; decode_stage(st, sc);
+  int worst = 1;
+  for (uint32_t r = 0; r < sc.n_rounds; ++r) {
+    RoundCtx rc; decode_round(st, r, rc);
+    uint32_t ngroups = 1u << (sc.m - rc.r);
+    for (uint32_t g0 = 0; g0 < ngroups && g0 < (uint32_t)nthreads; g0 += 8) {
+      for (uint32_t s = 0; s < (1u << rc.r); ++s) {
+        uint32_t off = 0;
+        for (uint32_t j = 0; j < rc.r; ++j) if ((s >> j) & 1) off |= 1u << rc.slot_pos[j];
+        int cnt[8] = {0};
+        for (uint32_t l = 0; l < 8 && g0 + l < ngroups; ++l) cnt[swz(group_idx0(rc, g0 + l) | off) & 7]++;
+        for (int b = 0; b < 8; ++b) if (cnt[b] > worst) worst = cnt[b];
+      }
+    }
+  }
+  return worst;
+}
+
+// Run one S_TILE stage on this rank's local slice.
+int emu_run_tile_stage(Emu* e, uint64_t si, double* state, const double* dev_vals, int nthreads) {
+  const Stage& S = e->plan.stages[si];
+  if (S.kind != S_TILE) return QCB_ERR_INVALID;
+  const uint64_t* st = e->plan.words.data() + e->plan.stage_offsets[si] + 2;
+  StageCtx sc; decode_stage(st, sc);
+  double2* gs = reinterpret_cast<double2*>(state);
+  const uint32_t tile_n = 1u << sc.m;
+  std::vector<double2> tile(tile_n);
+  const uint32_t nb = sc.n_local - sc.m;
+  const uint64_t tmask = (nb >= 64) ? ~0ULL : ((1ULL << nb) - 1ULL);
+  const uint64_t n_active = (1ULL << nb) >> __builtin_popcountll(sc.skip_mask & tmask);
+  // rank-level skip (the part of the condition that lives in the rank bits)
+  if (((sc.ext_hi_base & sc.skip_mask & ~tmask) != (sc.skip_val & ~tmask))) return QCB_OK;
+  for (uint64_t a = 0; a < n_active; ++a) {
+    const uint64_t t = active_to_tile(sc, a);
+    const uint64_t ext_hi = sc.ext_hi_base | t;
+    const uint64_t base = tile_base(st, sc, t);
+    for (uint32_t i = 0; i < tile_n; ++i)
+      tile[swz(i)] = gs[base + hi_offset(st, sc, i >> sc.L) + (i & ((1u << sc.L) - 1u))];
+    for (uint32_t r = 0; r < sc.n_rounds; ++r) {
+      RoundCtx rc; decode_round(st, r, rc);
+      for (uint32_t tid = 0; tid < (uint32_t)nthreads; ++tid) {
+        switch (rc.r) {
+          case 0: run_round_thread<0>(tile.data(), rc, sc.m, ext_hi, tid, nthreads, dev_vals); break;
+          case 1: run_round_thread<1>(tile.data(), rc, sc.m, ext_hi, tid, nthreads, dev_vals); break;
+          case 2: run_round_thread<2>(tile.data(), rc, sc.m, ext_hi, tid, nthreads, dev_vals); break;
+          default: run_round_thread<3>(tile.data(), rc, sc.m, ext_hi, tid, nthreads, dev_vals); break;
+        }
+      }
+    }
+    for (uint32_t i = 0; i < tile_n; ++i)
+      gs[base + hi_offset(st, sc, i >> sc.L) + (i & ((1u << sc.L) - 1u))] = tile[swz(i)];
+  }
+  return QCB_OK;
+}
+
+// S_SUM partial: sum of this rank's amplitudes
+void emu_local_sum(const double* state, uint64_t count, double out[2]) {
+  double re = 0, im = 0;
+  for (uint64_t i = 0; i < count; ++i) { re += state[2 * i]; im += state[2 * i + 1]; }
+  out[0] = re; out[1] = im;
+}
+
+uint64_t emu_program_words(Emu* e, uint64_t* out, uint64_t cap) {
+  uint64_t n = e->plan.words.size();
+  if (out) std::memcpy(out, e->plan.words.data(), sizeof(uint64_t) * (n < cap ? n : cap));
+  return n;
+}
+
+}  // extern "C"

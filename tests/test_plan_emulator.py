@@ -1,0 +1,174 @@
+"""CPU checks of the host side of the gate executor: lowering, fusion scheduler, program encoding
+and the op interpreters (shared header csrc/tile_core.h), run through the host emulator against the
+oracle.  The emulator is test infrastructure (tests/emu/); the GPU parity tests are in test_gpu_*.py."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import qc_oracle as O
+from qclojure_b200 import circuits as C
+from tests.emu import emu as E
+from tests.test_oracle_c import _all_gates_circuit
+
+TOL = 1e-10
+
+
+def _rand_state(n, seed):
+    rng = np.random.default_rng(seed)
+    s = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    return s / np.linalg.norm(s)
+
+
+@pytest.mark.parametrize("n,tile,low,fusion", [
+    (1, 0, 0, 1), (2, 0, 0, 1), (3, 0, 0, 1), (5, 0, 0, 1), (6, 4, 2, 1), (8, 5, 2, 1), (9, 6, 3, 0),
+    (10, 7, 4, 1), (11, 8, 3, 1), (13, 10, 4, 1), (14, 12, 4, 1), (12, 12, 4, 0)])
+def test_emulated_executor_matches_oracle_all_gates(n, tile, low, fusion):
+    rng = np.random.default_rng(7 * n + tile)
+    if n >= 3:
+        circ = _all_gates_circuit(n, rng)
+    else:
+        circ = C.create_circuit(n)
+        for _ in range(20):
+            q = int(rng.integers(0, n))
+            C.add_gate(circ, ["h", "x", "y", "z", "s", "t"][rng.integers(0, 6)], target=q)
+            C.rx(circ, q, rng.random()); C.rz(circ, q, rng.random())
+            if n == 2:
+                C.cnot(circ, q, 1 - q); C.crz(circ, 1 - q, q, 0.3); C.swap(circ, 0, 1)
+    init = _rand_state(n, n)
+    want = O.execute_circuit(circ, init)
+    got = E.run_world(n, circ["operations"], init, tile_bits=tile, low_bits=low, fusion=fusion)
+    assert np.max(np.abs(got - want)) <= TOL
+
+
+@pytest.mark.parametrize("builder", ["qft", "ghz", "brick"])
+def test_emulated_configs(builder):
+    n = 12
+    circ = {"qft": C.quantum_fourier_transform_circuit, "ghz": C.ghz_state_circuit,
+            "brick": lambda k: C.random_brickwork_circuit(k, 8)}[builder](n)
+    want = O.execute_circuit(circ)
+    got, plans = E.run_world(n, circ["operations"], tile_bits=8, low_bits=3, return_plans=True)
+    assert np.max(np.abs(got - want)) <= TOL
+    # fusion must actually fuse: far fewer sweeps than gates
+    assert plans[0].num_stages < plans[0].num_gates
+
+
+def test_unfused_mode_is_one_sweep_per_gate_with_partial_sweeps():
+    n = 12
+    circ = C.create_circuit(n)
+    C.h(circ, 0); C.cnot(circ, 0, 1); C.cz(circ, 2, 3); C.z(circ, 1); C.toffoli(circ, 0, 1, 2); C.rz(circ, 5, 0.2)
+    got, plans = E.run_world(n, circ["operations"], tile_bits=6, low_bits=3, fusion=0, return_plans=True)
+    assert np.max(np.abs(got - O.execute_circuit(circ))) <= TOL
+    p = plans[0]
+    assert p.num_stages == 6
+    fr = [p.stage_info(i)["fraction"] for i in range(6)]
+    # H: full sweep; CNOT: control-half only; CZ: quarter; Z: half; Toffoli: quarter; RZ: full
+    assert fr == [1.0, 0.5, 0.25, 0.5, 0.25, 1.0]
+    assert p.algorithmic_bytes() == pytest.approx(32 * 2 ** n * sum(fr))
+    assert p.unfused_bytes() == pytest.approx(32 * 2 ** n * sum(fr))
+
+
+def test_strict_parity_flag():
+    n = 4
+    circ = C.create_circuit(n)
+    C.h(circ, 0); C.h(circ, 2); C.cry(circ, 0, 1, 0.7); C.swap(circ, 0, 1); C.iswap(circ, 0, 2)
+    strict = E.run_world(n, circ["operations"], strict_parity=1)
+    assert np.max(np.abs(strict - O.execute_circuit(circ))) <= TOL
+    # textbook semantics: CRY applies RY(theta) (not the transpose), swap operands are qubit numbers
+    st = O.zero_state(n)
+    st = O.apply_single_qubit_gate(st, O.HADAMARD, 0)
+    st = O.apply_single_qubit_gate(st, O.HADAMARD, 2)
+    st = O.apply_controlled_gate(st, 0, 1, O.ry_gate(0.7).T)      # oracle applies U^T, so pass U^T to get U
+    st = O.swap_gate(st, n - 1 - 0, n - 1 - 1)
+    st = O.iswap_gate(st, n - 1 - 0, n - 1 - 2)
+    text = E.run_world(n, circ["operations"], strict_parity=0)
+    assert np.max(np.abs(text - st)) <= TOL
+    # :i and :cy: rejected like the reference under strict parity, accepted otherwise
+    bad = C.add_gate(C.create_circuit(2), "cy", control=0, target=1)
+    with pytest.raises(E.EmuError) as ei:
+        E.EmuPlan(2, bad["operations"], strict_parity=1)
+    assert ei.value.code == -2
+    ok = E.run_world(2, C.h(C.create_circuit(2), 0)["operations"] + bad["operations"], strict_parity=0)
+    want = O.apply_controlled_gate(O.apply_single_qubit_gate(O.zero_state(2), O.HADAMARD, 0), 0, 1, O.PAULI_Y.T)
+    assert np.max(np.abs(ok - want)) <= TOL
+
+
+def test_generic_ops_u1q_cu1q_u2q_mcphase_oracle_diffusion():
+    n = 6
+    rng = np.random.default_rng(3)
+    init = _rand_state(n, 11)
+
+    def runitary(d):
+        a = rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))
+        q, _ = np.linalg.qr(a)
+        return q
+
+    U1, U2, CU = runitary(2), runitary(4), runitary(2)
+    ops = [{"operation-type": "u1q", "operation-params": {"target": 4, "matrix": U1}},
+           {"operation-type": "cu1q", "operation-params": {"control": 1, "target": 3, "matrix": CU}},
+           {"operation-type": "u2q", "operation-params": {"qubit1": 5, "qubit2": 2, "matrix": U2}},
+           {"operation-type": "u2q", "operation-params": {"qubit1": 0, "qubit2": 4, "matrix": U2}},
+           {"operation-type": "mcphase", "operation-params": {"qubit-indices": [0, 2, 5], "angle": 0.9}},
+           {"operation-type": "phase-oracle", "operation-params": {"index": 37}},
+           {"operation-type": "grover-diffusion", "operation-params": {}},
+           {"operation-type": "h", "operation-params": {"target": 1}},
+           {"operation-type": "grover-diffusion", "operation-params": {}}]
+    # reference model with dense matrices
+    def kron_on(mats):  # mats: dict qubit->2x2
+        full = np.array([[1.0 + 0j]])
+        for q in range(n):
+            full = np.kron(full, mats.get(q, np.eye(2)))
+        return full
+    st = init.copy()
+    st = kron_on({4: U1}) @ st
+    st = O.apply_controlled_gate(st, 1, 3, CU.T)
+    def apply_u2(st, qa, qb, U):
+        idx = np.arange(1 << n)
+        out = np.zeros_like(st)
+        ba, bb = n - 1 - qa, n - 1 - qb
+        for i in idx:
+            col = (((i >> ba) & 1) << 1) | ((i >> bb) & 1)
+            base = i & ~((1 << ba) | (1 << bb))
+            for row in range(4):
+                j = base | (((row >> 1) & 1) << ba) | ((row & 1) << bb)
+                out[j] += U[row, col] * st[i]
+        return out
+    st = apply_u2(st, 5, 2, U2)
+    st = apply_u2(st, 0, 4, U2)
+    idx = np.arange(1 << n)
+    allone = np.ones_like(idx, dtype=bool)
+    for q in (0, 2, 5):
+        allone &= ((idx >> (n - 1 - q)) & 1) == 1
+    st = np.where(allone, st * np.exp(1j * 0.9), st)
+    st[37] *= -1
+    st = 2 * np.mean(st) - st
+    st = O.apply_single_qubit_gate(st, O.HADAMARD, 1)
+    st = 2 * np.mean(st) - st
+    got = E.run_world(n, ops, init, tile_bits=4, low_bits=2)
+    assert np.max(np.abs(got - st)) <= TOL
+
+
+def test_grover_operator_matches_gate_level_circuit():
+    """fused oracle+diffusion operators validated against the reference's
+    gate-level Grover circuit (tests/golden/tutorial_cases.json, doc/tutorial.md:5832; 3 qubits, target 5)."""
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tutorial_cases.json")) as f:
+        case = [c for c in json.load(f)["cases"] if c["name"] == "Grover Search"][0]
+    n = 3
+    ops = [{"operation-type": "global-h", "operation-params": {}}]
+    for _ in range(2):
+        ops += [{"operation-type": "phase-oracle", "operation-params": {"index": 5}},
+                {"operation-type": "grover-diffusion", "operation-params": {}}]
+    got = E.run_world(n, ops)
+    want_p = np.array(case["measurement_results"][":measurement-probabilities"])
+    assert np.max(np.abs(np.abs(got) ** 2 - want_p)) <= TOL
+
+
+def test_bank_conflict_free_lane_mapping():
+    """Every round of a 30-qubit brickwork plan must give conflict-free 16-byte shared-memory access
+    (the swizzle + lane choice of plan.cpp:choose_lanes)."""
+    circ = C.random_brickwork_circuit(30, 20)
+    p = E.EmuPlan(30, circ["operations"])
+    worst = max(p.max_conflict(i) for i in range(p.num_stages) if p.stage_kind(i) == E.S_TILE)
+    assert worst == 1
+    assert p.num_stages < p.num_gates / 4
