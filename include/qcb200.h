@@ -83,6 +83,9 @@ enum qcb_op_kind {
   QCB_OP_MCPHASE,          /* mask = qubit set: multiply by e^{i angle} where ALL listed qubits are 1 (multi-controlled Z/phase) */
   QCB_OP_PHASE_ORACLE,     /* mask = basis-state index to mark: amplitude[index] *= -1 (Grover oracle, application/algorithm/grover.clj:38-120 as an operator) */
   QCB_OP_GROVER_DIFFUSION, /* 2|s><s| - I over all qubits (grover.clj:122-190 as an operator)    */
+  QCB_OP_MEASURE,          /* :measure (circuit.clj:1086-1092): ext -> int32[n_mask] qubit list (outcome bit i <->
+                              i-th listed qubit), angle = the uniform draw u in [0,1) (ignored by qcb_run_noisy,
+                              which takes the draw from its stream); collapses + renormalises            */
   QCB_OP_KIND_COUNT
 };
 
@@ -94,7 +97,7 @@ typedef struct qcb_op {
   uint64_t mask;       /* qubit set or basis index, see kinds                            */
   double   angle;
   double   mat[8];     /* 2x2 complex row-major for U1Q / CU1Q                           */
-  const double* ext;   /* U2Q: 32 doubles; otherwise NULL. Only read during the call.    */
+  const void* ext;     /* U2Q: 32 doubles; MEASURE: int32[n_mask]; otherwise NULL. Only read during the call. */
 } qcb_op;
 
 /* ---- library-level ---- */
@@ -191,6 +194,10 @@ typedef struct qcb_stats {
   double   exchange_ms;       /* device time spent in exchanges                                 */
 } qcb_stats;
 int32_t qcb_get_stats(qcb_handle h, qcb_stats* out);
+/* CUDA-event stopwatch on the handle's own stream (the stream every kernel of this handle is launched on):
+   start records an event; stop records a second one, synchronises on it and returns the elapsed device ms. */
+int32_t qcb_timer_start(qcb_handle h);
+int32_t qcb_timer_stop(qcb_handle h, double* out_ms);
 
 /* ---- host-only planning API (no GPU needed): what the scheduler would do with an op list.
         Used by the CPU test-suite and by INTEGRATION diagnostics. ---- */

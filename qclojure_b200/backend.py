@@ -1,0 +1,440 @@
+"""Host-side mirror of the reference's backend protocol on top of libqcb200.so.
+
+`B200Simulator` mirrors `LocalQuantumSimulator` (src/org/soulspace/qclojure/adapter/backend/
+ideal_simulator.clj:100-176) and `B200HardwareSimulator` mirrors `QuantumHardwareSimulator`
+(adapter/backend/hardware_simulator.clj:281-391): the eight `QuantumBackend` protocol methods
+(application/backend.clj:72-112) with the same names (kebab-case -> snake_case), argument meaning,
+result-map keys and error behaviour, so that the parity tests read like the reference's own tests.
+Keyword keys are plain strings without the colon ("job-status", "measurement-results", ...).
+
+Differences that are deliberate and documented in DESIGN.md:
+  * randomness: the reference draws from Math/random with no seeding hook; here draws come from
+    `options["uniforms"]` (explicit array) or `options["seed"]`/config seed through NumPy's PCG64, so a run
+    is reproducible and can be compared shot by shot with the oracle;
+  * `:final-state` / `:measurement-probabilities` are returned as NumPy arrays up to `max_state_qubits`
+    (default 26) and as a lazy device handle above it (a 2^30-entry Clojure vector is not representable);
+  * small jobs (<= 20 qubits) complete inside `submit_circuit`, so the first status poll already sees
+    "completed" (the reference's blocking helper sleeps 100 ms between polls, backend.clj:255).
+"""
+from __future__ import annotations
+
+import itertools
+import threading
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _lib as L
+from . import noise as NZ
+from . import ops as OPS
+
+_job_counter = itertools.count(1)
+_jobs_lock = threading.Lock()
+# process-global job table shared by all simulator instances, like the reference's atom
+# (ideal_simulator.clj:56-57)
+_JOBS: Dict[str, dict] = {}
+
+NATIVE_GATES = sorted(["i", "x", "y", "z", "h", "s", "s-dag", "t", "t-dag", "rx", "ry", "rz", "phase", "cnot", "cz", "cy",
+                       "swap", "crx", "cry", "crz", "toffoli", "fredkin"])     # operation_registry.clj:380-383
+
+
+def _kw(x):
+    return x[1:] if isinstance(x, str) and x.startswith(":") else x
+
+
+def _opt(d: Optional[dict], key: str, default=None):
+    if not d:
+        return default
+    if key in d:
+        return d[key]
+    if ":" + key in d:
+        return d[":" + key]
+    return default
+
+
+def circuit_metadata(circuit: dict) -> dict:
+    """circuit-depth / operation-count / gate-count (domain/circuit.clj:1370-1440; greedy layering)."""
+    ops = OPS.circuit_ops(circuit)
+    n = OPS.circuit_num_qubits(circuit)
+    layers = [0] * n
+    gates = 0
+    for op in ops:
+        typ, p = OPS.normalize_op(op)
+        qs = []
+        for k in ("target", "control", "control1", "control2", "target1", "target2", "qubit1", "qubit2"):
+            if p.get(k) is not None:
+                qs.append(int(p[k]))
+        for k in ("measurement-qubits", "qubit-indices"):
+            if p.get(k) is not None:
+                qs += [int(q) for q in p[k]]
+        if typ.startswith("global-"):
+            qs = list(range(n))
+        if typ != "measure":
+            gates += 1
+        if not qs:
+            continue
+        lvl = max(layers[q] for q in qs) + 1
+        for q in qs:
+            layers[q] = lvl
+    return {"circuit-depth": max(layers) if ops else 0, "circuit-operation-count": len(ops), "circuit-gate-count": gates}
+
+
+class DeviceStateHandle:
+    """Lazy view of a final state that is too large to materialise as a host vector."""
+
+    def __init__(self, sv: L.StateVector):
+        self._sv = sv
+        self.num_qubits = sv.n
+
+    def slice(self, offset: int, count: int) -> np.ndarray:
+        return self._sv.get_state(offset, count)
+
+    def amplitudes(self, indices) -> np.ndarray:
+        return self._sv.get_amplitudes(indices)
+
+    def probabilities(self, offset: int, count: int) -> np.ndarray:
+        return self._sv.probabilities(offset, count)
+
+
+class _BackendBase:
+    backend_type = "simulator"
+
+    def __init__(self, config: Optional[dict] = None):
+        self.config = dict(config or {})
+        self._svs: Dict[int, L.StateVector] = {}
+        self._lock = threading.RLock()
+        self._rng = np.random.default_rng(_opt(self.config, "seed"))
+        self.max_state_qubits = int(_opt(self.config, "max-state-qubits", 26))
+        self._workers: List[threading.Thread] = []
+
+    # -- handles are cached per qubit count (one state vector resident in HBM each)
+    def _sv(self, n: int) -> L.StateVector:
+        sv = self._svs.get(n)
+        if sv is None:
+            for old in list(self._svs):            # keep HBM for the one in use
+                self._svs.pop(old).close()
+            sv = L.StateVector(n, device=int(_opt(self.config, "device", -1)),
+                               fusion=int(_opt(self.config, "fusion", 1)),
+                               strict_parity=int(_opt(self.config, "strict-parity", 1)))
+            self._svs[n] = sv
+        return sv
+
+    def close(self):
+        for t in self._workers:
+            t.join()
+        for sv in self._svs.values():
+            sv.close()
+        self._svs.clear()
+
+    # -- QuantumBackend protocol (application/backend.clj:72-112)
+    def available(self) -> bool:
+        return L.device_count() > 0
+
+    def job_status(self, job_id: str) -> str:
+        with _jobs_lock:
+            job = _JOBS.get(job_id)
+        return job["status"] if job else "not-found"
+
+    def job_result(self, job_id: str) -> dict:
+        with _jobs_lock:
+            job = _JOBS.get(job_id)
+        if not job:
+            return {"job-id": job_id, "job-status": "not-found", "error-message": "Job not found"}
+        if job["status"] == "completed":
+            return dict(job["result"], **{"job-id": job_id})
+        out = {"job-id": job_id, "job-status": job["status"], "error-message": "Job not completed"}
+        if job.get("result") and job["result"].get("error-message"):
+            out["failure-message"] = job["result"]["error-message"]        # superset: the reference drops it
+            out["exception-type"] = job["result"].get("exception-type")
+        return out
+
+    def cancel_job(self, job_id: str) -> str:
+        with _jobs_lock:
+            job = _JOBS.get(job_id)
+            if not job:
+                return "not-found"
+            if job["status"] in ("queued", "running"):
+                job["status"] = "cancelled"
+                job["completed-at"] = time.time()
+                return "cancelled"
+            return "cannot-cancel"
+
+    def queue_status(self) -> dict:
+        with _jobs_lock:
+            jobs = list(_JOBS.values())
+        cnt = lambda s: sum(1 for j in jobs if j["status"] == s)   # noqa: E731
+        return {"total-jobs": len(jobs), "queued": cnt("queued"), "running": cnt("running"), "completed": cnt("completed"),
+                "backend-load": 0.0, "estimated-wait-time": 0}
+
+    def submit_circuit(self, circuit: dict, options: Optional[dict] = None) -> str:
+        options = options or {}
+        job_id = f"{self._job_prefix}_{next(_job_counter)}_{int(time.time() * 1000)}"
+        job = {"job-id": job_id, "circuit": circuit, "options": options, "status": "queued", "result": None,
+               "created-at": time.time(), "completed-at": None}
+        with _jobs_lock:
+            _JOBS[job_id] = job
+
+        def work():
+            with _jobs_lock:
+                if job["status"] == "cancelled":
+                    return
+                job["status"] = "running"
+            result = self._execute_guarded(circuit, options)
+            with _jobs_lock:
+                if job["status"] != "cancelled":
+                    job["status"] = result["job-status"]
+                    job["result"] = result
+                    job["completed-at"] = time.time()
+
+        if OPS.circuit_num_qubits(circuit) <= 20:
+            work()
+        else:
+            t = threading.Thread(target=work, daemon=True)
+            self._workers.append(t)
+            t.start()
+        return job_id
+
+    def _execute_guarded(self, circuit, options) -> dict:
+        # never throw out of the worker (ideal_simulator.clj:93-96, hardware_simulator.clj:187-191)
+        t0 = time.time()
+        try:
+            with self._lock:
+                res = self._execute(circuit, options)
+            res["execution-time-ms"] = int((time.time() - t0) * 1000)
+            return res
+        except Exception as e:      # noqa: BLE001
+            return {"job-status": "failed", "error-message": str(e), "exception-type": type(e).__name__}
+
+    def _uniforms(self, options, shape):
+        u = _opt(options, "uniforms")
+        if u is not None:
+            u = np.asarray(u, dtype=np.float64)
+            if u.size < int(np.prod(shape)):
+                raise ValueError("not enough uniforms supplied")
+            return u.reshape(-1)[: int(np.prod(shape))].reshape(shape)
+        seed = _opt(options, "seed")
+        rng = np.random.default_rng(seed) if seed is not None else self._rng
+        return rng.random(shape)
+
+
+# =============================================================================== ideal simulator
+class B200Simulator(_BackendBase):
+    """Mirror of LocalQuantumSimulator (ideal_simulator.clj:100-176) running on the B200."""
+
+    _job_prefix = "sim_job"
+
+    def backend_info(self) -> dict:
+        return {"backend-type": "simulator", "backend-name": "B200 State-Vector Simulator",
+                "description": "B200-native fp64 state-vector simulator (libqcb200.so) behind the QuantumBackend protocol",
+                "backend-config": self.config, "max-qubits": int(_opt(self.config, "max-qubits", 33)),
+                "capabilities": {"quantum-backend"}, "device": self.device(), "version": "0.1.0"}
+
+    def device(self) -> dict:
+        return {"id": "b200-simulator", "name": "B200 Ideal Quantum Simulator", "provider": "qclojure_b200",
+                "platform": "Local", "technology": "simulator", "num-qubits": 33, "topology": "all-to-all",
+                "connectivity": "full", "native-gates": NATIVE_GATES, "virtual-gates": [],
+                "supported-operations": NATIVE_GATES, "measurement-basis": "any", "noise-model": {},
+                "performance": {"gate-fidelity": 1.0, "readout-fidelity": 1.0}}
+
+    # circuit/execute-circuit + result/extract-results (domain/circuit.clj:1778-1792, domain/result.clj:535-639)
+    def _execute(self, circuit: dict, options: dict) -> dict:
+        n = OPS.circuit_num_qubits(circuit)
+        ops = OPS.circuit_ops(circuit)
+        specs = _opt(options, "result-specs") or {}
+        sv = self._sv(n)
+        init = _opt(options, "initial-state")
+        if init is not None:
+            vec = init.get("state-vector", init.get(":state-vector")) if isinstance(init, dict) else init
+            sv.set_state(np.asarray(vec, dtype=np.complex128))
+        else:
+            sv.set_zero()
+        # :measure ops consume one draw each (state.clj:981)
+        segs = OPS.split_at_measurements(ops)
+        n_meas = sum(1 for k, _ in segs if k == "measure")
+        mdraws = iter(self._uniforms(options, (n_meas,)).tolist()) if n_meas else iter(())
+        for kind, payload in segs:
+            if kind == "gates":
+                sv.apply_ops(payload)
+            else:
+                sv.measure_qubits(payload, next(mdraws))
+        results: dict = {"result-types": sorted(_kw(k) for k in specs), "circuit": circuit,
+                         "circuit-metadata": circuit_metadata(circuit)}
+        results["final-state"] = ({"state-vector": sv.get_state(), "num-qubits": n} if n <= self.max_state_qubits
+                                  else DeviceStateHandle(sv))
+        ms = _opt(specs, "measurements")
+        if ms:
+            shots = int(_opt(ms, "shots") or 1)               # result.clj:573 — top-level :shots is ignored
+            outcomes = sv.sample(self._uniforms(options, (shots,)))
+            vals, counts = np.unique(outcomes, return_counts=True)
+            freq = {int(v): int(c) for v, c in zip(vals, counts)}
+            results["measurement-results"] = {
+                "measurement-outcomes": outcomes.tolist(),
+                "measurement-probabilities": sv.probabilities() if n <= self.max_state_qubits else DeviceStateHandle(sv),
+                "empirical-probabilities": {k: v / shots for k, v in freq.items()},
+                "shot-count": shots, "measurement-qubits": list(_opt(ms, "qubits") or range(n)),
+                "frequencies": freq, "source": "ideal-simulation"}
+        ham = _opt(specs, "hamiltonian")
+        if ham:
+            if isinstance(ham, dict):                        # noisy-path spelling {:hamiltonian H}
+                ham = _opt(ham, "hamiltonian")
+            results["hamiltonian-result"] = {"energy-expectation": sv.expect_hamiltonian(ham), "hamiltonian": ham}
+        ex = _opt(specs, "expectation")
+        if ex:
+            results["expectation-results"] = self._expect(sv, ex, variance=False)
+        va = _opt(specs, "variance")
+        if va:
+            results["variance-results"] = self._expect(sv, va, variance=True)
+        pr = _opt(specs, "probabilities")
+        if pr:
+            targets = _opt(pr, "targets")
+            if targets:
+                idx = [int(sum(int(b) << (len(t) - 1 - i) for i, b in enumerate(t))) if isinstance(t, (list, tuple)) else int(t)
+                       for t in targets]
+                amps = sv.get_amplitudes(idx)
+                results["probability-results"] = {
+                    "probability-outcomes": {(tuple(t) if isinstance(t, (list, tuple)) else t): float(abs(a) ** 2)
+                                             for t, a in zip(targets, amps)},
+                    "target-states": targets, "target-qubits": _opt(pr, "qubits")}
+            else:
+                allp = sv.probabilities()
+                results["probability-results"] = {"probability-outcomes": dict(enumerate(allp.tolist())) if n <= 16 else None,
+                                                  "target-qubits": list(_opt(pr, "qubits") or range(n)),
+                                                  "all-probabilities": allp}
+        am = _opt(specs, "amplitudes")
+        if am:
+            bs = list(_opt(am, "basis-states"))
+            results["amplitude-results"] = {"amplitude-values": dict(zip(bs, sv.get_amplitudes(bs).tolist())), "basis-states": bs}
+        if _opt(specs, "state-vector"):
+            results["state-vector-result"] = {"state-vector": sv.get_state(), "num-qubits": n}
+        if _opt(specs, "density-matrix"):
+            if n > 12:
+                raise ValueError("density-matrix result is limited to 12 qubits (4^n entries)")
+            st = sv.get_state()
+            rho = np.outer(st, np.conj(st))
+            results["density-matrix-result"] = {"density-matrix": rho, "num-qubits": n,
+                                                "trace-valid": bool(abs(np.trace(rho) - 1.0) < 1e-8)}
+        fi = _opt(specs, "fidelity")
+        if fi:
+            refs = _opt(fi, "references") or _opt(fi, "reference-states") or []
+            results["fidelity-results"] = {"fidelities": {f"reference-{i}": sv.fidelity(
+                np.asarray(r.get("state-vector", r.get(":state-vector")) if isinstance(r, dict) else r)) for i, r in enumerate(refs)}}
+        return {"job-status": "completed", "results": results}
+
+    @staticmethod
+    def _expect(sv, spec, variance: bool):
+        out = []
+        obs = _opt(spec, "observables") or []
+        targets = _opt(spec, "targets") or _opt(spec, "target-qubits") or [None] * len(obs)
+        for o, t in zip(obs, targets):
+            o = np.asarray(o, dtype=np.complex128)
+            if t is None:
+                if o.shape != (2, 2) or sv.n != 1:
+                    raise ValueError("full-register observables must be given as Pauli strings (use :hamiltonian)")
+                t = 0
+            e = sv.expect_1q(o, int(t))
+            if variance:
+                e2 = sv.expect_1q(o @ o, int(t))
+                v = e2 - e * e
+                out.append({"variance-value": v, "standard-deviation": float(np.sqrt(max(v, 0.0))), "observable": o, "target-qubits": [t]})
+            else:
+                out.append({"expectation-value": e, "observable": o, "target-qubits": [t]})
+        return out
+
+
+def create_simulator(config: Optional[dict] = None) -> B200Simulator:
+    """Mirror of `create-simulator` (ideal_simulator.clj:181-195)."""
+    return B200Simulator(config)
+
+
+# =============================================================================== hardware (noisy) simulator
+class B200HardwareSimulator(_BackendBase):
+    """Mirror of QuantumHardwareSimulator (hardware_simulator.clj:281-391): per-shot trajectories with gate
+    noise (Kraus channels) and readout noise from a device noise profile."""
+
+    _job_prefix = "job"
+    backend_type = "hardware-simulator"
+
+    def __init__(self, device: Optional[dict] = None, config: Optional[dict] = None):
+        super().__init__(config)
+        self._device = device or {"id": "b200-hardware-simulator", "noise-model": {}}
+
+    def backend_info(self) -> dict:
+        return {"backend-type": "hardware-simulator", "backend-name": "B200 Noisy Quantum Hardware Simulator",
+                "backend-config": self.config, "max-qubits": int(_opt(self.config, "max-qubits", 26)),
+                "capabilities": {"quantum-backend", "multi-device"}, "device": self._device, "version": "0.1.0"}
+
+    def device(self) -> dict:
+        return self._device
+
+    # MultiDeviceBackend (application/backend.clj:117-131)
+    def select_device(self, device: dict):
+        self._device = device
+        return device
+
+    def _execute(self, circuit: dict, options: dict) -> dict:
+        n = OPS.circuit_num_qubits(circuit)
+        ops = OPS.circuit_ops(circuit)
+        shots = int(_opt(options, "shots", 1024))                      # hardware_simulator.clj:123
+        max_traj = int(_opt(options, "max-trajectories", 100))
+        noise_model = _opt(self._device, "noise-model") or {}          # options :noise-model is ignored (:228)
+        specs = _opt(options, "result-specs")
+        sv = self._sv(n)
+        table, keep = NZ.build_noise_table(noise_model, n)
+        enc = OPS.encode_ops(ops)
+        dps = sv.noisy_draws_per_shot(enc, table)
+        u = self._uniforms(options, (shots, dps))
+        outcomes, traj = sv.run_noisy(enc, table, u, max_trajectories=max_traj if n <= 20 else 0)
+        counts: Dict[str, int] = {}
+        for o in outcomes.tolist():
+            bs = format(o, f"0{n}b")
+            counts[bs] = counts.get(bs, 0) + 1
+        results: dict = {"measurement-results": counts,
+                         "final-state": {"state-vector": sv.get_state(), "num-qubits": n} if n <= self.max_state_qubits else DeviceStateHandle(sv)}
+        if traj is not None and len(traj):
+            results["trajectories"] = [{"state-vector": t, "num-qubits": n} for t in traj]
+            results["trajectory-count"] = len(traj)
+            results["trajectory-weights"] = [1.0 / len(traj)] * len(traj)
+            if n <= 10:       # rho = mean projector (state.clj:781-786); 4^n entries, small n only
+                rho = sum(np.outer(t, np.conj(t)) for t in traj) / len(traj)
+                results["density-matrix"] = rho
+                results["density-matrix-trace"] = float(np.trace(rho).real)
+            if specs:
+                ham = _opt(specs, "hamiltonian")
+                if ham:
+                    H = _opt(ham, "hamiltonian") if isinstance(ham, dict) else ham
+                    es = []
+                    with L.StateVector(n) as tmp:
+                        for t in traj:
+                            tmp.set_state(t)
+                            es.append(tmp.expect_hamiltonian(H))
+                    # Tr(rho H) with rho the mean projector = mean over trajectories
+                    results["hamiltonian-result"] = {"energy-expectation": float(np.mean(es)), "hamiltonian": H}
+        if specs and _opt(specs, "measurements") is not None:
+            total = sum(counts.values())
+            results["measurement-results-detail"] = {
+                "measurement-outcomes": list(counts), "empirical-probabilities": {k: v / total for k, v in counts.items()},
+                "shot-count": total, "frequencies": counts, "source": "noisy-simulation"}
+        return {"job-status": "completed", "circuit": circuit, "circuit-metadata": circuit_metadata(circuit),
+                "shots-executed": shots, "results": results}
+
+
+def create_hardware_simulator(device: Optional[dict] = None, config: Optional[dict] = None) -> B200HardwareSimulator:
+    """Mirror of `create-hardware-simulator` (hardware_simulator.clj:396-414)."""
+    return B200HardwareSimulator(device, config)
+
+
+# =============================================================================== blocking helper
+def execute_circuit(backend: _BackendBase, circuit: dict, options: Optional[dict] = None, *, poll_s: float = 0.1,
+                    max_polls: int = 600) -> dict:
+    """Mirror of `backend/execute-circuit` (application/backend.clj:209-256): submit, poll every 100 ms up to
+    600 times, return the result map (status first checked immediately, so small jobs return without sleeping)."""
+    if not backend.available():
+        return {"job-status": "failed", "error-message": "Backend is not available"}
+    job_id = backend.submit_circuit(circuit, options or {})
+    for _ in range(max_polls):
+        st = backend.job_status(job_id)
+        if st in ("completed", "failed", "cancelled"):
+            return backend.job_result(job_id)
+        time.sleep(poll_s)
+    return {"job-status": "failed", "job-id": job_id, "error-message": "Job timed out"}

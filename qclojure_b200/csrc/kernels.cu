@@ -1,0 +1,599 @@
+// kernels.cu — hand-written sm_100a kernels of libqcb200.so.
+//
+//  k_tile_stage        the fused gate executor: one launch = one sweep over the local state.  A CTA
+//                      stages a tile of 2^m amplitudes in shared memory with cp.async (LDGSTS, 16-byte
+//                      coalesced runs), runs the stage's rounds with 2^r amplitudes per thread in
+//                      registers (tile_core.h), and writes the tile back in place.  HBM-bound:
+//                      algorithmic bytes = 32 * 2^n_local * (fraction of tiles visited).
+//  reductions          norm^2 / complex sum / Pauli expectation / marginal histogram: streaming reads
+//                      (16 B per amplitude), warp-shuffle + shared-memory block reduce, deterministic
+//                      two-pass finalisation (no floating-point atomics).
+//  sampling            chunk sums -> scan of chunk sums -> per-shot binary search + in-chunk scan;
+//                      implements the reference's measure-state rule (domain/state.clj:894-913).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "tile_core.h"
+
+namespace qcb {
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of K values per thread; result valid in thread 0.  smem: K * 32 doubles
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* sm) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) sm[k * 32 + wid] = v[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double x = (lane < nw) ? sm[k * 32 + lane] : 0.0;
+      v[k] = warp_sum(x);
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ the fused gate executor
+__global__ void __launch_bounds__(TILE_THREADS, 3)
+k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, uint32_t stage_words,
+             const double* __restrict__ dev_vals, uint64_t n_active) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StageCtx sc;
+  decode_stage(stage_g, sc);
+  const uint32_t m = sc.m, L = sc.L, tile_n = 1u << m, tid = threadIdx.x;
+  double2* tile = reinterpret_cast<double2*>(smem_raw);
+  uint64_t* sprog = reinterpret_cast<uint64_t*>(smem_raw + ((size_t)16 << m));
+  uint64_t* hoff = sprog + ((stage_words + 1u) & ~1u);
+
+  for (uint32_t i = tid; i < stage_words; i += TILE_THREADS) sprog[i] = stage_g[i];
+  for (uint32_t i = tid; i < (1u << (m - L)); i += TILE_THREADS) hoff[i] = hi_offset(stage_g, sc, i);
+  __syncthreads();
+
+  const uint32_t lowmask = (1u << L) - 1u;
+  for (uint64_t a = blockIdx.x; a < n_active; a += gridDim.x) {
+    const uint64_t t = active_to_tile(sc, a);
+    const uint64_t ext_hi = sc.ext_hi_base | t;
+    double2* gbase = state + tile_base(sprog, sc, t);
+
+    // ---- load: coalesced 16-byte async copies global -> swizzled shared tile
+    for (uint32_t i = tid; i < tile_n; i += TILE_THREADS)
+      cp_async16(&tile[swz(i)], gbase + hoff[i >> L] + (i & lowmask));
+    cp_async_commit_wait_all();
+    __syncthreads();
+
+    // ---- rounds
+    for (uint32_t r = 0; r < sc.n_rounds; ++r) {
+      RoundCtx rc;
+      decode_round(sprog, r, rc);
+      switch (rc.r) {
+        case 0: run_round_thread<0>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
+        case 1: run_round_thread<1>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
+        case 2: run_round_thread<2>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
+        default: run_round_thread<3>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
+      }
+      __syncthreads();
+    }
+
+    // ---- store back in place
+    for (uint32_t i = tid; i < tile_n; i += TILE_THREADS)
+      gbase[hoff[i >> L] + (i & lowmask)] = tile[swz(i)];
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const uint64_t* stage_host, uint32_t stage_words,
+                              const double* dev_vals, int num_sms, cudaStream_t stream, uint64_t* out_active) {
+  StageCtx sc;
+  decode_stage(stage_host, sc);
+  const uint32_t nb = sc.n_local - sc.m;
+  const uint64_t tmask = (nb >= 64) ? ~0ULL : ((1ULL << nb) - 1ULL);
+  // the part of the skip condition living in the rank bits is decided here, per rank
+  if ((sc.ext_hi_base & sc.skip_mask & ~tmask) != (sc.skip_val & ~tmask)) { if (out_active) *out_active = 0; return cudaSuccess; }
+  const uint64_t n_active = (1ULL << nb) >> __builtin_popcountll(sc.skip_mask & tmask);
+  if (out_active) *out_active = n_active;
+  const size_t smem = ((size_t)16 << sc.m) + 8 * (size_t)((stage_words + 1u) & ~1u) + 8 * ((size_t)1 << (sc.m - sc.L));
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_tile_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  int per_sm = 3;
+  while (per_sm > 1 && (smem + 1024) * per_sm > 227 * 1024) --per_sm;
+  uint64_t grid = (uint64_t)num_sms * per_sm;
+  if (grid > n_active) grid = n_active;
+  k_tile_stage<<<(unsigned)grid, TILE_THREADS, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ state initialisation
+__global__ void k_set_amp(double2* state, uint64_t idx, double re, double im) { state[idx] = double2{re, im}; }
+
+cudaError_t launch_set_amp(double2* state, uint64_t idx, double re, double im, cudaStream_t s) {
+  k_set_amp<<<1, 1, 0, s>>>(state, idx, re, im);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ reductions
+// mode 0: sum of amplitudes (re, im); mode 1: sum |a|^2 (out[0]).  partials: [grid][2]
+__global__ void __launch_bounds__(RED_THREADS)
+k_reduce(const double2* __restrict__ state, uint64_t count, int mode, double* __restrict__ partials) {
+  __shared__ double sm[2 * 32];
+  double v[2] = {0.0, 0.0};
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
+    const double2 a = state[i];
+    if (mode == 0) { v[0] += a.x; v[1] += a.y; }
+    else { v[0] += a.x * a.x + a.y * a.y; }
+  }
+  block_sum<2>(v, sm);
+  if (threadIdx.x == 0) { partials[2 * blockIdx.x] = v[0]; partials[2 * blockIdx.x + 1] = v[1]; }
+}
+
+// Sums `nparts` partial vectors of K doubles in a fixed order; one block.
+// post: 0 = plain; 1 = Grover reflection coefficients -> out = {-1, 0, 2*re/N, 2*im/N} (N = param);
+//       2 = normalisation coefficients -> out = {1/sqrt(s), 0, 0, 0} when sqrt(s) > tol (param) else {1,0,0,0}
+__global__ void __launch_bounds__(RED_THREADS)
+k_finalize(const double* __restrict__ partials, uint32_t nparts, uint32_t K, int post, double param, double* __restrict__ out) {
+  __shared__ double sm[32];
+  for (uint32_t k = 0; k < K; ++k) {
+    double v[1] = {0.0};
+    for (uint32_t p = threadIdx.x; p < nparts; p += RED_THREADS) v[0] += partials[(uint64_t)p * K + k];
+    block_sum<1>(v, sm);
+    if (threadIdx.x == 0) {
+      if (post == 0) out[k] = v[0];
+      else sm[16 + k] = v[0];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (post == 1) { out[0] = -1.0; out[1] = 0.0; out[2] = 2.0 * sm[16] / param; out[3] = 2.0 * sm[17] / param; }
+    else if (post == 2) {
+      const double nrm = sqrt(sm[16]);
+      out[0] = (nrm > 0.0 && nrm > param) ? 1.0 / nrm : 1.0; out[1] = 0.0; out[2] = 0.0; out[3] = 0.0;
+    }
+  }
+}
+
+cudaError_t launch_reduce(const double2* state, uint64_t count, int mode, double* partials, int grid, cudaStream_t s) {
+  k_reduce<<<grid, RED_THREADS, 0, s>>>(state, count, mode, partials);
+  return cudaGetLastError();
+}
+cudaError_t launch_finalize(const double* partials, uint32_t nparts, uint32_t K, int post, double param, double* out, cudaStream_t s) {
+  k_finalize<<<1, RED_THREADS, 0, s>>>(partials, nparts, K, post, param, out);
+  return cudaGetLastError();
+}
+
+// a *= (alpha from device memory: coef[0] + i coef[1])
+__global__ void __launch_bounds__(RED_THREADS)
+k_scale_dev(double2* __restrict__ state, uint64_t count, const double* __restrict__ coef) {
+  const double2 al{coef[0], coef[1]};
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) state[i] = cmul(al, state[i]);
+}
+cudaError_t launch_scale_dev(double2* state, uint64_t count, const double* coef, int grid, cudaStream_t s) {
+  k_scale_dev<<<grid, RED_THREADS, 0, s>>>(state, count, coef);
+  return cudaGetLastError();
+}
+
+// p_i = |a_i|^2 (domain/state.clj:676-682)
+__global__ void __launch_bounds__(RED_THREADS)
+k_probabilities(const double2* __restrict__ state, uint64_t offset, uint64_t count, double* __restrict__ out) {
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
+    const double2 a = state[offset + i];
+    out[i] = a.x * a.x + a.y * a.y;
+  }
+}
+cudaError_t launch_probabilities(const double2* state, uint64_t offset, uint64_t count, double* out, int grid, cudaStream_t s) {
+  k_probabilities<<<grid, RED_THREADS, 0, s>>>(state, offset, count, out);
+  return cudaGetLastError();
+}
+
+__global__ void k_gather(const double2* __restrict__ state, const uint64_t* __restrict__ idx, uint64_t n, double2* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = state[idx[i]];
+}
+cudaError_t launch_gather(const double2* state, const uint64_t* idx, uint64_t n, double2* out, cudaStream_t s) {
+  k_gather<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(state, idx, n, out);
+  return cudaGetLastError();
+}
+
+// <phi|psi> = sum conj(phi_i) psi_i ; partials [grid][2]
+__global__ void __launch_bounds__(RED_THREADS)
+k_inner(const double2* __restrict__ phi, const double2* __restrict__ psi, uint64_t count, double* __restrict__ partials) {
+  __shared__ double sm[2 * 32];
+  double v[2] = {0.0, 0.0};
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
+    const double2 a = phi[i], b = psi[i];
+    v[0] += a.x * b.x + a.y * b.y;
+    v[1] += a.x * b.y - a.y * b.x;
+  }
+  block_sum<2>(v, sm);
+  if (threadIdx.x == 0) { partials[2 * blockIdx.x] = v[0]; partials[2 * blockIdx.x + 1] = v[1]; }
+}
+cudaError_t launch_inner(const double2* phi, const double2* psi, uint64_t count, double* partials, int grid, cudaStream_t s) {
+  k_inner<<<grid, RED_THREADS, 0, s>>>(phi, psi, count, partials);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ Pauli expectation (x-mask / z-mask form)
+// Terms of one group share the X mask.  For a pair (i, j = i ^ xmask), i < j (bit `pivot` of i is 0):
+//   Re(conj(a_i) c_j a_j + conj(a_j) c_i a_i),  c_k = phase * (-1)^popc(k & zmask), phase = i^ny.
+// For xmask = 0 every index is its own partner: contribution (-1)^popc(i & z) |a_i|^2.
+// ext_or supplies the rank bits of the global index.  partials: [grid][EXPECT_TERMS]
+__global__ void __launch_bounds__(RED_THREADS)
+k_expect_group(const double2* __restrict__ state, uint64_t count, uint64_t xmask, int pivot, uint64_t ext_or,
+               ExpectTerms terms, double* __restrict__ partials) {
+  __shared__ double sm[EXPECT_TERMS * 32];
+  double acc[EXPECT_TERMS];
+#pragma unroll
+  for (int k = 0; k < EXPECT_TERMS; ++k) acc[k] = 0.0;
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  if (xmask == 0) {
+    for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
+      const double2 a = state[i];
+      const double p = a.x * a.x + a.y * a.y;
+      const uint64_t gi = i | ext_or;
+#pragma unroll
+      for (int k = 0; k < EXPECT_TERMS; ++k)
+        if (k < terms.n) acc[k] += (__popcll(gi & terms.zmask[k]) & 1) ? -p : p;
+    }
+  } else {
+    const uint64_t half = count >> 1;
+    for (uint64_t h = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; h < half; h += stride) {
+      const uint64_t i = ((h >> pivot) << (pivot + 1)) | (h & ((1ULL << pivot) - 1ULL));
+      const uint64_t j = i ^ xmask;
+      const double2 ai = state[i], aj = state[j];
+      // conj(ai)*aj = (x, y);  conj(aj)*ai = (x, -y)
+      const double x = ai.x * aj.x + ai.y * aj.y, y = ai.x * aj.y - ai.y * aj.x;
+      const uint64_t gi = i | ext_or, gj = j | ext_or;
+#pragma unroll
+      for (int k = 0; k < EXPECT_TERMS; ++k) {
+        if (k < terms.n) {
+          const double si = (__popcll(gi & terms.zmask[k]) & 1) ? -1.0 : 1.0;
+          const double sj = (__popcll(gj & terms.zmask[k]) & 1) ? -1.0 : 1.0;
+          // phase (pr, pi): Re(ph * sj * (x + iy)) + Re(ph * si * (x - iy))
+          acc[k] += sj * (terms.pr[k] * x - terms.pi[k] * y) + si * (terms.pr[k] * x + terms.pi[k] * y);
+        }
+      }
+    }
+  }
+  block_sum<EXPECT_TERMS>(acc, sm);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < EXPECT_TERMS; ++k) partials[(uint64_t)blockIdx.x * EXPECT_TERMS + k] = acc[k];
+  }
+}
+cudaError_t launch_expect_group(const double2* state, uint64_t count, uint64_t xmask, int pivot, uint64_t ext_or,
+                                const ExpectTerms& terms, double* partials, int grid, cudaStream_t s) {
+  k_expect_group<<<grid, RED_THREADS, 0, s>>>(state, count, xmask, pivot, ext_or, terms, partials);
+  return cudaGetLastError();
+}
+
+// <psi| (I..O_t..I) |psi> for a 2x2 observable on index bit `bit`; partials [grid][2] (re, im)
+__global__ void __launch_bounds__(RED_THREADS)
+k_expect_1q(const double2* __restrict__ state, uint64_t count, int bit, Mat2 O, double* __restrict__ partials) {
+  __shared__ double sm[2 * 32];
+  double v[2] = {0.0, 0.0};
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS, half = count >> 1;
+  for (uint64_t h = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; h < half; h += stride) {
+    const uint64_t i0 = ((h >> bit) << (bit + 1)) | (h & ((1ULL << bit) - 1ULL)), i1 = i0 | (1ULL << bit);
+    const double2 a0 = state[i0], a1 = state[i1];
+    const double2 b0 = cmul2(double2{O.m[0], O.m[1]}, a0, double2{O.m[2], O.m[3]}, a1);
+    const double2 b1 = cmul2(double2{O.m[4], O.m[5]}, a0, double2{O.m[6], O.m[7]}, a1);
+    v[0] += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y;
+    v[1] += a0.x * b0.y - a0.y * b0.x + a1.x * b1.y - a1.y * b1.x;
+  }
+  block_sum<2>(v, sm);
+  if (threadIdx.x == 0) { partials[2 * blockIdx.x] = v[0]; partials[2 * blockIdx.x + 1] = v[1]; }
+}
+cudaError_t launch_expect_1q(const double2* state, uint64_t count, int bit, const Mat2& O, double* partials, int grid, cudaStream_t s) {
+  k_expect_1q<<<grid, RED_THREADS, 0, s>>>(state, count, bit, O, partials);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ partial measurement (domain/state.clj:946-1014)
+// key(i) = sum_k bit(i, pos[k]) << k ; histogram of |a|^2 over keys, per block in shared memory.
+// partials: [grid][2^m]
+__global__ void __launch_bounds__(RED_THREADS)
+k_marginal(const double2* __restrict__ state, uint64_t count, uint64_t ext_or, BitList bl, double* __restrict__ partials) {
+  extern __shared__ double hist[];
+  const uint32_t nk = 1u << bl.n;
+  for (uint32_t k = threadIdx.x; k < nk; k += RED_THREADS) hist[k] = 0.0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
+    const double2 a = state[i];
+    const uint64_t gi = i | ext_or;
+    uint32_t key = 0;
+#pragma unroll 4
+    for (int k = 0; k < bl.n; ++k) key |= (uint32_t)((gi >> bl.pos[k]) & 1ULL) << k;
+    atomicAdd(&hist[key], a.x * a.x + a.y * a.y);
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < nk; k += RED_THREADS) partials[(uint64_t)blockIdx.x * nk + k] = hist[k];
+}
+cudaError_t launch_marginal(const double2* state, uint64_t count, uint64_t ext_or, const BitList& bl, double* partials, int grid, cudaStream_t s) {
+  k_marginal<<<grid, RED_THREADS, sizeof(double) << bl.n, s>>>(state, count, ext_or, bl, partials);
+  return cudaGetLastError();
+}
+
+// collapse: keep amplitudes whose key == sel (scaled by factor), zero the rest
+__global__ void __launch_bounds__(RED_THREADS)
+k_collapse(double2* __restrict__ state, uint64_t count, uint64_t ext_or, BitList bl, uint32_t sel, double factor) {
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
+    const uint64_t gi = i | ext_or;
+    uint32_t key = 0;
+#pragma unroll 4
+    for (int k = 0; k < bl.n; ++k) key |= (uint32_t)((gi >> bl.pos[k]) & 1ULL) << k;
+    double2 a = state[i];
+    if (key == sel) { a.x *= factor; a.y *= factor; } else { a.x = 0.0; a.y = 0.0; }
+    state[i] = a;
+  }
+}
+cudaError_t launch_collapse(double2* state, uint64_t count, uint64_t ext_or, const BitList& bl, uint32_t sel, double factor, int grid, cudaStream_t s) {
+  k_collapse<<<grid, RED_THREADS, 0, s>>>(state, count, ext_or, bl, sel, factor);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ sampling (domain/state.clj:894-913)
+// In-block inclusive scan of SAMPLE_CHUNK probabilities (SAMPLE_THREADS threads x SAMPLE_PER_THREAD each).
+// Returns this thread's inclusive prefix of its last element and fills `loc[]` with per-element
+// inclusive prefixes inside the chunk.  Both k_chunk_sums and k_sample use exactly this code so that
+// the chunk total and the in-chunk scan round identically.
+__device__ __forceinline__ double chunk_scan(const double2* __restrict__ src, uint64_t valid, double (&loc)[SAMPLE_PER_THREAD],
+                                             double* sm, double* smp) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // phase A: coalesced loads, |a|^2 into padded shared memory (index i + i/16: conflict-free in phase B)
+#pragma unroll
+  for (int k = 0; k < SAMPLE_PER_THREAD; ++k) {
+    const uint32_t i = (uint32_t)k * SAMPLE_THREADS + tid;
+    double p = 0.0;
+    if (i < valid) { const double2 a = src[i]; p = a.x * a.x + a.y * a.y; }
+    smp[i + (i >> 4)] = p;
+  }
+  __syncthreads();
+  // phase B: each thread owns SAMPLE_PER_THREAD consecutive elements
+  double run = 0.0;
+#pragma unroll
+  for (int k = 0; k < SAMPLE_PER_THREAD; ++k) {
+    run += smp[tid * (SAMPLE_PER_THREAD + 1) + k];
+    loc[k] = run;
+  }
+  // exclusive scan of per-thread totals across the block
+  double incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) sm[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    double w = (lane < SAMPLE_THREADS / 32) ? sm[lane] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    sm[32 + lane] = w;   // inclusive prefix of warp totals
+  }
+  __syncthreads();
+  const double warp_excl = (wid == 0) ? 0.0 : sm[32 + wid - 1];
+  const double thread_excl = warp_excl + (incl - run);
+#pragma unroll
+  for (int k = 0; k < SAMPLE_PER_THREAD; ++k) loc[k] += thread_excl;
+  const double total = sm[32 + SAMPLE_THREADS / 32 - 1];
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+k_chunk_sums(const double2* __restrict__ state, uint64_t count, double* __restrict__ sums) {
+  __shared__ double sm[64];
+  __shared__ double smp[SAMPLE_CHUNK + SAMPLE_CHUNK / 16];
+  double loc[SAMPLE_PER_THREAD];
+  for (uint64_t c = blockIdx.x; c * SAMPLE_CHUNK < count; c += gridDim.x) {
+    const uint64_t start = c * SAMPLE_CHUNK;
+    const uint64_t valid = (count - start < SAMPLE_CHUNK) ? (count - start) : SAMPLE_CHUNK;
+    const double total = chunk_scan(state + start, valid, loc, sm, smp);
+    if (threadIdx.x == 0) sums[c] = total;
+  }
+}
+
+// in-place inclusive scan of `n` doubles by one block (sequential over tiles of RED_THREADS with carry)
+__global__ void __launch_bounds__(RED_THREADS)
+k_scan_inclusive(double* __restrict__ v, uint64_t n) {
+  __shared__ double sm[64];
+  __shared__ double carry_s;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0.0;
+  __syncthreads();
+  for (uint64_t base = 0; base < n; base += RED_THREADS) {
+    const uint64_t i = base + tid;
+    double x = (i < n) ? v[i] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+    if (lane == 31) sm[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      double w = (lane < RED_THREADS / 32) ? sm[lane] : 0.0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      sm[32 + lane] = w;
+    }
+    __syncthreads();
+    const double carry = carry_s;
+    const double incl = carry + ((wid == 0) ? 0.0 : sm[32 + wid - 1]) + x;
+    if (i < n) v[i] = incl;
+    __syncthreads();
+    if (tid == RED_THREADS - 1) carry_s = incl;
+    __syncthreads();
+  }
+}
+
+// One block per shot.  r = total * u (+ nothing); `cum_chunks` = inclusive prefix of chunk sums, offset by
+// `rank_offset` (probability mass of lower ranks).  outcome = first index with cum >= r, clamped.
+// Shots whose r lies outside this rank's (lo, hi] range are left untouched (multi-GPU).
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+k_sample(const double2* __restrict__ state, uint64_t count, const double* __restrict__ cum_chunks, uint64_t n_chunks,
+         const double* __restrict__ uniforms, uint64_t n_shots, double total, double rank_offset, int is_first_rank,
+         int is_last_rank, uint64_t index_offset, unsigned long long* __restrict__ outcomes) {
+  __shared__ double sm[64];
+  __shared__ double smp[SAMPLE_CHUNK + SAMPLE_CHUNK / 16];
+  __shared__ unsigned long long best;
+  double loc[SAMPLE_PER_THREAD];
+  for (uint64_t shot = blockIdx.x; shot < n_shots; shot += gridDim.x) {
+    const double r = total * uniforms[shot];
+    const double local_total = cum_chunks[n_chunks - 1];
+    const double rl = r - rank_offset;                       // position inside this rank's mass
+    // ownership: first rank takes rl <= local_total (incl. r <= 0); others (0, local_total]; last rank also r > all
+    const bool below = !(rl > 0.0) && !is_first_rank;
+    const bool above = (rl > local_total) && !is_last_rank;
+    if (below || above) continue;                           // uniform across the block
+    // lower_bound over chunks: first c with cum_chunks[c] >= rl
+    uint64_t lo = 0, hi = n_chunks;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (cum_chunks[mid] < rl) lo = mid + 1; else hi = mid; }
+    uint64_t c = (lo < n_chunks) ? lo : n_chunks - 1;
+    const double excl = (c == 0) ? 0.0 : cum_chunks[c - 1];
+    const uint64_t start = c * SAMPLE_CHUNK;
+    const uint64_t valid = (count - start < SAMPLE_CHUNK) ? (count - start) : SAMPLE_CHUNK;
+    if (threadIdx.x == 0) best = ~0ULL;
+    chunk_scan(state + start, valid, loc, sm, smp);         // has __syncthreads inside
+    unsigned long long mine = ~0ULL;
+#pragma unroll
+    for (int k = SAMPLE_PER_THREAD - 1; k >= 0; --k) {
+      const uint64_t i = (uint64_t)threadIdx.x * SAMPLE_PER_THREAD + k;
+      if (i < valid && !(excl + loc[k] < rl)) mine = i;
+    }
+    if (mine != ~0ULL) atomicMin(&best, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t o = (best == ~0ULL) ? (start + valid - 1) : (start + best);
+      outcomes[shot] = o + index_offset;
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_chunk_sums(const double2* state, uint64_t count, double* sums, int grid, cudaStream_t s) {
+  k_chunk_sums<<<grid, SAMPLE_THREADS, 0, s>>>(state, count, sums);
+  return cudaGetLastError();
+}
+cudaError_t launch_scan_inclusive(double* v, uint64_t n, cudaStream_t s) {
+  k_scan_inclusive<<<1, RED_THREADS, 0, s>>>(v, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_sample(const double2* state, uint64_t count, const double* cum_chunks, uint64_t n_chunks, const double* uniforms,
+                          uint64_t n_shots, double total, double rank_offset, int first, int last, uint64_t index_offset,
+                          unsigned long long* outcomes, int grid, cudaStream_t s) {
+  k_sample<<<grid, SAMPLE_THREADS, 0, s>>>(state, count, cum_chunks, n_chunks, uniforms, n_shots, total, rank_offset, first, last,
+                                           index_offset, outcomes);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ chunked half exchange helpers (multi-GPU)
+// pack / unpack the half of the local slice whose bit `lbit` equals `want` into / from a contiguous buffer
+__global__ void __launch_bounds__(RED_THREADS)
+k_pack_half(const double2* __restrict__ state, double2* __restrict__ buf, uint64_t first, uint64_t n, int lbit, int want) {
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  for (uint64_t h = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; h < n; h += stride) {
+    const uint64_t k = first + h;
+    const uint64_t i = ((k >> lbit) << (lbit + 1)) | (k & ((1ULL << lbit) - 1ULL)) | ((uint64_t)want << lbit);
+    buf[h] = state[i];
+  }
+}
+__global__ void __launch_bounds__(RED_THREADS)
+k_unpack_half(double2* __restrict__ state, const double2* __restrict__ buf, uint64_t first, uint64_t n, int lbit, int want) {
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  for (uint64_t h = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; h < n; h += stride) {
+    const uint64_t k = first + h;
+    const uint64_t i = ((k >> lbit) << (lbit + 1)) | (k & ((1ULL << lbit) - 1ULL)) | ((uint64_t)want << lbit);
+    state[i] = buf[h];
+  }
+}
+cudaError_t launch_pack_half(const double2* state, double2* buf, uint64_t first, uint64_t n, int lbit, int want, int grid, cudaStream_t s) {
+  k_pack_half<<<grid, RED_THREADS, 0, s>>>(state, buf, first, n, lbit, want);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack_half(double2* state, const double2* buf, uint64_t first, uint64_t n, int lbit, int want, int grid, cudaStream_t s) {
+  k_unpack_half<<<grid, RED_THREADS, 0, s>>>(state, buf, first, n, lbit, want);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ P2: small dense complex linear algebra
+// (domain/math/protocols.clj MatrixAlgebra subset; row-major interleaved)
+__global__ void k_la_matmul(const double2* __restrict__ A, const double2* __restrict__ B, uint64_t m, uint64_t k, uint64_t n, double2* __restrict__ Cm) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * n) return;
+  const uint64_t r = idx / n, c = idx % n;
+  double2 acc{0.0, 0.0};
+  for (uint64_t t = 0; t < k; ++t) { const double2 p = cmul(A[r * k + t], B[t * n + c]); acc.x += p.x; acc.y += p.y; }
+  Cm[idx] = acc;
+}
+__global__ void k_la_kron(const double2* __restrict__ A, uint64_t ar, uint64_t ac, const double2* __restrict__ B, uint64_t br, uint64_t bc, double2* __restrict__ Cm) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t R = ar * br, Cc = ac * bc;
+  if (idx >= R * Cc) return;
+  const uint64_t r = idx / Cc, c = idx % Cc;
+  Cm[idx] = cmul(A[(r / br) * ac + (c / bc)], B[(r % br) * bc + (c % bc)]);
+}
+// out[i*m + j] = x_i * conj(y_j)
+__global__ void k_la_outer(const double2* __restrict__ x, const double2* __restrict__ y, uint64_t n, uint64_t m, double2* __restrict__ Cm) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * m) return;
+  const double2 a = x[idx / m], b = y[idx % m];
+  Cm[idx] = double2{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y};
+}
+__global__ void k_la_axpby(double2 alpha, const double2* __restrict__ x, double2 beta, const double2* __restrict__ y, uint64_t n, double2* __restrict__ out) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  double2 r = cmul(alpha, x[idx]);
+  if (y) { const double2 t = cmul(beta, y[idx]); r.x += t.x; r.y += t.y; }
+  out[idx] = r;
+}
+__global__ void k_la_trace(const double2* __restrict__ A, uint64_t n, double* __restrict__ partials) {
+  __shared__ double sm[2 * 32];
+  double v[2] = {0.0, 0.0};
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) { const double2 a = A[i * n + i]; v[0] += a.x; v[1] += a.y; }
+  block_sum<2>(v, sm);
+  if (threadIdx.x == 0) { partials[0] = v[0]; partials[1] = v[1]; }
+}
+
+static inline unsigned blocks_for(uint64_t n) { return (unsigned)((n + 255) / 256); }
+cudaError_t launch_la_matmul(const double2* A, const double2* B, uint64_t m, uint64_t k, uint64_t n, double2* C, cudaStream_t s) {
+  k_la_matmul<<<blocks_for(m * n), 256, 0, s>>>(A, B, m, k, n, C); return cudaGetLastError();
+}
+cudaError_t launch_la_kron(const double2* A, uint64_t ar, uint64_t ac, const double2* B, uint64_t br, uint64_t bc, double2* C, cudaStream_t s) {
+  k_la_kron<<<blocks_for(ar * br * ac * bc), 256, 0, s>>>(A, ar, ac, B, br, bc, C); return cudaGetLastError();
+}
+cudaError_t launch_la_outer(const double2* x, const double2* y, uint64_t n, uint64_t m, double2* C, cudaStream_t s) {
+  k_la_outer<<<blocks_for(n * m), 256, 0, s>>>(x, y, n, m, C); return cudaGetLastError();
+}
+cudaError_t launch_la_axpby(double2 alpha, const double2* x, double2 beta, const double2* y, uint64_t n, double2* out, cudaStream_t s) {
+  k_la_axpby<<<blocks_for(n), 256, 0, s>>>(alpha, x, beta, y, n, out); return cudaGetLastError();
+}
+cudaError_t launch_la_trace(const double2* A, uint64_t n, double* partials, cudaStream_t s) {
+  k_la_trace<<<1, 256, 0, s>>>(A, n, partials); return cudaGetLastError();
+}
+
+}  // namespace qcb

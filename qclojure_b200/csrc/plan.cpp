@@ -189,7 +189,8 @@ int lower_ops(const Config& cfg, const qcb_op* ops, uint64_t n_ops, std::vector<
         if (!need2() || !op.ext) return fail(QCB_ERR_INVALID, "U2Q needs two qubits and a 4x4 matrix", k);
         g.kind = G_MAT2; int bh = bit(q0), bl = bit(q1);   // q0 = more significant basis bit of the 4x4
         cplx M[16];
-        for (int i = 0; i < 16; ++i) M[i] = {op.ext[2 * i], op.ext[2 * i + 1]};
+        const double* ex = static_cast<const double*>(op.ext);
+        for (int i = 0; i < 16; ++i) M[i] = {ex[2 * i], ex[2 * i + 1]};
         if (bh > bl) { g.t1 = bh; g.t0 = bl; std::memcpy(g.m, M, sizeof M); }
         else {  // reorder basis so that t1 (higher index bit) is the more significant basis bit
           g.t1 = bl; g.t0 = bh;

@@ -1,0 +1,1335 @@
+// sim.cu — the handle behind include/qcb200.h: device state, plan execution, measurement, expectation,
+// noise trajectories, qubit exchanges (NCCL) and the job layer.  No CPU fallback anywhere: every entry
+// point that touches the state needs the CUDA device the handle was created on.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/qcb200.h"
+#include "kernels.h"
+#include "plan.h"
+
+using namespace qcb;
+
+// ------------------------------------------------------------------ NCCL, resolved at run time
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+bool load_nccl(std::string& err) {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.ok) return true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // reuse the copy torch already loaded
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+  g_nccl.lib = lib;
+#define QCB_SYM(field, name)                                                        \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name));       \
+  if (!g_nccl.field) { err = std::string("missing NCCL symbol ") + name; return false; }
+  QCB_SYM(GetUniqueId, "ncclGetUniqueId");
+  QCB_SYM(CommInitRank, "ncclCommInitRank");
+  QCB_SYM(CommDestroy, "ncclCommDestroy");
+  QCB_SYM(Send, "ncclSend");
+  QCB_SYM(Recv, "ncclRecv");
+  QCB_SYM(GroupStart, "ncclGroupStart");
+  QCB_SYM(GroupEnd, "ncclGroupEnd");
+  QCB_SYM(AllReduce, "ncclAllReduce");
+  QCB_SYM(AllGather, "ncclAllGather");
+  QCB_SYM(GetErrorString, "ncclGetErrorString");
+#undef QCB_SYM
+  g_nccl.ok = true;
+  return true;
+}
+
+std::string g_create_error;
+std::mutex g_create_mu;
+}  // namespace
+
+// ------------------------------------------------------------------ jobs
+struct Job {
+  uint64_t id = 0;
+  std::atomic<int> status{QCB_JOB_QUEUED};
+  std::atomic<bool> cancel{false};
+  std::vector<qcb_op> ops;
+  std::vector<std::vector<double>> ext_d;     // owned copies of op.ext payloads
+  std::vector<std::vector<int32_t>> ext_i;
+  std::vector<double> initial;
+  std::vector<double> uniforms;
+  std::vector<double> ham_coeffs;
+  std::vector<std::string> ham_strings;
+  int want_probs = 0, want_state = 0;
+  // results
+  double exec_ms = 0;
+  std::vector<uint64_t> outcomes;
+  double energy = 0; int has_energy = 0;
+  std::vector<double> probs, state;
+  std::string error;
+};
+
+// ------------------------------------------------------------------ the handle
+struct qcb_sim {
+  Config cfg;
+  int device = 0, num_sms = 148;
+  cudaStream_t stream = nullptr;
+  double2* state = nullptr;
+  uint64_t local_count = 0;
+  uint64_t* d_prog = nullptr; uint64_t* h_prog = nullptr; size_t prog_cap = 0;   // words
+  cudaEvent_t prog_ev = nullptr; bool prog_ev_valid = false;
+  double* d_vals = nullptr;                       // 256 doubles: device-side coefficients / small results
+  double* d_partials = nullptr; size_t partials_cap = 0;   // doubles
+  unsigned char* d_scratch = nullptr; size_t scratch_cap = 0;  // bytes
+  unsigned char* h_pin = nullptr; size_t pin_cap = 0;          // bytes (pinned)
+  std::vector<int> perm;                          // logical bit -> physical bit
+  qcb_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timing_pending = false;
+  cudaEvent_t xev0 = nullptr, xev1 = nullptr;
+  cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+  std::string err;
+  std::recursive_mutex mu;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  double2* xbuf = nullptr; uint64_t xbuf_count = 0;
+  // jobs
+  std::mutex jmu; std::condition_variable jcv;
+  std::map<uint64_t, std::shared_ptr<Job>> jobs;
+  std::deque<std::shared_ptr<Job>> queue;
+  std::thread worker; bool worker_started = false; bool stopping = false;
+  uint64_t next_job = 1;
+  std::atomic<bool>* active_cancel = nullptr;
+};
+
+namespace {
+
+int fail(qcb_sim* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else { std::lock_guard<std::mutex> lk(g_create_mu); g_create_error = msg; }
+  return code;
+}
+
+#define CU(h, expr)                                                                                   \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return fail(h, QCB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+#define NC(h, expr)                                                                                   \
+  do {                                                                                                \
+    ncclResult_t _r = (expr);                                                                         \
+    if (_r != ncclSuccess)                                                                            \
+      return fail(h, QCB_ERR_NCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(_r));            \
+  } while (0)
+
+#define RET(expr)                  \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != QCB_OK) return _rc; \
+  } while (0)
+
+int red_grid(const qcb_sim* h) { return h->num_sms * 4; }
+
+int ensure_partials(qcb_sim* h, size_t doubles) {
+  if (doubles <= h->partials_cap) return QCB_OK;
+  if (h->d_partials) cudaFree(h->d_partials);
+  h->d_partials = nullptr; h->partials_cap = 0;
+  CU(h, cudaMalloc(&h->d_partials, doubles * sizeof(double)));
+  h->partials_cap = doubles;
+  return QCB_OK;
+}
+int ensure_scratch(qcb_sim* h, size_t bytes) {
+  if (bytes <= h->scratch_cap) return QCB_OK;
+  if (h->d_scratch) cudaFree(h->d_scratch);
+  h->d_scratch = nullptr; h->scratch_cap = 0;
+  CU(h, cudaMalloc(&h->d_scratch, bytes));
+  h->scratch_cap = bytes;
+  return QCB_OK;
+}
+int ensure_pinned(qcb_sim* h, size_t bytes) {
+  if (bytes <= h->pin_cap) return QCB_OK;
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  h->h_pin = nullptr; h->pin_cap = 0;
+  CU(h, cudaMallocHost(&h->h_pin, bytes));
+  h->pin_cap = bytes;
+  return QCB_OK;
+}
+int ensure_prog(qcb_sim* h, size_t words) {
+  if (words <= h->prog_cap) return QCB_OK;
+  size_t cap = std::max<size_t>(words, 1 << 16);
+  if (h->d_prog) cudaFree(h->d_prog);
+  if (h->h_prog) cudaFreeHost(h->h_prog);
+  h->d_prog = nullptr; h->h_prog = nullptr; h->prog_cap = 0;
+  CU(h, cudaMalloc(&h->d_prog, cap * sizeof(uint64_t)));
+  CU(h, cudaMallocHost(&h->h_prog, cap * sizeof(uint64_t)));
+  h->prog_cap = cap;
+  return QCB_OK;
+}
+
+bool perm_is_identity(const qcb_sim* h) {
+  for (size_t b = 0; b < h->perm.size(); ++b) if (h->perm[b] != (int)b) return false;
+  return true;
+}
+
+// device -> host small copy through pinned memory, synchronising the stream
+int read_back(qcb_sim* h, const void* dev, size_t bytes, void* host) {
+  RET(ensure_pinned(h, bytes));
+  CU(h, cudaMemcpyAsync(h->h_pin, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  std::memcpy(host, h->h_pin, bytes);
+  return QCB_OK;
+}
+
+// sum over ranks of `count` doubles at dev (in place)
+int allreduce_sum(qcb_sim* h, double* dev, size_t count) {
+  if (h->cfg.world <= 1) return QCB_OK;
+  NC(h, g_nccl.AllReduce(dev, dev, count, ncclDouble, ncclSum, h->comm, h->stream));
+  return QCB_OK;
+}
+
+// ---- exchange: swap global physical bit gbit with local physical bit lbit
+int do_exchange(qcb_sim* h, int gbit, int lbit) {
+  const int nl = h->cfg.n_local;
+  const int j = gbit - nl;
+  const int myb = (h->cfg.rank >> j) & 1;
+  const int peer = h->cfg.rank ^ (1 << j);
+  const int want = 1 - myb;                         // the half of MY slice that moves: bit lbit == !myb
+  const uint64_t half = h->local_count >> 1;
+  if (!h->xbuf) {
+    uint64_t cnt = std::min<uint64_t>(half, 1ULL << 26);          // <= 1 GiB send + 1 GiB recv staging
+    CU(h, cudaMalloc(&h->xbuf, 2 * cnt * sizeof(double2)));
+    h->xbuf_count = cnt;
+  }
+  CU(h, cudaEventRecord(h->xev0, h->stream));
+  double2* sendbuf = h->xbuf;
+  double2* recvbuf = h->xbuf + h->xbuf_count;
+  const bool contiguous = (lbit == nl - 1);
+  for (uint64_t first = 0; first < half; first += h->xbuf_count) {
+    const uint64_t cnt = std::min<uint64_t>(h->xbuf_count, half - first);
+    const double2* src = sendbuf;
+    if (contiguous) src = h->state + ((uint64_t)want << lbit) + first;   // top local bit: the half is one block
+    else CU(h, launch_pack_half(h->state, sendbuf, first, cnt, lbit, want, red_grid(h), h->stream));
+    NC(h, g_nccl.GroupStart());
+    NC(h, g_nccl.Send(src, cnt * 2, ncclDouble, peer, h->comm, h->stream));
+    NC(h, g_nccl.Recv(recvbuf, cnt * 2, ncclDouble, peer, h->comm, h->stream));
+    NC(h, g_nccl.GroupEnd());
+    // partner's moving half (its bit lbit == myb) lands in MY moving positions (bit lbit == !myb)
+    if (contiguous) CU(h, cudaMemcpyAsync(h->state + ((uint64_t)want << lbit) + first, recvbuf, cnt * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
+    else CU(h, launch_unpack_half(h->state, recvbuf, first, cnt, lbit, want, red_grid(h), h->stream));
+    h->stats.n_kernel_launches += contiguous ? 0 : 2;
+    h->stats.bytes_exchanged += cnt * sizeof(double2);
+  }
+  CU(h, cudaEventRecord(h->xev1, h->stream));
+  CU(h, cudaEventSynchronize(h->xev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->xev0, h->xev1);
+  h->stats.exchange_ms += ms;
+  h->stats.n_exchanges++;
+  return QCB_OK;
+}
+
+// ---- run a scheduled plan on the device
+int execute_plan(qcb_sim* h, Plan& plan) {
+  if (plan.stages.empty()) { h->perm = plan.perm_out; return QCB_OK; }
+  RET(ensure_prog(h, plan.words.size()));
+  if (h->prog_ev_valid) CU(h, cudaEventSynchronize(h->prog_ev));
+  std::memcpy(h->h_prog, plan.words.data(), plan.words.size() * sizeof(uint64_t));
+  CU(h, cudaMemcpyAsync(h->d_prog, h->h_prog, plan.words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaEventRecord(h->prog_ev, h->stream));
+  h->prog_ev_valid = true;
+  for (size_t si = 0; si < plan.stages.size(); ++si) {
+    if (h->active_cancel && h->active_cancel->load()) return fail(h, QCB_ERR_STATE, "cancelled");
+    Stage& st = plan.stages[si];
+    const uint64_t off = plan.stage_offsets[si];
+    if (st.kind == S_TILE) {
+      const uint32_t words = (uint32_t)plan.words[off + 2 + 40];
+      uint64_t active = 0;
+      CU(h, launch_tile_stage(h->state, h->d_prog + off + 2, plan.words.data() + off + 2, words, h->d_vals, h->num_sms, h->stream, &active));
+      if (active) { h->stats.n_sweeps++; h->stats.n_kernel_launches++; h->stats.n_rounds += st.rounds.size(); }
+    } else if (st.kind == S_SUM) {
+      // Grover diffusion: sum of all amplitudes -> (alpha, beta) = (-1, 2*mean) in d_vals[0..4)
+      const int grid = red_grid(h);
+      RET(ensure_partials(h, (size_t)grid * 2));
+      CU(h, launch_reduce(h->state, h->local_count, 0, h->d_partials, grid, h->stream));
+      CU(h, launch_finalize(h->d_partials, grid, 2, 0, 0.0, h->d_vals + 8, h->stream));
+      RET(allreduce_sum(h, h->d_vals + 8, 2));
+      CU(h, launch_finalize(h->d_vals + 8, 1, 2, 1, std::ldexp(1.0, h->cfg.n_total), h->d_vals, h->stream));
+      h->stats.n_kernel_launches += 3;
+    } else if (st.kind == S_EXCHANGE) {
+      RET(do_exchange(h, st.gbit, st.lbit));
+    }
+  }
+  h->perm = plan.perm_out;
+  return QCB_OK;
+}
+
+int run_gates(qcb_sim* h, std::vector<Gate>&& gates) {
+  Plan plan;
+  plan.cfg = h->cfg;
+  plan.gates = std::move(gates);
+  int rc = schedule(plan, h->perm);
+  if (rc != QCB_OK) return fail(h, rc, plan.error);
+  h->stats.n_gates_lowered += plan.gates.size();
+  h->stats.algorithmic_bytes += plan.algorithmic_bytes;
+  h->stats.unfused_bytes += plan.unfused_bytes;
+  return execute_plan(h, plan);
+}
+
+// bring the state back to the canonical layout (logical bit b at physical bit b)
+int restore_layout(qcb_sim* h) {
+  if (perm_is_identity(h)) return QCB_OK;
+  const int n = h->cfg.n_total, nl = h->cfg.n_local;
+  std::vector<int> logical_of(n);
+  auto refresh = [&]() { for (int b = 0; b < n; ++b) logical_of[h->perm[b]] = b; };
+  refresh();
+  // 1) every global physical bit gets its own logical bit back, through a local staging position
+  for (int G = nl; G < n; ++G) {
+    if (logical_of[G] == G) continue;
+    int where = h->perm[G];                       // physical position of logical bit G
+    if (where >= nl) {                            // sits on another global bit: bring it local first
+      int l = nl - 1;
+      RET(do_exchange(h, where, l));
+      std::swap(h->perm[logical_of[where]], h->perm[logical_of[l]]);
+      refresh();
+      where = h->perm[G];
+    }
+    RET(do_exchange(h, G, where));
+    std::swap(h->perm[logical_of[G]], h->perm[logical_of[where]]);
+    refresh();
+  }
+  // 2) local permutation: swap gates on physical bits (fused into tile sweeps by the scheduler)
+  std::vector<Gate> swaps;
+  std::vector<int> perm = h->perm;
+  std::vector<int> lof(n);
+  for (int b = 0; b < n; ++b) lof[perm[b]] = b;
+  for (int b = 0; b < nl; ++b) {
+    if (perm[b] == b) continue;
+    // logical b lives at physical perm[b]; physical b holds logical lof[b]: swap physical bits b and perm[b]
+    int pa = b, pb = perm[b];
+    Gate g; g.kind = G_SWAPP; g.t0 = std::min(pa, pb); g.t1 = std::max(pa, pb); g.m[0] = {1, 0}; g.frac = 0.5;
+    swaps.push_back(g);
+    int la = lof[pa], lb = lof[pb];
+    std::swap(perm[la], perm[lb]);
+    lof[pa] = lb; lof[pb] = la;
+  }
+  if (!swaps.empty()) {
+    // the swap gates are expressed on PHYSICAL bits: schedule them with an identity permutation
+    Plan plan; plan.cfg = h->cfg; plan.gates = std::move(swaps);
+    int rc = schedule(plan, std::vector<int>());
+    if (rc != QCB_OK) return fail(h, rc, plan.error);
+    std::vector<int> keep = h->perm;
+    RET(execute_plan(h, plan));
+    h->perm = keep;
+  }
+  for (int b = 0; b < n; ++b) h->perm[b] = b;
+  return QCB_OK;
+}
+
+int begin_timing(qcb_sim* h) {
+  std::memset(&h->stats, 0, sizeof h->stats);
+  CU(h, cudaEventRecord(h->ev0, h->stream));
+  return QCB_OK;
+}
+int end_timing(qcb_sim* h) {
+  CU(h, cudaEventRecord(h->ev1, h->stream));
+  h->timing_pending = true;
+  return QCB_OK;
+}
+
+// normalize-state (domain/state.clj:544-551): divide by ||psi|| when the norm exceeds 1e-12
+int normalize_inplace(qcb_sim* h) {
+  const int grid = red_grid(h);
+  RET(ensure_partials(h, (size_t)grid * 2));
+  CU(h, launch_reduce(h->state, h->local_count, 1, h->d_partials, grid, h->stream));
+  CU(h, launch_finalize(h->d_partials, grid, 2, 0, 0.0, h->d_vals + 8, h->stream));
+  RET(allreduce_sum(h, h->d_vals + 8, 2));
+  CU(h, launch_finalize(h->d_vals + 8, 1, 2, 2, 1e-12, h->d_vals + 4, h->stream));
+  CU(h, launch_scale_dev(h->state, h->local_count, h->d_vals + 4, grid, h->stream));
+  h->stats.n_kernel_launches += 4;
+  return QCB_OK;
+}
+
+int norm_squared(qcb_sim* h, double* out) {
+  const int grid = red_grid(h);
+  RET(ensure_partials(h, (size_t)grid * 2));
+  CU(h, launch_reduce(h->state, h->local_count, 1, h->d_partials, grid, h->stream));
+  CU(h, launch_finalize(h->d_partials, grid, 2, 0, 0.0, h->d_vals + 8, h->stream));
+  RET(allreduce_sum(h, h->d_vals + 8, 2));
+  double v[2];
+  RET(read_back(h, h->d_vals + 8, sizeof v, v));
+  *out = v[0];
+  return QCB_OK;
+}
+
+// measure-specific-qubits (domain/state.clj:946-1014)
+int measure_qubits_impl(qcb_sim* h, const int32_t* qubits, int m, double u, int32_t* out_bits, double* out_prob,
+                        double* out_probs, bool collapse) {
+  const int n = h->cfg.n_total;
+  if (m <= 0 || m > MAX_MEASURE_BITS) return fail(h, QCB_ERR_UNSUPPORTED, "measure: 1.." + std::to_string(MAX_MEASURE_BITS) + " qubits per :measure op supported");
+  BitList bl; bl.n = m;
+  for (int k = 0; k < m; ++k) {
+    if (qubits[k] < 0 || qubits[k] >= n) return fail(h, QCB_ERR_INVALID, "measure: qubit out of range");
+    bl.pos[k] = h->perm[n - 1 - qubits[k]];
+  }
+  const uint64_t ext_or = (uint64_t)h->cfg.rank << h->cfg.n_local;
+  const int grid = std::min(red_grid(h), 296);
+  const uint32_t nk = 1u << m;
+  RET(ensure_partials(h, (size_t)grid * nk + nk));
+  CU(h, launch_marginal(h->state, h->local_count, ext_or, bl, h->d_partials, grid, h->stream));
+  double* d_out = h->d_partials + (size_t)grid * nk;
+  CU(h, launch_finalize(h->d_partials, grid, nk, 0, 0.0, d_out, h->stream));
+  RET(allreduce_sum(h, d_out, nk));
+  h->stats.n_kernel_launches += 2;
+  std::vector<double> probs(nk);
+  RET(read_back(h, d_out, nk * sizeof(double), probs.data()));
+  if (out_probs) std::memcpy(out_probs, probs.data(), nk * sizeof(double));
+  if (!collapse) return QCB_OK;
+  // select: r = total * u ; first outcome (enumeration order) with cum >= r, clamped (state.clj:979-985)
+  double total = 0;
+  std::vector<double> cum(nk);
+  for (uint32_t k = 0; k < nk; ++k) { total += probs[k]; cum[k] = total; }
+  const double r = total * u;
+  uint32_t sel = 0;
+  while (sel < nk && cum[sel] < r) ++sel;
+  if (sel >= nk) sel = nk - 1;
+  const double p = probs[sel];
+  const double factor = p > 0 ? 1.0 / std::sqrt(p) : 1.0;
+  CU(h, launch_collapse(h->state, h->local_count, ext_or, bl, sel, factor, red_grid(h), h->stream));
+  h->stats.n_kernel_launches += 1;
+  if (out_bits) for (int k = 0; k < m; ++k) out_bits[k] = (sel >> k) & 1;
+  if (out_prob) *out_prob = p;
+  return QCB_OK;
+}
+
+// apply a list of public ops (splitting at MEASURE ops); draws: optional external stream for MEASURE
+int apply_ops_impl(qcb_sim* h, const qcb_op* ops, uint64_t n_ops) {
+  uint64_t start = 0;
+  auto flush = [&](uint64_t end) -> int {
+    if (end <= start) return QCB_OK;
+    std::vector<Gate> gates;
+    std::string err;
+    int rc = lower_ops(h->cfg, ops + start, end - start, gates, err);
+    if (rc != QCB_OK) return fail(h, rc, err);
+    return run_gates(h, std::move(gates));
+  };
+  // validate everything first so that a bad op leaves the state untouched (reference: the whole job fails)
+  {
+    std::vector<Gate> tmp; std::string err; uint64_t s0 = 0;
+    for (uint64_t k = 0; k <= n_ops; ++k) {
+      if (k == n_ops || ops[k].kind == QCB_OP_MEASURE) {
+        if (k > s0) { int rc = lower_ops(h->cfg, ops + s0, k - s0, tmp, err); if (rc != QCB_OK) return fail(h, rc, err); }
+        s0 = k + 1;
+      }
+    }
+  }
+  for (uint64_t k = 0; k < n_ops; ++k) {
+    if (ops[k].kind == QCB_OP_MEASURE) {
+      RET(flush(k));
+      start = k + 1;
+      if (!ops[k].ext) return fail(h, QCB_ERR_INVALID, "Measure requires measurement-qubits parameter");
+      RET(measure_qubits_impl(h, static_cast<const int32_t*>(ops[k].ext), ops[k].n_mask, ops[k].angle, nullptr, nullptr, nullptr, true));
+    }
+  }
+  return flush(n_ops);
+}
+
+// ---- sampling (domain/state.clj:894-913)
+int sample_impl(qcb_sim* h, const double* uniforms, uint64_t n_shots, uint64_t* outcomes) {
+  RET(restore_layout(h));
+  const uint64_t n_chunks = (h->local_count + SAMPLE_CHUNK - 1) / SAMPLE_CHUNK;
+  const size_t off_u = ((n_chunks * 8 + 255) / 256) * 256;
+  const size_t off_o = off_u + ((n_shots * 8 + 255) / 256) * 256;
+  const size_t off_g = off_o + ((n_shots * 8 + 255) / 256) * 256;
+  RET(ensure_scratch(h, off_g + 8 * (size_t)h->cfg.world + 256));
+  double* d_chunks = reinterpret_cast<double*>(h->d_scratch);
+  double* d_u = reinterpret_cast<double*>(h->d_scratch + off_u);
+  unsigned long long* d_out = reinterpret_cast<unsigned long long*>(h->d_scratch + off_o);
+  double* d_totals = reinterpret_cast<double*>(h->d_scratch + off_g);
+  const int grid = (int)std::min<uint64_t>(n_chunks, (uint64_t)h->num_sms * 4);
+  CU(h, launch_chunk_sums(h->state, h->local_count, d_chunks, grid, h->stream));
+  CU(h, launch_scan_inclusive(d_chunks, n_chunks, h->stream));
+  h->stats.n_kernel_launches += 2;
+  // totals of all ranks
+  std::vector<double> totals(h->cfg.world, 0.0);
+  if (h->cfg.world > 1) {
+    NC(h, g_nccl.AllGather(d_chunks + (n_chunks - 1), d_totals, 1, ncclDouble, h->comm, h->stream));
+    RET(read_back(h, d_totals, 8 * (size_t)h->cfg.world, totals.data()));
+  } else {
+    RET(read_back(h, d_chunks + (n_chunks - 1), 8, totals.data()));
+  }
+  double total = 0, offset = 0;
+  for (int r = 0; r < h->cfg.world; ++r) { if (r == h->cfg.rank) offset = total; total += totals[r]; }
+  if (std::fabs(total - 1.0) > 1e-8)
+    return fail(h, QCB_ERR_STATE, "State is not properly normalized: total probability " + std::to_string(total));
+  if (n_shots == 0) return QCB_OK;
+  RET(ensure_pinned(h, n_shots * 8));
+  std::memcpy(h->h_pin, uniforms, n_shots * 8);
+  CU(h, cudaMemcpyAsync(d_u, h->h_pin, n_shots * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemsetAsync(d_out, 0, n_shots * 8, h->stream));
+  const int sgrid = (int)std::min<uint64_t>(n_shots, 65535);
+  CU(h, launch_sample(h->state, h->local_count, d_chunks, n_chunks, d_u, n_shots, total, offset, h->cfg.rank == 0,
+                      h->cfg.rank == h->cfg.world - 1, (uint64_t)h->cfg.rank << h->cfg.n_local, d_out, sgrid, h->stream));
+  h->stats.n_kernel_launches += 1;
+  if (h->cfg.world > 1) NC(h, g_nccl.AllReduce(d_out, d_out, n_shots, ncclUint64, ncclSum, h->comm, h->stream));
+  RET(read_back(h, d_out, n_shots * 8, outcomes));
+  return QCB_OK;
+}
+
+// ---- Pauli / Hamiltonian expectation (domain/observables.clj:216-251, domain/hamiltonian.clj:96-114)
+struct PTerm { uint64_t x = 0, z = 0; int ny = 0; size_t idx = 0; };
+
+int expect_terms_impl(qcb_sim* h, const char* const* strings, uint64_t n_terms, double* out_terms) {
+  const int n = h->cfg.n_total, nl = h->cfg.n_local;
+  const uint64_t local_mask = (nl >= 64) ? ~0ULL : ((1ULL << nl) - 1);
+  std::vector<PTerm> terms(n_terms);
+  for (uint64_t t = 0; t < n_terms; ++t) {
+    const char* s = strings[t];
+    if (!s || (int)std::strlen(s) != n) return fail(h, QCB_ERR_INVALID, "pauli string length must equal the number of qubits");
+    terms[t].idx = t;
+    for (int q = 0; q < n; ++q) {
+      const uint64_t b = 1ULL << h->perm[n - 1 - q];
+      switch (s[q]) {
+        case 'I': break;
+        case 'X': terms[t].x |= b; break;
+        case 'Z': terms[t].z |= b; break;
+        case 'Y': terms[t].x |= b; terms[t].z |= b; terms[t].ny++; break;
+        default: return fail(h, QCB_ERR_INVALID, "pauli string may contain only I, X, Y, Z");
+      }
+    }
+    if (terms[t].x & ~local_mask)
+      return fail(h, QCB_ERR_UNSUPPORTED, "X/Y factor on a global (rank) qubit: not supported in the sharded layout yet");
+  }
+  std::stable_sort(terms.begin(), terms.end(), [](const PTerm& a, const PTerm& b) { return a.x < b.x; });
+  const int grid = red_grid(h);
+  RET(ensure_partials(h, (size_t)grid * EXPECT_TERMS));
+  RET(ensure_scratch(h, (n_terms + EXPECT_TERMS) * 8 + 256));
+  double* d_res = reinterpret_cast<double*>(h->d_scratch);
+  const uint64_t ext_or = (uint64_t)h->cfg.rank << nl;
+  static const double PH[4][2] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
+  std::vector<size_t> order;     // result slot -> original term index
+  size_t t = 0, slot = 0;
+  while (t < terms.size()) {
+    ExpectTerms et; et.n = 0;
+    const uint64_t x = terms[t].x;
+    while (t < terms.size() && terms[t].x == x && et.n < EXPECT_TERMS) {
+      et.zmask[et.n] = terms[t].z; et.pr[et.n] = PH[terms[t].ny & 3][0]; et.pi[et.n] = PH[terms[t].ny & 3][1];
+      order.push_back(terms[t].idx);
+      ++et.n; ++t;
+    }
+    for (int k = et.n; k < EXPECT_TERMS; ++k) { et.zmask[k] = 0; et.pr[k] = 0; et.pi[k] = 0; }
+    const int pivot = x ? 63 - __builtin_clzll(x) : 0;
+    CU(h, launch_expect_group(h->state, h->local_count, x, pivot, ext_or, et, h->d_partials, grid, h->stream));
+    CU(h, launch_finalize(h->d_partials, grid, EXPECT_TERMS, 0, 0.0, d_res + slot, h->stream));
+    h->stats.n_kernel_launches += 2;
+    slot += et.n;     // next group overwrites the unused tail of this one
+  }
+  RET(allreduce_sum(h, d_res, slot));
+  std::vector<double> res(slot);
+  if (slot) RET(read_back(h, d_res, slot * 8, res.data()));
+  for (size_t k = 0; k < slot; ++k) out_terms[order[k]] = res[k];
+  return QCB_OK;
+}
+
+// Kraus operator K psi / ||K psi|| (domain/channel.clj:162-200).  Operators proportional to a unitary
+// are applied pre-scaled (identical up to rounding) to save the norm pass.
+bool proportional_to_unitary(const double K[8], double* scale) {
+  const double a = K[0] * K[0] + K[1] * K[1] + K[4] * K[4] + K[5] * K[5];   // (K^dagger K)_00
+  const double d = K[2] * K[2] + K[3] * K[3] + K[6] * K[6] + K[7] * K[7];   // (K^dagger K)_11
+  const double ore = K[0] * K[2] + K[1] * K[3] + K[4] * K[6] + K[5] * K[7]; // (K^dagger K)_01
+  const double oim = K[0] * K[3] - K[1] * K[2] + K[4] * K[7] - K[5] * K[6];
+  if (a <= 0) return false;
+  if (std::fabs(a - d) > 1e-15 * a || std::fabs(ore) > 1e-15 * a || std::fabs(oim) > 1e-15 * a) return false;
+  *scale = 1.0 / std::sqrt(a);
+  return true;
+}
+
+Gate kraus_gate(const qcb_sim* h, const double K[8], int target, double scale) {
+  Gate g; g.kind = G_MAT1; g.t0 = h->cfg.n_total - 1 - target; g.frac = 1.0;
+  for (int i = 0; i < 4; ++i) g.m[i] = {K[2 * i] * scale, K[2 * i + 1] * scale};
+  return g;
+}
+
+int noise_target(const qcb_op& op) {
+  // noise.clj:70 — (get-in gate [:operation-params :target] 0)
+  switch (op.kind) {
+    case QCB_OP_I: case QCB_OP_X: case QCB_OP_Y: case QCB_OP_Z: case QCB_OP_H: case QCB_OP_S: case QCB_OP_SDG:
+    case QCB_OP_T: case QCB_OP_TDG: case QCB_OP_RX: case QCB_OP_RY: case QCB_OP_RZ: case QCB_OP_PHASE: case QCB_OP_U1Q:
+      return op.q[0];
+    case QCB_OP_CNOT: case QCB_OP_CZ: case QCB_OP_CY: case QCB_OP_CRX: case QCB_OP_CRY: case QCB_OP_CRZ:
+    case QCB_OP_RYDBERG_CZ: case QCB_OP_RYDBERG_CPHASE: case QCB_OP_CU1Q:
+      return op.q[1];
+    case QCB_OP_TOFFOLI: return op.q[2];
+    default: return 0;
+  }
+}
+
+const qcb_noise_entry* find_noise(const qcb_noise_table* nt, int kind) {
+  if (!nt) return nullptr;
+  for (int i = 0; i < nt->n_entries; ++i) if (nt->entries[i].op_kind == kind) return &nt->entries[i];
+  return nullptr;
+}
+
+// channel.clj:225-242 — p_k = max |coeff|^2 ; first k with u < cumulative, else the last
+int select_kraus(const qcb_noise_entry* e, double u) {
+  double cum = 0;
+  for (int k = 0; k < e->n_kraus; ++k) {
+    double mx = 0;
+    for (int i = 0; i < 4; ++i) mx = std::max(mx, e->kraus[k][2 * i] * e->kraus[k][2 * i] + e->kraus[k][2 * i + 1] * e->kraus[k][2 * i + 1]);
+    cum += mx;
+    if (u < cum || k >= e->n_kraus - 1) return k;
+  }
+  return e->n_kraus - 1;
+}
+
+void worker_main(qcb_sim* h);
+int run_job(qcb_sim* h, Job& job);
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+int32_t qcb_abi_version(void) { return QCB_ABI_VERSION; }
+
+int32_t qcb_last_error(qcb_handle h, char* buf, size_t len) {
+  if (!buf || !len) return QCB_ERR_INVALID;
+  std::string m;
+  if (h) m = h->err;
+  else { std::lock_guard<std::mutex> lk(g_create_mu); m = g_create_error; }
+  std::snprintf(buf, len, "%s", m.c_str());
+  return QCB_OK;
+}
+
+int32_t qcb_device_count(int32_t* count) {
+  if (!count) return QCB_ERR_INVALID;
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { *count = 0; return fail(nullptr, QCB_ERR_CUDA, cudaGetErrorString(e)); }
+  *count = c;
+  return QCB_OK;
+}
+
+int32_t qcb_nccl_unique_id(void* out128) {
+  if (!out128) return QCB_ERR_INVALID;
+  std::string err;
+  if (!load_nccl(err)) return fail(nullptr, QCB_ERR_NCCL, err);
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(nullptr, QCB_ERR_NCCL, g_nccl.GetErrorString(r));
+  std::memcpy(out128, &id, sizeof id);
+  return QCB_OK;
+}
+
+int32_t qcb_config_default(qcb_config* cfg) {
+  if (!cfg) return QCB_ERR_INVALID;
+  std::memset(cfg, 0, sizeof *cfg);
+  cfg->device = -1; cfg->fusion = 1; cfg->strict_parity = 1; cfg->world_size = 1;
+  return QCB_OK;
+}
+
+int32_t qcb_create(const qcb_config* c, qcb_handle* out) {
+  if (!c || !out) return fail(nullptr, QCB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const int world = c->world_size > 0 ? c->world_size : 1;
+  if (world & (world - 1)) return fail(nullptr, QCB_ERR_INVALID, "world_size must be a power of two");
+  if (c->rank < 0 || c->rank >= world) return fail(nullptr, QCB_ERR_INVALID, "rank out of range");
+  Config cfg = config_from(*c);
+  if (cfg.n_total < 1 || cfg.n_total > 62 || cfg.n_local < 1)
+    return fail(nullptr, QCB_ERR_INVALID, "n_qubits out of range (need at least 1 local qubit)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, QCB_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  int dev = c->device;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= ndev) return fail(nullptr, QCB_ERR_INVALID, "device ordinal out of range");
+  std::unique_ptr<qcb_sim> h(new qcb_sim());
+  h->cfg = cfg; h->device = dev;
+  qcb_sim* hp = nullptr;   // errors before the handle exists go to the global slot
+#define CUC(expr)                                                                                         \
+  do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(hp, _e == cudaErrorMemoryAllocation ? QCB_ERR_NOMEM : QCB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+  CUC(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CUC(cudaGetDeviceProperties(&prop, dev));
+  h->num_sms = prop.multiProcessorCount;
+  CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->local_count = 1ULL << cfg.n_local;
+  CUC(cudaMalloc(&h->state, h->local_count * sizeof(double2)));
+  CUC(cudaMalloc(&h->d_vals, 256 * sizeof(double)));
+  CUC(cudaMemsetAsync(h->d_vals, 0, 256 * sizeof(double), h->stream));
+  CUC(cudaEventCreate(&h->ev0)); CUC(cudaEventCreate(&h->ev1));
+  CUC(cudaEventCreate(&h->xev0)); CUC(cudaEventCreate(&h->xev1));
+  CUC(cudaEventCreate(&h->tev0)); CUC(cudaEventCreate(&h->tev1));
+  CUC(cudaEventCreateWithFlags(&h->prog_ev, cudaEventDisableTiming));
+#undef CUC
+  h->perm.resize(cfg.n_total);
+  for (int b = 0; b < cfg.n_total; ++b) h->perm[b] = b;
+  if (world > 1) {
+    if (!c->nccl_unique_id) { cudaFree(h->state); return fail(nullptr, QCB_ERR_INVALID, "world_size > 1 needs nccl_unique_id"); }
+    std::string err;
+    if (!load_nccl(err)) { cudaFree(h->state); return fail(nullptr, QCB_ERR_NCCL, err); }
+    ncclUniqueId id;
+    std::memcpy(&id, c->nccl_unique_id, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, id, c->rank);
+    if (r != ncclSuccess) { cudaFree(h->state); return fail(nullptr, QCB_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); }
+  }
+  // |0...0>
+  cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream);
+  if (cfg.rank == 0) launch_set_amp(h->state, 0, 1.0, 0.0, h->stream);
+  *out = h.release();
+  return QCB_OK;
+}
+
+int32_t qcb_destroy(qcb_handle h) {
+  if (!h) return QCB_OK;
+  {
+    std::unique_lock<std::mutex> lk(h->jmu);
+    h->stopping = true;
+    h->jcv.notify_all();
+  }
+  if (h->worker_started && h->worker.joinable()) h->worker.join();
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm) g_nccl.CommDestroy(h->comm);
+  cudaFree(h->state); cudaFree(h->d_prog); cudaFree(h->d_vals); cudaFree(h->d_partials); cudaFree(h->d_scratch); cudaFree(h->xbuf);
+  if (h->h_prog) cudaFreeHost(h->h_prog);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->xev0) cudaEventDestroy(h->xev0);
+  if (h->xev1) cudaEventDestroy(h->xev1);
+  if (h->tev0) cudaEventDestroy(h->tev0);
+  if (h->tev1) cudaEventDestroy(h->tev1);
+  if (h->prog_ev) cudaEventDestroy(h->prog_ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return QCB_OK;
+}
+
+#define ENTER(h)                                               \
+  if (!(h)) return QCB_ERR_INVALID;                            \
+  std::lock_guard<std::recursive_mutex> _lk((h)->mu);          \
+  CU(h, cudaSetDevice((h)->device));
+
+int32_t qcb_synchronize(qcb_handle h) {
+  ENTER(h);
+  CU(h, cudaStreamSynchronize(h->stream));
+  return QCB_OK;
+}
+
+int32_t qcb_set_zero(qcb_handle h) {
+  ENTER(h);
+  CU(h, cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream));
+  if (h->cfg.rank == 0) CU(h, launch_set_amp(h->state, 0, 1.0, 0.0, h->stream));
+  for (size_t b = 0; b < h->perm.size(); ++b) h->perm[b] = (int)b;
+  return QCB_OK;
+}
+
+int32_t qcb_set_basis(qcb_handle h, uint64_t index) {
+  ENTER(h);
+  if (h->cfg.n_total < 64 && (index >> h->cfg.n_total)) return fail(h, QCB_ERR_INVALID, "basis index out of range");
+  CU(h, cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream));
+  if ((index >> h->cfg.n_local) == (uint64_t)h->cfg.rank)
+    CU(h, launch_set_amp(h->state, index & (h->local_count - 1), 1.0, 0.0, h->stream));
+  for (size_t b = 0; b < h->perm.size(); ++b) h->perm[b] = (int)b;
+  return QCB_OK;
+}
+
+int32_t qcb_set_state(qcb_handle h, const double* host, uint64_t count) {
+  ENTER(h);
+  if (!host || count != h->local_count) return fail(h, QCB_ERR_INVALID, "set_state: count must equal the local slice size 2^(n - log2 world)");
+  CU(h, cudaMemcpyAsync(h->state, host, count * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (size_t b = 0; b < h->perm.size(); ++b) h->perm[b] = (int)b;
+  return QCB_OK;
+}
+
+int32_t qcb_get_state(qcb_handle h, uint64_t offset, uint64_t count, double* out) {
+  ENTER(h);
+  if (!out || offset + count > h->local_count) return fail(h, QCB_ERR_INVALID, "get_state: range outside the local slice");
+  RET(restore_layout(h));
+  CU(h, cudaMemcpyAsync(out, h->state + offset, count * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return QCB_OK;
+}
+
+int32_t qcb_get_amplitudes(qcb_handle h, const uint64_t* idx, uint64_t n, double* out) {
+  ENTER(h);
+  if (!idx || !out) return fail(h, QCB_ERR_INVALID, "null argument");
+  if (n == 0) return QCB_OK;
+  RET(restore_layout(h));
+  std::vector<uint64_t> local(n);
+  std::vector<char> mine(n);
+  for (uint64_t k = 0; k < n; ++k) {
+    if (h->cfg.n_total < 64 && (idx[k] >> h->cfg.n_total)) return fail(h, QCB_ERR_INVALID, "basis index out of range");
+    mine[k] = (idx[k] >> h->cfg.n_local) == (uint64_t)h->cfg.rank;
+    local[k] = mine[k] ? (idx[k] & (h->local_count - 1)) : 0;
+  }
+  RET(ensure_scratch(h, n * 8 + n * 16 + 512));
+  uint64_t* d_idx = reinterpret_cast<uint64_t*>(h->d_scratch);
+  double2* d_out = reinterpret_cast<double2*>(h->d_scratch + ((n * 8 + 255) / 256) * 256);
+  CU(h, cudaMemcpyAsync(d_idx, local.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(h, launch_gather(h->state, d_idx, n, d_out, h->stream));
+  std::vector<double> tmp(2 * n);
+  RET(read_back(h, d_out, n * 16, tmp.data()));
+  for (uint64_t k = 0; k < n; ++k) { out[2 * k] = mine[k] ? tmp[2 * k] : 0.0; out[2 * k + 1] = mine[k] ? tmp[2 * k + 1] : 0.0; }
+  if (h->cfg.world > 1) {   // combine across ranks
+    CU(h, cudaMemcpyAsync(d_out, out, n * 16, cudaMemcpyHostToDevice, h->stream));
+    RET(allreduce_sum(h, reinterpret_cast<double*>(d_out), 2 * n));
+    RET(read_back(h, d_out, n * 16, out));
+  }
+  return QCB_OK;
+}
+
+int32_t qcb_normalize(qcb_handle h) {
+  ENTER(h);
+  return normalize_inplace(h);
+}
+
+int32_t qcb_state_dev_ptr(qcb_handle h, void** dev_ptr, uint64_t* local_count) {
+  ENTER(h);
+  if (dev_ptr) *dev_ptr = h->state;
+  if (local_count) *local_count = h->local_count;
+  return QCB_OK;
+}
+
+int32_t qcb_apply_ops(qcb_handle h, const qcb_op* ops, uint64_t n_ops) {
+  ENTER(h);
+  if (!ops && n_ops) return fail(h, QCB_ERR_INVALID, "null ops");
+  RET(begin_timing(h));
+  h->stats.n_ops = n_ops;
+  int rc = apply_ops_impl(h, ops, n_ops);
+  end_timing(h);
+  return rc;
+}
+
+int32_t qcb_norm2(qcb_handle h, double* out) {
+  ENTER(h);
+  if (!out) return fail(h, QCB_ERR_INVALID, "null argument");
+  double s = 0;
+  RET(norm_squared(h, &s));
+  *out = std::sqrt(s);
+  return QCB_OK;
+}
+
+int32_t qcb_probabilities(qcb_handle h, uint64_t offset, uint64_t count, double* out) {
+  ENTER(h);
+  if (!out || offset + count > h->local_count) return fail(h, QCB_ERR_INVALID, "probabilities: range outside the local slice");
+  if (!count) return QCB_OK;
+  RET(restore_layout(h));
+  // stream through a bounded device buffer so that no 2^n x 8 B scratch is needed next to a 128 GiB state
+  const uint64_t chunk = std::min<uint64_t>(count, 1ULL << 24);
+  RET(ensure_scratch(h, chunk * 8));
+  double* d = reinterpret_cast<double*>(h->d_scratch);
+  for (uint64_t done = 0; done < count; done += chunk) {
+    const uint64_t c = std::min(chunk, count - done);
+    CU(h, launch_probabilities(h->state, offset + done, c, d, (int)std::min<uint64_t>((c + RED_THREADS - 1) / RED_THREADS, (uint64_t)red_grid(h)), h->stream));
+    CU(h, cudaMemcpyAsync(out + done, d, c * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  return QCB_OK;
+}
+
+int32_t qcb_sample(qcb_handle h, const double* uniforms, uint64_t n_shots, uint64_t* outcomes) {
+  ENTER(h);
+  if (n_shots && (!uniforms || !outcomes)) return fail(h, QCB_ERR_INVALID, "null argument");
+  return sample_impl(h, uniforms, n_shots, outcomes);
+}
+
+int32_t qcb_measure_qubits(qcb_handle h, const int32_t* qubits, int32_t m, double u, int32_t* out_bits, double* out_prob) {
+  ENTER(h);
+  if (!qubits) return fail(h, QCB_ERR_INVALID, "null argument");
+  return measure_qubits_impl(h, qubits, m, u, out_bits, out_prob, nullptr, true);
+}
+
+int32_t qcb_marginal_probabilities(qcb_handle h, const int32_t* qubits, int32_t m, double* out_probs) {
+  ENTER(h);
+  if (!qubits || !out_probs) return fail(h, QCB_ERR_INVALID, "null argument");
+  return measure_qubits_impl(h, qubits, m, 0.0, nullptr, nullptr, out_probs, false);
+}
+
+int32_t qcb_expect_pauli(qcb_handle h, const char* s, double* out) {
+  ENTER(h);
+  if (!s || !out) return fail(h, QCB_ERR_INVALID, "null argument");
+  const char* arr[1] = {s};
+  return expect_terms_impl(h, arr, 1, out);
+}
+
+int32_t qcb_expect_hamiltonian(qcb_handle h, const double* coeffs, const char* const* strings, uint64_t n_terms,
+                               double* out_energy, double* out_terms) {
+  ENTER(h);
+  if ((n_terms && (!coeffs || !strings)) || !out_energy) return fail(h, QCB_ERR_INVALID, "null argument");
+  std::vector<double> t(n_terms);
+  if (n_terms) RET(expect_terms_impl(h, strings, n_terms, t.data()));
+  double e = 0;
+  for (uint64_t k = 0; k < n_terms; ++k) e += coeffs[k] * t[k];     // left to right, hamiltonian.clj:108-114
+  *out_energy = e;
+  if (out_terms) std::memcpy(out_terms, t.data(), n_terms * 8);
+  return QCB_OK;
+}
+
+int32_t qcb_expect_1q(qcb_handle h, const double mat[8], int32_t target, double* out) {
+  ENTER(h);
+  if (!mat || !out || target < 0 || target >= h->cfg.n_total) return fail(h, QCB_ERR_INVALID, "bad argument");
+  const int bit = h->perm[h->cfg.n_total - 1 - target];
+  if (bit >= h->cfg.n_local) return fail(h, QCB_ERR_UNSUPPORTED, "expect_1q on a global (rank) qubit: not supported in the sharded layout yet");
+  Mat2 O; std::memcpy(O.m, mat, sizeof O.m);
+  const int grid = red_grid(h);
+  RET(ensure_partials(h, (size_t)grid * 2));
+  CU(h, launch_expect_1q(h->state, h->local_count, bit, O, h->d_partials, grid, h->stream));
+  CU(h, launch_finalize(h->d_partials, grid, 2, 0, 0.0, h->d_vals + 8, h->stream));
+  RET(allreduce_sum(h, h->d_vals + 8, 2));
+  double v[2];
+  RET(read_back(h, h->d_vals + 8, sizeof v, v));
+  *out = v[0];
+  return QCB_OK;
+}
+
+int32_t qcb_fidelity(qcb_handle h, const double* host, uint64_t count, double* out) {
+  ENTER(h);
+  if (!host || !out || count != h->local_count) return fail(h, QCB_ERR_INVALID, "fidelity: count must equal the local slice size");
+  RET(restore_layout(h));
+  double2* phi = nullptr;
+  cudaError_t e = cudaMalloc(&phi, count * sizeof(double2));
+  if (e != cudaSuccess) return fail(h, QCB_ERR_NOMEM, "fidelity: cannot allocate a second state buffer");
+  const int grid = red_grid(h);
+  int rc = ensure_partials(h, (size_t)grid * 2);
+  if (rc == QCB_OK) {
+    cudaMemcpyAsync(phi, host, count * sizeof(double2), cudaMemcpyHostToDevice, h->stream);
+    // state-fidelity conjugates the FIRST state (the simulator's), domain/state.clj:1176-1185
+    launch_inner(h->state, phi, count, h->d_partials, grid, h->stream);
+    launch_finalize(h->d_partials, grid, 2, 0, 0.0, h->d_vals + 8, h->stream);
+    rc = allreduce_sum(h, h->d_vals + 8, 2);
+  }
+  double v[2] = {0, 0};
+  if (rc == QCB_OK) rc = read_back(h, h->d_vals + 8, sizeof v, v);
+  cudaFree(phi);
+  if (rc != QCB_OK) return rc;
+  *out = std::hypot(v[0], v[1]);
+  return QCB_OK;
+}
+
+int32_t qcb_apply_kraus_1q(qcb_handle h, const double mat[8], int32_t target) {
+  ENTER(h);
+  if (!mat || target < 0 || target >= h->cfg.n_total) return fail(h, QCB_ERR_INVALID, "bad argument");
+  RET(begin_timing(h));
+  std::vector<Gate> g;
+  g.push_back(kraus_gate(h, mat, target, 1.0));
+  RET(run_gates(h, std::move(g)));
+  int rc = normalize_inplace(h);
+  end_timing(h);
+  return rc;
+}
+
+int32_t qcb_noisy_draws_per_shot(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb_noise_table* noise, uint64_t* out) {
+  if (!h || !out) return QCB_ERR_INVALID;
+  uint64_t cnt = 0;
+  for (uint64_t k = 0; k < n_ops; ++k) {
+    if (ops[k].kind == QCB_OP_MEASURE) { ++cnt; continue; }
+    const qcb_noise_entry* e = find_noise(noise, ops[k].kind);
+    if (e && e->n_kraus > 1) ++cnt;
+  }
+  ++cnt;                                            // final measure-state
+  if (noise && noise->has_readout) cnt += (uint64_t)h->cfg.n_total;
+  *out = cnt;
+  return QCB_OK;
+}
+
+int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb_noise_table* noise, const double* uniforms,
+                      uint64_t draws_per_shot, uint64_t n_shots, uint64_t* out_outcomes, double* traj_out, uint64_t max_traj) {
+  ENTER(h);
+  if ((n_ops && !ops) || (n_shots && (!uniforms || !out_outcomes))) return fail(h, QCB_ERR_INVALID, "null argument");
+  if (h->cfg.world > 1) return fail(h, QCB_ERR_UNSUPPORTED, "noisy trajectories run as independent replicas per GPU (world_size must be 1)");
+  uint64_t need = 0;
+  qcb_noisy_draws_per_shot(h, ops, n_ops, noise, &need);
+  if (draws_per_shot < need) return fail(h, QCB_ERR_INVALID, "draws_per_shot too small: need " + std::to_string(need));
+  const int n = h->cfg.n_total;
+  // validate the circuit once
+  {
+    std::vector<Gate> tmp; std::string err;
+    for (uint64_t k = 0; k < n_ops; ++k) {
+      if (ops[k].kind == QCB_OP_MEASURE) continue;
+      int rc = lower_ops(h->cfg, ops + k, 1, tmp, err);
+      if (rc != QCB_OK) return fail(h, rc, err);
+    }
+  }
+  RET(begin_timing(h));
+  h->stats.n_ops = n_ops * n_shots;
+  for (uint64_t shot = 0; shot < n_shots; ++shot) {
+    const double* u = uniforms + shot * draws_per_shot;
+    uint64_t di = 0;
+    CU(h, cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream));
+    CU(h, launch_set_amp(h->state, 0, 1.0, 0.0, h->stream));
+    std::vector<Gate> pending;
+    std::string err;
+    auto flush = [&]() -> int { if (pending.empty()) return QCB_OK; std::vector<Gate> g; g.swap(pending); return run_gates(h, std::move(g)); };
+    for (uint64_t k = 0; k < n_ops; ++k) {
+      const qcb_op& op = ops[k];
+      if (op.kind == QCB_OP_MEASURE) {
+        RET(flush());
+        RET(measure_qubits_impl(h, static_cast<const int32_t*>(op.ext), op.n_mask, u[di++], nullptr, nullptr, nullptr, true));
+      } else {
+        int rc = lower_ops(h->cfg, &op, 1, pending, err);
+        if (rc != QCB_OK) return fail(h, rc, err);
+      }
+      const qcb_noise_entry* e = find_noise(noise, op.kind);
+      if (!e || e->n_kraus < 1) continue;
+      int tq = noise_target(op);
+      if (tq < 0 || tq >= n) tq = 0;
+      const int kidx = (e->n_kraus == 1) ? 0 : select_kraus(e, u[di++]);
+      double scale = 1.0;
+      if (proportional_to_unitary(e->kraus[kidx], &scale)) {
+        pending.push_back(kraus_gate(h, e->kraus[kidx], tq, scale));
+      } else {
+        pending.push_back(kraus_gate(h, e->kraus[kidx], tq, 1.0));
+        RET(flush());
+        RET(normalize_inplace(h));
+      }
+    }
+    RET(flush());
+    // final measurement with readout noise (noise.clj:193-202)
+    uint64_t outcome = 0;
+    RET(sample_impl(h, &u[di++], 1, &outcome));
+    if (noise && noise->has_readout) {
+      std::vector<int> flipped;
+      for (int q = 0; q < n; ++q) {
+        const int bitpos = n - 1 - q;
+        const int orig = (outcome >> bitpos) & 1;
+        double factor = 1.0;
+        if (noise->correlation) for (int src : flipped) factor *= noise->correlation[(size_t)src * n + q];
+        double eff = (orig ? noise->prob_1_to_0 : noise->prob_0_to_1) * factor;
+        eff = std::min(1.0, std::max(0.0, eff));
+        if (u[di++] < eff) { outcome ^= 1ULL << bitpos; flipped.push_back(q); }
+      }
+    }
+    out_outcomes[shot] = outcome;
+    if (traj_out && shot < max_traj)
+      CU(h, cudaMemcpyAsync(traj_out + shot * 2 * h->local_count, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(h, cudaStreamSynchronize(h->stream));
+  end_timing(h);
+  return QCB_OK;
+}
+
+int32_t qcb_get_stats(qcb_handle h, qcb_stats* out) {
+  ENTER(h);
+  if (!out) return fail(h, QCB_ERR_INVALID, "null argument");
+  if (h->timing_pending) {
+    CU(h, cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.gpu_ms = ms;
+    h->timing_pending = false;
+  }
+  *out = h->stats;
+  return QCB_OK;
+}
+
+int32_t qcb_timer_start(qcb_handle h) {
+  ENTER(h);
+  CU(h, cudaEventRecord(h->tev0, h->stream));
+  return QCB_OK;
+}
+
+int32_t qcb_timer_stop(qcb_handle h, double* out_ms) {
+  ENTER(h);
+  if (!out_ms) return fail(h, QCB_ERR_INVALID, "null argument");
+  CU(h, cudaEventRecord(h->tev1, h->stream));
+  CU(h, cudaEventSynchronize(h->tev1));
+  float ms = 0;
+  CU(h, cudaEventElapsedTime(&ms, h->tev0, h->tev1));
+  *out_ms = ms;
+  return QCB_OK;
+}
+
+// ---- host-only planning API
+struct qcb_plan { Plan plan; };
+
+int32_t qcb_plan_create(const qcb_config* cfg, const qcb_op* ops, uint64_t n_ops, qcb_plan** out) {
+  if (!cfg || !out || (!ops && n_ops)) return fail(nullptr, QCB_ERR_INVALID, "null argument");
+  std::unique_ptr<qcb_plan> p(new qcb_plan());
+  p->plan.cfg = config_from(*cfg);
+  if (p->plan.cfg.n_total < 1 || p->plan.cfg.n_local < 1) return fail(nullptr, QCB_ERR_INVALID, "n_qubits out of range");
+  std::string err;
+  int rc = lower_ops(p->plan.cfg, ops, n_ops, p->plan.gates, err);
+  if (rc != QCB_OK) return fail(nullptr, rc, err);
+  rc = schedule(p->plan, std::vector<int>());
+  if (rc != QCB_OK) return fail(nullptr, rc, p->plan.error);
+  *out = p.release();
+  return QCB_OK;
+}
+int32_t qcb_plan_destroy(qcb_plan* p) { delete p; return QCB_OK; }
+int32_t qcb_plan_serialize(const qcb_plan* p, uint64_t* out_words, uint64_t capacity, uint64_t* n_words) {
+  if (!p || !n_words) return QCB_ERR_INVALID;
+  *n_words = p->plan.words.size();
+  if (out_words) std::memcpy(out_words, p->plan.words.data(), 8 * std::min<uint64_t>(capacity, p->plan.words.size()));
+  return QCB_OK;
+}
+int32_t qcb_plan_summary(const qcb_plan* p, uint64_t* n_stages, uint64_t* n_rounds, uint64_t* n_exchanges) {
+  if (!p) return QCB_ERR_INVALID;
+  if (n_stages) *n_stages = p->plan.stages.size();
+  if (n_rounds) *n_rounds = p->plan.n_rounds;
+  if (n_exchanges) *n_exchanges = p->plan.n_exchanges;
+  return QCB_OK;
+}
+
+// ---- jobs (adapter/backend/ideal_simulator.clj:100-176)
+int32_t qcb_submit(qcb_handle h, const qcb_job_request* req, uint64_t* out_job_id) {
+  if (!h || !req || !out_job_id) return QCB_ERR_INVALID;
+  auto job = std::make_shared<Job>();
+  job->ops.assign(req->ops, req->ops + req->n_ops);
+  for (auto& op : job->ops) {           // own the ext payloads: the caller's pointers die after this call
+    if (!op.ext) continue;
+    if (op.kind == QCB_OP_U2Q) { job->ext_d.emplace_back(static_cast<const double*>(op.ext), static_cast<const double*>(op.ext) + 32); op.ext = nullptr; }
+    else if (op.kind == QCB_OP_MEASURE) { job->ext_i.emplace_back(static_cast<const int32_t*>(op.ext), static_cast<const int32_t*>(op.ext) + op.n_mask); op.ext = nullptr; }
+  }
+  { size_t di = 0, ii = 0;
+    for (auto& op : job->ops) {
+      if (op.kind == QCB_OP_U2Q && di < job->ext_d.size()) op.ext = job->ext_d[di++].data();
+      else if (op.kind == QCB_OP_MEASURE && ii < job->ext_i.size()) op.ext = job->ext_i[ii++].data();
+    } }
+  if (req->initial_state && req->initial_count) job->initial.assign(req->initial_state, req->initial_state + 2 * req->initial_count);
+  if (req->uniforms && req->n_shots) job->uniforms.assign(req->uniforms, req->uniforms + req->n_shots);
+  for (uint64_t t = 0; t < req->n_terms; ++t) { job->ham_coeffs.push_back(req->ham_coeffs[t]); job->ham_strings.emplace_back(req->ham_strings[t]); }
+  job->want_probs = req->want_probabilities; job->want_state = req->want_state;
+  bool inline_run;
+  {
+    std::unique_lock<std::mutex> lk(h->jmu);
+    job->id = h->next_job++;
+    h->jobs[job->id] = job;
+    // small jobs finish inside submit so that the caller's first status poll already sees :completed
+    // (the reference's blocking helper sleeps 100 ms between polls, application/backend.clj:255)
+    inline_run = h->cfg.n_total <= 20 && h->queue.empty();
+    if (!inline_run) {
+      h->queue.push_back(job);
+      if (!h->worker_started) { h->worker = std::thread(worker_main, h); h->worker_started = true; }
+      h->jcv.notify_all();
+    }
+  }
+  *out_job_id = job->id;
+  if (inline_run) {
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
+    run_job(h, *job);
+  }
+  return QCB_OK;
+}
+
+int32_t qcb_job_status(qcb_handle h, uint64_t id, int32_t* out_status) {
+  if (!h || !out_status) return QCB_ERR_INVALID;
+  std::unique_lock<std::mutex> lk(h->jmu);
+  auto it = h->jobs.find(id);
+  if (it == h->jobs.end()) { *out_status = QCB_JOB_NOT_FOUND; return QCB_OK; }
+  *out_status = it->second->status.load();
+  return QCB_OK;
+}
+
+int32_t qcb_job_result_get(qcb_handle h, uint64_t id, qcb_job_result* r) {
+  if (!h || !r) return QCB_ERR_INVALID;
+  std::shared_ptr<Job> job;
+  {
+    std::unique_lock<std::mutex> lk(h->jmu);
+    auto it = h->jobs.find(id);
+    if (it == h->jobs.end()) { r->status = QCB_JOB_NOT_FOUND; return QCB_ERR_NOTFOUND; }
+    job = it->second;
+  }
+  r->status = job->status.load();
+  r->execution_time_ms = job->exec_ms;
+  std::snprintf(r->error_message, sizeof r->error_message, "%s", job->error.c_str());
+  if (r->status != QCB_JOB_COMPLETED) return QCB_OK;
+  if (r->outcomes) std::memcpy(r->outcomes, job->outcomes.data(), 8 * std::min<uint64_t>(r->n_shots, job->outcomes.size()));
+  r->n_shots = job->outcomes.size();
+  r->energy = job->energy; r->has_energy = job->has_energy;
+  if (r->probabilities) std::memcpy(r->probabilities, job->probs.data(), 8 * std::min<uint64_t>(r->prob_capacity, job->probs.size()));
+  if (r->state) std::memcpy(r->state, job->state.data(), 8 * std::min<uint64_t>(2 * r->state_capacity, job->state.size()));
+  return QCB_OK;
+}
+
+int32_t qcb_cancel(qcb_handle h, uint64_t id, int32_t* out_status) {
+  if (!h) return QCB_ERR_INVALID;
+  std::unique_lock<std::mutex> lk(h->jmu);
+  auto it = h->jobs.find(id);
+  if (it == h->jobs.end()) { if (out_status) *out_status = QCB_JOB_NOT_FOUND; return QCB_OK; }
+  int st = it->second->status.load();
+  if (st == QCB_JOB_QUEUED || st == QCB_JOB_RUNNING) {
+    it->second->cancel.store(true);          // a running job stops between kernel stages
+    if (st == QCB_JOB_QUEUED) it->second->status.store(QCB_JOB_CANCELLED);
+    if (out_status) *out_status = QCB_JOB_CANCELLED;
+  } else if (out_status) {
+    *out_status = st;                        // :cannot-cancel: already finished
+  }
+  return QCB_OK;
+}
+
+int32_t qcb_queue_status(qcb_handle h, uint64_t* queued, uint64_t* running, uint64_t* completed) {
+  if (!h) return QCB_ERR_INVALID;
+  std::unique_lock<std::mutex> lk(h->jmu);
+  uint64_t q = 0, r = 0, c = 0;
+  for (auto& kv : h->jobs) {
+    int st = kv.second->status.load();
+    q += st == QCB_JOB_QUEUED; r += st == QCB_JOB_RUNNING; c += st == QCB_JOB_COMPLETED;
+  }
+  if (queued) *queued = q;
+  if (running) *running = r;
+  if (completed) *completed = c;
+  return QCB_OK;
+}
+
+// ---- P2: small dense linear algebra on the GPU (domain/math/protocols.clj MatrixAlgebra subset)
+static int la_run(qcb_handle h, const std::vector<std::pair<const double*, uint64_t>>& ins, uint64_t out_count, double* out,
+                  const std::function<cudaError_t(std::vector<double2*>&, double2*)>& body) {
+  size_t total = 0;
+  std::vector<size_t> offs;
+  for (auto& in : ins) { offs.push_back(total); total += ((in.second * 16 + 255) / 256) * 256; }
+  const size_t out_off = total;
+  total += out_count * 16 + 256;
+  RET(ensure_scratch(h, total));
+  std::vector<double2*> dptr;
+  for (size_t i = 0; i < ins.size(); ++i) {
+    double2* d = reinterpret_cast<double2*>(h->d_scratch + offs[i]);
+    if (ins[i].first) CU(h, cudaMemcpyAsync(d, ins[i].first, ins[i].second * 16, cudaMemcpyHostToDevice, h->stream));
+    dptr.push_back(ins[i].first ? d : nullptr);
+  }
+  double2* dout = reinterpret_cast<double2*>(h->d_scratch + out_off);
+  CU(h, body(dptr, dout));
+  CU(h, cudaMemcpyAsync(out, dout, out_count * 16, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return QCB_OK;
+}
+
+int32_t qcb_la_matmul(qcb_handle h, const double* A, const double* B, uint64_t m, uint64_t k, uint64_t n, double* C) {
+  ENTER(h);
+  if (!A || !B || !C) return fail(h, QCB_ERR_INVALID, "null argument");
+  return la_run(h, {{A, m * k}, {B, k * n}}, m * n, C, [&](std::vector<double2*>& d, double2* o) { return launch_la_matmul(d[0], d[1], m, k, n, o, h->stream); });
+}
+int32_t qcb_la_matvec(qcb_handle h, const double* A, const double* x, uint64_t rows, uint64_t cols, double* y) {
+  return qcb_la_matmul(h, A, x, rows, cols, 1, y);
+}
+int32_t qcb_la_kron(qcb_handle h, const double* A, uint64_t ar, uint64_t ac, const double* B, uint64_t br, uint64_t bc, double* C) {
+  ENTER(h);
+  if (!A || !B || !C) return fail(h, QCB_ERR_INVALID, "null argument");
+  return la_run(h, {{A, ar * ac}, {B, br * bc}}, ar * ac * br * bc, C, [&](std::vector<double2*>& d, double2* o) { return launch_la_kron(d[0], ar, ac, d[1], br, bc, o, h->stream); });
+}
+int32_t qcb_la_outer(qcb_handle h, const double* x, const double* y, uint64_t n, uint64_t m, double* C) {
+  ENTER(h);
+  if (!x || !y || !C) return fail(h, QCB_ERR_INVALID, "null argument");
+  return la_run(h, {{x, n}, {y, m}}, n * m, C, [&](std::vector<double2*>& d, double2* o) { return launch_la_outer(d[0], d[1], n, m, o, h->stream); });
+}
+int32_t qcb_la_axpby(qcb_handle h, const double alpha[2], const double* x, const double beta[2], const double* y, uint64_t n, double* out) {
+  ENTER(h);
+  if (!alpha || !x || !out || (y && !beta)) return fail(h, QCB_ERR_INVALID, "null argument");
+  const double2 al{alpha[0], alpha[1]}, be{beta ? beta[0] : 0.0, beta ? beta[1] : 0.0};
+  return la_run(h, {{x, n}, {y, n}}, n, out, [&](std::vector<double2*>& d, double2* o) { return launch_la_axpby(al, d[0], be, d[1], n, o, h->stream); });
+}
+int32_t qcb_la_inner(qcb_handle h, const double* x, const double* y, uint64_t n, double out[2]) {
+  ENTER(h);
+  if (!x || !y || !out) return fail(h, QCB_ERR_INVALID, "null argument");
+  const int grid = (int)std::min<uint64_t>((n + RED_THREADS - 1) / RED_THREADS, (uint64_t)red_grid(h));
+  RET(ensure_partials(h, (size_t)grid * 2));
+  RET(ensure_scratch(h, 2 * (n * 16 + 256)));
+  double2* dx = reinterpret_cast<double2*>(h->d_scratch);
+  double2* dy = reinterpret_cast<double2*>(h->d_scratch + ((n * 16 + 255) / 256) * 256);
+  CU(h, cudaMemcpyAsync(dx, x, n * 16, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(dy, y, n * 16, cudaMemcpyHostToDevice, h->stream));
+  CU(h, launch_inner(dx, dy, n, h->d_partials, grid, h->stream));     // conjugates the first argument
+  CU(h, launch_finalize(h->d_partials, grid, 2, 0, 0.0, h->d_vals + 8, h->stream));
+  return read_back(h, h->d_vals + 8, 16, out);
+}
+int32_t qcb_la_norm2(qcb_handle h, const double* x, uint64_t n, double* out) {
+  double v[2];
+  int rc = qcb_la_inner(h, x, x, n, v);
+  if (rc != QCB_OK) return rc;
+  *out = std::sqrt(v[0]);
+  return QCB_OK;
+}
+int32_t qcb_la_trace(qcb_handle h, const double* A, uint64_t n, double out[2]) {
+  ENTER(h);
+  if (!A || !out) return fail(h, QCB_ERR_INVALID, "null argument");
+  RET(ensure_scratch(h, n * n * 16 + 256));
+  double2* dA = reinterpret_cast<double2*>(h->d_scratch);
+  CU(h, cudaMemcpyAsync(dA, A, n * n * 16, cudaMemcpyHostToDevice, h->stream));
+  CU(h, launch_la_trace(dA, n, h->d_vals + 8, h->stream));
+  return read_back(h, h->d_vals + 8, 16, out);
+}
+
+}  // extern "C"
+
+// =================================================================== job execution
+namespace {
+
+int run_job(qcb_sim* h, Job& job) {
+  if (job.cancel.load()) { job.status.store(QCB_JOB_CANCELLED); return QCB_OK; }
+  job.status.store(QCB_JOB_RUNNING);
+  auto t0 = std::chrono::steady_clock::now();
+  h->active_cancel = &job.cancel;
+  int rc = QCB_OK;
+  auto step = [&](int r) { if (rc == QCB_OK) rc = r; };
+  if (!job.initial.empty()) step(qcb_set_state(h, job.initial.data(), job.initial.size() / 2));
+  else step(qcb_set_zero(h));
+  if (rc == QCB_OK) step(qcb_apply_ops(h, job.ops.data(), job.ops.size()));
+  if (rc == QCB_OK && !job.uniforms.empty()) {
+    job.outcomes.resize(job.uniforms.size());
+    step(qcb_sample(h, job.uniforms.data(), job.uniforms.size(), job.outcomes.data()));
+  }
+  if (rc == QCB_OK && !job.ham_coeffs.empty()) {
+    std::vector<const char*> ptrs;
+    for (auto& s : job.ham_strings) ptrs.push_back(s.c_str());
+    step(qcb_expect_hamiltonian(h, job.ham_coeffs.data(), ptrs.data(), ptrs.size(), &job.energy, nullptr));
+    job.has_energy = (rc == QCB_OK);
+  }
+  if (rc == QCB_OK && job.want_probs) { job.probs.resize(h->local_count); step(qcb_probabilities(h, 0, h->local_count, job.probs.data())); }
+  if (rc == QCB_OK && job.want_state) { job.state.resize(2 * h->local_count); step(qcb_get_state(h, 0, h->local_count, job.state.data())); }
+  if (rc == QCB_OK) step(qcb_synchronize(h));
+  h->active_cancel = nullptr;
+  job.exec_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (job.cancel.load()) job.status.store(QCB_JOB_CANCELLED);
+  else if (rc != QCB_OK) { job.error = h->err; job.status.store(QCB_JOB_FAILED); }   // never throw out of the worker (ideal_simulator.clj:93-96)
+  else job.status.store(QCB_JOB_COMPLETED);
+  return rc;
+}
+
+void worker_main(qcb_sim* h) {
+  for (;;) {
+    std::shared_ptr<Job> job;
+    {
+      std::unique_lock<std::mutex> lk(h->jmu);
+      h->jcv.wait(lk, [&] { return h->stopping || !h->queue.empty(); });
+      if (h->stopping && h->queue.empty()) return;
+      job = h->queue.front();
+      h->queue.pop_front();
+    }
+    if (job->status.load() == QCB_JOB_CANCELLED) continue;
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
+    run_job(h, *job);
+  }
+}
+
+}  // namespace

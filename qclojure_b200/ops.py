@@ -64,7 +64,7 @@ KIND_NAMES = ["i", "x", "y", "z", "h", "s", "s-dag", "t", "t-dag", "rx", "ry", "
               "cnot", "cz", "cy", "crx", "cry", "crz", "swap", "iswap", "toffoli", "fredkin",
               "rydberg-cz", "rydberg-cphase", "rydberg-blockade",
               "global-h", "global-x", "global-y", "global-z", "global-rx", "global-ry", "global-rz",
-              "u1q", "cu1q", "u2q", "mcphase", "phase-oracle", "grover-diffusion"]
+              "u1q", "cu1q", "u2q", "mcphase", "phase-oracle", "grover-diffusion", "measure"]
 KIND = {name: i for i, name in enumerate(KIND_NAMES)}
 
 # domain/operation_registry.clj:387-407
@@ -195,6 +195,13 @@ def encode_ops(ops: Iterable[dict]):
             o.mask = int(p["index"])
         elif g == "grover-diffusion":
             pass
+        elif g == "measure":
+            need("measurement-qubits")
+            qs = np.ascontiguousarray(np.asarray(p["measurement-qubits"], dtype=np.int32))
+            keep.append(qs)
+            o.ext = qs.ctypes.data
+            o.n_mask = int(qs.shape[0])
+            o.angle = float(p.get("uniform", 0.0))
     return arr, len(ops), keep
 
 
