@@ -1,0 +1,65 @@
+"""Worker of tests/test_multi_gpu_plan.py::test_gloo_two_process_exchange (CPU, gloo backend)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import qc_oracle as O  # noqa: E402
+from qclojure_b200 import circuits as C  # noqa: E402
+from tests.emu import emu as E  # noqa: E402
+
+
+def main():
+    rank, world = int(sys.argv[1]), int(sys.argv[2])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 12
+    p = world.bit_length() - 1
+    nl = n - p
+    circ = C.random_brickwork_circuit(n, 8)
+    C.h(circ, 0); C.cnot(circ, 0, n - 1); C.swap(circ, 0, n - 1); C.ry(circ, 0, 0.3)
+    plan = E.EmuPlan(n, circ["operations"], rank=rank, world=world, tile_bits=6, low_bits=3)
+    local = np.zeros(1 << nl, dtype=np.complex128)
+    if rank == 0:
+        local[0] = 1.0
+    dev_vals = np.zeros(64)
+    idx = np.arange(1 << nl, dtype=np.int64)
+    n_ex = 0
+    for i in range(plan.num_stages):
+        kind = plan.stage_kind(i)
+        if kind == E.S_TILE:
+            plan.run_tile_stage(i, local, dev_vals)
+        elif kind == E.S_EXCHANGE:
+            g, l = plan.stage_exchange(i)
+            j = g - nl
+            myb = (rank >> j) & 1
+            peer = rank ^ (1 << j)
+            sel = ((idx >> l) & 1) == (1 - myb)               # my moving half: bit l == !myb
+            send = torch.from_numpy(np.ascontiguousarray(local[sel]).view(np.float64).copy())
+            recv = torch.empty_like(send)
+            reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, send, peer), dist.P2POp(dist.irecv, recv, peer)])
+            for r in reqs:
+                r.wait()
+            local[sel] = recv.numpy().view(np.complex128)
+            n_ex += 1
+        else:
+            raise SystemExit("unexpected stage kind")
+    gathered = [torch.empty(2 << nl, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(local.view(np.float64).copy()))
+    if rank == 0:
+        full = np.concatenate([g.numpy().view(np.complex128) for g in gathered])
+        full = E.unpermute(full, plan.perm_out(), n)
+        want = O.execute_circuit(circ)
+        err = float(np.max(np.abs(full - want)))
+        assert err <= 1e-10, err
+        assert n_ex >= 1
+        print(f"PARITY OK err={err:.2e} exchanges={n_ex}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
