@@ -191,7 +191,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     sv = L.StateVector(n, device=local_rank, rank=rank, world_size=world, nccl_id=nccl_id,
-                       fusion=args.fusion, max_stage_cost=args.stage_cost, tile_bits=args.tile_bits, low_bits=args.low_bits)
+                       fusion=args.fusion, max_stage_cost=args.stage_cost, max_stage_rounds=args.stage_rounds,
+                       tile_bits=args.tile_bits, low_bits=args.low_bits)
 
     def step():
         sv.set_zero()
@@ -236,7 +237,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         prog_words = L.plan_summary(n, ops, fusion=args.fusion, max_stage_cost=args.stage_cost,
-                                    tile_bits=args.tile_bits, low_bits=args.low_bits)["program_words"]
+                                    max_stage_rounds=args.stage_rounds, tile_bits=args.tile_bits,
+                                    low_bits=args.low_bits)["program_words"]
         e2e = {"value": n_gates * args.steps / e2e_s, "unit": "gates/s",
                "h2d_bytes_per_step": int(prog_words * 8 + shots * 8), "d2h_bytes_per_step": int(shots * 8 + 8),
                "ms_per_step": 1000.0 * e2e_s / args.steps,
@@ -299,6 +301,7 @@ def main():
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--fusion", type=int, default=1)
     ap.add_argument("--stage-cost", type=int, default=0)
+    ap.add_argument("--stage-rounds", type=int, default=0)
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--low-bits", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

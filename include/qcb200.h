@@ -57,7 +57,8 @@ typedef struct qcb_config {
   int32_t world_size;      /* power of two; 1 = single GPU                                            */
   const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks (qcb_nccl_unique_id), or NULL */
   int32_t max_stage_cost;  /* 0 = default; scheduler knob: cost units one fused sweep may absorb       */
-  int32_t reserved[7];
+  int32_t max_stage_rounds;/* 0 = default; scheduler knob: shared-memory rounds one fused sweep may hold */
+  int32_t reserved[6];
 } qcb_config;
 
 /* ---- gate vocabulary: every branch of apply-gate-to-state (domain/circuit.clj:964-1071) ---- */

@@ -65,6 +65,7 @@ Config config_from(const qcb_config& c) {
   k.fusion = c.fusion;
   k.strict = c.strict_parity;
   k.max_stage_cost = c.max_stage_cost;
+  k.max_stage_rounds = c.max_stage_rounds;
   return k;
 }
 
@@ -215,15 +216,20 @@ int lower_ops(const Config& cfg, const qcb_op* ops, uint64_t n_ops, std::vector<
 static int gate_cost(const Gate& g) {
   switch (g.kind) {
     case G_MAT1: {
-      bool perm = g.m[0].re == 0 && g.m[0].im == 0 && g.m[3].re == 0 && g.m[3].im == 0;
-      return perm ? 2 : 8;
+      const cplx* M = g.m;
+      const bool perm = M[0].re == 0 && M[0].im == 0 && M[3].re == 0 && M[3].im == 0 && M[1].re == 1 && M[1].im == 0 && M[2].re == 1 && M[2].im == 0;
+      if (perm) return 1;
+      const bool real = M[0].im == 0 && M[1].im == 0 && M[2].im == 0 && M[3].im == 0;
+      const bool ri = M[0].im == 0 && M[3].im == 0 && M[1].re == 0 && M[2].re == 0;
+      int c = (real || ri) ? 4 : 8;
+      return g.cmask ? (c + 1) / 2 : c;
     }
     case G_MAT2: return 32;
-    case G_SWAPP: return 2;
-    case G_DMASK: return 2;
-    case G_DTAB1: return 4;
+    case G_SWAPP: return 1;
+    case G_DMASK: return (g.m[0].re == -1.0 && g.m[0].im == 0.0) ? 1 : 2;
+    case G_DTAB1: return g.cmask ? 2 : 4;
     case G_DPOP1: return 3;
-    default: return 8;
+    default: return 4;
   }
 }
 
@@ -255,31 +261,122 @@ static void choose_lanes(int m, const std::vector<int>& slots, std::vector<int>&
     if (!((used >> c) & 1)) { lanes.push_back(c); used |= 1ULL << c; }
 }
 
-static void put_gate_words(std::vector<uint64_t>& w, const Gate& g, const std::vector<int>& slot_pos) {
+struct SplitCond { uint32_t sel = 0, loc_mask = 0, loc_val = 0; uint64_t hi_mask = 0, hi_val = 0; };
+
+// Split a condition (idx & mask) == val given in ext space into its slot / tile-local / tile-id+rank parts.
+// `zero_slots`: slot indices that must be 0 in the patterns enumerated by sel (the op's own target slots).
+static SplitCond split_cond(uint64_t mask, uint64_t val, const std::vector<int>& slot_pos, int m, uint32_t zero_slots) {
+  SplitCond c;
+  uint32_t ms = 0, vs = 0;
+  for (int p = 0; p < 64; ++p) {
+    if (!((mask >> p) & 1)) continue;
+    const uint64_t vb = (val >> p) & 1;
+    int j = -1;
+    for (size_t k = 0; k < slot_pos.size(); ++k) if (slot_pos[k] == p) j = (int)k;
+    if (j >= 0) { ms |= 1u << j; vs |= (uint32_t)vb << j; }
+    else if (p < m) { c.loc_mask |= 1u << p; c.loc_val |= (uint32_t)vb << p; }
+    else { c.hi_mask |= 1ULL << (p - m); c.hi_val |= vb << (p - m); }
+  }
+  const int r = (int)slot_pos.size();
+  for (uint32_t s = 0; s < (1u << r); ++s)
+    if ((s & zero_slots) == 0 && (s & ms) == vs) c.sel |= 1u << s;
+  return c;
+}
+
+static uint64_t dbl_bits(double d) { uint64_t u; std::memcpy(&u, &d, 8); return u; }
+
+static size_t new_op(std::vector<uint64_t>& w, uint32_t kind, int j0, int j1, int nslots, const SplitCond& c) {
+  size_t base = w.size();
+  w.resize(base + (size_t)nslots * OP_WORDS, 0);
+  w[base + 0] = (uint64_t)kind | ((uint64_t)(j0 < 0 ? 0 : j0) << 8) | ((uint64_t)(j1 < 0 ? 0 : j1) << 16) |
+                ((uint64_t)nslots << 24) | ((uint64_t)c.sel << 32);
+  w[base + 1] = (uint64_t)c.loc_mask | ((uint64_t)c.loc_val << 32);
+  w[base + 2] = c.hi_mask;
+  w[base + 3] = c.hi_val;
+  return base;
+}
+
+static bool is_zero(cplx z) { return z.re == 0.0 && z.im == 0.0; }
+
+static void put_gate_words(std::vector<uint64_t>& w, const Gate& g, const std::vector<int>& slot_pos, int m) {
   auto slot_of = [&](int pos) {
     for (size_t j = 0; j < slot_pos.size(); ++j) if (slot_pos[j] == pos) return (int)j;
     return -1;
   };
-  auto dbl = [](double d) { uint64_t u; std::memcpy(&u, &d, 8); return u; };
-  size_t base = w.size();
-  int nslots = (g.kind == G_MAT2) ? 3 : 1;
-  w.resize(base + (size_t)nslots * OP_WORDS, 0);
-  uint64_t kind = 0, j0 = 0, j1 = 0;
   switch (g.kind) {
-    case G_MAT1: kind = D_MAT1; j0 = slot_of(g.t0); break;
-    case G_MAT2: kind = D_MAT2; j0 = slot_of(g.t0); j1 = slot_of(g.t1); break;
-    case G_SWAPP: kind = D_SWAPP; j0 = slot_of(g.t0); j1 = slot_of(g.t1); break;
-    case G_DMASK: kind = D_DMASK; break;
-    case G_DTAB1: kind = D_DTAB1; break;
-    case G_DPOP1: kind = D_DPOP1; break;
-    default: kind = D_AFFINE; break;
+    case G_MAT1: {
+      const int j = slot_of(g.t0);
+      SplitCond c = split_cond(g.cmask, g.cmask, slot_pos, m, 1u << j);
+      const cplx* M = g.m;
+      if (is_zero(M[0]) && is_zero(M[3]) && M[1].re == 1.0 && M[1].im == 0.0 && M[2].re == 1.0 && M[2].im == 0.0) {
+        new_op(w, D_PERMX, j, -1, 1, c);
+      } else if (M[0].im == 0.0 && M[1].im == 0.0 && M[2].im == 0.0 && M[3].im == 0.0) {
+        size_t b = new_op(w, D_MAT1R, j, -1, 1, c);
+        for (int i = 0; i < 4; ++i) w[b + 4 + i] = dbl_bits(M[i].re);
+      } else if (M[0].im == 0.0 && M[3].im == 0.0 && M[1].re == 0.0 && M[2].re == 0.0) {
+        size_t b = new_op(w, D_MAT1RI, j, -1, 1, c);
+        w[b + 4] = dbl_bits(M[0].re); w[b + 5] = dbl_bits(M[1].im); w[b + 6] = dbl_bits(M[2].im); w[b + 7] = dbl_bits(M[3].re);
+      } else {
+        size_t b = new_op(w, D_MAT1, j, -1, 1, c);
+        for (int i = 0; i < 4; ++i) { w[b + 4 + 2 * i] = dbl_bits(M[i].re); w[b + 5 + 2 * i] = dbl_bits(M[i].im); }
+      }
+      break;
+    }
+    case G_MAT2: {
+      const int j0 = slot_of(g.t0), j1 = slot_of(g.t1);
+      SplitCond c = split_cond(g.cmask, g.cmask, slot_pos, m, (1u << j0) | (1u << j1));
+      size_t b = new_op(w, D_MAT2, j0, j1, 3, c);
+      for (int i = 0; i < 16; ++i) { w[b + 4 + 2 * i] = dbl_bits(g.m[i].re); w[b + 5 + 2 * i] = dbl_bits(g.m[i].im); }
+      break;
+    }
+    case G_SWAPP: {
+      const int j0 = slot_of(g.t0), j1 = slot_of(g.t1);
+      SplitCond c = split_cond(g.cmask, g.cmask, slot_pos, m, (1u << j0) | (1u << j1));
+      size_t b = new_op(w, D_SWAPP, j0, j1, 1, c);
+      w[b + 4] = dbl_bits(g.m[0].re); w[b + 5] = dbl_bits(g.m[0].im);
+      break;
+    }
+    case G_DMASK: {
+      SplitCond c = split_cond(g.dmask, g.dval, slot_pos, m, 0);
+      if (g.m[0].re == -1.0 && g.m[0].im == 0.0) { new_op(w, D_DNEG, -1, -1, 1, c); break; }
+      size_t b = new_op(w, D_DMASK, -1, -1, 1, c);
+      w[b + 4] = dbl_bits(g.m[0].re); w[b + 5] = dbl_bits(g.m[0].im);
+      break;
+    }
+    case G_DTAB1: {   // phase table on one bit = two masked phases (bit = 0 -> m[0], bit = 1 -> m[1])
+      for (int bval = 0; bval < 2; ++bval) {
+        const cplx ph = g.m[bval];
+        if (ph.re == 1.0 && ph.im == 0.0) continue;
+        const uint64_t mask = g.cmask | (1ULL << g.t0), val = g.cmask | ((uint64_t)bval << g.t0);
+        SplitCond c = split_cond(mask, val, slot_pos, m, 0);
+        if (ph.re == -1.0 && ph.im == 0.0) { new_op(w, D_DNEG, -1, -1, 1, c); continue; }
+        size_t b = new_op(w, D_DMASK, -1, -1, 1, c);
+        w[b + 4] = dbl_bits(ph.re); w[b + 5] = dbl_bits(ph.im);
+      }
+      break;
+    }
+    case G_DENSE: {
+      const int r = (int)slot_pos.size(), dim = 1 << r;
+      SplitCond c; c.sel = 0xff;
+      const int nwords = 4 + 2 * dim * dim;
+      const int nslots = (nwords + OP_WORDS - 1) / OP_WORDS;
+      size_t b = new_op(w, D_DENSE, -1, -1, nslots, c);
+      for (int i = 0; i < dim * dim; ++i) { w[b + 4 + 2 * i] = dbl_bits(g.dense[i].re); w[b + 5 + 2 * i] = dbl_bits(g.dense[i].im); }
+      break;
+    }
+    case G_DPOP1: {
+      SplitCond c; c.sel = 0xff;
+      size_t b = new_op(w, D_DPOP1, -1, -1, 1, c);
+      w[b + 4] = g.dmask; w[b + 6] = dbl_bits(g.m[0].re); w[b + 7] = dbl_bits(g.m[0].im);
+      break;
+    }
+    default: {        // G_REFLECT -> affine a' = alpha a + beta with coefficients in device values slot dval
+      SplitCond c; c.sel = 0xff;
+      size_t b = new_op(w, D_AFFINE, -1, -1, 1, c);
+      w[b + 4] = g.dval;
+      break;
+    }
   }
-  w[base + 0] = kind | (j0 << 8) | (j1 << 16) | ((uint64_t)nslots << 24);
-  if (g.kind == G_DMASK || g.kind == G_DPOP1) { w[base + 1] = g.dmask; w[base + 2] = g.dval; }
-  else if (g.kind == G_DTAB1) { w[base + 1] = g.cmask; w[base + 2] = (uint64_t)g.t0; }
-  else { w[base + 1] = g.cmask; w[base + 2] = g.dval; }
-  int nc = (g.kind == G_MAT2) ? 16 : 4;
-  for (int i = 0; i < nc; ++i) { w[base + 4 + 2 * i] = dbl(g.m[i].re); w[base + 5 + 2 * i] = dbl(g.m[i].im); }
 }
 
 // translate a gate from physical bit space into the ext space of a stage
@@ -336,7 +433,7 @@ static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& wo
     std::vector<int> lanes;
     choose_lanes(m, rd.slot_pos, lanes);
     size_t ob = words.size();
-    for (const Gate& g : rd.gates) put_gate_words(words, g, rd.slot_pos);
+    for (const Gate& g : rd.gates) put_gate_words(words, g, rd.slot_pos, m);
     size_t rb = rbase + r * ROUND_WORDS;
     words[rb + 0] = rd.slot_pos.size();
     words[rb + 1] = (words.size() - ob) / OP_WORDS;
@@ -353,6 +450,107 @@ static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& wo
   words[base + 40] = words.size() - base;
 }
 
+// ---- dense fusion inside a round (north_star: "merges runs of gates on at most k qubits into one dense
+// 2^k x 2^k unitary applied from shared-memory tiles").  A gate is *pure* for a round when every bit it reads or
+// writes is one of the round's slot bits; a run of pure gates is multiplied on the host into one matrix.
+static bool gate_is_pure(const Gate& g, uint64_t slot_mask) {
+  switch (g.kind) {
+    case G_MAT1: case G_MAT2: case G_SWAPP: return ((g.target_mask() | g.cmask) & ~slot_mask) == 0;
+    case G_DMASK: return (g.dmask & ~slot_mask) == 0;
+    case G_DTAB1: return ((g.cmask | (1ULL << g.t0)) & ~slot_mask) == 0;
+    default: return false;
+  }
+}
+
+static inline cplx cm(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+static inline cplx ca(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
+
+// apply gate g (ext space, all bits among slot_pos) to a vector over the 2^r slot patterns
+static void small_apply(const Gate& g, const std::vector<int>& slot_pos, std::vector<cplx>& v) {
+  const int r = (int)slot_pos.size(), dim = 1 << r;
+  auto sbit = [&](int pos) { for (int j = 0; j < r; ++j) if (slot_pos[j] == pos) return j; return -1; };
+  auto smask = [&](uint64_t m) { uint32_t o = 0; for (int j = 0; j < r; ++j) if ((m >> slot_pos[j]) & 1) o |= 1u << j; return o; };
+  std::vector<cplx> o = v;
+  switch (g.kind) {
+    case G_MAT1: {
+      const int j = sbit(g.t0); const uint32_t c = smask(g.cmask);
+      for (int s = 0; s < dim; ++s) {
+        if ((s >> j) & 1) continue;
+        if ((s & c) != c) continue;
+        const int s1 = s | (1 << j);
+        o[s] = ca(cm(g.m[0], v[s]), cm(g.m[1], v[s1]));
+        o[s1] = ca(cm(g.m[2], v[s]), cm(g.m[3], v[s1]));
+      }
+      break;
+    }
+    case G_MAT2: {
+      const int j0 = sbit(g.t0), j1 = sbit(g.t1); const uint32_t c = smask(g.cmask);
+      for (int s = 0; s < dim; ++s) {
+        if (((s >> j0) & 1) || ((s >> j1) & 1) || (s & c) != c) continue;
+        const int id[4] = {s, s | (1 << j0), s | (1 << j1), s | (1 << j0) | (1 << j1)};
+        for (int row = 0; row < 4; ++row) {
+          cplx acc{0, 0};
+          for (int col = 0; col < 4; ++col) acc = ca(acc, cm(g.m[row * 4 + col], v[id[col]]));
+          o[id[row]] = acc;
+        }
+      }
+      break;
+    }
+    case G_SWAPP: {
+      const int j0 = sbit(g.t0), j1 = sbit(g.t1); const uint32_t c = smask(g.cmask);
+      for (int s = 0; s < dim; ++s) {
+        if (((s >> j0) & 1) || ((s >> j1) & 1) || (s & c) != c) continue;
+        const int u = s | (1 << j0), w = s | (1 << j1);
+        o[u] = cm(g.m[0], v[w]); o[w] = cm(g.m[0], v[u]);
+      }
+      break;
+    }
+    case G_DMASK: {
+      const uint32_t mk = smask(g.dmask), vl = smask(g.dval);
+      for (int s = 0; s < dim; ++s) if ((s & mk) == vl) o[s] = cm(v[s], g.m[0]);
+      break;
+    }
+    case G_DTAB1: {
+      const int j = sbit(g.t0); const uint32_t c = smask(g.cmask);
+      for (int s = 0; s < dim; ++s) if ((s & c) == c) o[s] = cm(v[s], g.m[(s >> j) & 1]);
+      break;
+    }
+    default: break;
+  }
+  v.swap(o);
+}
+
+static void fuse_round(Round& rd) {
+  const int r = (int)rd.slot_pos.size();
+  if (r == 0 || rd.gates.size() < 2) return;
+  uint64_t slot_mask = 0;
+  for (int p : rd.slot_pos) slot_mask |= 1ULL << p;
+  const int dim = 1 << r;
+  std::vector<Gate> out, run;
+  auto flush = [&]() {
+    if (run.size() >= 2) {
+      Gate d; d.kind = G_DENSE; d.fused = (int)run.size(); d.src_op = run[0].src_op;
+      d.dense.assign((size_t)dim * dim, cplx{0, 0});
+      for (int col = 0; col < dim; ++col) {           // column `col` = image of basis pattern `col`
+        std::vector<cplx> v(dim, cplx{0, 0});
+        v[col] = {1, 0};
+        for (const Gate& g : run) small_apply(g, rd.slot_pos, v);
+        for (int row = 0; row < dim; ++row) d.dense[(size_t)row * dim + col] = v[row];
+      }
+      out.push_back(std::move(d));
+    } else {
+      for (Gate& g : run) out.push_back(g);
+    }
+    run.clear();
+  };
+  for (Gate& g : rd.gates) {
+    if (gate_is_pure(g, slot_mask)) run.push_back(g);
+    else { flush(); out.push_back(g); }
+  }
+  flush();
+  rd.gates.swap(out);
+}
+
 // Form shared-memory rounds from the gates of one stage (gates already in ext space; targets < m).
 static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates) {
   std::vector<Gate> pending = gates;
@@ -362,19 +560,34 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates) 
     uint64_t R = 0;
     Blocker bl;
     std::vector<Gate> rest;
-    for (const Gate& g : pending) {
+    const uint64_t tile_mask = (1ULL << st.m) - 1ULL;
+    for (size_t gi = 0; gi < pending.size(); ++gi) {
+      const Gate& g = pending[gi];
       if (bl.conflicts(g)) { bl.block(g); rest.push_back(g); continue; }
-      uint64_t t = g.target_mask();
+      const uint64_t t = g.target_mask();
+      // prefer making the gate *pure* (every tile-local bit it touches becomes a slot bit): pure gates fold into
+      // the round's dense block for free; controls / diagonal operands on tile-id or rank bits can never be slots
+      const uint64_t all = (t | g.diag_mask());
+      const uint64_t want = all & tile_mask;
+      const bool can_be_pure = cfg.fusion && (all & ~tile_mask) == 0 && g.kind != G_DPOP1 && g.kind != G_REFLECT;
+      if (can_be_pure && popc(R | want) <= rmax) { R |= want; rd.gates.push_back(g); continue; }
+      if (can_be_pure && t == 0) {
+        // a diagonal gate that does not fit as pure now: defer it to a later round of this stage if one of its
+        // bits will be a slot there anyway (a later gate targets it); otherwise let it ride along as a masked phase
+        bool later = false;
+        for (size_t k = gi + 1; k < pending.size() && !later; ++k) later = (pending[k].target_mask() & want) != 0;
+        if (later) { bl.block(g); rest.push_back(g); continue; }
+      }
       if (popc(R | t) <= rmax) { R |= t; rd.gates.push_back(g); }
       else { bl.block(g); rest.push_back(g); }
     }
     // unfused mode keeps exactly one gate per round anyway (one gate per stage)
     for (int b = 0; b < st.m; ++b) if ((R >> b) & 1) rd.slot_pos.push_back(b);
     // pad with extra slot bits when the tile is so small that fewer than 8 lanes exist: not needed
+    if (cfg.fusion) fuse_round(rd);
     st.rounds.push_back(std::move(rd));
     pending.swap(rest);
   }
-  (void)cfg;
 }
 
 int schedule(Plan& plan, const std::vector<int>& perm_in) {
@@ -382,7 +595,8 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
   const int n = cfg.n_total, nl = cfg.n_local, m = std::min(cfg.tile_bits, nl), L = std::min(cfg.low_bits, m);
   std::vector<int> perm(n);
   for (int b = 0; b < n; ++b) perm[b] = perm_in.empty() ? b : perm_in[b];
-  const int max_cost = cfg.max_stage_cost > 0 ? cfg.max_stage_cost : 96;
+  const int max_cost = cfg.max_stage_cost > 0 ? cfg.max_stage_cost : 64;
+  const int max_rounds = cfg.max_stage_rounds > 0 ? cfg.max_stage_rounds : 64;
   const double sweep_bytes = 32.0 * std::ldexp(1.0, nl);
   const uint64_t local_mask = (nl >= 64) ? ~0ULL : ((1ULL << nl) - 1);
   const uint64_t tileid_mask = ((nl - m) >= 64) ? ~0ULL : ((1ULL << (nl - m)) - 1);
@@ -420,6 +634,18 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
         continue;
       }
       uint64_t need = g.target_mask() & ~A;
+      // diagonal gates do not need tile bits, but when the tile has room their operand bits are taken in so
+      // that the round fuser can fold them into a dense block (otherwise they ride along as masked phases)
+      if (cfg.fusion && (g.kind == G_DMASK || g.kind == G_DTAB1) && popc(g.diag_mask()) <= 2) {
+        const uint64_t soft = g.diag_mask() & local_mask & ~A & ~need;
+        if (popc(A) + popc(need) + popc(soft) <= m - 1) need |= soft;
+        else if (soft && !taken.empty() && !(g.kind == G_DMASK && g.m[0].re == -1.0 && g.m[0].im == 0.0)) {
+          // no room: a general phase on a bit outside the tile would cost a full complex multiply of every
+          // amplitude in this sweep; defer it to the sweep that owns the bit (sign flips stay: they are cheap)
+          bl.block(g);
+          continue;
+        }
+      }
       int c = gate_cost(g);
       if (popc(A) + popc(need) <= m && ((taken.empty() && !lead) || cost + c <= max_cost)) {
         A |= need; cost += c; taken.push_back((int)i);
@@ -444,19 +670,30 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
       for (int b = 0; b < nl; ++b) { if ((A >> b) & 1) ext_of_phys[b] = ti++; else ext_of_phys[b] = m + ni++; }
       for (int b = nl; b < 64; ++b) ext_of_phys[b] = b;
     }
+    // round budget: keep the longest prefix of the taken gates whose rounds fit max_rounds
     std::vector<Gate> eg;
-    std::vector<char> tk(pending.size(), 0);
-    for (int i : taken) { tk[i] = 1; eg.push_back(to_ext(to_phys(plan.gates[pending[i]]), ext_of_phys)); st.src_gates.push_back(pending[i]); }
-    if (eg.size() == 1 && !lead) {
-      const Gate& e = eg[0];
-      uint64_t cm = 0, cv = 0;
-      if (e.kind == G_MAT1 || e.kind == G_SWAPP || e.kind == G_MAT2 || e.kind == G_DTAB1) { cm = e.cmask; cv = e.cmask; }
-      else if (e.kind == G_DMASK) { cm = e.dmask; cv = e.dval; }
-      st.skip_mask = cm >> m; st.skip_val = cv >> m;
-      st.sweep_fraction = std::ldexp(1.0, -popc(st.skip_mask & tileid_mask));
+    size_t keep = taken.size();
+    for (;;) {
+      eg.clear();
+      st.rounds.clear();
+      st.src_gates.clear();
+      st.skip_mask = st.skip_val = 0; st.sweep_fraction = 1.0;
+      for (size_t k = 0; k < keep; ++k) { eg.push_back(to_ext(to_phys(plan.gates[pending[taken[k]]]), ext_of_phys)); st.src_gates.push_back(pending[taken[k]]); }
+      if (eg.size() == 1 && !lead) {
+        const Gate& e = eg[0];
+        uint64_t cm = 0, cv = 0;
+        if (e.kind == G_MAT1 || e.kind == G_SWAPP || e.kind == G_MAT2 || e.kind == G_DTAB1) { cm = e.cmask; cv = e.cmask; }
+        else if (e.kind == G_DMASK) { cm = e.dmask; cv = e.dval; }
+        st.skip_mask = cm >> m; st.skip_val = cv >> m;
+        st.sweep_fraction = std::ldexp(1.0, -popc(st.skip_mask & tileid_mask));
+      }
+      if (lead) { Round r0; r0.gates.push_back(*lead); st.rounds.push_back(r0); }
+      form_rounds(cfg, st, eg);
+      if ((int)st.rounds.size() <= max_rounds || keep <= 1) break;
+      keep -= std::max<size_t>(1, keep / 8);
     }
-    if (lead) { Round r0; r0.gates.push_back(*lead); st.rounds.push_back(r0); }
-    form_rounds(cfg, st, eg);
+    std::vector<char> tk(pending.size(), 0);
+    for (size_t k = 0; k < keep; ++k) tk[taken[k]] = 1;
     plan.stages.push_back(st);
     plan.algorithmic_bytes += sweep_bytes * st.sweep_fraction;
     std::vector<int> rest;

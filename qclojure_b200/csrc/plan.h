@@ -27,6 +27,7 @@ enum GateKind : int {
   G_DTAB1 = 4,   // diagonal: where (idx & cmask) == cmask: amp *= (bit t0 ? m[1] : m[0])
   G_DPOP1 = 5,   // diagonal: amp *= m[0] where popcount(idx & dmask) == 1
   G_REFLECT = 6, // Grover diffusion 2|s><s| - I  (needs the global mean: reduction + affine pass)
+  G_DENSE = 7,   // fused dense 2^r x 2^r block on ALL slot bits of its round (built by the round fuser)
 };
 
 struct Gate {
@@ -35,6 +36,8 @@ struct Gate {
   uint64_t cmask = 0;          // control bits (all must be 1)
   uint64_t dmask = 0, dval = 0;
   cplx m[16] = {};
+  std::vector<cplx> dense;     // G_DENSE: row-major 2^r x 2^r in slot space
+  int fused = 0;               // G_DENSE: number of gates folded in
   double frac = 1.0;           // fraction of the state a stand-alone application touches
   int src_op = -1;             // index of the originating qcb_op
 
@@ -48,7 +51,10 @@ constexpr int MAX_TILE_BITS = 13;
 constexpr int MAX_SLOT_BITS = 3;          // register-resident bits per round
 constexpr int MAX_RUNS = 16;
 
-enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_DTAB1 = 4, D_DPOP1 = 5, D_AFFINE = 6 };
+// D_MAT1: general complex 2x2; D_MAT1R: real 2x2 (H, RY, ...); D_MAT1RI: real diagonal + imaginary off-diagonal
+// (RX, Y); D_PERMX: pair exchange (X, CNOT, Toffoli); D_DNEG: masked sign flip (Z, CZ, phase oracle)
+enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_DNEG = 4, D_DPOP1 = 5, D_AFFINE = 6,
+                            D_MAT1R = 7, D_MAT1RI = 8, D_PERMX = 9, D_DENSE = 10 };
 
 // Descriptor words (all uint64) — see encode_stage() for the authoritative writer.
 //   StageDesc  (STAGE_WORDS words):
@@ -57,6 +63,10 @@ enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_
 //     [8..8+MAX_TILE_BITS)  physical position of tile bit k (k < m), ascending; first L are 0..L-1
 //     [24..24+MAX_RUNS)     run_start | run_len << 8 : contiguous runs of non-tile positions (ascending)
 //     [40] total words of this stage (desc + rounds + ops)  [41] flags
+//   Op slot (OP_WORDS words; MAT2 uses 3 slots):
+//     [0] kind | j0<<8 | j1<<16 | n_slots<<24 | sel<<32   (sel: bitmap over slot patterns, see tile_core.h)
+//     [1] loc_mask | loc_val<<32   (tile-local non-slot bits)      [2] hi_mask  [3] hi_val  (tile-id + rank bits)
+//     [4..] payload: 2x2 / 4x4 matrix, phase, popcount mask, or device-value index
 //   RoundDesc  (ROUND_WORDS words) x n_rounds, then op slots.
 //     [0] r  [1] n_op_slots  [2] op word offset (from stage start)  [3] n_lane
 //     [4..7)  slot_pos[3] (tile-local, ascending)   [7..10) lane_pos[3]
@@ -92,6 +102,7 @@ struct Config {
   int tile_bits = 12, low_bits = 4;
   int fusion = 1, strict = 1;
   int max_stage_cost = 0;
+  int max_stage_rounds = 0;
   int threads = 256;
 };
 

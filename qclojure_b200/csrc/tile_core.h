@@ -23,8 +23,9 @@
 
 namespace qcb {
 
-// must match plan.h
-enum : uint32_t { TD_MAT1 = 0, TD_MAT2 = 1, TD_SWAPP = 2, TD_DMASK = 3, TD_DTAB1 = 4, TD_DPOP1 = 5, TD_AFFINE = 6 };
+// must match plan.h (DevOpKind)
+enum : uint32_t { TD_MAT1 = 0, TD_MAT2 = 1, TD_SWAPP = 2, TD_DMASK = 3, TD_DNEG = 4, TD_DPOP1 = 5, TD_AFFINE = 6,
+                  TD_MAT1R = 7, TD_MAT1RI = 8, TD_PERMX = 9, TD_DENSE = 10 };
 constexpr int T_OP_WORDS = 16, T_STAGE_WORDS = 48, T_ROUND_WORDS = 20;
 
 QCB_HD uint32_t swz(uint32_t i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u); }
@@ -47,10 +48,26 @@ QCB_HD double as_double(uint64_t u) {
 #endif
 }
 
-QCB_HD double2 cmul(double2 a, double2 b) { return double2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
-// a*b + c*d
+#if defined(__CUDA_ARCH__)
+#define QCB_FMA(a, b, c) __fma_rn((a), (b), (c))
+#else
+#define QCB_FMA(a, b, c) ((a) * (b) + (c))
+#endif
+
+QCB_HD double2 cmul(double2 a, double2 b) {
+  return double2{QCB_FMA(a.x, b.x, -(a.y * b.y)), QCB_FMA(a.x, b.y, a.y * b.x)};
+}
+// a*b + c*d as two chains of 1 mul + 3 fma
 QCB_HD double2 cmul2(double2 a, double2 b, double2 c, double2 d) {
-  return double2{a.x * b.x - a.y * b.y + (c.x * d.x - c.y * d.y), a.x * b.y + a.y * b.x + (c.x * d.y + c.y * d.x)};
+  double re = c.x * d.x;
+  re = QCB_FMA(-c.y, d.y, re);
+  re = QCB_FMA(a.x, b.x, re);
+  re = QCB_FMA(-a.y, b.y, re);
+  double im = c.x * d.y;
+  im = QCB_FMA(c.y, d.x, im);
+  im = QCB_FMA(a.x, b.y, im);
+  im = QCB_FMA(a.y, b.x, im);
+  return double2{re, im};
 }
 
 struct RoundCtx {
@@ -79,12 +96,18 @@ QCB_HD uint32_t group_idx0(const RoundCtx& rc, uint32_t g) {
   return v;
 }
 
-// ---- op interpreters on 2^R register-resident amplitudes.  `ext0` = ext index with slot bits 0;
-//      off[s] = tile-local offset of slot pattern s.
-template <int R>
-QCB_HD void op_mat1(double2 (&a)[1 << R], uint32_t j, uint64_t cmask, const uint64_t* mw, uint64_t ext0, const uint32_t (&off)[1 << R]) {
-  const double2 m00{as_double(mw[0]), as_double(mw[1])}, m01{as_double(mw[2]), as_double(mw[3])};
-  const double2 m10{as_double(mw[4]), as_double(mw[5])}, m11{as_double(mw[6]), as_double(mw[7])};
+// ---- op interpreters on 2^R register-resident amplitudes.
+// The scheduler pre-splits every condition (controls / diagonal predicates) of an op into
+//   sel      8-bit bitmap over the slot patterns s for which the slot-bit part of the condition holds
+//            (for pair/quad ops: indexed by the base pattern, target bits = 0),
+//   loc      mask|val on the tile-local NON-slot bits (32-bit, compared against idx0 once per group),
+//   hi       mask/val on the tile-id + rank bits (64-bit, uniform over the CTA's current tile),
+// so the per-amplitude work is one bit test instead of 64-bit mask arithmetic.
+template <int R, int MODE>   // MODE 0: general complex 2x2; 1: real 2x2; 2: real diagonal, imaginary off-diagonal
+QCB_HD void op_mat1(double2 (&a)[1 << R], uint32_t j, uint32_t sel, const uint64_t* mw) {
+  double c[8];
+#pragma unroll
+  for (int k = 0; k < (MODE == 0 ? 8 : 4); ++k) c[k] = as_double(mw[k]);
 #pragma unroll
   for (int jj = 0; jj < R; ++jj) {
     if ((uint32_t)jj != j) continue;
@@ -92,17 +115,39 @@ QCB_HD void op_mat1(double2 (&a)[1 << R], uint32_t j, uint64_t cmask, const uint
     for (int s = 0; s < (1 << R); ++s) {
       if (s & (1 << jj)) continue;
       const int s1 = s | (1 << jj);
-      if (((ext0 | off[s]) & cmask) == cmask) {
-        double2 a0 = a[s], a1 = a[s1];
-        a[s] = cmul2(m00, a0, m01, a1);
-        a[s1] = cmul2(m10, a0, m11, a1);
+      if (sel & (1u << s)) {
+        const double2 a0 = a[s], a1 = a[s1];
+        if (MODE == 0) {
+          a[s] = cmul2(double2{c[0], c[1]}, a0, double2{c[2], c[3]}, a1);
+          a[s1] = cmul2(double2{c[4], c[5]}, a0, double2{c[6], c[7]}, a1);
+        } else if (MODE == 1) {      // m00 m01 m10 m11 real
+          a[s] = double2{QCB_FMA(c[0], a0.x, c[1] * a1.x), QCB_FMA(c[0], a0.y, c[1] * a1.y)};
+          a[s1] = double2{QCB_FMA(c[2], a0.x, c[3] * a1.x), QCB_FMA(c[2], a0.y, c[3] * a1.y)};
+        } else {                     // m00 = c0, m01 = i c1, m10 = i c2, m11 = c3
+          a[s] = double2{QCB_FMA(c[0], a0.x, -(c[1] * a1.y)), QCB_FMA(c[0], a0.y, c[1] * a1.x)};
+          a[s1] = double2{QCB_FMA(c[3], a1.x, -(c[2] * a0.y)), QCB_FMA(c[3], a1.y, c[2] * a0.x)};
+        }
       }
     }
   }
 }
 
 template <int R>
-QCB_HD void op_swapp(double2 (&a)[1 << R], uint32_t j0, uint32_t j1, uint64_t cmask, const uint64_t* mw, uint64_t ext0, const uint32_t (&off)[1 << R]) {
+QCB_HD void op_permx(double2 (&a)[1 << R], uint32_t j, uint32_t sel) {
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    if ((uint32_t)jj != j) continue;
+#pragma unroll
+    for (int s = 0; s < (1 << R); ++s) {
+      if (s & (1 << jj)) continue;
+      const int s1 = s | (1 << jj);
+      if (sel & (1u << s)) { const double2 t = a[s]; a[s] = a[s1]; a[s1] = t; }
+    }
+  }
+}
+
+template <int R>
+QCB_HD void op_swapp(double2 (&a)[1 << R], uint32_t j0, uint32_t j1, uint32_t sel, const uint64_t* mw) {
   const double2 ph{as_double(mw[0]), as_double(mw[1])};
   const bool unit = (ph.x == 1.0 && ph.y == 0.0);
 #pragma unroll
@@ -112,12 +157,12 @@ QCB_HD void op_swapp(double2 (&a)[1 << R], uint32_t j0, uint32_t j1, uint64_t cm
       if ((uint32_t)p0 != j0 || (uint32_t)p1 != j1) continue;
 #pragma unroll
       for (int s = 0; s < (1 << R); ++s) {
-        if (!((s >> p0) & 1) || ((s >> p1) & 1)) continue;     // s: bit p0 = 1, bit p1 = 0
-        const int t = (s ^ (1 << p0)) | (1 << p1);            // partner: bit p0 = 0, bit p1 = 1
-        if (((ext0 | off[s]) & cmask) == cmask) {
-          double2 x = a[s], y = a[t];
+        if (((s >> p0) & 1) || ((s >> p1) & 1)) continue;     // base pattern: both target bits 0
+        const int u = s | (1 << p0), v = s | (1 << p1);       // the two patterns that differ
+        if (sel & (1u << s)) {
+          double2 x = a[u], y = a[v];
           if (!unit) { x = cmul(ph, x); y = cmul(ph, y); }
-          a[s] = y; a[t] = x;
+          a[u] = y; a[v] = x;
         }
       }
     }
@@ -125,7 +170,7 @@ QCB_HD void op_swapp(double2 (&a)[1 << R], uint32_t j0, uint32_t j1, uint64_t cm
 }
 
 template <int R>
-QCB_HD void op_mat2(double2 (&a)[1 << R], uint32_t j0, uint32_t j1, uint64_t cmask, const uint64_t* mw, uint64_t ext0, const uint32_t (&off)[1 << R]) {
+QCB_HD void op_mat2(double2 (&a)[1 << R], uint32_t j0, uint32_t j1, uint32_t sel, const uint64_t* mw) {
 #pragma unroll
   for (int p0 = 0; p0 < R; ++p0) {
 #pragma unroll
@@ -134,7 +179,7 @@ QCB_HD void op_mat2(double2 (&a)[1 << R], uint32_t j0, uint32_t j1, uint64_t cma
 #pragma unroll
       for (int s = 0; s < (1 << R); ++s) {
         if (((s >> p0) & 1) || ((s >> p1) & 1)) continue;
-        if (((ext0 | off[s]) & cmask) != cmask) continue;
+        if (!(sel & (1u << s))) continue;
         const int i0 = s, i1 = s | (1 << p0), i2 = s | (1 << p1), i3 = s | (1 << p0) | (1 << p1);
         const double2 v0 = a[i0], v1 = a[i1], v2 = a[i2], v3 = a[i3];
         double2 o[4];
@@ -152,46 +197,69 @@ QCB_HD void op_mat2(double2 (&a)[1 << R], uint32_t j0, uint32_t j1, uint64_t cma
   }
 }
 
+// fused dense 2^R x 2^R block on all slot bits: out[row] = sum_col M[row][col] * a[col]
 template <int R>
-QCB_HD void apply_ops(double2 (&a)[1 << R], const uint64_t* ops, uint32_t n_slots, uint64_t ext0,
-                      const uint32_t (&off)[1 << R], const double* dev_vals) {
+QCB_HD void op_dense(double2 (&a)[1 << R], const uint64_t* mw) {
+  constexpr int D = 1 << R;
+  double2 o[D];
+#pragma unroll
+  for (int row = 0; row < D; ++row) {
+    double re = 0.0, im = 0.0;
+#pragma unroll
+    for (int col = 0; col < D; ++col) {
+      const double mr = as_double(mw[2 * (row * D + col)]), mi = as_double(mw[2 * (row * D + col) + 1]);
+      re = QCB_FMA(mr, a[col].x, re); re = QCB_FMA(-mi, a[col].y, re);
+      im = QCB_FMA(mr, a[col].y, im); im = QCB_FMA(mi, a[col].x, im);
+    }
+    o[row] = double2{re, im};
+  }
+#pragma unroll
+  for (int row = 0; row < D; ++row) a[row] = o[row];
+}
+
+template <int R>
+QCB_HD void apply_ops(double2 (&a)[1 << R], const uint64_t* ops, uint32_t n_slots, uint32_t idx0, uint64_t ext_hi,
+                      uint32_t m, const uint32_t (&off)[1 << R], const double* dev_vals) {
   for (uint32_t s = 0; s < n_slots;) {
     const uint64_t* w = ops + (uint64_t)s * T_OP_WORDS;
-    const uint64_t hdr = w[0];
-    const uint32_t kind = (uint32_t)(hdr & 0xff), j0 = (uint32_t)((hdr >> 8) & 0xff), j1 = (uint32_t)((hdr >> 16) & 0xff);
-    const uint32_t ns = (uint32_t)((hdr >> 24) & 0xff);
+    const uint64_t hdr = w[0], loc = w[1];
+    const uint32_t lo = (uint32_t)hdr, sel = (uint32_t)(hdr >> 32) & 0xffu;
+    const uint32_t kind = lo & 0xffu, j0 = (lo >> 8) & 0xffu, j1 = (lo >> 16) & 0xffu, ns = (lo >> 24) & 0xffu;
+    s += (ns ? ns : 1u);
+    if ((idx0 & (uint32_t)loc) != (uint32_t)(loc >> 32)) continue;
+    if ((ext_hi & w[2]) != w[3]) continue;
     switch (kind) {
-      case TD_MAT1: op_mat1<R>(a, j0, w[1], w + 4, ext0, off); break;
-      case TD_MAT2: op_mat2<R>(a, j0, j1, w[1], w + 4, ext0, off); break;
-      case TD_SWAPP: op_swapp<R>(a, j0, j1, w[1], w + 4, ext0, off); break;
+      case TD_MAT1: op_mat1<R, 0>(a, j0, sel, w + 4); break;
+      case TD_MAT1R: op_mat1<R, 1>(a, j0, sel, w + 4); break;
+      case TD_MAT1RI: op_mat1<R, 2>(a, j0, sel, w + 4); break;
+      case TD_PERMX: op_permx<R>(a, j0, sel); break;
+      case TD_DENSE: op_dense<R>(a, w + 4); break;
+      case TD_MAT2: op_mat2<R>(a, j0, j1, sel, w + 4); break;
+      case TD_SWAPP: op_swapp<R>(a, j0, j1, sel, w + 4); break;
       case TD_DMASK: {
-        const uint64_t mask = w[1], val = w[2];
         const double2 ph{as_double(w[4]), as_double(w[5])};
 #pragma unroll
         for (int k = 0; k < (1 << R); ++k)
-          if (((ext0 | off[k]) & mask) == val) a[k] = cmul(a[k], ph);
+          if (sel & (1u << k)) a[k] = cmul(a[k], ph);
         break;
       }
-      case TD_DTAB1: {
-        const uint64_t cmask = w[1]; const uint32_t bit = (uint32_t)w[2];
-        const double2 p0{as_double(w[4]), as_double(w[5])}, p1{as_double(w[6]), as_double(w[7])};
-#pragma unroll
-        for (int k = 0; k < (1 << R); ++k) {
-          const uint64_t e = ext0 | off[k];
-          if ((e & cmask) == cmask) a[k] = cmul(a[k], ((e >> bit) & 1) ? p1 : p0);
-        }
-        break;
-      }
-      case TD_DPOP1: {
-        const uint64_t mask = w[1];
-        const double2 ph{as_double(w[4]), as_double(w[5])};
+      case TD_DNEG: {
 #pragma unroll
         for (int k = 0; k < (1 << R); ++k)
-          if (popc64((ext0 | off[k]) & mask) == 1) a[k] = cmul(a[k], ph);
+          if (sel & (1u << k)) a[k] = double2{-a[k].x, -a[k].y};
+        break;
+      }
+      case TD_DPOP1: {   // phase where exactly one bit of the (ext-space) mask is set: rydberg-blockade
+        const uint64_t mask = w[4];
+        const double2 ph{as_double(w[6]), as_double(w[7])};
+        const uint64_t e0 = (ext_hi << m) | idx0;
+#pragma unroll
+        for (int k = 0; k < (1 << R); ++k)
+          if (popc64((e0 | off[k]) & mask) == 1) a[k] = cmul(a[k], ph);
         break;
       }
       case TD_AFFINE: {   // a' = alpha * a + beta, (alpha, beta) produced on the device by a reduction
-        const double* v = dev_vals + 4 * w[2];
+        const double* v = dev_vals + 4 * w[4];
         const double2 al{v[0], v[1]}, be{v[2], v[3]};
 #pragma unroll
         for (int k = 0; k < (1 << R); ++k) { double2 t = cmul(al, a[k]); a[k] = double2{t.x + be.x, t.y + be.y}; }
@@ -199,7 +267,6 @@ QCB_HD void apply_ops(double2 (&a)[1 << R], const uint64_t* ops, uint32_t n_slot
       }
       default: break;
     }
-    s += (ns ? ns : 1u);
   }
 }
 
@@ -221,7 +288,7 @@ QCB_HD void run_round_thread(double2* tile, const RoundCtx& rc, uint32_t m, uint
     double2 a[1 << R];
 #pragma unroll
     for (int s = 0; s < (1 << R); ++s) a[s] = tile[swz(idx0 | off[s])];
-    apply_ops<R>(a, rc.ops, rc.n_slots, (ext_hi << m) | idx0, off, dev_vals);
+    apply_ops<R>(a, rc.ops, rc.n_slots, idx0, ext_hi, m, off, dev_vals);
 #pragma unroll
     for (int s = 0; s < (1 << R); ++s) tile[swz(idx0 | off[s])] = a[s];
   }
