@@ -192,7 +192,7 @@ def run_ours(args):
 
     sv = L.StateVector(n, device=local_rank, rank=rank, world_size=world, nccl_id=nccl_id,
                        fusion=args.fusion, max_stage_cost=args.stage_cost, max_stage_rounds=args.stage_rounds,
-                       tile_bits=args.tile_bits, low_bits=args.low_bits)
+                       tile_bits=args.tile_bits, low_bits=args.low_bits, dense_mma=args.dense_mma)
 
     def step():
         sv.set_zero()
@@ -302,6 +302,7 @@ def main():
     ap.add_argument("--fusion", type=int, default=1)
     ap.add_argument("--stage-cost", type=int, default=0)
     ap.add_argument("--stage-rounds", type=int, default=0)
+    ap.add_argument("--dense-mma", type=int, default=0, help="0/1 = tensor-core rounds (default), 2 = interpreter only")
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--low-bits", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

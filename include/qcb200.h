@@ -58,7 +58,9 @@ typedef struct qcb_config {
   const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks (qcb_nccl_unique_id), or NULL */
   int32_t max_stage_cost;  /* 0 = default; scheduler knob: cost units one fused sweep may absorb       */
   int32_t max_stage_rounds;/* 0 = default; scheduler knob: shared-memory rounds one fused sweep may hold */
-  int32_t reserved[6];
+  int32_t dense_mma;       /* 0 = default (on); 1 = on: rounds run as dense 8x8 complex blocks on the fp64 tensor
+                              cores (DMMA); 2 = off: register-resident op interpreter only                 */
+  int32_t reserved[5];
 } qcb_config;
 
 /* ---- gate vocabulary: every branch of apply-gate-to-state (domain/circuit.clj:964-1071) ---- */

@@ -55,10 +55,72 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* sm) {
   __syncthreads();
 }
 
+// ------------------------------------------------------------------ tensor-core round
+// One warp applies the round's dense 16x16 real matrix to 8 groups at a time:
+//   D(16x8) = A(16x16) * B(16x8),  A = matrix variant (fragments straight from global/L2, reloaded only when the
+//   variant changes), B column n = the 16 reals of group n of the batch, gathered from the swizzled shared tile with
+//   8-byte loads in fragment order, D scattered back in place.  Fragment layouts: PTX ISA mma.m16n8k16 .f64
+//   (A reg i: row lane/4 + 8(i&1), col lane%4 + 4(i>>1); B reg v: row lane%4 + 4v, col lane/4;
+//    D reg i: row lane/4 + 8(i>>1), col 2(lane%4) + (i&1)).
+__device__ __forceinline__ void dmma_m16n8k16(double (&d)[4], const double (&a)[8], const double (&b)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, "
+      "{%16,%17,%18,%19};\n"
+      : "=d"(d[0]), "=d"(d[1]), "=d"(d[2]), "=d"(d[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+        "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]), "d"(0.0), "d"(0.0), "d"(0.0), "d"(0.0));
+}
+
+__device__ __forceinline__ void dmma_round_device(double2* tile, const uint64_t* sprog, const uint64_t* __restrict__ stage_g,
+                                                  uint32_t r, uint64_t ext_hi, uint32_t m, uint32_t tid) {
+  DmmaCtx c;
+  decode_dmma(sprog, r, c);
+  constexpr uint32_t NW = TILE_THREADS / 32;
+  const uint32_t lane = tid & 31u, warp = tid >> 5;
+  uint32_t Pl[4], Ps[4], cl, cs;
+  dmma_lane_setup(c, lane, Pl, Ps, cl, cs);
+  const uint32_t nbatch = 1u << (c.n_grp - 3u);
+  const uint32_t per = nbatch >= NW ? nbatch / NW : 1u;
+  // lane l prepares the l-th batch of this warp: swizzled base offset | variant << 16
+  uint32_t my_entry = 0;
+  {
+    const uint32_t bidx = warp * per + lane;
+    if (lane < per && bidx < nbatch) {
+      const uint32_t base = dmma_batch_base(c, bidx);
+      my_entry = swz(base) | (dmma_variant(c, base, ext_hi, m) << 16);
+    }
+  }
+  double* td = reinterpret_cast<double*>(tile);
+  const double* __restrict__ mats = reinterpret_cast<const double*>(stage_g + c.mat_off);
+  uint32_t cur = 0xffffffffu;
+  double A[8];
+  for (uint32_t b = 0; b < per; ++b) {
+    if (warp * per + b >= nbatch) break;                       // warp-uniform
+    const uint32_t entry = __shfl_sync(0xffffffffu, my_entry, b);
+    const uint32_t X = entry & 0xffffu, var = entry >> 16;
+    if (var != cur) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) A[i] = __ldg(mats + ((size_t)var * 8 + i) * 32 + lane);
+      cur = var;
+    }
+    double B[4], D[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) B[v] = td[2u * (X ^ Pl[v]) + cl];
+    dmma_m16n8k16(D, A, B);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) td[2u * (X ^ Ps[i]) + cs] = D[i];
+  }
+}
+
 // ------------------------------------------------------------------ the fused gate executor
+// MMA_ONLY = true: every round of the stage is a tensor-core round (the common case); the op interpreter is
+// compiled out, which keeps the A fragments in registers (no local-memory spills) at 3 CTAs per SM.
+template <bool MMA_ONLY>
 __global__ void __launch_bounds__(TILE_THREADS, 3)
 k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, uint32_t stage_words,
              const double* __restrict__ dev_vals, uint64_t n_active) {
+  // stage_words = descriptor part of the stage program (stage + round descriptors + interpreter op slots);
+  // tensor-core matrices follow it in global memory and are read through the read-only path
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StageCtx sc;
   decode_stage(stage_g, sc);
@@ -85,13 +147,17 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
 
     // ---- rounds
     for (uint32_t r = 0; r < sc.n_rounds; ++r) {
-      RoundCtx rc;
-      decode_round(sprog, r, rc);
-      switch (rc.r) {
-        case 0: run_round_thread<0>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
-        case 1: run_round_thread<1>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
-        case 2: run_round_thread<2>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
-        default: run_round_thread<3>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
+      if (MMA_ONLY || round_kind(sprog, r) == 1u) {
+        dmma_round_device(tile, sprog, stage_g, r, ext_hi, m, tid);
+      } else if (!MMA_ONLY) {
+        RoundCtx rc;
+        decode_round(sprog, r, rc);
+        switch (rc.r) {
+          case 0: run_round_thread<0>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
+          case 1: run_round_thread<1>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
+          case 2: run_round_thread<2>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
+          default: run_round_thread<3>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
+        }
       }
       __syncthreads();
     }
@@ -107,6 +173,8 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
                               const double* dev_vals, int num_sms, cudaStream_t stream, uint64_t* out_active) {
   StageCtx sc;
   decode_stage(stage_host, sc);
+  bool mma_only = sc.n_rounds > 0;
+  for (uint32_t r = 0; r < sc.n_rounds; ++r) mma_only = mma_only && round_kind(stage_host, r) == 1u;
   const uint32_t nb = sc.n_local - sc.m;
   const uint64_t tmask = (nb >= 64) ? ~0ULL : ((1ULL << nb) - 1ULL);
   // the part of the skip condition living in the rank bits is decided here, per rank
@@ -116,7 +184,8 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   const size_t smem = ((size_t)16 << sc.m) + 8 * (size_t)((stage_words + 1u) & ~1u) + 8 * ((size_t)1 << (sc.m - sc.L));
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_tile_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_tile_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
@@ -124,7 +193,8 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   while (per_sm > 1 && (smem + 1024) * per_sm > 227 * 1024) --per_sm;
   uint64_t grid = (uint64_t)num_sms * per_sm;
   if (grid > n_active) grid = n_active;
-  k_tile_stage<<<(unsigned)grid, TILE_THREADS, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active);
+  if (mma_only) k_tile_stage<true><<<(unsigned)grid, TILE_THREADS, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active);
+  else k_tile_stage<false><<<(unsigned)grid, TILE_THREADS, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active);
   return cudaGetLastError();
 }
 

@@ -66,6 +66,7 @@ Config config_from(const qcb_config& c) {
   k.strict = c.strict_parity;
   k.max_stage_cost = c.max_stage_cost;
   k.max_stage_rounds = c.max_stage_rounds;
+  k.dense_mma = (c.dense_mma == 2) ? 0 : 1;
   return k;
 }
 
@@ -425,27 +426,46 @@ static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& wo
   }
   words[base + 4] = (uint64_t)nruns;
   words[base + 41] = st.flags;
-  // rounds
+  // rounds: descriptors, then interpreter op slots, then (not copied to shared memory) tensor-core matrices
   size_t rbase = words.size();
   words.resize(rbase + st.rounds.size() * ROUND_WORDS, 0);
   for (size_t r = 0; r < st.rounds.size(); ++r) {
     Round& rd = st.rounds[r];
+    size_t rb = rbase + r * ROUND_WORDS;
+    words[rb + 0] = rd.slot_pos.size();
+    for (size_t j = 0; j < rd.slot_pos.size(); ++j) words[rb + 4 + j] = (uint64_t)rd.slot_pos[j];
+    if (rd.dmma) {
+      words[rb + 17] = 1;
+      words[rb + 18] = rd.grp_pos.size();
+      for (size_t j = 0; j < rd.grp_pos.size() && j < 10; ++j) words[rb + 19 + j] = (uint64_t)rd.grp_pos[j];
+      words[rb + 29] = rd.cond_pos.size();
+      for (size_t j = 0; j < rd.cond_pos.size(); ++j) words[rb + 30 + j] = (uint64_t)rd.cond_pos[j];
+      words[rb + 34] = (uint64_t)rd.j_load;
+      words[rb + 35] = (uint64_t)rd.j_store;
+      continue;
+    }
     std::vector<int> lanes;
     choose_lanes(m, rd.slot_pos, lanes);
     size_t ob = words.size();
     for (const Gate& g : rd.gates) put_gate_words(words, g, rd.slot_pos, m);
-    size_t rb = rbase + r * ROUND_WORDS;
-    words[rb + 0] = rd.slot_pos.size();
+    rb = rbase + r * ROUND_WORDS;
     words[rb + 1] = (words.size() - ob) / OP_WORDS;
     words[rb + 2] = ob - base;
     words[rb + 3] = lanes.size();
-    for (size_t j = 0; j < rd.slot_pos.size(); ++j) words[rb + 4 + j] = (uint64_t)rd.slot_pos[j];
     for (size_t j = 0; j < lanes.size(); ++j) words[rb + 7 + j] = (uint64_t)lanes[j];
     std::vector<int> ins(rd.slot_pos);
     ins.insert(ins.end(), lanes.begin(), lanes.end());
     std::sort(ins.begin(), ins.end());
     words[rb + 10] = ins.size();
     for (size_t j = 0; j < ins.size(); ++j) words[rb + 11 + j] = (uint64_t)ins[j];
+  }
+  words[base + 42] = words.size() - base;          // descriptor part (copied to shared memory by the kernel)
+  for (size_t r = 0; r < st.rounds.size(); ++r) {
+    Round& rd = st.rounds[r];
+    if (!rd.dmma) continue;
+    size_t rb = rbase + r * ROUND_WORDS;
+    words[rb + 2] = words.size() - base;
+    for (double d : rd.frag) words.push_back(dbl_bits(d));
   }
   words[base + 40] = words.size() - base;
 }
@@ -465,14 +485,19 @@ static bool gate_is_pure(const Gate& g, uint64_t slot_mask) {
 static inline cplx cm(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 static inline cplx ca(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
 
-// apply gate g (ext space, all bits among slot_pos) to a vector over the 2^r slot patterns
-static void small_apply(const Gate& g, const std::vector<int>& slot_pos, std::vector<cplx>& v) {
+// apply gate g (ext space) to a vector over the 2^r slot patterns.  Bits of g that are not slot bits are read
+// from `fixed` (an ext-space bit assignment): with them fixed, every supported gate acts linearly on the slots.
+static void small_apply(const Gate& g, const std::vector<int>& slot_pos, std::vector<cplx>& v, uint64_t fixed = 0) {
   const int r = (int)slot_pos.size(), dim = 1 << r;
+  uint64_t slot_mask = 0;
+  for (int p : slot_pos) slot_mask |= 1ULL << p;
   auto sbit = [&](int pos) { for (int j = 0; j < r; ++j) if (slot_pos[j] == pos) return j; return -1; };
   auto smask = [&](uint64_t m) { uint32_t o = 0; for (int j = 0; j < r; ++j) if ((m >> slot_pos[j]) & 1) o |= 1u << j; return o; };
+  auto outside_ok = [&](uint64_t mask, uint64_t val) { const uint64_t mo = mask & ~slot_mask; return (fixed & mo) == (val & mo); };
   std::vector<cplx> o = v;
   switch (g.kind) {
     case G_MAT1: {
+      if (!outside_ok(g.cmask, g.cmask)) break;
       const int j = sbit(g.t0); const uint32_t c = smask(g.cmask);
       for (int s = 0; s < dim; ++s) {
         if ((s >> j) & 1) continue;
@@ -484,6 +509,7 @@ static void small_apply(const Gate& g, const std::vector<int>& slot_pos, std::ve
       break;
     }
     case G_MAT2: {
+      if (!outside_ok(g.cmask, g.cmask)) break;
       const int j0 = sbit(g.t0), j1 = sbit(g.t1); const uint32_t c = smask(g.cmask);
       for (int s = 0; s < dim; ++s) {
         if (((s >> j0) & 1) || ((s >> j1) & 1) || (s & c) != c) continue;
@@ -497,6 +523,7 @@ static void small_apply(const Gate& g, const std::vector<int>& slot_pos, std::ve
       break;
     }
     case G_SWAPP: {
+      if (!outside_ok(g.cmask, g.cmask)) break;
       const int j0 = sbit(g.t0), j1 = sbit(g.t1); const uint32_t c = smask(g.cmask);
       for (int s = 0; s < dim; ++s) {
         if (((s >> j0) & 1) || ((s >> j1) & 1) || (s & c) != c) continue;
@@ -506,18 +533,142 @@ static void small_apply(const Gate& g, const std::vector<int>& slot_pos, std::ve
       break;
     }
     case G_DMASK: {
+      if (!outside_ok(g.dmask, g.dval)) break;
       const uint32_t mk = smask(g.dmask), vl = smask(g.dval);
       for (int s = 0; s < dim; ++s) if ((s & mk) == vl) o[s] = cm(v[s], g.m[0]);
       break;
     }
     case G_DTAB1: {
+      if (!outside_ok(g.cmask, g.cmask)) break;
       const int j = sbit(g.t0); const uint32_t c = smask(g.cmask);
-      for (int s = 0; s < dim; ++s) if ((s & c) == c) o[s] = cm(v[s], g.m[(s >> j) & 1]);
+      for (int s = 0; s < dim; ++s) {
+        if ((s & c) != c) continue;
+        const int tb = (j >= 0) ? ((s >> j) & 1) : (int)((fixed >> g.t0) & 1);
+        o[s] = cm(v[s], g.m[tb]);
+      }
+      break;
+    }
+    case G_DPOP1: {
+      const int outside_ones = popc(fixed & g.dmask & ~slot_mask);
+      const uint32_t mk = smask(g.dmask);
+      for (int s = 0; s < dim; ++s) if (outside_ones + popc((uint64_t)(s & mk)) == 1) o[s] = cm(v[s], g.m[0]);
       break;
     }
     default: break;
   }
   v.swap(o);
+}
+
+// bits of a gate that are read or written (ext space)
+static uint64_t gate_bits(const Gate& g) {
+  uint64_t b = g.target_mask() | g.diag_mask();
+  return b;
+}
+
+// ---- tensor-core round: the whole round as 2^k dense 16x16 real matrices in mma.m16n8k16 A-fragment order
+static bool dmma_eligible(const Config& cfg, const Stage& st, const Round& rd) {
+  if (!cfg.dense_mma || st.m < 6 || rd.slot_pos.size() > 3) return false;
+  uint64_t slot_mask = 0, cond = 0;
+  for (int p : rd.slot_pos) slot_mask |= 1ULL << p;
+  for (const Gate& g : rd.gates) {
+    if (g.kind == G_REFLECT || g.kind == G_DENSE) return false;
+    cond |= gate_bits(g) & ~slot_mask;
+  }
+  // padding the slot set to 3 needs free tile-local bits; lanes need 3 more
+  const int free_bits = st.m - (int)rd.slot_pos.size() - popc(cond & ((1ULL << st.m) - 1ULL));
+  if (free_bits < (3 - (int)rd.slot_pos.size()) + 3) return false;
+  return popc(cond) <= MAX_COND_BITS;
+}
+
+static void build_dmma_round(const Config& cfg, const Stage& st, Round& rd) {
+  const int m = st.m;
+  uint64_t slot_mask = 0;
+  for (int p : rd.slot_pos) slot_mask |= 1ULL << p;
+  // condition bits = every bit a gate touches that is not a slot bit
+  uint64_t cond = 0;
+  for (const Gate& g : rd.gates) cond |= gate_bits(g) & ~slot_mask;
+  rd.cond_pos.clear();
+  for (int p = 0; p < 64; ++p) if ((cond >> p) & 1) rd.cond_pos.push_back(p);
+  const uint64_t tile_mask = (1ULL << m) - 1ULL;
+  // pad the slot set to 3 bits with unused tile-local bits (identity on them), highest first
+  for (int p = m - 1; p >= 0 && rd.slot_pos.size() < 3; --p)
+    if (!((slot_mask >> p) & 1) && !((cond >> p) & 1)) { rd.slot_pos.push_back(p); slot_mask |= 1ULL << p; }
+  std::sort(rd.slot_pos.begin(), rd.slot_pos.end());
+  // lane bits: 3 tile-local bits that are neither slots nor conditions, with pairwise distinct residues mod 3
+  // (the XOR swizzle folds position p onto bank-group bit p % 3); then choose which slot bit rides on the
+  // half-warp's thread index for loads (j_load) and stores (j_store) so that 8-byte accesses are conflict-free
+  const uint64_t busy = slot_mask | (cond & tile_mask);
+  std::vector<int> lanes;
+  for (int res = 0; res < 3; ++res)
+    for (int p = res; p < m; p += 3)
+      if (!((busy >> p) & 1)) { lanes.push_back(p); break; }
+  uint64_t used = busy;
+  for (int p : lanes) used |= 1ULL << p;
+  for (int p = 0; p < m && lanes.size() < 3; ++p) if (!((used >> p) & 1)) { lanes.push_back(p); used |= 1ULL << p; }
+  // exhaustive search over lane orders and slot choices: loads vary (lanes[0], lanes[1], slot j_load) inside a
+  // half-warp, stores vary (lanes[1], lanes[2], slot j_store); each triple wants pairwise distinct residues mod 3
+  int jl = 0, js = 0;
+  {
+    int best = -1;
+    std::vector<int> base = lanes, bestl = lanes;
+    static const int P[6][3] = {{0,1,2},{0,2,1},{1,0,2},{1,2,0},{2,0,1},{2,1,0}};
+    if (base.size() == 3)
+      for (int perm = 0; perm < 6; ++perm) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
+        const int l0 = base[P[perm][0]], l1 = base[P[perm][1]], l2 = base[P[perm][2]];
+        const bool dl = (l0 % 3 != l1 % 3) && (l1 % 3 != l2 % 3) && (l0 % 3 != l2 % 3);
+        int score = 0;
+        if (dl && rd.slot_pos[a] % 3 == l2 % 3) ++score;
+        if (dl && rd.slot_pos[b] % 3 == l0 % 3) ++score;
+        if (score > best) { best = score; jl = a; js = b; bestl = {l0, l1, l2}; }
+      }
+    lanes = bestl;
+  }
+  rd.j_load = jl; rd.j_store = js;
+  // group-index bit order: lane bits, then free bits ascending, then tile-local condition bits (so that the
+  // batches of one warp share the variant)
+  rd.grp_pos = lanes;
+  uint64_t lane_mask = 0;
+  for (int p : lanes) lane_mask |= 1ULL << p;
+  for (int p = 0; p < m; ++p) if (!(((slot_mask | lane_mask | cond) >> p) & 1)) rd.grp_pos.push_back(p);
+  for (int p = 0; p < m; ++p) if (((cond >> p) & 1) && !((slot_mask >> p) & 1)) rd.grp_pos.push_back(p);
+  // matrices
+  const int k = (int)rd.cond_pos.size();
+  const size_t nvar = (size_t)1 << k;
+  rd.frag.assign(nvar * 256, 0.0);
+  // k-index / m-index -> (slot pattern, component): bit0 = component, bit1 = slot j (j_load / j_store),
+  // bits 2,3 = the two remaining slots in ascending slot order
+  auto idx_map = [&](int idx, int jsel, int& pattern, int& comp) {
+    comp = idx & 1;
+    int rem[2], nr = 0;
+    for (int j = 0; j < 3; ++j) if (j != jsel) rem[nr++] = j;
+    pattern = (((idx >> 1) & 1) << jsel) | (((idx >> 2) & 1) << rem[0]) | (((idx >> 3) & 1) << rem[1]);
+  };
+  for (size_t var = 0; var < nvar; ++var) {
+    uint64_t fixed = 0;
+    for (int j = 0; j < k; ++j) if ((var >> j) & 1) fixed |= 1ULL << rd.cond_pos[j];
+    cplx M[8][8];
+    for (int col = 0; col < 8; ++col) {
+      std::vector<cplx> v(8, cplx{0, 0});
+      v[col] = {1, 0};
+      for (const Gate& g : rd.gates) small_apply(g, rd.slot_pos, v, fixed);
+      for (int row = 0; row < 8; ++row) M[row][col] = v[row];
+    }
+    double W[16][16];
+    for (int mi = 0; mi < 16; ++mi) for (int ki = 0; ki < 16; ++ki) {
+      int pr, cr, pc, cc;
+      idx_map(mi, rd.j_store, pr, cr);
+      idx_map(ki, rd.j_load, pc, cc);
+      const cplx z = M[pr][pc];
+      // (re_out, im_out) = [[zr, -zi],[zi, zr]] (re_in, im_in)
+      W[mi][ki] = (cr == 0) ? (cc == 0 ? z.re : -z.im) : (cc == 0 ? z.im : z.re);
+    }
+    for (int i = 0; i < 8; ++i) for (int lane = 0; lane < 32; ++lane) {
+      const int mrow = lane / 4 + 8 * (i & 1), kcol = lane % 4 + 4 * (i >> 1);
+      rd.frag[var * 256 + (size_t)i * 32 + lane] = W[mrow][kcol];
+    }
+  }
+  rd.dmma = true;
+  (void)cfg;
 }
 
 static void fuse_round(Round& rd) {
@@ -561,6 +712,7 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates) 
     Blocker bl;
     std::vector<Gate> rest;
     const uint64_t tile_mask = (1ULL << st.m) - 1ULL;
+    const bool use_mma = cfg.dense_mma && st.m >= 6;
     for (size_t gi = 0; gi < pending.size(); ++gi) {
       const Gate& g = pending[gi];
       if (bl.conflicts(g)) { bl.block(g); rest.push_back(g); continue; }
@@ -570,6 +722,24 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates) 
       const uint64_t all = (t | g.diag_mask());
       const uint64_t want = all & tile_mask;
       const bool can_be_pure = cfg.fusion && (all & ~tile_mask) == 0 && g.kind != G_DPOP1 && g.kind != G_REFLECT;
+      if (use_mma && g.kind != G_REFLECT) {
+        // tensor-core round: every non-slot bit a gate touches becomes a condition bit (2^k matrix variants)
+        auto conds_after = [&](uint64_t Rn) {
+          uint64_t c = (gate_bits(g) & ~Rn);
+          for (const Gate& h : rd.gates) c |= gate_bits(h) & ~Rn;
+          return popc(c);
+        };
+        if (can_be_pure && popc(R | want) <= rmax && conds_after(R | want) <= MAX_COND_BITS) { R |= want; rd.gates.push_back(g); continue; }
+        if (can_be_pure && t == 0) {
+          bool later = false;
+          for (size_t k = gi + 1; k < pending.size() && !later; ++k) later = (pending[k].target_mask() & want) != 0;
+          if (later) { bl.block(g); rest.push_back(g); continue; }
+        }
+        if (popc(R | t) <= rmax && conds_after(R | t) <= MAX_COND_BITS) { R |= t; rd.gates.push_back(g); }
+        else if (rd.gates.empty()) { R |= t; rd.gates.push_back(g); }     // always make progress (falls back to the interpreter if needed)
+        else { bl.block(g); rest.push_back(g); }
+        continue;
+      }
       if (can_be_pure && popc(R | want) <= rmax) { R |= want; rd.gates.push_back(g); continue; }
       if (can_be_pure && t == 0) {
         // a diagonal gate that does not fit as pure now: defer it to a later round of this stage if one of its
@@ -584,7 +754,8 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates) 
     // unfused mode keeps exactly one gate per round anyway (one gate per stage)
     for (int b = 0; b < st.m; ++b) if ((R >> b) & 1) rd.slot_pos.push_back(b);
     // pad with extra slot bits when the tile is so small that fewer than 8 lanes exist: not needed
-    if (cfg.fusion) fuse_round(rd);
+    if (dmma_eligible(cfg, st, rd)) build_dmma_round(cfg, st, rd);
+    else if (cfg.fusion) fuse_round(rd);
     st.rounds.push_back(std::move(rd));
     pending.swap(rest);
   }

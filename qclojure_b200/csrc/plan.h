@@ -71,15 +71,28 @@ enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_
 //     [0] r  [1] n_op_slots  [2] op word offset (from stage start)  [3] n_lane
 //     [4..7)  slot_pos[3] (tile-local, ascending)   [7..10) lane_pos[3]
 //     [10] n_ins  [11..17) ins_pos[6] ascending (slot ∪ lane positions)
+//     [17] kind (0 = interpreter round, 1 = tensor-core round)   [18] n_grp_bits   [19..29) grp_pos[10]
+//     [29] k (condition bits)  [30..34) cond_pos[4] (ext positions)  [34] j_load  [35] j_store
+//     tensor-core rounds: [2] = word offset of the A-fragment matrices (2^k * 256 doubles, after all descriptors)
+//   StageDesc [42] = number of leading words (descriptors + interpreter op slots) that the kernel copies to smem
 constexpr int STAGE_WORDS = 48;
-constexpr int ROUND_WORDS = 20;
+constexpr int ROUND_WORDS = 40;
 constexpr uint64_t FLAG_NEEDS_SUM = 1;     // epilogue: accumulate sum of amplitudes (for the next REFLECT)
 
 enum StageKind : int { S_TILE = 0, S_EXCHANGE = 1, S_SUM = 2 };
 
+constexpr int MAX_COND_BITS = 4;          // outside-condition bits of a tensor-core round (2^k matrix variants)
+
 struct Round {
   std::vector<int> slot_pos;        // tile-local positions held in registers
   std::vector<Gate> gates;          // gates with bits already translated to ext space (see Stage)
+  // tensor-core ("dmma") round: the whole round is one of 2^k dense 16x16 real matrices, selected per group
+  // by the values of k outside-condition bits (controls / diagonal operands that are not slot bits)
+  bool dmma = false;
+  std::vector<int> cond_pos;        // ext positions of the condition bits (variant index bit j <-> cond_pos[j])
+  std::vector<int> grp_pos;         // tile-local position of group-index bit i (first 3 = lane bits)
+  int j_load = 0, j_store = 0;      // slot index paired with k bit 1 (loads) / m bit 1 (stores): bank-conflict control
+  std::vector<double> frag;         // 2^k * 256 doubles in mma.m16n8k16 A-fragment order [variant][reg][lane]
 };
 
 struct Stage {
@@ -103,6 +116,7 @@ struct Config {
   int fusion = 1, strict = 1;
   int max_stage_cost = 0;
   int max_stage_rounds = 0;
+  int dense_mma = 1;           // rounds as dense 8x8 complex blocks on the fp64 tensor cores
   int threads = 256;
 };
 

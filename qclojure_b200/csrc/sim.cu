@@ -271,7 +271,7 @@ int execute_plan(qcb_sim* h, Plan& plan) {
     Stage& st = plan.stages[si];
     const uint64_t off = plan.stage_offsets[si];
     if (st.kind == S_TILE) {
-      const uint32_t words = (uint32_t)plan.words[off + 2 + 40];
+      const uint32_t words = (uint32_t)plan.words[off + 2 + 42];      // descriptor part only (copied to smem)
       uint64_t active = 0;
       CU(h, launch_tile_stage(h->state, h->d_prog + off + 2, plan.words.data() + off + 2, words, h->d_vals, h->num_sms, h->stream, &active));
       if (active) { h->stats.n_sweeps++; h->stats.n_kernel_launches++; h->stats.n_rounds += st.rounds.size(); }

@@ -26,7 +26,7 @@ namespace qcb {
 // must match plan.h (DevOpKind)
 enum : uint32_t { TD_MAT1 = 0, TD_MAT2 = 1, TD_SWAPP = 2, TD_DMASK = 3, TD_DNEG = 4, TD_DPOP1 = 5, TD_AFFINE = 6,
                   TD_MAT1R = 7, TD_MAT1RI = 8, TD_PERMX = 9, TD_DENSE = 10 };
-constexpr int T_OP_WORDS = 16, T_STAGE_WORDS = 48, T_ROUND_WORDS = 20;
+constexpr int T_OP_WORDS = 16, T_STAGE_WORDS = 48, T_ROUND_WORDS = 40;
 
 QCB_HD uint32_t swz(uint32_t i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u); }
 
@@ -292,6 +292,75 @@ QCB_HD void run_round_thread(double2* tile, const RoundCtx& rc, uint32_t m, uint
 #pragma unroll
     for (int s = 0; s < (1 << R); ++s) tile[swz(idx0 | off[s])] = a[s];
   }
+}
+
+// ---- tensor-core ("dmma") rounds: the round is one of 2^k dense 16x16 real matrices applied to the 16 reals
+// (8 slot patterns x re/im) of every group with mma.sync.m16n8k16.f64; 8 groups (the lane bits) form one MMA.
+struct DmmaCtx {
+  uint32_t n_grp, k, j_load, j_store;
+  uint32_t slot_pos[3], grp_pos[10], cond_pos[4];
+  uint64_t mat_off;
+};
+
+QCB_HD uint32_t round_kind(const uint64_t* stage, uint32_t round_idx) {
+  return (uint32_t)stage[T_STAGE_WORDS + (uint64_t)round_idx * T_ROUND_WORDS + 17];
+}
+
+QCB_HD void decode_dmma(const uint64_t* stage, uint32_t round_idx, DmmaCtx& c) {
+  const uint64_t* w = stage + T_STAGE_WORDS + (uint64_t)round_idx * T_ROUND_WORDS;
+  c.mat_off = w[2]; c.n_grp = (uint32_t)w[18]; c.k = (uint32_t)w[29]; c.j_load = (uint32_t)w[34]; c.j_store = (uint32_t)w[35];
+  for (int j = 0; j < 3; ++j) c.slot_pos[j] = (uint32_t)w[4 + j];
+  for (int j = 0; j < 10; ++j) c.grp_pos[j] = (uint32_t)w[19 + j];
+  for (int j = 0; j < 4; ++j) c.cond_pos[j] = (uint32_t)w[30 + j];
+}
+
+// k-index / m-index of the MMA -> tile-local offset of the slot pattern: bit 1 = slot jsel, bits 2,3 = the two
+// remaining slots in ascending order (bit 0 is the re/im component).  Must match plan.cpp:build_dmma_round.
+QCB_HD uint32_t dmma_pattern_offset(const DmmaCtx& c, uint32_t idx, uint32_t jsel) {
+  uint32_t rem0 = (jsel == 0) ? 1u : 0u, rem1 = (jsel == 2) ? 1u : 2u;
+  uint32_t o = ((idx >> 1) & 1u) << (jsel == 0 ? c.slot_pos[0] : (jsel == 1 ? c.slot_pos[1] : c.slot_pos[2]));
+  o |= ((idx >> 2) & 1u) << (rem0 == 0 ? c.slot_pos[0] : c.slot_pos[1]);
+  o |= ((idx >> 3) & 1u) << (rem1 == 1 ? c.slot_pos[1] : c.slot_pos[2]);
+  return o;
+}
+
+// tile-local offset of the lane-bit pattern n (column of the MMA = group n of the batch)
+QCB_HD uint32_t dmma_lane_offset(const DmmaCtx& c, uint32_t n) {
+  return ((n & 1u) << c.grp_pos[0]) | (((n >> 1) & 1u) << c.grp_pos[1]) | (((n >> 2) & 1u) << c.grp_pos[2]);
+}
+
+// Per-lane swizzled element offsets (in double2 units) relative to a batch: loads Pl[v] (B fragment register v,
+// k = q + 4v, column n = g) and stores Ps[i] (D register i, row m = g + 8(i>>1), column n = 2q + (i&1)).
+QCB_HD void dmma_lane_setup(const DmmaCtx& c, uint32_t lane, uint32_t (&Pl)[4], uint32_t (&Ps)[4], uint32_t& comp_l, uint32_t& comp_s) {
+  const uint32_t g = lane >> 2, q = lane & 3u;
+  comp_l = q & 1u;
+  comp_s = g & 1u;
+#pragma unroll
+  for (uint32_t v = 0; v < 4; ++v) Pl[v] = swz(dmma_lane_offset(c, g) | dmma_pattern_offset(c, q + 4u * v, c.j_load));
+#pragma unroll
+  for (uint32_t i = 0; i < 4; ++i) Ps[i] = swz(dmma_lane_offset(c, 2u * q + (i & 1u)) | dmma_pattern_offset(c, g + 8u * (i >> 1), c.j_store));
+}
+
+// batch index -> tile-local base offset (group bits 3.. deposited at grp_pos[3..])
+QCB_HD uint32_t dmma_batch_base(const DmmaCtx& c, uint32_t batch) {
+  uint32_t o = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 7; ++i) if (i + 3u < c.n_grp) o |= ((batch >> i) & 1u) << c.grp_pos[i + 3];
+  return o;
+}
+
+// variant index of a batch: bit j = value of condition bit cond_pos[j] (tile-local -> from base, else from ext_hi)
+QCB_HD uint32_t dmma_variant(const DmmaCtx& c, uint32_t base, uint64_t ext_hi, uint32_t m) {
+  uint32_t v = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) {
+    if (j < c.k) {
+      const uint32_t p = c.cond_pos[j];
+      const uint32_t bit = (p < m) ? ((base >> p) & 1u) : (uint32_t)((ext_hi >> (p - m)) & 1ULL);
+      v |= bit << j;
+    }
+  }
+  return v;
 }
 
 // ---- tile addressing

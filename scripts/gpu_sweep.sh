@@ -4,6 +4,7 @@ TAG=${1:-sweep}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 $OUT/pytest_gpu.log
+QCB_DENSE_MMA=2 timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > $OUT/pytest_gpu_interp.log 2>&1; echo "pytest (interpreter only) exit $?"; tail -3 $OUT/pytest_gpu_interp.log
 [ -x scripts/dmma_bench ] && timeout 120 scripts/dmma_bench | tee $OUT/dmma.log
 SWEEP=${SWEEP:-0,0,0,0 200,2,0,0 200,3,0,0 200,4,0,0 200,5,0,0 400,6,0,0 200,3,11,0 200,4,12,6}
 for cfg in $SWEEP; do

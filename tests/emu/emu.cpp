@@ -58,6 +58,23 @@ int emu_stage_max_conflict(Emu* e, uint64_t si, int nthreads) {
   StageCtx sc; decode_stage(st, sc);
   int worst = 1;
   for (uint32_t r = 0; r < sc.n_rounds; ++r) {
+    if (round_kind(st, r) == 1u) {
+      // 8-byte accesses are served per half-warp (16 lanes x 8 B = 128 B): count lanes per 8-byte bank pair
+      DmmaCtx c; decode_dmma(st, r, c);
+      for (int half = 0; half < 2; ++half) {
+        for (int which = 0; which < 8; ++which) {      // 4 load registers + 4 store registers
+          int cnt[16] = {0};
+          for (uint32_t l = 0; l < 16; ++l) {
+            uint32_t lane = half * 16 + l, Pl[4], Ps[4], cl, cs;
+            dmma_lane_setup(c, lane, Pl, Ps, cl, cs);
+            uint32_t dw = which < 4 ? 2u * Pl[which] + cl : 2u * Ps[which - 4] + cs;   // index in doubles
+            cnt[dw & 15]++;
+          }
+          for (int b = 0; b < 16; ++b) if (cnt[b] > worst) worst = cnt[b];
+        }
+      }
+      continue;
+    }
     RoundCtx rc; decode_round(st, r, rc);
     uint32_t ngroups = 1u << (sc.m - rc.r);
     for (uint32_t g0 = 0; g0 < ngroups && g0 < (uint32_t)nthreads; g0 += 8) {
@@ -71,6 +88,43 @@ int emu_stage_max_conflict(Emu* e, uint64_t si, int nthreads) {
     }
   }
   return worst;
+}
+
+// Software model of mma.sync.m16n8k16.f64 (PTX ISA fragment layouts, the same ones kernels.cu relies on) and of
+// kernels.cu:dmma_round_device, warp by warp.
+static void emu_dmma_round(double2* tile, const uint64_t* st, uint32_t r, uint64_t ext_hi, uint32_t m, int nthreads) {
+  DmmaCtx c; decode_dmma(st, r, c);
+  const uint32_t NW = nthreads / 32;
+  const uint32_t nbatch = 1u << (c.n_grp - 3u);
+  const uint32_t per = nbatch >= NW ? nbatch / NW : 1u;
+  double* td = reinterpret_cast<double*>(tile);
+  const double* mats = reinterpret_cast<const double*>(st + c.mat_off);
+  for (uint32_t warp = 0; warp < NW; ++warp) {
+    for (uint32_t b = 0; b < per; ++b) {
+      const uint32_t bidx = warp * per + b;
+      if (bidx >= nbatch) break;
+      const uint32_t base = dmma_batch_base(c, bidx);
+      const uint32_t X = swz(base), var = dmma_variant(c, base, ext_hi, m);
+      double A[32][8], B[32][4], D[32][4];
+      uint32_t Ps[32][4], cs[32];
+      for (uint32_t lane = 0; lane < 32; ++lane) {
+        uint32_t Pl[4], cl;
+        dmma_lane_setup(c, lane, Pl, Ps[lane], cl, cs[lane]);
+        for (int i = 0; i < 8; ++i) A[lane][i] = mats[((size_t)var * 8 + i) * 32 + lane];
+        for (int v = 0; v < 4; ++v) B[lane][v] = td[2u * (X ^ Pl[v]) + cl];
+      }
+      double Am[16][16], Bm[16][8], Dm[16][8];
+      for (uint32_t lane = 0; lane < 32; ++lane) {
+        for (int i = 0; i < 8; ++i) Am[lane / 4 + 8 * (i & 1)][lane % 4 + 4 * (i >> 1)] = A[lane][i];
+        for (int v = 0; v < 4; ++v) Bm[lane % 4 + 4 * v][lane / 4] = B[lane][v];
+      }
+      for (int i = 0; i < 16; ++i) for (int j = 0; j < 8; ++j) { double acc = 0; for (int k = 0; k < 16; ++k) acc += Am[i][k] * Bm[k][j]; Dm[i][j] = acc; }
+      for (uint32_t lane = 0; lane < 32; ++lane)
+        for (int i = 0; i < 4; ++i) D[lane][i] = Dm[lane / 4 + 8 * (i >> 1)][2 * (lane % 4) + (i & 1)];
+      for (uint32_t lane = 0; lane < 32; ++lane)
+        for (int i = 0; i < 4; ++i) td[2u * (X ^ Ps[lane][i]) + cs[lane]] = D[lane][i];
+    }
+  }
 }
 
 // Run one S_TILE stage on this rank's local slice.
@@ -94,6 +148,7 @@ int emu_run_tile_stage(Emu* e, uint64_t si, double* state, const double* dev_val
     for (uint32_t i = 0; i < tile_n; ++i)
       tile[swz(i)] = gs[base + hi_offset(st, sc, i >> sc.L) + (i & ((1u << sc.L) - 1u))];
     for (uint32_t r = 0; r < sc.n_rounds; ++r) {
+      if (round_kind(st, r) == 1u) { emu_dmma_round(tile.data(), st, r, ext_hi, sc.m, nthreads); continue; }
       RoundCtx rc; decode_round(st, r, rc);
       for (uint32_t tid = 0; tid < (uint32_t)nthreads; ++tid) {
         switch (rc.r) {

@@ -22,8 +22,10 @@ def _rand_state(n, seed):
 
 @pytest.mark.parametrize("n,tile,low,fusion", [
     (1, 0, 0, 1), (2, 0, 0, 1), (3, 0, 0, 1), (5, 0, 0, 1), (6, 4, 2, 1), (8, 5, 2, 1), (9, 6, 3, 0),
-    (10, 7, 4, 1), (11, 8, 3, 1), (13, 10, 4, 1), (14, 12, 4, 1), (12, 12, 4, 0)])
-def test_emulated_executor_matches_oracle_all_gates(n, tile, low, fusion):
+    (10, 7, 4, 1), (11, 8, 3, 1), (13, 10, 4, 1), (14, 12, 4, 1), (12, 12, 4, 0), (15, 13, 6, 1), (14, 13, 4, 0),
+    (9, 6, 2, 1), (10, 9, 3, 1)])
+@pytest.mark.parametrize("dense_mma", [1, 2])
+def test_emulated_executor_matches_oracle_all_gates(n, tile, low, fusion, dense_mma):
     rng = np.random.default_rng(7 * n + tile)
     if n >= 3:
         circ = _all_gates_circuit(n, rng)
@@ -37,7 +39,7 @@ def test_emulated_executor_matches_oracle_all_gates(n, tile, low, fusion):
                 C.cnot(circ, q, 1 - q); C.crz(circ, 1 - q, q, 0.3); C.swap(circ, 0, 1)
     init = _rand_state(n, n)
     want = O.execute_circuit(circ, init)
-    got = E.run_world(n, circ["operations"], init, tile_bits=tile, low_bits=low, fusion=fusion)
+    got = E.run_world(n, circ["operations"], init, tile_bits=tile, low_bits=low, fusion=fusion, dense_mma=dense_mma)
     assert np.max(np.abs(got - want)) <= TOL
 
 
