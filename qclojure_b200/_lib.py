@@ -15,7 +15,7 @@ import numpy as np
 from . import ops as OPS
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libqcb200.so")
+LIB_PATH = os.environ.get("QCB_LIB") or os.path.join(HERE, "lib", "libqcb200.so")   # QCB_LIB: profiling build (make PROFILE=1)
 CSRC = os.path.join(HERE, "csrc")
 
 QCB_OK = 0

@@ -12,6 +12,8 @@
 //                      implements the reference's measure-state rule (domain/state.clj:894-913).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "tile_core.h"
@@ -55,9 +57,36 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* sm) {
   __syncthreads();
 }
 
+// ------------------------------------------------------------------ mbarrier / named-barrier primitives
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+template <bool BACKOFF = false>
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok;
+  for (;;) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) break;
+    if (BACKOFF) __nanosleep(64);      // keep the pollers out of the issue slots of the working warps
+  }
+}
+// arrive on `bar` once every cp.async issued so far by this thread has landed in shared memory
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ------------------------------------------------------------------ tensor-core round
 // One warp applies the round's dense 16x16 real matrix to 8 groups at a time:
-//   D(16x8) = A(16x16) * B(16x8),  A = matrix variant (fragments straight from global/L2, reloaded only when the
+//   D(16x8) = A(16x16) * B(16x8),  A = matrix variant (fragments from global through L1, reloaded only when the
 //   variant changes), B column n = the 16 reals of group n of the batch, gathered from the swizzled shared tile with
 //   8-byte loads in fragment order, D scattered back in place.  Fragment layouts: PTX ISA mma.m16n8k16 .f64
 //   (A reg i: row lane/4 + 8(i&1), col lane%4 + 4(i>>1); B reg v: row lane%4 + 4v, col lane/4;
@@ -71,102 +100,308 @@ __device__ __forceinline__ void dmma_m16n8k16(double (&d)[4], const double (&a)[
         "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]), "d"(0.0), "d"(0.0), "d"(0.0), "d"(0.0));
 }
 
-__device__ __forceinline__ void dmma_round_device(double2* tile, const uint64_t* sprog, const uint64_t* __restrict__ stage_g,
-                                                  uint32_t r, uint64_t ext_hi, uint32_t m, uint32_t tid) {
-  DmmaCtx c;
-  decode_dmma(sprog, r, c);
-  constexpr uint32_t NW = TILE_THREADS / 32;
-  const uint32_t lane = tid & 31u, warp = tid >> 5;
-  uint32_t Pl[4], Ps[4], cl, cs;
-  dmma_lane_setup(c, lane, Pl, Ps, cl, cs);
-  const uint32_t nbatch = 1u << (c.n_grp - 3u);
-  const uint32_t per = nbatch >= NW ? nbatch / NW : 1u;
-  // lane l prepares the l-th batch of this warp: swizzled base offset | variant << 16
-  uint32_t my_entry = 0;
-  {
-    const uint32_t bidx = warp * per + lane;
-    if (lane < per && bidx < nbatch) {
-      const uint32_t base = dmma_batch_base(c, bidx);
-      my_entry = swz(base) | (dmma_variant(c, base, ext_hi, m) << 16);
-    }
+// Per-round tables live in shared memory (built once per launch): lane_tab[r][lane] = 8 byte offsets
+// (tile_core.h: dmma_lane_entry), batch_tab[r][b] = swizzled byte offset | local variant bits << 20.
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void dmma_load_A(double (&A)[8], const double* __restrict__ mats, uint32_t var) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) A[i] = __ldg(mats + ((size_t)var * 8 + i) * 32);
+}
+
+// What a warp needs to know about its share of a tensor-core round before the round barrier opens: the first
+// matrix variant (prefetched into registers while the previous round is still running).
+struct DmmaNext {
+  uint32_t var;
+  bool active;
+};
+
+template <int WPG>
+__device__ __forceinline__ void dmma_geometry(const uint64_t* w, uint32_t gwarp, uint32_t& per, uint32_t& b0, bool& active) {
+  const uint32_t nbatch = 1u << ((uint32_t)w[18] - 3u);
+  per = nbatch >= (uint32_t)WPG ? nbatch / WPG : 1u;
+  b0 = gwarp * per;
+  active = b0 < nbatch;                                         // warp-uniform
+}
+
+__device__ __forceinline__ uint32_t dmma_var_hi(const uint64_t* w, uint64_t ext_hi, uint32_t m) {
+  const uint32_t k = (uint32_t)w[29];
+  uint32_t var_hi = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) {
+    const uint32_t p = (uint32_t)w[30 + j];
+    if (j < k && p >= m) var_hi |= (uint32_t)((ext_hi >> (p - m)) & 1ULL) << j;
   }
-  double* td = reinterpret_cast<double*>(tile);
-  const double* __restrict__ mats = reinterpret_cast<const double*>(stage_g + c.mat_off);
-  uint32_t cur = 0xffffffffu;
-  double A[8];
-  for (uint32_t b = 0; b < per; ++b) {
-    if (warp * per + b >= nbatch) break;                       // warp-uniform
-    const uint32_t entry = __shfl_sync(0xffffffffu, my_entry, b);
-    const uint32_t X = entry & 0xffffu, var = entry >> 16;
-    if (var != cur) {
+  return var_hi;
+}
+
+// One warp's share of a tensor-core round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
+// Fast path (every batch of the warp uses the same variant): software pipeline  LDS(i+1) | DMMA(i) | STS(i-1), so the
+// warp's stream of tensor instructions is not interrupted by shared-memory latency.
+template <int WPG>
+__device__ __forceinline__ void dmma_round_run(uint32_t tile_s, const uint64_t* w, const uint64_t* __restrict__ stage_g,
+                                               const uint4* lane_tab_r, const uint32_t* btab, uint64_t ext_hi, uint32_t m,
+                                               uint32_t gwarp, uint32_t lane, double (&A)[8], uint32_t cur) {
+  uint32_t per, b0;
+  bool active;
+  dmma_geometry<WPG>(w, gwarp, per, b0, active);
+  if (!active) return;
+  const uint32_t var_hi = dmma_var_hi(w, ext_hi, m);
+  const uint4 l0 = lane_tab_r[2u * lane], l1 = lane_tab_r[2u * lane + 1u];
+  const uint32_t pl[4] = {l0.x, l0.y, l0.z, l0.w};
+  const uint32_t ps[4] = {l1.x, l1.y, l1.z, l1.w};
+  btab += b0;
+  auto load_B = [&](uint32_t X, double (&B)[4]) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) A[i] = __ldg(mats + ((size_t)var * 8 + i) * 32 + lane);
-      cur = var;
+    for (int v = 0; v < 4; ++v) B[v] = lds_f64(tile_s + (pl[v] ^ X));
+  };
+  auto store_D = [&](uint32_t X, const double (&D)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sts_f64(tile_s + (ps[i] ^ X), D[i]);
+  };
+  const uint32_t e_first = btab[0], e_last = btab[per - 1u];
+  if ((e_first >> 20) == (e_last >> 20)) {
+    // local condition bits are the top bits of the batch index: equal at both ends => equal throughout
+    double Bc[4], Dp[4];
+    uint32_t X = e_first & DMMA_BATCH_OFF_MASK, Xp = X;
+    load_B(X, Bc);
+#pragma unroll 2
+    for (uint32_t i = 0; i < per; ++i) {
+      double Bn[4], D[4];
+      uint32_t Xn = X;
+      if (i + 1u < per) {
+        Xn = btab[i + 1u] & DMMA_BATCH_OFF_MASK;
+        load_B(Xn, Bn);
+      }
+      dmma_m16n8k16(D, A, Bc);
+      if (i) store_D(Xp, Dp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { Dp[q] = D[q]; Bc[q] = Bn[q]; }
+      Xp = X; X = Xn;
     }
+    store_D(Xp, Dp);
+    return;
+  }
+  const double* __restrict__ mats = reinterpret_cast<const double*>(stage_g + w[2]) + lane;
+  for (uint32_t bi = 0; bi < per; ++bi) {
+    const uint32_t e = btab[bi];
+    const uint32_t v = var_hi | (e >> 20), X = e & DMMA_BATCH_OFF_MASK;
+    if (v != cur) { dmma_load_A(A, mats, v); cur = v; }
     double B[4], D[4];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) B[v] = td[2u * (X ^ Pl[v]) + cl];
+    load_B(X, B);
     dmma_m16n8k16(D, A, B);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) td[2u * (X ^ Ps[i]) + cs] = D[i];
+    store_D(X, D);
   }
 }
 
+// ------------------------------------------------------------------ optional cycle accounting (make PROFILE=1)
+#ifdef QCB_TILE_PROFILE
+enum { PF_C_WAIT_FULL = 0, PF_C_BARRIER, PF_C_SETUP, PF_C_ROUND, PF_C_TOTAL, PF_M_LOAD, PF_M_WAIT_DONE, PF_M_STORE, PF_M_TOTAL, PF_N };
+__device__ unsigned long long g_tile_prof[PF_N];
+#define PF_DECL long long pf_t = clock64(), pf_t0 = pf_t
+#define PF_ADD(cat) do { const long long pf_n = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_tile_prof[cat], (unsigned long long)(pf_n - pf_t)); pf_t = pf_n; } while (0)
+#define PF_TOTAL(cat) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_tile_prof[cat], (unsigned long long)(clock64() - pf_t0)); } while (0)
+void tile_prof_dump() {
+  unsigned long long h[PF_N];
+  if (cudaMemcpyFromSymbol(h, g_tile_prof, sizeof h) != cudaSuccess) return;
+  static const char* names[PF_N] = {"consumer wait full", "consumer round barrier", "consumer setup+prefetch", "consumer round work", "consumer total",
+                                    "mover load issue", "mover wait done", "mover store", "mover total"};
+  for (int i = 0; i < PF_N; ++i) {
+    const unsigned long long tot = h[i < PF_M_LOAD ? PF_C_TOTAL : PF_M_TOTAL];
+    fprintf(stderr, "[tile-prof] %-26s %14llu warp-cycles  %5.1f%%\n", names[i], h[i], tot ? 100.0 * (double)h[i] / (double)tot : 0.0);
+  }
+  unsigned long long z[PF_N] = {};
+  cudaMemcpyToSymbol(g_tile_prof, z, sizeof z);
+}
+#else
+#define PF_DECL
+#define PF_ADD(cat)
+#define PF_TOTAL(cat)
+void tile_prof_dump() {}
+#endif
+
 // ------------------------------------------------------------------ the fused gate executor
+// One persistent CTA per SM, warp-specialised over a ring of `nbuf` tile buffers in shared memory:
+//   mover warps      stream tile j into buffer j % nbuf with cp.async (completion signalled on full[]), then write
+//                    tile j-(nbuf-1) back to HBM once its consumer group has signalled done[];
+//   consumer groups  NG groups of WPG warps; group g runs the stage's rounds on tiles j = g, g+NG, ... in shared
+//                    memory (tensor-core rounds or interpreter rounds), rounds separated by the group's own named
+//                    barrier.  Two groups on different tiles keep the fp64 tensor pipe fed while the other group
+//                    sits at a round barrier or waits for operands.
+// HBM traffic of the tiles ahead (loads) and behind (stores) overlaps the arithmetic.  Each mover thread loads and
+// stores the same elements of a buffer, so buffer re-use needs no further barrier than its own program order.
+constexpr int MOVER_WARPS = 4;
+constexpr int MOVER_THREADS = MOVER_WARPS * 32;
+
 // MMA_ONLY = true: every round of the stage is a tensor-core round (the common case); the op interpreter is
-// compiled out, which keeps the A fragments in registers (no local-memory spills) at 3 CTAs per SM.
-template <bool MMA_ONLY>
-__global__ void __launch_bounds__(TILE_THREADS, 3)
+// compiled out, which keeps the hot loop free of register spills.
+template <int NG, int WPG, bool MMA_ONLY>
+__global__ void __launch_bounds__((NG * WPG + MOVER_WARPS) * 32, 1)
 k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, uint32_t stage_words,
-             const double* __restrict__ dev_vals, uint64_t n_active) {
+             const double* __restrict__ dev_vals, uint64_t n_active, uint32_t nbuf) {
   // stage_words = descriptor part of the stage program (stage + round descriptors + interpreter op slots);
   // tensor-core matrices follow it in global memory and are read through the read-only path
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr uint32_t NCW = NG * WPG, NTHREADS = (NCW + MOVER_WARPS) * 32, NCT = NCW * 32, GT = WPG * 32;
   StageCtx sc;
   decode_stage(stage_g, sc);
-  const uint32_t m = sc.m, L = sc.L, tile_n = 1u << m, tid = threadIdx.x;
-  double2* tile = reinterpret_cast<double2*>(smem_raw);
-  uint64_t* sprog = reinterpret_cast<uint64_t*>(smem_raw + ((size_t)16 << m));
-  uint64_t* hoff = sprog + ((stage_words + 1u) & ~1u);
+  const uint32_t m = sc.m, L = sc.L, tile_n = 1u << m, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const size_t tile_bytes = (size_t)16 << m;
+  const uint32_t nbstride = tile_n >= 64u ? (tile_n >> 6) : 1u;
+  unsigned char* p = smem_raw + (size_t)nbuf * tile_bytes;
+  uint64_t* sprog = reinterpret_cast<uint64_t*>(p);       p += 8 * (size_t)((stage_words + 1u) & ~1u);
+  uint64_t* hoff = reinterpret_cast<uint64_t*>(p);        p += ((size_t)(8u << (m - L)) + 15u) & ~(size_t)15u;
+  uint4* lane_tab = reinterpret_cast<uint4*>(p);          p += (size_t)1024 * sc.n_rounds;
+  uint32_t* batch_tab = reinterpret_cast<uint32_t*>(p);   p += (((size_t)4 * nbstride * sc.n_rounds) + 15u) & ~(size_t)15u;
+  uint64_t* full = reinterpret_cast<uint64_t*>(p);
+  uint64_t* done = full + nbuf;
 
-  for (uint32_t i = tid; i < stage_words; i += TILE_THREADS) sprog[i] = stage_g[i];
-  for (uint32_t i = tid; i < (1u << (m - L)); i += TILE_THREADS) hoff[i] = hi_offset(stage_g, sc, i);
+  for (uint32_t i = tid; i < stage_words; i += NTHREADS) sprog[i] = stage_g[i];
+  for (uint32_t i = tid; i < (1u << (m - L)); i += NTHREADS) hoff[i] = hi_offset(stage_g, sc, i);
+  if (tid == 0)
+    for (uint32_t b = 0; b < nbuf; ++b) { mbar_init(full + b, MOVER_THREADS); mbar_init(done + b, WPG); }
+  __syncthreads();
+  for (uint32_t idx = tid; idx < sc.n_rounds * 32u; idx += NTHREADS) {
+    const uint32_t r = idx >> 5;
+    if (round_kind(sprog, r) != 1u) continue;
+    DmmaCtx c;
+    decode_dmma(sprog, r, c);
+    uint32_t e[8];
+    dmma_lane_entry(c, idx & 31u, e);
+    lane_tab[2u * idx] = make_uint4(e[0], e[1], e[2], e[3]);
+    lane_tab[2u * idx + 1u] = make_uint4(e[4], e[5], e[6], e[7]);
+  }
+  for (uint32_t idx = tid; idx < sc.n_rounds * nbstride; idx += NTHREADS) {
+    const uint32_t r = idx / nbstride, b = idx - r * nbstride;
+    if (round_kind(sprog, r) != 1u) continue;
+    DmmaCtx c;
+    decode_dmma(sprog, r, c);
+    if (b < (1u << (c.n_grp - 3u))) batch_tab[idx] = dmma_batch_entry(c, b, m);
+  }
   __syncthreads();
 
+  const uint32_t T = (uint32_t)((n_active - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
   const uint32_t lowmask = (1u << L) - 1u;
-  for (uint64_t a = blockIdx.x; a < n_active; a += gridDim.x) {
-    const uint64_t t = active_to_tile(sc, a);
-    const uint64_t ext_hi = sc.ext_hi_base | t;
-    double2* gbase = state + tile_base(sprog, sc, t);
 
-    // ---- load: coalesced 16-byte async copies global -> swizzled shared tile
-    for (uint32_t i = tid; i < tile_n; i += TILE_THREADS)
-      cp_async16(&tile[swz(i)], gbase + hoff[i >> L] + (i & lowmask));
-    cp_async_commit_wait_all();
-    __syncthreads();
-
-    // ---- rounds
-    for (uint32_t r = 0; r < sc.n_rounds; ++r) {
-      if (MMA_ONLY || round_kind(sprog, r) == 1u) {
-        dmma_round_device(tile, sprog, stage_g, r, ext_hi, m, tid);
-      } else if (!MMA_ONLY) {
-        RoundCtx rc;
-        decode_round(sprog, r, rc);
-        switch (rc.r) {
-          case 0: run_round_thread<0>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
-          case 1: run_round_thread<1>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
-          case 2: run_round_thread<2>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
-          default: run_round_thread<3>(tile, rc, m, ext_hi, tid, TILE_THREADS, dev_vals); break;
+  if (warp >= NCW) {
+    // ---------------- mover warps
+    const uint32_t mt = tid - NCT;
+    PF_DECL;
+    for (uint32_t j = 0; j < T + nbuf - 1u; ++j) {
+      if (j < T) {
+        const uint64_t t = active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
+        const double2* gbase = state + tile_base(sprog, sc, t);
+        double2* buf = reinterpret_cast<double2*>(smem_raw + (size_t)(j % nbuf) * tile_bytes);
+        for (uint32_t i = mt; i < tile_n; i += MOVER_THREADS)
+          cp_async16(&buf[swz(i)], gbase + hoff[i >> L] + (i & lowmask));
+        cp_async_mbar_arrive(full + (j % nbuf));
+        PF_ADD(PF_M_LOAD);
+      }
+      if (j + 1u >= nbuf) {
+        const uint32_t s = j + 1u - nbuf;                      // tile to write back (s < T by the loop bound)
+        mbar_wait<true>(done + (s % nbuf), (s / nbuf) & 1u);
+        PF_ADD(PF_M_WAIT_DONE);
+        const uint64_t t = active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x);
+        double2* gbase = state + tile_base(sprog, sc, t);
+        const double2* buf = reinterpret_cast<const double2*>(smem_raw + (size_t)(s % nbuf) * tile_bytes);
+        for (uint32_t i0 = mt; i0 < tile_n; i0 += MOVER_THREADS * 8u) {
+          double2 v[8];
+#pragma unroll
+          for (uint32_t u = 0; u < 8; ++u) {
+            const uint32_t i = i0 + u * MOVER_THREADS;
+            if (i < tile_n) v[u] = buf[swz(i)];
+          }
+#pragma unroll
+          for (uint32_t u = 0; u < 8; ++u) {
+            const uint32_t i = i0 + u * MOVER_THREADS;
+            if (i < tile_n) __stcs(gbase + hoff[i >> L] + (i & lowmask), v[u]);
+          }
+        }
+        PF_ADD(PF_M_STORE);
+      }
+    }
+    PF_TOTAL(PF_M_TOTAL);
+  } else {
+    // ---------------- consumer groups
+    const uint32_t grp = warp / WPG, gwarp = warp - grp * WPG, gtid = tid - grp * GT;
+    const uint32_t smem_s = smem_u32(smem_raw);
+    double A[8];
+    uint32_t cur = 0xffffffffu;
+    // prefetch the first matrix variant this warp needs in (tile j, round r) while earlier work is still in flight
+    auto prefetch = [&](uint32_t j, uint32_t r) {
+      const uint64_t* w = sprog + T_STAGE_WORDS + (uint64_t)r * T_ROUND_WORDS;
+      uint32_t per, b0;
+      bool active;
+      dmma_geometry<WPG>(w, gwarp, per, b0, active);
+      if (!active) return;
+      const uint64_t ext_hi = sc.ext_hi_base | active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
+      cur = dmma_var_hi(w, ext_hi, m) | (batch_tab[r * nbstride + b0] >> 20);
+      dmma_load_A(A, reinterpret_cast<const double*>(stage_g + w[2]) + lane, cur);
+    };
+    if (grp < T && (MMA_ONLY || round_kind(sprog, 0) == 1u)) prefetch(grp, 0);
+    PF_DECL;
+    for (uint32_t j = grp; j < T; j += NG) {
+      const uint32_t b = j % nbuf;
+      const uint64_t ext_hi = sc.ext_hi_base | active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
+      mbar_wait(full + b, (j / nbuf) & 1u);
+      PF_ADD(PF_C_WAIT_FULL);
+      for (uint32_t r = 0; r < sc.n_rounds; ++r) {
+        if (r) named_bar_sync(1 + grp, GT);
+        PF_ADD(PF_C_BARRIER);
+        uint32_t nj = j, nr = r + 1u;
+        if (nr == sc.n_rounds) { nr = 0; nj = j + NG; }
+        const bool next_mma = nj < T && (MMA_ONLY || round_kind(sprog, nr) == 1u);
+        if (MMA_ONLY || round_kind(sprog, r) == 1u) {
+          double Ac[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) Ac[i] = A[i];
+          const uint32_t curc = cur;
+          if (next_mma) prefetch(nj, nr);
+          PF_ADD(PF_C_SETUP);
+          dmma_round_run<WPG>(smem_s + b * (uint32_t)tile_bytes, sprog + T_STAGE_WORDS + (uint64_t)r * T_ROUND_WORDS, stage_g,
+                              lane_tab + (size_t)r * 64u, batch_tab + r * nbstride, ext_hi, m, gwarp, lane, Ac, curc);
+          PF_ADD(PF_C_ROUND);
+        } else if (!MMA_ONLY) {
+          RoundCtx rc;
+          decode_round(sprog, r, rc);
+          double2* t2 = reinterpret_cast<double2*>(smem_raw + (size_t)b * tile_bytes);
+          switch (rc.r) {
+            case 0: run_round_thread<0>(t2, rc, m, ext_hi, gtid, GT, dev_vals); break;
+            case 1: run_round_thread<1>(t2, rc, m, ext_hi, gtid, GT, dev_vals); break;
+            case 2: run_round_thread<2>(t2, rc, m, ext_hi, gtid, GT, dev_vals); break;
+            default: run_round_thread<3>(t2, rc, m, ext_hi, gtid, GT, dev_vals); break;
+          }
+          if (next_mma) prefetch(nj, nr);
         }
       }
-      __syncthreads();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(done + b);
     }
-
-    // ---- store back in place
-    for (uint32_t i = tid; i < tile_n; i += TILE_THREADS)
-      gbase[hoff[i >> L] + (i & lowmask)] = tile[swz(i)];
-    __syncthreads();
+    PF_TOTAL(PF_C_TOTAL);
   }
+}
+
+template <int NG, int WPG>
+static cudaError_t launch_tile_stage_t(bool mma_only, unsigned grid, size_t smem, size_t limit, cudaStream_t stream, double2* state,
+                                       const uint64_t* stage_dev, uint32_t stage_words, const double* dev_vals, uint64_t n_active,
+                                       uint32_t nbuf) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const unsigned threads = (NG * WPG + MOVER_WARPS) * 32;
+  if (mma_only) k_tile_stage<NG, WPG, true><<<grid, threads, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active, nbuf);
+  else k_tile_stage<NG, WPG, false><<<grid, threads, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active, nbuf);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const uint64_t* stage_host, uint32_t stage_words,
@@ -181,21 +416,33 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   if ((sc.ext_hi_base & sc.skip_mask & ~tmask) != (sc.skip_val & ~tmask)) { if (out_active) *out_active = 0; return cudaSuccess; }
   const uint64_t n_active = (1ULL << nb) >> __builtin_popcountll(sc.skip_mask & tmask);
   if (out_active) *out_active = n_active;
-  const size_t smem = ((size_t)16 << sc.m) + 8 * (size_t)((stage_words + 1u) & ~1u) + 8 * ((size_t)1 << (sc.m - sc.L));
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_tile_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  int per_sm = 3;
-  while (per_sm > 1 && (smem + 1024) * per_sm > 227 * 1024) --per_sm;
-  uint64_t grid = (uint64_t)num_sms * per_sm;
+  const size_t tile_n = (size_t)1 << sc.m, nbstride = tile_n >= 64 ? (tile_n >> 6) : 1;
+  const size_t fixed = 8 * (size_t)((stage_words + 1u) & ~1u) + ((((size_t)8 << (sc.m - sc.L)) + 15) & ~(size_t)15) +
+                       (size_t)1024 * sc.n_rounds + ((4 * nbstride * sc.n_rounds + 15) & ~(size_t)15) + 16 * 8;   // + full[]/done[] mbarriers (nbuf <= 8)
+  const size_t limit = 227 * 1024;
+  uint64_t grid = (uint64_t)num_sms;
   if (grid > n_active) grid = n_active;
-  if (mma_only) k_tile_stage<true><<<(unsigned)grid, TILE_THREADS, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active);
-  else k_tile_stage<false><<<(unsigned)grid, TILE_THREADS, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active);
-  return cudaGetLastError();
+  const uint64_t tiles_per_cta = (n_active + grid - 1) / grid;
+  static const int max_buf = [] { const char* e = getenv("QCB_TILE_BUFFERS"); return e ? atoi(e) : 8; }();
+  uint32_t nbuf = (uint32_t)(max_buf < 1 ? 1 : (max_buf > 8 ? 8 : max_buf));
+  while (nbuf > 1 && (fixed + nbuf * (tile_n * 16) > limit || nbuf > tiles_per_cta + 1)) --nbuf;
+  const size_t smem = fixed + nbuf * (tile_n * 16);
+  if (smem > limit) return cudaErrorInvalidConfiguration;
+  // consumer layout: groups x warps-per-group (QCB_CONSUMERS = "2x4" default, "2x8", "1x16", "1x8")
+  static const int layout = [] {
+    const char* e = getenv("QCB_CONSUMERS");
+    if (!e) return 24;
+    return (e[0] - '0') * 10 + atoi(e + 2);
+  }();
+#define QCB_LAUNCH(NG, WPG) \
+  return launch_tile_stage_t<NG, WPG>(mma_only, (unsigned)grid, smem, limit, stream, state, stage_dev, stage_words, dev_vals, n_active, nbuf)
+  switch (layout) {
+    case 26: case 116: QCB_LAUNCH(1, 16);
+    case 18: QCB_LAUNCH(1, 8);
+    case 28: QCB_LAUNCH(2, 8);
+    default: QCB_LAUNCH(2, 4);
+  }
+#undef QCB_LAUNCH
 }
 
 // ------------------------------------------------------------------ state initialisation

@@ -720,6 +720,7 @@ int32_t qcb_destroy(qcb_handle h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) g_nccl.CommDestroy(h->comm);
+  tile_prof_dump();
   cudaFree(h->state); cudaFree(h->d_prog); cudaFree(h->d_vals); cudaFree(h->d_partials); cudaFree(h->d_scratch); cudaFree(h->xbuf);
   if (h->h_prog) cudaFreeHost(h->h_prog);
   if (h->h_pin) cudaFreeHost(h->h_pin);

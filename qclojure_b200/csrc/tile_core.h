@@ -363,6 +363,39 @@ QCB_HD uint32_t dmma_variant(const DmmaCtx& c, uint32_t base, uint64_t ext_hi, u
   return v;
 }
 
+// ---- precomputed tables of a tensor-core round (built once per launch, shared by every tile of the stage).
+// lane entry: 8 byte offsets inside the tile buffer: [0..4) loads (B register v), [4..8) stores (D register i); the
+// re/im component select is folded in as bit 3.  XOR with the batch's swizzled byte offset gives the address
+// (swz is linear over XOR and batch / lane / pattern bits are disjoint).
+QCB_HD void dmma_lane_entry(const DmmaCtx& c, uint32_t lane, uint32_t (&e)[8]) {
+  uint32_t Pl[4], Ps[4], cl, cs;
+  dmma_lane_setup(c, lane, Pl, Ps, cl, cs);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) e[v] = (Pl[v] << 4) | (cl << 3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) e[4 + i] = (Ps[i] << 4) | (cs << 3);
+}
+
+// batch entry: swizzled byte offset of the batch base (low 20 bits) | variant bits contributed by tile-local
+// condition bits (<< 20).  The remaining variant bits come from the tile id / rank (dmma_variant_hi).
+constexpr uint32_t DMMA_BATCH_OFF_MASK = 0xfffffu;
+QCB_HD uint32_t dmma_batch_entry(const DmmaCtx& c, uint32_t batch, uint32_t m) {
+  const uint32_t base = dmma_batch_base(c, batch);
+  uint32_t v = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j)
+    if (j < c.k && c.cond_pos[j] < m) v |= ((base >> c.cond_pos[j]) & 1u) << j;
+  return (swz(base) << 4) | (v << 20);
+}
+
+QCB_HD uint32_t dmma_variant_hi(const DmmaCtx& c, uint64_t ext_hi, uint32_t m) {
+  uint32_t v = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j)
+    if (j < c.k && c.cond_pos[j] >= m) v |= (uint32_t)((ext_hi >> (c.cond_pos[j] - m)) & 1ULL) << j;
+  return v;
+}
+
 // ---- tile addressing
 struct StageCtx {
   uint32_t n_local, m, L, n_rounds, n_runs;

@@ -7,6 +7,7 @@
 // oracle without a GPU.  It is built into tests/emu/libqcbemu.so by the tests themselves; nothing in
 // qclojure_b200/ or libqcb200.so links, loads or falls back to it.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -97,21 +98,23 @@ static void emu_dmma_round(double2* tile, const uint64_t* st, uint32_t r, uint64
   const uint32_t NW = nthreads / 32;
   const uint32_t nbatch = 1u << (c.n_grp - 3u);
   const uint32_t per = nbatch >= NW ? nbatch / NW : 1u;
-  double* td = reinterpret_cast<double*>(tile);
+  unsigned char* tb = reinterpret_cast<unsigned char*>(tile);
   const double* mats = reinterpret_cast<const double*>(st + c.mat_off);
+  // the kernel's per-launch tables (tile_core.h: dmma_lane_entry / dmma_batch_entry), byte-offset addressing
+  uint32_t lt[32][8];
+  for (uint32_t lane = 0; lane < 32; ++lane) dmma_lane_entry(c, lane, lt[lane]);
+  const uint32_t var_hi = dmma_variant_hi(c, ext_hi, m);
   for (uint32_t warp = 0; warp < NW; ++warp) {
     for (uint32_t b = 0; b < per; ++b) {
       const uint32_t bidx = warp * per + b;
       if (bidx >= nbatch) break;
-      const uint32_t base = dmma_batch_base(c, bidx);
-      const uint32_t X = swz(base), var = dmma_variant(c, base, ext_hi, m);
+      const uint32_t e = dmma_batch_entry(c, bidx, m);
+      const uint32_t X = e & DMMA_BATCH_OFF_MASK, var = var_hi | (e >> 20);
+      if (var != dmma_variant(c, dmma_batch_base(c, bidx), ext_hi, m)) std::abort();
       double A[32][8], B[32][4], D[32][4];
-      uint32_t Ps[32][4], cs[32];
       for (uint32_t lane = 0; lane < 32; ++lane) {
-        uint32_t Pl[4], cl;
-        dmma_lane_setup(c, lane, Pl, Ps[lane], cl, cs[lane]);
         for (int i = 0; i < 8; ++i) A[lane][i] = mats[((size_t)var * 8 + i) * 32 + lane];
-        for (int v = 0; v < 4; ++v) B[lane][v] = td[2u * (X ^ Pl[v]) + cl];
+        for (int v = 0; v < 4; ++v) std::memcpy(&B[lane][v], tb + (X ^ lt[lane][v]), 8);
       }
       double Am[16][16], Bm[16][8], Dm[16][8];
       for (uint32_t lane = 0; lane < 32; ++lane) {
@@ -122,7 +125,7 @@ static void emu_dmma_round(double2* tile, const uint64_t* st, uint32_t r, uint64
       for (uint32_t lane = 0; lane < 32; ++lane)
         for (int i = 0; i < 4; ++i) D[lane][i] = Dm[lane / 4 + 8 * (i >> 1)][2 * (lane % 4) + (i & 1)];
       for (uint32_t lane = 0; lane < 32; ++lane)
-        for (int i = 0; i < 4; ++i) td[2u * (X ^ Ps[lane][i]) + cs[lane]] = D[lane][i];
+        for (int i = 0; i < 4; ++i) std::memcpy(tb + (X ^ lt[lane][4 + i]), &D[lane][i], 8);
     }
   }
 }

@@ -131,7 +131,7 @@ class EmuPlan:
         return dict(kind=self.stage_kind(i), gates=int(lib().emu_stage_num_gates(self.h, i)),
                     rounds=int(lib().emu_stage_num_rounds(self.h, i)), fraction=float(lib().emu_stage_fraction(self.h, i)))
 
-    def max_conflict(self, i, nthreads=256):
+    def max_conflict(self, i, nthreads=512):
         return int(lib().emu_stage_max_conflict(self.h, i, nthreads))
 
     def algorithmic_bytes(self):
@@ -140,7 +140,7 @@ class EmuPlan:
     def unfused_bytes(self):
         return float(lib().emu_unfused_bytes(self.h))
 
-    def run_tile_stage(self, i, local_state, dev_vals, nthreads=256):
+    def run_tile_stage(self, i, local_state, dev_vals, nthreads=512):
         assert local_state.dtype == np.complex128 and local_state.flags.c_contiguous
         rc = lib().emu_run_tile_stage(self.h, i, local_state.ctypes.data, dev_vals.ctypes.data, nthreads)
         if rc != 0:
@@ -164,7 +164,7 @@ def exchange_halves(slices, gbit, lbit, n_local):
             slices[p][sel_p] = tmp
 
 
-def run_world(n, ops, state=None, *, world=1, nthreads=256, return_plans=False, **cfgkw):
+def run_world(n, ops, state=None, *, world=1, nthreads=512, return_plans=False, **cfgkw):
     """Emulate all ranks of a `world`-GPU run in one process; returns the full state in LOGICAL order."""
     p = world.bit_length() - 1
     n_local = n - p
