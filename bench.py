@@ -102,7 +102,7 @@ def cpu_leg(n: int, depth: int, budget_s: float = 20.0):
     from qclojure_b200 import circuits as C
     import psutil
     avail = psutil.virtual_memory().available
-    n_cpu = n
+    n_cpu = min(n, 30)      # bounded sample: 16 GiB of host state at most (first touch of a larger one alone takes minutes)
     while (16 << n_cpu) * 1.25 > avail and n_cpu > 20:
         n_cpu -= 1
     circ = C.random_brickwork_circuit(n_cpu, depth)
@@ -192,7 +192,7 @@ def run_ours(args):
 
     sv = L.StateVector(n, device=local_rank, rank=rank, world_size=world, nccl_id=nccl_id,
                        fusion=args.fusion, max_stage_cost=args.stage_cost, max_stage_rounds=args.stage_rounds,
-                       tile_bits=args.tile_bits, low_bits=args.low_bits, dense_mma=args.dense_mma)
+                       tile_bits=args.tile_bits, low_bits=args.low_bits, dense_mma=args.dense_mma, tile_mover=args.tile_mover)
 
     def step():
         sv.set_zero()
@@ -258,6 +258,11 @@ def run_ours(args):
                     traffic = json.load(f).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        tile_s = (stats["gpu_ms"] - stats["exchange_ms"]) / 1000.0
+        # second roofline of the fused kernel: every tensor-core round is a dense 16x16 real block per 8 amplitudes
+        # = 32 fp64 MAC per amplitude; peak = DMMA rate measured by scripts/dmma_bench2 (profiles/r1c_dmma_microbench.log)
+        dmma_flops = 64.0 * stats["n_rounds"] * float(1 << args.qubits)
+        dmma_peak = 37.0
         line = {
             "metric": "gates_per_sec", "value": n_gates * args.steps / (gpu_ms / 1000.0), "unit": "gates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": gpu_ms / args.steps,
@@ -271,7 +276,11 @@ def run_ours(args):
             "gates_per_sweep": n_gates / sweeps,
             "roofline": {"bound": "hbm", "kernel": "k_tile_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes / sweeps, "avg_launch_ms": (stats["gpu_ms"] - stats["exchange_ms"]) / sweeps},
+                         "algorithmic_bytes_per_launch": alg_bytes / sweeps, "avg_launch_ms": (stats["gpu_ms"] - stats["exchange_ms"]) / sweeps,
+                         "fp64_tensor": {"achieved": dmma_flops / tile_s / 1e12 if tile_s > 0 else 0.0, "peak": dmma_peak, "unit": "TFLOP/s",
+                                         "frac": dmma_flops / tile_s / 1e12 / dmma_peak if tile_s > 0 else 0.0,
+                                         "peak_source": "mma.m16n8k16.f64 microbenchmark on this pool (profiles/r1c_dmma_microbench.log)",
+                                         "flops_per_launch": dmma_flops / sweeps}},
             "exchange": {"count": stats["n_exchanges"], "bytes_sent_per_rank": stats["bytes_exchanged"], "ms": stats["exchange_ms"],
                          "gbs_per_direction": (stats["bytes_exchanged"] / (stats["exchange_ms"] / 1000.0) / 1e9) if stats["exchange_ms"] > 0 else None,
                          "frac_of_900": (stats["bytes_exchanged"] / (stats["exchange_ms"] / 1000.0) / 1e9 / 900.0) if stats["exchange_ms"] > 0 else None},
@@ -303,6 +312,7 @@ def main():
     ap.add_argument("--stage-cost", type=int, default=0)
     ap.add_argument("--stage-rounds", type=int, default=0)
     ap.add_argument("--dense-mma", type=int, default=0, help="0/1 = tensor-core rounds (default), 2 = interpreter only")
+    ap.add_argument("--tile-mover", type=int, default=0, help="0/1 = cp.async mover (default), 2 = TMA tensor-copy mover")
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--low-bits", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")

@@ -60,7 +60,10 @@ typedef struct qcb_config {
   int32_t max_stage_rounds;/* 0 = default; scheduler knob: shared-memory rounds one fused sweep may hold */
   int32_t dense_mma;       /* 0 = default (on); 1 = on: rounds run as dense 8x8 complex blocks on the fp64 tensor
                               cores (DMMA); 2 = off: register-resident op interpreter only                 */
-  int32_t reserved[5];
+  int32_t tile_mover;      /* 0 = default; 1 = tiles move between HBM and shared memory with cp.async / st.global
+                              (16 bytes per thread, arbitrary swizzle: conflict-free rounds); 2 = TMA tensor copies,
+                              one per contiguous run, with the hardware 128-byte swizzle                            */
+  int32_t reserved[4];
 } qcb_config;
 
 /* ---- gate vocabulary: every branch of apply-gate-to-state (domain/circuit.clj:964-1071) ---- */

@@ -147,17 +147,20 @@ class StateVector:
 
     def __init__(self, n_qubits: int, *, device: int = -1, fusion: int = 1, strict_parity: int = 1, tile_bits: int = 0,
                  low_bits: int = 0, rank: int = 0, world_size: int = 1, nccl_id: Optional[bytes] = None, max_stage_cost: int = 0,
-                 max_stage_rounds: int = 0, dense_mma: int = 0):
+                 max_stage_rounds: int = 0, dense_mma: int = 0, tile_mover: int = 0):
         self._lib = load()
         if dense_mma == 0 and os.environ.get("QCB_DENSE_MMA"):
             dense_mma = int(os.environ["QCB_DENSE_MMA"])     # 1 = tensor-core rounds (default), 2 = interpreter only
+        if tile_mover == 0 and os.environ.get("QCB_TILE_MOVER"):
+            tile_mover = int(os.environ["QCB_TILE_MOVER"])   # 1 = cp.async mover (default), 2 = TMA mover
         self.n = int(n_qubits)
         self.rank, self.world_size = rank, world_size
         self._idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
         cfg = OPS.make_config(self.n, device=device, fusion=fusion, strict_parity=strict_parity, tile_bits=tile_bits,
                               low_bits=low_bits, rank=rank, world_size=world_size,
                               nccl_unique_id=C.cast(self._idbuf, C.c_void_p) if self._idbuf is not None else None,
-                              max_stage_cost=max_stage_cost, max_stage_rounds=max_stage_rounds, dense_mma=dense_mma)
+                              max_stage_cost=max_stage_cost, max_stage_rounds=max_stage_rounds, dense_mma=dense_mma,
+                              tile_mover=tile_mover)
         h = C.c_void_p()
         rc = self._lib.qcb_create(C.byref(cfg), C.byref(h))
         if rc != QCB_OK:

@@ -10,6 +10,7 @@
 //                      two-pass finalisation (no floating-point atomics).
 //  sampling            chunk sums -> scan of chunk sums -> per-shot binary search + in-chunk scan;
 //                      implements the reference's measure-state rule (domain/state.clj:894-913).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -24,6 +25,14 @@ namespace qcb {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_addr, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -84,6 +93,65 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ------------------------------------------------------------------ TMA (cp.async.bulk.tensor) primitives
+// The state is described to the TMA unit as a 2-D tensor of doubles [rows = 2^(n_local-3)][16] (one row = 8 amplitudes =
+// 128 bytes) with the 128-byte swizzle; a box is one contiguous run of 2^c amplitudes = 2^(c-3) rows.
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_rows(uint32_t dst_s, const CUtensorMap* map, int32_t row, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+               ::"r"(dst_s), "l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(row), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_rows(const CUtensorMap* map, int32_t row, uint32_t src_s) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(row), "r"(src_s) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// make this thread's generic-proxy writes to shared memory visible to the async proxy (TMA store reads them)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// ------------------------------------------------------------------ optional cycle accounting (make PROFILE=1)
+#ifdef QCB_TILE_PROFILE
+// ablation switches of the profiling build (QCB_TILE_DBG): 1 = skip the DMMAs, 2 = skip the fragment LDS/STS,
+// 4 = skip the HBM traffic of the mover (results are then wrong on purpose: timing experiments only)
+__device__ int g_tile_dbg;
+#ifdef QCB_TILE_ABLATE
+__device__ __forceinline__ int tile_dbg() { int v; asm volatile("ld.global.cv.s32 %0, [%1];" : "=r"(v) : "l"(&g_tile_dbg)); return v; }
+#define DBG_DECL const int dbg_bits = tile_dbg()
+#define DBG_ON(bit) (dbg_bits & (bit))
+#else
+#define DBG_DECL const int dbg_bits = 0; (void)dbg_bits
+#define DBG_ON(bit) false
+#endif
+enum { PF_C_WAIT_FULL = 0, PF_C_BARRIER, PF_C_SETUP, PF_C_ROUND, PF_C_TOTAL, PF_M_LOAD, PF_M_WAIT_DONE, PF_M_STORE, PF_M_TOTAL, PF_N };
+__device__ unsigned long long g_tile_prof[PF_N];
+// per-warp accumulation in registers, one atomic per category at the end of the kernel
+#define PF_DECL long long pf_t = clock64(), pf_t0 = pf_t; unsigned long long pf_acc[PF_N] = {}
+#define PF_ADD(cat) do { const long long pf_n = clock64(); pf_acc[cat] += (unsigned long long)(pf_n - pf_t); pf_t = pf_n; } while (0)
+#define PF_TOTAL(cat) do { pf_acc[cat] = (unsigned long long)(clock64() - pf_t0); if ((threadIdx.x & 31) == 0) { for (int pf_i = 0; pf_i < PF_N; ++pf_i) if (pf_acc[pf_i]) atomicAdd(&g_tile_prof[pf_i], pf_acc[pf_i]); } } while (0)
+void tile_prof_dump() {
+  unsigned long long h[PF_N];
+  if (cudaMemcpyFromSymbol(h, g_tile_prof, sizeof h) != cudaSuccess) return;
+  static const char* names[PF_N] = {"consumer wait full", "consumer round barrier", "consumer setup+prefetch", "consumer round work", "consumer total",
+                                    "mover load issue", "mover wait done", "mover store", "mover total"};
+  for (int i = 0; i < PF_N; ++i) {
+    const unsigned long long tot = h[i < PF_M_LOAD ? PF_C_TOTAL : PF_M_TOTAL];
+    fprintf(stderr, "[tile-prof] %-26s %14llu warp-cycles  %5.1f%%\n", names[i], h[i], tot ? 100.0 * (double)h[i] / (double)tot : 0.0);
+  }
+  unsigned long long z[PF_N] = {};
+  cudaMemcpyToSymbol(g_tile_prof, z, sizeof z);
+}
+#else
+#define DBG_DECL const int dbg_bits = 0; (void)dbg_bits
+#define DBG_ON(bit) false
+#define PF_DECL
+#define PF_ADD(cat)
+#define PF_TOTAL(cat)
+void tile_prof_dump() {}
+#endif
+
 // ------------------------------------------------------------------ tensor-core round
 // One warp applies the round's dense 16x16 real matrix to 8 groups at a time:
 //   D(16x8) = A(16x16) * B(16x8),  A = matrix variant (fragments from global through L1, reloaded only when the
@@ -98,6 +166,18 @@ __device__ __forceinline__ void dmma_m16n8k16(double (&d)[4], const double (&a)[
       : "=d"(d[0]), "=d"(d[1]), "=d"(d[2]), "=d"(d[3])
       : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
         "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]), "d"(0.0), "d"(0.0), "d"(0.0), "d"(0.0));
+}
+
+// One k-step of the 16x8x16 product as the native 8x8x4 operation (the m16n8k16 fragments ARE the m8n8k4 fragments:
+// A reg i = m-half (i & 1), k-step (i >> 1); B reg v = k-step v; D regs {0,1} / {2,3} = m-half 0 / 1).  Issuing the eight
+// steps as separate instructions lets the round interleave its shared-memory traffic between them (dmma_round_run).
+__device__ __forceinline__ void dmma_884_first(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
+               : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+__device__ __forceinline__ void dmma_884_acc(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
 // Per-round tables live in shared memory (built once per launch): lane_tab[r][lane] = 8 byte offsets
@@ -115,80 +195,93 @@ __device__ __forceinline__ void dmma_load_A(double (&A)[8], const double* __rest
   for (int i = 0; i < 8; ++i) A[i] = __ldg(mats + ((size_t)var * 8 + i) * 32);
 }
 
-// What a warp needs to know about its share of a tensor-core round before the round barrier opens: the first
-// matrix variant (prefetched into registers while the previous round is still running).
-struct DmmaNext {
-  uint32_t var;
-  bool active;
-};
-
-template <int WPG>
-__device__ __forceinline__ void dmma_geometry(const uint64_t* w, uint32_t gwarp, uint32_t& per, uint32_t& b0, bool& active) {
-  const uint32_t nbatch = 1u << ((uint32_t)w[18] - 3u);
-  per = nbatch >= (uint32_t)WPG ? nbatch / WPG : 1u;
-  b0 = gwarp * per;
-  active = b0 < nbatch;                                         // warp-uniform
-}
-
-__device__ __forceinline__ uint32_t dmma_var_hi(const uint64_t* w, uint64_t ext_hi, uint32_t m) {
-  const uint32_t k = (uint32_t)w[29];
-  uint32_t var_hi = 0;
+// Variant bits contributed by the tile-id / rank condition bits of a round.  hi_desc packs, for each of the (at most 4)
+// condition bits, a 6-bit field: the bit's position above the tile bits, or 63 when the bit is tile-local / unused.
+__device__ __forceinline__ uint32_t dmma_var_hi(uint32_t hi_desc, uint64_t ext_hi) {
+  uint32_t v = 0;
 #pragma unroll
   for (uint32_t j = 0; j < 4; ++j) {
-    const uint32_t p = (uint32_t)w[30 + j];
-    if (j < k && p >= m) var_hi |= (uint32_t)((ext_hi >> (p - m)) & 1ULL) << j;
+    const uint32_t f = (hi_desc >> (6u * j)) & 63u;
+    if (f != 63u) v |= (uint32_t)((ext_hi >> f) & 1ULL) << j;
   }
-  return var_hi;
+  return v;
 }
 
-// One warp's share of a tensor-core round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
-// Fast path (every batch of the warp uses the same variant): software pipeline  LDS(i+1) | DMMA(i) | STS(i-1), so the
-// warp's stream of tensor instructions is not interrupted by shared-memory latency.
-template <int WPG>
-__device__ __forceinline__ void dmma_round_run(uint32_t tile_s, const uint64_t* w, const uint64_t* __restrict__ stage_g,
-                                               const uint4* lane_tab_r, const uint32_t* btab, uint64_t ext_hi, uint32_t m,
-                                               uint32_t gwarp, uint32_t lane, double (&A)[8], uint32_t cur) {
-  uint32_t per, b0;
-  bool active;
-  dmma_geometry<WPG>(w, gwarp, per, b0, active);
-  if (!active) return;
-  const uint32_t var_hi = dmma_var_hi(w, ext_hi, m);
+// One warp's share of a tensor-core round on the tile at shared address `tile_s`: batches btab[0..per).  A holds variant
+// `cur` on entry.  Fast path (every batch of the warp uses the same variant): software pipeline
+// LDS(i+1) | DMMA(i) | STS(i-1), so the warp's stream of tensor instructions is not interrupted by shared-memory latency.
+__device__ __forceinline__ void dmma_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
+                                               uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[8],
+                                               uint32_t cur, int dbg_bits) {
+  (void)dbg_bits;
   const uint4 l0 = lane_tab_r[2u * lane], l1 = lane_tab_r[2u * lane + 1u];
   const uint32_t pl[4] = {l0.x, l0.y, l0.z, l0.w};
   const uint32_t ps[4] = {l1.x, l1.y, l1.z, l1.w};
-  btab += b0;
   auto load_B = [&](uint32_t X, double (&B)[4]) {
+    if (DBG_ON(2)) { for (int v = 0; v < 4; ++v) B[v] = (double)(X + v); return; }
 #pragma unroll
     for (int v = 0; v < 4; ++v) B[v] = lds_f64(tile_s + (pl[v] ^ X));
   };
   auto store_D = [&](uint32_t X, const double (&D)[4]) {
+    if (DBG_ON(2)) { if (D[0] + D[1] + D[2] + D[3] == 1.2345) sts_f64(tile_s, D[0]); return; }
 #pragma unroll
     for (int i = 0; i < 4; ++i) sts_f64(tile_s + (ps[i] ^ X), D[i]);
   };
   const uint32_t e_first = btab[0], e_last = btab[per - 1u];
   if ((e_first >> 20) == (e_last >> 20)) {
     // local condition bits are the top bits of the batch index: equal at both ends => equal throughout
+    // Each 8x8x4 step occupies the tensor pipe of the SM partition for 16 cycles and a warp issues in order: the loads of
+    // batch i+1 and the stores of batch i-1 are slotted between the steps of batch i, so the pipe never waits for a warp
+    // that is busy with its shared-memory traffic (two warps interleaving their steps otherwise finish - and idle - together).
     double Bc[4], Dp[4];
     uint32_t X = e_first & DMMA_BATCH_OFF_MASK, Xp = X;
     load_B(X, Bc);
-#pragma unroll 2
-    for (uint32_t i = 0; i < per; ++i) {
+    auto step = [&](uint32_t i, bool more) {
       double Bn[4], D[4];
-      uint32_t Xn = X;
-      if (i + 1u < per) {
-        Xn = btab[i + 1u] & DMMA_BATCH_OFF_MASK;
-        load_B(Xn, Bn);
+      const uint32_t Xn = more ? (btab[i + 1u] & DMMA_BATCH_OFF_MASK) : X;
+      if (DBG_ON(1)) {
+        for (int q = 0; q < 4; ++q) D[q] = Bc[q];
+        if (more) load_B(Xn, Bn);
+        if (i) store_D(Xp, Dp);
+      } else {
+        dmma_884_first(D[0], D[1], A[0], Bc[0]);
+        if (more) Bn[0] = lds_f64(tile_s + (pl[0] ^ Xn));
+        dmma_884_first(D[2], D[3], A[1], Bc[0]);
+        if (more) Bn[1] = lds_f64(tile_s + (pl[1] ^ Xn));
+        dmma_884_acc(D[0], D[1], A[2], Bc[1]);
+        if (more) Bn[2] = lds_f64(tile_s + (pl[2] ^ Xn));
+        dmma_884_acc(D[2], D[3], A[3], Bc[1]);
+        if (more) Bn[3] = lds_f64(tile_s + (pl[3] ^ Xn));
+        dmma_884_acc(D[0], D[1], A[4], Bc[2]);
+        if (i) sts_f64(tile_s + (ps[0] ^ Xp), Dp[0]);
+        dmma_884_acc(D[2], D[3], A[5], Bc[2]);
+        if (i) sts_f64(tile_s + (ps[1] ^ Xp), Dp[1]);
+        dmma_884_acc(D[0], D[1], A[6], Bc[3]);
+        if (i) sts_f64(tile_s + (ps[2] ^ Xp), Dp[2]);
+        dmma_884_acc(D[2], D[3], A[7], Bc[3]);
+        if (i) sts_f64(tile_s + (ps[3] ^ Xp), Dp[3]);
       }
-      dmma_m16n8k16(D, A, Bc);
-      if (i) store_D(Xp, Dp);
 #pragma unroll
       for (int q = 0; q < 4; ++q) { Dp[q] = D[q]; Bc[q] = Bn[q]; }
       Xp = X; X = Xn;
+    };
+    // Each 8x8x4 step occupies the tensor pipe of the SM partition for 16 cycles and a warp issues in order: the loads of
+    // batch i+1 and the stores of batch i-1 are slotted between the steps of batch i, so the pipe never waits for a warp
+    // that is busy with its shared-memory traffic (two warps interleaving their steps otherwise finish - and idle - together).
+    // The common trip counts are unrolled completely (no register rotation moves).
+    if (per == 16u) {
+#pragma unroll
+      for (uint32_t i = 0; i < 16; ++i) step(i, i + 1u < 16u);
+    } else if (per == 8u) {
+#pragma unroll
+      for (uint32_t i = 0; i < 8; ++i) step(i, i + 1u < 8u);
+    } else {
+#pragma unroll 2
+      for (uint32_t i = 0; i < per; ++i) step(i, i + 1u < per);
     }
     store_D(Xp, Dp);
     return;
   }
-  const double* __restrict__ mats = reinterpret_cast<const double*>(stage_g + w[2]) + lane;
   for (uint32_t bi = 0; bi < per; ++bi) {
     const uint32_t e = btab[bi];
     const uint32_t v = var_hi | (e >> 20), X = e & DMMA_BATCH_OFF_MASK;
@@ -200,42 +293,70 @@ __device__ __forceinline__ void dmma_round_run(uint32_t tile_s, const uint64_t* 
   }
 }
 
-// ------------------------------------------------------------------ optional cycle accounting (make PROFILE=1)
-#ifdef QCB_TILE_PROFILE
-enum { PF_C_WAIT_FULL = 0, PF_C_BARRIER, PF_C_SETUP, PF_C_ROUND, PF_C_TOTAL, PF_M_LOAD, PF_M_WAIT_DONE, PF_M_STORE, PF_M_TOTAL, PF_N };
-__device__ unsigned long long g_tile_prof[PF_N];
-#define PF_DECL long long pf_t = clock64(), pf_t0 = pf_t
-#define PF_ADD(cat) do { const long long pf_n = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_tile_prof[cat], (unsigned long long)(pf_n - pf_t)); pf_t = pf_n; } while (0)
-#define PF_TOTAL(cat) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_tile_prof[cat], (unsigned long long)(clock64() - pf_t0)); } while (0)
-void tile_prof_dump() {
-  unsigned long long h[PF_N];
-  if (cudaMemcpyFromSymbol(h, g_tile_prof, sizeof h) != cudaSuccess) return;
-  static const char* names[PF_N] = {"consumer wait full", "consumer round barrier", "consumer setup+prefetch", "consumer round work", "consumer total",
-                                    "mover load issue", "mover wait done", "mover store", "mover total"};
-  for (int i = 0; i < PF_N; ++i) {
-    const unsigned long long tot = h[i < PF_M_LOAD ? PF_C_TOTAL : PF_M_TOTAL];
-    fprintf(stderr, "[tile-prof] %-26s %14llu warp-cycles  %5.1f%%\n", names[i], h[i], tot ? 100.0 * (double)h[i] / (double)tot : 0.0);
+// ------------------------------------------------------------------ LSU mover, specialised
+// Tiles of 128 * KE amplitudes with 256-byte runs and the default layout (the common case): mover thread mt moves
+// elements mt + 128 k (k < KE); their global run offsets stay in registers for the whole sweep and the swizzled
+// shared-memory offsets are XORs with compile-time constants (swz is linear), so one element costs an address add and
+// one LDGSTS / LDS + STG.
+template <int KE>
+__device__ __forceinline__ void mover_fast(double2* __restrict__ state, const uint64_t* sprog, const StageCtx& sc, const uint64_t* hoff,
+                                           uint32_t smem_s, uint32_t tile_bytes, uint32_t mt, uint32_t T, uint32_t nbuf,
+                                           uint64_t* full, uint64_t* done) {
+  const uint32_t low = mt & 15u;
+  const uint32_t s_mt = swz(mt, 0u) << 4;
+  DBG_DECL;
+  uint32_t roff[KE];                                           // run offsets in units of 256 bytes
+#pragma unroll
+  for (uint32_t k = 0; k < KE; ++k) roff[k] = (uint32_t)(hoff[(mt >> 4) + 8u * k] >> 4);
+  PF_DECL;
+  for (uint32_t j = 0; j < T + nbuf - 1u; ++j) {
+    if (j < T) {
+      const uint64_t t = active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
+      const char* gb = reinterpret_cast<const char*>(state + tile_base(sprog, sc, t) + low);
+      const uint32_t bs = smem_s + (j % nbuf) * tile_bytes;
+      if (!DBG_ON(4)) {
+#pragma unroll
+        for (uint32_t k = 0; k < KE; ++k)
+          cp_async16_s(bs + (s_mt ^ (swz(128u * k, 0u) << 4)), gb + ((uint64_t)roff[k] << 8));
+      }
+      cp_async_mbar_arrive(full + (j % nbuf));
+      PF_ADD(PF_M_LOAD);
+    }
+    if (j + 1u >= nbuf) {
+      const uint32_t s = j + 1u - nbuf;                        // tile to write back (s < T by the loop bound)
+      mbar_wait<true>(done + (s % nbuf), (s / nbuf) & 1u);
+      PF_ADD(PF_M_WAIT_DONE);
+      const uint64_t t = active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x);
+      char* gb = reinterpret_cast<char*>(state + tile_base(sprog, sc, t) + low);
+      const uint32_t bs = smem_s + (s % nbuf) * tile_bytes;
+#pragma unroll
+      for (uint32_t k0 = 0; k0 < (DBG_ON(4) ? 0u : (uint32_t)KE); k0 += 8) {
+        double2 v[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8; ++u) v[u] = lds_f64x2(bs + (s_mt ^ (swz(128u * (k0 + u), 0u) << 4)));
+#pragma unroll
+        for (uint32_t u = 0; u < 8; ++u) __stcs(reinterpret_cast<double2*>(gb + ((uint64_t)roff[k0 + u] << 8)), v[u]);
+      }
+      PF_ADD(PF_M_STORE);
+    }
   }
-  unsigned long long z[PF_N] = {};
-  cudaMemcpyToSymbol(g_tile_prof, z, sizeof z);
+  PF_TOTAL(PF_M_TOTAL);
 }
-#else
-#define PF_DECL
-#define PF_ADD(cat)
-#define PF_TOTAL(cat)
-void tile_prof_dump() {}
-#endif
 
 // ------------------------------------------------------------------ the fused gate executor
 // One persistent CTA per SM, warp-specialised over a ring of `nbuf` tile buffers in shared memory:
-//   mover warps      stream tile j into buffer j % nbuf with cp.async (completion signalled on full[]), then write
-//                    tile j-(nbuf-1) back to HBM once its consumer group has signalled done[];
+//   mover            streams tile j into buffer j % nbuf (completion signalled on full[]), then writes tile j-(nbuf-1)
+//                    back to HBM once its consumer group has signalled done[].  TMA mode (the normal case): ONE warp
+//                    issues a cp.async.bulk.tensor copy per contiguous run of the tile, the TMA unit swizzles on the
+//                    fly and the LSU pipe stays free for the consumers.  Fallback (tiles smaller than a 128-byte row
+//                    or no tensor map): four warps move 16 bytes per thread with cp.async / st.global;
 //   consumer groups  NG groups of WPG warps; group g runs the stage's rounds on tiles j = g, g+NG, ... in shared
 //                    memory (tensor-core rounds or interpreter rounds), rounds separated by the group's own named
 //                    barrier.  Two groups on different tiles keep the fp64 tensor pipe fed while the other group
 //                    sits at a round barrier or waits for operands.
-// HBM traffic of the tiles ahead (loads) and behind (stores) overlaps the arithmetic.  Each mover thread loads and
-// stores the same elements of a buffer, so buffer re-use needs no further barrier than its own program order.
+// HBM traffic of the tiles ahead (loads) and behind (stores) overlaps the arithmetic.  In the fallback each mover thread
+// loads and stores the same elements of a buffer, so buffer re-use needs no further barrier than its own program order;
+// in TMA mode the mover waits for its bulk stores to have read the buffer (wait_group.read) before reloading it.
 constexpr int MOVER_WARPS = 4;
 constexpr int MOVER_THREADS = MOVER_WARPS * 32;
 
@@ -244,14 +365,18 @@ constexpr int MOVER_THREADS = MOVER_WARPS * 32;
 template <int NG, int WPG, bool MMA_ONLY>
 __global__ void __launch_bounds__((NG * WPG + MOVER_WARPS) * 32, 1)
 k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, uint32_t stage_words,
-             const double* __restrict__ dev_vals, uint64_t n_active, uint32_t nbuf) {
+             const double* __restrict__ dev_vals, uint64_t n_active, uint32_t nbuf, const __grid_constant__ CUtensorMap tmap,
+             uint32_t use_tma) {
   // stage_words = descriptor part of the stage program (stage + round descriptors + interpreter op slots);
   // tensor-core matrices follow it in global memory and are read through the read-only path
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ unsigned char smem_dyn[];
+  // the hardware swizzle is a function of the shared-memory address: tile buffers start on a 1024-byte boundary
+  unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   constexpr uint32_t NCW = NG * WPG, NTHREADS = (NCW + MOVER_WARPS) * 32, NCT = NCW * 32, GT = WPG * 32;
   StageCtx sc;
   decode_stage(stage_g, sc);
-  const uint32_t m = sc.m, L = sc.L, tile_n = 1u << m, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const uint32_t m = sc.m, LC = sc.c, tile_n = 1u << m, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const uint32_t L = use_tma ? sc.c : sc.L;               // run bits: amplitudes moved per copy (TMA) / per hoff entry (LSU)
   const size_t tile_bytes = (size_t)16 << m;
   const uint32_t nbstride = tile_n >= 64u ? (tile_n >> 6) : 1u;
   unsigned char* p = smem_raw + (size_t)nbuf * tile_bytes;
@@ -259,13 +384,18 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
   uint64_t* hoff = reinterpret_cast<uint64_t*>(p);        p += ((size_t)(8u << (m - L)) + 15u) & ~(size_t)15u;
   uint4* lane_tab = reinterpret_cast<uint4*>(p);          p += (size_t)1024 * sc.n_rounds;
   uint32_t* batch_tab = reinterpret_cast<uint32_t*>(p);   p += (((size_t)4 * nbstride * sc.n_rounds) + 15u) & ~(size_t)15u;
+  uint32_t* run_dst = reinterpret_cast<uint32_t*>(p);     p += ((size_t)(4u << (m - L)) + 15u) & ~(size_t)15u;
+  uint2* rtab = reinterpret_cast<uint2*>(p);              p += ((size_t)8 * sc.n_rounds + 15u) & ~(size_t)15u;   // {hi_desc, matrix word offset}
   uint64_t* full = reinterpret_cast<uint64_t*>(p);
   uint64_t* done = full + nbuf;
 
   for (uint32_t i = tid; i < stage_words; i += NTHREADS) sprog[i] = stage_g[i];
-  for (uint32_t i = tid; i < (1u << (m - L)); i += NTHREADS) hoff[i] = hi_offset(stage_g, sc, i);
+  for (uint32_t i = tid; i < (1u << (m - L)); i += NTHREADS) {
+    hoff[i] = hi_offset_from(stage_g, sc, i, L);         // global offset (amplitudes) of run i inside a tile
+    run_dst[i] = (swz(i << L, LC) >> 3) << 7;            // byte offset of the first 128-byte row of run i in a tile buffer
+  }
   if (tid == 0)
-    for (uint32_t b = 0; b < nbuf; ++b) { mbar_init(full + b, MOVER_THREADS); mbar_init(done + b, WPG); }
+    for (uint32_t b = 0; b < nbuf; ++b) { mbar_init(full + b, use_tma ? 1u : MOVER_THREADS); mbar_init(done + b, WPG); }
   __syncthreads();
   for (uint32_t idx = tid; idx < sc.n_rounds * 32u; idx += NTHREADS) {
     const uint32_t r = idx >> 5;
@@ -276,6 +406,15 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
     dmma_lane_entry(c, idx & 31u, e);
     lane_tab[2u * idx] = make_uint4(e[0], e[1], e[2], e[3]);
     lane_tab[2u * idx + 1u] = make_uint4(e[4], e[5], e[6], e[7]);
+  }
+  for (uint32_t r = tid; r < sc.n_rounds; r += NTHREADS) {
+    const uint64_t* w = sprog + T_STAGE_WORDS + (uint64_t)r * T_ROUND_WORDS;
+    uint32_t hd = 0;
+    for (uint32_t j = 0; j < 4; ++j) {
+      const uint32_t pz = (uint32_t)w[30 + j];
+      hd |= ((j < (uint32_t)w[29] && pz >= m) ? (pz - m) : 63u) << (6u * j);
+    }
+    rtab[r] = make_uint2(hd, (uint32_t)w[2]);
   }
   for (uint32_t idx = tid; idx < sc.n_rounds * nbstride; idx += NTHREADS) {
     const uint32_t r = idx / nbstride, b = idx - r * nbstride;
@@ -289,8 +428,43 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
   const uint32_t T = (uint32_t)((n_active - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
   const uint32_t lowmask = (1u << L) - 1u;
 
-  if (warp >= NCW) {
-    // ---------------- mover warps
+  if (warp >= NCW && use_tma) {
+    // ---------------- mover (TMA): one warp, one bulk tensor copy per run
+    if (warp > NCW) return;
+    const uint32_t nruns = 1u << (m - L), smem_s = smem_u32(smem_raw);
+    PF_DECL;
+    for (uint32_t j = 0; j < T + nbuf - 1u; ++j) {
+      if (j < T) {
+        const uint32_t b = j % nbuf;
+        const uint64_t t = active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
+        const uint64_t gb = tile_base(sprog, sc, t);
+        if (lane == 0) mbar_arrive_expect_tx(full + b, (uint32_t)tile_bytes);
+        __syncwarp();
+        for (uint32_t h = lane; h < nruns; h += 32u)
+          tma_load_rows(smem_s + b * (uint32_t)tile_bytes + run_dst[h], &tmap, (int32_t)((gb + hoff[h]) >> 3), full + b);
+        PF_ADD(PF_M_LOAD);
+      }
+      if (j + 1u >= nbuf) {
+        const uint32_t s = j + 1u - nbuf, b = s % nbuf;        // tile to write back (s < T by the loop bound)
+        mbar_wait<true>(done + b, (s / nbuf) & 1u);
+        PF_ADD(PF_M_WAIT_DONE);
+        const uint64_t t = active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x);
+        const uint64_t gb = tile_base(sprog, sc, t);
+        for (uint32_t h = lane; h < nruns; h += 32u)
+          tma_store_rows(&tmap, (int32_t)((gb + hoff[h]) >> 3), smem_s + b * (uint32_t)tile_bytes + run_dst[h]);
+        tma_store_commit();
+        tma_store_wait_read();                                 // the buffer has been read: it may be reloaded
+        __syncwarp();
+        PF_ADD(PF_M_STORE);
+      }
+    }
+    PF_TOTAL(PF_M_TOTAL);
+  } else if (warp >= NCW && L == 4u && LC == 0u && (m == 12u || m == 11u)) {
+    // ---------------- mover warps, 64 KB / 32 KB tiles with 256-byte runs (the common case)
+    if (m == 12u) mover_fast<32>(state, sprog, sc, hoff, smem_u32(smem_raw), (uint32_t)tile_bytes, tid - NCT, T, nbuf, full, done);
+    else mover_fast<16>(state, sprog, sc, hoff, smem_u32(smem_raw), (uint32_t)tile_bytes, tid - NCT, T, nbuf, full, done);
+  } else if (warp >= NCW) {
+    // ---------------- mover warps (fallback: 16 bytes per thread through the LSU)
     const uint32_t mt = tid - NCT;
     PF_DECL;
     for (uint32_t j = 0; j < T + nbuf - 1u; ++j) {
@@ -299,7 +473,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
         const double2* gbase = state + tile_base(sprog, sc, t);
         double2* buf = reinterpret_cast<double2*>(smem_raw + (size_t)(j % nbuf) * tile_bytes);
         for (uint32_t i = mt; i < tile_n; i += MOVER_THREADS)
-          cp_async16(&buf[swz(i)], gbase + hoff[i >> L] + (i & lowmask));
+          cp_async16(&buf[swz(i, LC)], gbase + hoff[i >> L] + (i & lowmask));
         cp_async_mbar_arrive(full + (j % nbuf));
         PF_ADD(PF_M_LOAD);
       }
@@ -315,7 +489,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
 #pragma unroll
           for (uint32_t u = 0; u < 8; ++u) {
             const uint32_t i = i0 + u * MOVER_THREADS;
-            if (i < tile_n) v[u] = buf[swz(i)];
+            if (i < tile_n) v[u] = buf[swz(i, LC)];
           }
 #pragma unroll
           for (uint32_t u = 0; u < 8; ++u) {
@@ -331,24 +505,26 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
     // ---------------- consumer groups
     const uint32_t grp = warp / WPG, gwarp = warp - grp * WPG, gtid = tid - grp * GT;
     const uint32_t smem_s = smem_u32(smem_raw);
+    // every tensor-core round has m - 3 group bits: the batch geometry of this warp is a kernel constant
+    const uint32_t nbatch = tile_n >= 64u ? (tile_n >> 6) : 1u;
+    const uint32_t per = nbatch >= (uint32_t)WPG ? nbatch / WPG : 1u, b0 = gwarp * per;
+    const bool active = b0 < nbatch;
     double A[8];
-    uint32_t cur = 0xffffffffu;
-    // prefetch the first matrix variant this warp needs in (tile j, round r) while earlier work is still in flight
+    uint32_t cur = 0xffffffffu, var_hi = 0;
+    DBG_DECL;
+    // operands of (tile j, round r): variant bits from the tile id, first variant of this warp, its A fragments
     auto prefetch = [&](uint32_t j, uint32_t r) {
-      const uint64_t* w = sprog + T_STAGE_WORDS + (uint64_t)r * T_ROUND_WORDS;
-      uint32_t per, b0;
-      bool active;
-      dmma_geometry<WPG>(w, gwarp, per, b0, active);
       if (!active) return;
       const uint64_t ext_hi = sc.ext_hi_base | active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
-      cur = dmma_var_hi(w, ext_hi, m) | (batch_tab[r * nbstride + b0] >> 20);
-      dmma_load_A(A, reinterpret_cast<const double*>(stage_g + w[2]) + lane, cur);
+      const uint2 rt = rtab[r];
+      var_hi = dmma_var_hi(rt.x, ext_hi);
+      cur = var_hi | (batch_tab[r * nbstride + b0] >> 20);
+      dmma_load_A(A, reinterpret_cast<const double*>(stage_g + rt.y) + lane, cur);
     };
     if (grp < T && (MMA_ONLY || round_kind(sprog, 0) == 1u)) prefetch(grp, 0);
     PF_DECL;
     for (uint32_t j = grp; j < T; j += NG) {
       const uint32_t b = j % nbuf;
-      const uint64_t ext_hi = sc.ext_hi_base | active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
       mbar_wait(full + b, (j / nbuf) & 1u);
       PF_ADD(PF_C_WAIT_FULL);
       for (uint32_t r = 0; r < sc.n_rounds; ++r) {
@@ -361,25 +537,29 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
           double Ac[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) Ac[i] = A[i];
-          const uint32_t curc = cur;
+          const uint32_t curc = cur, var_hic = var_hi;
+          const double* mats = reinterpret_cast<const double*>(stage_g + rtab[r].y) + lane;
           if (next_mma) prefetch(nj, nr);
           PF_ADD(PF_C_SETUP);
-          dmma_round_run<WPG>(smem_s + b * (uint32_t)tile_bytes, sprog + T_STAGE_WORDS + (uint64_t)r * T_ROUND_WORDS, stage_g,
-                              lane_tab + (size_t)r * 64u, batch_tab + r * nbstride, ext_hi, m, gwarp, lane, Ac, curc);
+          if (active)
+            dmma_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
+                           mats, lane, Ac, curc, dbg_bits);
           PF_ADD(PF_C_ROUND);
         } else if (!MMA_ONLY) {
           RoundCtx rc;
           decode_round(sprog, r, rc);
+          const uint64_t ext_hi = sc.ext_hi_base | active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
           double2* t2 = reinterpret_cast<double2*>(smem_raw + (size_t)b * tile_bytes);
           switch (rc.r) {
-            case 0: run_round_thread<0>(t2, rc, m, ext_hi, gtid, GT, dev_vals); break;
-            case 1: run_round_thread<1>(t2, rc, m, ext_hi, gtid, GT, dev_vals); break;
-            case 2: run_round_thread<2>(t2, rc, m, ext_hi, gtid, GT, dev_vals); break;
-            default: run_round_thread<3>(t2, rc, m, ext_hi, gtid, GT, dev_vals); break;
+            case 0: run_round_thread<0>(t2, rc, m, LC, ext_hi, gtid, GT, dev_vals); break;
+            case 1: run_round_thread<1>(t2, rc, m, LC, ext_hi, gtid, GT, dev_vals); break;
+            case 2: run_round_thread<2>(t2, rc, m, LC, ext_hi, gtid, GT, dev_vals); break;
+            default: run_round_thread<3>(t2, rc, m, LC, ext_hi, gtid, GT, dev_vals); break;
           }
           if (next_mma) prefetch(nj, nr);
         }
       }
+      if (use_tma) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(done + b);
     }
@@ -390,7 +570,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
 template <int NG, int WPG>
 static cudaError_t launch_tile_stage_t(bool mma_only, unsigned grid, size_t smem, size_t limit, cudaStream_t stream, double2* state,
                                        const uint64_t* stage_dev, uint32_t stage_words, const double* dev_vals, uint64_t n_active,
-                                       uint32_t nbuf) {
+                                       uint32_t nbuf, const CUtensorMap& tmap, uint32_t use_tma) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
@@ -399,13 +579,13 @@ static cudaError_t launch_tile_stage_t(bool mma_only, unsigned grid, size_t smem
     configured = true;
   }
   const unsigned threads = (NG * WPG + MOVER_WARPS) * 32;
-  if (mma_only) k_tile_stage<NG, WPG, true><<<grid, threads, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active, nbuf);
-  else k_tile_stage<NG, WPG, false><<<grid, threads, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active, nbuf);
+  if (mma_only) k_tile_stage<NG, WPG, true><<<grid, threads, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active, nbuf, tmap, use_tma);
+  else k_tile_stage<NG, WPG, false><<<grid, threads, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active, nbuf, tmap, use_tma);
   return cudaGetLastError();
 }
 
 cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const uint64_t* stage_host, uint32_t stage_words,
-                              const double* dev_vals, int num_sms, cudaStream_t stream, uint64_t* out_active) {
+                              const double* dev_vals, int num_sms, cudaStream_t stream, uint64_t* out_active, const TileMaps* maps) {
   StageCtx sc;
   decode_stage(stage_host, sc);
   bool mma_only = sc.n_rounds > 0;
@@ -416,9 +596,20 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   if ((sc.ext_hi_base & sc.skip_mask & ~tmask) != (sc.skip_val & ~tmask)) { if (out_active) *out_active = 0; return cudaSuccess; }
   const uint64_t n_active = (1ULL << nb) >> __builtin_popcountll(sc.skip_mask & tmask);
   if (out_active) *out_active = n_active;
+  // TMA mode needs a tensor map whose box is one run of 2^c amplitudes (c >= 3: at least one 128-byte row)
+#ifdef QCB_TILE_PROFILE
+  static const int dbg_once = [] { const char* e = getenv("QCB_TILE_DBG"); int v = e ? atoi(e) : 0; cudaMemcpyToSymbol(g_tile_dbg, &v, sizeof v); return v; }();
+  (void)dbg_once;
+#endif
+  static const bool no_tma = getenv("QCB_NO_TMA") != nullptr;
+  static const CUtensorMap dummy_map = {};
+  const uint32_t use_tma = (!no_tma && maps && sc.c >= 3 && sc.c <= 11 && maps->valid[sc.c]) ? 1u : 0u;
+  const CUtensorMap* tm = use_tma ? reinterpret_cast<const CUtensorMap*>(maps->map[sc.c]) : &dummy_map;
+  const uint32_t rb = use_tma ? sc.c : sc.L;            // run bits (kernel: L)
   const size_t tile_n = (size_t)1 << sc.m, nbstride = tile_n >= 64 ? (tile_n >> 6) : 1;
-  const size_t fixed = 8 * (size_t)((stage_words + 1u) & ~1u) + ((((size_t)8 << (sc.m - sc.L)) + 15) & ~(size_t)15) +
-                       (size_t)1024 * sc.n_rounds + ((4 * nbstride * sc.n_rounds + 15) & ~(size_t)15) + 16 * 8;   // + full[]/done[] mbarriers (nbuf <= 8)
+  const size_t fixed = 8 * (size_t)((stage_words + 1u) & ~1u) + ((((size_t)8 << (sc.m - rb)) + 15) & ~(size_t)15) +
+                       (size_t)1024 * sc.n_rounds + ((4 * nbstride * sc.n_rounds + 15) & ~(size_t)15) +
+                       ((((size_t)4 << (sc.m - rb)) + 15) & ~(size_t)15) + (((size_t)8 * sc.n_rounds + 15) & ~(size_t)15) + 16 * 8 + 1024;   // + run / round tables, mbarriers (nbuf <= 8), alignment slack
   const size_t limit = 227 * 1024;
   uint64_t grid = (uint64_t)num_sms;
   if (grid > n_active) grid = n_active;
@@ -428,21 +619,50 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   while (nbuf > 1 && (fixed + nbuf * (tile_n * 16) > limit || nbuf > tiles_per_cta + 1)) --nbuf;
   const size_t smem = fixed + nbuf * (tile_n * 16);
   if (smem > limit) return cudaErrorInvalidConfiguration;
-  // consumer layout: groups x warps-per-group (QCB_CONSUMERS = "2x4" default, "2x8", "1x16", "1x8")
+  // consumer layout: groups x warps-per-group (QCB_CONSUMERS = "2x4" default, "3x4", "2x8", "1x16", "1x8")
   static const int layout = [] {
     const char* e = getenv("QCB_CONSUMERS");
     if (!e) return 24;
     return (e[0] - '0') * 10 + atoi(e + 2);
   }();
 #define QCB_LAUNCH(NG, WPG) \
-  return launch_tile_stage_t<NG, WPG>(mma_only, (unsigned)grid, smem, limit, stream, state, stage_dev, stage_words, dev_vals, n_active, nbuf)
+  return launch_tile_stage_t<NG, WPG>(mma_only, (unsigned)grid, smem, limit, stream, state, stage_dev, stage_words, dev_vals, n_active, nbuf, \
+                                      *tm, use_tma)
   switch (layout) {
     case 26: case 116: QCB_LAUNCH(1, 16);
     case 18: QCB_LAUNCH(1, 8);
     case 28: QCB_LAUNCH(2, 8);
+    case 34: QCB_LAUNCH(3, 4);
     default: QCB_LAUNCH(2, 4);
   }
 #undef QCB_LAUNCH
+}
+
+// ------------------------------------------------------------------ tensor maps of the state (host)
+cudaError_t build_tile_maps(double2* state, int n_local, TileMaps* out) {
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is a 128-byte opaque object");
+  for (int c = 0; c < 12; ++c) out->valid[c] = false;
+  if (n_local < 3) return cudaSuccess;                     // smaller than one 128-byte row: LSU mover only
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess) return e;
+  if (!fn || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+  const cuuint64_t rows = 1ULL << (n_local - 3);
+  for (int c = 3; c <= 11 && c <= n_local; ++c) {
+    const cuuint64_t gdim[2] = {16, rows};                 // 16 doubles = 8 amplitudes = 128 bytes per row
+    const cuuint64_t gstride[1] = {128};                   // bytes between rows
+    const cuuint32_t box[2] = {16, 1u << (c - 3)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeFn>(fn)(reinterpret_cast<CUtensorMap*>(out->map[c]), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, state,
+                                                gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    out->valid[c] = (r == CUDA_SUCCESS);
+  }
+  return cudaSuccess;
 }
 
 // ------------------------------------------------------------------ state initialisation

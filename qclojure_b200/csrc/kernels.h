@@ -17,8 +17,16 @@ struct ExpectTerms { int n; uint64_t zmask[EXPECT_TERMS]; double pr[EXPECT_TERMS
 struct Mat2 { double m[8]; };
 struct BitList { int n; int pos[MAX_MEASURE_BITS]; };
 
+// TMA tensor maps of one state allocation, indexed by run bits c (box = 2^(c-3) rows of 128 bytes); opaque 128-byte
+// CUtensorMap objects so that this header does not need <cuda.h>.
+struct TileMaps {
+  alignas(64) unsigned char map[12][128];
+  bool valid[12];
+};
+// Builds the maps for a state of 2^n_local amplitudes at `state` (driver entry point resolved at run time).
+cudaError_t build_tile_maps(double2* state, int n_local, TileMaps* out);
 cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const uint64_t* stage_host, uint32_t stage_words,
-                              const double* dev_vals, int num_sms, cudaStream_t stream, uint64_t* out_active);
+                              const double* dev_vals, int num_sms, cudaStream_t stream, uint64_t* out_active, const TileMaps* maps);
 void tile_prof_dump();   // prints the cycle accounting of k_tile_stage (only in a PROFILE=1 build)
 cudaError_t launch_set_amp(double2* state, uint64_t idx, double re, double im, cudaStream_t s);
 cudaError_t launch_reduce(const double2* state, uint64_t count, int mode, double* partials, int grid, cudaStream_t s);

@@ -67,6 +67,7 @@ Config config_from(const qcb_config& c) {
   k.max_stage_cost = c.max_stage_cost;
   k.max_stage_rounds = c.max_stage_rounds;
   k.dense_mma = (c.dense_mma == 2) ? 0 : 1;
+  k.tma = (c.tile_mover == 2) ? 1 : 0;
   return k;
 }
 
@@ -245,21 +246,30 @@ struct Blocker {
 
 static inline int popc(uint64_t v) { return __builtin_popcountll(v); }
 
-// choose lane positions so that the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank groups
-// under the swizzle  phys = i ^ (((i>>3) ^ (i>>6) ^ (i>>9)) & 7)   (tile_core.h: swz)
-static void choose_lanes(int m, const std::vector<int>& slots, std::vector<int>& lanes) {
+// Chunk bit (0..2) of the 128-byte shared-memory row that tile-local index bit p is XORed onto by the tile layout
+// (tile_core.h: swz; c = run bits of the stage), or -1 when the bit does not move the bank group at all.
+static int chunk_class(int p, int c) {
+  if (p < 6) return p % 3;
+  if (c >= 6) return -1;
+  const int lo = c > 3 ? c - 3 : 0;
+  return lo + (p - 6) % (3 - lo);
+}
+
+// choose lane positions so that the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank groups: three tile-local
+// bits that are not slots, one per chunk class
+static void choose_lanes(int m, int c, const std::vector<int>& slots, std::vector<int>& lanes) {
   lanes.clear();
   uint64_t used = 0;
   for (int s : slots) used |= 1ULL << s;
   int want = std::min(3, m - (int)slots.size());
   for (int k = 0; k < 3 && (int)lanes.size() < want; ++k) {
     int pick = -1;
-    for (int c = k; c < m; c += 3)
-      if (!((used >> c) & 1)) { pick = c; break; }
+    for (int p = 0; p < m; ++p)
+      if (!((used >> p) & 1) && chunk_class(p, c) == k) { pick = p; break; }
     if (pick >= 0) { lanes.push_back(pick); used |= 1ULL << pick; }
   }
-  for (int c = 0; c < m && (int)lanes.size() < want; ++c)
-    if (!((used >> c) & 1)) { lanes.push_back(c); used |= 1ULL << c; }
+  for (int p = 0; p < m && (int)lanes.size() < want; ++p)
+    if (!((used >> p) & 1)) { lanes.push_back(p); used |= 1ULL << p; }
 }
 
 struct SplitCond { uint32_t sel = 0, loc_mask = 0, loc_val = 0; uint64_t hi_mask = 0, hi_val = 0; };
@@ -426,6 +436,7 @@ static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& wo
   }
   words[base + 4] = (uint64_t)nruns;
   words[base + 41] = st.flags;
+  words[base + 43] = (uint64_t)st.layout_c;
   // rounds: descriptors, then interpreter op slots, then (not copied to shared memory) tensor-core matrices
   size_t rbase = words.size();
   words.resize(rbase + st.rounds.size() * ROUND_WORDS, 0);
@@ -445,7 +456,7 @@ static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& wo
       continue;
     }
     std::vector<int> lanes;
-    choose_lanes(m, rd.slot_pos, lanes);
+    choose_lanes(m, st.layout_c, rd.slot_pos, lanes);
     size_t ob = words.size();
     for (const Gate& g : rd.gates) put_gate_words(words, g, rd.slot_pos, m);
     rb = rbase + r * ROUND_WORDS;
@@ -594,34 +605,43 @@ static void build_dmma_round(const Config& cfg, const Stage& st, Round& rd) {
   for (int p = m - 1; p >= 0 && rd.slot_pos.size() < 3; --p)
     if (!((slot_mask >> p) & 1) && !((cond >> p) & 1)) { rd.slot_pos.push_back(p); slot_mask |= 1ULL << p; }
   std::sort(rd.slot_pos.begin(), rd.slot_pos.end());
-  // lane bits: 3 tile-local bits that are neither slots nor conditions, with pairwise distinct residues mod 3
-  // (the XOR swizzle folds position p onto bank-group bit p % 3); then choose which slot bit rides on the
-  // half-warp's thread index for loads (j_load) and stores (j_store) so that 8-byte accesses are conflict-free
+  // lane bits: 3 tile-local bits that are neither slots nor conditions, one per chunk class of the tile layout
+  // (chunk_class); then choose which slot bit rides on the half-warp's thread index for loads (j_load) and stores
+  // (j_store) so that 8-byte accesses are conflict-free
+  const int rb = st.layout_c;
   const uint64_t busy = slot_mask | (cond & tile_mask);
   std::vector<int> lanes;
-  for (int res = 0; res < 3; ++res)
-    for (int p = res; p < m; p += 3)
-      if (!((busy >> p) & 1)) { lanes.push_back(p); break; }
+  for (int cl = 0; cl < 3; ++cl)
+    for (int p = 0; p < m; ++p)
+      if (!((busy >> p) & 1) && chunk_class(p, rb) == cl) { lanes.push_back(p); break; }
   uint64_t used = busy;
   for (int p : lanes) used |= 1ULL << p;
   for (int p = 0; p < m && lanes.size() < 3; ++p) if (!((used >> p) & 1)) { lanes.push_back(p); used |= 1ULL << p; }
-  // exhaustive search over lane orders and slot choices: loads vary (lanes[0], lanes[1], slot j_load) inside a
-  // half-warp, stores vary (lanes[1], lanes[2], slot j_store); each triple wants pairwise distinct residues mod 3
+  // exhaustive search over the candidate lane bits (every free tile-local bit), their order and the slot choices:
+  // loads vary (lanes[0], lanes[1], slot j_load) inside a half-warp, stores vary (lanes[1], lanes[2], slot j_store);
+  // each triple wants three distinct chunk classes
   int jl = 0, js = 0;
   {
+    std::vector<int> cand;
+    for (int p = 0; p < m; ++p) if (!((busy >> p) & 1)) cand.push_back(p);
+    auto distinct3 = [&](int a, int b, int d) {
+      const int ca = chunk_class(a, rb), cb = chunk_class(b, rb), cd = chunk_class(d, rb);
+      return ca >= 0 && cb >= 0 && cd >= 0 && ca != cb && cb != cd && ca != cd;
+    };
     int best = -1;
-    std::vector<int> base = lanes, bestl = lanes;
-    static const int P[6][3] = {{0,1,2},{0,2,1},{1,0,2},{1,2,0},{2,0,1},{2,1,0}};
-    if (base.size() == 3)
-      for (int perm = 0; perm < 6; ++perm) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
-        const int l0 = base[P[perm][0]], l1 = base[P[perm][1]], l2 = base[P[perm][2]];
-        const bool dl = (l0 % 3 != l1 % 3) && (l1 % 3 != l2 % 3) && (l0 % 3 != l2 % 3);
-        int score = 0;
-        if (dl && rd.slot_pos[a] % 3 == l2 % 3) ++score;
-        if (dl && rd.slot_pos[b] % 3 == l0 % 3) ++score;
-        if (score > best) { best = score; jl = a; js = b; bestl = {l0, l1, l2}; }
-      }
-    lanes = bestl;
+    std::vector<int> bestl = lanes;
+    const int nc = (int)cand.size();
+    for (int i0 = 0; i0 < nc; ++i0) for (int i1 = 0; i1 < nc; ++i1) for (int i2 = 0; i2 < nc; ++i2) {
+      if (i0 == i1 || i1 == i2 || i0 == i2) continue;
+      const int l0 = cand[i0], l1 = cand[i1], l2 = cand[i2];
+      int bl = -1, bs = -1;
+      for (int a = 0; a < 3 && bl < 0; ++a) if (distinct3(l0, l1, rd.slot_pos[a])) bl = a;
+      for (int b = 0; b < 3 && bs < 0; ++b) if (distinct3(l1, l2, rd.slot_pos[b])) bs = b;
+      const int score = (bl >= 0) + (bs >= 0);
+      if (score > best) { best = score; jl = bl >= 0 ? bl : 0; js = bs >= 0 ? bs : 0; bestl = {l0, l1, l2}; }
+      if (best == 2) break;
+    }
+    if (bestl.size() == 3) lanes = bestl;
   }
   rd.j_load = jl; rd.j_store = js;
   // group-index bit order: lane bits, then free bits ascending, then tile-local condition bits (so that the
@@ -766,8 +786,11 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
   const int n = cfg.n_total, nl = cfg.n_local, m = std::min(cfg.tile_bits, nl), L = std::min(cfg.low_bits, m);
   std::vector<int> perm(n);
   for (int b = 0; b < n; ++b) perm[b] = perm_in.empty() ? b : perm_in[b];
-  const int max_cost = cfg.max_stage_cost > 0 ? cfg.max_stage_cost : 64;
-  const int max_rounds = cfg.max_stage_rounds > 0 ? cfg.max_stage_rounds : 64;
+  // Budget of one fused sweep.  A sweep costs ~3.5 ms of HBM/pipeline time plus ~2 ms per tensor-core round at 30 qubits
+  // (profiles/r1d_sweep_budgets.log), so gates/s keeps rising until the tile bits, not the budget, end the sweep; 12 rounds
+  // is what the per-round tables leave room for next to three 64 KB tile buffers in shared memory.
+  const int max_cost = cfg.max_stage_cost > 0 ? cfg.max_stage_cost : 800;
+  const int max_rounds = cfg.max_stage_rounds > 0 ? cfg.max_stage_rounds : 12;
   const double sweep_bytes = 32.0 * std::ldexp(1.0, nl);
   const uint64_t local_mask = (nl >= 64) ? ~0ULL : ((1ULL << nl) - 1);
   const uint64_t tileid_mask = ((nl - m) >= 64) ? ~0ULL : ((1ULL << (nl - m)) - 1);
@@ -835,6 +858,13 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
     for (int b = 0; b < nl && popc(A) < m; ++b) if (!((avoid >> b) & 1)) A |= 1ULL << b;
     for (int b = 0; b < nl && popc(A) < m; ++b) A |= 1ULL << b;
     for (int b = 0; b < nl; ++b) if ((A >> b) & 1) st.tile_pos.push_back(b);
+    // TMA mover: one tensor copy moves a run of 2^layout_c amplitudes = the contiguous low tile bits (box rows <= 256
+    // => at most 11; at least one 128-byte row => at least 3, else the stage falls back to the LSU mover and layout 0)
+    st.layout_c = 0;
+    if (cfg.tma) {
+      while (st.layout_c < m && st.layout_c < 11 && ((A >> st.layout_c) & 1)) ++st.layout_c;
+      if (st.layout_c < 3) st.layout_c = 0;
+    }
     std::vector<int> ext_of_phys(64, 0);
     {
       int ti = 0, ni = 0;

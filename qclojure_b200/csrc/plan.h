@@ -62,7 +62,7 @@ enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_
 //     [6] skip_mask [7] skip_val  (tile skipped unless (ext_hi & skip_mask) == skip_val)
 //     [8..8+MAX_TILE_BITS)  physical position of tile bit k (k < m), ascending; first L are 0..L-1
 //     [24..24+MAX_RUNS)     run_start | run_len << 8 : contiguous runs of non-tile positions (ascending)
-//     [40] total words of this stage (desc + rounds + ops)  [41] flags
+//     [40] total words of this stage (desc + rounds + ops)  [41] flags  [43] layout_c (tile_core.h: swz; > 0 = TMA mover)
 //   Op slot (OP_WORDS words; MAT2 uses 3 slots):
 //     [0] kind | j0<<8 | j1<<16 | n_slots<<24 | sel<<32   (sel: bitmap over slot patterns, see tile_core.h)
 //     [1] loc_mask | loc_val<<32   (tile-local non-slot bits)      [2] hi_mask  [3] hi_val  (tile-id + rank bits)
@@ -99,6 +99,8 @@ struct Stage {
   int kind = S_TILE;
   // S_TILE
   int m = 0, L = 0;
+  int layout_c = 0;                 // layout parameter of the shared tile (tile_core.h: swz): 0 = full XOR fold (LSU mover);
+                                    // TMA mover: number of contiguous low tile bits = run of one tensor copy (3..11)
   std::vector<int> tile_pos;        // physical positions of the tile bits, ascending
   uint64_t skip_mask = 0, skip_val = 0;
   uint64_t flags = 0;
@@ -117,6 +119,7 @@ struct Config {
   int max_stage_cost = 0;
   int max_stage_rounds = 0;
   int dense_mma = 1;           // rounds as dense 8x8 complex blocks on the fp64 tensor cores
+  int tma = 0;                 // tiles move by TMA tensor copies (layout follows the hardware 128-byte swizzle)
   int threads = 256;
 };
 

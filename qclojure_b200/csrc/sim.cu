@@ -107,6 +107,7 @@ struct qcb_sim {
   uint64_t* d_prog = nullptr; uint64_t* h_prog = nullptr; size_t prog_cap = 0;   // words
   cudaEvent_t prog_ev = nullptr; bool prog_ev_valid = false;
   double* d_vals = nullptr;                       // 256 doubles: device-side coefficients / small results
+  TileMaps maps;                                  // TMA tensor maps of `state` (one per run length)
   double* d_partials = nullptr; size_t partials_cap = 0;   // doubles
   unsigned char* d_scratch = nullptr; size_t scratch_cap = 0;  // bytes
   unsigned char* h_pin = nullptr; size_t pin_cap = 0;          // bytes (pinned)
@@ -273,7 +274,7 @@ int execute_plan(qcb_sim* h, Plan& plan) {
     if (st.kind == S_TILE) {
       const uint32_t words = (uint32_t)plan.words[off + 2 + 42];      // descriptor part only (copied to smem)
       uint64_t active = 0;
-      CU(h, launch_tile_stage(h->state, h->d_prog + off + 2, plan.words.data() + off + 2, words, h->d_vals, h->num_sms, h->stream, &active));
+      CU(h, launch_tile_stage(h->state, h->d_prog + off + 2, plan.words.data() + off + 2, words, h->d_vals, h->num_sms, h->stream, &active, &h->maps));
       if (active) { h->stats.n_sweeps++; h->stats.n_kernel_launches++; h->stats.n_rounds += st.rounds.size(); }
     } else if (st.kind == S_SUM) {
       // Grover diffusion: sum of all amplitudes -> (alpha, beta) = (-1, 2*mean) in d_vals[0..4)
@@ -684,6 +685,7 @@ int32_t qcb_create(const qcb_config* c, qcb_handle* out) {
   CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->local_count = 1ULL << cfg.n_local;
   CUC(cudaMalloc(&h->state, h->local_count * sizeof(double2)));
+  CUC(build_tile_maps(h->state, cfg.n_local, &h->maps));
   CUC(cudaMalloc(&h->d_vals, 256 * sizeof(double)));
   CUC(cudaMemsetAsync(h->d_vals, 0, 256 * sizeof(double), h->stream));
   CUC(cudaEventCreate(&h->ev0)); CUC(cudaEventCreate(&h->ev1));

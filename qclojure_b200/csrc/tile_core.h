@@ -28,7 +28,28 @@ enum : uint32_t { TD_MAT1 = 0, TD_MAT2 = 1, TD_SWAPP = 2, TD_DMASK = 3, TD_DNEG 
                   TD_MAT1R = 7, TD_MAT1RI = 8, TD_PERMX = 9, TD_DENSE = 10 };
 constexpr int T_OP_WORDS = 16, T_STAGE_WORDS = 48, T_ROUND_WORDS = 40;
 
-QCB_HD uint32_t swz(uint32_t i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u); }
+// Shared-memory layout of a tile (16-byte units), parameter c = stage word [43].
+// c = 0 (LSU mover, the default): every row bit >= 3 is XOR-folded onto the three chunk bits - any three index bits
+// with distinct residues mod 3 give conflict-free access.
+// c >= 3 (TMA mover): the tile is written by TMA tensor copies with the hardware 128-byte swizzle, one copy per
+// contiguous run of 2^c amplitudes (c = number of contiguous low tile bits), i.e. 2^(c-3) rows of 128 bytes whose
+// 16-byte chunk index is XORed with bits 7..9 of the shared-memory address.  Row index r = i >> 3; the run is placed at row address r ^ fold(r), where fold() XORs the row bits >= 3
+// cyclically onto the row-address bits [c-3, 3) that a run does not fix itself.  Net effect: index bit p lands on
+// chunk bit  p (p < 3),  p-3 (3 <= p < 6),  and for p >= 6:  (c-3) + (p-6) mod (6-c)  when c < 6, none otherwise.
+// Accesses whose varying index bits fall on three distinct chunk bits are bank-conflict free (plan.cpp: chunk_class).
+// The map is linear over GF(2): swz(a ^ b, c) == swz(a, c) ^ swz(b, c).
+QCB_HD uint32_t swz_fold(uint32_t r, uint32_t c) {
+  if (c >= 6) return 0;
+  const uint32_t t = r >> 3;
+  if (c <= 3) return (t ^ (t >> 3) ^ (t >> 6) ^ (t >> 9)) & 7u;
+  if (c == 4) return ((t ^ (t >> 2) ^ (t >> 4) ^ (t >> 6) ^ (t >> 8)) & 3u) << 1;
+  uint32_t x = t; x ^= x >> 8; x ^= x >> 4; x ^= x >> 2; x ^= x >> 1;      // c == 5: parity
+  return (x & 1u) << 2;
+}
+QCB_HD uint32_t swz(uint32_t i, uint32_t c) {
+  const uint32_t r = i >> 3, ra = r ^ swz_fold(r, c);
+  return (ra << 3) | ((i & 7u) ^ (ra & 7u));
+}
 
 QCB_HD uint32_t insert_zero(uint32_t v, uint32_t pos) { return ((v >> pos) << (pos + 1)) | (v & ((1u << pos) - 1u)); }
 
@@ -272,32 +293,33 @@ QCB_HD void apply_ops(double2 (&a)[1 << R], const uint64_t* ops, uint32_t n_slot
 
 // One thread's share of a round: groups g = tid, tid+T, ... ; tile = swizzled shared-memory tile.
 template <int R>
-QCB_HD void run_round_thread(double2* tile, const RoundCtx& rc, uint32_t m, uint64_t ext_hi, uint32_t tid, uint32_t nthreads,
-                             const double* dev_vals) {
-  uint32_t off[1 << R];
+QCB_HD void run_round_thread(double2* tile, const RoundCtx& rc, uint32_t m, uint32_t c, uint64_t ext_hi, uint32_t tid,
+                             uint32_t nthreads, const double* dev_vals) {
+  uint32_t off[1 << R], soff[1 << R];
 #pragma unroll
   for (int s = 0; s < (1 << R); ++s) {
     uint32_t o = 0;
 #pragma unroll
     for (int j = 0; j < R; ++j) if ((s >> j) & 1) o |= 1u << rc.slot_pos[j];
     off[s] = o;
+    soff[s] = swz(o, c);
   }
   const uint32_t ngroups = 1u << (m - R);
   for (uint32_t g = tid; g < ngroups; g += nthreads) {
-    const uint32_t idx0 = group_idx0(rc, g);
+    const uint32_t idx0 = group_idx0(rc, g), s0 = swz(idx0, c);        // swz is linear: swz(idx0 | off) = s0 ^ soff
     double2 a[1 << R];
 #pragma unroll
-    for (int s = 0; s < (1 << R); ++s) a[s] = tile[swz(idx0 | off[s])];
+    for (int s = 0; s < (1 << R); ++s) a[s] = tile[s0 ^ soff[s]];
     apply_ops<R>(a, rc.ops, rc.n_slots, idx0, ext_hi, m, off, dev_vals);
 #pragma unroll
-    for (int s = 0; s < (1 << R); ++s) tile[swz(idx0 | off[s])] = a[s];
+    for (int s = 0; s < (1 << R); ++s) tile[s0 ^ soff[s]] = a[s];
   }
 }
 
 // ---- tensor-core ("dmma") rounds: the round is one of 2^k dense 16x16 real matrices applied to the 16 reals
 // (8 slot patterns x re/im) of every group with mma.sync.m16n8k16.f64; 8 groups (the lane bits) form one MMA.
 struct DmmaCtx {
-  uint32_t n_grp, k, j_load, j_store;
+  uint32_t n_grp, k, j_load, j_store, c;     // c: run bits of the stage (layout parameter of swz)
   uint32_t slot_pos[3], grp_pos[10], cond_pos[4];
   uint64_t mat_off;
 };
@@ -308,6 +330,7 @@ QCB_HD uint32_t round_kind(const uint64_t* stage, uint32_t round_idx) {
 
 QCB_HD void decode_dmma(const uint64_t* stage, uint32_t round_idx, DmmaCtx& c) {
   const uint64_t* w = stage + T_STAGE_WORDS + (uint64_t)round_idx * T_ROUND_WORDS;
+  c.c = (uint32_t)stage[43];
   c.mat_off = w[2]; c.n_grp = (uint32_t)w[18]; c.k = (uint32_t)w[29]; c.j_load = (uint32_t)w[34]; c.j_store = (uint32_t)w[35];
   for (int j = 0; j < 3; ++j) c.slot_pos[j] = (uint32_t)w[4 + j];
   for (int j = 0; j < 10; ++j) c.grp_pos[j] = (uint32_t)w[19 + j];
@@ -336,9 +359,9 @@ QCB_HD void dmma_lane_setup(const DmmaCtx& c, uint32_t lane, uint32_t (&Pl)[4], 
   comp_l = q & 1u;
   comp_s = g & 1u;
 #pragma unroll
-  for (uint32_t v = 0; v < 4; ++v) Pl[v] = swz(dmma_lane_offset(c, g) | dmma_pattern_offset(c, q + 4u * v, c.j_load));
+  for (uint32_t v = 0; v < 4; ++v) Pl[v] = swz(dmma_lane_offset(c, g) | dmma_pattern_offset(c, q + 4u * v, c.j_load), c.c);
 #pragma unroll
-  for (uint32_t i = 0; i < 4; ++i) Ps[i] = swz(dmma_lane_offset(c, 2u * q + (i & 1u)) | dmma_pattern_offset(c, g + 8u * (i >> 1), c.j_store));
+  for (uint32_t i = 0; i < 4; ++i) Ps[i] = swz(dmma_lane_offset(c, 2u * q + (i & 1u)) | dmma_pattern_offset(c, g + 8u * (i >> 1), c.j_store), c.c);
 }
 
 // batch index -> tile-local base offset (group bits 3.. deposited at grp_pos[3..])
@@ -385,7 +408,7 @@ QCB_HD uint32_t dmma_batch_entry(const DmmaCtx& c, uint32_t batch, uint32_t m) {
 #pragma unroll
   for (uint32_t j = 0; j < 4; ++j)
     if (j < c.k && c.cond_pos[j] < m) v |= ((base >> c.cond_pos[j]) & 1u) << j;
-  return (swz(base) << 4) | (v << 20);
+  return (swz(base, c.c) << 4) | (v << 20);
 }
 
 QCB_HD uint32_t dmma_variant_hi(const DmmaCtx& c, uint64_t ext_hi, uint32_t m) {
@@ -398,13 +421,13 @@ QCB_HD uint32_t dmma_variant_hi(const DmmaCtx& c, uint64_t ext_hi, uint32_t m) {
 
 // ---- tile addressing
 struct StageCtx {
-  uint32_t n_local, m, L, n_rounds, n_runs;
+  uint32_t n_local, m, L, n_rounds, n_runs, c;
   uint64_t ext_hi_base, skip_mask, skip_val;
 };
 
 QCB_HD void decode_stage(const uint64_t* st, StageCtx& sc) {
   sc.n_local = (uint32_t)st[0]; sc.m = (uint32_t)st[1]; sc.L = (uint32_t)st[2]; sc.n_rounds = (uint32_t)st[3];
-  sc.n_runs = (uint32_t)st[4]; sc.ext_hi_base = st[5]; sc.skip_mask = st[6]; sc.skip_val = st[7];
+  sc.n_runs = (uint32_t)st[4]; sc.ext_hi_base = st[5]; sc.skip_mask = st[6]; sc.skip_val = st[7]; sc.c = (uint32_t)st[43];
 }
 
 // active-tile ordinal -> tile id (deposit into the tile-id bits not fixed by skip_mask, OR the fixed value)
@@ -431,10 +454,11 @@ QCB_HD uint64_t tile_base(const uint64_t* st, const StageCtx& sc, uint64_t tile)
 }
 
 // offset contributed by the high tile bits (tile-local bits L..m-1) for hi = local >> L
-QCB_HD uint64_t hi_offset(const uint64_t* st, const StageCtx& sc, uint32_t hi) {
+QCB_HD uint64_t hi_offset_from(const uint64_t* st, const StageCtx& sc, uint32_t hi, uint32_t from) {
   uint64_t o = 0;
-  for (uint32_t k = sc.L; k < sc.m; ++k) o |= (uint64_t)((hi >> (k - sc.L)) & 1u) << st[8 + k];
+  for (uint32_t k = from; k < sc.m; ++k) o |= (uint64_t)((hi >> (k - from)) & 1u) << st[8 + k];
   return o;
 }
+QCB_HD uint64_t hi_offset(const uint64_t* st, const StageCtx& sc, uint32_t hi) { return hi_offset_from(st, sc, hi, sc.L); }
 
 }  // namespace qcb

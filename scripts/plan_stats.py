@@ -43,3 +43,20 @@ print(f"n={n} gates={len(ops)} stages={ns} tile_sweeps={len(rounds)} rounds={sum
 print("rounds/stage histogram:", sorted(Counter(rounds).items()))
 print("cond-bit k histogram:", sorted(kc.items()))
 print("matrix bytes/stage: max", max(matbytes), "mean", sum(matbytes) / len(matbytes), "hist(KB)", sorted(Counter(b // 1024 for b in matbytes).items()))
+# local (tile-local) vs tile-id condition bits per tensor-core round: a warp's batches share one matrix variant when the
+# local condition bits fit in the bits of the batch index that select the warp (2 for 4 warps per group, 3 for 8)
+pos, kl_hist = 4, Counter()
+for s in range(ns):
+    kind = int(w[pos]); pos += 2
+    if kind != 0:
+        continue
+    st = w[pos:]
+    nr = int(st[3]); total = int(st[40]); m = int(st[1])
+    for r in range(nr):
+        rd = st[48 + 40 * r: 48 + 40 * (r + 1)]
+        if int(rd[17]) == 1:
+            k = int(rd[29])
+            kl = sum(1 for j in range(k) if int(rd[30 + j]) < m)
+            kl_hist[(kl, k - kl)] += 1
+    pos += total
+print("(local, tile-id) condition bits per round:", sorted(kl_hist.items()))

@@ -83,7 +83,7 @@ int emu_stage_max_conflict(Emu* e, uint64_t si, int nthreads) {
         uint32_t off = 0;
         for (uint32_t j = 0; j < rc.r; ++j) if ((s >> j) & 1) off |= 1u << rc.slot_pos[j];
         int cnt[8] = {0};
-        for (uint32_t l = 0; l < 8 && g0 + l < ngroups; ++l) cnt[swz(group_idx0(rc, g0 + l) | off) & 7]++;
+        for (uint32_t l = 0; l < 8 && g0 + l < ngroups; ++l) cnt[swz(group_idx0(rc, g0 + l) | off, sc.c) & 7]++;
         for (int b = 0; b < 8; ++b) if (cnt[b] > worst) worst = cnt[b];
       }
     }
@@ -149,21 +149,21 @@ int emu_run_tile_stage(Emu* e, uint64_t si, double* state, const double* dev_val
     const uint64_t ext_hi = sc.ext_hi_base | t;
     const uint64_t base = tile_base(st, sc, t);
     for (uint32_t i = 0; i < tile_n; ++i)
-      tile[swz(i)] = gs[base + hi_offset(st, sc, i >> sc.L) + (i & ((1u << sc.L) - 1u))];
+      tile[swz(i, sc.c)] = gs[base + hi_offset(st, sc, i >> sc.L) + (i & ((1u << sc.L) - 1u))];
     for (uint32_t r = 0; r < sc.n_rounds; ++r) {
       if (round_kind(st, r) == 1u) { emu_dmma_round(tile.data(), st, r, ext_hi, sc.m, nthreads); continue; }
       RoundCtx rc; decode_round(st, r, rc);
       for (uint32_t tid = 0; tid < (uint32_t)nthreads; ++tid) {
         switch (rc.r) {
-          case 0: run_round_thread<0>(tile.data(), rc, sc.m, ext_hi, tid, nthreads, dev_vals); break;
-          case 1: run_round_thread<1>(tile.data(), rc, sc.m, ext_hi, tid, nthreads, dev_vals); break;
-          case 2: run_round_thread<2>(tile.data(), rc, sc.m, ext_hi, tid, nthreads, dev_vals); break;
-          default: run_round_thread<3>(tile.data(), rc, sc.m, ext_hi, tid, nthreads, dev_vals); break;
+          case 0: run_round_thread<0>(tile.data(), rc, sc.m, sc.c, ext_hi, tid, nthreads, dev_vals); break;
+          case 1: run_round_thread<1>(tile.data(), rc, sc.m, sc.c, ext_hi, tid, nthreads, dev_vals); break;
+          case 2: run_round_thread<2>(tile.data(), rc, sc.m, sc.c, ext_hi, tid, nthreads, dev_vals); break;
+          default: run_round_thread<3>(tile.data(), rc, sc.m, sc.c, ext_hi, tid, nthreads, dev_vals); break;
         }
       }
     }
     for (uint32_t i = 0; i < tile_n; ++i)
-      gs[base + hi_offset(st, sc, i >> sc.L) + (i & ((1u << sc.L) - 1u))] = tile[swz(i)];
+      gs[base + hi_offset(st, sc, i >> sc.L) + (i & ((1u << sc.L) - 1u))] = tile[swz(i, sc.c)];
   }
   return QCB_OK;
 }
@@ -174,6 +174,8 @@ void emu_local_sum(const double* state, uint64_t count, double out[2]) {
   for (uint64_t i = 0; i < count; ++i) { re += state[2 * i]; im += state[2 * i + 1]; }
   out[0] = re; out[1] = im;
 }
+
+uint32_t emu_swz(uint32_t i, uint32_t c) { return swz(i, c); }
 
 uint64_t emu_program_words(Emu* e, uint64_t* out, uint64_t cap) {
   uint64_t n = e->plan.words.size();

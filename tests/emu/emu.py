@@ -68,6 +68,10 @@ def lib():
         L.emu_run_tile_stage.restype = C.c_int
         L.emu_run_tile_stage.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
         L.emu_local_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.emu_swz.restype = C.c_uint32
+        L.emu_swz.argtypes = [C.c_uint32, C.c_uint32]
+        L.emu_program_words.restype = C.c_uint64
+        L.emu_program_words.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
 

@@ -479,3 +479,32 @@ def test_p2_linear_algebra_ops():
         assert abs(la.norm2(x) - np.linalg.norm(x)) <= TOL
         assert np.max(np.abs(la.add(A, A) - 2 * A)) <= TOL
         assert np.max(np.abs(la.scale(A, 2 - 1j) - (2 - 1j) * A)) <= TOL
+
+
+# ------------------------------------------------------------------ mover variants of the tile kernel
+_MOVER_SCRIPT = r"""
+import numpy as np
+from oracle import qc_oracle as O
+from qclojure_b200 import _lib as L, circuits as C
+for n, depth in ((9, 6), (14, 6), (18, 8)):
+    circ = C.random_brickwork_circuit(n, depth)
+    want = O.execute_circuit(circ)
+    with L.StateVector(n) as sv:
+        sv.apply_circuit(circ)
+        err = float(np.max(np.abs(sv.get_state() - want)))
+    assert err <= 1e-10, (n, err)
+print("mover ok")
+"""
+
+
+@pytest.mark.parametrize("env", [{"QCB_TILE_MOVER": "2"}, {"QCB_TILE_MOVER": "2", "QCB_NO_TMA": "1"}, {"QCB_CONSUMERS": "2x8"},
+                                 {"QCB_CONSUMERS": "1x8", "QCB_TILE_BUFFERS": "2"}])
+def test_tile_kernel_variants_match_oracle(env):
+    """The TMA mover (tensor copies + hardware swizzle layout), the same layout moved by the LSU mover, the other consumer
+    layouts and a shorter buffer ring give the same amplitudes (the knobs are read once per process, hence the subprocess)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", _MOVER_SCRIPT], cwd=root, env={**os.environ, **env}, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and "mover ok" in out.stdout, out.stderr[-2000:]
