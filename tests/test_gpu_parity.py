@@ -508,3 +508,19 @@ def test_tile_kernel_variants_match_oracle(env):
     out = subprocess.run([sys.executable, "-c", _MOVER_SCRIPT], cwd=root, env={**os.environ, **env}, capture_output=True,
                          text=True, timeout=600)
     assert out.returncode == 0 and "mover ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_multi_gpu_sharded_matches_oracle():
+    """The sharded path (top log2 P qubits global, NCCL qubit exchanges) on every GPU of the box against the oracle:
+    tests/multi_gpu_check.py under torchrun.  Skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    ngpu = L.device_count()
+    world = 1 << (ngpu.bit_length() - 1)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "multi-gpu ok" in out.stdout, (out.stdout[-2000:], out.stderr[-3000:])
