@@ -812,7 +812,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
 
   // Build one fused tile stage from the head of `pending`.  `lead` (optional) is an op that must run
   // first on every amplitude (the affine pass of a Grover diffusion).
-  auto build_tile_stage = [&](const Gate* lead) {
+  auto build_tile_stage = [&](const Gate* lead) -> size_t {
     Stage st; st.kind = S_TILE; st.m = m; st.L = L;
     uint64_t A = 0; for (int k = 0; k < L; ++k) A |= 1ULL << k;
     Blocker bl; int cost = lead ? 4 : 0;
@@ -847,6 +847,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
         bl.block(g);
       }
     }
+    if (taken.empty() && !lead) return 0;          // nothing executable in the current layout (multi-GPU: exchange first)
     // single-gate stage: keep its condition bits OUT of the tile so that whole tiles can be skipped
     uint64_t avoid = 0;
     if (taken.size() == 1 && !lead) {
@@ -900,6 +901,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
     std::vector<int> rest;
     for (size_t i = 0; i < pending.size(); ++i) if (!tk[i]) rest.push_back(pending[i]);
     pending.swap(rest);
+    return keep + (lead ? 1 : 0);
   };
 
   while (!pending.empty()) {
@@ -913,34 +915,34 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
       build_tile_stage(&a);
       continue;
     }
-    // ---- multi-GPU: a non-diagonal target on a global physical bit needs a remap first
+    // ---- everything executable in the current layout goes first: gates with a non-diagonal target on a global
+    // physical bit (and whatever depends on them) are skipped by the stage builder, so an exchange is only paid for
+    // when no gate at all can run without it
+    if (build_tile_stage(nullptr)) continue;
+    // ---- multi-GPU remap: the head-of-line gate targets a global bit.  Swap it with the local bit (among the top 8:
+    // large contiguous chunks) whose logical occupant is needed latest as a non-diagonal target
     {
       Gate g0 = to_phys(plan.gates[pending[0]]);
       uint64_t gt = g0.target_mask() & ~local_mask;
-      if (gt) {
-        int gbit = 63 - __builtin_clzll(gt);
-        std::vector<int> logical_of(n);
-        for (int b = 0; b < n; ++b) logical_of[perm[b]] = b;
-        // swap with the local bit (among the top 8: large contiguous chunks) whose logical occupant is
-        // needed latest as a non-diagonal target
-        int best = -1; size_t best_next = 0;
-        for (int cand = nl - 1; cand >= std::max(L, nl - 8) && cand >= 0; --cand) {
-          if ((g0.target_mask() >> cand) & 1) continue;
-          int lb = logical_of[cand];
-          size_t next = pending.size() + 1;
-          for (size_t i = 0; i < pending.size() && i < 2048; ++i)
-            if ((plan.gates[pending[i]].target_mask() >> lb) & 1) { next = i; break; }
-          if (best < 0 || next > best_next) { best = cand; best_next = next; }
-        }
-        if (best < 0) { plan.error = "no local qubit available for remap"; return QCB_ERR_INVALID; }
-        Stage s; s.kind = S_EXCHANGE; s.gbit = gbit; s.lbit = best;
-        plan.stages.push_back(s);
-        plan.n_exchanges++;
-        std::swap(perm[logical_of[gbit]], perm[logical_of[best]]);
-        continue;
+      if (!gt) { plan.error = "scheduler made no progress"; return QCB_ERR_INVALID; }
+      int gbit = 63 - __builtin_clzll(gt);
+      std::vector<int> logical_of(n);
+      for (int b = 0; b < n; ++b) logical_of[perm[b]] = b;
+      int best = -1; size_t best_next = 0;
+      for (int cand = nl - 1; cand >= std::max(L, nl - 8) && cand >= 0; --cand) {
+        if ((g0.target_mask() >> cand) & 1) continue;
+        int lb = logical_of[cand];
+        size_t next = pending.size() + 1;
+        for (size_t i = 0; i < pending.size() && i < 4096; ++i)
+          if ((plan.gates[pending[i]].target_mask() >> lb) & 1) { next = i; break; }
+        if (best < 0 || next > best_next) { best = cand; best_next = next; }
       }
+      if (best < 0) { plan.error = "no local qubit available for remap"; return QCB_ERR_INVALID; }
+      Stage s; s.kind = S_EXCHANGE; s.gbit = gbit; s.lbit = best;
+      plan.stages.push_back(s);
+      plan.n_exchanges++;
+      std::swap(perm[logical_of[gbit]], perm[logical_of[best]]);
     }
-    build_tile_stage(nullptr);
   }
 
   plan.perm_out = perm;

@@ -115,6 +115,8 @@ struct qcb_sim {
   qcb_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timing_pending = false;
   cudaEvent_t xev0 = nullptr, xev1 = nullptr;
+  cudaStream_t xstream = nullptr;                 // copy-back stream of the qubit exchange
+  cudaEvent_t xrecv[2] = {nullptr, nullptr}, xcopy[2] = {nullptr, nullptr}, xpack[2] = {nullptr, nullptr};
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;
   std::string err;
   std::recursive_mutex mu;
@@ -219,36 +221,69 @@ int allreduce_sum(qcb_sim* h, double* dev, size_t count) {
 
 // ---- exchange: swap global physical bit gbit with local physical bit lbit
 int do_exchange(qcb_sim* h, int gbit, int lbit) {
+  // Swap global physical bit gbit with local physical bit lbit: rank r and partner r ^ 2^j exchange the half of their
+  // slice whose bit lbit differs from their own rank bit.  The half moves in chunks of <= 512 MiB through a two-deep
+  // software pipeline: chunk c+1 is gathered into a send buffer (k_pack_half; skipped when the chunk is contiguous in
+  // the state) and chunk c-1 is scattered back from its receive buffer (k_unpack_half / memcpy) on a second stream
+  // while chunk c is on the wire as ONE ncclSend/ncclRecv pair (NCCL moves few large messages much faster than many
+  // small ones: profiles/r1d_exchange_bench.log).
   const int nl = h->cfg.n_local;
   const int j = gbit - nl;
   const int myb = (h->cfg.rank >> j) & 1;
   const int peer = h->cfg.rank ^ (1 << j);
   const int want = 1 - myb;                         // the half of MY slice that moves: bit lbit == !myb
-  const uint64_t half = h->local_count >> 1;
+  const uint64_t half = h->local_count >> 1, block = 1ULL << lbit;
   if (!h->xbuf) {
-    uint64_t cnt = std::min<uint64_t>(half, 1ULL << 26);          // <= 1 GiB send + 1 GiB recv staging
-    CU(h, cudaMalloc(&h->xbuf, 2 * cnt * sizeof(double2)));
+    static const int xlog = [] { const char* e = getenv("QCB_XCHUNK_LOG2"); int v = e ? atoi(e) : 25; return v < 4 ? 4 : (v > 28 ? 28 : v); }();
+    uint64_t cnt = std::min<uint64_t>(half, 1ULL << xlog);        // 2 send + 2 receive buffers of <= 512 MiB
+    CU(h, cudaMalloc(&h->xbuf, 4 * cnt * sizeof(double2)));
     h->xbuf_count = cnt;
+    CU(h, cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CU(h, cudaEventCreateWithFlags(&h->xrecv[i], cudaEventDisableTiming));
+      CU(h, cudaEventCreateWithFlags(&h->xcopy[i], cudaEventDisableTiming));
+      CU(h, cudaEventCreateWithFlags(&h->xpack[i], cudaEventDisableTiming));
+    }
   }
+  const uint64_t chunk = h->xbuf_count;              // amplitudes of the moving half per chunk
+  const uint64_t n_chunks = (half + chunk - 1) / chunk;
+  const bool contiguous = block >= chunk;            // a chunk lies inside one contiguous block of the state
+  auto state_pos = [&](uint64_t first) {             // address of moving-half offset `first` (contiguous case)
+    const uint64_t bi = first >> lbit, in = first & (block - 1);
+    return h->state + (((bi << 1) | (uint64_t)want) << lbit) + in;
+  };
+  auto sendbuf = [&](uint64_t c) { return h->xbuf + (c & 1) * chunk; };
+  auto recvbuf = [&](uint64_t c) { return h->xbuf + (2 + (c & 1)) * chunk; };
+  auto count_of = [&](uint64_t c) { return std::min<uint64_t>(chunk, half - c * chunk); };
   CU(h, cudaEventRecord(h->xev0, h->stream));
-  double2* sendbuf = h->xbuf;
-  double2* recvbuf = h->xbuf + h->xbuf_count;
-  const bool contiguous = (lbit == nl - 1);
-  for (uint64_t first = 0; first < half; first += h->xbuf_count) {
-    const uint64_t cnt = std::min<uint64_t>(h->xbuf_count, half - first);
-    const double2* src = sendbuf;
-    if (contiguous) src = h->state + ((uint64_t)want << lbit) + first;   // top local bit: the half is one block
-    else CU(h, launch_pack_half(h->state, sendbuf, first, cnt, lbit, want, red_grid(h), h->stream));
+  CU(h, cudaStreamWaitEvent(h->xstream, h->xev0, 0));                       // the state is final before anything is gathered
+  auto pack = [&](uint64_t c) -> int {
+    if (contiguous) return QCB_OK;
+    CU(h, launch_pack_half(h->state, sendbuf(c), c * chunk, count_of(c), lbit, want, red_grid(h), h->xstream));
+    CU(h, cudaEventRecord(h->xpack[c & 1], h->xstream));
+    h->stats.n_kernel_launches++;
+    return QCB_OK;
+  };
+  RET(pack(0));
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    const int sb = (int)(c & 1);
+    const uint64_t cnt = count_of(c);
+    if (!contiguous) CU(h, cudaStreamWaitEvent(h->stream, h->xpack[sb], 0));
+    if (c >= 2) CU(h, cudaStreamWaitEvent(h->stream, h->xcopy[sb], 0));       // receive buffer free again
     NC(h, g_nccl.GroupStart());
-    NC(h, g_nccl.Send(src, cnt * 2, ncclDouble, peer, h->comm, h->stream));
-    NC(h, g_nccl.Recv(recvbuf, cnt * 2, ncclDouble, peer, h->comm, h->stream));
+    NC(h, g_nccl.Send(contiguous ? state_pos(c * chunk) : sendbuf(c), cnt * 2, ncclDouble, peer, h->comm, h->stream));
+    NC(h, g_nccl.Recv(recvbuf(c), cnt * 2, ncclDouble, peer, h->comm, h->stream));
     NC(h, g_nccl.GroupEnd());
-    // partner's moving half (its bit lbit == myb) lands in MY moving positions (bit lbit == !myb)
-    if (contiguous) CU(h, cudaMemcpyAsync(h->state + ((uint64_t)want << lbit) + first, recvbuf, cnt * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
-    else CU(h, launch_unpack_half(h->state, recvbuf, first, cnt, lbit, want, red_grid(h), h->stream));
-    h->stats.n_kernel_launches += contiguous ? 0 : 2;
+    CU(h, cudaEventRecord(h->xrecv[sb], h->stream));
+    if (c + 1 < n_chunks) RET(pack(c + 1));          // queued before the scatter of chunk c: overlaps the wire time of chunk c
+    // partner's moving half (its bit lbit == myb) lands in MY moving positions (bit lbit == !myb), vacated by the send
+    CU(h, cudaStreamWaitEvent(h->xstream, h->xrecv[sb], 0));
+    if (contiguous) CU(h, cudaMemcpyAsync(state_pos(c * chunk), recvbuf(c), cnt * sizeof(double2), cudaMemcpyDeviceToDevice, h->xstream));
+    else { CU(h, launch_unpack_half(h->state, recvbuf(c), c * chunk, cnt, lbit, want, red_grid(h), h->xstream)); h->stats.n_kernel_launches++; }
+    CU(h, cudaEventRecord(h->xcopy[sb], h->xstream));
     h->stats.bytes_exchanged += cnt * sizeof(double2);
   }
+  for (uint64_t i = 0; i < 2 && i < n_chunks; ++i) CU(h, cudaStreamWaitEvent(h->stream, h->xcopy[i], 0));
   CU(h, cudaEventRecord(h->xev1, h->stream));
   CU(h, cudaEventSynchronize(h->xev1));
   float ms = 0;
@@ -728,6 +763,8 @@ int32_t qcb_destroy(qcb_handle h) {
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < 2; ++i) { if (h->xrecv[i]) cudaEventDestroy(h->xrecv[i]); if (h->xcopy[i]) cudaEventDestroy(h->xcopy[i]); if (h->xpack[i]) cudaEventDestroy(h->xpack[i]); }
+  if (h->xstream) cudaStreamDestroy(h->xstream);
   if (h->xev0) cudaEventDestroy(h->xev0);
   if (h->xev1) cudaEventDestroy(h->xev1);
   if (h->tev0) cudaEventDestroy(h->tev0);

@@ -207,6 +207,42 @@ def test_config3_brickwork_matches_c_oracle(n):
         assert np.max(np.abs(got_u - want)) <= TOL
 
 
+def _inverse_ops(ops):
+    """Exact inverse of a brickwork op list: reverse order, RX/RZ angles negated, H / CNOT / CZ are involutions."""
+    inv = []
+    for op in reversed(ops):
+        t, p = op["operation-type"], dict(op["operation-params"])
+        if t in ("rx", "rz"):
+            p["angle"] = -p["angle"]
+        else:
+            assert t in ("h", "cnot", "cz"), t
+        inv.append({"operation-type": t, "operation-params": p})
+    return inv
+
+
+def test_config3_full_size_properties_30q():
+    """BASELINE.json's full size (30 qubits, 16 GiB state) through size-independent properties: the norm stays 1, 4096
+    spot amplitudes are stable under re-execution, and circuit followed by its exact inverse returns |0...0> to 1e-10
+    (890 + 890 gates through the fused executor; the C oracle would need minutes at this size)."""
+    n = 30
+    circ = C.random_brickwork_circuit(n, 20)
+    ops = circ["operations"]
+    idx = np.random.default_rng(30).integers(0, 1 << n, 4096)
+    with L.StateVector(n) as sv:
+        sv.apply_ops(ops)
+        assert abs(sv.norm2() - 1.0) <= 1e-10
+        spot = sv.get_amplitudes(idx)
+        assert np.max(np.abs(spot)) < 1e-3 and np.any(np.abs(spot) > 0)          # a scrambled state, not a basis state
+        sv.apply_ops(_inverse_ops(ops))
+        assert abs(sv.norm2() - 1.0) <= 1e-10
+        back = sv.get_amplitudes(np.concatenate([[0], idx]))
+        assert abs(back[0] - 1.0) <= 1e-10
+        assert np.max(np.abs(back[1:][idx != 0])) <= 1e-10
+        sv.set_zero()
+        sv.apply_ops(ops)
+        assert np.array_equal(sv.get_amplitudes(idx), spot)                        # deterministic re-execution
+
+
 def test_tutorial_golden_cases_on_gpu():
     """The reference's own recorded runs (doc/tutorial.md) replayed through the CUDA path."""
     with open(os.path.join(GOLDEN, "tutorial_cases.json")) as f:
