@@ -293,6 +293,10 @@ __device__ __forceinline__ void dmma_round_run(uint32_t tile_s, const uint4* lan
   }
 }
 
+// Pacing of the mover (QCB_MOVER_PAUSE_NS, experiment knob): nanoseconds slept between groups of 8 element copies so that a
+// burst of mover LDGSTS / LDS.128 does not monopolise the LSU pipe the consumers' fragment loads depend on.  0 = off.
+__device__ unsigned g_mover_pause_ns;
+
 // ------------------------------------------------------------------ LSU mover, specialised
 // Tiles of 128 * KE amplitudes with 256-byte runs and the default layout (the common case): mover thread mt moves
 // elements mt + 128 k (k < KE); their global run offsets stay in registers for the whole sweep and the swizzled
@@ -304,6 +308,7 @@ __device__ __forceinline__ void mover_fast(double2* __restrict__ state, const ui
                                            uint64_t* full, uint64_t* done) {
   const uint32_t low = mt & 15u;
   const uint32_t s_mt = swz(mt, 0u) << 4;
+  const unsigned pause = g_mover_pause_ns;
   DBG_DECL;
   uint32_t roff[KE];                                           // run offsets in units of 256 bytes
 #pragma unroll
@@ -316,8 +321,10 @@ __device__ __forceinline__ void mover_fast(double2* __restrict__ state, const ui
       const uint32_t bs = smem_s + (j % nbuf) * tile_bytes;
       if (!DBG_ON(4)) {
 #pragma unroll
-        for (uint32_t k = 0; k < KE; ++k)
+        for (uint32_t k = 0; k < KE; ++k) {
           cp_async16_s(bs + (s_mt ^ (swz(128u * k, 0u) << 4)), gb + ((uint64_t)roff[k] << 8));
+          if (pause && (k & 7u) == 7u) __nanosleep(pause);
+        }
       }
       cp_async_mbar_arrive(full + (j % nbuf));
       PF_ADD(PF_M_LOAD);
@@ -336,6 +343,7 @@ __device__ __forceinline__ void mover_fast(double2* __restrict__ state, const ui
         for (uint32_t u = 0; u < 8; ++u) v[u] = lds_f64x2(bs + (s_mt ^ (swz(128u * (k0 + u), 0u) << 4)));
 #pragma unroll
         for (uint32_t u = 0; u < 8; ++u) __stcs(reinterpret_cast<double2*>(gb + ((uint64_t)roff[k0 + u] << 8)), v[u]);
+        if (pause) __nanosleep(pause);
       }
       PF_ADD(PF_M_STORE);
     }
@@ -601,6 +609,8 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   static const int dbg_once = [] { const char* e = getenv("QCB_TILE_DBG"); int v = e ? atoi(e) : 0; cudaMemcpyToSymbol(g_tile_dbg, &v, sizeof v); return v; }();
   (void)dbg_once;
 #endif
+  static const unsigned pause_once = [] { const char* e = getenv("QCB_MOVER_PAUSE_NS"); unsigned v = e ? (unsigned)atoi(e) : 0u; cudaMemcpyToSymbol(g_mover_pause_ns, &v, sizeof v); return v; }();
+  (void)pause_once;
   static const bool no_tma = getenv("QCB_NO_TMA") != nullptr;
   static const CUtensorMap dummy_map = {};
   const uint32_t use_tma = (!no_tma && maps && sc.c >= 3 && sc.c <= 11 && maps->valid[sc.c]) ? 1u : 0u;
