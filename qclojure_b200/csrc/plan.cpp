@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace qcb {
@@ -68,6 +69,7 @@ Config config_from(const qcb_config& c) {
   k.max_stage_rounds = c.max_stage_rounds;
   k.dense_mma = (c.dense_mma == 2) ? 0 : 1;
   k.tma = (c.tile_mover == 2) ? 1 : 0;
+  if (const char* e = std::getenv("QCB_WINDOW_SEARCH")) k.window_search = std::atoi(e);   // 0 = greedy tiles / rounds only
   return k;
 }
 
@@ -722,62 +724,94 @@ static void fuse_round(Round& rd) {
   rd.gates.swap(out);
 }
 
+// Per-gate facts a round candidate needs, computed once per round (not per candidate).
+struct RoundGate {
+  uint64_t t, d, bits, want;   // non-diagonal targets, diagonal operands, all bits touched, tile-local part of them
+  bool can_be_pure, later, reflect;
+};
+
+// One candidate round: scan the pending gates in order and take every gate that fits slot bits inside `Rcap` (at most
+// MAX_SLOT_BITS of them).  Returns indices into the pending list (taken / rest, order preserved) - no gate is copied.
+static void pick_round(const Config& cfg, const Stage& st, const std::vector<RoundGate>& pg, uint64_t Rcap, std::vector<int>& taken,
+                       std::vector<int>& rest, uint64_t& R_out) {
+  const int rmax = std::min(MAX_SLOT_BITS, st.m);
+  const bool use_mma = cfg.dense_mma && st.m >= 6;
+  uint64_t R = 0, touched = 0, bx = 0, bz = 0;          // touched = bits of accepted gates; bx / bz = Blocker state
+  taken.clear();
+  rest.clear();
+  auto fits = [&](uint64_t Rn) { return popc(Rn) <= rmax && (Rn & ~Rcap) == 0; };
+  for (size_t gi = 0; gi < pg.size(); ++gi) {
+    const RoundGate& g = pg[gi];
+    auto block = [&]() { bx |= g.t; bz |= g.d; rest.push_back((int)gi); };
+    auto accept = [&](uint64_t Rn) { R = Rn; touched |= g.bits; taken.push_back((int)gi); };
+    if ((g.t & (bx | bz)) || (g.d & bx)) { block(); continue; }
+    // prefer making the gate *pure* (every tile-local bit it touches becomes a slot bit): pure gates fold into
+    // the round's dense block for free; controls / diagonal operands on tile-id or rank bits can never be slots
+    if (use_mma && !g.reflect) {
+      // tensor-core round: every non-slot bit a gate touches becomes a condition bit (2^k matrix variants)
+      auto conds_after = [&](uint64_t Rn) { return popc((touched | g.bits) & ~Rn); };
+      if (g.can_be_pure && fits(R | g.want) && conds_after(R | g.want) <= MAX_COND_BITS) { accept(R | g.want); continue; }
+      // a diagonal gate that does not fit as pure now: defer it to a later round of this stage if one of its
+      // bits will be a slot there anyway (a later gate targets it); otherwise let it ride along as condition bits
+      if (g.can_be_pure && g.t == 0 && g.later) { block(); continue; }
+      if (fits(R | g.t) && conds_after(R | g.t) <= MAX_COND_BITS) accept(R | g.t);
+      else if (taken.empty() && Rcap == ~0ULL) accept(R | g.t);     // always make progress (falls back to the interpreter if needed)
+      else block();
+      continue;
+    }
+    if (g.can_be_pure && fits(R | g.want)) { accept(R | g.want); continue; }
+    if (g.can_be_pure && g.t == 0 && g.later) { block(); continue; }
+    if (fits(R | g.t)) accept(R | g.t);
+    else block();
+  }
+  R_out = R;
+}
+
 // Form shared-memory rounds from the gates of one stage (gates already in ext space; targets < m).
 static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates) {
   std::vector<Gate> pending = gates;
-  const int rmax = std::min(MAX_SLOT_BITS, st.m);
+  const bool search = cfg.fusion && cfg.window_search && cfg.dense_mma && st.m >= 6;
+  const uint64_t tile_mask = (1ULL << st.m) - 1ULL;
+  std::vector<RoundGate> pg;
+  std::vector<int> taken, rest, ctaken, crest;
   while (!pending.empty()) {
-    Round rd;
-    uint64_t R = 0;
-    Blocker bl;
-    std::vector<Gate> rest;
-    const uint64_t tile_mask = (1ULL << st.m) - 1ULL;
-    const bool use_mma = cfg.dense_mma && st.m >= 6;
-    for (size_t gi = 0; gi < pending.size(); ++gi) {
-      const Gate& g = pending[gi];
-      if (bl.conflicts(g)) { bl.block(g); rest.push_back(g); continue; }
-      const uint64_t t = g.target_mask();
-      // prefer making the gate *pure* (every tile-local bit it touches becomes a slot bit): pure gates fold into
-      // the round's dense block for free; controls / diagonal operands on tile-id or rank bits can never be slots
-      const uint64_t all = (t | g.diag_mask());
-      const uint64_t want = all & tile_mask;
-      const bool can_be_pure = cfg.fusion && (all & ~tile_mask) == 0 && g.kind != G_DPOP1 && g.kind != G_REFLECT;
-      if (use_mma && g.kind != G_REFLECT) {
-        // tensor-core round: every non-slot bit a gate touches becomes a condition bit (2^k matrix variants)
-        auto conds_after = [&](uint64_t Rn) {
-          uint64_t c = (gate_bits(g) & ~Rn);
-          for (const Gate& h : rd.gates) c |= gate_bits(h) & ~Rn;
-          return popc(c);
-        };
-        if (can_be_pure && popc(R | want) <= rmax && conds_after(R | want) <= MAX_COND_BITS) { R |= want; rd.gates.push_back(g); continue; }
-        if (can_be_pure && t == 0) {
-          bool later = false;
-          for (size_t k = gi + 1; k < pending.size() && !later; ++k) later = (pending[k].target_mask() & want) != 0;
-          if (later) { bl.block(g); rest.push_back(g); continue; }
-        }
-        if (popc(R | t) <= rmax && conds_after(R | t) <= MAX_COND_BITS) { R |= t; rd.gates.push_back(g); }
-        else if (rd.gates.empty()) { R |= t; rd.gates.push_back(g); }     // always make progress (falls back to the interpreter if needed)
-        else { bl.block(g); rest.push_back(g); }
-        continue;
-      }
-      if (can_be_pure && popc(R | want) <= rmax) { R |= want; rd.gates.push_back(g); continue; }
-      if (can_be_pure && t == 0) {
-        // a diagonal gate that does not fit as pure now: defer it to a later round of this stage if one of its
-        // bits will be a slot there anyway (a later gate targets it); otherwise let it ride along as a masked phase
-        bool later = false;
-        for (size_t k = gi + 1; k < pending.size() && !later; ++k) later = (pending[k].target_mask() & want) != 0;
-        if (later) { bl.block(g); rest.push_back(g); continue; }
-      }
-      if (popc(R | t) <= rmax) { R |= t; rd.gates.push_back(g); }
-      else { bl.block(g); rest.push_back(g); }
+    pg.resize(pending.size());
+    uint64_t later_targets = 0, targeted = 0;
+    for (size_t i = pending.size(); i-- > 0;) {
+      const Gate& g = pending[i];
+      RoundGate& r = pg[i];
+      r.t = g.target_mask(); r.d = g.diag_mask(); r.bits = r.t | r.d; r.want = r.bits & tile_mask;
+      r.reflect = g.kind == G_REFLECT;
+      r.can_be_pure = cfg.fusion && (r.bits & ~tile_mask) == 0 && g.kind != G_DPOP1 && g.kind != G_REFLECT;
+      r.later = (later_targets & r.want) != 0;       // some later gate targets one of its bits
+      later_targets |= r.t;
+      targeted |= r.t;
     }
+    uint64_t R = 0;
+    pick_round(cfg, st, pg, ~0ULL, taken, rest, R);             // greedy: slot bits follow the first gates in line
+    if (search && pending.size() > taken.size()) {
+      // every triple of tile-local bits some pending gate targets is a candidate slot set; keep the round that absorbs
+      // most gates (a tensor-core round costs the same however many gates it folds)
+      std::vector<int> tb;
+      for (int b = 0; b < st.m; ++b) if ((targeted >> b) & 1) tb.push_back(b);
+      uint64_t cR = 0;
+      for (size_t i = 0; i < tb.size(); ++i) for (size_t j = i + 1; j < tb.size(); ++j) for (size_t k = j + 1; k < tb.size(); ++k) {
+        const uint64_t cap = (1ULL << tb[i]) | (1ULL << tb[j]) | (1ULL << tb[k]);
+        pick_round(cfg, st, pg, cap, ctaken, crest, cR);
+        if (ctaken.size() > taken.size()) { taken.swap(ctaken); rest.swap(crest); R = cR; }
+      }
+    }
+    Round rd;
+    for (int i : taken) rd.gates.push_back(pending[i]);
+    std::vector<Gate> next;
+    next.reserve(rest.size());
+    for (int i : rest) next.push_back(std::move(pending[i]));
     // unfused mode keeps exactly one gate per round anyway (one gate per stage)
     for (int b = 0; b < st.m; ++b) if ((R >> b) & 1) rd.slot_pos.push_back(b);
-    // pad with extra slot bits when the tile is so small that fewer than 8 lanes exist: not needed
     if (dmma_eligible(cfg, st, rd)) build_dmma_round(cfg, st, rd);
     else if (cfg.fusion) fuse_round(rd);
     st.rounds.push_back(std::move(rd));
-    pending.swap(rest);
+    pending.swap(next);
   }
 }
 
@@ -812,11 +846,12 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
 
   // Build one fused tile stage from the head of `pending`.  `lead` (optional) is an op that must run
   // first on every amplitude (the affine pass of a Grover diffusion).
-  auto build_tile_stage = [&](const Gate* lead) -> size_t {
-    Stage st; st.kind = S_TILE; st.m = m; st.L = L;
-    uint64_t A = 0; for (int k = 0; k < L; ++k) A |= 1ULL << k;
+  // Select the gates of one sweep from the head of `pending`.  A_init = tile bits fixed in advance; with `fixed` the tile
+  // may not grow (every target must already be a tile bit), otherwise bits are added greedily in gate order.
+  auto select_gates = [&](const Gate* lead, uint64_t A_init, bool fixed, std::vector<int>& taken, uint64_t& A_out) {
+    uint64_t A = A_init;
     Blocker bl; int cost = lead ? 4 : 0;
-    std::vector<int> taken;
+    taken.clear();
     const size_t window = cfg.fusion ? 4096 : (lead ? 0 : 1);
     for (size_t i = 0; i < pending.size() && i < window; ++i) {
       const Gate& lg = plan.gates[pending[i]];
@@ -828,14 +863,14 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
         continue;
       }
       uint64_t need = g.target_mask() & ~A;
+      if (fixed && need) { bl.block(g); continue; }
       // diagonal gates do not need tile bits, but when the tile has room their operand bits are taken in so
-      // that the round fuser can fold them into a dense block (otherwise they ride along as masked phases)
-      if (cfg.fusion && (g.kind == G_DMASK || g.kind == G_DTAB1) && popc(g.diag_mask()) <= 2) {
+      // that the round fuser can fold them into a dense block (otherwise they ride along as condition bits)
+      if (!fixed && cfg.fusion && (g.kind == G_DMASK || g.kind == G_DTAB1) && popc(g.diag_mask()) <= 2) {
         const uint64_t soft = g.diag_mask() & local_mask & ~A & ~need;
         if (popc(A) + popc(need) + popc(soft) <= m - 1) need |= soft;
         else if (soft && !taken.empty() && !(g.kind == G_DMASK && g.m[0].re == -1.0 && g.m[0].im == 0.0)) {
-          // no room: a general phase on a bit outside the tile would cost a full complex multiply of every
-          // amplitude in this sweep; defer it to the sweep that owns the bit (sign flips stay: they are cheap)
+          // no room: defer a general phase on a bit outside the tile to the sweep that owns the bit (sign flips stay)
           bl.block(g);
           continue;
         }
@@ -845,6 +880,26 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
         A |= need; cost += c; taken.push_back((int)i);
       } else {
         bl.block(g);
+      }
+    }
+    A_out = A;
+  };
+
+  auto build_tile_stage = [&](const Gate* lead) -> size_t {
+    Stage st; st.kind = S_TILE; st.m = m; st.L = L;
+    uint64_t low = 0; for (int k = 0; k < L; ++k) low |= 1ULL << k;
+    std::vector<int> taken;
+    uint64_t A = low;
+    select_gates(lead, low, false, taken, A);                // greedy: the tile follows the first gates in line
+    if (cfg.fusion && cfg.window_search && !lead && nl > m) {
+      // candidate tiles = every contiguous window of m - L physical bits above the low bits (nearest-neighbour circuits
+      // leave seams between greedy tiles whose gates then straggle in low-yield sweeps); keep whichever absorbs most gates
+      std::vector<int> cand_taken;
+      for (int p = L; p + (m - L) <= nl; ++p) {
+        uint64_t Aw = low, Aout = 0;
+        for (int b = p; b < p + (m - L); ++b) Aw |= 1ULL << b;
+        select_gates(lead, Aw, true, cand_taken, Aout);
+        if (cand_taken.size() > taken.size()) { taken = cand_taken; A = Aw; }
       }
     }
     if (taken.empty() && !lead) return 0;          // nothing executable in the current layout (multi-GPU: exchange first)

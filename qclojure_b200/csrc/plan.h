@@ -119,6 +119,7 @@ struct Config {
   int max_stage_cost = 0;
   int max_stage_rounds = 0;
   int dense_mma = 1;           // rounds as dense 8x8 complex blocks on the fp64 tensor cores
+  int window_search = 1;       // stage builder also tries contiguous tile windows and keeps the best yield
   int tma = 0;                 // tiles move by TMA tensor copies (layout follows the hardware 128-byte swizzle)
   int threads = 256;
 };

@@ -51,6 +51,21 @@ void emu_perm_out(Emu* e, int32_t* out) { for (size_t b = 0; b < e->plan.perm_ou
 uint64_t emu_stage_num_gates(Emu* e, uint64_t i) { return e->plan.stages[i].src_gates.size(); }
 uint64_t emu_stage_num_rounds(Emu* e, uint64_t i) { return e->plan.stages[i].rounds.size(); }
 double emu_stage_fraction(Emu* e, uint64_t i) { return e->plan.stages[i].sweep_fraction; }
+// per-round detail for plan analysis: number of gates, slot bits (as a mask over tile-local positions), condition bits
+uint64_t emu_round_info(Emu* e, uint64_t si, uint64_t r, uint64_t* n_gates, uint64_t* slot_mask, uint64_t* n_cond) {
+  const Round& rd = e->plan.stages[si].rounds[r];
+  *n_gates = rd.gates.size();
+  uint64_t m = 0;
+  for (int p : rd.slot_pos) m |= 1ULL << p;
+  *slot_mask = m;
+  *n_cond = rd.cond_pos.size();
+  return rd.dmma ? 1 : 0;
+}
+uint64_t emu_stage_tile_mask(Emu* e, uint64_t si) {
+  uint64_t m = 0;
+  for (int p : e->plan.stages[si].tile_pos) m |= 1ULL << p;
+  return m;
+}
 
 // bank-conflict audit of one stage: worst number of distinct 16-byte bank-group collisions in any
 // quarter-warp of any round (1 = conflict free)
