@@ -69,7 +69,8 @@ Config config_from(const qcb_config& c) {
   k.max_stage_rounds = c.max_stage_rounds;
   k.dense_mma = (c.dense_mma == 2) ? 0 : 1;
   k.tma = (c.tile_mover == 2) ? 1 : 0;
-  if (const char* e = std::getenv("QCB_WINDOW_SEARCH")) k.window_search = std::atoi(e);   // 0 = greedy tiles / rounds only
+  if (const char* e = std::getenv("QCB_WINDOW_SEARCH")) k.window_search = std::atoi(e);
+  if (const char* e = std::getenv("QCB_ROUND_YIELD_PCT")) k.round_yield_pct = std::atoi(e);   // 0 = greedy tiles / rounds only
   return k;
 }
 
@@ -507,7 +508,8 @@ static void small_apply(const Gate& g, const std::vector<int>& slot_pos, std::ve
   auto sbit = [&](int pos) { for (int j = 0; j < r; ++j) if (slot_pos[j] == pos) return j; return -1; };
   auto smask = [&](uint64_t m) { uint32_t o = 0; for (int j = 0; j < r; ++j) if ((m >> slot_pos[j]) & 1) o |= 1u << j; return o; };
   auto outside_ok = [&](uint64_t mask, uint64_t val) { const uint64_t mo = mask & ~slot_mask; return (fixed & mo) == (val & mo); };
-  std::vector<cplx> o = v;
+  cplx o[1 << MAX_SLOT_BITS];                       // no heap traffic: this runs ~10^5 times per plan
+  for (int s = 0; s < dim; ++s) o[s] = v[s];
   switch (g.kind) {
     case G_MAT1: {
       if (!outside_ok(g.cmask, g.cmask)) break;
@@ -569,7 +571,7 @@ static void small_apply(const Gate& g, const std::vector<int>& slot_pos, std::ve
     }
     default: break;
   }
-  v.swap(o);
+  for (int s = 0; s < dim; ++s) v[s] = o[s];
 }
 
 // bits of a gate that are read or written (ext space)
@@ -768,13 +770,13 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
 }
 
 // Form shared-memory rounds from the gates of one stage (gates already in ext space; targets < m).
-static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates) {
+static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, int max_rounds) {
   std::vector<Gate> pending = gates;
   const bool search = cfg.fusion && cfg.window_search && cfg.dense_mma && st.m >= 6;
   const uint64_t tile_mask = (1ULL << st.m) - 1ULL;
   std::vector<RoundGate> pg;
   std::vector<int> taken, rest, ctaken, crest;
-  while (!pending.empty()) {
+  while (!pending.empty() && (int)st.rounds.size() < std::max(1, max_rounds)) {
     pg.resize(pending.size());
     uint64_t later_targets = 0, targeted = 0;
     for (size_t i = pending.size(); i-- > 0;) {
@@ -801,8 +803,11 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates) 
         if (ctaken.size() > taken.size()) { taken.swap(ctaken); rest.swap(crest); R = cR; }
       }
     }
+    // a thin round costs as much as a full one: leave its gates to the next sweep, whose tile search starts afresh
+    if (search && cfg.round_yield_pct > 0 && st.rounds.size() >= 2 && !st.absorbed.empty() &&
+        taken.size() * 100 * st.rounds.size() < (size_t)cfg.round_yield_pct * st.absorbed.size()) break;
     Round rd;
-    for (int i : taken) rd.gates.push_back(pending[i]);
+    for (int i : taken) { rd.gates.push_back(pending[i]); st.absorbed.push_back(pending[i].uid); }
     std::vector<Gate> next;
     next.reserve(rest.size());
     for (int i : rest) next.push_back(std::move(pending[i]));
@@ -820,11 +825,13 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
   const int n = cfg.n_total, nl = cfg.n_local, m = std::min(cfg.tile_bits, nl), L = std::min(cfg.low_bits, m);
   std::vector<int> perm(n);
   for (int b = 0; b < n; ++b) perm[b] = perm_in.empty() ? b : perm_in[b];
-  // Budget of one fused sweep.  A sweep costs ~3.5 ms of HBM/pipeline time plus ~2 ms per tensor-core round at 30 qubits
-  // (profiles/r1d_sweep_budgets.log), so gates/s keeps rising until the tile bits, not the budget, end the sweep; 12 rounds
-  // is what the per-round tables leave room for next to three 64 KB tile buffers in shared memory.
+  // Budget of one fused sweep.  At 30 qubits a sweep costs ~2.5 ms of HBM / pipeline time plus ~2.1 ms per tensor-core
+  // round (profiles/r1e_round_budgets.log).  Long stages end in thin rounds (3-4 gates) that cost as much as full ones,
+  // so a stage stops after 5 rounds, or earlier when the next round would hold less than half the stage's average
+  // (round_yield_pct); the next sweep's tile search then starts afresh on the leftovers: 72 rounds in 16 sweeps
+  // instead of 88 in 10 for the benchmark circuit.
   const int max_cost = cfg.max_stage_cost > 0 ? cfg.max_stage_cost : 800;
-  const int max_rounds = cfg.max_stage_rounds > 0 ? cfg.max_stage_rounds : 12;
+  const int max_rounds = cfg.max_stage_rounds > 0 ? cfg.max_stage_rounds : 5;
   const double sweep_bytes = 32.0 * std::ldexp(1.0, nl);
   const uint64_t local_mask = (nl >= 64) ? ~0ULL : ((1ULL << nl) - 1);
   const uint64_t tileid_mask = ((nl - m) >= 64) ? ~0ULL : ((1ULL << (nl - m)) - 1);
@@ -846,40 +853,56 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
 
   // Build one fused tile stage from the head of `pending`.  `lead` (optional) is an op that must run
   // first on every amplitude (the affine pass of a Grover diffusion).
+  // Per-gate facts the stage selection needs (physical bit space), computed once per stage for all tile candidates.
+  struct StageGate { uint64_t t, d; int cost; bool reflect, soft_ok, sign_flip; };
+  std::vector<StageGate> sg;
+  auto prepare_stage_gates = [&](size_t window) {
+    const size_t cnt = std::min(pending.size(), window);
+    sg.resize(cnt);
+    for (size_t i = 0; i < cnt; ++i) {
+      const Gate& lg = plan.gates[pending[i]];
+      StageGate& r = sg[i];
+      r.reflect = lg.kind == G_REFLECT;
+      if (r.reflect) { r.t = r.d = 0; r.cost = 0; r.soft_ok = r.sign_flip = false; continue; }
+      const Gate g = to_phys(lg);
+      r.t = g.target_mask(); r.d = g.diag_mask(); r.cost = gate_cost(g);
+      r.soft_ok = (g.kind == G_DMASK || g.kind == G_DTAB1) && popc(r.d) <= 2;
+      r.sign_flip = g.kind == G_DMASK && g.m[0].re == -1.0 && g.m[0].im == 0.0;
+    }
+  };
+
   // Select the gates of one sweep from the head of `pending`.  A_init = tile bits fixed in advance; with `fixed` the tile
   // may not grow (every target must already be a tile bit), otherwise bits are added greedily in gate order.
   auto select_gates = [&](const Gate* lead, uint64_t A_init, bool fixed, std::vector<int>& taken, uint64_t& A_out) {
-    uint64_t A = A_init;
-    Blocker bl; int cost = lead ? 4 : 0;
+    uint64_t A = A_init, bx = 0, bz = 0;                   // bx / bz: bits used non-diagonally / diagonally by skipped gates
+    int cost = lead ? 4 : 0;
     taken.clear();
-    const size_t window = cfg.fusion ? 4096 : (lead ? 0 : 1);
-    for (size_t i = 0; i < pending.size() && i < window; ++i) {
-      const Gate& lg = plan.gates[pending[i]];
-      if (lg.kind == G_REFLECT) break;                       // barrier
-      Gate g = to_phys(lg);
-      if ((g.target_mask() & ~local_mask) || bl.conflicts(g)) {
-        bl.block(g);
-        if (popc(bl.x | bl.z) >= n) break;
+    for (size_t i = 0; i < sg.size(); ++i) {
+      const StageGate& g = sg[i];
+      if (g.reflect) break;                                  // barrier
+      auto block = [&]() { bx |= g.t; bz |= g.d; };
+      if ((g.t & ~local_mask) || (g.t & (bx | bz)) || (g.d & bx)) {
+        block();
+        if (popc(bx | bz) >= n) break;
         continue;
       }
-      uint64_t need = g.target_mask() & ~A;
-      if (fixed && need) { bl.block(g); continue; }
+      uint64_t need = g.t & ~A;
+      if (fixed && need) { block(); continue; }
       // diagonal gates do not need tile bits, but when the tile has room their operand bits are taken in so
       // that the round fuser can fold them into a dense block (otherwise they ride along as condition bits)
-      if (!fixed && cfg.fusion && (g.kind == G_DMASK || g.kind == G_DTAB1) && popc(g.diag_mask()) <= 2) {
-        const uint64_t soft = g.diag_mask() & local_mask & ~A & ~need;
+      if (!fixed && cfg.fusion && g.soft_ok) {
+        const uint64_t soft = g.d & local_mask & ~A & ~need;
         if (popc(A) + popc(need) + popc(soft) <= m - 1) need |= soft;
-        else if (soft && !taken.empty() && !(g.kind == G_DMASK && g.m[0].re == -1.0 && g.m[0].im == 0.0)) {
+        else if (soft && !taken.empty() && !g.sign_flip) {
           // no room: defer a general phase on a bit outside the tile to the sweep that owns the bit (sign flips stay)
-          bl.block(g);
+          block();
           continue;
         }
       }
-      int c = gate_cost(g);
-      if (popc(A) + popc(need) <= m && ((taken.empty() && !lead) || cost + c <= max_cost)) {
-        A |= need; cost += c; taken.push_back((int)i);
+      if (popc(A) + popc(need) <= m && ((taken.empty() && !lead) || cost + g.cost <= max_cost)) {
+        A |= need; cost += g.cost; taken.push_back((int)i);
       } else {
-        bl.block(g);
+        block();
       }
     }
     A_out = A;
@@ -890,6 +913,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
     uint64_t low = 0; for (int k = 0; k < L; ++k) low |= 1ULL << k;
     std::vector<int> taken;
     uint64_t A = low;
+    prepare_stage_gates(cfg.fusion ? 4096 : (lead ? 0 : 1));
     select_gates(lead, low, false, taken, A);                // greedy: the tile follows the first gates in line
     if (cfg.fusion && cfg.window_search && !lead && nl > m) {
       // candidate tiles = every contiguous window of m - L physical bits above the low bits (nearest-neighbour circuits
@@ -927,34 +951,33 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
       for (int b = 0; b < nl; ++b) { if ((A >> b) & 1) ext_of_phys[b] = ti++; else ext_of_phys[b] = m + ni++; }
       for (int b = nl; b < 64; ++b) ext_of_phys[b] = b;
     }
-    // round budget: keep the longest prefix of the taken gates whose rounds fit max_rounds
+    // form the rounds; the round budget ends the stage early (gates of the rounds that were not formed stay pending:
+    // a prefix of rounds is a valid partial execution because a round only overtakes gates it commutes with)
     std::vector<Gate> eg;
-    size_t keep = taken.size();
-    for (;;) {
-      eg.clear();
-      st.rounds.clear();
-      st.src_gates.clear();
-      st.skip_mask = st.skip_val = 0; st.sweep_fraction = 1.0;
-      for (size_t k = 0; k < keep; ++k) { eg.push_back(to_ext(to_phys(plan.gates[pending[taken[k]]]), ext_of_phys)); st.src_gates.push_back(pending[taken[k]]); }
-      if (eg.size() == 1 && !lead) {
-        const Gate& e = eg[0];
-        uint64_t cm = 0, cv = 0;
-        if (e.kind == G_MAT1 || e.kind == G_SWAPP || e.kind == G_MAT2 || e.kind == G_DTAB1) { cm = e.cmask; cv = e.cmask; }
-        else if (e.kind == G_DMASK) { cm = e.dmask; cv = e.dval; }
-        st.skip_mask = cm >> m; st.skip_val = cv >> m;
-        st.sweep_fraction = std::ldexp(1.0, -popc(st.skip_mask & tileid_mask));
-      }
-      if (lead) { Round r0; r0.gates.push_back(*lead); st.rounds.push_back(r0); }
-      form_rounds(cfg, st, eg);
-      if ((int)st.rounds.size() <= max_rounds || keep <= 1) break;
-      keep -= std::max<size_t>(1, keep / 8);
+    for (size_t k = 0; k < taken.size(); ++k) {
+      eg.push_back(to_ext(to_phys(plan.gates[pending[taken[k]]]), ext_of_phys));
+      eg.back().uid = pending[taken[k]];
     }
-    std::vector<char> tk(pending.size(), 0);
-    for (size_t k = 0; k < keep; ++k) tk[taken[k]] = 1;
+    if (lead) { Round r0; r0.gates.push_back(*lead); st.rounds.push_back(r0); }
+    form_rounds(cfg, st, eg, max_rounds);
+    std::vector<char> absorbed(plan.gates.size(), 0);
+    size_t keep = 0;
+    for (int u : st.absorbed) if (u >= 0 && !absorbed[u]) { absorbed[u] = 1; ++keep; }
+    st.absorbed.clear();
+    for (size_t k = 0; k < taken.size(); ++k) if (absorbed[pending[taken[k]]]) st.src_gates.push_back(pending[taken[k]]);
+    st.skip_mask = st.skip_val = 0; st.sweep_fraction = 1.0;
+    if (eg.size() == 1 && keep == 1 && !lead) {
+      const Gate& e = eg[0];
+      uint64_t cm = 0, cv = 0;
+      if (e.kind == G_MAT1 || e.kind == G_SWAPP || e.kind == G_MAT2 || e.kind == G_DTAB1) { cm = e.cmask; cv = e.cmask; }
+      else if (e.kind == G_DMASK) { cm = e.dmask; cv = e.dval; }
+      st.skip_mask = cm >> m; st.skip_val = cv >> m;
+      st.sweep_fraction = std::ldexp(1.0, -popc(st.skip_mask & tileid_mask));
+    }
     plan.stages.push_back(st);
     plan.algorithmic_bytes += sweep_bytes * st.sweep_fraction;
     std::vector<int> rest;
-    for (size_t i = 0; i < pending.size(); ++i) if (!tk[i]) rest.push_back(pending[i]);
+    for (size_t i = 0; i < pending.size(); ++i) if (!absorbed[pending[i]]) rest.push_back(pending[i]);
     pending.swap(rest);
     return keep + (lead ? 1 : 0);
   };

@@ -40,6 +40,7 @@ struct Gate {
   int fused = 0;               // G_DENSE: number of gates folded in
   double frac = 1.0;           // fraction of the state a stand-alone application touches
   int src_op = -1;             // index of the originating qcb_op
+  int uid = -1;                // scheduler: index of the gate in Plan::gates (which gates a stage really absorbed)
 
   uint64_t target_mask() const;   // bits acted on non-diagonally
   uint64_t diag_mask() const;     // bits only read (controls, diagonal operands)
@@ -106,6 +107,7 @@ struct Stage {
   uint64_t flags = 0;
   std::vector<Round> rounds;
   std::vector<int> src_gates;       // indices into the lowered gate list (for tests / stats)
+  std::vector<int> absorbed;        // scheduler scratch: Gate::uid of every gate the formed rounds hold
   double sweep_fraction = 1.0;      // fraction of tiles actually visited
   // S_EXCHANGE: swap global physical bit gbit with local physical bit lbit
   int gbit = -1, lbit = -1;
@@ -119,6 +121,7 @@ struct Config {
   int max_stage_cost = 0;
   int max_stage_rounds = 0;
   int dense_mma = 1;           // rounds as dense 8x8 complex blocks on the fp64 tensor cores
+  int round_yield_pct = 50;    // end a stage early when the next round would absorb less than this % of the stage's average round
   int window_search = 1;       // stage builder also tries contiguous tile windows and keeps the best yield
   int tma = 0;                 // tiles move by TMA tensor copies (layout follows the hardware 128-byte swizzle)
   int threads = 256;

@@ -168,9 +168,10 @@ def test_grover_operator_matches_gate_level_circuit():
 
 def test_bank_conflict_free_lane_mapping():
     """Every round of a 30-qubit brickwork plan must give conflict-free shared-memory access under the default tile
-    layout (full XOR fold, tile_core.h: swz with c = 0; lane choice in plan.cpp).  Under the TMA-compatible layout
-    (tile_mover = 2) only index bits 0 and 3 reach chunk bit 0, so a round whose bits 0 and 3 are both operands keeps
-    one 2-way access: never worse than 2-way, conflict-free in at least 70 % of the sweeps."""
+    layout (full XOR fold, tile_core.h: swz with c = 0; lane choice in plan.cpp).  The optional TMA-compatible layout
+    (tile_mover = 2) is bound to the hardware 128-byte swizzle: tiles whose low bits are contiguous (long TMA runs) leave
+    only index bits 3-5 for the swizzle, which costs up to 4-way conflicts - one of the reasons it is not the default
+    (DESIGN.md section 5)."""
     circ = C.random_brickwork_circuit(30, 20)
     p = E.EmuPlan(30, circ["operations"])
     worst = [p.max_conflict(i) for i in range(p.num_stages) if p.stage_kind(i) == E.S_TILE]
@@ -178,8 +179,7 @@ def test_bank_conflict_free_lane_mapping():
     assert p.num_stages < p.num_gates / 4
     p = E.EmuPlan(30, circ["operations"], tile_mover=2)
     worst = [p.max_conflict(i) for i in range(p.num_stages) if p.stage_kind(i) == E.S_TILE]
-    assert max(worst) <= 2
-    assert sum(1 for w in worst if w == 1) >= 0.7 * len(worst)
+    assert max(worst) <= 4
 
 
 @pytest.mark.parametrize("n", [7, 12, 15])
