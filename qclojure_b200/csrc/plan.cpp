@@ -820,7 +820,7 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
   }
 }
 
-int schedule(Plan& plan, const std::vector<int>& perm_in) {
+int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
   const Config& cfg = plan.cfg;
   const int n = cfg.n_total, nl = cfg.n_local, m = std::min(cfg.tile_bits, nl), L = std::min(cfg.low_bits, m);
   std::vector<int> perm(n);
@@ -845,6 +845,29 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
     p.cmask = mp(g.cmask);
     if (g.kind == G_DMASK || g.kind == G_DPOP1) { p.dmask = mp(g.dmask); p.dval = mp(g.dval); }
     return p;
+  };
+
+  // the program is encoded stage by stage as the plan grows (header word [1] = number of stages, patched at the end)
+  plan.words.clear();
+  plan.stage_offsets.clear();
+  plan.words.push_back(0x51434232ULL);                 // magic "QCB2"
+  plan.words.push_back(0);
+  plan.words.push_back((uint64_t)n);
+  plan.words.push_back((uint64_t)nl);
+  plan.n_rounds = 0;
+  int sink_rc = QCB_OK;
+  auto emit_new_stages = [&]() {
+    while (plan.stage_offsets.size() < plan.stages.size() && sink_rc == QCB_OK) {
+      const size_t si = plan.stage_offsets.size();
+      Stage& s = plan.stages[si];
+      plan.stage_offsets.push_back(plan.words.size());
+      plan.words.push_back((uint64_t)s.kind);
+      if (s.kind == S_TILE) { plan.words.push_back(0); encode_stage(cfg, s, plan.words); plan.n_rounds += s.rounds.size(); }
+      else if (s.kind == S_EXCHANGE) { plan.words.push_back((uint64_t)s.gbit | ((uint64_t)s.lbit << 8)); }
+      else { plan.words.push_back(0); }
+      plan.words[1] = (uint64_t)plan.stage_offsets.size();
+      if (sink) sink_rc = sink->on_stage(plan, si);
+    }
   };
 
   std::vector<int> pending(plan.gates.size());
@@ -983,6 +1006,8 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
   };
 
   while (!pending.empty()) {
+    emit_new_stages();
+    if (sink_rc != QCB_OK) { plan.error = "stage sink failed"; return sink_rc; }
     // ---- Grover diffusion 2|s><s| - I: a read-only sum sweep, then a' = 2*mean - a opens the next sweep
     if (plan.gates[pending[0]].kind == G_REFLECT) {
       Stage s; s.kind = S_SUM; s.src_gates.push_back(pending[0]);
@@ -1024,21 +1049,8 @@ int schedule(Plan& plan, const std::vector<int>& perm_in) {
   }
 
   plan.perm_out = perm;
-  // ---- encode
-  plan.words.clear();
-  plan.stage_offsets.clear();
-  plan.words.push_back(0x51434232ULL);                 // magic "QCB2"
-  plan.words.push_back((uint64_t)plan.stages.size());
-  plan.words.push_back((uint64_t)n);
-  plan.words.push_back((uint64_t)nl);
-  plan.n_rounds = 0;
-  for (Stage& s : plan.stages) {
-    plan.stage_offsets.push_back(plan.words.size());
-    plan.words.push_back((uint64_t)s.kind);
-    if (s.kind == S_TILE) { plan.words.push_back(0); encode_stage(cfg, s, plan.words); plan.n_rounds += s.rounds.size(); }
-    else if (s.kind == S_EXCHANGE) { plan.words.push_back((uint64_t)s.gbit | ((uint64_t)s.lbit << 8)); }
-    else { plan.words.push_back(0); }
-  }
+  emit_new_stages();
+  if (sink_rc != QCB_OK) { plan.error = "stage sink failed"; return sink_rc; }
   return QCB_OK;
 }
 

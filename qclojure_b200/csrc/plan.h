@@ -142,8 +142,15 @@ struct Plan {
 // qcb_op[] -> Gate[] ; returns QCB_OK or an error code with `err` set.
 int lower_ops(const Config& cfg, const qcb_op* ops, uint64_t n_ops, std::vector<Gate>& out, std::string& err);
 
+// Receives every stage as soon as the scheduler has finished and encoded it (Plan::words / stage_offsets are valid up
+// to and including that stage), so that execution can start while later stages are still being planned.
+struct StageSink {
+  virtual ~StageSink() {}
+  virtual int on_stage(Plan& plan, size_t stage_index) = 0;     // QCB_OK or an error code (aborts scheduling)
+};
+
 // Gate[] -> stages (+ encoded program).  perm_in: logical->physical bit map (identity when empty).
-int schedule(Plan& plan, const std::vector<int>& perm_in);
+int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink = nullptr);
 
 // Standard 2x2 matrices of the reference (domain/gate.clj:38-283)
 void gate_matrix(int kind, double angle, cplx out[4]);

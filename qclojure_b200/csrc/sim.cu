@@ -294,50 +294,74 @@ int do_exchange(qcb_sim* h, int gbit, int lbit) {
 }
 
 // ---- run a scheduled plan on the device
-int execute_plan(qcb_sim* h, Plan& plan) {
-  if (plan.stages.empty()) { h->perm = plan.perm_out; return QCB_OK; }
-  RET(ensure_prog(h, plan.words.size()));
-  if (h->prog_ev_valid) CU(h, cudaEventSynchronize(h->prog_ev));
-  std::memcpy(h->h_prog, plan.words.data(), plan.words.size() * sizeof(uint64_t));
-  CU(h, cudaMemcpyAsync(h->d_prog, h->h_prog, plan.words.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaEventRecord(h->prog_ev, h->stream));
-  h->prog_ev_valid = true;
-  for (size_t si = 0; si < plan.stages.size(); ++si) {
-    if (h->active_cancel && h->active_cancel->load()) return fail(h, QCB_ERR_STATE, "cancelled");
-    Stage& st = plan.stages[si];
-    const uint64_t off = plan.stage_offsets[si];
-    if (st.kind == S_TILE) {
-      const uint32_t words = (uint32_t)plan.words[off + 2 + 42];      // descriptor part only (copied to smem)
-      uint64_t active = 0;
-      CU(h, launch_tile_stage(h->state, h->d_prog + off + 2, plan.words.data() + off + 2, words, h->d_vals, h->num_sms, h->stream, &active, &h->maps));
-      if (active) { h->stats.n_sweeps++; h->stats.n_kernel_launches++; h->stats.n_rounds += st.rounds.size(); }
-    } else if (st.kind == S_SUM) {
-      // Grover diffusion: sum of all amplitudes -> (alpha, beta) = (-1, 2*mean) in d_vals[0..4)
-      const int grid = red_grid(h);
-      RET(ensure_partials(h, (size_t)grid * 2));
-      CU(h, launch_reduce(h->state, h->local_count, 0, h->d_partials, grid, h->stream));
-      CU(h, launch_finalize(h->d_partials, grid, 2, 0, 0.0, h->d_vals + 8, h->stream));
-      RET(allreduce_sum(h, h->d_vals + 8, 2));
-      CU(h, launch_finalize(h->d_vals + 8, 1, 2, 1, std::ldexp(1.0, h->cfg.n_total), h->d_vals, h->stream));
-      h->stats.n_kernel_launches += 3;
-    } else if (st.kind == S_EXCHANGE) {
-      RET(do_exchange(h, st.gbit, st.lbit));
-    }
+// Launches one planned stage.  Tile stages read their program from d_prog (uploaded by the caller at word offset `off`).
+int execute_stage(qcb_sim* h, Plan& plan, size_t si) {
+  if (h->active_cancel && h->active_cancel->load()) return fail(h, QCB_ERR_STATE, "cancelled");
+  Stage& st = plan.stages[si];
+  const uint64_t off = plan.stage_offsets[si];
+  if (st.kind == S_TILE) {
+    const uint32_t words = (uint32_t)plan.words[off + 2 + 42];      // descriptor part only (copied to smem)
+    uint64_t active = 0;
+    CU(h, launch_tile_stage(h->state, h->d_prog + off + 2, plan.words.data() + off + 2, words, h->d_vals, h->num_sms, h->stream, &active, &h->maps));
+    if (active) { h->stats.n_sweeps++; h->stats.n_kernel_launches++; h->stats.n_rounds += st.rounds.size(); }
+  } else if (st.kind == S_SUM) {
+    // Grover diffusion: sum of all amplitudes -> (alpha, beta) = (-1, 2*mean) in d_vals[0..4)
+    const int grid = red_grid(h);
+    RET(ensure_partials(h, (size_t)grid * 2));
+    CU(h, launch_reduce(h->state, h->local_count, 0, h->d_partials, grid, h->stream));
+    CU(h, launch_finalize(h->d_partials, grid, 2, 0, 0.0, h->d_vals + 8, h->stream));
+    RET(allreduce_sum(h, h->d_vals + 8, 2));
+    CU(h, launch_finalize(h->d_vals + 8, 1, 2, 1, std::ldexp(1.0, h->cfg.n_total), h->d_vals, h->stream));
+    h->stats.n_kernel_launches += 3;
+  } else if (st.kind == S_EXCHANGE) {
+    RET(do_exchange(h, st.gbit, st.lbit));
   }
-  h->perm = plan.perm_out;
   return QCB_OK;
 }
+
+// Executes stages while the scheduler is still planning the rest of the circuit: every finished stage is copied into the
+// pinned program buffer, uploaded and launched at once (kernel launches are asynchronous, so the host-side planning of
+// stage k+1 overlaps the sweep of stage k).  The program buffers are sized for the whole op list up front: they must
+// not move while earlier stages are in flight.
+struct StreamingExecutor : StageSink {
+  qcb_sim* h;
+  explicit StreamingExecutor(qcb_sim* hh) : h(hh) {}
+  int on_stage(Plan& plan, size_t si) override {
+    const size_t begin = plan.stage_offsets[si], end = plan.words.size();
+    if (end > h->prog_cap) {
+      // rare (bound below exceeded): let everything in flight finish, then grow
+      CU(h, cudaStreamSynchronize(h->stream));
+      RET(ensure_prog(h, end * 2));
+      std::memcpy(h->h_prog, plan.words.data(), begin * sizeof(uint64_t));
+    }
+    std::memcpy(h->h_prog + begin, plan.words.data() + begin, (end - begin) * sizeof(uint64_t));
+    CU(h, cudaMemcpyAsync(h->d_prog + begin, h->h_prog + begin, (end - begin) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    return execute_stage(h, plan, si);
+  }
+};
 
 int run_gates(qcb_sim* h, std::vector<Gate>&& gates) {
   Plan plan;
   plan.cfg = h->cfg;
   plan.gates = std::move(gates);
-  int rc = schedule(plan, h->perm);
-  if (rc != QCB_OK) return fail(h, rc, plan.error);
+  // program size bound: a tensor-core round holds at most 2^MAX_COND_BITS matrices of 256 doubles, and there are at most
+  // as many rounds as gates; typical programs are ~80 words per gate
+  RET(ensure_prog(h, std::max<size_t>(1 << 17, plan.gates.size() * 512)));
+  if (h->prog_ev_valid) CU(h, cudaEventSynchronize(h->prog_ev));      // the previous call's uploads have left the pinned buffer
+  StreamingExecutor sink(h);
+  int rc = schedule(plan, h->perm, &sink);
+  CU(h, cudaEventRecord(h->prog_ev, h->stream));
+  h->prog_ev_valid = true;
+  if (rc != QCB_OK) {
+    // a sink failure has already recorded its own message (CUDA / NCCL error); scheduler errors carry plan.error
+    if (plan.error != "stage sink failed") return fail(h, rc, plan.error);
+    return rc;
+  }
   h->stats.n_gates_lowered += plan.gates.size();
   h->stats.algorithmic_bytes += plan.algorithmic_bytes;
   h->stats.unfused_bytes += plan.unfused_bytes;
-  return execute_plan(h, plan);
+  h->perm = plan.perm_out;
+  return QCB_OK;
 }
 
 // bring the state back to the canonical layout (logical bit b at physical bit b)
@@ -380,11 +404,13 @@ int restore_layout(qcb_sim* h) {
   if (!swaps.empty()) {
     // the swap gates are expressed on PHYSICAL bits: schedule them with an identity permutation
     Plan plan; plan.cfg = h->cfg; plan.gates = std::move(swaps);
-    int rc = schedule(plan, std::vector<int>());
-    if (rc != QCB_OK) return fail(h, rc, plan.error);
-    std::vector<int> keep = h->perm;
-    RET(execute_plan(h, plan));
-    h->perm = keep;
+    RET(ensure_prog(h, std::max<size_t>(1 << 17, plan.gates.size() * 512)));
+    if (h->prog_ev_valid) CU(h, cudaEventSynchronize(h->prog_ev));
+    StreamingExecutor sink(h);
+    int rc = schedule(plan, std::vector<int>(), &sink);
+    CU(h, cudaEventRecord(h->prog_ev, h->stream));
+    h->prog_ev_valid = true;
+    if (rc != QCB_OK) return plan.error != "stage sink failed" ? fail(h, rc, plan.error) : rc;
   }
   for (int b = 0; b < n; ++b) h->perm[b] = b;
   return QCB_OK;
