@@ -13,7 +13,7 @@ echo "== bench"; timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.l
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.log 2>&1; tail -2 $OUT/bench_reference.log | cut -c1-1500
 echo "== bench unfused"; timeout 600 python bench.py --steps 1 --warmup 1 --fusion 0 --no-cpu --no-e2e > $OUT/bench_unfused.log 2>&1; tail -2 $OUT/bench_unfused.log | cut -c1-1500
 echo "== bench budget sweep"
-for cfg in 200,2 200,3 200,4 400,6 800,12; do
+for cfg in 200,2 800,3 800,5 800,8 800,12; do
   IFS=, read c r <<< "$cfg"
   echo "-- stage-cost $c stage-rounds $r" >> $OUT/budgets.log
   timeout 300 python bench.py --steps 3 --warmup 1 --no-cpu --no-e2e --stage-cost $c --stage-rounds $r 2>&1 | tail -1 >> $OUT/budgets.log
