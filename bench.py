@@ -244,6 +244,30 @@ def run_ours(args):
                "ms_per_step": 1000.0 * e2e_s / args.steps,
                "api": "backend.execute_circuit(B200Simulator, circuit, {:result-specs {:measurements {:shots 1024}}})"}
         sim._svs.pop(n, None)
+    elif world > 1 and not args.no_e2e:
+        # multi-GPU: the same metric through the C ABI with HOST buffers on every rank (qcb_set_zero, qcb_apply_ops on the
+        # host op array, qcb_sample on host uniforms -> host outcomes), wall clock between barriers, max over ranks
+        shots = 1024
+        u = np.random.default_rng(20261017).random(shots)
+        sv.set_zero(); sv.apply_ops(enc); sv.sample(u)          # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sv.set_zero()
+            sv.apply_ops(enc)
+            outcomes = sv.sample(u)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te[0])
+        assert outcomes.shape[0] == shots
+        prog_words = L.plan_summary(n, ops, fusion=args.fusion, max_stage_cost=args.stage_cost, max_stage_rounds=args.stage_rounds,
+                                    tile_bits=args.tile_bits, low_bits=args.low_bits, rank=rank, world_size=world)["program_words"]
+        e2e = {"value": n_gates * args.steps / e2e_s, "unit": "gates/s",
+               "h2d_bytes_per_step": int(world * (prog_words * 8 + shots * 8)), "d2h_bytes_per_step": int(world * shots * 8),
+               "ms_per_step": 1000.0 * e2e_s / args.steps,
+               "api": "C ABI per rank: qcb_set_zero + qcb_apply_ops(host qcb_op[]) + qcb_sample(host uniforms -> host outcomes)"}
 
     if rank == 0:
         peak, peak_src = _peaks()
