@@ -770,7 +770,7 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
 }
 
 // Form shared-memory rounds from the gates of one stage (gates already in ext space; targets < m).
-static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, int max_rounds) {
+static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, int max_rounds, bool materialize = true) {
   std::vector<Gate> pending = gates;
   const bool search = cfg.fusion && cfg.window_search && cfg.dense_mma && st.m >= 6;
   const uint64_t tile_mask = (1ULL << st.m) - 1ULL;
@@ -813,8 +813,10 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
     for (int i : rest) next.push_back(std::move(pending[i]));
     // unfused mode keeps exactly one gate per round anyway (one gate per stage)
     for (int b = 0; b < st.m; ++b) if ((R >> b) & 1) rd.slot_pos.push_back(b);
-    if (dmma_eligible(cfg, st, rd)) build_dmma_round(cfg, st, rd);
-    else if (cfg.fusion) fuse_round(rd);
+    if (materialize) {
+      if (dmma_eligible(cfg, st, rd)) build_dmma_round(cfg, st, rd);
+      else if (cfg.fusion) fuse_round(rd);
+    }
     st.rounds.push_back(std::move(rd));
     pending.swap(next);
   }
@@ -931,25 +933,12 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
     A_out = A;
   };
 
-  auto build_tile_stage = [&](const Gate* lead) -> size_t {
-    Stage st; st.kind = S_TILE; st.m = m; st.L = L;
-    uint64_t low = 0; for (int k = 0; k < L; ++k) low |= 1ULL << k;
-    std::vector<int> taken;
-    uint64_t A = low;
-    prepare_stage_gates(cfg.fusion ? 4096 : (lead ? 0 : 1));
-    select_gates(lead, low, false, taken, A);                // greedy: the tile follows the first gates in line
-    if (cfg.fusion && cfg.window_search && !lead && nl > m) {
-      // candidate tiles = every contiguous window of m - L physical bits above the low bits (nearest-neighbour circuits
-      // leave seams between greedy tiles whose gates then straggle in low-yield sweeps); keep whichever absorbs most gates
-      std::vector<int> cand_taken;
-      for (int p = L; p + (m - L) <= nl; ++p) {
-        uint64_t Aw = low, Aout = 0;
-        for (int b = p; b < p + (m - L); ++b) Aw |= 1ULL << b;
-        select_gates(lead, Aw, true, cand_taken, Aout);
-        if (cand_taken.size() > taken.size()) { taken = cand_taken; A = Aw; }
-      }
-    }
-    if (taken.empty() && !lead) return 0;          // nothing executable in the current layout (multi-GPU: exchange first)
+  // Turn a tile choice (A = tile bits so far, taken = indices into `pending`) into a stage: complete the tile, translate the
+  // gates into its ext space and form the rounds.  `absorbed_out` = Gate::uid of the gates the formed rounds hold (the round
+  // budget / thin-round cut may leave some of `taken` pending).  materialize = false skips the matrix building (scoring).
+  auto make_stage = [&](const Gate* lead, uint64_t A, const std::vector<int>& taken, bool materialize, Stage& st,
+                        std::vector<int>& absorbed_out) {
+    st = Stage(); st.kind = S_TILE; st.m = m; st.L = L;
     // single-gate stage: keep its condition bits OUT of the tile so that whole tiles can be skipped
     uint64_t avoid = 0;
     if (taken.size() == 1 && !lead) {
@@ -982,14 +971,11 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
       eg.back().uid = pending[taken[k]];
     }
     if (lead) { Round r0; r0.gates.push_back(*lead); st.rounds.push_back(r0); }
-    form_rounds(cfg, st, eg, max_rounds);
-    std::vector<char> absorbed(plan.gates.size(), 0);
-    size_t keep = 0;
-    for (int u : st.absorbed) if (u >= 0 && !absorbed[u]) { absorbed[u] = 1; ++keep; }
+    form_rounds(cfg, st, eg, max_rounds, materialize);
+    absorbed_out.swap(st.absorbed);
     st.absorbed.clear();
-    for (size_t k = 0; k < taken.size(); ++k) if (absorbed[pending[taken[k]]]) st.src_gates.push_back(pending[taken[k]]);
     st.skip_mask = st.skip_val = 0; st.sweep_fraction = 1.0;
-    if (eg.size() == 1 && keep == 1 && !lead) {
+    if (eg.size() == 1 && absorbed_out.size() == 1 && !lead) {
       const Gate& e = eg[0];
       uint64_t cm = 0, cv = 0;
       if (e.kind == G_MAT1 || e.kind == G_SWAPP || e.kind == G_MAT2 || e.kind == G_DTAB1) { cm = e.cmask; cv = e.cmask; }
@@ -997,6 +983,34 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
       st.skip_mask = cm >> m; st.skip_val = cv >> m;
       st.sweep_fraction = std::ldexp(1.0, -popc(st.skip_mask & tileid_mask));
     }
+  };
+
+  auto build_tile_stage = [&](const Gate* lead) -> size_t {
+    uint64_t low = 0; for (int k = 0; k < L; ++k) low |= 1ULL << k;
+    std::vector<int> taken;
+    uint64_t A = low;
+    prepare_stage_gates(cfg.fusion ? 4096 : (lead ? 0 : 1));
+    select_gates(lead, low, false, taken, A);                // greedy: the tile follows the first gates in line
+    if (cfg.fusion && cfg.window_search && !lead && nl > m) {
+      // candidate tiles = every contiguous window of m - L physical bits above the low bits (nearest-neighbour circuits
+      // leave seams between greedy tiles whose gates then straggle in low-yield sweeps); keep whichever could absorb most
+      // gates.  (Scoring the candidates by what their first rounds really hold per estimated millisecond was tried and is
+      // no better: 18 sweeps / 72 rounds instead of 16 / 72 for the benchmark circuit.)
+      std::vector<int> cand_taken;
+      for (int p = L; p + (m - L) <= nl; ++p) {
+        uint64_t Aw = low, Aout = 0;
+        for (int b = p; b < p + (m - L); ++b) Aw |= 1ULL << b;
+        select_gates(lead, Aw, true, cand_taken, Aout);
+        if (cand_taken.size() > taken.size()) { taken = cand_taken; A = Aw; }
+      }
+    }
+    if (taken.empty() && !lead) return 0;          // nothing executable in the current layout (multi-GPU: exchange first)
+    Stage st; std::vector<int> abs_uids;
+    make_stage(lead, A, taken, true, st, abs_uids);
+    std::vector<char> absorbed(plan.gates.size(), 0);
+    size_t keep = 0;
+    for (int u : abs_uids) if (u >= 0 && !absorbed[u]) { absorbed[u] = 1; ++keep; }
+    for (size_t k = 0; k < taken.size(); ++k) if (absorbed[pending[taken[k]]]) st.src_gates.push_back(pending[taken[k]]);
     plan.stages.push_back(st);
     plan.algorithmic_bytes += sweep_bytes * st.sweep_fraction;
     std::vector<int> rest;
