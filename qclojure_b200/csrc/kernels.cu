@@ -1,10 +1,12 @@
 // kernels.cu — hand-written sm_100a kernels of libqcb200.so.
 //
-//  k_tile_stage        the fused gate executor: one launch = one sweep over the local state.  A CTA
-//                      stages a tile of 2^m amplitudes in shared memory with cp.async (LDGSTS, 16-byte
-//                      coalesced runs), runs the stage's rounds with 2^r amplitudes per thread in
-//                      registers (tile_core.h), and writes the tile back in place.  HBM-bound:
-//                      algorithmic bytes = 32 * 2^n_local * (fraction of tiles visited).
+//  k_tile_stage        the fused gate executor: one launch = one sweep over the local state.  One persistent,
+//                      warp-specialised CTA per SM: mover warps stream tiles of 2^m amplitudes through a ring
+//                      of shared-memory buffers (cp.async / st.global, or TMA tensor copies), two consumer
+//                      groups apply the stage's rounds - dense 8x8 complex blocks on the fp64 tensor cores
+//                      (DMMA.8x8x4) or interpreter rounds (tile_core.h) - and the tile is written back in
+//                      place.  Algorithmic bytes = 32 * 2^n_local * (fraction of tiles visited); HBM-bound up
+//                      to two rounds per sweep, fp64-tensor-bound beyond.
 //  reductions          norm^2 / complex sum / Pauli expectation / marginal histogram: streaming reads
 //                      (16 B per amplitude), warp-shuffle + shared-memory block reduce, deterministic
 //                      two-pass finalisation (no floating-point atomics).
@@ -34,11 +36,6 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -629,7 +626,8 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   while (nbuf > 1 && (fixed + nbuf * (tile_n * 16) > limit || nbuf > tiles_per_cta + 1)) --nbuf;
   const size_t smem = fixed + nbuf * (tile_n * 16);
   if (smem > limit) return cudaErrorInvalidConfiguration;
-  // consumer layout: groups x warps-per-group (QCB_CONSUMERS = "2x4" default, "3x4", "2x8", "1x16", "1x8")
+  // consumer layout: groups x warps-per-group (QCB_CONSUMERS = "2x4" default, "2x8", "1x8"; 1x16 and 3x4 were measured
+  // and dropped: profiles/r1c_sweep_pipelined_groups.log, profiles/r1d_layout_sweep.log)
   static const int layout = [] {
     const char* e = getenv("QCB_CONSUMERS");
     if (!e) return 24;
@@ -639,10 +637,8 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   return launch_tile_stage_t<NG, WPG>(mma_only, (unsigned)grid, smem, limit, stream, state, stage_dev, stage_words, dev_vals, n_active, nbuf, \
                                       *tm, use_tma)
   switch (layout) {
-    case 26: case 116: QCB_LAUNCH(1, 16);
     case 18: QCB_LAUNCH(1, 8);
     case 28: QCB_LAUNCH(2, 8);
-    case 34: QCB_LAUNCH(3, 4);
     default: QCB_LAUNCH(2, 4);
   }
 #undef QCB_LAUNCH
