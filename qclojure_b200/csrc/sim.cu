@@ -116,6 +116,10 @@ struct qcb_sim {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timing_pending = false;
   cudaEvent_t xev0 = nullptr, xev1 = nullptr;
   cudaStream_t xstream = nullptr;                 // copy-back stream of the qubit exchange
+  // peer-to-peer exchange: every rank's state allocation is IPC-mapped by its exchange partners (ranks differing in
+  // one bit), so the moving half is pulled straight out of the partner's HBM over NVLink by the copy engines
+  bool p2p = false;
+  std::vector<double2*> peer_state;               // [world], nullptr = not a partner
   cudaEvent_t xrecv[2] = {nullptr, nullptr}, xcopy[2] = {nullptr, nullptr}, xpack[2] = {nullptr, nullptr};
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;
   std::string err;
@@ -198,6 +202,91 @@ int ensure_prog(qcb_sim* h, size_t words) {
   return QCB_OK;
 }
 
+int do_exchange_nccl(qcb_sim* h, int gbit, int lbit);
+
+int ensure_exchange_buffers(qcb_sim* h, uint64_t half) {
+  if (h->xbuf) return QCB_OK;
+  static const int xlog = [] { const char* e = getenv("QCB_XCHUNK_LOG2"); int v = e ? atoi(e) : 25; return v < 4 ? 4 : (v > 28 ? 28 : v); }();
+  uint64_t cnt = std::min<uint64_t>(half, 1ULL << xlog);        // 2 send + 2 receive buffers of <= 512 MiB
+  CU(h, cudaMalloc(&h->xbuf, 4 * cnt * sizeof(double2)));
+  h->xbuf_count = cnt;
+  CU(h, cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CU(h, cudaEventCreateWithFlags(&h->xrecv[i], cudaEventDisableTiming));
+    CU(h, cudaEventCreateWithFlags(&h->xcopy[i], cudaEventDisableTiming));
+    CU(h, cudaEventCreateWithFlags(&h->xpack[i], cudaEventDisableTiming));
+  }
+  return QCB_OK;
+}
+
+// Peer-to-peer variant of the exchange: each rank PULLS the partner's moving half out of the partner's HBM
+// (IPC-mapped at create time) into a local staging buffer with the copy engines, then scatters it into its own vacated
+// positions.  Cross-process ordering rides on one-double ncclSend/ncclRecv handshakes, which are stream-ordered on both
+// sides: H0 = "my earlier kernels are done, you may read my state", HS(c) = "I have pulled chunk c of yours, you may
+// overwrite it".  A plain peer copy reaches ~770 GB/s per direction on this pool; ncclSend/ncclRecv ~520.
+int do_exchange_p2p(qcb_sim* h, int gbit, int lbit) {
+  const int nl = h->cfg.n_local;
+  const int j = gbit - nl;
+  const int myb = (h->cfg.rank >> j) & 1;
+  const int peer = h->cfg.rank ^ (1 << j);
+  const uint64_t want = (uint64_t)(1 - myb), want_p = (uint64_t)myb;   // moving half: mine has bit lbit == !myb, the partner's == myb
+  const uint64_t half = h->local_count >> 1, block = 1ULL << lbit;
+  RET(ensure_exchange_buffers(h, half));
+  const double2* pstate = h->peer_state[peer];
+  const uint64_t chunk = h->xbuf_count;
+  const uint64_t n_chunks = (half + chunk - 1) / chunk;
+  const bool contiguous = block >= chunk;
+  auto pos = [&](const double2* base, uint64_t sel, uint64_t first) {      // address of moving-half offset `first`
+    const uint64_t bi = first >> lbit, in = first & (block - 1);
+    return base + (((bi << 1) | sel) << lbit) + in;
+  };
+  auto recvbuf = [&](uint64_t c) { return h->xbuf + (2 + (c & 1)) * chunk; };
+  auto count_of = [&](uint64_t c) { return std::min<uint64_t>(chunk, half - c * chunk); };
+  double* token = h->d_vals + 200;
+  auto handshake = [&]() -> int {
+    NC(h, g_nccl.GroupStart());
+    NC(h, g_nccl.Send(token, 1, ncclDouble, peer, h->comm, h->stream));
+    NC(h, g_nccl.Recv(token + 1, 1, ncclDouble, peer, h->comm, h->stream));
+    NC(h, g_nccl.GroupEnd());
+    return QCB_OK;
+  };
+  CU(h, cudaEventRecord(h->xev0, h->stream));
+  RET(handshake());                                                         // H0
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    const int sb = (int)(c & 1);
+    const uint64_t cnt = count_of(c), first = c * chunk;
+    if (c >= 2) CU(h, cudaStreamWaitEvent(h->stream, h->xcopy[sb], 0));     // staging buffer free again
+    if (contiguous)
+      CU(h, cudaMemcpyAsync(recvbuf(c), pos(pstate, want_p, first), cnt * sizeof(double2), cudaMemcpyDefault, h->stream));
+    else
+      CU(h, cudaMemcpy2DAsync(recvbuf(c), block * sizeof(double2), pos(pstate, want_p, first), 2 * block * sizeof(double2),
+                              block * sizeof(double2), cnt >> lbit, cudaMemcpyDefault, h->stream));
+    RET(handshake());                                                       // HS(c)
+    CU(h, cudaEventRecord(h->xrecv[sb], h->stream));
+    CU(h, cudaStreamWaitEvent(h->xstream, h->xrecv[sb], 0));
+    double2* dst = h->state + (pos(h->state, want, first) - h->state);
+    if (contiguous)
+      CU(h, cudaMemcpyAsync(dst, recvbuf(c), cnt * sizeof(double2), cudaMemcpyDeviceToDevice, h->xstream));
+    else
+      CU(h, cudaMemcpy2DAsync(dst, 2 * block * sizeof(double2), recvbuf(c), block * sizeof(double2), block * sizeof(double2),
+                              cnt >> lbit, cudaMemcpyDeviceToDevice, h->xstream));
+    CU(h, cudaEventRecord(h->xcopy[sb], h->xstream));
+    h->stats.bytes_exchanged += cnt * sizeof(double2);
+  }
+  for (uint64_t i = 0; i < 2 && i < n_chunks; ++i) CU(h, cudaStreamWaitEvent(h->stream, h->xcopy[i], 0));
+  CU(h, cudaEventRecord(h->xev1, h->stream));
+  CU(h, cudaEventSynchronize(h->xev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->xev0, h->xev1);
+  h->stats.exchange_ms += ms;
+  h->stats.n_exchanges++;
+  return QCB_OK;
+}
+
+int do_exchange(qcb_sim* h, int gbit, int lbit) {
+  return h->p2p ? do_exchange_p2p(h, gbit, lbit) : do_exchange_nccl(h, gbit, lbit);
+}
+
 bool perm_is_identity(const qcb_sim* h) {
   for (size_t b = 0; b < h->perm.size(); ++b) if (h->perm[b] != (int)b) return false;
   return true;
@@ -220,7 +309,7 @@ int allreduce_sum(qcb_sim* h, double* dev, size_t count) {
 }
 
 // ---- exchange: swap global physical bit gbit with local physical bit lbit
-int do_exchange(qcb_sim* h, int gbit, int lbit) {
+int do_exchange_nccl(qcb_sim* h, int gbit, int lbit) {
   // Swap global physical bit gbit with local physical bit lbit: rank r and partner r ^ 2^j exchange the half of their
   // slice whose bit lbit differs from their own rank bit.  The half moves in chunks of <= 512 MiB through a two-deep
   // software pipeline: chunk c+1 is gathered into a send buffer (k_pack_half; skipped when the chunk is contiguous in
@@ -233,18 +322,7 @@ int do_exchange(qcb_sim* h, int gbit, int lbit) {
   const int peer = h->cfg.rank ^ (1 << j);
   const int want = 1 - myb;                         // the half of MY slice that moves: bit lbit == !myb
   const uint64_t half = h->local_count >> 1, block = 1ULL << lbit;
-  if (!h->xbuf) {
-    static const int xlog = [] { const char* e = getenv("QCB_XCHUNK_LOG2"); int v = e ? atoi(e) : 25; return v < 4 ? 4 : (v > 28 ? 28 : v); }();
-    uint64_t cnt = std::min<uint64_t>(half, 1ULL << xlog);        // 2 send + 2 receive buffers of <= 512 MiB
-    CU(h, cudaMalloc(&h->xbuf, 4 * cnt * sizeof(double2)));
-    h->xbuf_count = cnt;
-    CU(h, cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CU(h, cudaEventCreateWithFlags(&h->xrecv[i], cudaEventDisableTiming));
-      CU(h, cudaEventCreateWithFlags(&h->xcopy[i], cudaEventDisableTiming));
-      CU(h, cudaEventCreateWithFlags(&h->xpack[i], cudaEventDisableTiming));
-    }
-  }
+  RET(ensure_exchange_buffers(h, half));
   const uint64_t chunk = h->xbuf_count;              // amplitudes of the moving half per chunk
   const uint64_t n_chunks = (half + chunk - 1) / chunk;
   const bool contiguous = block >= chunk;            // a chunk lies inside one contiguous block of the state
@@ -718,6 +796,42 @@ int32_t qcb_config_default(qcb_config* cfg) {
   return QCB_OK;
 }
 
+// Exchange the IPC handles of the state allocations and map the partners' states.  Every rank must reach the same verdict
+// (a rank pulling while its partner sends would hang), so the outcome is agreed on with a min-all-reduce; any failure
+// simply leaves the NCCL send/recv exchange in place.  QCB_EXCHANGE=nccl forces that path.
+static void setup_p2p(qcb_sim* h) {
+  const int world = h->cfg.world;
+  h->peer_state.assign(world, nullptr);
+  const char* mode = getenv("QCB_EXCHANGE");
+  double ok = (mode && std::string(mode) == "nccl") ? 0.0 : 1.0;
+  unsigned char* d_ipc = nullptr;
+  std::vector<cudaIpcMemHandle_t> handles(world);
+  if (cudaMalloc(&d_ipc, (size_t)world * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, h->state) != cudaSuccess) { cudaGetLastError(); ok = 0.0; std::memset(&mine, 0, sizeof mine); }
+  cudaMemcpyAsync(d_ipc + (size_t)h->cfg.rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream);
+  bool comm_ok = g_nccl.AllGather(d_ipc + (size_t)h->cfg.rank * sizeof mine, d_ipc, sizeof mine, ncclChar, h->comm, h->stream) == ncclSuccess;
+  comm_ok = comm_ok && cudaMemcpyAsync(handles.data(), d_ipc, (size_t)world * sizeof mine, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
+  comm_ok = comm_ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
+  if (!comm_ok) ok = 0.0;
+  if (ok > 0.0)
+    for (int bit = 1; bit < world; bit <<= 1) {
+      const int peer = h->cfg.rank ^ bit;
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, handles[peer], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0.0; break; }
+      h->peer_state[peer] = static_cast<double2*>(p);
+    }
+  // agree: p2p only if every rank mapped all of its partners
+  double* d_ok = h->d_vals + 202;
+  cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, h->stream);
+  if (g_nccl.AllReduce(d_ok, d_ok, 1, ncclDouble, ncclMin, h->comm, h->stream) == ncclSuccess &&
+      cudaMemcpyAsync(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess && cudaStreamSynchronize(h->stream) == cudaSuccess)
+    h->p2p = ok > 0.5;
+  cudaFree(d_ipc);
+  if (!h->p2p)
+    for (auto& p : h->peer_state) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+}
+
 int32_t qcb_create(const qcb_config* c, qcb_handle* out) {
   if (!c || !out) return fail(nullptr, QCB_ERR_INVALID, "null argument");
   *out = nullptr;
@@ -764,6 +878,7 @@ int32_t qcb_create(const qcb_config* c, qcb_handle* out) {
     std::memcpy(&id, c->nccl_unique_id, sizeof id);
     ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, id, c->rank);
     if (r != ncclSuccess) { cudaFree(h->state); return fail(nullptr, QCB_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); }
+    setup_p2p(h.get());
   }
   // |0...0>
   cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream);
@@ -782,6 +897,7 @@ int32_t qcb_destroy(qcb_handle h) {
   if (h->worker_started && h->worker.joinable()) h->worker.join();
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& p : h->peer_state) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
   if (h->comm) g_nccl.CommDestroy(h->comm);
   tile_prof_dump();
   cudaFree(h->state); cudaFree(h->d_prog); cudaFree(h->d_vals); cudaFree(h->d_partials); cudaFree(h->d_scratch); cudaFree(h->xbuf);
