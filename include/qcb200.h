@@ -259,6 +259,32 @@ int32_t qcb_la_trace(qcb_handle h, const double* A, uint64_t n, double out[2]);
 int32_t qcb_la_norm2(qcb_handle h, const double* x, uint64_t n, double* out);
 int32_t qcb_la_axpby(qcb_handle h, const double alpha[2], const double* x, const double beta[2], const double* y, uint64_t n, double* out);
 
+/* ---- P2, remaining protocol methods (domain/math/protocols.clj:81-521; reference implementation
+        domain/math/fastmath/complex_linear_algebra.clj:174-1470).  Small dense matrices: computed on the HOST inside the
+        library (cyclic Jacobi, Householder, shifted QR), no GPU work, `h` may be NULL.  Row-major interleaved buffers,
+        caller-allocated outputs.  Conventions: eigenvalues ascending (general: by real part, then imaginary part),
+        eigenvector k stored at [k*n, (k+1)*n) and normalised, singular values descending with FULL U (m x m) and
+        V^H (n x n), A = P L U, A = Q R with Q m x m, A = L L^H, principal branches for log and sqrt. ---- */
+int32_t qcb_la_hadamard(qcb_handle h, const double* A, const double* B, uint64_t n_elements, double* C);          /* hadamard-product :213 */
+int32_t qcb_la_transpose(qcb_handle h, const double* A, uint64_t rows, uint64_t cols, int32_t conjugate, double* out); /* transpose :239, conjugate-transpose :249 */
+int32_t qcb_la_solve(qcb_handle h, const double* A, const double* B, uint64_t n, uint64_t nrhs, double* X);        /* solve-linear-system :284 */
+int32_t qcb_la_inverse(qcb_handle h, const double* A, uint64_t n, double* out);                                    /* inverse :295 */
+int32_t qcb_la_is_hermitian(qcb_handle h, const double* A, uint64_t n, double eps, int32_t* out);                  /* hermitian? :306 */
+int32_t qcb_la_is_diagonal(qcb_handle h, const double* A, uint64_t n, double eps, int32_t* out);                   /* diagonal? :317 */
+int32_t qcb_la_is_unitary(qcb_handle h, const double* A, uint64_t n, double eps, int32_t* out);                    /* unitary? :328 */
+int32_t qcb_la_is_positive_semidefinite(qcb_handle h, const double* A, uint64_t n, double eps, int32_t* out);      /* positive-semidefinite? :339 (error if not Hermitian) */
+int32_t qcb_la_eigen_hermitian(qcb_handle h, const double* A, uint64_t n, double* eigenvalues, double* eigenvectors); /* eigen-hermitian :363 */
+int32_t qcb_la_eigen_general(qcb_handle h, const double* A, uint64_t n, double* eigenvalues /* complex[n] */, double* eigenvectors); /* eigen-general :375 */
+int32_t qcb_la_svd(qcb_handle h, const double* A, uint64_t m, uint64_t n, double* U, double* S, double* Vh);       /* svd :390 */
+int32_t qcb_la_lu(qcb_handle h, const double* A, uint64_t n, double* P, double* L, double* U);                     /* lu-decomposition :403 */
+int32_t qcb_la_qr(qcb_handle h, const double* A, uint64_t m, uint64_t n, double* Q, double* R);                    /* qr-decomposition :416 */
+int32_t qcb_la_cholesky(qcb_handle h, const double* A, uint64_t n, double* L);                                     /* cholesky-decomposition :431 */
+int32_t qcb_la_matrix_exp(qcb_handle h, const double* A, uint64_t n, double* out);                                 /* matrix-exp :453 */
+int32_t qcb_la_matrix_log(qcb_handle h, const double* A, uint64_t n, double* out);                                 /* matrix-log :466 */
+int32_t qcb_la_matrix_sqrt(qcb_handle h, const double* A, uint64_t n, double* out);                                /* matrix-sqrt :479 */
+int32_t qcb_la_spectral_norm(qcb_handle h, const double* A, uint64_t m, uint64_t n, double* out);                  /* spectral-norm :500 */
+int32_t qcb_la_condition_number(qcb_handle h, const double* A, uint64_t m, uint64_t n, double* out);               /* condition-number :510 */
+
 #ifdef __cplusplus
 }
 #endif

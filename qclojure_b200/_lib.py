@@ -94,6 +94,26 @@ _PROTOS = {
     "qcb_la_trace": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "qcb_la_norm2": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, _P(C.c_double)]),
     "qcb_la_axpby": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    # host-side protocol methods (la_host.cpp): handle may be NULL
+    "qcb_la_hadamard": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "qcb_la_transpose": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
+    "qcb_la_solve": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "qcb_la_inverse": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "qcb_la_is_hermitian": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, _P(C.c_int32)]),
+    "qcb_la_is_diagonal": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, _P(C.c_int32)]),
+    "qcb_la_is_unitary": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, _P(C.c_int32)]),
+    "qcb_la_is_positive_semidefinite": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, _P(C.c_int32)]),
+    "qcb_la_eigen_hermitian": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "qcb_la_eigen_general": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "qcb_la_svd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qcb_la_lu": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qcb_la_qr": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "qcb_la_cholesky": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "qcb_la_matrix_exp": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "qcb_la_matrix_log": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "qcb_la_matrix_sqrt": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "qcb_la_spectral_norm": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, _P(C.c_double)]),
+    "qcb_la_condition_number": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, _P(C.c_double)]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 

@@ -18,6 +18,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "kernels.h"
 #include "tile_core.h"
 
@@ -576,12 +578,16 @@ template <int NG, int WPG>
 static cudaError_t launch_tile_stage_t(bool mma_only, unsigned grid, size_t smem, size_t limit, cudaStream_t stream, double2* state,
                                        const uint64_t* stage_dev, uint32_t stage_words, const double* dev_vals, uint64_t n_active,
                                        uint32_t nbuf, const CUtensorMap& tmap, uint32_t use_tma) {
-  static bool configured = false;
-  if (!configured) {
+  // function attributes are per device: handles on different GPUs may live in one process
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t dev_bit = 1ULL << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & dev_bit)) {
     cudaError_t e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.fetch_or(dev_bit, std::memory_order_release);
   }
   const unsigned threads = (NG * WPG + MOVER_WARPS) * 32;
   if (mma_only) k_tile_stage<NG, WPG, true><<<grid, threads, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active, nbuf, tmap, use_tma);
@@ -602,12 +608,20 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   const uint64_t n_active = (1ULL << nb) >> __builtin_popcountll(sc.skip_mask & tmask);
   if (out_active) *out_active = n_active;
   // TMA mode needs a tensor map whose box is one run of 2^c amplitudes (c >= 3: at least one 128-byte row)
+  {
+    // experiment knobs live in per-device __device__ symbols: set them once per device
+    static std::atomic<uint64_t> knobs_set{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t dev_bit = 1ULL << (dev & 63);
+    if (!(knobs_set.load(std::memory_order_acquire) & dev_bit)) {
 #ifdef QCB_TILE_PROFILE
-  static const int dbg_once = [] { const char* e = getenv("QCB_TILE_DBG"); int v = e ? atoi(e) : 0; cudaMemcpyToSymbol(g_tile_dbg, &v, sizeof v); return v; }();
-  (void)dbg_once;
+      { const char* e = getenv("QCB_TILE_DBG"); int v = e ? atoi(e) : 0; cudaMemcpyToSymbol(g_tile_dbg, &v, sizeof v); }
 #endif
-  static const unsigned pause_once = [] { const char* e = getenv("QCB_MOVER_PAUSE_NS"); unsigned v = e ? (unsigned)atoi(e) : 0u; cudaMemcpyToSymbol(g_mover_pause_ns, &v, sizeof v); return v; }();
-  (void)pause_once;
+      { const char* e = getenv("QCB_MOVER_PAUSE_NS"); unsigned v = e ? (unsigned)atoi(e) : 0u; cudaMemcpyToSymbol(g_mover_pause_ns, &v, sizeof v); }
+      knobs_set.fetch_or(dev_bit, std::memory_order_release);
+    }
+  }
   static const bool no_tma = getenv("QCB_NO_TMA") != nullptr;
   static const CUtensorMap dummy_map = {};
   const uint32_t use_tma = (!no_tma && maps && sc.c >= 3 && sc.c <= 11 && maps->valid[sc.c]) ? 1u : 0u;

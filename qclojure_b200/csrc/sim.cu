@@ -23,6 +23,7 @@
 
 #include "../../include/qcb200.h"
 #include "kernels.h"
+#include "la_host.h"
 #include "plan.h"
 
 using namespace qcb;
@@ -1452,6 +1453,102 @@ int32_t qcb_la_norm2(qcb_handle h, const double* x, uint64_t n, double* out) {
   *out = std::sqrt(v[0]);
   return QCB_OK;
 }
+
+// ---- P2, host side: decompositions, matrix functions, predicates (la_host.cpp).  Small dense matrices, no GPU work:
+// `h` may be NULL (errors then go to the global slot read by qcb_last_error(NULL, ...)).
+#define LA_ARGS(cond) do { if (!(cond)) return fail(h, QCB_ERR_INVALID, "null argument or empty matrix"); } while (0)
+#define LA_LOCK std::unique_lock<std::recursive_mutex> _lk; if (h) _lk = std::unique_lock<std::recursive_mutex>(h->mu)
+int32_t qcb_la_hadamard(qcb_handle h, const double* A, const double* B, uint64_t n, double* C) {
+  LA_LOCK; LA_ARGS(A && B && C);
+  la_hadamard(A, B, n, C); return QCB_OK;
+}
+int32_t qcb_la_transpose(qcb_handle h, const double* A, uint64_t rows, uint64_t cols, int32_t conjugate, double* out) {
+  LA_LOCK; LA_ARGS(A && out);
+  la_transpose(A, rows, cols, conjugate, out); return QCB_OK;
+}
+int32_t qcb_la_solve(qcb_handle h, const double* A, const double* B, uint64_t n, uint64_t nrhs, double* X) {
+  LA_LOCK; LA_ARGS(A && B && X && n && nrhs);
+  std::string err;
+  return la_solve(A, B, n, nrhs, X, err) == 0 ? QCB_OK : fail(h, QCB_ERR_STATE, err);
+}
+int32_t qcb_la_inverse(qcb_handle h, const double* A, uint64_t n, double* out) {
+  LA_LOCK; LA_ARGS(A && out && n);
+  std::string err;
+  return la_inverse(A, n, out, err) == 0 ? QCB_OK : fail(h, QCB_ERR_STATE, err);
+}
+int32_t qcb_la_is_hermitian(qcb_handle h, const double* A, uint64_t n, double eps, int32_t* out) {
+  LA_LOCK; LA_ARGS(A && out);
+  *out = la_is_hermitian(A, n, eps); return QCB_OK;
+}
+int32_t qcb_la_is_diagonal(qcb_handle h, const double* A, uint64_t n, double eps, int32_t* out) {
+  LA_LOCK; LA_ARGS(A && out);
+  *out = la_is_diagonal(A, n, eps); return QCB_OK;
+}
+int32_t qcb_la_is_unitary(qcb_handle h, const double* A, uint64_t n, double eps, int32_t* out) {
+  LA_LOCK; LA_ARGS(A && out);
+  *out = la_is_unitary(A, n, eps); return QCB_OK;
+}
+int32_t qcb_la_is_positive_semidefinite(qcb_handle h, const double* A, uint64_t n, double eps, int32_t* out) {
+  LA_LOCK; LA_ARGS(A && out && n);
+  std::string err;
+  const int r = la_is_psd(A, n, eps, err);
+  if (r < 0) return fail(h, QCB_ERR_INVALID, err);
+  *out = r; return QCB_OK;
+}
+int32_t qcb_la_eigen_hermitian(qcb_handle h, const double* A, uint64_t n, double* eigenvalues, double* eigenvectors) {
+  LA_LOCK; LA_ARGS(A && eigenvalues && eigenvectors && n);
+  la_eigh(A, n, eigenvalues, eigenvectors); return QCB_OK;
+}
+int32_t qcb_la_eigen_general(qcb_handle h, const double* A, uint64_t n, double* eigenvalues, double* eigenvectors) {
+  LA_LOCK; LA_ARGS(A && eigenvalues && eigenvectors && n);
+  std::string err;
+  return la_eig(A, n, eigenvalues, eigenvectors, err) == 0 ? QCB_OK : fail(h, QCB_ERR_STATE, err);
+}
+int32_t qcb_la_svd(qcb_handle h, const double* A, uint64_t m, uint64_t n, double* U, double* S, double* Vh) {
+  LA_LOCK; LA_ARGS(A && U && S && Vh && m && n);
+  la_svd(A, m, n, U, S, Vh); return QCB_OK;
+}
+int32_t qcb_la_lu(qcb_handle h, const double* A, uint64_t n, double* P, double* L, double* U) {
+  LA_LOCK; LA_ARGS(A && P && L && U && n);
+  la_lu(A, n, P, L, U); return QCB_OK;
+}
+int32_t qcb_la_qr(qcb_handle h, const double* A, uint64_t m, uint64_t n, double* Q, double* R) {
+  LA_LOCK; LA_ARGS(A && Q && R && m && n);
+  la_qr(A, m, n, Q, R); return QCB_OK;
+}
+int32_t qcb_la_cholesky(qcb_handle h, const double* A, uint64_t n, double* L) {
+  LA_LOCK; LA_ARGS(A && L && n);
+  std::string err;
+  return la_cholesky(A, n, L, err) == 0 ? QCB_OK : fail(h, QCB_ERR_STATE, err);
+}
+int32_t qcb_la_matrix_exp(qcb_handle h, const double* A, uint64_t n, double* out) {
+  LA_LOCK; LA_ARGS(A && out && n);
+  la_expm(A, n, out); return QCB_OK;
+}
+int32_t qcb_la_matrix_log(qcb_handle h, const double* A, uint64_t n, double* out) {
+  LA_LOCK; LA_ARGS(A && out && n);
+  std::string err;
+  return la_logm(A, n, out, err) == 0 ? QCB_OK : fail(h, QCB_ERR_STATE, err);
+}
+int32_t qcb_la_matrix_sqrt(qcb_handle h, const double* A, uint64_t n, double* out) {
+  LA_LOCK; LA_ARGS(A && out && n);
+  std::string err;
+  return la_sqrtm(A, n, out, err) == 0 ? QCB_OK : fail(h, QCB_ERR_STATE, err);
+}
+int32_t qcb_la_spectral_norm(qcb_handle h, const double* A, uint64_t m, uint64_t n, double* out) {
+  LA_LOCK; LA_ARGS(A && out && m && n);
+  std::vector<double> s;
+  la_singular_values(A, m, n, s);
+  *out = s.empty() ? 0.0 : s[0]; return QCB_OK;
+}
+int32_t qcb_la_condition_number(qcb_handle h, const double* A, uint64_t m, uint64_t n, double* out) {
+  LA_LOCK; LA_ARGS(A && out && m && n);
+  std::vector<double> s;
+  la_singular_values(A, m, n, s);
+  *out = (s.empty() || s.back() <= 0.0) ? HUGE_VAL : s[0] / s.back(); return QCB_OK;
+}
+#undef LA_ARGS
+#undef LA_LOCK
 int32_t qcb_la_trace(qcb_handle h, const double* A, uint64_t n, double out[2]) {
   ENTER(h);
   if (!A || !out) return fail(h, QCB_ERR_INVALID, "null argument");

@@ -21,12 +21,19 @@ def _c(a):
 
 
 class B200ComplexBackend:
-    def __init__(self, device: int = -1):
-        self._sv = L.StateVector(1, device=device)
-        self._lib, self._h = self._sv._lib, self._sv._h
+    """`host_only=True` skips the device handle: the decompositions / matrix functions / predicates below run on the
+    host inside libqcb200 (qcb_la_* with a NULL handle); the MatrixAlgebra products need the GPU handle."""
+
+    def __init__(self, device: int = -1, host_only: bool = False):
+        if host_only:
+            self._sv, self._lib, self._h = None, L.load(), None
+        else:
+            self._sv = L.StateVector(1, device=device)
+            self._lib, self._h = self._sv._lib, self._sv._h
 
     def close(self):
-        self._sv.close()
+        if self._sv is not None:
+            self._sv.close()
 
     def __enter__(self):
         return self
@@ -102,3 +109,132 @@ class B200ComplexBackend:
 
     def scale(self, A, alpha):
         return self._axpby(alpha, A, 0.0, None)
+
+    # ------------------------------------------------------------------ host-side protocol methods (la_host.cpp)
+    def _sq(self, A):
+        A = _c(A)
+        assert A.ndim == 2 and A.shape[0] == A.shape[1], "square matrix expected"
+        return A, A.shape[0]
+
+    def hadamard_product(self, A, B):
+        A, B = _c(A), _c(B)
+        out = np.empty_like(A)
+        self._ck(self._lib.qcb_la_hadamard(self._h, A.ctypes.data, B.ctypes.data, A.size, out.ctypes.data))
+        return out
+
+    def transpose(self, A, conjugate: bool = False):
+        A = _c(A)
+        out = np.empty((A.shape[1], A.shape[0]), dtype=np.complex128)
+        self._ck(self._lib.qcb_la_transpose(self._h, A.ctypes.data, A.shape[0], A.shape[1], int(conjugate), out.ctypes.data))
+        return out
+
+    def conjugate_transpose(self, A):
+        return self.transpose(A, True)
+
+    def negate(self, A):
+        return -_c(A)
+
+    def shape(self, A):
+        return list(np.shape(A))
+
+    def solve_linear_system(self, A, b):
+        A, n = self._sq(A)
+        b = _c(b)
+        B = b.reshape(n, -1)
+        out = np.empty_like(B)
+        self._ck(self._lib.qcb_la_solve(self._h, A.ctypes.data, np.ascontiguousarray(B).ctypes.data, n, B.shape[1], out.ctypes.data))
+        return out.reshape(b.shape)
+
+    def inverse(self, A):
+        A, n = self._sq(A)
+        out = np.empty_like(A)
+        self._ck(self._lib.qcb_la_inverse(self._h, A.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def _pred(self, fn, A, eps):
+        A, n = self._sq(A)
+        v = C.c_int32()
+        self._ck(fn(self._h, A.ctypes.data, n, C.c_double(eps), C.byref(v)))
+        return bool(v.value)
+
+    def is_hermitian(self, A, eps: float = 1e-12):
+        return self._pred(self._lib.qcb_la_is_hermitian, A, eps)
+
+    def is_diagonal(self, A, eps: float = 1e-12):
+        return self._pred(self._lib.qcb_la_is_diagonal, A, eps)
+
+    def is_unitary(self, U, eps: float = 1e-12):
+        return self._pred(self._lib.qcb_la_is_unitary, U, eps)
+
+    def is_positive_semidefinite(self, A, eps: float = 1e-12):
+        return self._pred(self._lib.qcb_la_is_positive_semidefinite, A, eps)
+
+    def eigen_hermitian(self, A):
+        A, n = self._sq(A)
+        w = np.empty(n, dtype=np.float64)
+        v = np.empty((n, n), dtype=np.complex128)
+        self._ck(self._lib.qcb_la_eigen_hermitian(self._h, A.ctypes.data, n, w.ctypes.data, v.ctypes.data))
+        return {"eigenvalues": w, "eigenvectors": [v[k].copy() for k in range(n)]}
+
+    def eigen_general(self, A):
+        A, n = self._sq(A)
+        w = np.empty(n, dtype=np.complex128)
+        v = np.empty((n, n), dtype=np.complex128)
+        self._ck(self._lib.qcb_la_eigen_general(self._h, A.ctypes.data, n, w.ctypes.data, v.ctypes.data))
+        return {"eigenvalues": w, "eigenvectors": [v[k].copy() for k in range(n)]}
+
+    def svd(self, A):
+        A = _c(A)
+        m, n = A.shape
+        U = np.empty((m, m), dtype=np.complex128)
+        S = np.empty(min(m, n), dtype=np.float64)
+        Vh = np.empty((n, n), dtype=np.complex128)
+        self._ck(self._lib.qcb_la_svd(self._h, A.ctypes.data, m, n, U.ctypes.data, S.ctypes.data, Vh.ctypes.data))
+        return {"U": U, "S": S, "V†": Vh}
+
+    def lu_decomposition(self, A):
+        A, n = self._sq(A)
+        P, Lm, U = (np.empty((n, n), dtype=np.complex128) for _ in range(3))
+        self._ck(self._lib.qcb_la_lu(self._h, A.ctypes.data, n, P.ctypes.data, Lm.ctypes.data, U.ctypes.data))
+        return {"P": P, "L": Lm, "U": U}
+
+    def qr_decomposition(self, A):
+        A = _c(A)
+        m, n = A.shape
+        Q = np.empty((m, m), dtype=np.complex128)
+        R = np.empty((m, n), dtype=np.complex128)
+        self._ck(self._lib.qcb_la_qr(self._h, A.ctypes.data, m, n, Q.ctypes.data, R.ctypes.data))
+        return {"Q": Q, "R": R}
+
+    def cholesky_decomposition(self, A):
+        A, n = self._sq(A)
+        Lm = np.empty((n, n), dtype=np.complex128)
+        self._ck(self._lib.qcb_la_cholesky(self._h, A.ctypes.data, n, Lm.ctypes.data))
+        return {"L": Lm}
+
+    def _fun(self, fn, A):
+        A, n = self._sq(A)
+        out = np.empty_like(A)
+        self._ck(fn(self._h, A.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def matrix_exp(self, A):
+        return self._fun(self._lib.qcb_la_matrix_exp, A)
+
+    def matrix_log(self, A):
+        return self._fun(self._lib.qcb_la_matrix_log, A)
+
+    def matrix_sqrt(self, A):
+        return self._fun(self._lib.qcb_la_matrix_sqrt, A)
+
+    def spectral_norm(self, A):
+        A = _c(A)
+        v = C.c_double()
+        self._ck(self._lib.qcb_la_spectral_norm(self._h, A.ctypes.data, A.shape[0], A.shape[1], C.byref(v)))
+        return float(v.value)
+
+    def condition_number(self, A):
+        A = _c(A)
+        v = C.c_double()
+        self._ck(self._lib.qcb_la_condition_number(self._h, A.ctypes.data, A.shape[0], A.shape[1], C.byref(v)))
+        return float(v.value)
