@@ -28,6 +28,7 @@ import numpy as np
 from . import _lib as L
 from . import noise as NZ
 from . import ops as OPS
+from . import results as RS
 
 _job_counter = itertools.count(1)
 _jobs_lock = threading.Lock()
@@ -262,84 +263,9 @@ class B200Simulator(_BackendBase):
                          "circuit-metadata": circuit_metadata(circuit)}
         results["final-state"] = ({"state-vector": sv.get_state(), "num-qubits": n} if n <= self.max_state_qubits
                                   else DeviceStateHandle(sv))
-        ms = _opt(specs, "measurements")
-        if ms:
-            shots = int(_opt(ms, "shots") or 1)               # result.clj:573 — top-level :shots is ignored
-            outcomes = sv.sample(self._uniforms(options, (shots,)))
-            vals, counts = np.unique(outcomes, return_counts=True)
-            freq = {int(v): int(c) for v, c in zip(vals, counts)}
-            results["measurement-results"] = {
-                "measurement-outcomes": outcomes.tolist(),
-                "measurement-probabilities": sv.probabilities() if n <= self.max_state_qubits else DeviceStateHandle(sv),
-                "empirical-probabilities": {k: v / shots for k, v in freq.items()},
-                "shot-count": shots, "measurement-qubits": list(_opt(ms, "qubits") or range(n)),
-                "frequencies": freq, "source": "ideal-simulation"}
-        ham = _opt(specs, "hamiltonian")
-        if ham:
-            if isinstance(ham, dict):                        # noisy-path spelling {:hamiltonian H}
-                ham = _opt(ham, "hamiltonian")
-            results["hamiltonian-result"] = {"energy-expectation": sv.expect_hamiltonian(ham), "hamiltonian": ham}
-        ex = _opt(specs, "expectation")
-        if ex:
-            results["expectation-results"] = self._expect(sv, ex, variance=False)
-        va = _opt(specs, "variance")
-        if va:
-            results["variance-results"] = self._expect(sv, va, variance=True)
-        pr = _opt(specs, "probabilities")
-        if pr:
-            targets = _opt(pr, "targets")
-            if targets:
-                idx = [int(sum(int(b) << (len(t) - 1 - i) for i, b in enumerate(t))) if isinstance(t, (list, tuple)) else int(t)
-                       for t in targets]
-                amps = sv.get_amplitudes(idx)
-                results["probability-results"] = {
-                    "probability-outcomes": {(tuple(t) if isinstance(t, (list, tuple)) else t): float(abs(a) ** 2)
-                                             for t, a in zip(targets, amps)},
-                    "target-states": targets, "target-qubits": _opt(pr, "qubits")}
-            else:
-                allp = sv.probabilities()
-                results["probability-results"] = {"probability-outcomes": dict(enumerate(allp.tolist())) if n <= 16 else None,
-                                                  "target-qubits": list(_opt(pr, "qubits") or range(n)),
-                                                  "all-probabilities": allp}
-        am = _opt(specs, "amplitudes")
-        if am:
-            bs = list(_opt(am, "basis-states"))
-            results["amplitude-results"] = {"amplitude-values": dict(zip(bs, sv.get_amplitudes(bs).tolist())), "basis-states": bs}
-        if _opt(specs, "state-vector"):
-            results["state-vector-result"] = {"state-vector": sv.get_state(), "num-qubits": n}
-        if _opt(specs, "density-matrix"):
-            if n > 12:
-                raise ValueError("density-matrix result is limited to 12 qubits (4^n entries)")
-            st = sv.get_state()
-            rho = np.outer(st, np.conj(st))
-            results["density-matrix-result"] = {"density-matrix": rho, "num-qubits": n,
-                                                "trace-valid": bool(abs(np.trace(rho) - 1.0) < 1e-8)}
-        fi = _opt(specs, "fidelity")
-        if fi:
-            refs = _opt(fi, "references") or _opt(fi, "reference-states") or []
-            results["fidelity-results"] = {"fidelities": {f"reference-{i}": sv.fidelity(
-                np.asarray(r.get("state-vector", r.get(":state-vector")) if isinstance(r, dict) else r)) for i, r in enumerate(refs)}}
+        results.update(RS.extract_results(sv, specs, lambda shape: self._uniforms(options, shape),
+                                          max_state_qubits=self.max_state_qubits, state_handle=DeviceStateHandle(sv)))
         return {"job-status": "completed", "results": results}
-
-    @staticmethod
-    def _expect(sv, spec, variance: bool):
-        out = []
-        obs = _opt(spec, "observables") or []
-        targets = _opt(spec, "targets") or _opt(spec, "target-qubits") or [None] * len(obs)
-        for o, t in zip(obs, targets):
-            o = np.asarray(o, dtype=np.complex128)
-            if t is None:
-                if o.shape != (2, 2) or sv.n != 1:
-                    raise ValueError("full-register observables must be given as Pauli strings (use :hamiltonian)")
-                t = 0
-            e = sv.expect_1q(o, int(t))
-            if variance:
-                e2 = sv.expect_1q(o @ o, int(t))
-                v = e2 - e * e
-                out.append({"variance-value": v, "standard-deviation": float(np.sqrt(max(v, 0.0))), "observable": o, "target-qubits": [t]})
-            else:
-                out.append({"expectation-value": e, "observable": o, "target-qubits": [t]})
-        return out
 
 
 def create_simulator(config: Optional[dict] = None) -> B200Simulator:
@@ -399,22 +325,11 @@ class B200HardwareSimulator(_BackendBase):
                 rho = sum(np.outer(t, np.conj(t)) for t in traj) / len(traj)
                 results["density-matrix"] = rho
                 results["density-matrix-trace"] = float(np.trace(rho).real)
-            if specs:
-                ham = _opt(specs, "hamiltonian")
-                if ham:
-                    H = _opt(ham, "hamiltonian") if isinstance(ham, dict) else ham
-                    es = []
-                    with L.StateVector(n) as tmp:
-                        for t in traj:
-                            tmp.set_state(t)
-                            es.append(tmp.expect_hamiltonian(H))
-                    # Tr(rho H) with rho the mean projector = mean over trajectories
-                    results["hamiltonian-result"] = {"energy-expectation": float(np.mean(es)), "hamiltonian": H}
-        if specs and _opt(specs, "measurements") is not None:
-            total = sum(counts.values())
-            results["measurement-results-detail"] = {
-                "measurement-outcomes": list(counts), "empirical-probabilities": {k: v / total for k, v in counts.items()},
-                "shot-count": total, "frequencies": counts, "source": "noisy-simulation"}
+        if specs:                                                      # result.clj:642-804
+            results["shots-executed"] = shots
+            results = RS.extract_noisy_results(results, specs, n, lambda: L.StateVector(n),
+                                               lambda shape: self._uniforms(options, shape))
+            results.pop("shots-executed", None)
         return {"job-status": "completed", "circuit": circuit, "circuit-metadata": circuit_metadata(circuit),
                 "shots-executed": shots, "results": results}
 

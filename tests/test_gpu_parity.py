@@ -455,6 +455,81 @@ def test_job_layer():
     sim.close()
 
 
+def test_result_extraction_every_spec_on_device():
+    """every result spec of result.clj:535-639 through the backend on the real device state."""
+    from qclojure_b200 import backend as B
+    sim = B.create_simulator()
+    circ = C.ghz_state_circuit(6)
+    C.ry(circ, 2, 0.9); C.rx(circ, 5, 0.3)
+    psi = O.execute_circuit(circ)
+    H = [{"coefficient": 0.5, "pauli-string": "ZZIIII"}, {"coefficient": -0.25, "pauli-string": "XXXXXX"}]
+    full = np.kron(np.kron(O.PAULI_Z, O.PAULI_X), np.eye(16))
+    specs = {"measurements": {"shots": 128}, "expectation": {"observables": [O.PAULI_Z, O.PAULI_X], "targets": [0, 2]},
+             "variance": {"observables": [O.PAULI_Z], "targets": [2]}, "hamiltonian": H,
+             "probabilities": {"targets": [[1, 1, 1, 1, 1, 1], 0]}, "amplitudes": {"basis-states": [0, 63]},
+             "state-vector": True, "density-matrix": True, "fidelity": {"references": [O.zero_state(6), psi]},
+             "sample": {"observables": [O.PAULI_Z], "shots": 64, "targets": [2]}}
+    u = np.random.default_rng(3).random(128 + 64)
+    res = B.execute_circuit(sim, circ, {"result-specs": specs, "uniforms": u})
+    assert res["job-status"] == "completed", res
+    r = res["results"]
+    assert r["measurement-results"]["measurement-outcomes"] == O.sample_outcomes(psi, u[:128]).tolist()
+    assert abs(r["expectation-results"][1]["expectation-value"] - O.expectation_1q(psi, O.PAULI_X, 2)) <= TOL
+    assert abs(r["variance-results"][0]["variance-value"] - O.variance_1q(psi, O.PAULI_Z, 2)) <= TOL
+    assert abs(r["hamiltonian-result"]["energy-expectation"] - O.hamiltonian_expectation(H, psi)) <= TOL
+    assert abs(r["probability-results"]["probability-outcomes"][(1, 1, 1, 1, 1, 1)] - abs(psi[63]) ** 2) <= TOL
+    assert abs(r["amplitude-results"]["amplitude-values"][63] - psi[63]) <= TOL
+    assert np.max(np.abs(r["state-vector-result"]["state-vector"] - psi)) <= TOL
+    assert np.max(np.abs(r["density-matrix-result"]["density-matrix"] - np.outer(psi, psi.conj()))) <= TOL
+    assert r["density-matrix-result"]["trace-valid"]
+    assert abs(r["fidelity-results"]["fidelities"]["reference-1"] - 1.0) <= TOL
+    assert abs(r["fidelity-results"]["fidelities"]["reference-0"] - abs(psi[0])) <= TOL
+    sa = r["sample-results"][0]
+    from qclojure_b200 import results as RS
+    p_up = (1 + O.expectation_1q(psi, O.PAULI_Z, 2)) / 2
+    assert sa["sample-outcomes"] == RS.sample_eigenvalues({-1.0: 1 - p_up, 1.0: p_up}, u[:64])
+    # full-register dense observable through the P2 ops (result.clj:279-280)
+    res = B.execute_circuit(sim, circ, {"result-specs": {"expectation": {"observables": [full]}}})
+    assert abs(res["results"]["expectation-results"][0]["expectation-value"] - np.vdot(psi, full @ psi).real) <= TOL
+    sim.close()
+
+
+def test_hardware_simulator_backend_and_noisy_extraction():
+    """hardware_simulator.clj:84-240 + result.clj:642-804 through the protocol methods: counts identical to the oracle on
+    the same draws, Tr(rho O) quantities equal to the density-matrix formulas."""
+    from qclojure_b200 import backend as B
+    with open(os.path.join(GOLDEN, "device_profiles.json")) as f:
+        nm = [d for d in json.load(f)["devices"] if d["id"] == ":ibm-lagos"][0]["noise_model"]
+    n, shots = 4, 80
+    circ = C.ghz_state_circuit(n)
+    C.rx(circ, 3, 0.4)
+    dps = O.draws_per_shot(circ, nm)
+    u = np.random.default_rng(9).random((shots, dps))
+    want = O.run_noisy(circ, nm, u, max_trajectories=100)
+    rho = O.trajectory_to_density_matrix(want["trajectories"])
+    H = [{"coefficient": 1.0, "pauli-string": "ZZII"}, {"coefficient": 0.5, "pauli-string": "IIXX"}]
+    Hm = np.kron(np.kron(O.PAULI_Z, O.PAULI_Z), np.eye(4)) + 0.5 * np.kron(np.eye(4), np.kron(O.PAULI_X, O.PAULI_X))
+    sim = B.create_hardware_simulator({"id": "ibm-lagos", "noise-model": nm})
+    res = B.execute_circuit(sim, circ, {"shots": shots, "uniforms": u})
+    assert res["job-status"] == "completed", res
+    assert res["shots-executed"] == shots and res["results"]["measurement-results"] == want["measurement-results"]
+    assert np.max(np.abs(res["results"]["density-matrix"] - rho)) <= TOL
+    specs = {"measurements": {}, "hamiltonian": {"hamiltonian": H}, "probability": {"target-states": [0, 15]},
+             "expectation": {"observables": [O.PAULI_Z], "target-qubits": [1]}, "density-matrix": True}
+    res = B.execute_circuit(sim, circ, {"shots": shots, "uniforms": u, "result-specs": specs})
+    r = res["results"]
+    assert r["measurement-results"]["frequencies"] == want["measurement-results"]
+    assert abs(r["hamiltonian-result"]["energy-expectation"] - np.trace(rho @ Hm).real) <= TOL
+    Z1 = np.kron(np.kron(np.eye(2), O.PAULI_Z), np.eye(4))
+    assert abs(r["expectation-results"][0] - np.trace(rho @ Z1).real) <= TOL
+    assert abs(r["probability-results"]["probability-outcomes"][15] - rho[15, 15].real) <= TOL
+    assert r["density-matrix-result"]["from-trajectories"] is True
+    # the bare :hamiltonian spelling the variational objective sends (variational_algorithm.clj:345)
+    res = B.execute_circuit(sim, circ, {"shots": shots, "uniforms": u, "result-specs": {"hamiltonian": H}})
+    assert abs(res["results"]["hamiltonian-result"]["energy-expectation"] - np.trace(rho @ Hm).real) <= TOL
+    sim.close()
+
+
 def test_c_job_api():
     """qcb_submit / qcb_job_status / qcb_job_result_get / qcb_cancel / qcb_queue_status through ctypes."""
     import ctypes as CT
