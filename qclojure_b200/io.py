@@ -248,12 +248,18 @@ def import_quantum_state(fmt: str, filename: str) -> dict:
 
 
 def export_quantum_circuit(fmt: str, circuit: dict, filename: str) -> bool:
+    if str(fmt).lstrip(":").lower() == "qasm3":              # adapter/io/qasm.clj:21-27
+        from . import qasm3
+        return qasm3.export_quantum_circuit(circuit, filename)
     with open(filename, "w") as f:
         f.write(_dump(fmt, serialize_quantum_circuit(circuit)))
     return True
 
 
 def import_quantum_circuit(fmt: str, filename: str) -> dict:
+    if str(fmt).lstrip(":").lower() == "qasm3":
+        from . import qasm3
+        return qasm3.import_quantum_circuit(filename)
     with open(filename) as f:
         return deserialize_quantum_circuit(_load(fmt, f.read()))
 
