@@ -11,6 +11,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -1167,8 +1168,43 @@ int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb
   }
   RET(begin_timing(h));
   h->stats.n_ops = n_ops * n_shots;
-  for (uint64_t shot = 0; shot < n_shots; ++shot) {
-    const double* u = uniforms + shot * draws_per_shot;
+  // The Kraus operator applied after a noisy gate is chosen by a draw and a state-independent probability table
+  // (channel.clj:225-233), so without mid-circuit :measure ops the final state of a shot is a function of its sequence of
+  // choices only.  Shots are grouped by that sequence: one state evolution per distinct sequence, then all of the group's
+  // final measure-state draws go through one sampler call.  Same draws -> same outcomes as the shot-by-shot loop.
+  bool has_measure = false;
+  std::vector<uint64_t> choice_draw;                 // draw index of every multi-Kraus choice
+  std::vector<const qcb_noise_entry*> choice_entry;
+  {
+    uint64_t di = 0;
+    for (uint64_t k = 0; k < n_ops; ++k) {
+      if (ops[k].kind == QCB_OP_MEASURE) { has_measure = true; ++di; }
+      const qcb_noise_entry* e = find_noise(noise, ops[k].kind);
+      if (e && e->n_kraus > 1) { choice_draw.push_back(di++); choice_entry.push_back(e); }
+    }
+  }
+  static const bool no_grouping = std::getenv("QCB_NOISY_GROUPING") && std::atoi(std::getenv("QCB_NOISY_GROUPING")) == 0;
+  std::vector<std::vector<uint64_t>> groups;         // shot indices per distinct choice sequence
+  if (has_measure || no_grouping) {
+    groups.resize(n_shots);
+    for (uint64_t s = 0; s < n_shots; ++s) groups[s].push_back(s);
+  } else {
+    std::map<std::string, size_t> index;
+    std::string sig(choice_draw.size(), '\0');
+    for (uint64_t s = 0; s < n_shots; ++s) {
+      const double* u = uniforms + s * draws_per_shot;
+      for (size_t c = 0; c < choice_draw.size(); ++c) sig[c] = (char)select_kraus(choice_entry[c], u[choice_draw[c]]);
+      auto it = index.find(sig);
+      if (it == index.end()) { it = index.emplace(sig, groups.size()).first; groups.emplace_back(); }
+      groups[it->second].push_back(s);
+    }
+    // the handle keeps the LAST shot's state (:final-state, hardware_simulator.clj:150-160): its group runs last
+    if (n_shots) std::swap(groups[index[sig]], groups.back());
+  }
+  std::vector<double> us;
+  std::vector<uint64_t> outs;
+  for (const auto& grp : groups) {
+    const double* u = uniforms + grp[0] * draws_per_shot;
     uint64_t di = 0;
     CU(h, cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream));
     CU(h, launch_set_amp(h->state, 0, 1.0, 0.0, h->stream));
@@ -1199,24 +1235,32 @@ int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb
       }
     }
     RET(flush());
-    // final measurement with readout noise (noise.clj:193-202)
-    uint64_t outcome = 0;
-    RET(sample_impl(h, &u[di++], 1, &outcome));
-    if (noise && noise->has_readout) {
-      std::vector<int> flipped;
-      for (int q = 0; q < n; ++q) {
-        const int bitpos = n - 1 - q;
-        const int orig = (outcome >> bitpos) & 1;
-        double factor = 1.0;
-        if (noise->correlation) for (int src : flipped) factor *= noise->correlation[(size_t)src * n + q];
-        double eff = (orig ? noise->prob_1_to_0 : noise->prob_0_to_1) * factor;
-        eff = std::min(1.0, std::max(0.0, eff));
-        if (u[di++] < eff) { outcome ^= 1ULL << bitpos; flipped.push_back(q); }
+    // final measurement of every shot of the group (one measure-state draw each), then readout noise (noise.clj:193-202)
+    us.resize(grp.size());
+    outs.assign(grp.size(), 0);
+    for (size_t j = 0; j < grp.size(); ++j) us[j] = uniforms[grp[j] * draws_per_shot + di];
+    RET(sample_impl(h, us.data(), grp.size(), outs.data()));
+    for (size_t j = 0; j < grp.size(); ++j) {
+      const double* uj = uniforms + grp[j] * draws_per_shot;
+      uint64_t dj = di + 1;
+      uint64_t outcome = outs[j];
+      if (noise && noise->has_readout) {
+        std::vector<int> flipped;
+        for (int q = 0; q < n; ++q) {
+          const int bitpos = n - 1 - q;
+          const int orig = (outcome >> bitpos) & 1;
+          double factor = 1.0;
+          if (noise->correlation) for (int src : flipped) factor *= noise->correlation[(size_t)src * n + q];
+          double eff = (orig ? noise->prob_1_to_0 : noise->prob_0_to_1) * factor;
+          eff = std::min(1.0, std::max(0.0, eff));
+          if (uj[dj++] < eff) { outcome ^= 1ULL << bitpos; flipped.push_back(q); }
+        }
       }
+      out_outcomes[grp[j]] = outcome;
+      if (traj_out && grp[j] < max_traj)
+        CU(h, cudaMemcpyAsync(traj_out + grp[j] * 2 * h->local_count, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
     }
-    out_outcomes[shot] = outcome;
-    if (traj_out && shot < max_traj)
-      CU(h, cudaMemcpyAsync(traj_out + shot * 2 * h->local_count, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    // the copies above read h->state, which the next group overwrites: stream order keeps them correct
   }
   CU(h, cudaStreamSynchronize(h->stream));
   end_timing(h);
