@@ -296,6 +296,10 @@ def run_ours(args):
                        "gates": n_gates, "seed": 1000 + n, "l2": "state 16*2^n B >> 126 MB L2, no flush needed",
                        "parallelism": f"top {p} qubits global, NCCL send/recv qubit swaps" if p else "single GPU"},
             "effective_hbm_gbs": stats["unfused_bytes"] * args.steps / (gpu_ms / 1000.0) / 1e9,
+            # weak scaling: the circuit grows by one qubit (twice the amplitudes, ~3 % more gates) per doubling of N, so
+            # gates/s of the whole job cannot grow with N; amplitude updates per second (gates x 2^n / time, all ranks)
+            # is the quantity whose per-GPU share stays constant under perfect weak scaling
+            "amplitude_updates_per_sec": n_gates * float(1 << n) * args.steps / (gpu_ms / 1000.0),
             "sweeps_per_step": stats["n_sweeps"], "rounds_per_step": stats["n_rounds"],
             "gates_per_sweep": n_gates / sweeps,
             "roofline": {"bound": "hbm", "kernel": "k_tile_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
