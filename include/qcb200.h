@@ -209,6 +209,10 @@ int32_t qcb_timer_stop(qcb_handle h, double* out_ms);
         Used by the CPU test-suite and by INTEGRATION diagnostics. ---- */
 typedef struct qcb_plan qcb_plan;
 int32_t qcb_plan_create(const qcb_config* cfg, const qcb_op* ops, uint64_t n_ops, qcb_plan** out);
+/* plans `ops` by REPLAYING the scheduler decisions recorded on `ops_recorded` (same gates and qubits, other angles):
+   what a handle does when a variational loop (VQE / QAOA objective, application/algorithm/variational_algorithm.clj:
+   330-360) submits the same ansatz again.  Fails with QCB_ERR_INVALID when the two lists differ in structure. */
+int32_t qcb_plan_create_replayed(const qcb_config* cfg, const qcb_op* ops_recorded, const qcb_op* ops, uint64_t n_ops, qcb_plan** out);
 int32_t qcb_plan_destroy(qcb_plan* p);
 /* serialises the plan as a flat little-endian word stream (layout documented in csrc/plan.h) */
 int32_t qcb_plan_serialize(const qcb_plan* p, uint64_t* out_words, uint64_t capacity, uint64_t* n_words);

@@ -78,6 +78,7 @@ _PROTOS = {
     "qcb_timer_start": (C.c_int32, [C.c_void_p]),
     "qcb_timer_stop": (C.c_int32, [C.c_void_p, _P(C.c_double)]),
     "qcb_plan_create": (C.c_int32, [_P(OPS.QcbConfig), _P(OPS.QcbOp), C.c_uint64, _P(C.c_void_p)]),
+    "qcb_plan_create_replayed": (C.c_int32, [_P(OPS.QcbConfig), _P(OPS.QcbOp), _P(OPS.QcbOp), C.c_uint64, _P(C.c_void_p)]),
     "qcb_plan_destroy": (C.c_int32, [C.c_void_p]),
     "qcb_plan_serialize": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, _P(C.c_uint64)]),
     "qcb_plan_summary": (C.c_int32, [C.c_void_p, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint64)]),

@@ -635,7 +635,7 @@ static void build_dmma_round(const Config& cfg, const Stage& st, Round& rd) {
     int best = -1;
     std::vector<int> bestl = lanes;
     const int nc = (int)cand.size();
-    for (int i0 = 0; i0 < nc; ++i0) for (int i1 = 0; i1 < nc; ++i1) for (int i2 = 0; i2 < nc; ++i2) {
+    for (int i0 = 0; i0 < nc && best < 2; ++i0) for (int i1 = 0; i1 < nc && best < 2; ++i1) for (int i2 = 0; i2 < nc; ++i2) {
       if (i0 == i1 || i1 == i2 || i0 == i2) continue;
       const int l0 = cand[i0], l1 = cand[i1], l2 = cand[i2];
       int bl = -1, bs = -1;
@@ -807,7 +807,8 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
     if (search && cfg.round_yield_pct > 0 && st.rounds.size() >= 2 && !st.absorbed.empty() &&
         taken.size() * 100 * st.rounds.size() < (size_t)cfg.round_yield_pct * st.absorbed.size()) break;
     Round rd;
-    for (int i : taken) { rd.gates.push_back(pending[i]); st.absorbed.push_back(pending[i].uid); }
+    for (int i : taken) { rd.gates.push_back(pending[i]); st.absorbed.push_back(pending[i].uid); rd.uids.push_back(pending[i].uid); }
+    rd.slot_mask = R;
     std::vector<Gate> next;
     next.reserve(rest.size());
     for (int i : rest) next.push_back(std::move(pending[i]));
@@ -822,7 +823,43 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
   }
 }
 
-int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
+// Rounds of one stage rebuilt from a recorded trace: same gates per round, same slot bits, fresh matrices.
+static void replay_rounds(const Config& cfg, Stage& st, const std::vector<Gate>& gates, const StageTrace& tr) {
+  for (size_t r = 0; r < tr.round_uids.size(); ++r) {
+    Round rd;
+    rd.uids = tr.round_uids[r];
+    rd.slot_mask = tr.round_slots[r];
+    for (int u : rd.uids) {
+      for (const Gate& g : gates) if (g.uid == u) { rd.gates.push_back(g); break; }
+      st.absorbed.push_back(u);
+    }
+    for (int b = 0; b < st.m; ++b) if ((rd.slot_mask >> b) & 1) rd.slot_pos.push_back(b);
+    if (dmma_eligible(cfg, st, rd)) build_dmma_round(cfg, st, rd);
+    else if (cfg.fusion) fuse_round(rd);
+    st.rounds.push_back(std::move(rd));
+  }
+}
+
+void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const std::vector<int>& perm_in, std::vector<uint64_t>& key) {
+  key.clear();
+  key.reserve(16 + perm_in.size() + 6 * gates.size());
+  const int c[] = {cfg.n_total, cfg.n_local, cfg.rank, cfg.world, cfg.tile_bits, cfg.low_bits, cfg.fusion, cfg.max_stage_cost,
+                   cfg.max_stage_rounds, cfg.dense_mma, cfg.round_yield_pct, cfg.window_search, cfg.tma};
+  for (int v : c) key.push_back((uint64_t)(int64_t)v);
+  key.push_back(perm_in.size());
+  for (int v : perm_in) key.push_back((uint64_t)v);
+  key.push_back(gates.size());
+  for (const Gate& g : gates) {
+    const uint64_t sign_flip = g.kind == G_DMASK && g.m[0].re == -1.0 && g.m[0].im == 0.0;
+    key.push_back((uint64_t)g.kind | ((uint64_t)(uint8_t)(g.t0 + 1) << 8) | ((uint64_t)(uint8_t)(g.t1 + 1) << 16) |
+                  ((uint64_t)gate_cost(g) << 24) | (sign_flip << 40));
+    key.push_back(g.cmask);
+    key.push_back(g.dmask);
+    key.push_back(g.dval);
+  }
+}
+
+int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanTrace* record, const PlanTrace* replay) {
   const Config& cfg = plan.cfg;
   const int n = cfg.n_total, nl = cfg.n_local, m = std::min(cfg.tile_bits, nl), L = std::min(cfg.low_bits, m);
   std::vector<int> perm(n);
@@ -937,12 +974,12 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
   // gates into its ext space and form the rounds.  `absorbed_out` = Gate::uid of the gates the formed rounds hold (the round
   // budget / thin-round cut may leave some of `taken` pending).  materialize = false skips the matrix building (scoring).
   auto make_stage = [&](const Gate* lead, uint64_t A, const std::vector<int>& taken, bool materialize, Stage& st,
-                        std::vector<int>& absorbed_out) {
+                        std::vector<int>& absorbed_out, const StageTrace* tr) {     // taken = gate uids
     st = Stage(); st.kind = S_TILE; st.m = m; st.L = L;
     // single-gate stage: keep its condition bits OUT of the tile so that whole tiles can be skipped
     uint64_t avoid = 0;
     if (taken.size() == 1 && !lead) {
-      Gate g = to_phys(plan.gates[pending[taken[0]]]);
+      Gate g = to_phys(plan.gates[taken[0]]);
       if (g.kind == G_MAT1 || g.kind == G_SWAPP || g.kind == G_MAT2 || g.kind == G_DTAB1) avoid = g.cmask;
       else if (g.kind == G_DMASK) avoid = g.dmask;
       avoid &= local_mask;
@@ -967,11 +1004,12 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
     // a prefix of rounds is a valid partial execution because a round only overtakes gates it commutes with)
     std::vector<Gate> eg;
     for (size_t k = 0; k < taken.size(); ++k) {
-      eg.push_back(to_ext(to_phys(plan.gates[pending[taken[k]]]), ext_of_phys));
-      eg.back().uid = pending[taken[k]];
+      eg.push_back(to_ext(to_phys(plan.gates[taken[k]]), ext_of_phys));
+      eg.back().uid = taken[k];
     }
     if (lead) { Round r0; r0.gates.push_back(*lead); st.rounds.push_back(r0); }
-    form_rounds(cfg, st, eg, max_rounds, materialize);
+    if (tr) replay_rounds(cfg, st, eg, *tr);
+    else form_rounds(cfg, st, eg, max_rounds, materialize);
     absorbed_out.swap(st.absorbed);
     st.absorbed.clear();
     st.skip_mask = st.skip_val = 0; st.sweep_fraction = 1.0;
@@ -1005,12 +1043,18 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
       }
     }
     if (taken.empty() && !lead) return 0;          // nothing executable in the current layout (multi-GPU: exchange first)
-    Stage st; std::vector<int> abs_uids;
-    make_stage(lead, A, taken, true, st, abs_uids);
+    Stage st; std::vector<int> abs_uids, taken_uids(taken.size());
+    for (size_t k = 0; k < taken.size(); ++k) taken_uids[k] = pending[taken[k]];
+    make_stage(lead, A, taken_uids, true, st, abs_uids, nullptr);
     std::vector<char> absorbed(plan.gates.size(), 0);
     size_t keep = 0;
     for (int u : abs_uids) if (u >= 0 && !absorbed[u]) { absorbed[u] = 1; ++keep; }
     for (size_t k = 0; k < taken.size(); ++k) if (absorbed[pending[taken[k]]]) st.src_gates.push_back(pending[taken[k]]);
+    if (record) {
+      StageTrace tr; tr.kind = S_TILE; tr.lead = lead != nullptr; tr.tile_bits = A; tr.taken = taken_uids;
+      for (size_t r = lead ? 1 : 0; r < st.rounds.size(); ++r) { tr.round_uids.push_back(st.rounds[r].uids); tr.round_slots.push_back(st.rounds[r].slot_mask); }
+      record->stages.push_back(std::move(tr));
+    }
     plan.stages.push_back(st);
     plan.algorithmic_bytes += sweep_bytes * st.sweep_fraction;
     std::vector<int> rest;
@@ -1019,6 +1063,38 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
     return keep + (lead ? 1 : 0);
   };
 
+  if (record) { record->stages.clear(); plan_structure_key(cfg, plan.gates, perm_in, record->key); }
+  if (replay) {
+    // ---- the decisions come from a trace of a structurally identical circuit: no searching
+    Gate lead_gate;
+    for (const StageTrace& tr : replay->stages) {
+      emit_new_stages();
+      if (sink_rc != QCB_OK) { plan.error = "stage sink failed"; return sink_rc; }
+      if (tr.kind == S_SUM) {
+        Stage s; s.kind = S_SUM; s.src_gates.push_back(tr.lead_uid);
+        plan.stages.push_back(s);
+        plan.algorithmic_bytes += 0.5 * sweep_bytes;
+      } else if (tr.kind == S_EXCHANGE) {
+        std::vector<int> logical_of(n);
+        for (int b = 0; b < n; ++b) logical_of[perm[b]] = b;
+        Stage s; s.kind = S_EXCHANGE; s.gbit = tr.gbit; s.lbit = tr.lbit;
+        plan.stages.push_back(s);
+        plan.n_exchanges++;
+        std::swap(perm[logical_of[tr.gbit]], perm[logical_of[tr.lbit]]);
+      } else {
+        const Gate* lead = nullptr;
+        if (tr.lead) { lead_gate = Gate(); lead_gate.kind = G_REFLECT; lead_gate.src_op = plan.gates[tr.lead_uid].src_op; lead = &lead_gate; }
+        Stage st; std::vector<int> abs_uids;
+        make_stage(lead, tr.tile_bits, tr.taken, true, st, abs_uids, &tr);
+        std::vector<char> absorbed(plan.gates.size(), 0);
+        for (int u : abs_uids) if (u >= 0) absorbed[u] = 1;
+        for (int u : tr.taken) if (absorbed[u]) st.src_gates.push_back(u);
+        plan.stages.push_back(st);
+        plan.algorithmic_bytes += sweep_bytes * st.sweep_fraction;
+      }
+    }
+    pending.clear();
+  }
   while (!pending.empty()) {
     emit_new_stages();
     if (sink_rc != QCB_OK) { plan.error = "stage sink failed"; return sink_rc; }
@@ -1028,8 +1104,11 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
       plan.stages.push_back(s);
       plan.algorithmic_bytes += 0.5 * sweep_bytes;
       Gate a; a.kind = G_REFLECT; a.src_op = plan.gates[pending[0]].src_op;
+      const int reflect_uid = pending[0];
+      if (record) { StageTrace tr; tr.kind = S_SUM; tr.lead_uid = reflect_uid; record->stages.push_back(tr); }
       pending.erase(pending.begin());
       build_tile_stage(&a);
+      if (record) record->stages.back().lead_uid = reflect_uid;
       continue;
     }
     // ---- everything executable in the current layout goes first: gates with a non-diagonal target on a global
@@ -1058,6 +1137,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink) {
       Stage s; s.kind = S_EXCHANGE; s.gbit = gbit; s.lbit = best;
       plan.stages.push_back(s);
       plan.n_exchanges++;
+      if (record) { StageTrace tr; tr.kind = S_EXCHANGE; tr.gbit = gbit; tr.lbit = best; record->stages.push_back(tr); }
       std::swap(perm[logical_of[gbit]], perm[logical_of[best]]);
     }
   }

@@ -94,6 +94,8 @@ struct Round {
   std::vector<int> grp_pos;         // tile-local position of group-index bit i (first 3 = lane bits)
   int j_load = 0, j_store = 0;      // slot index paired with k bit 1 (loads) / m bit 1 (stores): bank-conflict control
   std::vector<double> frag;         // 2^k * 256 doubles in mma.m16n8k16 A-fragment order [variant][reg][lane]
+  std::vector<int> uids;            // Gate::uid of the gates the scheduler put into this round, in order (plan traces)
+  uint64_t slot_mask = 0;           // the slot bits the scheduler chose (before a tensor-core round pads them to 3)
 };
 
 struct Stage {
@@ -139,6 +141,28 @@ struct Plan {
   std::string error;
 };
 
+// ---- plan traces: the scheduler's decisions for one circuit STRUCTURE (which gates share a sweep / a round, tile and slot
+// bits, exchanges), recorded once and replayed for every later circuit with the same structure and different angles
+// (variational loops: VQE / QAOA evaluate the same ansatz thousands of times).  Replay skips the tile-window and
+// slot-triple searches; the matrices are rebuilt from the new gates.  `key` holds everything a decision depends on.
+struct StageTrace {
+  int kind = S_TILE;
+  bool lead = false;                         // S_TILE opened by the affine pass of a Grover diffusion
+  int lead_uid = -1;                         // S_SUM / lead: the G_REFLECT gate
+  uint64_t tile_bits = 0;                    // tile choice handed to the stage builder
+  std::vector<int> taken;                    // gates handed to the stage builder (uids, in order)
+  std::vector<std::vector<int>> round_uids;  // per formed round
+  std::vector<uint64_t> round_slots;
+  int gbit = -1, lbit = -1;                  // S_EXCHANGE
+};
+struct PlanTrace {
+  std::vector<uint64_t> key;
+  std::vector<StageTrace> stages;
+};
+// Everything the scheduler's decisions depend on: configuration, incoming bit permutation, and per gate its kind, bits,
+// cost class and sign-flip flag (never the angles themselves).
+void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const std::vector<int>& perm_in, std::vector<uint64_t>& key);
+
 // qcb_op[] -> Gate[] ; returns QCB_OK or an error code with `err` set.
 int lower_ops(const Config& cfg, const qcb_op* ops, uint64_t n_ops, std::vector<Gate>& out, std::string& err);
 
@@ -150,7 +174,10 @@ struct StageSink {
 };
 
 // Gate[] -> stages (+ encoded program).  perm_in: logical->physical bit map (identity when empty).
-int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink = nullptr);
+// record != nullptr: the decisions are written to *record (its key is filled in).  replay != nullptr: the decisions are
+// taken from *replay instead of searched (the caller has checked that the keys match).
+int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink = nullptr, PlanTrace* record = nullptr,
+             const PlanTrace* replay = nullptr);
 
 // Standard 2x2 matrices of the reference (domain/gate.clj:38-283)
 void gate_matrix(int kind, double angle, cplx out[4]);

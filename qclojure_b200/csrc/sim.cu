@@ -20,6 +20,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/qcb200.h"
@@ -114,6 +115,11 @@ struct qcb_sim {
   unsigned char* d_scratch = nullptr; size_t scratch_cap = 0;  // bytes
   unsigned char* h_pin = nullptr; size_t pin_cap = 0;          // bytes (pinned)
   std::vector<int> perm;                          // logical bit -> physical bit
+  // plan traces by circuit structure (plan.h: PlanTrace): a variational loop re-plans the same ansatz with new angles
+  // every evaluation; a hit replays the recorded decisions and only rebuilds the matrices
+  std::unordered_map<uint64_t, std::vector<std::shared_ptr<PlanTrace>>> traces;
+  size_t n_traces = 0;
+  uint64_t trace_hits = 0, trace_misses = 0;
   qcb_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timing_pending = false;
   cudaEvent_t xev0 = nullptr, xev1 = nullptr;
@@ -429,13 +435,33 @@ int run_gates(qcb_sim* h, std::vector<Gate>&& gates) {
   RET(ensure_prog(h, std::max<size_t>(1 << 17, plan.gates.size() * 512)));
   if (h->prog_ev_valid) CU(h, cudaEventSynchronize(h->prog_ev));      // the previous call's uploads have left the pinned buffer
   StreamingExecutor sink(h);
-  int rc = schedule(plan, h->perm, &sink);
+  // plan-trace cache (QCB_PLAN_CACHE=0 disables it)
+  static const bool cache_on = !(std::getenv("QCB_PLAN_CACHE") && std::atoi(std::getenv("QCB_PLAN_CACHE")) == 0);
+  const bool cacheable = cache_on && plan.gates.size() >= 16 && plan.gates.size() <= (1u << 18);
+  std::shared_ptr<PlanTrace> hit, rec;
+  uint64_t hash = 1469598103934665603ULL;
+  if (cacheable) {
+    rec = std::make_shared<PlanTrace>();
+    plan_structure_key(plan.cfg, plan.gates, h->perm, rec->key);
+    for (uint64_t w : rec->key) { hash ^= w; hash *= 1099511628211ULL; hash ^= hash >> 29; }
+    auto it = h->traces.find(hash);
+    if (it != h->traces.end())
+      for (auto& t : it->second) if (t->key == rec->key) { hit = t; break; }
+  }
+  int rc = schedule(plan, h->perm, &sink, (cacheable && !hit) ? rec.get() : nullptr, hit.get());
   CU(h, cudaEventRecord(h->prog_ev, h->stream));
   h->prog_ev_valid = true;
   if (rc != QCB_OK) {
     // a sink failure has already recorded its own message (CUDA / NCCL error); scheduler errors carry plan.error
     if (plan.error != "stage sink failed") return fail(h, rc, plan.error);
     return rc;
+  }
+  if (hit) ++h->trace_hits;
+  else if (cacheable) {
+    ++h->trace_misses;
+    if (h->n_traces >= 128) { h->traces.clear(); h->n_traces = 0; }
+    h->traces[hash].push_back(rec);
+    ++h->n_traces;
   }
   h->stats.n_gates_lowered += plan.gates.size();
   h->stats.algorithmic_bytes += plan.algorithmic_bytes;
@@ -1310,6 +1336,29 @@ int32_t qcb_plan_create(const qcb_config* cfg, const qcb_op* ops, uint64_t n_ops
   int rc = lower_ops(p->plan.cfg, ops, n_ops, p->plan.gates, err);
   if (rc != QCB_OK) return fail(nullptr, rc, err);
   rc = schedule(p->plan, std::vector<int>());
+  if (rc != QCB_OK) return fail(nullptr, rc, p->plan.error);
+  *out = p.release();
+  return QCB_OK;
+}
+int32_t qcb_plan_create_replayed(const qcb_config* cfg, const qcb_op* ops_recorded, const qcb_op* ops, uint64_t n_ops, qcb_plan** out) {
+  if (!cfg || !out || ((!ops || !ops_recorded) && n_ops)) return fail(nullptr, QCB_ERR_INVALID, "null argument");
+  const Config c = config_from(*cfg);
+  if (c.n_total < 1 || c.n_local < 1) return fail(nullptr, QCB_ERR_INVALID, "n_qubits out of range");
+  std::string err;
+  Plan first; first.cfg = c;
+  int rc = lower_ops(c, ops_recorded, n_ops, first.gates, err);
+  if (rc != QCB_OK) return fail(nullptr, rc, err);
+  PlanTrace trace;
+  rc = schedule(first, std::vector<int>(), nullptr, &trace, nullptr);
+  if (rc != QCB_OK) return fail(nullptr, rc, first.error);
+  std::unique_ptr<qcb_plan> p(new qcb_plan());
+  p->plan.cfg = c;
+  rc = lower_ops(c, ops, n_ops, p->plan.gates, err);
+  if (rc != QCB_OK) return fail(nullptr, rc, err);
+  std::vector<uint64_t> key;
+  plan_structure_key(c, p->plan.gates, std::vector<int>(), key);
+  if (key != trace.key) return fail(nullptr, QCB_ERR_INVALID, "the two op lists differ in structure");
+  rc = schedule(p->plan, std::vector<int>(), nullptr, nullptr, &trace);
   if (rc != QCB_OK) return fail(nullptr, rc, p->plan.error);
   *out = p.release();
   return QCB_OK;
