@@ -755,6 +755,46 @@ cudaError_t launch_scale_dev(double2* state, uint64_t count, const double* coef,
   return cudaGetLastError();
 }
 
+// One Grover iteration as a single streaming pass (32 B per amplitude): a' = alpha * a + beta with (alpha, beta) =
+// (-1, 2*mean) left in coef[0..4) by the preceding sum, then the sign flips of the phase oracles that follow the diffusion
+// (marked = local indices on this rank), then - when another diffusion follows - the sum of the new amplitudes for it
+// (partials: [grid][2], finalised by k_finalize exactly like k_reduce's).
+__global__ void __launch_bounds__(RED_THREADS)
+k_grover_step(double2* __restrict__ state, uint64_t count, const double* __restrict__ coef, GroverMarks marks,
+              double* __restrict__ partials) {
+  __shared__ double sm[2 * 32];
+  const double2 al{coef[0], coef[1]}, be{coef[2], coef[3]};
+  double v[2] = {0.0, 0.0};
+  auto step = [&](uint64_t i, double2 a) {
+    double2 t = cmul(al, a);
+    t.x += be.x; t.y += be.y;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < marks.n && i == marks.idx[k]) { t.x = -t.x; t.y = -t.y; }
+    __stcs(state + i, t);
+    v[0] += t.x; v[1] += t.y;
+  };
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  // four independent 16-byte loads in flight per thread before the first store (a store to `state` would otherwise
+  // order the next iteration's load behind it)
+  for (; i + 3 * stride < count; i += 4 * stride) {
+    const double2 a0 = __ldcs(state + i), a1 = __ldcs(state + i + stride), a2 = __ldcs(state + i + 2 * stride),
+                  a3 = __ldcs(state + i + 3 * stride);
+    step(i, a0); step(i + stride, a1); step(i + 2 * stride, a2); step(i + 3 * stride, a3);
+  }
+  for (; i < count; i += stride) step(i, __ldcs(state + i));
+  if (partials) {
+    block_sum<2>(v, sm);
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = v[0]; partials[2 * blockIdx.x + 1] = v[1]; }
+  }
+}
+cudaError_t launch_grover_step(double2* state, uint64_t count, const double* coef, const GroverMarks& marks, double* partials,
+                               int grid, cudaStream_t s) {
+  k_grover_step<<<grid, RED_THREADS, 0, s>>>(state, count, coef, marks, partials);
+  return cudaGetLastError();
+}
+
 // p_i = |a_i|^2 (domain/state.clj:676-682)
 __global__ void __launch_bounds__(RED_THREADS)
 k_probabilities(const double2* __restrict__ state, uint64_t offset, uint64_t count, double* __restrict__ out) {

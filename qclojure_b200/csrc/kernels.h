@@ -16,6 +16,7 @@ constexpr int MAX_MEASURE_BITS = 12;
 struct ExpectTerms { int n; uint64_t zmask[EXPECT_TERMS]; double pr[EXPECT_TERMS], pi[EXPECT_TERMS]; };
 struct Mat2 { double m[8]; };
 struct BitList { int n; int pos[MAX_MEASURE_BITS]; };
+struct GroverMarks { int n; uint64_t idx[8]; };                    // marked basis states of the phase oracles (local indices)
 
 // TMA tensor maps of one state allocation, indexed by run bits c (box = 2^(c-3) rows of 128 bytes); opaque 128-byte
 // CUtensorMap objects so that this header does not need <cuda.h>.
@@ -31,6 +32,8 @@ void tile_prof_dump();   // prints the cycle accounting of k_tile_stage (only in
 cudaError_t launch_set_amp(double2* state, uint64_t idx, double re, double im, cudaStream_t s);
 cudaError_t launch_reduce(const double2* state, uint64_t count, int mode, double* partials, int grid, cudaStream_t s);
 cudaError_t launch_finalize(const double* partials, uint32_t nparts, uint32_t K, int post, double param, double* out, cudaStream_t s);
+cudaError_t launch_grover_step(double2* state, uint64_t count, const double* coef, const GroverMarks& marks, double* partials,
+                               int grid, cudaStream_t s);
 cudaError_t launch_scale_dev(double2* state, uint64_t count, const double* coef, int grid, cudaStream_t s);
 cudaError_t launch_probabilities(const double2* state, uint64_t offset, uint64_t count, double* out, int grid, cudaStream_t s);
 cudaError_t launch_gather(const double2* state, const uint64_t* idx, uint64_t n, double2* out, cudaStream_t s);

@@ -903,6 +903,10 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
       plan.words.push_back((uint64_t)s.kind);
       if (s.kind == S_TILE) { plan.words.push_back(0); encode_stage(cfg, s, plan.words); plan.n_rounds += s.rounds.size(); }
       else if (s.kind == S_EXCHANGE) { plan.words.push_back((uint64_t)s.gbit | ((uint64_t)s.lbit << 8)); }
+      else if (s.kind == S_GROVER) {
+        plan.words.push_back((uint64_t)s.marked.size() | ((uint64_t)s.needs_sum << 8));
+        for (uint64_t mk : s.marked) plan.words.push_back(mk);
+      }
       else { plan.words.push_back(0); }
       plan.words[1] = (uint64_t)plan.stage_offsets.size();
       if (sink) sink_rc = sink->on_stage(plan, si);
@@ -1063,6 +1067,20 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
     return keep + (lead ? 1 : 0);
   };
 
+  // phase oracle = sign flip of exactly one basis state (all n bits compared)
+  const uint64_t full_mask = (n >= 64) ? ~0ULL : ((1ULL << n) - 1);
+  auto is_oracle_flip = [&](const Gate& g) {
+    return g.kind == G_DMASK && g.dmask == full_mask && g.m[0].re == -1.0 && g.m[0].im == 0.0;
+  };
+  // uids = {diffusion, oracle...}: the marked indices in the current physical layout, kept when they live on this rank
+  auto make_grover_stage = [&](const std::vector<int>& uids, bool needs_sum) {
+    Stage s; s.kind = S_GROVER; s.needs_sum = needs_sum; s.src_gates = uids;
+    for (size_t i = 1; i < uids.size(); ++i) {
+      const uint64_t idx = to_phys(plan.gates[uids[i]]).dval;
+      if (nl >= 64 || (idx >> nl) == (uint64_t)cfg.rank) s.marked.push_back(idx & local_mask);
+    }
+    return s;
+  };
   if (record) { record->stages.clear(); plan_structure_key(cfg, plan.gates, perm_in, record->key); }
   if (replay) {
     // ---- the decisions come from a trace of a structurally identical circuit: no searching
@@ -1074,6 +1092,9 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
         Stage s; s.kind = S_SUM; s.src_gates.push_back(tr.lead_uid);
         plan.stages.push_back(s);
         plan.algorithmic_bytes += 0.5 * sweep_bytes;
+      } else if (tr.kind == S_GROVER) {
+        plan.stages.push_back(make_grover_stage(tr.taken, tr.needs_sum));
+        plan.algorithmic_bytes += sweep_bytes;
       } else if (tr.kind == S_EXCHANGE) {
         std::vector<int> logical_of(n);
         for (int b = 0; b < n; ++b) logical_of[perm[b]] = b;
@@ -1100,6 +1121,34 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
     if (sink_rc != QCB_OK) { plan.error = "stage sink failed"; return sink_rc; }
     // ---- Grover diffusion 2|s><s| - I: a read-only sum sweep, then a' = 2*mean - a opens the next sweep
     if (plan.gates[pending[0]].kind == G_REFLECT) {
+      // the sum is already on the device when the previous stage was a fused Grover pass that computed it
+      const bool have_sum = !plan.stages.empty() && plan.stages.back().kind == S_GROVER && plan.stages.back().needs_sum;
+      // diffusion followed by nothing but phase oracles up to the next diffusion (or the end): one streaming pass
+      size_t k = 1;
+      while (k < pending.size() && k <= (size_t)MAX_GROVER_MARKED && is_oracle_flip(plan.gates[pending[k]])) ++k;
+      const bool next_reflect = k < pending.size() && plan.gates[pending[k]].kind == G_REFLECT;
+      if (cfg.fusion && (next_reflect || k == pending.size())) {
+        if (!have_sum) {
+          Stage s; s.kind = S_SUM; s.src_gates.push_back(pending[0]);
+          plan.stages.push_back(s);
+          plan.algorithmic_bytes += 0.5 * sweep_bytes;
+          if (record) { StageTrace tr; tr.kind = S_SUM; tr.lead_uid = pending[0]; record->stages.push_back(tr); }
+        }
+        std::vector<int> uids(pending.begin(), pending.begin() + k);
+        plan.stages.push_back(make_grover_stage(uids, next_reflect));
+        plan.algorithmic_bytes += sweep_bytes;
+        if (record) { StageTrace tr; tr.kind = S_GROVER; tr.taken = uids; tr.needs_sum = next_reflect; record->stages.push_back(tr); }
+        pending.erase(pending.begin(), pending.begin() + k);
+        continue;
+      }
+      if (have_sum) {
+        Gate a; a.kind = G_REFLECT; a.src_op = plan.gates[pending[0]].src_op;
+        const int reflect_uid = pending[0];
+        pending.erase(pending.begin());
+        build_tile_stage(&a);
+        if (record) record->stages.back().lead_uid = reflect_uid;
+        continue;
+      }
       Stage s; s.kind = S_SUM; s.src_gates.push_back(pending[0]);
       plan.stages.push_back(s);
       plan.algorithmic_bytes += 0.5 * sweep_bytes;

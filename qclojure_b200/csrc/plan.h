@@ -80,7 +80,11 @@ constexpr int STAGE_WORDS = 48;
 constexpr int ROUND_WORDS = 40;
 constexpr uint64_t FLAG_NEEDS_SUM = 1;     // epilogue: accumulate sum of amplitudes (for the next REFLECT)
 
-enum StageKind : int { S_TILE = 0, S_EXCHANGE = 1, S_SUM = 2 };
+// S_GROVER: one streaming pass a' = alpha * a + beta (the Grover diffusion, coefficients from the preceding sum) followed by
+// the sign flips of the phase oracles that come next, and - when another diffusion follows - the sum of the result, so that
+// a Grover iteration is ONE 32-byte-per-amplitude pass (kernels.cu: k_grover_step)
+enum StageKind : int { S_TILE = 0, S_EXCHANGE = 1, S_SUM = 2, S_GROVER = 3 };
+constexpr int MAX_GROVER_MARKED = 8;
 
 constexpr int MAX_COND_BITS = 4;          // outside-condition bits of a tensor-core round (2^k matrix variants)
 
@@ -113,6 +117,9 @@ struct Stage {
   double sweep_fraction = 1.0;      // fraction of tiles actually visited
   // S_EXCHANGE: swap global physical bit gbit with local physical bit lbit
   int gbit = -1, lbit = -1;
+  // S_GROVER: physical LOCAL indices of the marked states that live on this rank; needs_sum = a diffusion follows
+  std::vector<uint64_t> marked;
+  bool needs_sum = false;
 };
 
 struct Config {
@@ -154,6 +161,7 @@ struct StageTrace {
   std::vector<std::vector<int>> round_uids;  // per formed round
   std::vector<uint64_t> round_slots;
   int gbit = -1, lbit = -1;                  // S_EXCHANGE
+  bool needs_sum = false;                    // S_GROVER (taken = the diffusion and the oracles it absorbs)
 };
 struct PlanTrace {
   std::vector<uint64_t> key;

@@ -399,6 +399,20 @@ int execute_stage(qcb_sim* h, Plan& plan, size_t si) {
     RET(allreduce_sum(h, h->d_vals + 8, 2));
     CU(h, launch_finalize(h->d_vals + 8, 1, 2, 1, std::ldexp(1.0, h->cfg.n_total), h->d_vals, h->stream));
     h->stats.n_kernel_launches += 3;
+  } else if (st.kind == S_GROVER) {
+    // diffusion + following phase oracles (+ the sum for the next diffusion) in one streaming pass
+    const int grid = h->num_sms * 8;
+    RET(ensure_partials(h, (size_t)grid * 2));
+    GroverMarks mk; mk.n = (int)std::min<size_t>(st.marked.size(), 8);
+    for (int k = 0; k < 8; ++k) mk.idx[k] = k < mk.n ? st.marked[k] : ~0ULL;
+    CU(h, launch_grover_step(h->state, h->local_count, h->d_vals, mk, st.needs_sum ? h->d_partials : nullptr, grid, h->stream));
+    h->stats.n_sweeps++; h->stats.n_kernel_launches++;
+    if (st.needs_sum) {
+      CU(h, launch_finalize(h->d_partials, grid, 2, 0, 0.0, h->d_vals + 8, h->stream));
+      RET(allreduce_sum(h, h->d_vals + 8, 2));
+      CU(h, launch_finalize(h->d_vals + 8, 1, 2, 1, std::ldexp(1.0, h->cfg.n_total), h->d_vals, h->stream));
+      h->stats.n_kernel_launches += 2;
+    }
   } else if (st.kind == S_EXCHANGE) {
     RET(do_exchange(h, st.gbit, st.lbit));
   }

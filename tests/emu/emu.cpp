@@ -43,6 +43,13 @@ void emu_destroy(Emu* e) { delete e; }
 uint64_t emu_num_stages(Emu* e) { return e->plan.stages.size(); }
 int emu_stage_kind(Emu* e, uint64_t i) { return e->plan.stages[i].kind; }
 void emu_stage_exchange(Emu* e, uint64_t i, int* gbit, int* lbit) { *gbit = e->plan.stages[i].gbit; *lbit = e->plan.stages[i].lbit; }
+// S_GROVER: marked local indices of this rank (out, capacity 8), returns their number; *needs_sum = a diffusion follows
+int emu_stage_grover(Emu* e, uint64_t i, uint64_t* marked, int* needs_sum) {
+  const Stage& st = e->plan.stages[i];
+  *needs_sum = st.needs_sum ? 1 : 0;
+  for (size_t k = 0; k < st.marked.size() && k < 8; ++k) marked[k] = st.marked[k];
+  return (int)st.marked.size();
+}
 uint64_t emu_num_rounds(Emu* e) { return e->plan.n_rounds; }
 uint64_t emu_num_gates(Emu* e) { return e->plan.gates.size(); }
 double emu_algorithmic_bytes(Emu* e) { return e->plan.algorithmic_bytes; }

@@ -21,7 +21,7 @@ DEPS = SRCS + [os.path.join(ROOT, "qclojure_b200", "csrc", "plan.h"),
                os.path.join(ROOT, "qclojure_b200", "csrc", "tile_core.h"),
                os.path.join(ROOT, "include", "qcb200.h")]
 
-S_TILE, S_EXCHANGE, S_SUM = 0, 1, 2
+S_TILE, S_EXCHANGE, S_SUM, S_GROVER = 0, 1, 2, 3
 
 
 def build():
@@ -51,6 +51,8 @@ def lib():
             getattr(L, nm).argtypes = [C.c_void_p]
         L.emu_stage_kind.restype = C.c_int
         L.emu_stage_kind.argtypes = [C.c_void_p, C.c_uint64]
+        L.emu_stage_grover.restype = C.c_int
+        L.emu_stage_grover.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         L.emu_stage_exchange.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.emu_algorithmic_bytes.restype = C.c_double
         L.emu_algorithmic_bytes.argtypes = [C.c_void_p]
@@ -120,6 +122,12 @@ class EmuPlan:
 
     def stage_kind(self, i):
         return int(lib().emu_stage_kind(self.h, i))
+
+    def stage_grover(self, i):
+        marked = (C.c_uint64 * 8)()
+        needs = C.c_int()
+        k = int(lib().emu_stage_grover(self.h, i, marked, C.byref(needs)))
+        return [int(marked[j]) for j in range(k)], bool(needs.value)
 
     def stage_exchange(self, i):
         g, l = C.c_int(), C.c_int()
@@ -191,6 +199,19 @@ def run_world(n, ops, state=None, *, world=1, nthreads=512, return_plans=False, 
             tot = sum(complex(np.sum(s)) for s in slices)
             N = float(1 << n)
             dev_vals[0:4] = [-1.0, 0.0, 2.0 * tot.real / N, 2.0 * tot.imag / N]   # a' = -a + 2*mean
+        elif kind == S_GROVER:
+            # kernels.cu: k_grover_step — a' = alpha a + beta, sign flips of this rank's marked states, sum for the next diffusion
+            al, be = complex(dev_vals[0], dev_vals[1]), complex(dev_vals[2], dev_vals[3])
+            needs = False
+            for r in range(world):
+                marked, needs = plans[r].stage_grover(i)
+                slices[r][:] = al * slices[r] + be
+                for mk in marked:
+                    slices[r][mk] = -slices[r][mk]
+            if needs:
+                tot = sum(complex(np.sum(s)) for s in slices)
+                N = float(1 << n)
+                dev_vals[0:4] = [-1.0, 0.0, 2.0 * tot.real / N, 2.0 * tot.imag / N]
     full = np.concatenate(slices)
     perm = plans[0].perm_out()
     if perm != list(range(n)):

@@ -169,6 +169,30 @@ def test_grover_full_iteration_count_12q_and_16q():
         assert abs(got[target]) ** 2 > 0.99
 
 
+@pytest.mark.parametrize("n,marked", [(3, [5]), (9, [1, 77, 300]), (14, [0x2AAA & 0x3FFF, 5]), (20, [0xABCDE]), (11, [])])
+def test_fused_grover_pass_on_device(n, marked):
+    """plan.h S_GROVER / kernels.cu k_grover_step: diffusion + the phase oracles after it + the sum for the next diffusion in
+    one streaming pass; several marked states; a diffusion followed by ordinary gates falls back to the tile path."""
+    its = 6
+    ops = [{"operation-type": "global-h", "operation-params": {}}]
+    st = np.full(1 << n, 1.0 / math.sqrt(1 << n), dtype=np.complex128)
+    for it in range(its):
+        ops += [{"operation-type": "phase-oracle", "operation-params": {"index": mk}} for mk in marked]
+        ops += [{"operation-type": "grover-diffusion", "operation-params": {}}]
+        for mk in marked:
+            st[mk] *= -1
+        st = 2 * np.mean(st) - st
+        if it == 2:
+            ops += [{"operation-type": "h", "operation-params": {"target": n - 1}}]
+            st = O.apply_single_qubit_gate(st, O.HADAMARD, n - 1)
+    with L.StateVector(n) as sv:
+        sv.apply_ops(ops)
+        got = sv.get_state()
+        stats = sv.stats()
+    assert np.max(np.abs(got - st)) <= TOL
+    assert abs(np.linalg.norm(got) - 1.0) <= 1e-12
+
+
 # ------------------------------------------------------------------ BASELINE configs (parity legs)
 @pytest.mark.parametrize("n", [20])
 def test_config1_qft_ghz_20q_with_shots(n):

@@ -166,6 +166,61 @@ def test_grover_operator_matches_gate_level_circuit():
     assert np.max(np.abs(np.abs(got) ** 2 - want_p)) <= TOL
 
 
+def _grover_reference(n, iterations, marked, extra=None):
+    st = np.full(1 << n, 1.0 / math.sqrt(1 << n), dtype=np.complex128)
+    for it in range(iterations):
+        for mk in marked:
+            st[mk] *= -1
+        st = 2 * np.mean(st) - st
+        if extra is not None and it == extra[0]:
+            st = O.apply_single_qubit_gate(st, O.HADAMARD, extra[1])
+    return st
+
+
+@pytest.mark.parametrize("n,world,marked", [(8, 1, [0xA5]), (10, 1, [3, 700, 1023]), (10, 4, [3, 700, 1023]), (12, 8, [0xABC]),
+                                            (9, 2, [])])
+def test_fused_grover_pass(n, world, marked):
+    """Diffusion + following phase oracles (+ the sum for the next diffusion) run as ONE streaming stage (plan.h: S_GROVER,
+    kernels.cu: k_grover_step): one S_SUM for the whole loop, one pass per iteration; marked states land on the rank that
+    holds them."""
+    its = 5
+    ops = [{"operation-type": "global-h", "operation-params": {}}]
+    for _ in range(its):
+        ops += [{"operation-type": "phase-oracle", "operation-params": {"index": mk}} for mk in marked]
+        ops += [{"operation-type": "grover-diffusion", "operation-params": {}}]
+    got, plans = E.run_world(n, ops, world=world, tile_bits=min(6, n - 3), low_bits=2, return_plans=True)
+    assert np.max(np.abs(got - _grover_reference(n, its, marked))) <= TOL
+    kinds = [plans[0].stage_kind(i) for i in range(plans[0].num_stages)]
+    assert kinds.count(E.S_SUM) == 1 and kinds.count(E.S_GROVER) == its
+    if marked:
+        # every marked state is flipped by exactly one rank
+        for i in range(plans[0].num_stages):
+            if kinds[i] == E.S_GROVER and i != len(kinds) - 1:
+                assert sum(len(p.stage_grover(i)[0]) for p in plans) == len(marked)
+
+
+def test_fused_grover_pass_mixed_with_gates_and_permuted_layout():
+    """A diffusion followed by ordinary gates keeps the tile path (affine lead round) and reuses the sum a fused pass left
+    on the device; after a qubit exchange the marked index is translated to the physical layout."""
+    n, world = 10, 4
+    marked = [0x155, 0x2AA]
+    ops = [{"operation-type": "global-h", "operation-params": {}},
+           {"operation-type": "h", "operation-params": {"target": 0}},          # non-diagonal on a global qubit: exchange
+           {"operation-type": "h", "operation-params": {"target": 0}}]
+    for it in range(4):
+        ops += [{"operation-type": "phase-oracle", "operation-params": {"index": mk}} for mk in marked]
+        ops += [{"operation-type": "grover-diffusion", "operation-params": {}}]
+        if it == 1:
+            ops += [{"operation-type": "h", "operation-params": {"target": 7}}]
+    got, plans = E.run_world(n, ops, world=world, tile_bits=5, low_bits=2, return_plans=True)
+    assert np.max(np.abs(got - _grover_reference(n, 4, marked, extra=(1, 7)))) <= TOL
+    kinds = [plans[0].stage_kind(i) for i in range(plans[0].num_stages)]
+    assert E.S_EXCHANGE in kinds and kinds.count(E.S_GROVER) >= 2
+    # unfused mode never forms the fused pass
+    got = E.run_world(n, ops, world=1, fusion=0)
+    assert np.max(np.abs(got - _grover_reference(n, 4, marked, extra=(1, 7)))) <= TOL
+
+
 def test_bank_conflict_free_lane_mapping():
     """Every round of a 30-qubit brickwork plan must give conflict-free shared-memory access under the default tile
     layout (full XOR fold, tile_core.h: swz with c = 0; lane choice in plan.cpp).  The optional TMA-compatible layout
