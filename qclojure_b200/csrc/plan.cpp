@@ -69,6 +69,7 @@ Config config_from(const qcb_config& c) {
   k.max_stage_rounds = c.max_stage_rounds;
   k.dense_mma = (c.dense_mma == 2) ? 0 : 1;
   k.tma = (c.tile_mover == 2) ? 1 : 0;
+  if (const char* e = std::getenv("QCB_THIN_DEFER")) k.thin_defer = std::atoi(e);            // experiment knob
   if (const char* e = std::getenv("QCB_WINDOW_SEARCH")) k.window_search = std::atoi(e);
   if (const char* e = std::getenv("QCB_ROUND_YIELD_PCT")) k.round_yield_pct = std::atoi(e);   // 0 = greedy tiles / rounds only
   return k;
@@ -844,7 +845,7 @@ void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const
   key.clear();
   key.reserve(16 + perm_in.size() + 6 * gates.size());
   const int c[] = {cfg.n_total, cfg.n_local, cfg.rank, cfg.world, cfg.tile_bits, cfg.low_bits, cfg.fusion, cfg.max_stage_cost,
-                   cfg.max_stage_rounds, cfg.dense_mma, cfg.round_yield_pct, cfg.window_search, cfg.tma};
+                   cfg.max_stage_rounds, cfg.dense_mma, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer};
   for (int v : c) key.push_back((uint64_t)(int64_t)v);
   key.push_back(perm_in.size());
   for (int v : perm_in) key.push_back((uint64_t)v);
@@ -1163,31 +1164,78 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
     // ---- everything executable in the current layout goes first: gates with a non-diagonal target on a global
     // physical bit (and whatever depends on them) are skipped by the stage builder, so an exchange is only paid for
     // when no gate at all can run without it
-    if (build_tile_stage(nullptr)) continue;
-    // ---- multi-GPU remap: the head-of-line gate targets a global bit.  Swap it with the local bit (among the top 8:
-    // large contiguous chunks) whose logical occupant is needed latest as a non-diagonal target
     {
-      Gate g0 = to_phys(plan.gates[pending[0]]);
-      uint64_t gt = g0.target_mask() & ~local_mask;
+      // Experiment knob, OFF by default (thin_defer = 0): do not run a THIN stage (fewer gates than thin_defer) while gates
+      // wait for an exchange, so that its gates ride along in the fuller sweeps after the exchange.  Brickwork gains 3 %
+      // in the cost model (33 q on 8 GPUs: 23 -> 21 sweeps), but circuits without free exchange partners pay for the
+      // earlier exchanges with many more of them (QFT-26 on 8 GPUs: 7 -> 11..22 exchanges), hence off.
+      const bool may_defer = cfg.world > 1 && cfg.fusion && cfg.thin_defer > 0 &&
+                             !(plan.stages.size() && plan.stages.back().kind == S_EXCHANGE);
+      std::vector<int> saved_pending;
+      double saved_bytes = plan.algorithmic_bytes;
+      const size_t saved_traces = record ? record->stages.size() : 0;
+      if (may_defer) saved_pending = pending;
+      const size_t got = build_tile_stage(nullptr);
+      if (got && may_defer && (int)got < cfg.thin_defer && got < pending.size() + got) {
+        // is anything blocked on a global bit?
+        bool blocked = false;
+        for (size_t i = 0; i < pending.size() && i < 4096 && !blocked; ++i)
+          blocked = (to_phys(plan.gates[pending[i]]).target_mask() & ~local_mask) != 0;
+        if (blocked) {
+          plan.stages.pop_back();
+          plan.algorithmic_bytes = saved_bytes;
+          if (record) record->stages.resize(saved_traces);
+          pending.swap(saved_pending);
+        } else continue;
+      } else if (got) continue;
+    }
+    // ---- multi-GPU remap: the head-of-line gate targets a global bit.  Swap it with the local bit (bit 12 and up: rows of
+    // >= 64 KiB for the strided copies) whose logical occupant is needed latest as a non-diagonal target.  Every other
+    // global bit that pending gates target as well is swapped in the same breath when a partner exists that no pending
+    // gate targets any more: those exchanges have to happen anyway, and done back to back they spare the thin sweeps that
+    // would otherwise run between them (33-qubit benchmark on 8 GPUs: 6 exchanges + 27 sweeps -> 3 + 21).
+    {
+      Gate g0; uint64_t gt = 0;
+      for (size_t i = 0; i < pending.size() && !gt; ++i) { g0 = to_phys(plan.gates[pending[i]]); gt = g0.target_mask() & ~local_mask; }
       if (!gt) { plan.error = "scheduler made no progress"; return QCB_ERR_INVALID; }
-      int gbit = 63 - __builtin_clzll(gt);
+      const int lo_cand = std::max(L, std::min(nl - 8, 12));
+      const size_t window = std::min<size_t>(pending.size(), 4096);
+      const size_t never = pending.size() + 1;
       std::vector<int> logical_of(n);
-      for (int b = 0; b < n; ++b) logical_of[perm[b]] = b;
+      auto refresh = [&]() { for (int b = 0; b < n; ++b) logical_of[perm[b]] = b; };
+      refresh();
+      // next use (index into pending) of the logical occupant of physical bit `pb` as a non-diagonal target
+      auto next_use = [&](int pb) {
+        const int lb = logical_of[pb];
+        for (size_t i = 0; i < window; ++i)
+          if ((plan.gates[pending[i]].target_mask() >> lb) & 1) return i;
+        return never;
+      };
+      auto emit_exchange = [&](int gbit, int lbit) {
+        Stage s; s.kind = S_EXCHANGE; s.gbit = gbit; s.lbit = lbit;
+        plan.stages.push_back(s);
+        plan.n_exchanges++;
+        if (record) { StageTrace tr; tr.kind = S_EXCHANGE; tr.gbit = gbit; tr.lbit = lbit; record->stages.push_back(tr); }
+        std::swap(perm[logical_of[gbit]], perm[logical_of[lbit]]);
+        refresh();
+      };
+      const int gbit = 63 - __builtin_clzll(gt);
       int best = -1; size_t best_next = 0;
-      for (int cand = nl - 1; cand >= std::max(L, nl - 8) && cand >= 0; --cand) {
+      for (int cand = nl - 1; cand >= lo_cand && cand >= 0; --cand) {
         if ((g0.target_mask() >> cand) & 1) continue;
-        int lb = logical_of[cand];
-        size_t next = pending.size() + 1;
-        for (size_t i = 0; i < pending.size() && i < 4096; ++i)
-          if ((plan.gates[pending[i]].target_mask() >> lb) & 1) { next = i; break; }
+        const size_t next = next_use(cand);
         if (best < 0 || next > best_next) { best = cand; best_next = next; }
       }
       if (best < 0) { plan.error = "no local qubit available for remap"; return QCB_ERR_INVALID; }
-      Stage s; s.kind = S_EXCHANGE; s.gbit = gbit; s.lbit = best;
-      plan.stages.push_back(s);
-      plan.n_exchanges++;
-      if (record) { StageTrace tr; tr.kind = S_EXCHANGE; tr.gbit = gbit; tr.lbit = best; record->stages.push_back(tr); }
-      std::swap(perm[logical_of[gbit]], perm[logical_of[best]]);
+      emit_exchange(gbit, best);
+      for (int gb = n - 1; gb >= nl; --gb) {
+        if (next_use(gb) == never) continue;               // nothing pending targets this global bit
+        int partner = -1;
+        for (int cand = nl - 1; cand >= lo_cand && cand >= 0; --cand)
+          if (next_use(cand) == never) { partner = cand; break; }
+        if (partner < 0) break;                            // no free partner: leave the choice to the next trigger
+        emit_exchange(gb, partner);
+      }
     }
   }
 

@@ -132,6 +132,7 @@ struct Config {
   int dense_mma = 1;           // rounds as dense 8x8 complex blocks on the fp64 tensor cores
   int round_yield_pct = 50;    // end a stage early when the next round would absorb less than this % of the stage's average round
   int window_search = 1;       // stage builder also tries contiguous tile windows and keeps the best yield
+  int thin_defer = 0;          // multi-GPU: a stage with fewer gates than this is not run while gates wait for an exchange
   int tma = 0;                 // tiles move by TMA tensor copies (layout follows the hardware 128-byte swizzle)
   int threads = 256;
 };

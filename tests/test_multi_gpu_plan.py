@@ -66,6 +66,37 @@ def test_exchange_count_is_small_for_brickwork():
     assert ex <= 70
 
 
+@pytest.mark.parametrize("n,world,max_ex,max_sweeps", [(31, 2, 1, 19), (32, 4, 2, 20), (33, 8, 3, 24), (36, 8, 3, 22)])
+def test_batched_exchanges_with_free_partners(n, world, max_ex, max_sweeps):
+    """Weak-scaling benchmark plans: once the local part of the circuit is done, every global qubit
+    is swapped against a qubit no pending gate targets any more, back to back - log2(P) exchanges for the whole circuit
+    and no thin sweeps between them (was 2 / 4 / 6 / 6 exchanges and 19 / 21 / 27 / 31 sweeps)."""
+    circ = C.random_brickwork_circuit(n, 20)
+    p = E.EmuPlan(n, circ["operations"], rank=0, world=world)
+    kinds = [p.stage_kind(i) for i in range(p.num_stages)]
+    ex = kinds.count(E.S_EXCHANGE)
+    assert ex <= max_ex and len(kinds) - ex <= max_sweeps
+    # the exchanges come back to back, and their local partners are low-traffic bits with >= 64 KiB rows
+    first = kinds.index(E.S_EXCHANGE)
+    assert kinds[first:first + ex] == [E.S_EXCHANGE] * ex
+    n_local = n - (world.bit_length() - 1)
+    for i in range(first, first + ex):
+        g, l = p.stage_exchange(i)
+        assert g >= n_local and 12 <= l < n_local
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_batched_exchanges_emulated_parity(world):
+    """Deep brickwork at a size the emulator finishes: the local part completes, all global qubits come in at once, the
+    rest runs - amplitudes against the oracle, layout restored through perm_out."""
+    n = 13
+    circ = C.random_brickwork_circuit(n, 12, seed=5)
+    got, plans = E.run_world(n, circ["operations"], world=world, tile_bits=5, low_bits=2, return_plans=True)
+    assert np.max(np.abs(got - O.execute_circuit(circ))) <= TOL
+    kinds = [plans[0].stage_kind(i) for i in range(plans[0].num_stages)]
+    assert kinds.count(E.S_EXCHANGE) >= 1
+
+
 def test_gloo_two_process_exchange():
     """world_size-2 run over torch.distributed (gloo): each process emulates its rank's tile stages and
     exchanges halves with real send/recv; rank 0 compares the gathered state with the oracle."""
