@@ -118,7 +118,7 @@ struct qcb_sim {
   // plan traces by circuit structure (plan.h: PlanTrace): a variational loop re-plans the same ansatz with new angles
   // every evaluation; a hit replays the recorded decisions and only rebuilds the matrices
   std::unordered_map<uint64_t, std::vector<std::shared_ptr<PlanTrace>>> traces;
-  size_t n_traces = 0;
+  size_t n_traces = 0, trace_words = 0;
   uint64_t trace_hits = 0, trace_misses = 0;
   qcb_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timing_pending = false;
@@ -473,7 +473,9 @@ int run_gates(qcb_sim* h, std::vector<Gate>&& gates) {
   if (hit) ++h->trace_hits;
   else if (cacheable) {
     ++h->trace_misses;
-    if (h->n_traces >= 128) { h->traces.clear(); h->n_traces = 0; }
+    // bounded: at most 128 traces and 32 MB of keys per handle, then start over
+    if (h->n_traces >= 128 || h->trace_words + rec->key.size() > (4u << 20)) { h->traces.clear(); h->n_traces = 0; h->trace_words = 0; }
+    h->trace_words += rec->key.size();
     h->traces[hash].push_back(rec);
     ++h->n_traces;
   }
