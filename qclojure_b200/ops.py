@@ -90,9 +90,18 @@ def _kw(x):
 
 
 def normalize_op(op: dict) -> Tuple[str, dict]:
-    typ = _kw(op.get("operation-type", op.get(":operation-type")))
-    params = op.get("operation-params", op.get(":operation-params")) or {}
-    return typ, {_kw(k): v for k, v in params.items()}
+    typ = op.get("operation-type")
+    if typ is None:
+        typ = op.get(":operation-type")
+    if type(typ) is not str or typ[:1] == ":":
+        typ = _kw(typ)
+    params = op.get("operation-params")
+    if params is None:
+        params = op.get(":operation-params") or {}
+    for k in params:                      # keys spelled without the colon (the common case) are used as they are
+        if type(k) is str and k[:1] == ":":
+            return typ, {_kw(k): v for k, v in params.items()}
+    return typ, params
 
 
 def circuit_ops(circuit: dict) -> list:
@@ -124,16 +133,64 @@ def split_at_measurements(ops: Sequence[dict]) -> List[Tuple[str, object]]:
     return out
 
 
+# numpy view of qcb_op (same layout as the ctypes struct): columns are filled in bulk, which is what makes encoding a
+# 1000-gate circuit cost a few hundred microseconds instead of milliseconds
+OP_DTYPE = np.dtype({"names": ["kind", "q", "n_mask", "mask", "angle", "mat", "ext"],
+                     "formats": [np.int32, (np.int32, 3), np.int32, np.uint64, np.float64, (np.float64, 8), np.uint64],
+                     "offsets": [QcbOp.kind.offset, QcbOp.q.offset, QcbOp.n_mask.offset, QcbOp.mask.offset, QcbOp.angle.offset,
+                                 QcbOp.mat.offset, QcbOp.ext.offset],
+                     "itemsize": C.sizeof(QcbOp)})
+_K1 = {g: KIND[g] for g in _ONE_QUBIT}
+_K2 = {g: KIND[g] for g in _CTRL}
+_K2A = {g: KIND[g] for g in _CTRL_ANGLE}
+
+
 def encode_ops(ops: Iterable[dict]):
-    """QClojure gate maps -> (ctypes array of qcb_op, keepalive list).  No :measure ops here."""
+    """QClojure gate maps -> (ctypes array of qcb_op, count, keepalive list)."""
     ops = list(ops)
-    arr = (QcbOp * max(1, len(ops)))()
+    n = len(ops)
+    arr = (QcbOp * max(1, n))()
     keep = []
+    kinds, q0, q1, q2, angles = [0] * n, [-1] * n, [-1] * n, [-1] * n, [0.0] * n
+    slow = []                                    # (index, gate name, params): kinds that carry more than qubits + angle
     for k, op in enumerate(ops):
         typ, p = normalize_op(op)
         g = GATE_ALIASES.get(typ, typ)
+        get = p.get
+        if g in _K1:
+            kinds[k] = _K1[g]
+            t = get("target")
+            q0[k] = 0 if t is None else int(t)            # (or target 0), circuit.clj:977-984
+            if g in _ANGLE_1Q:
+                a = get("angle")
+                if a is None:
+                    raise GateError(f"{g} requires angle")
+                angles[k] = float(a)
+        elif g in _K2:
+            c, t = get("control"), get("target")
+            if c is None or t is None:
+                raise GateError(f"{g} requires control, target")
+            kinds[k], q0[k], q1[k] = _K2[g], int(c), int(t)
+        elif g in _K2A:
+            c, t, a = get("control"), get("target"), get("angle")
+            if c is None or t is None or a is None:
+                raise GateError(f"{g} requires control, target, angle")
+            kinds[k], q0[k], q1[k], angles[k] = _K2A[g], int(c), int(t), float(a)
+        elif g not in KIND:
+            raise GateError(f"Unknown gate type {g}")
+        else:
+            kinds[k] = KIND[g]
+            slow.append((k, g, p))
+    if n:
+        view = np.frombuffer(arr, dtype=OP_DTYPE, count=n)
+        view["kind"] = kinds
+        qv = view["q"]
+        qv[:, 0] = q0
+        qv[:, 1] = q1
+        qv[:, 2] = q2
+        view["angle"] = angles
+    for k, g, p in slow:
         o = arr[k]
-        o.q[0] = o.q[1] = o.q[2] = -1
         angle = p.get("angle")
 
         def need(*names):
@@ -141,23 +198,7 @@ def encode_ops(ops: Iterable[dict]):
                 if p.get(nm) is None:
                     raise GateError(f"{g} requires {', '.join(names)}")
 
-        if g not in KIND:
-            raise GateError(f"Unknown gate type {g}")
-        o.kind = KIND[g]
-        if g in _ONE_QUBIT:
-            t = p.get("target")
-            o.q[0] = 0 if t is None else int(t)          # (or target 0), circuit.clj:977-984
-            if g in _ANGLE_1Q:
-                if angle is None:
-                    raise GateError(f"{g} requires angle")
-                o.angle = float(angle)
-        elif g in _CTRL:
-            need("control", "target")
-            o.q[0], o.q[1] = int(p["control"]), int(p["target"])
-        elif g in _CTRL_ANGLE:
-            need("control", "target", "angle")
-            o.q[0], o.q[1], o.angle = int(p["control"]), int(p["target"]), float(angle)
-        elif g in ("swap", "iswap"):
+        if g in ("swap", "iswap"):
             need("qubit1", "qubit2")
             o.q[0], o.q[1] = int(p["qubit1"]), int(p["qubit2"])
         elif g == "toffoli":
@@ -203,7 +244,7 @@ def encode_ops(ops: Iterable[dict]):
             o.ext = qs.ctypes.data
             o.n_mask = int(qs.shape[0])
             o.angle = float(p.get("uniform", 0.0))
-    return arr, len(ops), keep
+    return arr, n, keep
 
 
 def _put_mat(o: QcbOp, mat) -> None:
