@@ -694,52 +694,95 @@ struct PTerm { uint64_t x = 0, z = 0; int ny = 0; size_t idx = 0; };
 int expect_terms_impl(qcb_sim* h, const char* const* strings, uint64_t n_terms, double* out_terms) {
   const int n = h->cfg.n_total, nl = h->cfg.n_local;
   const uint64_t local_mask = (nl >= 64) ? ~0ULL : ((1ULL << nl) - 1);
-  std::vector<PTerm> terms(n_terms);
+  // Pauli strings as LOGICAL bit masks (char k <-> qubit k <-> bit n-1-k); the physical masks follow the current layout
+  struct LTerm { uint64_t x = 0, z = 0; int ny = 0; };
+  std::vector<LTerm> lterms(n_terms);
   for (uint64_t t = 0; t < n_terms; ++t) {
     const char* s = strings[t];
     if (!s || (int)std::strlen(s) != n) return fail(h, QCB_ERR_INVALID, "pauli string length must equal the number of qubits");
-    terms[t].idx = t;
     for (int q = 0; q < n; ++q) {
-      const uint64_t b = 1ULL << h->perm[n - 1 - q];
+      const uint64_t b = 1ULL << (n - 1 - q);
       switch (s[q]) {
         case 'I': break;
-        case 'X': terms[t].x |= b; break;
-        case 'Z': terms[t].z |= b; break;
-        case 'Y': terms[t].x |= b; terms[t].z |= b; terms[t].ny++; break;
+        case 'X': lterms[t].x |= b; break;
+        case 'Z': lterms[t].z |= b; break;
+        case 'Y': lterms[t].x |= b; lterms[t].z |= b; lterms[t].ny++; break;
         default: return fail(h, QCB_ERR_INVALID, "pauli string may contain only I, X, Y, Z");
       }
     }
-    if (terms[t].x & ~local_mask)
-      return fail(h, QCB_ERR_UNSUPPORTED, "X/Y factor on a global (rank) qubit: not supported in the sharded layout yet");
   }
-  std::stable_sort(terms.begin(), terms.end(), [](const PTerm& a, const PTerm& b) { return a.x < b.x; });
+  auto phys = [&](uint64_t m) { uint64_t r = 0; for (int b = 0; b < n; ++b) if ((m >> b) & 1) r |= 1ULL << h->perm[b]; return r; };
   const int grid = red_grid(h);
   RET(ensure_partials(h, (size_t)grid * EXPECT_TERMS));
   RET(ensure_scratch(h, (n_terms + EXPECT_TERMS) * 8 + 256));
   double* d_res = reinterpret_cast<double*>(h->d_scratch);
   const uint64_t ext_or = (uint64_t)h->cfg.rank << nl;
   static const double PH[4][2] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}};
-  std::vector<size_t> order;     // result slot -> original term index
-  size_t t = 0, slot = 0;
-  while (t < terms.size()) {
-    ExpectTerms et; et.n = 0;
-    const uint64_t x = terms[t].x;
-    while (t < terms.size() && terms[t].x == x && et.n < EXPECT_TERMS) {
-      et.zmask[et.n] = terms[t].z; et.pr[et.n] = PH[terms[t].ny & 3][0]; et.pi[et.n] = PH[terms[t].ny & 3][1];
-      order.push_back(terms[t].idx);
-      ++et.n; ++t;
+  // evaluates the given terms (X masks all local): groups of <= 16 terms sharing an X mask, one pass over the state each
+  auto evaluate = [&](std::vector<PTerm>& terms) -> int {
+    std::stable_sort(terms.begin(), terms.end(), [](const PTerm& a, const PTerm& b) { return a.x < b.x; });
+    std::vector<size_t> order;     // result slot -> original term index
+    size_t t = 0, slot = 0;
+    while (t < terms.size()) {
+      ExpectTerms et; et.n = 0;
+      const uint64_t x = terms[t].x;
+      while (t < terms.size() && terms[t].x == x && et.n < EXPECT_TERMS) {
+        et.zmask[et.n] = terms[t].z; et.pr[et.n] = PH[terms[t].ny & 3][0]; et.pi[et.n] = PH[terms[t].ny & 3][1];
+        order.push_back(terms[t].idx);
+        ++et.n; ++t;
+      }
+      for (int k = et.n; k < EXPECT_TERMS; ++k) { et.zmask[k] = 0; et.pr[k] = 0; et.pi[k] = 0; }
+      const int pivot = x ? 63 - __builtin_clzll(x) : 0;
+      CU(h, launch_expect_group(h->state, h->local_count, x, pivot, ext_or, et, h->d_partials, grid, h->stream));
+      CU(h, launch_finalize(h->d_partials, grid, EXPECT_TERMS, 0, 0.0, d_res + slot, h->stream));
+      h->stats.n_kernel_launches += 2;
+      slot += et.n;     // next group overwrites the unused tail of this one
     }
-    for (int k = et.n; k < EXPECT_TERMS; ++k) { et.zmask[k] = 0; et.pr[k] = 0; et.pi[k] = 0; }
-    const int pivot = x ? 63 - __builtin_clzll(x) : 0;
-    CU(h, launch_expect_group(h->state, h->local_count, x, pivot, ext_or, et, h->d_partials, grid, h->stream));
-    CU(h, launch_finalize(h->d_partials, grid, EXPECT_TERMS, 0, 0.0, d_res + slot, h->stream));
-    h->stats.n_kernel_launches += 2;
-    slot += et.n;     // next group overwrites the unused tail of this one
+    RET(allreduce_sum(h, d_res, slot));
+    std::vector<double> res(slot);
+    if (slot) RET(read_back(h, d_res, slot * 8, res.data()));
+    for (size_t k = 0; k < slot; ++k) out_terms[order[k]] = res[k];
+    return QCB_OK;
+  };
+  std::vector<char> done(n_terms, 0);
+  size_t n_done = 0;
+  while (n_done < n_terms) {
+    std::vector<PTerm> terms;
+    for (uint64_t t = 0; t < n_terms; ++t) {
+      if (done[t]) continue;
+      const uint64_t px = phys(lterms[t].x);
+      if (px & ~local_mask) continue;              // an X / Y factor on a rank bit: its pair partner lives on another GPU
+      PTerm pt; pt.x = px; pt.z = phys(lterms[t].z); pt.ny = lterms[t].ny; pt.idx = t;
+      terms.push_back(pt);
+      done[t] = 1; ++n_done;
+    }
+    if (!terms.empty()) { RET(evaluate(terms)); continue; }
+    // Sharded layout, nothing evaluable: bring the X / Y qubits of the first remaining term into local positions with
+    // qubit exchanges (the layout permutation is tracked, nothing needs to be moved back), preferring partners that the
+    // remaining terms use least
+    uint64_t t0 = 0;
+    while (done[t0]) ++t0;
+    const uint64_t px0 = phys(lterms[t0].x);
+    if (__builtin_popcountll(px0) > nl)
+      return fail(h, QCB_ERR_UNSUPPORTED, "pauli string has more X/Y factors than one GPU holds qubits: not supported in the sharded layout");
+    for (int g = n - 1; g >= nl; --g) {
+      if (!((px0 >> g) & 1)) continue;
+      const uint64_t cur = phys(lterms[t0].x);
+      int best = -1; size_t best_uses = 0;
+      for (int l = nl - 1; l >= 0; --l) {
+        if ((cur >> l) & 1) continue;
+        size_t uses = 0;
+        for (uint64_t t = 0; t < n_terms; ++t) if (!done[t] && ((phys(lterms[t].x) >> l) & 1)) ++uses;
+        if (best < 0 || uses < best_uses) { best = l; best_uses = uses; }
+        if (l < nl - 8 && best_uses == 0) break;   // a free partner among the high bits is good enough
+      }
+      if (best < 0) return fail(h, QCB_ERR_UNSUPPORTED, "no local qubit available to localise the pauli string");
+      RET(do_exchange(h, g, best));
+      std::vector<int> logical_of(n);
+      for (int b = 0; b < n; ++b) logical_of[h->perm[b]] = b;
+      std::swap(h->perm[logical_of[g]], h->perm[logical_of[best]]);
+    }
   }
-  RET(allreduce_sum(h, d_res, slot));
-  std::vector<double> res(slot);
-  if (slot) RET(read_back(h, d_res, slot * 8, res.data()));
-  for (size_t k = 0; k < slot; ++k) out_terms[order[k]] = res[k];
   return QCB_OK;
 }
 

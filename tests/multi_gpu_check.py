@@ -41,11 +41,15 @@ def main():
         want = CO.apply_circuit(circ) if n > 16 else O.execute_circuit(circ)
         u = np.random.default_rng(n).random(512)
         H = C.max_cut_hamiltonian(C.random_regular_graph(n, 3 if n % 2 == 0 else 4, seed=11), n)
+        HX = C.standard_mixer_hamiltonian(n) + [
+            {"coefficient": 0.7, "pauli-string": "XY" + "I" * (n - 3) + "Z"}, {"coefficient": -0.4, "pauli-string": "Y" * 3 + "I" * (n - 3)},
+            {"coefficient": 0.2, "pauli-string": "Z" + "X" * (n - 4) + "III"}]
         with L.StateVector(n, device=local_rank, rank=rank, world_size=world, nccl_id=new_nccl_id()) as sv:
             sv.apply_circuit(circ)
             stats = sv.stats()
             nrm = sv.norm2()
             energy = sv.expect_hamiltonian(H)
+            energy_x = sv.expect_hamiltonian(HX)      # X / Y factors on the global qubits: localised by qubit exchanges
             shots = sv.sample(u)
             got = sv.get_state()
         lc = 1 << (n - p)
@@ -54,6 +58,7 @@ def main():
         assert err <= 1e-10, f"rank {rank} n={n}: amplitude mismatch {err}"
         assert abs(nrm - 1.0) <= 1e-10, f"rank {rank} n={n}: norm {nrm}"
         assert abs(energy - O.hamiltonian_expectation(H, want)) <= 1e-9, f"rank {rank} n={n}: energy"
+        assert abs(energy_x - O.hamiltonian_expectation(HX, want)) <= 1e-9, f"rank {rank} n={n}: energy with X/Y on global qubits"
         ref = O.sample_outcomes(want, u)
         dist_b = O.sample_boundary_distance(want, u)
         assert not ((shots != ref) & (dist_b > 1e-12)).any(), f"rank {rank} n={n}: shot outcomes differ"
