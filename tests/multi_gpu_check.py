@@ -36,7 +36,9 @@ def main():
 
     p = world.bit_length() - 1
     worst = 0.0
-    for n, depth in ((12 + p, 6), (18 + p, 8), (22 + p, 8)):
+    # QCB_MGC_LOCAL="12:6,18:8,22:8" (local qubits : depth) overrides the sizes, e.g. for a short run on a tight GPU budget
+    sizes = [tuple(int(v) for v in item.split(":")) for item in os.environ.get("QCB_MGC_LOCAL", "12:6,18:8,22:8").split(",")]
+    for n, depth in [(nl + p, d) for nl, d in sizes]:
         circ = C.random_brickwork_circuit(n, depth)
         want = CO.apply_circuit(circ) if n > 16 else O.execute_circuit(circ)
         u = np.random.default_rng(n).random(512)
