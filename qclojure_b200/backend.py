@@ -284,6 +284,13 @@ class B200HardwareSimulator(_BackendBase):
     def __init__(self, device: Optional[dict] = None, config: Optional[dict] = None):
         super().__init__(config)
         self._device = device or {"id": "b200-hardware-simulator", "noise-model": {}}
+        # the device catalogue (hardware_simulator.clj:44-52 loads resources/simulator-devices.edn): a list of device maps
+        # under config "devices", or the path of such an EDN file under "devices-file"
+        self._devices: List[dict] = list(_opt(self.config, "devices") or [])
+        if _opt(self.config, "devices-file"):
+            self._devices += load_device_catalog(_opt(self.config, "devices-file"))
+        if device is not None and all(_opt(d, "id") != _opt(device, "id") for d in self._devices):
+            self._devices.append(device)                     # create-hardware-simulator adds it (:407-411)
 
     def backend_info(self) -> dict:
         return {"backend-type": "hardware-simulator", "backend-name": "B200 Noisy Quantum Hardware Simulator",
@@ -293,8 +300,19 @@ class B200HardwareSimulator(_BackendBase):
     def device(self) -> dict:
         return self._device
 
-    # MultiDeviceBackend (application/backend.clj:117-131)
-    def select_device(self, device: dict):
+    # MultiDeviceBackend (application/backend.clj:117-131, hardware_simulator.clj:382-391)
+    def devices(self) -> List[dict]:
+        return list(self._devices)
+
+    def select_device(self, device):
+        """A device map, or the id of a catalogue entry.  (The reference's keyword branch looks up `:device` instead of
+        the id and selects nil, hardware_simulator.clj:387-389; here the id is resolved, unknown ids raise.)"""
+        if not isinstance(device, dict):
+            want = _kw(str(device))
+            found = [d for d in self._devices if _kw(str(_opt(d, "id"))) == want]
+            if not found:
+                raise KeyError(f"unknown device {device!r}")
+            device = found[0]
         self._device = device
         return device
 
@@ -332,6 +350,17 @@ class B200HardwareSimulator(_BackendBase):
             results.pop("shots-executed", None)
         return {"job-status": "completed", "circuit": circuit, "circuit-metadata": circuit_metadata(circuit),
                 "shots-executed": shots, "results": results}
+
+
+def load_device_catalog(path: str) -> List[dict]:
+    """Reads a device catalogue in the reference's format (`resources/simulator-devices.edn`: a vector of device maps with
+    `:id :num-qubits :native-gates :coupling :noise-model {:gate-noise {...} :readout-error {...}} ...`)."""
+    from . import io as QIO
+    with open(path) as f:
+        data = QIO.read_edn(f.read())
+    if isinstance(data, dict):
+        data = list(data.values())
+    return [d for d in data if isinstance(d, dict)]
 
 
 def create_hardware_simulator(device: Optional[dict] = None, config: Optional[dict] = None) -> B200HardwareSimulator:

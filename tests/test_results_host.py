@@ -2,6 +2,7 @@
 oracle-backed stand-in for the device state (tests/fake_sv.py).  The same extractors run against the real device state
 in tests/test_gpu_parity.py::test_result_extraction_*.  Reference: src/org/soulspace/qclojure/domain/result.clj."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -230,3 +231,52 @@ def test_edn_circuit_to_backend(fake_device, tmp_path):
     QIO.export_quantum_state("json", st, str(tmp_path / "s.json"))
     assert np.array_equal(QIO.import_quantum_state("json", str(tmp_path / "s.json"))["state-vector"], st["state-vector"])
     sim.close()
+
+
+def test_device_catalogue_in_the_reference_format(fake_device, tmp_path):
+    """MultiDeviceBackend (application/backend.clj:117-131): the catalogue is an EDN vector of device maps like
+    resources/simulator-devices.edn; the noise model of a selected entry feeds the C-ABI noise table unchanged."""
+    import json
+    import os
+    from qclojure_b200 import backend as B
+    from qclojure_b200 import io as QIO
+    from qclojure_b200 import noise as NZ
+    prof = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "device_profiles.json")))["devices"]
+    prof = [d for d in prof if ":gate-noise" in d["noise_model"]]
+
+    def unkw(x):      # the golden fixture spells keywords with the colon; rebuild the EDN text a QClojure resource holds
+        if isinstance(x, dict):
+            return {(k[1:] if isinstance(k, str) and k.startswith(":") else k): unkw(v) for k, v in x.items()}
+        if isinstance(x, list):
+            return [unkw(v) for v in x]
+        return QIO.Keyword(x[1:]) if isinstance(x, str) and x.startswith(":") else x
+    cat = [{"id": unkw(d["id"]), "name": d["id"][1:], "num-qubits": 7, "noise-model": unkw(d["noise_model"])} for d in prof[:4]]
+    f = tmp_path / "devices.edn"
+    f.write_text(QIO.write_edn(cat))
+    sim = B.create_hardware_simulator(config={"devices-file": str(f)})
+    ids = [str(d["id"]) for d in sim.devices()]
+    assert ids == [d["id"][1:] for d in prof[:4]]
+    dev = sim.select_device(ids[1])
+    assert sim.device() is dev and sim.backend_info()["device"] is dev
+    with pytest.raises(KeyError):
+        sim.select_device("no-such-device")
+    # the parsed noise model builds the same C-ABI table as the fixture's own spelling
+    a, _ka = NZ.build_noise_table(dev["noise-model"], 7)
+    b, _kb = NZ.build_noise_table(prof[1]["noise_model"], 7)
+    assert a.n_entries == b.n_entries and a.has_readout == b.has_readout
+    assert a.prob_0_to_1 == b.prob_0_to_1 and a.prob_1_to_0 == b.prob_1_to_0
+    for k in range(a.n_entries):
+        assert bytes(a.entries[k]) == bytes(b.entries[k])
+    own = {"id": "mine", "noise-model": {}}
+    sim2 = B.create_hardware_simulator(own, {"devices": cat})
+    assert len(sim2.devices()) == 5 and sim2.device() is own
+    sim.close(); sim2.close()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/resources/simulator-devices.edn"), reason="reference tree not present")
+def test_reference_device_resource_parses():
+    from qclojure_b200 import backend as B
+    cat = B.load_device_catalog("/root/reference/resources/simulator-devices.edn")
+    assert len(cat) >= 10 and all("id" in d and "noise-model" in d for d in cat)
+    lagos = [d for d in cat if d["id"] == "ibm-lagos"][0]
+    assert lagos["noise-model"]["readout-error"]["prob-0-to-1"] == 0.013       # simulator-devices.edn:532-560
