@@ -63,6 +63,11 @@ Config config_from(const qcb_config& c) {
   if (k.tile_bits > MAX_TILE_BITS) k.tile_bits = MAX_TILE_BITS;
   if (k.tile_bits > k.n_local) k.tile_bits = k.n_local;
   if (k.low_bits > k.tile_bits) k.low_bits = k.tile_bits;
+  // a tile smaller than the slice must have room for the two targets of a swap / dense two-qubit gate next to its fixed low bits
+  if (k.tile_bits < k.n_local) {
+    if (k.tile_bits < 2) k.tile_bits = std::min(2, k.n_local);
+    if (k.tile_bits < k.n_local && k.low_bits > k.tile_bits - 2) k.low_bits = k.tile_bits - 2;
+  }
   k.fusion = c.fusion;
   k.strict = c.strict_parity;
   k.max_stage_cost = c.max_stage_cost;
@@ -1197,7 +1202,9 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
     {
       Gate g0; uint64_t gt = 0;
       for (size_t i = 0; i < pending.size() && !gt; ++i) { g0 = to_phys(plan.gates[pending[i]]); gt = g0.target_mask() & ~local_mask; }
-      if (!gt) { plan.error = "scheduler made no progress"; return QCB_ERR_INVALID; }
+      size_t trailing_exchanges = 0;
+      for (size_t i = plan.stages.size(); i-- > 0 && plan.stages[i].kind == S_EXCHANGE;) ++trailing_exchanges;
+      if (!gt || trailing_exchanges > (size_t)(2 * n)) { plan.error = "scheduler made no progress"; return QCB_ERR_INVALID; }
       const int lo_cand = std::max(L, std::min(nl - 8, 12));
       const size_t window = std::min<size_t>(pending.size(), 4096);
       const size_t never = pending.size() + 1;
@@ -1221,10 +1228,13 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
       };
       const int gbit = 63 - __builtin_clzll(gt);
       int best = -1; size_t best_next = 0;
-      for (int cand = nl - 1; cand >= lo_cand && cand >= 0; --cand) {
-        if ((g0.target_mask() >> cand) & 1) continue;
-        const size_t next = next_use(cand);
-        if (best < 0 || next > best_next) { best = cand; best_next = next; }
+      for (int lo = lo_cand; best < 0; lo = 0) {             // tiny slices: fall back to any local bit
+        for (int cand = nl - 1; cand >= lo && cand >= 0; --cand) {
+          if ((g0.target_mask() >> cand) & 1) continue;
+          const size_t next = next_use(cand);
+          if (best < 0 || next > best_next) { best = cand; best_next = next; }
+        }
+        if (lo == 0) break;
       }
       if (best < 0) { plan.error = "no local qubit available for remap"; return QCB_ERR_INVALID; }
       emit_exchange(gbit, best);

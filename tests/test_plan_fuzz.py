@@ -1,0 +1,120 @@
+"""Randomised checks of the host side of the gate executor (lowering, scheduler, exchanges, program encoding, interpreters)
+on the CPU: random circuits over the whole gate vocabulary of SURVEY.md §8a', random tile geometry, 1 / 2 / 4 / 8 emulated
+ranks, against the oracle; and plan-trace replay against fresh scheduling.  Fixed seeds (a wider sweep of 3000 seeds was
+run while developing; it found the tile-geometry hang and the tiny-slice exchange gap that `config_from` / the exchange
+partner fallback now close)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import qc_oracle as O
+from qclojure_b200 import circuits as C
+from tests.emu import emu as E
+from tests.test_plan_trace import _fresh, _reangle, _replayed
+
+TOL = 1e-10
+_ONE = ["h", "x", "y", "z", "s", "t", "s-dag", "t-dag"]
+
+
+def random_circuit(n, rng, length, grover=False):
+    circ = C.create_circuit(n)
+    for _ in range(length):
+        r = int(rng.integers(0, 15 if grover else 14))
+        q = [int(x) for x in rng.permutation(n)[:3]]
+        a = float(rng.uniform(0, 2 * math.pi))
+        if r == 0:
+            C.add_gate(circ, _ONE[rng.integers(0, len(_ONE))], target=q[0])
+        elif r == 1:
+            C.rx(circ, q[0], a)
+        elif r == 2:
+            C.ry(circ, q[0], a)
+        elif r == 3:
+            C.rz(circ, q[0], a)
+        elif r == 4:
+            C.phase(circ, q[0], a if rng.random() < 0.8 else math.pi)
+        elif r == 5:
+            C.cnot(circ, q[0], q[1])
+        elif r == 6:
+            C.cz(circ, q[0], q[1])
+        elif r == 7:
+            C.add_gate(circ, ["crx", "cry", "crz"][rng.integers(0, 3)], control=q[0], target=q[1], angle=a)
+        elif r == 8:
+            (C.swap if rng.random() < 0.5 else C.iswap)(circ, q[0], q[1])
+        elif r == 9 and n >= 3:
+            C.toffoli(circ, q[0], q[1], q[2])
+        elif r == 10 and n >= 3:
+            C.fredkin(circ, q[0], q[1], q[2])
+        elif r == 11:
+            C.add_gate(circ, "rydberg-cphase", control=q[0], target=q[1], angle=a)
+        elif r == 12 and n >= 3:
+            C.add_gate(circ, "rydberg-blockade", qubit_indices=q[:int(rng.integers(2, 4))], angle=a)
+        elif r == 13:
+            C.add_gate(circ, ["global-h", "global-rx", "global-rz", "global-x"][rng.integers(0, 4)], angle=a)
+        elif r == 14:
+            for _k in range(int(rng.integers(0, 3))):
+                C.add_gate(circ, "phase-oracle", index=int(rng.integers(0, 1 << n)))
+            C.add_gate(circ, "grover-diffusion")
+    return circ
+
+
+def _reference(circ, init):
+    """Oracle semantics + the two operator-level ops the oracle does not know."""
+    st = init.copy()
+    for op in circ["operations"]:
+        t = op["operation-type"]
+        if t == "phase-oracle":
+            st[op["operation-params"]["index"]] *= -1
+        elif t == "grover-diffusion":
+            st = 2 * np.mean(st) - st
+        else:
+            st = O.apply_gate_to_state(st, op)
+    return st
+
+
+def _case(seed, grover=False):
+    rng = np.random.default_rng(seed)
+    world = int(rng.choice([1, 1, 2, 4, 8]))
+    p = world.bit_length() - 1
+    n = int(rng.integers(max(3, p + 3), 12))
+    nl = n - p
+    tile = int(rng.integers(min(3, nl), min(nl, 9) + 1))
+    low = int(rng.integers(1, max(2, min(tile, 4)) + 1))
+    circ = random_circuit(n, rng, int(rng.integers(5, 70)), grover)
+    init = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    init /= np.linalg.norm(init)
+    return n, world, tile, low, circ, init, int(rng.choice([1, 2]))
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_random_circuits_random_geometry_emulated_ranks(block):
+    for seed in range(40 * block, 40 * block + 40):
+        n, world, tile, low, circ, init, mma = _case(seed, grover=(seed % 3 == 0))
+        got = E.run_world(n, circ["operations"], init, world=world, tile_bits=tile, low_bits=low, dense_mma=mma)
+        err = float(np.max(np.abs(got - _reference(circ, init))))
+        assert err <= TOL, f"seed {seed}: n={n} world={world} tile={tile} low={low} err={err}"
+
+
+def test_degenerate_tile_geometry_is_sanitised():
+    # tile_bits == low_bits < n_local used to leave no room for a gate's targets (scheduler never finished)
+    n = 9
+    circ = C.create_circuit(n)
+    C.swap(circ, 0, 1); C.iswap(circ, 2, 8); C.fredkin(circ, 0, 3, 4); C.h(circ, 0); C.cnot(circ, 8, 0)
+    for kw in ({"tile_bits": 3, "low_bits": 3}, {"tile_bits": 5, "low_bits": 4, "world": 8}, {"tile_bits": 1, "low_bits": 1}):
+        got = E.run_world(n, circ["operations"], **kw)
+        assert np.max(np.abs(got - O.execute_circuit(circ))) <= TOL
+    # slices of 3 local qubits: exchange partners fall back to any local bit
+    circ = C.random_brickwork_circuit(6, 6, seed=2)
+    got = E.run_world(6, circ["operations"], world=8)
+    assert np.max(np.abs(got - O.execute_circuit(circ))) <= TOL
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_trace_replay_equals_fresh_schedule_on_random_circuits(block):
+    for seed in range(1000 + 25 * block, 1000 + 25 * block + 25):
+        n, world, tile, low, circ, _init, mma = _case(seed, grover=(seed % 2 == 0))
+        ops = circ["operations"]
+        new = _reangle(ops, seed)
+        for rank in {0, world - 1}:
+            kw = {"tile_bits": tile, "low_bits": low, "rank": rank, "world_size": world, "dense_mma": mma}
+            assert np.array_equal(_replayed(n, ops, new, **kw), _fresh(n, new, **kw)), f"seed {seed} rank {rank}"
