@@ -130,8 +130,24 @@
               req (.allocate a 88 8) idseg (.allocate a 8 8)]
           ;; struct qcb_job_request (include/qcb200.h): ops, n_ops, initial_state, initial_count, uniforms, n_shots, ham..., flags
           (.set req PTR 0 ops) (.set req I64 8 (long n-ops))
-          (.set req PTR 16 MemorySegment/NULL) (.set req I64 24 0)
+          ;; :initial-state (ideal_simulator.clj:84-86): interleaved re/im doubles, copied by qcb_submit
+          (if-let [init (:initial-state options)]
+            (let [amps (:state-vector init)
+                  iseg (.allocate a (long (* 16 (count amps))) 8)]
+              (doseq [[i z] (map-indexed vector amps)]
+                (.setAtIndex iseg F64 (long (* 2 i)) (double (fc/re z)))
+                (.setAtIndex iseg F64 (long (inc (* 2 i))) (double (fc/im z))))
+              (.set req PTR 16 iseg) (.set req I64 24 (long (count amps))))
+            (do (.set req PTR 16 MemorySegment/NULL) (.set req I64 24 0)))
           (.set req PTR 32 useg) (.set req I64 40 (long shots))
+          ;; :hamiltonian spec = collection of {:coefficient c :pauli-string "XIZ..."} (domain/hamiltonian.clj:35-62), the
+          ;; form the variational objective sends (variational_algorithm.clj:345); the noisy path's {:hamiltonian H} too
+          (when-let [ham (let [h (:hamiltonian specs)] (if (map? h) (:hamiltonian h) h))]
+            (let [cseg (.allocateFrom a F64 (double-array (map :coefficient ham)))
+                  pseg (.allocate a (long (* 8 (count ham))) 8)]
+              (doseq [[i term] (map-indexed vector ham)]
+                (.setAtIndex pseg PTR (long i) (.allocateFrom a ^String (:pauli-string term))))
+              (.set req PTR 48 cseg) (.set req PTR 56 pseg) (.set req I64 64 (long (count ham)))))
           (.set req I32 72 (int (if (<= n 24) 1 0)))             ; probabilities only where a Clojure vector can hold them
           (.set req I32 76 (int (if (<= n 24) 1 0)))
           (check! handle (.invokeWithArguments ^MethodHandle @qcb-submit [handle req idseg]))
@@ -155,13 +171,23 @@
                 res (.allocate a 344 8)]
             (.set res I64 16 (long shots)) (.set res PTR 24 outc)
             (check! handle (.invokeWithArguments ^MethodHandle @qcb-job-result [handle (long native-id) res]))
-            (let [outcomes (vec (for [i (range shots)] (.getAtIndex outc I64 (long i))))]
+            (let [outcomes (vec (for [i (range shots)] (.getAtIndex outc I64 (long i))))
+                  freq (frequencies outcomes)
+                  specs (:specs (@job-table job-id))]
               {:job-id job-id :job-status :completed
                :execution-time-ms (.get res F64 8)
-               :results {:measurement-results {:measurement-outcomes outcomes
-                                               :frequencies (frequencies outcomes)
-                                               :shot-count shots
-                                               :source :b200-simulation}}})))
+               :results (cond-> {:result-types (set (keys specs))}
+                          (:measurements specs)
+                          (assoc :measurement-results {:measurement-outcomes outcomes
+                                                       :frequencies freq
+                                                       :empirical-probabilities (into {} (map (fn [[k v]] [k (/ v (max 1 shots))]) freq))
+                                                       :shot-count shots
+                                                       :measurement-qubits (or (get-in specs [:measurements :qubits]) (range n))
+                                                       :source :ideal-simulation})
+                          ;; qcb_job_result.energy / has_energy (offsets 32 / 40): result.clj:327-344
+                          (pos? (.get res I32 40))
+                          (assoc :hamiltonian-result {:energy-expectation (.get res F64 32)
+                                                      :hamiltonian (let [h (:hamiltonian specs)] (if (map? h) (:hamiltonian h) h))}))})))
         {:job-id job-id :job-status (backend/job-status this job-id) :error-message "Job not completed"})
       {:job-id job-id :job-status :not-found :error-message "Job not found"}))
 
