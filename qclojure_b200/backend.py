@@ -345,7 +345,8 @@ class B200HardwareSimulator(_BackendBase):
                 results["density-matrix-trace"] = float(np.trace(rho).real)
         if specs:                                                      # result.clj:642-804
             results["shots-executed"] = shots
-            results = RS.extract_noisy_results(results, specs, n, lambda: L.StateVector(n),
+            dev = int(_opt(self.config, "device", -1))
+            results = RS.extract_noisy_results(results, specs, n, lambda: L.StateVector(n, device=dev),
                                                lambda shape: self._uniforms(options, shape))
             results.pop("shots-executed", None)
         return {"job-status": "completed", "circuit": circuit, "circuit-metadata": circuit_metadata(circuit),

@@ -580,6 +580,87 @@ static void small_apply(const Gate& g, const std::vector<int>& slot_pos, std::ve
   for (int s = 0; s < dim; ++s) v[s] = o[s];
 }
 
+// The same map applied to `ncol` vectors at once (M[pattern][column]): what build_dmma_round needs for the 8 basis columns of
+// a round's dense block.  Per column the arithmetic and its order are exactly small_apply's.
+static void small_apply_cols(const Gate& g, const std::vector<int>& slot_pos, cplx (*M)[8], int ncol, uint64_t fixed) {
+  const int r = (int)slot_pos.size(), dim = 1 << r;
+  uint64_t slot_mask = 0;
+  for (int p : slot_pos) slot_mask |= 1ULL << p;
+  auto sbit = [&](int pos) { for (int j = 0; j < r; ++j) if (slot_pos[j] == pos) return j; return -1; };
+  auto smask = [&](uint64_t m) { uint32_t o = 0; for (int j = 0; j < r; ++j) if ((m >> slot_pos[j]) & 1) o |= 1u << j; return o; };
+  auto outside_ok = [&](uint64_t mask, uint64_t val) { const uint64_t mo = mask & ~slot_mask; return (fixed & mo) == (val & mo); };
+  switch (g.kind) {
+    case G_MAT1: {
+      if (!outside_ok(g.cmask, g.cmask)) break;
+      const int j = sbit(g.t0); const uint32_t c = smask(g.cmask);
+      for (int s = 0; s < dim; ++s) {
+        if (((s >> j) & 1) || (s & c) != c) continue;
+        const int s1 = s | (1 << j);
+        for (int col = 0; col < ncol; ++col) {
+          const cplx a = M[s][col], b = M[s1][col];
+          M[s][col] = ca(cm(g.m[0], a), cm(g.m[1], b));
+          M[s1][col] = ca(cm(g.m[2], a), cm(g.m[3], b));
+        }
+      }
+      break;
+    }
+    case G_MAT2: {
+      if (!outside_ok(g.cmask, g.cmask)) break;
+      const int j0 = sbit(g.t0), j1 = sbit(g.t1); const uint32_t c = smask(g.cmask);
+      for (int s = 0; s < dim; ++s) {
+        if (((s >> j0) & 1) || ((s >> j1) & 1) || (s & c) != c) continue;
+        const int id[4] = {s, s | (1 << j0), s | (1 << j1), s | (1 << j0) | (1 << j1)};
+        for (int col = 0; col < ncol; ++col) {
+          const cplx in[4] = {M[id[0]][col], M[id[1]][col], M[id[2]][col], M[id[3]][col]};
+          for (int row = 0; row < 4; ++row) {
+            cplx acc{0, 0};
+            for (int k = 0; k < 4; ++k) acc = ca(acc, cm(g.m[row * 4 + k], in[k]));
+            M[id[row]][col] = acc;
+          }
+        }
+      }
+      break;
+    }
+    case G_SWAPP: {
+      if (!outside_ok(g.cmask, g.cmask)) break;
+      const int j0 = sbit(g.t0), j1 = sbit(g.t1); const uint32_t c = smask(g.cmask);
+      for (int s = 0; s < dim; ++s) {
+        if (((s >> j0) & 1) || ((s >> j1) & 1) || (s & c) != c) continue;
+        const int u = s | (1 << j0), w = s | (1 << j1);
+        for (int col = 0; col < ncol; ++col) {
+          const cplx a = M[u][col], b = M[w][col];
+          M[u][col] = cm(g.m[0], b); M[w][col] = cm(g.m[0], a);
+        }
+      }
+      break;
+    }
+    case G_DMASK: {
+      if (!outside_ok(g.dmask, g.dval)) break;
+      const uint32_t mk = smask(g.dmask), vl = smask(g.dval);
+      for (int s = 0; s < dim; ++s) if ((s & mk) == vl) for (int col = 0; col < ncol; ++col) M[s][col] = cm(M[s][col], g.m[0]);
+      break;
+    }
+    case G_DTAB1: {
+      if (!outside_ok(g.cmask, g.cmask)) break;
+      const int j = sbit(g.t0); const uint32_t c = smask(g.cmask);
+      for (int s = 0; s < dim; ++s) {
+        if ((s & c) != c) continue;
+        const int tb = (j >= 0) ? ((s >> j) & 1) : (int)((fixed >> g.t0) & 1);
+        for (int col = 0; col < ncol; ++col) M[s][col] = cm(M[s][col], g.m[tb]);
+      }
+      break;
+    }
+    case G_DPOP1: {
+      const int outside_ones = popc(fixed & g.dmask & ~slot_mask);
+      const uint32_t mk = smask(g.dmask);
+      for (int s = 0; s < dim; ++s)
+        if (outside_ones + popc((uint64_t)(s & mk)) == 1) for (int col = 0; col < ncol; ++col) M[s][col] = cm(M[s][col], g.m[0]);
+      break;
+    }
+    default: break;
+  }
+}
+
 // bits of a gate that are read or written (ext space)
 static uint64_t gate_bits(const Gate& g) {
   uint64_t b = g.target_mask() | g.diag_mask();
@@ -677,12 +758,8 @@ static void build_dmma_round(const Config& cfg, const Stage& st, Round& rd) {
     uint64_t fixed = 0;
     for (int j = 0; j < k; ++j) if ((var >> j) & 1) fixed |= 1ULL << rd.cond_pos[j];
     cplx M[8][8];
-    for (int col = 0; col < 8; ++col) {
-      std::vector<cplx> v(8, cplx{0, 0});
-      v[col] = {1, 0};
-      for (const Gate& g : rd.gates) small_apply(g, rd.slot_pos, v, fixed);
-      for (int row = 0; row < 8; ++row) M[row][col] = v[row];
-    }
+    for (int row = 0; row < 8; ++row) for (int col = 0; col < 8; ++col) M[row][col] = cplx{row == col ? 1.0 : 0.0, 0.0};
+    for (const Gate& g : rd.gates) small_apply_cols(g, rd.slot_pos, M, 8, fixed);
     double W[16][16];
     for (int mi = 0; mi < 16; ++mi) for (int ki = 0; ki < 16; ++ki) {
       int pr, cr, pc, cc;
