@@ -219,6 +219,30 @@ def run_ours(args):
     gpu_ms, wall_ms = float(t[0]), float(t[1])
     norm = sv.norm2()
 
+    # ---- the HBM-bound configuration of the same kernel on the same circuit (at most two tensor-core rounds per sweep):
+    # fewer gates/s than the default five-round sweeps, but this is where the north-star ">= 75 % of the HBM roofline"
+    # is read off; reported next to the headline, never instead of it
+    hbm_leg = None
+    if world == 1 and args.fusion and args.stage_rounds == 0 and not args.no_hbm_leg:
+        try:
+            with L.StateVector(n, device=local_rank, fusion=1, max_stage_rounds=2, tile_bits=args.tile_bits,
+                               low_bits=args.low_bits) as sv2:
+                for _ in range(2):
+                    sv2.set_zero(); sv2.apply_ops(enc)
+                sv2.synchronize()
+                sv2.timer_start()
+                for _ in range(3):
+                    sv2.set_zero(); sv2.apply_ops(enc)
+                ms2 = sv2.timer_stop()
+                st2 = sv2.stats()
+            peak2, _src = _peaks()
+            ach2 = st2["algorithmic_bytes"] / (st2["gpu_ms"] / 1000.0) / 1e9
+            hbm_leg = {"max_stage_rounds": 2, "gates_per_sec": n_gates * 3 / (ms2 / 1000.0), "ms_per_step": ms2 / 3,
+                       "sweeps_per_step": st2["n_sweeps"], "rounds_per_step": st2["n_rounds"], "achieved": ach2, "peak": peak2,
+                       "unit": "GB/s", "frac": ach2 / peak2}
+        except Exception as ex:    # noqa: BLE001 — an auxiliary leg must never take the headline down
+            hbm_leg = {"error": str(ex)}
+
     # ---- e2e: public backend API, host circuit in -> host shots out
     e2e = None
     if world == 1 and not args.no_e2e:
@@ -315,6 +339,8 @@ def run_ours(args):
             "gpu_launches": int(stats["n_kernel_launches"] + 1) * args.steps,
             "wall_ms_per_step": wall_ms / args.steps, "norm": norm, "clocks": clocks,
         }
+        if hbm_leg:
+            line["roofline"]["hbm_bound_config"] = hbm_leg
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
@@ -345,6 +371,7 @@ def main():
     ap.add_argument("--low-bits", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-hbm-leg", action="store_true", help="skip the auxiliary 2-rounds-per-sweep (HBM-bound) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
