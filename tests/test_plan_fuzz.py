@@ -118,3 +118,38 @@ def test_trace_replay_equals_fresh_schedule_on_random_circuits(block):
         for rank in {0, world - 1}:
             kw = {"tile_bits": tile, "low_bits": low, "rank": rank, "world_size": world, "dense_mma": mma}
             assert np.array_equal(_replayed(n, ops, new, **kw), _fresh(n, new, **kw)), f"seed {seed} rank {rank}"
+
+
+def test_empty_and_single_gate_programs():
+    from qclojure_b200 import _lib as L
+    assert L.plan_summary(5, []) == {"stages": 0, "rounds": 0, "exchanges": 0, "program_words": 4}
+    st = E.run_world(5, [])
+    assert st[0] == 1.0 and np.count_nonzero(st) == 1
+    for n in (1, 2, 13):
+        circ = C.h(C.create_circuit(n), n - 1)
+        assert np.max(np.abs(E.run_world(n, circ["operations"]) - O.execute_circuit(circ))) <= TOL
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_wire_formats_round_trip_random_circuits(seed):
+    """EDN / JSON / OpenQASM 3 carry a random circuit (every gate kind the formats know) without loss: the re-imported
+    circuit encodes to the same qcb_op array."""
+    from qclojure_b200 import io as QIO
+    from qclojure_b200 import ops as OPS
+    from qclojure_b200 import qasm3 as Q
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(3, 9))
+    circ = random_circuit(n, rng, 60)
+    a, na, _k = OPS.encode_ops(circ["operations"])
+    for fmt in ("edn", "json"):
+        back = QIO.deserialize_quantum_circuit(QIO._load(fmt, QIO._dump(fmt, QIO.serialize_quantum_circuit(circ))))
+        b, nb, _k2 = OPS.encode_ops(back["operations"])
+        assert na == nb and bytes(a) == bytes(b)
+    # QASM 3 has no spelling for the neutral-atom gates (they are emitted as decompositions / comments): leave them out
+    plain = C.create_circuit(n)
+    plain["operations"] = [o for o in circ["operations"]
+                           if not o["operation-type"].startswith(("global-", "rydberg-"))]
+    a, na, _k = OPS.encode_ops(plain["operations"])
+    back = Q.qasm_to_circuit(Q.circuit_to_qasm(plain))
+    b, nb, _k2 = OPS.encode_ops(back["operations"])
+    assert na == nb and bytes(a) == bytes(b)
