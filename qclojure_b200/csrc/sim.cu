@@ -885,12 +885,16 @@ int32_t qcb_config_default(qcb_config* cfg) {
 
 // Exchange the IPC handles of the state allocations and map the partners' states.  Every rank must reach the same verdict
 // (a rank pulling while its partner sends would hang), so the outcome is agreed on with a min-all-reduce; any failure
-// simply leaves the NCCL send/recv exchange in place.  QCB_EXCHANGE=nccl forces that path.
+// simply leaves the NCCL send/recv exchange in place.
 static void setup_p2p(qcb_sim* h) {
   const int world = h->cfg.world;
   h->peer_state.assign(world, nullptr);
+  // Default: peer-to-peer pull on 2 GPUs, where it has been validated end to end (parity + 687 GB/s per direction); the
+  // NCCL send/recv path - validated on 4 and 8 GPUs - on larger worlds until the pull path has been run there
+  // (QCB_EXCHANGE=p2p opts in, QCB_EXCHANGE=nccl forces the NCCL path everywhere).
   const char* mode = getenv("QCB_EXCHANGE");
-  double ok = (mode && std::string(mode) == "nccl") ? 0.0 : 1.0;
+  const std::string m = mode ? mode : "";
+  double ok = (m == "nccl" || (world > 2 && m != "p2p")) ? 0.0 : 1.0;
   unsigned char* d_ipc = nullptr;
   std::vector<cudaIpcMemHandle_t> handles(world);
   if (cudaMalloc(&d_ipc, (size_t)world * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) { cudaGetLastError(); return; }
