@@ -202,6 +202,36 @@ def qaoa_ansatz_circuit(problem_h, mixer_h, parameters: Sequence[float], n: int)
     return c
 
 
+def hhl_circuit(matrix: Sequence[Sequence[float]], b_vector: Sequence[float], precision_qubits: int = 4,
+                ancilla_qubits: int = 1) -> dict:
+    """application/algorithm/hhl.clj:625-714 (`hhl-circuit`): vector qubit(s), precision register, ancilla.  RY state
+    preparation for a 2-element b, H on the precision register, CRZ(0.1 * A[0][0] * 2^k) from precision qubit k onto the
+    vector qubit, RY(pi/8) on the ancilla, CRY(pi/(2+k)) from precision qubit k onto the ancilla, H on the precision
+    register in reverse order."""
+    n = len(matrix)
+    vq = max(1, int(math.ceil(math.log(n) / math.log(2))))
+    total = vq + precision_qubits + ancilla_qubits
+    c = create_circuit(total, "Working HHL Algorithm", f"Functional HHL for {n}×{n} matrix")
+    vec = list(range(vq))
+    prec = list(range(vq, vq + precision_qubits))
+    anc = list(range(vq + precision_qubits, total))
+    if n == 2:
+        b1, b2 = b_vector
+        norm = math.sqrt(b1 * b1 + b2 * b2)
+        nb1, nb2 = b1 / norm, b2 / norm
+        ry(c, vec[0], 2 * math.atan2(abs(nb2), abs(nb1)) if abs(nb2) > 1e-10 else 0.0)
+    for q in prec:
+        h(c, q)
+    for k, pq in enumerate(prec):
+        crz(c, pq, vec[0], 0.1 * matrix[0][0] * math.pow(2, k))
+    ry(c, anc[0], math.pi / 8)
+    for k, pq in enumerate(prec):
+        cry(c, pq, anc[0], math.pi / (2 + k))
+    for q in reversed(prec):
+        h(c, q)
+    return c
+
+
 def random_regular_graph(n: int, degree: int = 3, seed: int = 11) -> List[List[float]]:
     """3-regular random graph for the QAOA sweep of SURVEY §8(d) config 5 (pairing model with
     rejection; default_rng(seed))."""

@@ -393,6 +393,21 @@ def test_qaoa_energy_sweep_12q():
                 assert abs(sv.expect_hamiltonian(Hp) - want) <= TOL
 
 
+def test_hhl_tutorial_probabilities_on_gpu():
+    """JVM-recorded HHL run of the reference's tutorial (tests/golden/hhl_tutorial.json): 64 probabilities of a circuit with
+    four :cry gates - pins the transposed controlled gate on the CUDA path (strict_parity = 1)."""
+    with open(os.path.join(GOLDEN, "hhl_tutorial.json")) as f:
+        g = json.load(f)
+    circ = C.hhl_circuit(g["matrix"], g["vector"], g["precision_qubits"], g["ancilla_qubits"])
+    want = np.array(g["all_probabilities"])
+    with L.StateVector(6) as sv:
+        sv.apply_circuit(circ)
+        assert np.max(np.abs(sv.probabilities() - want)) <= TOL
+    with L.StateVector(6, strict_parity=0) as sv:
+        sv.apply_circuit(circ)
+        assert np.max(np.abs(sv.probabilities() - want)) > 0.05
+
+
 # ------------------------------------------------------------------ noise
 def _noise_table(nm, n):
     from qclojure_b200 import noise as NZ

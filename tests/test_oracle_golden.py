@@ -304,3 +304,27 @@ def test_dense_reference_form_equals_pairwise():
         a = O.apply_single_qubit_gate(st, O.rx_gate(0.37), q)
         b = O.apply_single_qubit_gate_dense(st, O.rx_gate(0.37), q)
         assert np.max(np.abs(a - b)) <= 1e-15
+
+
+def test_hhl_tutorial_run_pins_the_transposed_controlled_gate():
+    """doc/tutorial.md (HHL section): the JVM-recorded 64 probabilities of `hhl-circuit [[3 1] [1 2]] [7 5] 4 1` are
+    reproduced to 1e-15 by the oracle's literal `apply-controlled-gate` (transposed 2x2, gate.clj:473-483) and are off by
+    0.1 under the textbook CRY: the recorded run pins the convention SURVEY §8a row 5 lists as unpinned by the
+    reference's tests."""
+    import math
+    from qclojure_b200 import circuits as CB
+    with open(os.path.join(GOLDEN, "hhl_tutorial.json")) as f:
+        g = json.load(f)
+    circ = CB.hhl_circuit(g["matrix"], g["vector"], g["precision_qubits"], g["ancilla_qubits"])
+    assert circ["num-qubits"] == 6 and [o["operation-type"] for o in circ["operations"]].count("cry") == 4
+    want = np.array(g["all_probabilities"])
+    got = O.measurement_probabilities(O.execute_circuit(circ))
+    assert np.max(np.abs(got - want)) <= 1e-15
+    st = O.zero_state(6)
+    for op in circ["operations"]:
+        if op["operation-type"] == "cry":
+            p = op["operation-params"]
+            st = O.apply_controlled_gate(st, p["control"], p["target"], O.ry_gate(p["angle"]).T)   # U^T of U^T = textbook U
+        else:
+            st = O.apply_gate_to_state(st, op)
+    assert np.max(np.abs(O.measurement_probabilities(st) - want)) > 0.05

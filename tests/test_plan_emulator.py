@@ -221,6 +221,22 @@ def test_fused_grover_pass_mixed_with_gates_and_permuted_layout():
     assert np.max(np.abs(got - _grover_reference(n, 4, marked, extra=(1, 7)))) <= TOL
 
 
+def test_hhl_tutorial_probabilities_through_the_executor():
+    """The JVM-recorded HHL run (tests/golden/hhl_tutorial.json, doc/tutorial.md HHL section) through lowering + scheduler +
+    interpreters: matches under strict_parity = 1 (the reference's transposed controlled gate), differs by 0.1 under
+    textbook semantics."""
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "hhl_tutorial.json")) as f:
+        g = json.load(f)
+    circ = C.hhl_circuit(g["matrix"], g["vector"], g["precision_qubits"], g["ancilla_qubits"])
+    want = np.array(g["all_probabilities"])
+    for kw in ({}, {"tile_bits": 4, "low_bits": 2}, {"world": 4}):
+        got = E.run_world(6, circ["operations"], strict_parity=1, **kw)
+        assert np.max(np.abs(np.abs(got) ** 2 - want)) <= TOL
+    text = E.run_world(6, circ["operations"], strict_parity=0)
+    assert np.max(np.abs(np.abs(text) ** 2 - want)) > 0.05
+
+
 def test_bank_conflict_free_lane_mapping():
     """Every round of a 30-qubit brickwork plan must give conflict-free shared-memory access under the default tile
     layout (full XOR fold, tile_core.h: swz with c = 0; lane choice in plan.cpp).  The optional TMA-compatible layout
