@@ -236,10 +236,12 @@ def _load(fmt: str, text: str) -> dict:
     return read_edn(text) if _fmt(fmt) == "edn" else json.loads(text)
 
 
-def export_quantum_state(fmt: str, state: dict, filename: str) -> bool:
+def export_quantum_state(fmt: str, state: dict, filename: str):
+    """Returns the file name like the reference's `save-file` - except for :edn, where the reference's method returns nil
+    (`((io/serialize-quantum-state state) (qio/save-file ...))`, io/edn.clj:12-15; doc/tutorial.md prints `nil` there)."""
     with open(filename, "w") as f:
         f.write(_dump(fmt, serialize_quantum_state(state)))
-    return True
+    return None if _fmt(fmt) == "edn" else filename
 
 
 def import_quantum_state(fmt: str, filename: str) -> dict:
@@ -247,27 +249,29 @@ def import_quantum_state(fmt: str, filename: str) -> dict:
         return deserialize_quantum_state(_load(fmt, f.read()))
 
 
-def export_quantum_circuit(fmt: str, circuit: dict, filename: str) -> bool:
-    if str(fmt).lstrip(":").lower() == "qasm3":              # adapter/io/qasm.clj:21-27
-        from . import qasm3
-        return qasm3.export_quantum_circuit(circuit, filename)
+def export_quantum_circuit(fmt: str, circuit: dict, filename: str) -> str:
+    f3 = str(fmt).lstrip(":").lower()
+    if f3 in ("qasm2", "qasm3"):                             # adapter/io/qasm.clj:12-27
+        from . import qasm2, qasm3
+        return (qasm3 if f3 == "qasm3" else qasm2).export_quantum_circuit(circuit, filename)
     with open(filename, "w") as f:
         f.write(_dump(fmt, serialize_quantum_circuit(circuit)))
-    return True
+    return filename
 
 
 def import_quantum_circuit(fmt: str, filename: str) -> dict:
-    if str(fmt).lstrip(":").lower() == "qasm3":
-        from . import qasm3
-        return qasm3.import_quantum_circuit(filename)
+    f3 = str(fmt).lstrip(":").lower()
+    if f3 in ("qasm2", "qasm3"):
+        from . import qasm2, qasm3
+        return (qasm3 if f3 == "qasm3" else qasm2).import_quantum_circuit(filename)
     with open(filename) as f:
         return deserialize_quantum_circuit(_load(fmt, f.read()))
 
 
-def export_quantum_data(fmt: str, data: dict, filename: str) -> bool:
+def export_quantum_data(fmt: str, data: dict, filename: str) -> str:
     with open(filename, "w") as f:
         f.write(_dump(fmt, serialize_quantum_data(data)))
-    return True
+    return filename
 
 
 def import_quantum_data(fmt: str, filename: str) -> dict:

@@ -264,10 +264,10 @@ def qasm_to_circuit(qasm: str) -> dict:
 
 
 # ------------------------------------------------------------------ adapter/io/qasm.clj
-def export_quantum_circuit(circuit: dict, filename: str, options: Optional[dict] = None) -> bool:
+def export_quantum_circuit(circuit: dict, filename: str, options: Optional[dict] = None) -> str:
     with open(filename, "w") as f:
         f.write(circuit_to_qasm(circuit, options))
-    return True
+    return filename                      # util/io save-file returns the file name (doc/tutorial.md prints it)
 
 
 def import_quantum_circuit(filename: str) -> dict:

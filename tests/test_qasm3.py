@@ -154,7 +154,7 @@ def test_file_import_export_and_encoder(tmp_path):
     from qclojure_b200 import ops as OPS
     c = C.quantum_fourier_transform_circuit(5)
     f = tmp_path / "qft.qasm"
-    assert Q.export_quantum_circuit(c, str(f)) is True
+    assert Q.export_quantum_circuit(c, str(f)) == str(f)
     back = Q.import_quantum_circuit(str(f))
     a, na, _ = OPS.encode_ops(OPS.circuit_ops(c))
     b, nb, _ = OPS.encode_ops(OPS.circuit_ops(back))
@@ -164,3 +164,90 @@ def test_file_import_export_and_encoder(tmp_path):
     # the multimethod dispatch of adapter/io.clj on :qasm3
     QIO.export_quantum_circuit(":qasm3", c, str(tmp_path / "m.qasm"))
     assert len(QIO.import_quantum_circuit("qasm3", str(tmp_path / "m.qasm"))["operations"]) == len(c["operations"])
+
+
+# ------------------------------------------------------------------ the reference's own recorded output (doc/tutorial.md:755-940)
+def _tutorial_io_circuit():
+    c = C.create_circuit(3, "I/O Test Circuit", "A circuit with medium complexity")
+    C.h(c, 0); C.cnot(c, 0, 1); C.t_gate(c, 1); C.cnot(c, 1, 2); C.measure(c, [0, 1, 2])
+    return c
+
+
+TUTORIAL_QASM3 = '''OPENQASM 3.0;
+include "stdgates.inc";
+
+qubit[3] q;
+bit[3] c;
+
+h q[0];
+cx q[0], q[1];
+t q[1];
+cx q[1], q[2];
+c[0] = measure q[0];
+c[1] = measure q[1];
+c[2] = measure q[2];'''
+
+TUTORIAL_QASM2 = '''OPENQASM 2.0;
+include "qelib1.inc";
+qreg q[3];
+creg c[3];
+
+h q[0];
+cx q[0],q[1];
+t q[1];
+cx q[1],q[2];
+// Measurement will be handled by final measure statement
+measure q -> c;'''
+
+
+def test_tutorial_qasm_text_is_reproduced_exactly(tmp_path):
+    """The QASM 2 / QASM 3 files the reference's tutorial prints for its I/O test circuit, the circuits it reads back and
+    the return values of the export calls (doc/tutorial.md: 'OpenQASM Support')."""
+    from qclojure_b200 import qasm2 as Q2
+    c = _tutorial_io_circuit()
+    assert Q.circuit_to_qasm(c) == TUTORIAL_QASM3
+    assert Q2.circuit_to_qasm(c) == TUTORIAL_QASM2
+    f3, f2 = str(tmp_path / "test-circuit-qasm3.qasm"), str(tmp_path / "test-circuit-qasm2.qasm")
+    assert QIO.export_quantum_circuit(":qasm3", c, f3) == f3 and QIO.export_quantum_circuit(":qasm2", c, f2) == f2
+    back3 = QIO.import_quantum_circuit(":qasm3", f3)
+    assert [(str(o["operation-type"]), o["operation-params"]) for o in back3["operations"]] == [
+        ("h", {"target": 0}), ("cnot", {"control": 0, "target": 1}), ("t", {"target": 1}), ("cnot", {"control": 1, "target": 2}),
+        ("measure", {"measurement-qubits": [0]}), ("measure", {"measurement-qubits": [1]}), ("measure", {"measurement-qubits": [2]})]
+    assert back3["num-qubits"] == 3 and back3["name"] == "Converted Circuit" and back3["result-specs"] == {}
+    back2 = QIO.import_quantum_circuit(":qasm2", f2)
+    assert [(str(o["operation-type"]), o["operation-params"]) for o in back2["operations"]] == [
+        ("h", {"target": 0}), ("cnot", {"control": 0, "target": 1}), ("t", {"target": 1}), ("cnot", {"control": 1, "target": 2})]
+    assert back2["num-qubits"] == 3 and back2["name"] == "Converted Circuit" and "result-specs" not in back2
+
+
+def test_qasm2_round_trip_and_quirks():
+    from qclojure_b200 import qasm2 as Q2
+    c = C.create_circuit(4)
+    C.h(c, 0); C.add_gate(c, "s-dag", target=1); C.rx(c, 2, 0.5); C.phase(c, 3, 1e-7); C.crz(c, 0, 1, 0.25); C.cz(c, 1, 2)
+    C.add_gate(c, "cy", control=2, target=3); C.swap(c, 0, 3); C.iswap(c, 1, 2); C.toffoli(c, 0, 1, 2); C.fredkin(c, 3, 0, 1)
+    text = Q2.circuit_to_qasm(c)
+    for ln in ("sdg q[1];", "rx(0.5) q[2];", "p(1.0E-7) q[3];", "crz(0.25) q[0],q[1];", "cy q[2],q[3];", "swap q[0],q[3];",
+               "ccx q[0],q[1],q[2];", "cswap q[3],q[0],q[1];", "measure q -> c;"):
+        assert ln in text.splitlines(), ln
+    back = Q2.qasm_to_circuit(text)
+    assert [(o["operation-type"], o["operation-params"]) for o in back["operations"]] == \
+        [(o["operation-type"], o["operation-params"]) for o in c["operations"]]
+    # lines are matched untrimmed and angles are plain numbers (qasm2.clj:165-262)
+    assert Q2.qasm_to_circuit("qreg q[1];\n  h q[0];")["operations"] == []
+    with pytest.raises(ValueError):
+        Q2.qasm_to_circuit("qreg q[1];\nrx(pi/2) q[0];")
+    g = Q2.circuit_to_qasm(C.add_gate(C.create_circuit(2), "global-h"))
+    assert "// Global Hadamard gate - decomposed to individual H gates" in g and "h q[1];" in g
+
+
+def test_tutorial_state_files(tmp_path):
+    """doc/tutorial.md 'EDN Support' / 'JSON Support': |+> written and read back; EDN export returns nil, JSON the file name."""
+    st = {"state-vector": [0.7071067811865475, 0.7071067811865475], "num-qubits": 1}
+    fe, fj = str(tmp_path / "plus-state.edn"), str(tmp_path / "plus-state.json")
+    assert QIO.export_quantum_state(":edn", st, fe) is None and QIO.export_quantum_state(":json", st, fj) == fj
+    for fmt, f in ((":edn", fe), (":json", fj)):
+        back = QIO.import_quantum_state(fmt, f)
+        assert back["num-qubits"] == 1 and back["metadata"] == {}
+        assert back["state-vector"].tolist() == [0.7071067811865475 + 0j, 0.7071067811865475 + 0j]
+    assert open(fe).read() == ('{:state-vector [{:real 0.7071067811865475, :imag 0.0} {:real 0.7071067811865475, :imag 0.0}], '
+                               ':num-qubits 1, :metadata {}, :format-version "1.0"}')
