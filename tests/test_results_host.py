@@ -280,3 +280,30 @@ def test_reference_device_resource_parses():
     assert len(cat) >= 10 and all("id" in d and "noise-model" in d for d in cat)
     lagos = [d for d in cat if d["id"] == "ibm-lagos"][0]
     assert lagos["noise-model"]["readout-error"]["prob-0-to-1"] == 0.013       # simulator-devices.edn:532-560
+
+
+def test_observables_test_clj_known_answers():
+    """test/.../domain/observables_test.clj:62-142: expectation values, variances and eigenvalue measurement probabilities of
+    the Pauli observables on |0>, |1>, |+>, through the extractors (device faked by the oracle)."""
+    from qclojure_b200 import states as S
+    R = 1 / math.sqrt(2)
+    ident = np.eye(2)
+
+    def sv_of(st):
+        sv = FakeStateVector(1)
+        sv.set_state(st["state-vector"])
+        return sv
+    z0, z1, plus = sv_of(S.zero_state()), sv_of(S.one_state()), sv_of(S.plus_state())
+    exp = RS.observable_expectation
+    assert exp(z0, O.PAULI_Z, None) == pytest.approx(1.0) and exp(z1, O.PAULI_Z, None) == pytest.approx(-1.0)
+    assert exp(plus, O.PAULI_Z, None) == pytest.approx(0.0, abs=TOL) and exp(plus, O.PAULI_X, None) == pytest.approx(1.0)
+    assert exp(z0, O.PAULI_X, None) == pytest.approx(0.0, abs=TOL) and exp(z1, ident, None) == pytest.approx(1.0)
+    var = lambda sv, o: RS.extract_variance_results(sv, [o])[0]["variance-value"]      # noqa: E731
+    assert var(z0, O.PAULI_Z) == pytest.approx(0.0, abs=TOL) and var(z1, O.PAULI_Z) == pytest.approx(0.0, abs=TOL)
+    assert var(plus, O.PAULI_Z) == pytest.approx(1.0) and var(plus, O.PAULI_X) == pytest.approx(0.0, abs=TOL)
+    mp = RS.observable_measurement_probabilities
+    assert mp(z0, O.PAULI_Z) == pytest.approx({-1.0: 0.0, 1.0: 1.0}) and mp(z1, O.PAULI_Z) == pytest.approx({-1.0: 1.0, 1.0: 0.0})
+    px = mp(plus, O.PAULI_X)
+    assert sum(px.values()) == pytest.approx(1.0) and sum(v for v in px.values() if v > 0.9) == pytest.approx(1.0)
+    assert px[max(px)] == pytest.approx(1.0)                                            # the +1 eigenvalue of X on |+>
+    assert R * R == pytest.approx(mp(plus, O.PAULI_Z)[1.0])
