@@ -293,9 +293,19 @@ class B200HardwareSimulator(_BackendBase):
             self._devices.append(device)                     # create-hardware-simulator adds it (:407-411)
 
     def backend_info(self) -> dict:
+        # hardware_simulator.clj:284-290: :backend-type :backend-name :devices :device :config :capabilities #{:multi-device}
         return {"backend-type": "hardware-simulator", "backend-name": "B200 Noisy Quantum Hardware Simulator",
-                "backend-config": self.config, "max-qubits": int(_opt(self.config, "max-qubits", 26)),
-                "capabilities": {"quantum-backend", "multi-device"}, "device": self._device, "version": "0.1.0"}
+                "backend-config": self.config, "config": self.config, "max-qubits": int(_opt(self.config, "max-qubits", 26)),
+                "capabilities": {"quantum-backend", "multi-device"}, "device": self._device, "devices": self.devices(),
+                "version": "0.1.0"}
+
+    def queue_status(self) -> dict:
+        """hardware_simulator.clj:372-381 reports :total-jobs :active-jobs :completed-jobs (the ideal simulator's keys are kept
+        as well)."""
+        qs = super().queue_status()
+        qs["active-jobs"] = qs["queued"] + qs["running"]
+        qs["completed-jobs"] = qs["completed"]
+        return qs
 
     def device(self) -> dict:
         return self._device

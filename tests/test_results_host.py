@@ -307,3 +307,16 @@ def test_observables_test_clj_known_answers():
     assert sum(px.values()) == pytest.approx(1.0) and sum(v for v in px.values() if v > 0.9) == pytest.approx(1.0)
     assert px[max(px)] == pytest.approx(1.0)                                            # the +1 eigenvalue of X on |+>
     assert R * R == pytest.approx(mp(plus, O.PAULI_Z)[1.0])
+
+
+def test_hardware_simulator_protocol_surface(fake_device):
+    """test/.../adapter/backend/hardware_simulator_test.clj:21-33, 76-102: protocol surface without running a noisy job."""
+    from qclojure_b200 import backend as B
+    sim = B.create_hardware_simulator({"id": "dev", "noise-model": {}})
+    info = sim.backend_info()
+    assert info["backend-type"] == "hardware-simulator" and "multi-device" in info["capabilities"]
+    assert info["device"]["id"] == "dev" and [d["id"] for d in info["devices"]] == ["dev"] and sim.available()
+    qs = sim.queue_status()
+    assert {"total-jobs", "active-jobs", "completed-jobs"} <= set(qs)
+    assert sim.job_status("fake-job-id") == "not-found" and sim.job_result("fake-job-id")["job-status"] == "not-found"
+    sim.close()
