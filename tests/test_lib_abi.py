@@ -99,3 +99,37 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", "Makefile")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not banned.search(src), f
+
+
+def test_lowering_rejects_malformed_ops_without_crashing():
+    """The C ABI never throws or crashes on malformed qcb_op records (host-only planning entry): random kinds, qubit numbers
+    out of range, garbage masks -> an error code with a message, or a valid plan."""
+    import ctypes as CT
+    from qclojure_b200 import ops as OPS
+    lib = L.load()
+    rng = np.random.default_rng(0)
+    n = 6
+    cfg = OPS.make_config(n)
+    rejected = 0
+    for _ in range(600):
+        k = int(rng.integers(1, 6))
+        arr = (OPS.QcbOp * k)()
+        for i in range(k):
+            o = arr[i]
+            o.kind = int(rng.integers(-2, 45))
+            for j in range(3):
+                o.q[j] = int(rng.integers(-3, n + 3))
+            o.n_mask = int(rng.integers(-1, 9))
+            o.mask = int(rng.integers(0, 1 << 12))
+            o.angle = float(rng.normal())
+            for j in range(8):
+                o.mat[j] = float(rng.normal())
+        p = CT.c_void_p()
+        rc = lib.qcb_plan_create(CT.byref(cfg), arr, k, CT.byref(p))
+        if rc == 0:
+            lib.qcb_plan_destroy(p)
+        else:
+            rejected += 1
+            assert L.last_error(None)
+    assert rejected > 300
+    assert lib.qcb_plan_create(None, None, 0, None) != 0
