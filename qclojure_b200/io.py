@@ -34,6 +34,7 @@ class Keyword(str):
 _TOKEN = re.compile(r"""[\s,]*(~@|[\[\]{}()]|#\{|"(?:\\.|[^\\"])*"|;[^\n]*|[^\s\[\]{}()"`,;]+)""")
 _INT = re.compile(r"^[+-]?\d+N?$")
 _FLOAT = re.compile(r"^[+-]?(\d+\.?\d*([eE][+-]?\d+)?|\.\d+([eE][+-]?\d+)?)M?$")
+_RATIO = re.compile(r"^[+-]?\d+/\d+$")
 _ESC = {"n": "\n", "t": "\t", "r": "\r", '"': '"', "\\": "\\"}
 
 
@@ -66,6 +67,11 @@ def _atom(tok: str):
         return int(tok.rstrip("N"))
     if _FLOAT.match(tok):
         return float(tok.rstrip("M"))
+    if _RATIO.match(tok):                      # Clojure ratio literal, e.g. an angle written as 1/2
+        num, den = tok.split("/")
+        return int(num) / int(den)
+    if tok.startswith("\\") and len(tok) > 1:  # character literal
+        return {"\\newline": "\n", "\\space": " ", "\\tab": "\t"}.get(tok, tok[1:])
     if tok in ("##Inf", "##-Inf", "##NaN"):
         return {"##Inf": float("inf"), "##-Inf": float("-inf"), "##NaN": float("nan")}[tok]
     return tok                      # symbol

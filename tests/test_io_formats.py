@@ -77,6 +77,7 @@ def test_edn_scalars_and_errors():
         [1, -2, 3, 1.5, -2.0e-5, 1000.0, 4.5, float("inf"), float("-inf"), None, True, False, 'a"b', "k"]
     assert math.isnan(QIO.read_edn("##NaN"))
     assert QIO.read_edn("#{1 2}") == {1, 2}
+    assert QIO.read_edn("[1/2 -3/4 \\a \\newline :ns/kw]") == [0.5, -0.75, "a", "\n", "ns/kw"]
     assert QIO.write_edn(1e-7) == "1.0E-7" and QIO.write_edn(1e22) == "1.0E22" and QIO.write_edn(0.1) == "0.1"
     for bad in ("", "[1 2", "{:a}", "]"):
         with pytest.raises(ValueError):
