@@ -393,21 +393,6 @@ def test_qaoa_energy_sweep_12q():
                 assert abs(sv.expect_hamiltonian(Hp) - want) <= TOL
 
 
-def test_hhl_tutorial_probabilities_on_gpu():
-    """JVM-recorded HHL run of the reference's tutorial (tests/golden/hhl_tutorial.json): 64 probabilities of a circuit with
-    four :cry gates - pins the transposed controlled gate on the CUDA path (strict_parity = 1)."""
-    with open(os.path.join(GOLDEN, "hhl_tutorial.json")) as f:
-        g = json.load(f)
-    circ = C.hhl_circuit(g["matrix"], g["vector"], g["precision_qubits"], g["ancilla_qubits"])
-    want = np.array(g["all_probabilities"])
-    with L.StateVector(6) as sv:
-        sv.apply_circuit(circ)
-        assert np.max(np.abs(sv.probabilities() - want)) <= TOL
-    with L.StateVector(6, strict_parity=0) as sv:
-        sv.apply_circuit(circ)
-        assert np.max(np.abs(sv.probabilities() - want)) > 0.05
-
-
 # ------------------------------------------------------------------ noise
 def _noise_table(nm, n):
     from qclojure_b200 import noise as NZ
@@ -674,3 +659,18 @@ def test_multi_gpu_sharded_matches_oracle():
            "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")]
     out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "multi-gpu ok" in out.stdout, (out.stdout[-2000:], out.stderr[-3000:])
+
+
+def test_hhl_tutorial_probabilities_on_gpu():
+    """JVM-recorded HHL run of the reference's tutorial (tests/golden/hhl_tutorial.json): 64 probabilities of a circuit with
+    four :cry gates - pins the transposed controlled gate on the CUDA path (strict_parity = 1)."""
+    with open(os.path.join(GOLDEN, "hhl_tutorial.json")) as f:
+        g = json.load(f)
+    circ = C.hhl_circuit(g["matrix"], g["vector"], g["precision_qubits"], g["ancilla_qubits"])
+    want = np.array(g["all_probabilities"])
+    with L.StateVector(6) as sv:
+        sv.apply_circuit(circ)
+        assert np.max(np.abs(sv.probabilities() - want)) <= TOL
+    with L.StateVector(6, strict_parity=0) as sv:
+        sv.apply_circuit(circ)
+        assert np.max(np.abs(sv.probabilities() - want)) > 0.05
