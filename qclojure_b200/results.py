@@ -137,6 +137,14 @@ def extract_expectation_results(sv, observables, target_qubits=None) -> List[dic
              "target-qubits": None if t is None else [t]} for o, t in zip(observables, tq)]
 
 
+def _square(m: np.ndarray) -> np.ndarray:
+    """O^2 through the P2 product (`cla/matrix-multiply`, observables.clj:316); a 2x2 is squared in place."""
+    if m.shape == (2, 2):
+        return m @ m
+    with _la() as la:
+        return np.asarray(la.matrix_multiply(m, m))
+
+
 def extract_variance_results(sv, observables, target_qubits=None) -> List[dict]:
     """result.clj:290-325 with observables.clj:305-320: <O^2> - <O>^2."""
     tq = list(target_qubits) if target_qubits else [None] * len(observables)
@@ -144,7 +152,7 @@ def extract_variance_results(sv, observables, target_qubits=None) -> List[dict]:
     for o, t in zip(observables, tq):
         m = np.asarray(o, dtype=np.complex128)
         e = observable_expectation(sv, m, t)
-        v = observable_expectation(sv, m @ m, t) - e * e
+        v = observable_expectation(sv, _square(m), t) - e * e
         out.append({"variance-value": v, "standard-deviation": math.sqrt(v) if v >= 0 else float("nan"), "observable": o,
                     "target-qubits": None if t is None else [t]})
     return out
@@ -375,7 +383,8 @@ def extract_noisy_results(base: dict, specs: dict, n: int, make_sv: Callable, un
                 for o, t in zip(obs, tq or [None] * len(obs)):
                     m = np.asarray(o, dtype=np.complex128)
                     e = mean(lambda s: observable_expectation(s, m, t))
-                    e2 = mean(lambda s: observable_expectation(s, m @ m, t))
+                    m2 = _square(m)
+                    e2 = mean(lambda s: observable_expectation(s, m2, t))
                     res.append({"variance-value": e2 - e * e, "observable": o, "target-qubits": tq, "source": "density-matrix"})
                 out["variance-results"] = res
             elif typ == "hamiltonian":

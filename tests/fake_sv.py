@@ -85,6 +85,9 @@ class FakeLinearAlgebra:
     def matrix_vector_product(self, A, x):
         return np.asarray(A) @ np.asarray(x)
 
+    def matrix_multiply(self, A, B):
+        return np.asarray(A) @ np.asarray(B)
+
     def trace(self, A):
         return np.trace(A)
 
