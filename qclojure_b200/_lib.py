@@ -33,7 +33,8 @@ class QcbError(RuntimeError):
 
 def build(force: bool = False) -> str:
     """Compile libqcb200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "sim.cu", "plan.cpp", "kernels.h", "plan.h", "tile_core.h")]
+    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "sim.cu", "plan.cpp", "la_host.cpp", "kernels.h", "plan.h",
+                                             "tile_core.h", "la_host.h")]
     srcs.append(os.path.join(os.path.dirname(HERE), "include", "qcb200.h"))
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:

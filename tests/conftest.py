@@ -29,4 +29,13 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _library_present():
+    """A fresh checkout has no libqcb200.so yet (built artefacts are not in the history): compile it once (nvcc cross-compiles
+    without a GPU).  An existing library is used as it is - `__graft_entry__.build()` is what rebuilds a stale one."""
+    from qclojure_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
