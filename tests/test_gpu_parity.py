@@ -661,6 +661,28 @@ def test_multi_gpu_sharded_matches_oracle():
     assert out.returncode == 0 and "multi-gpu ok" in out.stdout, (out.stdout[-2000:], out.stderr[-3000:])
 
 
+def test_config2_grover_26q_full_size_property():
+    """BASELINE.json configs[1] at its full size (26 qubits, 1 GiB state): after k oracle + diffusion operators the marked
+    amplitude is sin((2k+1) theta) and every other amplitude cos((2k+1) theta) / sqrt(N-1), theta = asin(1/sqrt(N)) - a
+    size-independent closed form (the oracle would need minutes here).  64 iterations through the fused Grover pass."""
+    n, k, target = 26, 64, 0x2AAAAAA
+    N = 1 << n
+    ops = [{"operation-type": "global-h", "operation-params": {}}]
+    for _ in range(k):
+        ops += [{"operation-type": "phase-oracle", "operation-params": {"index": target}},
+                {"operation-type": "grover-diffusion", "operation-params": {}}]
+    theta = math.asin(1.0 / math.sqrt(N))
+    idx = np.random.default_rng(26).integers(0, N, 1024)
+    idx = idx[idx != target]
+    with L.StateVector(n) as sv:
+        sv.apply_ops(ops)
+        amps = sv.get_amplitudes(np.concatenate([[target], idx]))
+        assert abs(sv.norm2() - 1.0) <= TOL
+        assert sv.stats()["n_sweeps"] <= k + 8                     # one streaming pass per iteration
+    assert abs(amps[0] - math.sin((2 * k + 1) * theta)) <= TOL
+    assert np.max(np.abs(amps[1:] - math.cos((2 * k + 1) * theta) / math.sqrt(N - 1))) <= TOL
+
+
 def test_hhl_tutorial_probabilities_on_gpu():
     """JVM-recorded HHL run of the reference's tutorial (tests/golden/hhl_tutorial.json): 64 probabilities of a circuit with
     four :cry gates - pins the transposed controlled gate on the CUDA path (strict_parity = 1)."""
