@@ -144,7 +144,10 @@ int32_t qcb_measure_qubits(qcb_handle h, const int32_t* qubits, int32_t m, doubl
 /* marginal distribution only (no collapse): out_probs[2^m] */
 int32_t qcb_marginal_probabilities(qcb_handle h, const int32_t* qubits, int32_t m, double* out_probs);
 
-/* ---- expectation: domain/observables.clj:216-251, domain/hamiltonian.clj:91-114, result.clj:266-288 ---- */
+/* ---- expectation: domain/observables.clj:216-251, domain/hamiltonian.clj:91-114, result.clj:266-288 ----
+   Sharded states: a Pauli string with X / Y factors on global qubits is evaluated after the term's qubits have been brought
+   into local positions by qubit exchanges (the layout permutation is tracked; nothing is moved back until a read needs the
+   canonical order).  Only a string with more X / Y factors than one GPU holds qubits fails (QCB_ERR_UNSUPPORTED). */
 int32_t qcb_expect_pauli(qcb_handle h, const char* pauli_string, double* out);
 int32_t qcb_expect_hamiltonian(qcb_handle h, const double* coeffs, const char* const* pauli_strings,
                                uint64_t n_terms, double* out_energy, double* out_terms /* may be NULL */);
