@@ -73,15 +73,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// BACKOFF: the waiter has nothing else to do for a long time (the mover waiting for a tile to be finished): let the hardware
+// suspend the thread inside try_wait (suspend-time hint, ns) instead of polling - a polling warp competes for issue slots and
+// for the shared-memory pipe with the consumers (round 1: 27 % of all stall samples sat on the two polling branches).
 template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t ok;
   for (;;) {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (BACKOFF)
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(ok) : "r"(a), "r"(parity), "r"(20000u) : "memory");
+    else
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     if (ok) break;
-    if (BACKOFF) __nanosleep(64);      // keep the pollers out of the issue slots of the working warps
   }
 }
 // arrive on `bar` once every cp.async issued so far by this thread has landed in shared memory
@@ -292,6 +298,120 @@ __device__ __forceinline__ void dmma_round_run(uint32_t tile_s, const uint4* lan
   }
 }
 
+// ------------------------------------------------------------------ tensor-core round, three-product form (round kind 2)
+// tile_core.h: K3Ctx.  Per batch of 8 groups a lane issues two 16-byte loads (complex amplitudes of pattern lane%4 + 4s,
+// group lane/4), four DADD (Br + Bi, Bi - Br), six DMMA.8x8x4 (K = P Br; Re = N (Br + Bi) + K; Im = R (Bi - Br) + K) and two
+// 16-byte stores - against eight DMMA, four 8-byte loads and four 8-byte stores of the 16x16 real form.
+__device__ __forceinline__ void lds_c128(uint32_t addr, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(x), "=d"(y) : "r"(addr));
+}
+__device__ __forceinline__ void sts_c128(uint32_t addr, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void dmma_884_c(double& d0, double& d1, double a, double b, double c0, double c1) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
+               : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+__device__ __forceinline__ void k3_load_A(double (&A)[6], const double* __restrict__ mats, uint32_t var) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) A[i] = __ldg(mats + (size_t)var * K3_FRAG_DOUBLES + i * 32);
+}
+
+// Batches btab[0..per) of one warp, all with the matrix variant held in A (P0 P1 N0 N1 R0 R1).  Software pipeline over
+// batches: in the steady state the warp issues, for batch i,   Re0(i) K0(i+1) Im0(i) K1(i+1) Re1(i) Im1(i)   - every
+// dependent pair is at least two tensor instructions apart (a DMMA.8x8x4 holds the pipe of the SM partition for 16 cycles,
+// its result is ready after 26), so a single warp can keep the pipe busy - with the DADDs of batch i+1, the loads of batch
+// i+2 and the stores of batch i-1 slotted in between.  The loop stays ROLLED on purpose: ptxas re-schedules a fully
+// unrolled body batch by batch (dependent K0 -> K1 -> Re0 back to back, loads sunk to their first use), which undoes the
+// pipeline; across a loop back edge it cannot.  (-DQCB_K3_UNROLL builds the unrolled variant for comparison.)
+struct K3State {
+  double K0, K1, s0, s1, d0, d1;              // batch i: K = P Br and (Br + Bi), (Bi - Br) of k-steps 0, 1
+  double nr0, ni0, nr1, ni1;                  // batch i+1: raw loads
+  double pr0, pr1, pi0, pi1;                  // batch i-1: results waiting for their stores
+  uint32_t X, Xp, Xn;                         // swizzled byte offsets of batches i, i-1, i+1
+};
+template <bool HAS1, bool HAS2, bool HASP>
+__device__ __forceinline__ void k3_iter(K3State& t, uint32_t tile_s, const uint4& lt, uint32_t x_next2, const double (&A)[6]) {
+  double re0, re1, im0, im1, k0n = 0, k1n = 0, ns0 = 0, ns1 = 0, nd0 = 0, nd1 = 0;
+  dmma_884_c(re0, re1, A[2], t.s0, t.K0, t.K1);
+  if (HAS1) dmma_884_c(k0n, k1n, A[0], t.nr0, 0.0, 0.0);
+  dmma_884_c(im0, im1, A[4], t.d0, t.K0, t.K1);
+  if (HAS1) {
+    dmma_884_c(k0n, k1n, A[1], t.nr1, k0n, k1n);
+    ns0 = t.nr0 + t.ni0; nd0 = t.ni0 - t.nr0; ns1 = t.nr1 + t.ni1; nd1 = t.ni1 - t.nr1;
+  }
+  if (HAS2) {
+    lds_c128(tile_s + (lt.x ^ x_next2), t.nr0, t.ni0);
+    lds_c128(tile_s + (lt.y ^ x_next2), t.nr1, t.ni1);
+  }
+  dmma_884_c(re0, re1, A[3], t.s1, re0, re1);
+  if (HASP) {
+    sts_c128(tile_s + (lt.z ^ t.Xp), t.pr0, t.pi0);
+    sts_c128(tile_s + (lt.w ^ t.Xp), t.pr1, t.pi1);
+  }
+  dmma_884_c(im0, im1, A[5], t.d1, im0, im1);
+  t.pr0 = re0; t.pr1 = re1; t.pi0 = im0; t.pi1 = im1;
+  t.Xp = t.X; t.X = t.Xn; t.Xn = x_next2;
+  t.K0 = k0n; t.K1 = k1n; t.s0 = ns0; t.s1 = ns1; t.d0 = nd0; t.d1 = nd1;
+}
+__device__ __forceinline__ void k3_batches(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[6]) {
+  K3State t;
+  t.X = btab[0] & DMMA_BATCH_OFF_MASK; t.Xp = t.X; t.Xn = t.X;
+  t.pr0 = t.pr1 = t.pi0 = t.pi1 = 0.0;
+  {
+    double r0, i0, r1, i1;
+    lds_c128(tile_s + (lt.x ^ t.X), r0, i0);
+    lds_c128(tile_s + (lt.y ^ t.X), r1, i1);
+    if (per > 1u) {
+      t.Xn = btab[1] & DMMA_BATCH_OFF_MASK;
+      lds_c128(tile_s + (lt.x ^ t.Xn), t.nr0, t.ni0);
+      lds_c128(tile_s + (lt.y ^ t.Xn), t.nr1, t.ni1);
+    } else { t.nr0 = t.ni0 = t.nr1 = t.ni1 = 0.0; }
+    t.s0 = r0 + i0; t.d0 = i0 - r0; t.s1 = r1 + i1; t.d1 = i1 - r1;
+    dmma_884_c(t.K0, t.K1, A[0], r0, 0.0, 0.0);
+    dmma_884_c(t.K0, t.K1, A[1], r1, t.K0, t.K1);
+  }
+  if (per >= 3u) {
+    k3_iter<true, true, false>(t, tile_s, lt, btab[2] & DMMA_BATCH_OFF_MASK, A);
+#ifdef QCB_K3_UNROLL
+#pragma unroll 16
+#else
+#pragma unroll 1
+#endif
+    for (uint32_t i = 1; i + 2u < per; ++i) k3_iter<true, true, true>(t, tile_s, lt, btab[i + 2u] & DMMA_BATCH_OFF_MASK, A);
+    k3_iter<true, false, true>(t, tile_s, lt, 0u, A);
+    k3_iter<false, false, true>(t, tile_s, lt, 0u, A);
+  } else if (per == 2u) {
+    k3_iter<true, false, false>(t, tile_s, lt, 0u, A);
+    k3_iter<false, false, true>(t, tile_s, lt, 0u, A);
+  } else {
+    k3_iter<false, false, false>(t, tile_s, lt, 0u, A);
+  }
+  sts_c128(tile_s + (lt.z ^ t.Xp), t.pr0, t.pi0);
+  sts_c128(tile_s + (lt.w ^ t.Xp), t.pr1, t.pi1);
+}
+
+// One warp's share of a three-product round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
+__device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
+                                             uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[6], uint32_t cur) {
+  const uint4 lt = lane_tab_r[2u * lane];
+  if ((btab[0] >> 20) == (btab[per - 1u] >> 20)) {
+    // local condition bits are the top bits of the batch index: equal at both ends => one variant for the whole share
+    k3_batches(tile_s, lt, btab, per, A);
+    return;
+  }
+  // the variant changes inside the share: runs of equal variants, each through the pipelined loop
+  uint32_t b = 0;
+  while (b < per) {
+    const uint32_t v = var_hi | (btab[b] >> 20);
+    uint32_t e = b + 1u;
+    while (e < per && (btab[e] >> 20) == (btab[b] >> 20)) ++e;
+    if (v != cur) { k3_load_A(A, mats, v); cur = v; }
+    k3_batches(tile_s, lt, btab + b, e - b, A);
+    b = e;
+  }
+}
+
 // Pacing of the mover (QCB_MOVER_PAUSE_NS, experiment knob): nanoseconds slept between groups of 8 element copies so that a
 // burst of mover LDGSTS / LDS.128 does not monopolise the LSU pipe the consumers' fragment loads depend on.  0 = off.
 __device__ unsigned g_mover_pause_ns;
@@ -369,7 +489,8 @@ constexpr int MOVER_THREADS = MOVER_WARPS * 32;
 
 // MMA_ONLY = true: every round of the stage is a tensor-core round (the common case); the op interpreter is
 // compiled out, which keeps the hot loop free of register spills.
-template <int NG, int WPG, bool MMA_ONLY>
+// FORM: kind of the stage's tensor-core rounds (one per plan): 2 = three-product form (default), 1 = 16x16 real block.
+template <int NG, int WPG, bool MMA_ONLY, int FORM>
 __global__ void __launch_bounds__((NG * WPG + MOVER_WARPS) * 32, 1)
 k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, uint32_t stage_words,
              const double* __restrict__ dev_vals, uint64_t n_active, uint32_t nbuf, const __grid_constant__ CUtensorMap tmap,
@@ -406,13 +527,21 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
   __syncthreads();
   for (uint32_t idx = tid; idx < sc.n_rounds * 32u; idx += NTHREADS) {
     const uint32_t r = idx >> 5;
-    if (round_kind(sprog, r) != 1u) continue;
-    DmmaCtx c;
-    decode_dmma(sprog, r, c);
-    uint32_t e[8];
-    dmma_lane_entry(c, idx & 31u, e);
-    lane_tab[2u * idx] = make_uint4(e[0], e[1], e[2], e[3]);
-    lane_tab[2u * idx + 1u] = make_uint4(e[4], e[5], e[6], e[7]);
+    if (round_kind(sprog, r) != (uint32_t)FORM) continue;
+    if (FORM == 2) {
+      K3Ctx c;
+      decode_k3(sprog, r, c);
+      uint32_t e[4];
+      k3_lane_entry(c, idx & 31u, e);
+      lane_tab[2u * idx] = make_uint4(e[0], e[1], e[2], e[3]);
+    } else {
+      DmmaCtx c;
+      decode_dmma(sprog, r, c);
+      uint32_t e[8];
+      dmma_lane_entry(c, idx & 31u, e);
+      lane_tab[2u * idx] = make_uint4(e[0], e[1], e[2], e[3]);
+      lane_tab[2u * idx + 1u] = make_uint4(e[4], e[5], e[6], e[7]);
+    }
   }
   for (uint32_t r = tid; r < sc.n_rounds; r += NTHREADS) {
     const uint64_t* w = sprog + T_STAGE_WORDS + (uint64_t)r * T_ROUND_WORDS;
@@ -425,8 +554,8 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
   }
   for (uint32_t idx = tid; idx < sc.n_rounds * nbstride; idx += NTHREADS) {
     const uint32_t r = idx / nbstride, b = idx - r * nbstride;
-    if (round_kind(sprog, r) != 1u) continue;
-    DmmaCtx c;
+    if (round_kind(sprog, r) != (uint32_t)FORM) continue;
+    DmmaCtx c;                                            // the batch geometry words are common to both forms
     decode_dmma(sprog, r, c);
     if (b < (1u << (c.n_grp - 3u))) batch_tab[idx] = dmma_batch_entry(c, b, m);
   }
@@ -434,8 +563,17 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
 
   const uint32_t T = (uint32_t)((n_active - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
   const uint32_t lowmask = (1u << L) - 1u;
+  // Optional register re-allocation between the warpgroups (setmaxnreg; -DQCB_REALLOC): the kernel is compiled for 168
+  // registers per thread (384 threads, one CTA per SM); the mover warpgroup would hand registers to the consumer warpgroups.
+#ifdef QCB_REALLOC
+  constexpr bool REALLOC = (NCW == 8 && MOVER_WARPS == 4);
+#else
+  constexpr bool REALLOC = false;     // the consumer path needs ~120 registers: no re-allocation required (experiment switch)
+#endif
 
-  if (warp >= NCW && use_tma) {
+  if (warp >= NCW) {
+  if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n");
+  if (use_tma) {
     // ---------------- mover (TMA): one warp, one bulk tensor copy per run
     if (warp > NCW) return;
     const uint32_t nruns = 1u << (m - L), smem_s = smem_u32(smem_raw);
@@ -466,11 +604,11 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
       }
     }
     PF_TOTAL(PF_M_TOTAL);
-  } else if (warp >= NCW && L == 4u && LC == 0u && (m == 12u || m == 11u)) {
+  } else if (L == 4u && LC == 0u && (m == 12u || m == 11u)) {
     // ---------------- mover warps, 64 KB / 32 KB tiles with 256-byte runs (the common case)
     if (m == 12u) mover_fast<32>(state, sprog, sc, hoff, smem_u32(smem_raw), (uint32_t)tile_bytes, tid - NCT, T, nbuf, full, done);
     else mover_fast<16>(state, sprog, sc, hoff, smem_u32(smem_raw), (uint32_t)tile_bytes, tid - NCT, T, nbuf, full, done);
-  } else if (warp >= NCW) {
+  } else {
     // ---------------- mover warps (fallback: 16 bytes per thread through the LSU)
     const uint32_t mt = tid - NCT;
     PF_DECL;
@@ -508,15 +646,18 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
       }
     }
     PF_TOTAL(PF_M_TOTAL);
+  }
   } else {
     // ---------------- consumer groups
+    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;\n");
     const uint32_t grp = warp / WPG, gwarp = warp - grp * WPG, gtid = tid - grp * GT;
     const uint32_t smem_s = smem_u32(smem_raw);
     // every tensor-core round has m - 3 group bits: the batch geometry of this warp is a kernel constant
     const uint32_t nbatch = tile_n >= 64u ? (tile_n >> 6) : 1u;
     const uint32_t per = nbatch >= (uint32_t)WPG ? nbatch / WPG : 1u, b0 = gwarp * per;
     const bool active = b0 < nbatch;
-    double A[8];
+    constexpr int NA = FORM == 2 ? 6 : 8;                 // A-fragment registers of one matrix variant
+    double A[NA];
     uint32_t cur = 0xffffffffu, var_hi = 0;
     DBG_DECL;
     // operands of (tile j, round r): variant bits from the tile id, first variant of this warp, its A fragments
@@ -526,9 +667,10 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
       const uint2 rt = rtab[r];
       var_hi = dmma_var_hi(rt.x, ext_hi);
       cur = var_hi | (batch_tab[r * nbstride + b0] >> 20);
-      dmma_load_A(A, reinterpret_cast<const double*>(stage_g + rt.y) + lane, cur);
+      if constexpr (FORM == 2) k3_load_A(A, reinterpret_cast<const double*>(stage_g + rt.y) + lane, cur);
+      else dmma_load_A(A, reinterpret_cast<const double*>(stage_g + rt.y) + lane, cur);
     };
-    if (grp < T && (MMA_ONLY || round_kind(sprog, 0) == 1u)) prefetch(grp, 0);
+    if (grp < T && (MMA_ONLY || round_kind(sprog, 0) == (uint32_t)FORM)) prefetch(grp, 0);
     PF_DECL;
     for (uint32_t j = grp; j < T; j += NG) {
       const uint32_t b = j % nbuf;
@@ -539,18 +681,23 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
         PF_ADD(PF_C_BARRIER);
         uint32_t nj = j, nr = r + 1u;
         if (nr == sc.n_rounds) { nr = 0; nj = j + NG; }
-        const bool next_mma = nj < T && (MMA_ONLY || round_kind(sprog, nr) == 1u);
-        if (MMA_ONLY || round_kind(sprog, r) == 1u) {
-          double Ac[8];
+        const bool next_mma = nj < T && (MMA_ONLY || round_kind(sprog, nr) == (uint32_t)FORM);
+        if (MMA_ONLY || round_kind(sprog, r) == (uint32_t)FORM) {
+          double Ac[NA];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) Ac[i] = A[i];
+          for (int i = 0; i < NA; ++i) Ac[i] = A[i];
           const uint32_t curc = cur, var_hic = var_hi;
           const double* mats = reinterpret_cast<const double*>(stage_g + rtab[r].y) + lane;
           if (next_mma) prefetch(nj, nr);
           PF_ADD(PF_C_SETUP);
-          if (active)
-            dmma_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                           mats, lane, Ac, curc, dbg_bits);
+          if (active) {
+            if constexpr (FORM == 2)
+              k3_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
+                           mats, lane, Ac, curc);
+            else
+              dmma_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
+                             mats, lane, Ac, curc, dbg_bits);
+          }
           PF_ADD(PF_C_ROUND);
         } else if (!MMA_ONLY) {
           RoundCtx rc;
@@ -575,7 +722,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
 }
 
 template <int NG, int WPG>
-static cudaError_t launch_tile_stage_t(bool mma_only, unsigned grid, size_t smem, size_t limit, cudaStream_t stream, double2* state,
+static cudaError_t launch_tile_stage_t(bool mma_only, int form, unsigned grid, size_t smem, size_t limit, cudaStream_t stream, double2* state,
                                        const uint64_t* stage_dev, uint32_t stage_words, const double* dev_vals, uint64_t n_active,
                                        uint32_t nbuf, const CUtensorMap& tmap, uint32_t use_tma) {
   // function attributes are per device: handles on different GPUs may live in one process
@@ -584,14 +731,18 @@ static cudaError_t launch_tile_stage_t(bool mma_only, unsigned grid, size_t smem
   cudaGetDevice(&dev);
   const uint64_t dev_bit = 1ULL << (dev & 63);
   if (!(configured.load(std::memory_order_acquire) & dev_bit)) {
-    cudaError_t e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    cudaError_t e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_stage<NG, WPG, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
     if (e != cudaSuccess) return e;
     configured.fetch_or(dev_bit, std::memory_order_release);
   }
   const unsigned threads = (NG * WPG + MOVER_WARPS) * 32;
-  if (mma_only) k_tile_stage<NG, WPG, true><<<grid, threads, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active, nbuf, tmap, use_tma);
-  else k_tile_stage<NG, WPG, false><<<grid, threads, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active, nbuf, tmap, use_tma);
+#define QCB_TS_ARGS <<<grid, threads, smem, stream>>>(state, stage_dev, stage_words, dev_vals, n_active, nbuf, tmap, use_tma)
+  if (form == 1) { if (mma_only) k_tile_stage<NG, WPG, true, 1> QCB_TS_ARGS; else k_tile_stage<NG, WPG, false, 1> QCB_TS_ARGS; }
+  else { if (mma_only) k_tile_stage<NG, WPG, true, 2> QCB_TS_ARGS; else k_tile_stage<NG, WPG, false, 2> QCB_TS_ARGS; }
+#undef QCB_TS_ARGS
   return cudaGetLastError();
 }
 
@@ -600,7 +751,12 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   StageCtx sc;
   decode_stage(stage_host, sc);
   bool mma_only = sc.n_rounds > 0;
-  for (uint32_t r = 0; r < sc.n_rounds; ++r) mma_only = mma_only && round_kind(stage_host, r) == 1u;
+  int form = 2;                                          // kind of the tensor-core rounds (the same for every round of a plan)
+  for (uint32_t r = 0; r < sc.n_rounds; ++r) {
+    const uint32_t kd = round_kind(stage_host, r);
+    mma_only = mma_only && kd != 0u;
+    if (kd == 1u) form = 1;
+  }
   const uint32_t nb = sc.n_local - sc.m;
   const uint64_t tmask = (nb >= 64) ? ~0ULL : ((1ULL << nb) - 1ULL);
   // the part of the skip condition living in the rank bits is decided here, per rank
@@ -648,7 +804,7 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
     return (e[0] - '0') * 10 + atoi(e + 2);
   }();
 #define QCB_LAUNCH(NG, WPG) \
-  return launch_tile_stage_t<NG, WPG>(mma_only, (unsigned)grid, smem, limit, stream, state, stage_dev, stage_words, dev_vals, n_active, nbuf, \
+  return launch_tile_stage_t<NG, WPG>(mma_only, form, (unsigned)grid, smem, limit, stream, state, stage_dev, stage_words, dev_vals, n_active, nbuf, \
                                       *tm, use_tma)
   switch (layout) {
     case 18: QCB_LAUNCH(1, 8);

@@ -73,6 +73,8 @@ Config config_from(const qcb_config& c) {
   k.max_stage_cost = c.max_stage_cost;
   k.max_stage_rounds = c.max_stage_rounds;
   k.dense_mma = (c.dense_mma == 2) ? 0 : 1;
+  k.mma_form = (c.dense_mma == 3) ? 1 : 0;
+  if (const char* e = std::getenv("QCB_MMA_FORM")) k.mma_form = std::atoi(e) ? 1 : 0;      // experiment knob
   k.tma = (c.tile_mover == 2) ? 1 : 0;
   if (const char* e = std::getenv("QCB_THIN_DEFER")) k.thin_defer = std::atoi(e);            // experiment knob
   if (const char* e = std::getenv("QCB_WINDOW_SEARCH")) k.window_search = std::atoi(e);
@@ -254,6 +256,7 @@ struct Blocker {
 };
 
 static inline int popc(uint64_t v) { return __builtin_popcountll(v); }
+constexpr size_t K3_FRAG_DOUBLES_HOST = 192;   // tile_core.h: K3_FRAG_DOUBLES
 
 // Chunk bit (0..2) of the 128-byte shared-memory row that tile-local index bit p is XORed onto by the tile layout
 // (tile_core.h: swz; c = run bits of the stage), or -1 when the bit does not move the bank group at all.
@@ -455,13 +458,13 @@ static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& wo
     words[rb + 0] = rd.slot_pos.size();
     for (size_t j = 0; j < rd.slot_pos.size(); ++j) words[rb + 4 + j] = (uint64_t)rd.slot_pos[j];
     if (rd.dmma) {
-      words[rb + 17] = 1;
+      words[rb + 17] = rd.k3 ? 2 : 1;
       words[rb + 18] = rd.grp_pos.size();
       for (size_t j = 0; j < rd.grp_pos.size() && j < 10; ++j) words[rb + 19 + j] = (uint64_t)rd.grp_pos[j];
       words[rb + 29] = rd.cond_pos.size();
       for (size_t j = 0; j < rd.cond_pos.size(); ++j) words[rb + 30 + j] = (uint64_t)rd.cond_pos[j];
-      words[rb + 34] = (uint64_t)rd.j_load;
-      words[rb + 35] = (uint64_t)rd.j_store;
+      words[rb + 34] = rd.k3 ? ((uint64_t)rd.kmap[0] | ((uint64_t)rd.kmap[1] << 4) | ((uint64_t)rd.kmap[2] << 8)) : (uint64_t)rd.j_load;
+      words[rb + 35] = rd.k3 ? ((uint64_t)rd.mmap[0] | ((uint64_t)rd.mmap[1] << 4) | ((uint64_t)rd.mmap[2] << 8)) : (uint64_t)rd.j_store;
       continue;
     }
     std::vector<int> lanes;
@@ -778,6 +781,78 @@ static void build_dmma_round(const Config& cfg, const Stage& st, Round& rd) {
   (void)cfg;
 }
 
+// The same round in the three-product form (tile_core.h: K3Ctx): 2^k variants of three 8x8 real matrices P = Mr + Mi,
+// N = -Mi, R = Mr in mma.m8n8k4 A-fragment order.  Shared-memory accesses are 16 bytes per lane, served per quarter-warp:
+// a load quarter varies k-index bits 0, 1 (two slot bits) and group bit 0; a store quarter varies m-index bit 0 (one slot
+// bit) and group bits 1, 2 - each triple wants three distinct chunk classes of the tile layout (chunk_class).
+static void build_k3_round(const Config& cfg, const Stage& st, Round& rd) {
+  const int m = st.m;
+  uint64_t slot_mask = 0;
+  for (int p : rd.slot_pos) slot_mask |= 1ULL << p;
+  uint64_t cond = 0;
+  for (const Gate& g : rd.gates) cond |= gate_bits(g) & ~slot_mask;
+  rd.cond_pos.clear();
+  for (int p = 0; p < 64; ++p) if ((cond >> p) & 1) rd.cond_pos.push_back(p);
+  const uint64_t tile_mask = (1ULL << m) - 1ULL;
+  for (int p = m - 1; p >= 0 && rd.slot_pos.size() < 3; --p)
+    if (!((slot_mask >> p) & 1) && !((cond >> p) & 1)) { rd.slot_pos.push_back(p); slot_mask |= 1ULL << p; }
+  std::sort(rd.slot_pos.begin(), rd.slot_pos.end());
+  const int rb = st.layout_c;
+  const uint64_t busy = slot_mask | (cond & tile_mask);
+  std::vector<int> cand;
+  for (int p = 0; p < m; ++p) if (!((busy >> p) & 1)) cand.push_back(p);
+  auto distinct3 = [&](int a, int b, int d) {
+    const int ca = chunk_class(a, rb), cb = chunk_class(b, rb), cd = chunk_class(d, rb);
+    return ca >= 0 && cb >= 0 && cd >= 0 && ca != cb && cb != cd && ca != cd;
+  };
+  // search: slot left out of the load quarter (kc), slot riding on the store quarter (mx), lane bits l0 (loads), l1, l2 (stores)
+  int best = -1, bkc = 2, bmx = 0;
+  std::vector<int> lanes = {cand[0], cand[1], cand[2]};
+  const int nc = (int)cand.size();
+  for (int kc = 0; kc < 3 && best < 2; ++kc) for (int mx = 0; mx < 3 && best < 2; ++mx) {
+    const int ka = (kc + 1) % 3, kb = (kc + 2) % 3;
+    for (int i0 = 0; i0 < nc && best < 2; ++i0) for (int i1 = 0; i1 < nc && best < 2; ++i1) for (int i2 = i1 + 1; i2 < nc; ++i2) {
+      if (i0 == i1 || i0 == i2) continue;
+      const int score = (distinct3(rd.slot_pos[ka], rd.slot_pos[kb], cand[i0]) ? 1 : 0) + (distinct3(rd.slot_pos[mx], cand[i1], cand[i2]) ? 1 : 0);
+      if (score > best) { best = score; bkc = kc; bmx = mx; lanes = {cand[i0], cand[i1], cand[i2]}; }
+      if (best == 2) break;
+    }
+  }
+  {
+    int a = (bkc + 1) % 3, b = (bkc + 2) % 3;
+    if (a > b) std::swap(a, b);
+    rd.kmap[0] = a; rd.kmap[1] = b; rd.kmap[2] = bkc;
+    int r0 = (bmx + 1) % 3, r1 = (bmx + 2) % 3;
+    if (r0 > r1) std::swap(r0, r1);
+    rd.mmap[0] = bmx; rd.mmap[1] = r0; rd.mmap[2] = r1;
+  }
+  rd.grp_pos = lanes;
+  uint64_t lane_mask = 0;
+  for (int p : lanes) lane_mask |= 1ULL << p;
+  for (int p = 0; p < m; ++p) if (!(((slot_mask | lane_mask | cond) >> p) & 1)) rd.grp_pos.push_back(p);
+  for (int p = 0; p < m; ++p) if (((cond >> p) & 1) && !((slot_mask >> p) & 1)) rd.grp_pos.push_back(p);
+  const int k = (int)rd.cond_pos.size();
+  const size_t nvar = (size_t)1 << k;
+  rd.frag.assign(nvar * K3_FRAG_DOUBLES_HOST, 0.0);
+  auto pattern_of = [&](int idx, const int (&map)[3]) { return (((idx >> 0) & 1) << map[0]) | (((idx >> 1) & 1) << map[1]) | (((idx >> 2) & 1) << map[2]); };
+  for (size_t var = 0; var < nvar; ++var) {
+    uint64_t fixed = 0;
+    for (int j = 0; j < k; ++j) if ((var >> j) & 1) fixed |= 1ULL << rd.cond_pos[j];
+    cplx M[8][8];
+    for (int row = 0; row < 8; ++row) for (int col = 0; col < 8; ++col) M[row][col] = cplx{row == col ? 1.0 : 0.0, 0.0};
+    for (const Gate& g : rd.gates) small_apply_cols(g, rd.slot_pos, M, 8, fixed);
+    for (int reg = 0; reg < 6; ++reg) for (int lane = 0; lane < 32; ++lane) {
+      const int mi = lane / 4, ki = lane % 4 + 4 * (reg & 1);
+      const cplx z = M[pattern_of(mi, rd.mmap)][pattern_of(ki, rd.kmap)];
+      const double v = (reg < 2) ? (z.re + z.im) : (reg < 4 ? -z.im : z.re);
+      rd.frag[var * K3_FRAG_DOUBLES_HOST + (size_t)reg * 32 + lane] = v;
+    }
+  }
+  rd.dmma = true;
+  rd.k3 = true;
+  (void)cfg;
+}
+
 static void fuse_round(Round& rd) {
   const int r = (int)rd.slot_pos.size();
   if (r == 0 || rd.gates.size() < 2) return;
@@ -837,15 +912,17 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
       auto conds_after = [&](uint64_t Rn) { return popc((touched | g.bits) & ~Rn); };
       if (g.can_be_pure && fits(R | g.want) && conds_after(R | g.want) <= MAX_COND_BITS) { accept(R | g.want); continue; }
       // a diagonal gate that does not fit as pure now: defer it to a later round of this stage if one of its
-      // bits will be a slot there anyway (a later gate targets it); otherwise let it ride along as condition bits
-      if (g.can_be_pure && g.t == 0 && g.later) { block(); continue; }
+      // bits will be a slot there anyway (a later gate targets it) - but only a gate that CAN ever be pure (at most rmax
+      // tile-local bits; a wider one would be deferred for ever and block everything behind it); otherwise let it ride
+      // along as condition bits
+      if (g.can_be_pure && g.t == 0 && g.later && popc(g.want) <= rmax) { block(); continue; }
       if (fits(R | g.t) && conds_after(R | g.t) <= MAX_COND_BITS) accept(R | g.t);
       else if (taken.empty() && Rcap == ~0ULL) accept(R | g.t);     // always make progress (falls back to the interpreter if needed)
       else block();
       continue;
     }
     if (g.can_be_pure && fits(R | g.want)) { accept(R | g.want); continue; }
-    if (g.can_be_pure && g.t == 0 && g.later) { block(); continue; }
+    if (g.can_be_pure && g.t == 0 && g.later && popc(g.want) <= rmax) { block(); continue; }
     if (fits(R | g.t)) accept(R | g.t);
     else block();
   }
@@ -886,6 +963,7 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
         if (ctaken.size() > taken.size()) { taken.swap(ctaken); rest.swap(crest); R = cR; }
       }
     }
+    if (taken.empty()) break;                              // nothing fits a round of this stage: leave the rest pending
     // a thin round costs as much as a full one: leave its gates to the next sweep, whose tile search starts afresh
     if (search && cfg.round_yield_pct > 0 && st.rounds.size() >= 2 && !st.absorbed.empty() &&
         taken.size() * 100 * st.rounds.size() < (size_t)cfg.round_yield_pct * st.absorbed.size()) break;
@@ -898,7 +976,7 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
     // unfused mode keeps exactly one gate per round anyway (one gate per stage)
     for (int b = 0; b < st.m; ++b) if ((R >> b) & 1) rd.slot_pos.push_back(b);
     if (materialize) {
-      if (dmma_eligible(cfg, st, rd)) build_dmma_round(cfg, st, rd);
+      if (dmma_eligible(cfg, st, rd)) { if (cfg.mma_form == 0) build_k3_round(cfg, st, rd); else build_dmma_round(cfg, st, rd); }
       else if (cfg.fusion) fuse_round(rd);
     }
     st.rounds.push_back(std::move(rd));
@@ -917,7 +995,7 @@ static void replay_rounds(const Config& cfg, Stage& st, const std::vector<Gate>&
       st.absorbed.push_back(u);
     }
     for (int b = 0; b < st.m; ++b) if ((rd.slot_mask >> b) & 1) rd.slot_pos.push_back(b);
-    if (dmma_eligible(cfg, st, rd)) build_dmma_round(cfg, st, rd);
+    if (dmma_eligible(cfg, st, rd)) { if (cfg.mma_form == 0) build_k3_round(cfg, st, rd); else build_dmma_round(cfg, st, rd); }
     else if (cfg.fusion) fuse_round(rd);
     st.rounds.push_back(std::move(rd));
   }
@@ -927,7 +1005,7 @@ void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const
   key.clear();
   key.reserve(16 + perm_in.size() + 6 * gates.size());
   const int c[] = {cfg.n_total, cfg.n_local, cfg.rank, cfg.world, cfg.tile_bits, cfg.low_bits, cfg.fusion, cfg.max_stage_cost,
-                   cfg.max_stage_rounds, cfg.dense_mma, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer};
+                   cfg.max_stage_rounds, cfg.dense_mma + 16 * cfg.mma_form, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer};
   for (int v : c) key.push_back((uint64_t)(int64_t)v);
   key.push_back(perm_in.size());
   for (int v : perm_in) key.push_back((uint64_t)v);

@@ -72,9 +72,10 @@ enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_
 //     [0] r  [1] n_op_slots  [2] op word offset (from stage start)  [3] n_lane
 //     [4..7)  slot_pos[3] (tile-local, ascending)   [7..10) lane_pos[3]
 //     [10] n_ins  [11..17) ins_pos[6] ascending (slot ∪ lane positions)
-//     [17] kind (0 = interpreter round, 1 = tensor-core round)   [18] n_grp_bits   [19..29) grp_pos[10]
-//     [29] k (condition bits)  [30..34) cond_pos[4] (ext positions)  [34] j_load  [35] j_store
-//     tensor-core rounds: [2] = word offset of the A-fragment matrices (2^k * 256 doubles, after all descriptors)
+//     [17] kind (0 = interpreter round, 1 = tensor-core round as a 16x16 real block, 2 = tensor-core round in the
+//          three-product form, tile_core.h: K3Ctx)   [18] n_grp_bits   [19..29) grp_pos[10]
+//     [29] k (condition bits)  [30..34) cond_pos[4] (ext positions)  [34] j_load (kind 2: kmap)  [35] j_store (kind 2: mmap)
+//     tensor-core rounds: [2] = word offset of the A-fragment matrices (2^k * 256 / 192 doubles, after all descriptors)
 //   StageDesc [42] = number of leading words (descriptors + interpreter op slots) that the kernel copies to smem
 constexpr int STAGE_WORDS = 48;
 constexpr int ROUND_WORDS = 40;
@@ -97,7 +98,10 @@ struct Round {
   std::vector<int> cond_pos;        // ext positions of the condition bits (variant index bit j <-> cond_pos[j])
   std::vector<int> grp_pos;         // tile-local position of group-index bit i (first 3 = lane bits)
   int j_load = 0, j_store = 0;      // slot index paired with k bit 1 (loads) / m bit 1 (stores): bank-conflict control
-  std::vector<double> frag;         // 2^k * 256 doubles in mma.m16n8k16 A-fragment order [variant][reg][lane]
+  bool k3 = false;                  // round kind 2 (tile_core.h: K3Ctx): three 8x8 real matrices, six m8n8k4 steps per batch
+  int kmap[3] = {0, 1, 2}, mmap[3] = {0, 1, 2};   // k3: slot index carried by bit b of the k-index (loads) / m-index (stores)
+  std::vector<double> frag;         // kind 1: 2^k * 256 doubles in mma.m16n8k16 A-fragment order [variant][reg][lane];
+                                    // kind 2: 2^k * 192 doubles [variant][P0 P1 N0 N1 R0 R1][lane]
   std::vector<int> uids;            // Gate::uid of the gates the scheduler put into this round, in order (plan traces)
   uint64_t slot_mask = 0;           // the slot bits the scheduler chose (before a tensor-core round pads them to 3)
 };
@@ -130,6 +134,8 @@ struct Config {
   int max_stage_cost = 0;
   int max_stage_rounds = 0;
   int dense_mma = 1;           // rounds as dense 8x8 complex blocks on the fp64 tensor cores
+  int mma_form = 0;            // 0 = three-product form (six m8n8k4 steps per batch, 16-byte shared accesses);
+                               // 1 = 16x16 real block (m16n8k16 = eight steps, 8-byte accesses), the round-1 kernel
   int round_yield_pct = 50;    // end a stage early when the next round would absorb less than this % of the stage's average round
   int window_search = 1;       // stage builder also tries contiguous tile windows and keeps the best yield
   int thin_defer = 0;          // multi-GPU: a stage with fewer gates than this is not run while gates wait for an exchange

@@ -419,6 +419,82 @@ QCB_HD uint32_t dmma_variant_hi(const DmmaCtx& c, uint64_t ext_hi, uint32_t m) {
   return v;
 }
 
+// ---- "k3" tensor-core rounds (round kind 2): the dense 8x8 complex block M = Mr + i Mi of a round applied with Gauss's
+// three real products instead of four.  With the amplitudes of a group as B = Br + i Bi:
+//     K  = (Mr + Mi) Br            Re = K - Mi (Br + Bi)            Im = K + Mr (Bi - Br)
+// i.e. three 8x8 real matrices P = Mr + Mi, N = -Mi, R = Mr (built by the host) and six m8n8k4 steps per 8 groups instead of
+// the eight of the 16x16 real form; K is the C operand of both remaining products, so no extra additions on the result side.
+// Fragment roles (PTX ISA mma.m8n8k4 .f64): A reg: row lane/4, col lane%4 (+4 per k-step); B reg: row lane%4 (+4 per k-step),
+// col lane/4; C/D regs {0,1}: row lane/4, cols 2(lane%4) + {0,1}.  A lane therefore loads the COMPLEX amplitudes
+// (pattern k = lane%4 + 4s, group lane/4), s = 0, 1, with two 16-byte loads and stores the complex results (pattern lane/4,
+// groups 2(lane%4) + {0,1}) with two 16-byte stores.
+// Round words [34] / [35] hold the slot roles: kmap = slot index carried by k-index bit 0 | bit 1 << 4 | bit 2 << 8 (columns of
+// the matrices = input patterns), mmap likewise for the m-index (rows = output patterns).
+struct K3Ctx {
+  uint32_t n_grp, k, c;
+  uint32_t slot_pos[3], grp_pos[10], cond_pos[4];
+  uint32_t kmap[3], mmap[3];
+  uint64_t mat_off;
+};
+constexpr uint32_t K3_FRAG_DOUBLES = 192;   // per variant: 6 A registers x 32 lanes (P0 P1 N0 N1 R0 R1)
+
+QCB_HD void decode_k3(const uint64_t* stage, uint32_t round_idx, K3Ctx& c) {
+  const uint64_t* w = stage + T_STAGE_WORDS + (uint64_t)round_idx * T_ROUND_WORDS;
+  c.c = (uint32_t)stage[43];
+  c.mat_off = w[2]; c.n_grp = (uint32_t)w[18]; c.k = (uint32_t)w[29];
+  for (int j = 0; j < 3; ++j) {
+    c.slot_pos[j] = (uint32_t)w[4 + j];
+    c.kmap[j] = (uint32_t)(w[34] >> (4 * j)) & 15u;
+    c.mmap[j] = (uint32_t)(w[35] >> (4 * j)) & 15u;
+  }
+  for (int j = 0; j < 10; ++j) c.grp_pos[j] = (uint32_t)w[19 + j];
+  for (int j = 0; j < 4; ++j) c.cond_pos[j] = (uint32_t)w[30 + j];
+}
+// tile-local offset of the slot pattern selected by a k-index / m-index
+QCB_HD uint32_t k3_pattern_offset(const K3Ctx& c, uint32_t idx, const uint32_t (&map)[3]) {
+  uint32_t o = 0;
+#pragma unroll
+  for (uint32_t b = 0; b < 3; ++b) {
+    const uint32_t j = map[b];
+    const uint32_t pos = (j == 0) ? c.slot_pos[0] : (j == 1 ? c.slot_pos[1] : c.slot_pos[2]);
+    o |= ((idx >> b) & 1u) << pos;
+  }
+  return o;
+}
+QCB_HD uint32_t k3_group_offset(const K3Ctx& c, uint32_t n) {
+  return ((n & 1u) << c.grp_pos[0]) | (((n >> 1) & 1u) << c.grp_pos[1]) | (((n >> 2) & 1u) << c.grp_pos[2]);
+}
+// lane entry: byte offsets inside the tile buffer of the two loads (k-steps 0, 1) and the two stores (result columns 0, 1)
+QCB_HD void k3_lane_entry(const K3Ctx& c, uint32_t lane, uint32_t (&e)[4]) {
+  const uint32_t g = lane >> 2, q = lane & 3u;
+#pragma unroll
+  for (uint32_t s = 0; s < 2; ++s) e[s] = swz(k3_group_offset(c, g) | k3_pattern_offset(c, q + 4u * s, c.kmap), c.c) << 4;
+#pragma unroll
+  for (uint32_t i = 0; i < 2; ++i) e[2 + i] = swz(k3_group_offset(c, 2u * q + i) | k3_pattern_offset(c, g, c.mmap), c.c) << 4;
+}
+QCB_HD uint32_t k3_batch_base(const K3Ctx& c, uint32_t batch) {
+  uint32_t o = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 7; ++i) if (i + 3u < c.n_grp) o |= ((batch >> i) & 1u) << c.grp_pos[i + 3];
+  return o;
+}
+// batch entry: swizzled byte offset of the batch base (low 20 bits) | variant bits of tile-local condition bits << 20
+QCB_HD uint32_t k3_batch_entry(const K3Ctx& c, uint32_t batch, uint32_t m) {
+  const uint32_t base = k3_batch_base(c, batch);
+  uint32_t v = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j)
+    if (j < c.k && c.cond_pos[j] < m) v |= ((base >> c.cond_pos[j]) & 1u) << j;
+  return (swz(base, c.c) << 4) | (v << 20);
+}
+QCB_HD uint32_t k3_variant_hi(const K3Ctx& c, uint64_t ext_hi, uint32_t m) {
+  uint32_t v = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j)
+    if (j < c.k && c.cond_pos[j] >= m) v |= (uint32_t)((ext_hi >> (c.cond_pos[j] - m)) & 1ULL) << j;
+  return v;
+}
+
 // ---- tile addressing
 struct StageCtx {
   uint32_t n_local, m, L, n_rounds, n_runs, c;

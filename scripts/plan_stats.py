@@ -33,7 +33,7 @@ for s in range(ns):
     mb = 0
     for r in range(nr):
         rd = st[48 + 40 * r: 48 + 40 * (r + 1)]
-        if int(rd[17]) == 1:
+        if int(rd[17]) in (1, 2):
             k = int(rd[29]); kc[k] += 1; mb += (1 << k) * 2048
         else:
             interp += 1
@@ -54,7 +54,7 @@ for s in range(ns):
     nr = int(st[3]); total = int(st[40]); m = int(st[1])
     for r in range(nr):
         rd = st[48 + 40 * r: 48 + 40 * (r + 1)]
-        if int(rd[17]) == 1:
+        if int(rd[17]) in (1, 2):
             k = int(rd[29])
             kl = sum(1 for j in range(k) if int(rd[30 + j]) < m)
             kl_hist[(kl, k - kl)] += 1

@@ -81,6 +81,21 @@ int emu_stage_max_conflict(Emu* e, uint64_t si, int nthreads) {
   StageCtx sc; decode_stage(st, sc);
   int worst = 1;
   for (uint32_t r = 0; r < sc.n_rounds; ++r) {
+    if (round_kind(st, r) == 2u) {
+      // 16-byte accesses are served per quarter-warp (8 lanes x 16 B = 128 B): count lanes per 16-byte bank group
+      K3Ctx c; decode_k3(st, r, c);
+      for (int quarter = 0; quarter < 4; ++quarter)
+        for (int which = 0; which < 4; ++which) {
+          int cnt[8] = {0};
+          for (uint32_t l = 0; l < 8; ++l) {
+            uint32_t e[4];
+            k3_lane_entry(c, quarter * 8 + l, e);
+            cnt[(e[which] >> 4) & 7]++;
+          }
+          for (int b = 0; b < 8; ++b) if (cnt[b] > worst) worst = cnt[b];
+        }
+      continue;
+    }
     if (round_kind(st, r) == 1u) {
       // 8-byte accesses are served per half-warp (16 lanes x 8 B = 128 B): count lanes per 8-byte bank pair
       DmmaCtx c; decode_dmma(st, r, c);
@@ -152,6 +167,52 @@ static void emu_dmma_round(double2* tile, const uint64_t* st, uint32_t r, uint64
   }
 }
 
+// Software model of the three-product round (tile_core.h: K3Ctx; kernels.cu: k3_round_run), warp by warp, with the
+// mma.m8n8k4 .f64 fragment layouts: K = P Br, Re = K + N (Br + Bi), Im = K + R (Bi - Br).
+static void emu_k3_round(double2* tile, const uint64_t* st, uint32_t r, uint64_t ext_hi, uint32_t m, int nthreads) {
+  K3Ctx c; decode_k3(st, r, c);
+  const uint32_t NW = nthreads / 32;
+  const uint32_t nbatch = 1u << (c.n_grp - 3u);
+  const uint32_t per = nbatch >= NW ? nbatch / NW : 1u;
+  unsigned char* tb = reinterpret_cast<unsigned char*>(tile);
+  const double* mats = reinterpret_cast<const double*>(st + c.mat_off);
+  uint32_t lt[32][4];
+  for (uint32_t lane = 0; lane < 32; ++lane) k3_lane_entry(c, lane, lt[lane]);
+  const uint32_t var_hi = k3_variant_hi(c, ext_hi, m);
+  for (uint32_t warp = 0; warp < NW; ++warp) {
+    for (uint32_t b = 0; b < per; ++b) {
+      const uint32_t bidx = warp * per + b;
+      if (bidx >= nbatch) break;
+      const uint32_t e = k3_batch_entry(c, bidx, m);
+      const uint32_t X = e & DMMA_BATCH_OFF_MASK, var = var_hi | (e >> 20);
+      double Pm[8][8], Nm[8][8], Rm[8][8], Br[8][8], Bi[8][8];
+      for (uint32_t lane = 0; lane < 32; ++lane) {
+        for (int s = 0; s < 2; ++s) {
+          const int row = lane / 4, col = lane % 4 + 4 * s;
+          Pm[row][col] = mats[(size_t)var * K3_FRAG_DOUBLES + (0 + s) * 32 + lane];
+          Nm[row][col] = mats[(size_t)var * K3_FRAG_DOUBLES + (2 + s) * 32 + lane];
+          Rm[row][col] = mats[(size_t)var * K3_FRAG_DOUBLES + (4 + s) * 32 + lane];
+          double2 a; std::memcpy(&a, tb + (X ^ lt[lane][s]), 16);
+          Br[lane % 4 + 4 * s][lane / 4] = a.x; Bi[lane % 4 + 4 * s][lane / 4] = a.y;
+        }
+      }
+      double Re[8][8], Im[8][8];
+      for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) {
+        double k = 0, re = 0, im = 0;
+        for (int t = 0; t < 8; ++t) k += Pm[i][t] * Br[t][j];
+        re = k; im = k;
+        for (int t = 0; t < 8; ++t) { re += Nm[i][t] * (Br[t][j] + Bi[t][j]); im += Rm[i][t] * (Bi[t][j] - Br[t][j]); }
+        Re[i][j] = re; Im[i][j] = im;
+      }
+      for (uint32_t lane = 0; lane < 32; ++lane)
+        for (int i = 0; i < 2; ++i) {
+          const double2 o{Re[lane / 4][2 * (lane % 4) + i], Im[lane / 4][2 * (lane % 4) + i]};
+          std::memcpy(tb + (X ^ lt[lane][2 + i]), &o, 16);
+        }
+    }
+  }
+}
+
 // Run one S_TILE stage on this rank's local slice.
 int emu_run_tile_stage(Emu* e, uint64_t si, double* state, const double* dev_vals, int nthreads) {
   const Stage& S = e->plan.stages[si];
@@ -174,6 +235,7 @@ int emu_run_tile_stage(Emu* e, uint64_t si, double* state, const double* dev_val
       tile[swz(i, sc.c)] = gs[base + hi_offset(st, sc, i >> sc.L) + (i & ((1u << sc.L) - 1u))];
     for (uint32_t r = 0; r < sc.n_rounds; ++r) {
       if (round_kind(st, r) == 1u) { emu_dmma_round(tile.data(), st, r, ext_hi, sc.m, nthreads); continue; }
+      if (round_kind(st, r) == 2u) { emu_k3_round(tile.data(), st, r, ext_hi, sc.m, nthreads); continue; }
       RoundCtx rc; decode_round(st, r, rc);
       for (uint32_t tid = 0; tid < (uint32_t)nthreads; ++tid) {
         switch (rc.r) {

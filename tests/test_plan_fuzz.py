@@ -59,12 +59,19 @@ def random_circuit(n, rng, length, grover=False):
 
 
 def _reference(circ, init):
-    """Oracle semantics + the two operator-level ops the oracle does not know."""
+    """Oracle semantics + the operator-level ops the oracle does not know."""
     st = init.copy()
+    n = int(math.log2(st.shape[0]))
+    idx = np.arange(st.shape[0])
     for op in circ["operations"]:
         t = op["operation-type"]
         if t == "phase-oracle":
             st[op["operation-params"]["index"]] *= -1
+        elif t == "mcphase":
+            sel = np.ones(st.shape[0], dtype=bool)
+            for q in op["operation-params"]["qubit-indices"]:
+                sel &= ((idx >> (n - 1 - q)) & 1) == 1
+            st = np.where(sel, st * np.exp(1j * op["operation-params"]["angle"]), st)
         elif t == "grover-diffusion":
             st = 2 * np.mean(st) - st
         else:
@@ -93,6 +100,57 @@ def test_random_circuits_random_geometry_emulated_ranks(block):
         got = E.run_world(n, circ["operations"], init, world=world, tile_bits=tile, low_bits=low, dense_mma=mma)
         err = float(np.max(np.abs(got - _reference(circ, init))))
         assert err <= TOL, f"seed {seed}: n={n} world={world} tile={tile} low={low} err={err}"
+
+
+def test_wide_diagonal_gate_followed_by_gates_on_its_bits():
+    """A diagonal gate on more than MAX_SLOT_BITS tile-local bits (phase oracle, multi-controlled phase) followed by a gate
+    that targets one of its bits used to be deferred for ever ("scheduler made no progress")."""
+    for n in range(4, 13):
+        circ = C.create_circuit(n)
+        C.add_gate(circ, "phase-oracle", index=(1 << n) - 2)
+        C.h(circ, n - 1)
+        st = E.run_world(n, circ["operations"])
+        init = np.zeros(1 << n, dtype=complex); init[0] = 1
+        assert np.max(np.abs(st - _reference(circ, init))) <= TOL
+    # textbook Grover iteration with explicit gates: H^n, oracle, H^n X^n, multi-controlled Z, X^n H^n
+    for n, world in ((5, 1), (9, 1), (11, 2), (12, 4)):
+        circ = C.create_circuit(n)
+        for q in range(n): C.h(circ, q)
+        for _it in range(2):
+            C.add_gate(circ, "phase-oracle", index=5)
+            for q in range(n): C.h(circ, q)
+            for q in range(n): C.x(circ, q)
+            C.add_gate(circ, "mcphase", qubit_indices=list(range(n)), angle=math.pi)
+            for q in range(n): C.x(circ, q)
+            for q in range(n): C.h(circ, q)
+        init = np.zeros(1 << n, dtype=complex); init[0] = 1
+        st = E.run_world(n, circ["operations"], world=world)
+        assert np.max(np.abs(st - _reference(circ, init))) <= TOL
+    # random: wide mcphase / oracles sprinkled between ordinary gates, random geometry
+    for seed in range(60):
+        rng = np.random.default_rng(7000 + seed)
+        n = int(rng.integers(5, 12))
+        world = int(rng.choice([1, 1, 2, 4]))
+        circ = C.create_circuit(n)
+        for _ in range(int(rng.integers(6, 30))):
+            r = rng.random()
+            if r < 0.25:
+                k = int(rng.integers(4, n + 1))
+                C.add_gate(circ, "mcphase", qubit_indices=[int(x) for x in rng.permutation(n)[:k]], angle=float(rng.uniform(0, 6.28)))
+            elif r < 0.4:
+                C.add_gate(circ, "phase-oracle", index=int(rng.integers(0, 1 << n)))
+            elif r < 0.7:
+                C.add_gate(circ, ["h", "x", "t"][rng.integers(0, 3)], target=int(rng.integers(0, n)))
+            else:
+                a, b = [int(x) for x in rng.permutation(n)[:2]]
+                C.cnot(circ, a, b)
+        init = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+        init /= np.linalg.norm(init)
+        nl = n - (world.bit_length() - 1)
+        tile = int(rng.integers(min(4, nl), min(nl, 9) + 1))
+        got = E.run_world(n, circ["operations"], init, world=world, tile_bits=tile)
+        err = float(np.max(np.abs(got - _reference(circ, init))))
+        assert err <= TOL, f"seed {seed}: n={n} world={world} tile={tile} err={err}"
 
 
 def test_degenerate_tile_geometry_is_sanitised():
