@@ -16,6 +16,9 @@
  *   - qubit indices use the REFERENCE's numbering: qubit 0 is the MOST significant bit of the
  *     amplitude index (domain/state.clj:114-162); the library translates to bit positions inside.
  *   - a handle is used by one thread at a time; different handles are independent (own stream).
+ *   - multi-GPU: either one handle per process and rank (qcb_config.rank / world_size / nccl_unique_id, SPMD under
+ *     torchrun; buffers then address the rank's slice), or ONE handle for all devices of the process (qcb_config.n_gpus;
+ *     buffers address the whole state).
  *   - there is NO CPU fallback: qcb_create fails with QCB_ERR_CUDA when no CUDA device is usable.
  */
 #ifndef QCB200_H
@@ -28,7 +31,7 @@
 extern "C" {
 #endif
 
-#define QCB_ABI_VERSION 1
+#define QCB_ABI_VERSION 2
 
 /* ---- status codes ---- */
 #define QCB_OK              0
@@ -59,11 +62,20 @@ typedef struct qcb_config {
   int32_t max_stage_cost;  /* 0 = default; scheduler knob: cost units one fused sweep may absorb       */
   int32_t max_stage_rounds;/* 0 = default; scheduler knob: shared-memory rounds one fused sweep may hold */
   int32_t dense_mma;       /* 0 = default (on); 1 = on: rounds run as dense 8x8 complex blocks on the fp64 tensor
-                              cores (DMMA); 2 = off: register-resident op interpreter only                 */
+                              cores (DMMA) in the three-product form (six DMMA.8x8x4 per 8 groups); 2 = off: register-
+                              resident op interpreter only; 3 = on, 16x16 real form (eight DMMA.8x8x4 per 8 groups)     */
   int32_t tile_mover;      /* 0 = default; 1 = tiles move between HBM and shared memory with cp.async / st.global
                               (16 bytes per thread, arbitrary swizzle: conflict-free rounds); 2 = TMA tensor copies,
                               one per contiguous run, with the hardware 128-byte swizzle                            */
-  int32_t reserved[4];
+  /* ---- single-process multi-GPU (ABI 2): ONE handle owns the whole sharded state.  n_gpus = 2, 4 or 8 (world_size must
+     then be 0 or 1): the state's top log2(n_gpus) qubits select the device, the library runs one host thread per device
+     and its own NCCL communicator / peer mappings inside, and every entry point below works on the WHOLE state (offsets and
+     counts are global, results are returned once).  This is the mode a JVM host uses (one `submit-circuit` caller, one job
+     id: application/backend.clj:72-112).  n_gpus = 0 or 1: one device (or, with world_size > 1, one SPMD rank per process as
+     launched by torchrun). */
+  int32_t n_gpus;
+  int32_t device_ids[8];   /* CUDA ordinals of the n_gpus devices, in slice order; all -1 (or n_gpus entries of -1) = 0 .. n_gpus-1 */
+  int32_t reserved[3];
 } qcb_config;
 
 /* ---- gate vocabulary: every branch of apply-gate-to-state (domain/circuit.clj:964-1071) ---- */
@@ -128,7 +140,8 @@ int32_t qcb_set_state(qcb_handle h, const double* host_amps, uint64_t count);
 int32_t qcb_get_state(qcb_handle h, uint64_t offset, uint64_t count, double* out_amps);
 int32_t qcb_get_amplitudes(qcb_handle h, const uint64_t* indices, uint64_t n, double* out_amps); /* result.clj:393-402 */
 int32_t qcb_normalize(qcb_handle h);                 /* normalize-state, domain/state.clj:544-551 */
-/* raw device pointer of the local slice (for zero-copy plumbing: torch views, peer access) */
+/* raw device pointer of the local slice (for zero-copy plumbing: torch views, peer access); a multi-GPU handle (n_gpus > 1)
+   returns the slice of device `device_ids[0]` */
 int32_t qcb_state_dev_ptr(qcb_handle h, void** dev_ptr, uint64_t* local_count);
 
 /* ---- gates: replaces (reduce apply-operation-to-state state ops), domain/circuit.clj:1782 ---- */
@@ -182,6 +195,10 @@ typedef struct qcb_noise_table {
  * trajectories_out (may be NULL): first min(n_shots, max_traj) final states, 2^n complex each.
  * The handle's state holds the last shot's final state afterwards (:final-state).
  */
+/* :initial-state of the trajectory loop ((or (:initial-state options) zero-state), hardware_simulator.clj:128-131): every
+   trajectory of the following qcb_run_noisy calls starts from these amplitudes (2^n complex, kept on the device) instead
+   of |0...0>; host_amps == NULL restores |0...0>. */
+int32_t qcb_noisy_set_initial_state(qcb_handle h, const double* host_amps, uint64_t count);
 int32_t qcb_noisy_draws_per_shot(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb_noise_table* noise,
                                  uint64_t* out_draws);
 int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb_noise_table* noise,
@@ -252,6 +269,10 @@ int32_t qcb_submit(qcb_handle h, const qcb_job_request* req, uint64_t* out_job_i
 int32_t qcb_job_status(qcb_handle h, uint64_t job_id, int32_t* out_status);
 int32_t qcb_job_result_get(qcb_handle h, uint64_t job_id, qcb_job_result* inout);
 int32_t qcb_cancel(qcb_handle h, uint64_t job_id, int32_t* out_status);
+/* Drops a finished job and everything it holds (outcomes, probabilities, final state); later queries answer
+   QCB_JOB_NOT_FOUND.  Without it the library keeps the payload of the 64 most recently finished jobs only (older ones keep
+   their status and timing, their buffers are freed) - a VQE / QAOA loop through the job API does not grow the host heap. */
+int32_t qcb_job_release(qcb_handle h, uint64_t job_id);
 int32_t qcb_queue_status(qcb_handle h, uint64_t* queued, uint64_t* running, uint64_t* completed);
 
 /* ---- P2: small dense complex linear algebra (domain/math/protocols.clj MatrixAlgebra subset used on the

@@ -72,6 +72,7 @@ _PROTOS = {
     "qcb_expect_1q": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, _P(C.c_double)]),
     "qcb_fidelity": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, _P(C.c_double)]),
     "qcb_apply_kraus_1q": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "qcb_noisy_set_initial_state": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "qcb_noisy_draws_per_shot": (C.c_int32, [C.c_void_p, _P(OPS.QcbOp), C.c_uint64, _P(OPS.QcbNoiseTable), _P(C.c_uint64)]),
     "qcb_run_noisy": (C.c_int32, [C.c_void_p, _P(OPS.QcbOp), C.c_uint64, _P(OPS.QcbNoiseTable), C.c_void_p, C.c_uint64,
                                   C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -87,6 +88,7 @@ _PROTOS = {
     "qcb_job_status": (C.c_int32, [C.c_void_p, C.c_uint64, _P(C.c_int32)]),
     "qcb_job_result_get": (C.c_int32, [C.c_void_p, C.c_uint64, _P(OPS.QcbJobResult)]),
     "qcb_cancel": (C.c_int32, [C.c_void_p, C.c_uint64, _P(C.c_int32)]),
+    "qcb_job_release": (C.c_int32, [C.c_void_p, C.c_uint64]),
     "qcb_queue_status": (C.c_int32, [C.c_void_p, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint64)]),
     "qcb_la_matvec": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "qcb_la_matmul": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
@@ -163,13 +165,16 @@ def _c128(a) -> np.ndarray:
 
 
 class StateVector:
-    """One n-qubit fp64 complex state vector resident in HBM (one rank's slice when world_size > 1).
+    """One n-qubit fp64 complex state vector resident in HBM: on one GPU, as one rank's slice of an SPMD job
+    (world_size > 1, one process per GPU), or - n_gpus > 1 - the WHOLE state sharded over the GPUs of this process behind
+    one handle (offsets, counts and results are then global).
 
     Thin 1:1 wrapper over the C ABI; qubit numbering is the reference's (qubit 0 = MSB)."""
 
     def __init__(self, n_qubits: int, *, device: int = -1, fusion: int = 1, strict_parity: int = 1, tile_bits: int = 0,
                  low_bits: int = 0, rank: int = 0, world_size: int = 1, nccl_id: Optional[bytes] = None, max_stage_cost: int = 0,
-                 max_stage_rounds: int = 0, dense_mma: int = 0, tile_mover: int = 0):
+                 max_stage_rounds: int = 0, dense_mma: int = 0, tile_mover: int = 0, n_gpus: int = 0,
+                 device_ids: Optional[Sequence[int]] = None):
         self._lib = load()
         if dense_mma == 0 and os.environ.get("QCB_DENSE_MMA"):
             dense_mma = int(os.environ["QCB_DENSE_MMA"])     # 1 = tensor-core rounds (default), 2 = interpreter only
@@ -182,14 +187,15 @@ class StateVector:
                               low_bits=low_bits, rank=rank, world_size=world_size,
                               nccl_unique_id=C.cast(self._idbuf, C.c_void_p) if self._idbuf is not None else None,
                               max_stage_cost=max_stage_cost, max_stage_rounds=max_stage_rounds, dense_mma=dense_mma,
-                              tile_mover=tile_mover)
+                              tile_mover=tile_mover, n_gpus=n_gpus, device_ids=device_ids)
+        self.n_gpus = n_gpus
         h = C.c_void_p()
         rc = self._lib.qcb_create(C.byref(cfg), C.byref(h))
         if rc != QCB_OK:
             raise QcbError(rc, last_error(None))
         self._h = h
         p = world_size.bit_length() - 1
-        self.local_count = 1 << (self.n - p)
+        self.local_count = 1 << (self.n - p)      # amplitudes this handle addresses (a multi-GPU handle: all of them)
 
     # -- lifecycle
     def close(self):
@@ -327,6 +333,14 @@ class StateVector:
         out = C.c_uint64()
         self._ck(self._lib.qcb_noisy_draws_per_shot(self._h, arr, cnt, C.byref(noise_table) if noise_table is not None else None, C.byref(out)))
         return int(out.value)
+
+    def noisy_set_initial_state(self, amps=None):
+        """Initial state of the trajectories of the following run_noisy calls (None = |0...0>)."""
+        if amps is None:
+            self._ck(self._lib.qcb_noisy_set_initial_state(self._h, None, 0))
+        else:
+            a = _c128(amps)
+            self._ck(self._lib.qcb_noisy_set_initial_state(self._h, a.ctypes.data, a.shape[0]))
 
     def run_noisy(self, ops_enc, noise_table, uniforms: np.ndarray, max_trajectories: int = 0):
         arr, cnt, _ = ops_enc

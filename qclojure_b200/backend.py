@@ -81,21 +81,57 @@ def circuit_metadata(circuit: dict) -> dict:
     return {"circuit-depth": max(layers) if ops else 0, "circuit-operation-count": len(ops), "circuit-gate-count": gates}
 
 
+class StaleStateHandle(RuntimeError):
+    """The device state behind a DeviceStateHandle has been reused by a later job (or released)."""
+
+
 class DeviceStateHandle:
-    """Lazy view of a final state that is too large to materialise as a host vector."""
+    """Lazy view of a final state that is too large to materialise as a host vector.  The view is valid until the backend
+    runs its next job on the same state vector (HBM holds one such state); afterwards every access raises
+    `StaleStateHandle` instead of silently returning the later job's amplitudes."""
 
     def __init__(self, sv: L.StateVector):
         self._sv = sv
         self.num_qubits = sv.n
+        self._generation = getattr(sv, "generation", 0)
+
+    def _live(self) -> L.StateVector:
+        if getattr(self._sv, "_h", None) is None or getattr(self._sv, "generation", 0) != self._generation:
+            raise StaleStateHandle("the device state of this result has been reused by a later job; results of jobs above "
+                                   "max-state-qubits must be read before the next job runs")
+        return self._sv
 
     def slice(self, offset: int, count: int) -> np.ndarray:
-        return self._sv.get_state(offset, count)
+        return self._live().get_state(offset, count)
 
     def amplitudes(self, indices) -> np.ndarray:
-        return self._sv.get_amplitudes(indices)
+        return self._live().get_amplitudes(indices)
 
     def probabilities(self, offset: int, count: int) -> np.ndarray:
-        return self._sv.probabilities(offset, count)
+        return self._live().probabilities(offset, count)
+
+
+class _DrawSource:
+    """One stream of uniform draws per job: consecutive, non-overlapping slices of `options["uniforms"]`, or one generator
+    seeded from `options["seed"]` (else the backend's), so that mid-circuit :measure draws, the shot draws, :sample draws and
+    the noisy trajectory matrix never reuse the same numbers inside a job."""
+
+    def __init__(self, options, fallback_rng):
+        u = _opt(options, "uniforms")
+        self._u = None if u is None else np.asarray(u, dtype=np.float64).reshape(-1)
+        self._pos = 0
+        seed = _opt(options, "seed")
+        self._rng = np.random.default_rng(seed) if seed is not None else fallback_rng
+
+    def take(self, shape):
+        cnt = int(np.prod(shape))
+        if self._u is not None:
+            if self._pos + cnt > self._u.size:
+                raise ValueError(f"not enough uniforms supplied: {self._u.size} given, {self._pos + cnt} needed so far")
+            out = self._u[self._pos:self._pos + cnt].reshape(shape)
+            self._pos += cnt
+            return out
+        return self._rng.random(shape)
 
 
 class _BackendBase:
@@ -111,14 +147,22 @@ class _BackendBase:
 
     # -- handles are cached per qubit count (one state vector resident in HBM each)
     def _sv(self, n: int) -> L.StateVector:
+        """The state vector a job runs on.  config "n-gpus" (2, 4, 8; optional "device-ids") shards states of more than
+        "multi-gpu-min-qubits" (default 31) qubits over the GPUs of this process behind ONE handle."""
         sv = self._svs.get(n)
         if sv is None:
             for old in list(self._svs):            # keep HBM for the one in use
                 self._svs.pop(old).close()
+            n_gpus = int(_opt(self.config, "n-gpus", 0) or 0)
+            if n_gpus > 1 and n < int(_opt(self.config, "multi-gpu-min-qubits", 31)):
+                n_gpus = 0
             sv = L.StateVector(n, device=int(_opt(self.config, "device", -1)),
                                fusion=int(_opt(self.config, "fusion", 1)),
-                               strict_parity=int(_opt(self.config, "strict-parity", 1)))
+                               strict_parity=int(_opt(self.config, "strict-parity", 1)),
+                               n_gpus=n_gpus, device_ids=_opt(self.config, "device-ids"))
+            sv.generation = 0
             self._svs[n] = sv
+        sv.generation = getattr(sv, "generation", 0) + 1     # invalidates the lazy handles of earlier jobs' results
         return sv
 
     def close(self):
@@ -201,6 +245,8 @@ class _BackendBase:
         t0 = time.time()
         try:
             with self._lock:
+                options = dict(options or {})
+                options["__draws"] = _DrawSource(options, self._rng)
                 res = self._execute(circuit, options)
             res["execution-time-ms"] = int((time.time() - t0) * 1000)
             return res
@@ -208,15 +254,12 @@ class _BackendBase:
             return {"job-status": "failed", "error-message": str(e), "exception-type": type(e).__name__}
 
     def _uniforms(self, options, shape):
-        u = _opt(options, "uniforms")
-        if u is not None:
-            u = np.asarray(u, dtype=np.float64)
-            if u.size < int(np.prod(shape)):
-                raise ValueError("not enough uniforms supplied")
-            return u.reshape(-1)[: int(np.prod(shape))].reshape(shape)
-        seed = _opt(options, "seed")
-        rng = np.random.default_rng(seed) if seed is not None else self._rng
-        return rng.random(shape)
+        src = options.get("__draws") if isinstance(options, dict) else None
+        if src is None:
+            src = _DrawSource(options, self._rng)
+            if isinstance(options, dict):
+                options["__draws"] = src
+        return src.take(shape)
 
 
 # =============================================================================== ideal simulator
@@ -337,6 +380,12 @@ class B200HardwareSimulator(_BackendBase):
         table, keep = NZ.build_noise_table(noise_model, n)
         enc = OPS.encode_ops(ops)
         dps = sv.noisy_draws_per_shot(enc, table)
+        init = _opt(options, "initial-state")                          # (or (:initial-state options) zero-state), :128-131
+        if init is not None:
+            vec = init.get("state-vector", init.get(":state-vector")) if isinstance(init, dict) else init
+            sv.noisy_set_initial_state(np.asarray(vec, dtype=np.complex128))
+        else:
+            sv.noisy_set_initial_state(None)
         u = self._uniforms(options, (shots, dps))
         outcomes, traj = sv.run_noisy(enc, table, u, max_trajectories=max_traj if n <= 20 else 0)
         counts: Dict[str, int] = {}

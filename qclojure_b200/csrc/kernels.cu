@@ -391,12 +391,81 @@ __device__ __forceinline__ void k3_batches(uint32_t tile_s, const uint4 lt, cons
   sts_c128(tile_s + (lt.w ^ t.Xp), t.pr1, t.pi1);
 }
 
+// ---- the same pipeline without register rotation: two operand sets that swap roles every batch (the loop body handles two
+// batches), so every value is consumed before the instruction that produces its successor and ptxas needs no moves.  Round 2
+// profile of the rotating loop: 24 IMAD.MOV per batch, the ones that copy fresh DMMA results stall the warp on the short
+// scoreboard, and the batch-offset LDS sits in the address chain of the loads.  Here the batch offset is fetched one batch
+// ahead of its first use and the operand loads of batch i+2 are issued at the top of batch i.
+struct K3Set {
+  double K0, K1, s0, s1, d0, d1;     // K = P Br; Br + Bi and Bi - Br of k-steps 0, 1
+  double r0, i0, r1, i1;             // raw loads
+  uint32_t X;                        // swizzled byte offset of the batch the set currently belongs to
+};
+// one batch: c = its operands (K, s, d ready), n = the next batch's (raw loads in flight); HAS1 / HAS2 / HASP: a batch i+1 /
+// i+2 / i-1 exists.  pr / pi = the results (stored at the top of the NEXT call), pa0 / pa1 their shared-memory addresses.
+template <bool HAS1, bool HAS2, bool HASP>
+__device__ __forceinline__ void k3_pp(K3Set& c, K3Set& n, double& pr0, double& pr1, double& pi0, double& pi1, uint32_t& pa0, uint32_t& pa1,
+                                      uint32_t tile_s, const uint4& lt, uint32_t xq, const double (&A)[6]) {
+  if (HASP) { sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1); }
+  pa0 = tile_s + (lt.z ^ c.X); pa1 = tile_s + (lt.w ^ c.X);
+  if (HAS2) {
+    c.X = xq & DMMA_BATCH_OFF_MASK;
+    lds_c128(tile_s + (lt.x ^ c.X), c.r0, c.i0);
+    lds_c128(tile_s + (lt.y ^ c.X), c.r1, c.i1);
+  }
+  dmma_884_c(pr0, pr1, A[2], c.s0, c.K0, c.K1);
+  if (HAS1) dmma_884_c(n.K0, n.K1, A[0], n.r0, 0.0, 0.0);
+  dmma_884_c(pi0, pi1, A[4], c.d0, c.K0, c.K1);
+  if (HAS1) {
+    dmma_884_c(n.K0, n.K1, A[1], n.r1, n.K0, n.K1);
+    n.s0 = n.r0 + n.i0; n.d0 = n.i0 - n.r0;
+  }
+  dmma_884_c(pr0, pr1, A[3], c.s1, pr0, pr1);
+  if (HAS1) { n.s1 = n.r1 + n.i1; n.d1 = n.i1 - n.r1; }
+  dmma_884_c(pi0, pi1, A[5], c.d1, pi0, pi1);
+}
+// per even and >= 4
+__device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[6]) {
+  K3Set a, b;
+  double pr0 = 0, pr1 = 0, pi0 = 0, pi1 = 0;
+  uint32_t pa0 = 0, pa1 = 0;
+  a.X = btab[0] & DMMA_BATCH_OFF_MASK;
+  b.X = btab[1] & DMMA_BATCH_OFF_MASK;
+  lds_c128(tile_s + (lt.x ^ a.X), a.r0, a.i0);
+  lds_c128(tile_s + (lt.y ^ a.X), a.r1, a.i1);
+  lds_c128(tile_s + (lt.x ^ b.X), b.r0, b.i0);
+  lds_c128(tile_s + (lt.y ^ b.X), b.r1, b.i1);
+  uint32_t xq = btab[2];
+  a.s0 = a.r0 + a.i0; a.d0 = a.i0 - a.r0; a.s1 = a.r1 + a.i1; a.d1 = a.i1 - a.r1;
+  dmma_884_c(a.K0, a.K1, A[0], a.r0, 0.0, 0.0);
+  dmma_884_c(a.K0, a.K1, A[1], a.r1, a.K0, a.K1);
+  // batches 0, 1
+  k3_pp<true, true, false>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  xq = btab[3];
+  k3_pp<true, true, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  // batches 2 .. per-3 (both look-aheads exist)
+#pragma unroll 1
+  for (uint32_t i = 2; i + 2u < per; i += 2u) {
+    xq = btab[i + 2u];
+    k3_pp<true, true, true>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+    xq = btab[i + 3u];
+    k3_pp<true, true, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  }
+  k3_pp<true, false, true>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
+  k3_pp<false, false, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
+  sts_c128(pa0, pr0, pi0);
+  sts_c128(pa1, pr1, pi1);
+}
+
 // One warp's share of a three-product round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
 __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
                                              uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[6], uint32_t cur) {
   const uint4 lt = lane_tab_r[2u * lane];
   if ((btab[0] >> 20) == (btab[per - 1u] >> 20)) {
     // local condition bits are the top bits of the batch index: equal at both ends => one variant for the whole share
+#ifndef QCB_K3_ROTATE
+    if (per >= 4u && !(per & 1u)) { k3_batches_pp(tile_s, lt, btab, per, A); return; }
+#endif
     k3_batches(tile_s, lt, btab, per, A);
     return;
   }
@@ -563,12 +632,12 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
 
   const uint32_t T = (uint32_t)((n_active - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
   const uint32_t lowmask = (1u << L) - 1u;
-  // Optional register re-allocation between the warpgroups (setmaxnreg; -DQCB_REALLOC): the kernel is compiled for 168
-  // registers per thread (384 threads, one CTA per SM); the mover warpgroup would hand registers to the consumer warpgroups.
-#ifdef QCB_REALLOC
-  constexpr bool REALLOC = (NCW == 8 && MOVER_WARPS == 4);
+  // Register re-allocation between the warpgroups (setmaxnreg): the kernel is compiled for 168 registers per thread (384
+  // threads, one CTA per SM); the mover warpgroup hands registers to the two consumer warpgroups (104 / 200 per thread).
+#ifndef QCB_NO_REALLOC
+  constexpr bool REALLOC = (NCW == 8 && MOVER_WARPS == 4);      // measured: +6 % (5166 -> 5473 gates/s, profiles/r2a_ab.log)
 #else
-  constexpr bool REALLOC = false;     // the consumer path needs ~120 registers: no re-allocation required (experiment switch)
+  constexpr bool REALLOC = false;
 #endif
 
   if (warp >= NCW) {
@@ -1290,6 +1359,61 @@ cudaError_t launch_pack_half(const double2* state, double2* buf, uint64_t first,
 }
 cudaError_t launch_unpack_half(double2* state, const double2* buf, uint64_t first, uint64_t n, int lbit, int want, int grid, cudaStream_t s) {
   k_unpack_half<<<grid, RED_THREADS, 0, s>>>(state, buf, first, n, lbit, want);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ in-place qubit exchange over peer-mapped memory (multi-GPU)
+// Swaps k global physical bits with k local physical bits in ONE pass over NVLink, without staging buffers.  With g = the
+// values of this rank's k exchanged rank bits and v = the values of an amplitude's k exchanged local bits, the amplitude
+// (rank g, local v) trades places with (rank v, local g); amplitudes with v == g stay.  Of the 2^k ranks that differ only in
+// the exchanged rank bits, each pair (g, v) owns a pair of sub-blocks; the pair's two ranks split the work by the top bit
+// of the remaining index, so every rank reads and writes the same number of remote bytes and both NVLink directions carry
+// (2^k - 1) / 2^k of a slice - against k / 2 slices for k pairwise half-slice exchanges.  One work item = one amplitude
+// pair: local load + remote load, local store + remote store (16 bytes each, consecutive threads on consecutive amplitudes;
+// the lowest exchanged local bit is >= 4, so a warp's 512 bytes are contiguous on both sides).  The caller brackets the launch
+// with stream-ordered barriers across the ranks (nobody touches a peer's slice before its earlier kernels are done, nobody
+// reads its own slice before the peers' writes have landed).
+__global__ void __launch_bounds__(RED_THREADS)
+k_swap_global(double2* __restrict__ mine, SwapPeers peers, SwapBits sb, uint32_t g, uint64_t n_rest_half) {
+  const uint32_t k = (uint32_t)sb.k;
+  const uint64_t per_partner = n_rest_half;                       // work items per partner
+  const uint64_t total = per_partner * ((1ull << k) - 1ull);
+  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  auto locate = [&](uint64_t w, uint64_t& x, uint64_t& xp, double2*& peer) {
+    const uint32_t pi = (uint32_t)(w / per_partner);              // partner ordinal 0 .. 2^k - 2
+    uint64_t rest = w - (uint64_t)pi * per_partner;
+    const uint32_t v = pi + (pi >= g ? 1u : 0u);                  // partner's value of the exchanged bits (skips g)
+    // the pair's lower rank takes the items whose top rest bit is 0, the higher rank those with 1
+    if (g > v) rest |= n_rest_half;
+    uint64_t base = rest;
+#pragma unroll
+    for (int j = 0; j < MAX_SWAP_BITS; ++j) if (j < sb.k) base = ((base >> sb.lpos[j]) << (sb.lpos[j] + 1)) | (base & ((1ull << sb.lpos[j]) - 1ull));
+    uint64_t dv = 0, dg = 0;
+#pragma unroll
+    for (int j = 0; j < MAX_SWAP_BITS; ++j)
+      if (j < sb.k) { dv |= (uint64_t)((v >> sb.pair[j]) & 1u) << sb.lpos[j]; dg |= (uint64_t)((g >> sb.pair[j]) & 1u) << sb.lpos[j]; }
+    x = base | dv; xp = base | dg;
+    peer = peers.p[v];
+  };
+  uint64_t w = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  for (; w + 3 * stride < total; w += 4 * stride) {
+    uint64_t x[4], xp[4]; double2* pr[4]; double2 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) locate(w + u * stride, x[u], xp[u], pr[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a[u] = __ldcs(mine + x[u]); b[u] = __ldcg(pr[u] + xp[u]); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { __stcs(mine + x[u], b[u]); __stcg(pr[u] + xp[u], a[u]); }
+  }
+  for (; w < total; w += stride) {
+    uint64_t x, xp; double2* pr;
+    locate(w, x, xp, pr);
+    const double2 a = __ldcs(mine + x), b = __ldcg(pr + xp);
+    __stcs(mine + x, b); __stcg(pr + xp, a);
+  }
+}
+cudaError_t launch_swap_global(double2* mine, const SwapPeers& peers, const SwapBits& sb, uint32_t g, uint64_t n_rest_half, int grid, cudaStream_t s) {
+  k_swap_global<<<grid, RED_THREADS, 0, s>>>(mine, peers, sb, g, n_rest_half);
   return cudaGetLastError();
 }
 

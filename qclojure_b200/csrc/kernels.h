@@ -17,6 +17,12 @@ struct ExpectTerms { int n; uint64_t zmask[EXPECT_TERMS]; double pr[EXPECT_TERMS
 struct Mat2 { double m[8]; };
 struct BitList { int n; int pos[MAX_MEASURE_BITS]; };
 struct GroverMarks { int n; uint64_t idx[8]; };                    // marked basis states of the phase oracles (local indices)
+// multi-qubit exchange (k_swap_global): lpos[j] = j-th exchanged LOCAL bit position, ASCENDING; pair[j] = which bit of the
+// group value (the exchanged rank bits, in ascending rank-bit order) it trades places with; peers.p[v] = slice of the rank whose
+// exchanged rank bits have the value v (p[own value] unused)
+constexpr int MAX_SWAP_BITS = 3;
+struct SwapBits { int k; int lpos[MAX_SWAP_BITS]; int pair[MAX_SWAP_BITS]; };
+struct SwapPeers { double2* p[1 << MAX_SWAP_BITS]; };
 
 // TMA tensor maps of one state allocation, indexed by run bits c (box = 2^(c-3) rows of 128 bytes); opaque 128-byte
 // CUtensorMap objects so that this header does not need <cuda.h>.
@@ -50,6 +56,7 @@ cudaError_t launch_sample(const double2* state, uint64_t count, const double* cu
                           unsigned long long* outcomes, int grid, cudaStream_t s);
 cudaError_t launch_pack_half(const double2* state, double2* buf, uint64_t first, uint64_t n, int lbit, int want, int grid, cudaStream_t s);
 cudaError_t launch_unpack_half(double2* state, const double2* buf, uint64_t first, uint64_t n, int lbit, int want, int grid, cudaStream_t s);
+cudaError_t launch_swap_global(double2* mine, const SwapPeers& peers, const SwapBits& sb, uint32_t g, uint64_t n_rest_half, int grid, cudaStream_t s);
 cudaError_t launch_la_matmul(const double2* A, const double2* B, uint64_t m, uint64_t k, uint64_t n, double2* C, cudaStream_t s);
 cudaError_t launch_la_kron(const double2* A, uint64_t ar, uint64_t ac, const double2* B, uint64_t br, uint64_t bc, double2* C, cudaStream_t s);
 cudaError_t launch_la_outer(const double2* x, const double2* y, uint64_t n, uint64_t m, double2* C, cudaStream_t s);

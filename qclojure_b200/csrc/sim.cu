@@ -97,11 +97,36 @@ struct Job {
   std::vector<uint64_t> outcomes;
   double energy = 0; int has_energy = 0;
   std::vector<double> probs, state;
+  bool payload_dropped = false;               // pruned: outcomes / probabilities / state are gone (64 newest finished jobs keep theirs)
   std::string error;
+};
+
+// ------------------------------------------------------------------ single-process multi-GPU: what the member handles share
+// One qcb_handle created with qcb_config.n_gpus > 1 is a *group*: it owns one ordinary rank handle per device (the same
+// SPMD code path torchrun ranks run, one host thread per device for every call) and presents the whole state.
+struct GroupShared {
+  int n = 0;
+  std::vector<double2*> states;                   // state allocation of every member (direct peer access inside one process)
+  std::vector<int> devices;
+  std::mutex mu; std::condition_variable cv;
+  int arrived = 0; uint64_t gen = 0; bool all_ok = true, verdict = true;
+  // host barrier that also agrees on a flag: returns true when EVERY member passed ok = true
+  bool agree(bool ok) {
+    std::unique_lock<std::mutex> lk(mu);
+    all_ok = all_ok && ok;
+    const uint64_t my_gen = gen;
+    if (++arrived == n) { verdict = all_ok; all_ok = true; arrived = 0; ++gen; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != my_gen; });
+    return verdict;
+  }
 };
 
 // ------------------------------------------------------------------ the handle
 struct qcb_sim {
+  // group handle (n_gpus > 1): no device state of its own, every entry point fans out to `members`
+  bool is_group = false;
+  std::vector<qcb_sim*> members;
+  std::shared_ptr<GroupShared> gs;                // set on group handles and on their members
   Config cfg;
   int device = 0, num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -127,7 +152,12 @@ struct qcb_sim {
   // peer-to-peer exchange: every rank's state allocation is IPC-mapped by its exchange partners (ranks differing in
   // one bit), so the moving half is pulled straight out of the partner's HBM over NVLink by the copy engines
   bool p2p = false;
-  std::vector<double2*> peer_state;               // [world], nullptr = not a partner
+  bool peers_ipc = false;                         // peer_state entries are IPC mappings (closed on destroy); else direct pointers
+  int xmode = 0;                                  // 0 = in-place swap kernel over peer memory, 1 = copy-engine pull, 2 = NCCL send/recv
+  std::vector<double2*> peer_state;               // [world], nullptr = not mapped
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> xtimes;   // exchange event pairs of the current call (resolved by qcb_get_stats)
+  std::vector<cudaEvent_t> xev_pool;
+  double2* noisy_init = nullptr;                  // qcb_noisy_set_initial_state: device copy of the trajectories' initial state
   cudaEvent_t xrecv[2] = {nullptr, nullptr}, xcopy[2] = {nullptr, nullptr}, xpack[2] = {nullptr, nullptr};
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;
   std::string err;
@@ -139,6 +169,7 @@ struct qcb_sim {
   std::mutex jmu; std::condition_variable jcv;
   std::map<uint64_t, std::shared_ptr<Job>> jobs;
   std::deque<std::shared_ptr<Job>> queue;
+  std::deque<uint64_t> finished;                  // ids of finished jobs whose payload is still held (newest last)
   std::thread worker; bool worker_started = false; bool stopping = false;
   uint64_t next_job = 1;
   std::atomic<bool>* active_cancel = nullptr;
@@ -212,6 +243,41 @@ int ensure_prog(qcb_sim* h, size_t words) {
 
 int do_exchange_nccl(qcb_sim* h, int gbit, int lbit);
 
+// Exchange timing without host synchronisation: an event pair per exchange on the handle's stream, resolved when the
+// statistics are read (qcb_get_stats), so that the scheduler keeps planning while an exchange is in flight.
+cudaEvent_t xev_get(qcb_sim* h) {
+  if (!h->xev_pool.empty()) { cudaEvent_t e = h->xev_pool.back(); h->xev_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+int xtime_begin(qcb_sim* h) {
+  cudaEvent_t e = xev_get(h);
+  if (!e) return fail(h, QCB_ERR_CUDA, "cudaEventCreate failed");
+  CU(h, cudaEventRecord(e, h->stream));
+  h->xtimes.emplace_back(e, nullptr);
+  return QCB_OK;
+}
+int xtime_end(qcb_sim* h) {
+  cudaEvent_t e = xev_get(h);
+  if (!e) return fail(h, QCB_ERR_CUDA, "cudaEventCreate failed");
+  CU(h, cudaEventRecord(e, h->stream));
+  h->xtimes.back().second = e;
+  return QCB_OK;
+}
+// adds the elapsed time of every finished exchange to stats.exchange_ms (synchronises on their end events)
+void xtime_resolve(qcb_sim* h) {
+  for (auto& pr : h->xtimes) {
+    if (pr.first && pr.second && cudaEventSynchronize(pr.second) == cudaSuccess) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) h->stats.exchange_ms += ms;
+    }
+    if (pr.first) h->xev_pool.push_back(pr.first);
+    if (pr.second) h->xev_pool.push_back(pr.second);
+  }
+  h->xtimes.clear();
+}
+
 int ensure_exchange_buffers(qcb_sim* h, uint64_t half) {
   if (h->xbuf) return QCB_OK;
   static const int xlog = [] { const char* e = getenv("QCB_XCHUNK_LOG2"); int v = e ? atoi(e) : 25; return v < 4 ? 4 : (v > 28 ? 28 : v); }();
@@ -258,7 +324,7 @@ int do_exchange_p2p(qcb_sim* h, int gbit, int lbit) {
     NC(h, g_nccl.GroupEnd());
     return QCB_OK;
   };
-  CU(h, cudaEventRecord(h->xev0, h->stream));
+  RET(xtime_begin(h));
   RET(handshake());                                                         // H0
   for (uint64_t c = 0; c < n_chunks; ++c) {
     const int sb = (int)(c & 1);
@@ -282,17 +348,78 @@ int do_exchange_p2p(qcb_sim* h, int gbit, int lbit) {
     h->stats.bytes_exchanged += cnt * sizeof(double2);
   }
   for (uint64_t i = 0; i < 2 && i < n_chunks; ++i) CU(h, cudaStreamWaitEvent(h->stream, h->xcopy[i], 0));
-  CU(h, cudaEventRecord(h->xev1, h->stream));
-  CU(h, cudaEventSynchronize(h->xev1));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, h->xev0, h->xev1);
-  h->stats.exchange_ms += ms;
+  RET(xtime_end(h));
   h->stats.n_exchanges++;
   return QCB_OK;
 }
 
+// stream-ordered barrier across all ranks: a one-double all-reduce on the handle's stream completes only when every rank's
+// stream has reached it
+int stream_barrier(qcb_sim* h) {
+  double* token = h->d_vals + 204;
+  NC(h, g_nccl.AllReduce(token, token, 1, ncclDouble, ncclMax, h->comm, h->stream));
+  return QCB_OK;
+}
+
+// Simultaneous swap of up to MAX_SWAP_BITS (global bit, local bit) pairs with disjoint bits: one in-place pass of
+// k_swap_global over the peer-mapped slices, bracketed by stream-ordered barriers (nobody touches a peer's slice before
+// the peer's earlier kernels are done; nobody reads its own slice before the peers' stores have landed).  No staging
+// buffers, no host synchronisation.
+int do_exchange_swap(qcb_sim* h, const std::pair<int, int>* pairs, int k) {
+  const int nl = h->cfg.n_local;
+  std::vector<int> gb(k), order(k);
+  for (int j = 0; j < k; ++j) gb[j] = pairs[j].first;
+  std::sort(gb.begin(), gb.end());                                            // group-value bit i <-> gb[i]
+  for (int j = 0; j < k; ++j) order[j] = j;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return pairs[a].second < pairs[b].second; });
+  SwapBits sb; sb.k = k;
+  for (int j = 0; j < MAX_SWAP_BITS; ++j) { sb.lpos[j] = 0; sb.pair[j] = 0; }
+  for (int j = 0; j < k; ++j) {
+    sb.lpos[j] = pairs[order[j]].second;
+    sb.pair[j] = (int)(std::find(gb.begin(), gb.end(), pairs[order[j]].first) - gb.begin());
+  }
+  uint32_t g = 0;
+  for (int i = 0; i < k; ++i) g |= (uint32_t)((h->cfg.rank >> (gb[i] - nl)) & 1) << i;
+  SwapPeers peers;
+  for (int v = 0; v < (1 << MAX_SWAP_BITS); ++v) peers.p[v] = nullptr;
+  for (uint32_t v = 0; v < (1u << k); ++v) {
+    if (v == g) continue;
+    int r = h->cfg.rank;
+    for (int i = 0; i < k; ++i) r = (r & ~(1 << (gb[i] - nl))) | (int)((v >> i) & 1u) << (gb[i] - nl);
+    if (!h->peer_state[r]) return fail(h, QCB_ERR_NCCL, "exchange partner " + std::to_string(r) + " is not peer-mapped");
+    peers.p[v] = h->peer_state[r];
+  }
+  const uint64_t n_rest_half = h->local_count >> (k + 1);
+  RET(stream_barrier(h));
+  RET(xtime_begin(h));
+  const uint64_t total = n_rest_half * ((1ull << k) - 1ull);
+  const int grid = (int)std::min<uint64_t>((total + RED_THREADS - 1) / RED_THREADS, (uint64_t)h->num_sms * 8);
+  if (grid > 0) CU(h, launch_swap_global(h->state, peers, sb, g, n_rest_half, grid, h->stream));
+  RET(stream_barrier(h));
+  RET(xtime_end(h));
+  h->stats.n_kernel_launches++;
+  h->stats.n_exchanges += (uint64_t)k;
+  h->stats.bytes_exchanged += (h->local_count - (h->local_count >> k)) * sizeof(double2);
+  return QCB_OK;
+}
+
 int do_exchange(qcb_sim* h, int gbit, int lbit) {
-  return h->p2p ? do_exchange_p2p(h, gbit, lbit) : do_exchange_nccl(h, gbit, lbit);
+  if (h->p2p && h->xmode == 0) { const std::pair<int, int> pr(gbit, lbit); return do_exchange_swap(h, &pr, 1); }
+  return (h->p2p && h->xmode == 1) ? do_exchange_p2p(h, gbit, lbit) : do_exchange_nccl(h, gbit, lbit);
+}
+
+// A run of exchanges with pairwise disjoint bits (what the scheduler emits "in one breath", and what restore_layout needs):
+// with the swap kernel up to MAX_SWAP_BITS pairs move in one pass ((2^k - 1) / 2^k of a slice instead of k / 2)
+int do_exchange_multi(qcb_sim* h, const std::vector<std::pair<int, int>>& pairs) {
+  if (pairs.empty()) return QCB_OK;
+  if (!(h->p2p && h->xmode == 0)) {
+    for (auto& pr : pairs) RET(do_exchange(h, pr.first, pr.second));
+    return QCB_OK;
+  }
+  static const int max_k = [] { const char* e = getenv("QCB_SWAP_BITS"); int v = e ? atoi(e) : MAX_SWAP_BITS; return v < 1 ? 1 : (v > MAX_SWAP_BITS ? MAX_SWAP_BITS : v); }();
+  for (size_t i = 0; i < pairs.size(); i += (size_t)max_k)
+    RET(do_exchange_swap(h, pairs.data() + i, (int)std::min<size_t>((size_t)max_k, pairs.size() - i)));
+  return QCB_OK;
 }
 
 bool perm_is_identity(const qcb_sim* h) {
@@ -341,6 +468,7 @@ int do_exchange_nccl(qcb_sim* h, int gbit, int lbit) {
   auto sendbuf = [&](uint64_t c) { return h->xbuf + (c & 1) * chunk; };
   auto recvbuf = [&](uint64_t c) { return h->xbuf + (2 + (c & 1)) * chunk; };
   auto count_of = [&](uint64_t c) { return std::min<uint64_t>(chunk, half - c * chunk); };
+  RET(xtime_begin(h));
   CU(h, cudaEventRecord(h->xev0, h->stream));
   CU(h, cudaStreamWaitEvent(h->xstream, h->xev0, 0));                       // the state is final before anything is gathered
   auto pack = [&](uint64_t c) -> int {
@@ -370,11 +498,7 @@ int do_exchange_nccl(qcb_sim* h, int gbit, int lbit) {
     h->stats.bytes_exchanged += cnt * sizeof(double2);
   }
   for (uint64_t i = 0; i < 2 && i < n_chunks; ++i) CU(h, cudaStreamWaitEvent(h->stream, h->xcopy[i], 0));
-  CU(h, cudaEventRecord(h->xev1, h->stream));
-  CU(h, cudaEventSynchronize(h->xev1));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, h->xev0, h->xev1);
-  h->stats.exchange_ms += ms;
+  RET(xtime_end(h));
   h->stats.n_exchanges++;
   return QCB_OK;
 }
@@ -414,7 +538,7 @@ int execute_stage(qcb_sim* h, Plan& plan, size_t si) {
       h->stats.n_kernel_launches += 2;
     }
   } else if (st.kind == S_EXCHANGE) {
-    RET(do_exchange(h, st.gbit, st.lbit));
+    RET(do_exchange(h, st.gbit, st.lbit));         // (the streaming executor batches exchanges itself and never gets here)
   }
   return QCB_OK;
 }
@@ -425,8 +549,24 @@ int execute_stage(qcb_sim* h, Plan& plan, size_t si) {
 // not move while earlier stages are in flight.
 struct StreamingExecutor : StageSink {
   qcb_sim* h;
+  std::vector<std::pair<int, int>> xq;             // consecutive exchange stages with pairwise disjoint bits, not yet executed
   explicit StreamingExecutor(qcb_sim* hh) : h(hh) {}
+  int flush_exchanges() {
+    if (xq.empty()) return QCB_OK;
+    std::vector<std::pair<int, int>> q;
+    q.swap(xq);
+    return do_exchange_multi(h, q);
+  }
   int on_stage(Plan& plan, size_t si) override {
+    if (plan.stages[si].kind == S_EXCHANGE) {
+      // consecutive exchanges on disjoint bits commute: queue them and move them in one pass
+      const int gb = plan.stages[si].gbit, lb = plan.stages[si].lbit;
+      for (auto& pr : xq) if (pr.first == gb || pr.second == lb || pr.first == lb || pr.second == gb) { RET(flush_exchanges()); break; }
+      xq.emplace_back(gb, lb);
+      if (h->active_cancel && h->active_cancel->load()) return fail(h, QCB_ERR_STATE, "cancelled");
+      return QCB_OK;
+    }
+    RET(flush_exchanges());
     const size_t begin = plan.stage_offsets[si], end = plan.words.size();
     if (end > h->prog_cap) {
       // rare (bound below exceeded): let everything in flight finish, then grow
@@ -463,6 +603,7 @@ int run_gates(qcb_sim* h, std::vector<Gate>&& gates) {
       for (auto& t : it->second) if (t->key == rec->key) { hit = t; break; }
   }
   int rc = schedule(plan, h->perm, &sink, (cacheable && !hit) ? rec.get() : nullptr, hit.get());
+  if (rc == QCB_OK) { rc = sink.flush_exchanges(); if (rc != QCB_OK) plan.error = "stage sink failed"; }
   CU(h, cudaEventRecord(h->prog_ev, h->stream));
   h->prog_ev_valid = true;
   if (rc != QCB_OK) {
@@ -493,20 +634,32 @@ int restore_layout(qcb_sim* h) {
   std::vector<int> logical_of(n);
   auto refresh = [&]() { for (int b = 0; b < n; ++b) logical_of[h->perm[b]] = b; };
   refresh();
-  // 1) every global physical bit gets its own logical bit back, through a local staging position
-  for (int G = nl; G < n; ++G) {
-    if (logical_of[G] == G) continue;
-    int where = h->perm[G];                       // physical position of logical bit G
-    if (where >= nl) {                            // sits on another global bit: bring it local first
-      int l = nl - 1;
-      RET(do_exchange(h, where, l));
-      std::swap(h->perm[logical_of[where]], h->perm[logical_of[l]]);
+  // 1) every global physical bit gets its own logical bit back, through a local staging position.  The swaps are worked
+  // out on the host first; consecutive ones with pairwise disjoint bits then move in one pass (do_exchange_multi).
+  {
+    std::vector<std::pair<int, int>> seq;
+    for (int G = nl; G < n; ++G) {
+      if (logical_of[G] == G) continue;
+      int where = h->perm[G];                       // physical position of logical bit G
+      if (where >= nl) {                            // sits on another global bit: bring it local first
+        int l = nl - 1;
+        seq.emplace_back(where, l);
+        std::swap(h->perm[logical_of[where]], h->perm[logical_of[l]]);
+        refresh();
+        where = h->perm[G];
+      }
+      seq.emplace_back(G, where);
+      std::swap(h->perm[logical_of[G]], h->perm[logical_of[where]]);
       refresh();
-      where = h->perm[G];
     }
-    RET(do_exchange(h, G, where));
-    std::swap(h->perm[logical_of[G]], h->perm[logical_of[where]]);
-    refresh();
+    std::vector<std::pair<int, int>> batch;
+    for (auto& pr : seq) {
+      bool clash = false;
+      for (auto& b : batch) clash = clash || b.first == pr.first || b.second == pr.second || b.first == pr.second || b.second == pr.first;
+      if (clash) { RET(do_exchange_multi(h, batch)); batch.clear(); }
+      batch.push_back(pr);
+    }
+    RET(do_exchange_multi(h, batch));
   }
   // 2) local permutation: swap gates on physical bits (fused into tile sweeps by the scheduler)
   std::vector<Gate> swaps;
@@ -530,6 +683,7 @@ int restore_layout(qcb_sim* h) {
     if (h->prog_ev_valid) CU(h, cudaEventSynchronize(h->prog_ev));
     StreamingExecutor sink(h);
     int rc = schedule(plan, std::vector<int>(), &sink);
+    if (rc == QCB_OK) rc = sink.flush_exchanges();
     CU(h, cudaEventRecord(h->prog_ev, h->stream));
     h->prog_ev_valid = true;
     if (rc != QCB_OK) return plan.error != "stage sink failed" ? fail(h, rc, plan.error) : rc;
@@ -539,6 +693,7 @@ int restore_layout(qcb_sim* h) {
 }
 
 int begin_timing(qcb_sim* h) {
+  xtime_resolve(h);                                 // exchanges of earlier calls whose statistics were never read
   std::memset(&h->stats, 0, sizeof h->stats);
   CU(h, cudaEventRecord(h->ev0, h->stream));
   return QCB_OK;
@@ -842,6 +997,21 @@ int run_job(qcb_sim* h, Job& job);
 
 }  // namespace
 
+// ---- group handles: fan a call out to the member handles, one host thread per device
+template <class F>
+static int group_run(qcb_sim* g, F&& f) {
+  const int n = (int)g->members.size();
+  std::vector<int> rc(n, QCB_OK);
+  std::vector<std::thread> th;
+  th.reserve(n);
+  for (int r = 1; r < n; ++r) th.emplace_back([&, r] { rc[r] = f(g->members[r], r); });
+  rc[0] = f(g->members[0], 0);
+  for (auto& t : th) t.join();
+  for (int r = 0; r < n; ++r)
+    if (rc[r] != QCB_OK) { g->err = "device " + std::to_string(g->members[r]->device) + ": " + g->members[r]->err; return rc[r]; }
+  return QCB_OK;
+}
+
 // =================================================================== C ABI
 extern "C" {
 
@@ -883,48 +1053,72 @@ int32_t qcb_config_default(qcb_config* cfg) {
   return QCB_OK;
 }
 
-// Exchange the IPC handles of the state allocations and map the partners' states.  Every rank must reach the same verdict
-// (a rank pulling while its partner sends would hang), so the outcome is agreed on with a min-all-reduce; any failure
-// simply leaves the NCCL send/recv exchange in place.
+// Map the state allocations of ALL other ranks (the multi-qubit swap kernel exchanges with up to 7 partners at once).
+// Ranks in other processes: cudaIpcGetMemHandle -> all-gather -> cudaIpcOpenMemHandle.  Ranks of the same process (a group
+// handle): direct pointers + cudaDeviceEnablePeerAccess.  Every rank must reach the same verdict (a rank using peer memory
+// while its partner sends through NCCL would hang), so the outcome is agreed on with a min-all-reduce; any failure simply
+// leaves the NCCL send/recv exchange in place.  QCB_EXCHANGE = swap (default: in-place swap kernel) | ce (copy-engine pull
+// through staging buffers, the round-1 path) | nccl (ncclSend/ncclRecv).
 static void setup_p2p(qcb_sim* h) {
   const int world = h->cfg.world;
   h->peer_state.assign(world, nullptr);
-  // Default: peer-to-peer pull on 2 GPUs, where it has been validated end to end (parity + 687 GB/s per direction); the
-  // NCCL send/recv path - validated on 4 and 8 GPUs - on larger worlds until the pull path has been run there
-  // (QCB_EXCHANGE=p2p opts in, QCB_EXCHANGE=nccl forces the NCCL path everywhere).
   const char* mode = getenv("QCB_EXCHANGE");
   const std::string m = mode ? mode : "";
-  double ok = (m == "nccl" || (world > 2 && m != "p2p")) ? 0.0 : 1.0;
-  unsigned char* d_ipc = nullptr;
-  std::vector<cudaIpcMemHandle_t> handles(world);
-  if (cudaMalloc(&d_ipc, (size_t)world * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) { cudaGetLastError(); return; }
-  cudaIpcMemHandle_t mine;
-  if (cudaIpcGetMemHandle(&mine, h->state) != cudaSuccess) { cudaGetLastError(); ok = 0.0; std::memset(&mine, 0, sizeof mine); }
-  cudaMemcpyAsync(d_ipc + (size_t)h->cfg.rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream);
-  bool comm_ok = g_nccl.AllGather(d_ipc + (size_t)h->cfg.rank * sizeof mine, d_ipc, sizeof mine, ncclChar, h->comm, h->stream) == ncclSuccess;
-  comm_ok = comm_ok && cudaMemcpyAsync(handles.data(), d_ipc, (size_t)world * sizeof mine, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
-  comm_ok = comm_ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
-  if (!comm_ok) ok = 0.0;
-  if (ok > 0.0)
-    for (int bit = 1; bit < world; bit <<= 1) {
-      const int peer = h->cfg.rank ^ bit;
-      void* p = nullptr;
-      if (cudaIpcOpenMemHandle(&p, handles[peer], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0.0; break; }
-      h->peer_state[peer] = static_cast<double2*>(p);
-    }
-  // agree: p2p only if every rank mapped all of its partners
+  h->xmode = (m == "nccl") ? 2 : ((m == "ce" || m == "p2p") ? 1 : 0);
+  double ok = (h->xmode == 2) ? 0.0 : 1.0;
+  if (h->gs) {
+    // ---- same process: publish the pointer, wait for everybody, enable peer access
+    h->gs->states[h->cfg.rank] = h->state;
+    h->gs->devices[h->cfg.rank] = h->device;
+    h->gs->agree(true);
+    if (ok > 0.0)
+      for (int r = 0; r < world; ++r) {
+        if (r == h->cfg.rank) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, h->device, h->gs->devices[r]) != cudaSuccess || !can) { cudaGetLastError(); ok = 0.0; break; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(h->gs->devices[r], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = 0.0; break; }
+        cudaGetLastError();
+        h->peer_state[r] = h->gs->states[r];
+      }
+    h->peers_ipc = false;
+  } else {
+    unsigned char* d_ipc = nullptr;
+    std::vector<cudaIpcMemHandle_t> handles(world);
+    if (cudaMalloc(&d_ipc, (size_t)world * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, h->state) != cudaSuccess) { cudaGetLastError(); ok = 0.0; std::memset(&mine, 0, sizeof mine); }
+    cudaMemcpyAsync(d_ipc + (size_t)h->cfg.rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream);
+    bool comm_ok = g_nccl.AllGather(d_ipc + (size_t)h->cfg.rank * sizeof mine, d_ipc, sizeof mine, ncclChar, h->comm, h->stream) == ncclSuccess;
+    comm_ok = comm_ok && cudaMemcpyAsync(handles.data(), d_ipc, (size_t)world * sizeof mine, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
+    comm_ok = comm_ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
+    if (!comm_ok) ok = 0.0;
+    if (ok > 0.0)
+      for (int peer = 0; peer < world; ++peer) {
+        if (peer == h->cfg.rank) continue;
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, handles[peer], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0.0; break; }
+        h->peer_state[peer] = static_cast<double2*>(p);
+      }
+    h->peers_ipc = true;
+    cudaFree(d_ipc);
+  }
+  // agree: peer memory only if every rank mapped all of its partners
   double* d_ok = h->d_vals + 202;
   cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, h->stream);
   if (g_nccl.AllReduce(d_ok, d_ok, 1, ncclDouble, ncclMin, h->comm, h->stream) == ncclSuccess &&
       cudaMemcpyAsync(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess && cudaStreamSynchronize(h->stream) == cudaSuccess)
     h->p2p = ok > 0.5;
-  cudaFree(d_ipc);
-  if (!h->p2p)
-    for (auto& p : h->peer_state) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+  if (!h->p2p) {
+    for (auto& p : h->peer_state) if (p) { if (h->peers_ipc) cudaIpcCloseMemHandle(p); p = nullptr; }
+    h->xmode = 2;
+  }
 }
 
-int32_t qcb_create(const qcb_config* c, qcb_handle* out) {
-  if (!c || !out) return fail(nullptr, QCB_ERR_INVALID, "null argument");
+static int32_t create_group(const qcb_config* c, qcb_handle* out);
+
+// one rank handle on one device; gs != nullptr: member of a single-process group (see create_group)
+static int32_t create_single(const qcb_config* c, const std::shared_ptr<GroupShared>& gs, qcb_handle* out) {
   *out = nullptr;
   const int world = c->world_size > 0 ? c->world_size : 1;
   if (world & (world - 1)) return fail(nullptr, QCB_ERR_INVALID, "world_size must be a power of two");
@@ -941,40 +1135,119 @@ int32_t qcb_create(const qcb_config* c, qcb_handle* out) {
   if (dev >= ndev) return fail(nullptr, QCB_ERR_INVALID, "device ordinal out of range");
   std::unique_ptr<qcb_sim> h(new qcb_sim());
   h->cfg = cfg; h->device = dev;
-  qcb_sim* hp = nullptr;   // errors before the handle exists go to the global slot
+  h->gs = gs;
+  auto allocate = [&]() -> int {
+    qcb_sim* hp = nullptr;   // errors before the handle exists go to the global slot
 #define CUC(expr)                                                                                         \
   do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(hp, _e == cudaErrorMemoryAllocation ? QCB_ERR_NOMEM : QCB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
-  CUC(cudaSetDevice(dev));
-  cudaDeviceProp prop;
-  CUC(cudaGetDeviceProperties(&prop, dev));
-  h->num_sms = prop.multiProcessorCount;
-  CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  h->local_count = 1ULL << cfg.n_local;
-  CUC(cudaMalloc(&h->state, h->local_count * sizeof(double2)));
-  CUC(build_tile_maps(h->state, cfg.n_local, &h->maps));
-  CUC(cudaMalloc(&h->d_vals, 256 * sizeof(double)));
-  CUC(cudaMemsetAsync(h->d_vals, 0, 256 * sizeof(double), h->stream));
-  CUC(cudaEventCreate(&h->ev0)); CUC(cudaEventCreate(&h->ev1));
-  CUC(cudaEventCreate(&h->xev0)); CUC(cudaEventCreate(&h->xev1));
-  CUC(cudaEventCreate(&h->tev0)); CUC(cudaEventCreate(&h->tev1));
-  CUC(cudaEventCreateWithFlags(&h->prog_ev, cudaEventDisableTiming));
+    CUC(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, dev));
+    h->num_sms = prop.multiProcessorCount;
+    CUC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->local_count = 1ULL << cfg.n_local;
+    CUC(cudaMalloc(&h->state, h->local_count * sizeof(double2)));
+    CUC(build_tile_maps(h->state, cfg.n_local, &h->maps));
+    CUC(cudaMalloc(&h->d_vals, 256 * sizeof(double)));
+    CUC(cudaMemsetAsync(h->d_vals, 0, 256 * sizeof(double), h->stream));
+    CUC(cudaEventCreate(&h->ev0)); CUC(cudaEventCreate(&h->ev1));
+    CUC(cudaEventCreate(&h->xev0)); CUC(cudaEventCreate(&h->xev1));
+    CUC(cudaEventCreate(&h->tev0)); CUC(cudaEventCreate(&h->tev1));
+    CUC(cudaEventCreateWithFlags(&h->prog_ev, cudaEventDisableTiming));
 #undef CUC
+    if (world > 1) {
+      if (!c->nccl_unique_id) return fail(nullptr, QCB_ERR_INVALID, "world_size > 1 needs nccl_unique_id");
+      std::string err;
+      if (!load_nccl(err)) return fail(nullptr, QCB_ERR_NCCL, err);
+    }
+    return QCB_OK;
+  };
+  int rc = allocate();
+  // members of a group agree before anybody enters the (collective) communicator set-up: one failing device must not
+  // leave the others waiting inside ncclCommInitRank
+  if (gs && !gs->agree(rc == QCB_OK) && rc == QCB_OK) rc = fail(nullptr, QCB_ERR_CUDA, "another device of the group failed to initialise");
+  if (rc != QCB_OK) { qcb_destroy(h.release()); return rc; }
   h->perm.resize(cfg.n_total);
   for (int b = 0; b < cfg.n_total; ++b) h->perm[b] = b;
   if (world > 1) {
-    if (!c->nccl_unique_id) { cudaFree(h->state); return fail(nullptr, QCB_ERR_INVALID, "world_size > 1 needs nccl_unique_id"); }
-    std::string err;
-    if (!load_nccl(err)) { cudaFree(h->state); return fail(nullptr, QCB_ERR_NCCL, err); }
     ncclUniqueId id;
     std::memcpy(&id, c->nccl_unique_id, sizeof id);
     ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, id, c->rank);
-    if (r != ncclSuccess) { cudaFree(h->state); return fail(nullptr, QCB_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); }
+    if (r != ncclSuccess) {
+      const std::string msg = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r);
+      h->comm = nullptr;
+      qcb_destroy(h.release());
+      return fail(nullptr, QCB_ERR_NCCL, msg);
+    }
     setup_p2p(h.get());
   }
   // |0...0>
   cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream);
   if (cfg.rank == 0) launch_set_amp(h->state, 0, 1.0, 0.0, h->stream);
   *out = h.release();
+  return QCB_OK;
+}
+
+int32_t qcb_create(const qcb_config* c, qcb_handle* out) {
+  if (!c || !out) return fail(nullptr, QCB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (c->n_gpus > 1) return create_group(c, out);
+  return create_single(c, nullptr, out);
+}
+
+static int32_t create_group(const qcb_config* c, qcb_handle* out) {
+  const int n = c->n_gpus;
+  if (n & (n - 1) || n > 8) return fail(nullptr, QCB_ERR_INVALID, "n_gpus must be 2, 4 or 8");
+  if (c->world_size > 1) return fail(nullptr, QCB_ERR_INVALID, "n_gpus > 1 and world_size > 1 are mutually exclusive (one handle for all devices, or one SPMD rank per process)");
+  int p = 0;
+  while ((1 << p) < n) ++p;
+  if (c->n_qubits - p < 1 || c->n_qubits > 62) return fail(nullptr, QCB_ERR_INVALID, "n_qubits out of range (need at least 1 local qubit)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, QCB_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  std::vector<int> ids(n);
+  for (int i = 0; i < n; ++i) {
+    ids[i] = c->device_ids[i] >= 0 ? c->device_ids[i] : i;
+    if (ids[i] >= ndev) return fail(nullptr, QCB_ERR_INVALID, "n_gpus = " + std::to_string(n) + " but device " + std::to_string(ids[i]) + " does not exist (" + std::to_string(ndev) + " visible)");
+    for (int j = 0; j < i; ++j) if (ids[j] == ids[i]) return fail(nullptr, QCB_ERR_INVALID, "device_ids must be distinct");
+  }
+  std::string err;
+  if (!load_nccl(err)) return fail(nullptr, QCB_ERR_NCCL, err);
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(nullptr, QCB_ERR_NCCL, g_nccl.GetErrorString(r));
+  std::unique_ptr<qcb_sim> g(new qcb_sim());
+  g->is_group = true;
+  g->gs = std::make_shared<GroupShared>();
+  g->gs->n = n; g->gs->states.assign(n, nullptr); g->gs->devices.assign(n, -1);
+  qcb_config single = *c;                       // what the group looks like from outside: one device holding everything
+  single.n_gpus = 0; single.world_size = 1; single.rank = 0;
+  g->cfg = config_from(single);
+  g->local_count = 1ULL << c->n_qubits;
+  g->device = ids[0];
+  g->members.assign(n, nullptr);
+  std::vector<int> rc(n, QCB_OK);
+  std::vector<std::string> msgs(n);
+  {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; ++i)
+      th.emplace_back([&, i] {
+        qcb_config mc = *c;
+        mc.n_gpus = 0; mc.world_size = n; mc.rank = i; mc.device = ids[i]; mc.nccl_unique_id = &id;
+        rc[i] = create_single(&mc, g->gs, &g->members[i]);
+        if (rc[i] != QCB_OK) { std::lock_guard<std::mutex> lk(g_create_mu); msgs[i] = g_create_error; }
+      });
+    for (auto& t : th) t.join();
+  }
+  for (int i = 0; i < n; ++i)
+    if (rc[i] != QCB_OK) {
+      const int code = rc[i];
+      const std::string msg = "device " + std::to_string(ids[i]) + ": " + msgs[i];
+      qcb_destroy(g.release());
+      return fail(nullptr, code, msg);
+    }
+  *out = g.release();
   return QCB_OK;
 }
 
@@ -986,17 +1259,28 @@ int32_t qcb_destroy(qcb_handle h) {
     h->jcv.notify_all();
   }
   if (h->worker_started && h->worker.joinable()) h->worker.join();
+  if (h->is_group) {
+    // members are torn down concurrently (communicator destruction is collective)
+    std::vector<std::thread> th;
+    for (qcb_sim* m : h->members) if (m) th.emplace_back([m] { qcb_destroy(m); });
+    for (auto& t : th) t.join();
+    delete h;
+    return QCB_OK;
+  }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (auto& p : h->peer_state) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+  xtime_resolve(h);
+  for (auto& p : h->peer_state) if (p) { if (h->peers_ipc) cudaIpcCloseMemHandle(p); p = nullptr; }
   if (h->comm) g_nccl.CommDestroy(h->comm);
   tile_prof_dump();
   cudaFree(h->state); cudaFree(h->d_prog); cudaFree(h->d_vals); cudaFree(h->d_partials); cudaFree(h->d_scratch); cudaFree(h->xbuf);
+  cudaFree(h->noisy_init);
   if (h->h_prog) cudaFreeHost(h->h_prog);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 2; ++i) { if (h->xrecv[i]) cudaEventDestroy(h->xrecv[i]); if (h->xcopy[i]) cudaEventDestroy(h->xcopy[i]); if (h->xpack[i]) cudaEventDestroy(h->xpack[i]); }
+  for (cudaEvent_t e : h->xev_pool) cudaEventDestroy(e);
   if (h->xstream) cudaStreamDestroy(h->xstream);
   if (h->xev0) cudaEventDestroy(h->xev0);
   if (h->xev1) cudaEventDestroy(h->xev1);
@@ -1008,18 +1292,24 @@ int32_t qcb_destroy(qcb_handle h) {
   return QCB_OK;
 }
 
+// Group handles (qcb_config.n_gpus > 1) dispatch before ENTER: GROUP_ALL runs the same call on every member (identical
+// arguments, outputs taken from member 0 where the SPMD path already returns the same result on every rank).
+#define GROUP_ALL(h, call_on_m)                                                              \
+  if ((h) && (h)->is_group) { std::lock_guard<std::recursive_mutex> _glk((h)->mu); return group_run((h), [&](qcb_sim* m, int r) -> int { (void)r; return (call_on_m); }); }
 #define ENTER(h)                                               \
   if (!(h)) return QCB_ERR_INVALID;                            \
   std::lock_guard<std::recursive_mutex> _lk((h)->mu);          \
   CU(h, cudaSetDevice((h)->device));
 
 int32_t qcb_synchronize(qcb_handle h) {
+  GROUP_ALL(h, qcb_synchronize(m));
   ENTER(h);
   CU(h, cudaStreamSynchronize(h->stream));
   return QCB_OK;
 }
 
 int32_t qcb_set_zero(qcb_handle h) {
+  GROUP_ALL(h, qcb_set_zero(m));
   ENTER(h);
   CU(h, cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream));
   if (h->cfg.rank == 0) CU(h, launch_set_amp(h->state, 0, 1.0, 0.0, h->stream));
@@ -1028,6 +1318,7 @@ int32_t qcb_set_zero(qcb_handle h) {
 }
 
 int32_t qcb_set_basis(qcb_handle h, uint64_t index) {
+  GROUP_ALL(h, qcb_set_basis(m, index));
   ENTER(h);
   if (h->cfg.n_total < 64 && (index >> h->cfg.n_total)) return fail(h, QCB_ERR_INVALID, "basis index out of range");
   CU(h, cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream));
@@ -1038,6 +1329,10 @@ int32_t qcb_set_basis(qcb_handle h, uint64_t index) {
 }
 
 int32_t qcb_set_state(qcb_handle h, const double* host, uint64_t count) {
+  if (h && h->is_group) {      // the whole state: member r takes its slice
+    if (!host || count != h->local_count) return fail(h, QCB_ERR_INVALID, "set_state: count must equal 2^n_qubits");
+    GROUP_ALL(h, qcb_set_state(m, host + 2 * (uint64_t)r * m->local_count, m->local_count));
+  }
   ENTER(h);
   if (!host || count != h->local_count) return fail(h, QCB_ERR_INVALID, "set_state: count must equal the local slice size 2^(n - log2 world)");
   CU(h, cudaMemcpyAsync(h->state, host, count * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
@@ -1046,7 +1341,23 @@ int32_t qcb_set_state(qcb_handle h, const double* host, uint64_t count) {
   return QCB_OK;
 }
 
+// the part of the global range [offset, offset + count) that lies in member r's slice: local offset, count, position in `out`
+static void group_slice(const qcb_sim* m, int r, uint64_t offset, uint64_t count, uint64_t& loff, uint64_t& lcnt, uint64_t& opos) {
+  const uint64_t lo = (uint64_t)r * m->local_count, hi = lo + m->local_count;
+  const uint64_t a = std::max(offset, lo), b = std::min(offset + count, hi);
+  if (a >= b) { loff = 0; lcnt = 0; opos = 0; return; }
+  loff = a - lo; lcnt = b - a; opos = a - offset;
+}
+
 int32_t qcb_get_state(qcb_handle h, uint64_t offset, uint64_t count, double* out) {
+  if (h && h->is_group) {      // global range; every member takes part (restoring the canonical layout is collective)
+    if (!out || offset + count > h->local_count) return fail(h, QCB_ERR_INVALID, "get_state: range outside the state");
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    return group_run(h, [&](qcb_sim* m, int r) -> int {
+      uint64_t lo, lc, op; group_slice(m, r, offset, count, lo, lc, op);
+      return qcb_get_state(m, lo, lc, out + 2 * op);
+    });
+  }
   ENTER(h);
   if (!out || offset + count > h->local_count) return fail(h, QCB_ERR_INVALID, "get_state: range outside the local slice");
   RET(restore_layout(h));
@@ -1056,6 +1367,13 @@ int32_t qcb_get_state(qcb_handle h, uint64_t offset, uint64_t count, double* out
 }
 
 int32_t qcb_get_amplitudes(qcb_handle h, const uint64_t* idx, uint64_t n, double* out) {
+  if (h && h->is_group) {      // the SPMD path combines across ranks: every member returns the full answer
+    if (!idx || !out) return fail(h, QCB_ERR_INVALID, "null argument");
+    std::vector<std::vector<double>> tmp(h->members.size(), std::vector<double>(2 * n));
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    int rc = group_run(h, [&](qcb_sim* m, int r) -> int { return qcb_get_amplitudes(m, idx, n, r == 0 ? out : tmp[r].data()); });
+    return rc;
+  }
   ENTER(h);
   if (!idx || !out) return fail(h, QCB_ERR_INVALID, "null argument");
   if (n == 0) return QCB_OK;
@@ -1084,11 +1402,13 @@ int32_t qcb_get_amplitudes(qcb_handle h, const uint64_t* idx, uint64_t n, double
 }
 
 int32_t qcb_normalize(qcb_handle h) {
+  GROUP_ALL(h, qcb_normalize(m));
   ENTER(h);
   return normalize_inplace(h);
 }
 
 int32_t qcb_state_dev_ptr(qcb_handle h, void** dev_ptr, uint64_t* local_count) {
+  if (h && h->is_group) return qcb_state_dev_ptr(h->members[0], dev_ptr, local_count);
   ENTER(h);
   if (dev_ptr) *dev_ptr = h->state;
   if (local_count) *local_count = h->local_count;
@@ -1096,6 +1416,7 @@ int32_t qcb_state_dev_ptr(qcb_handle h, void** dev_ptr, uint64_t* local_count) {
 }
 
 int32_t qcb_apply_ops(qcb_handle h, const qcb_op* ops, uint64_t n_ops) {
+  GROUP_ALL(h, qcb_apply_ops(m, ops, n_ops));
   ENTER(h);
   if (!ops && n_ops) return fail(h, QCB_ERR_INVALID, "null ops");
   RET(begin_timing(h));
@@ -1106,6 +1427,14 @@ int32_t qcb_apply_ops(qcb_handle h, const qcb_op* ops, uint64_t n_ops) {
 }
 
 int32_t qcb_norm2(qcb_handle h, double* out) {
+  if (h && h->is_group) {
+    if (!out) return fail(h, QCB_ERR_INVALID, "null argument");
+    std::vector<double> v(h->members.size(), 0.0);
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    int rc = group_run(h, [&](qcb_sim* m, int r) -> int { return qcb_norm2(m, &v[r]); });
+    *out = v[0];
+    return rc;
+  }
   ENTER(h);
   if (!out) return fail(h, QCB_ERR_INVALID, "null argument");
   double s = 0;
@@ -1115,6 +1444,15 @@ int32_t qcb_norm2(qcb_handle h, double* out) {
 }
 
 int32_t qcb_probabilities(qcb_handle h, uint64_t offset, uint64_t count, double* out) {
+  if (h && h->is_group) {
+    if (!out || offset + count > h->local_count) return fail(h, QCB_ERR_INVALID, "probabilities: range outside the state");
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    return group_run(h, [&](qcb_sim* m, int r) -> int {
+      uint64_t lo, lc, op; group_slice(m, r, offset, count, lo, lc, op);
+      if (!lc) { std::lock_guard<std::recursive_mutex> lk(m->mu); if (cudaSetDevice(m->device) != cudaSuccess) return QCB_ERR_CUDA; return restore_layout(m); }
+      return qcb_probabilities(m, lo, lc, out + op);
+    });
+  }
   ENTER(h);
   if (!out || offset + count > h->local_count) return fail(h, QCB_ERR_INVALID, "probabilities: range outside the local slice");
   if (!count) return QCB_OK;
@@ -1133,24 +1471,54 @@ int32_t qcb_probabilities(qcb_handle h, uint64_t offset, uint64_t count, double*
 }
 
 int32_t qcb_sample(qcb_handle h, const double* uniforms, uint64_t n_shots, uint64_t* outcomes) {
+  if (h && h->is_group) {
+    if (n_shots && (!uniforms || !outcomes)) return fail(h, QCB_ERR_INVALID, "null argument");
+    std::vector<std::vector<uint64_t>> tmp(h->members.size(), std::vector<uint64_t>(n_shots));
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    return group_run(h, [&](qcb_sim* m, int r) -> int { return qcb_sample(m, uniforms, n_shots, r == 0 ? outcomes : tmp[r].data()); });
+  }
   ENTER(h);
   if (n_shots && (!uniforms || !outcomes)) return fail(h, QCB_ERR_INVALID, "null argument");
   return sample_impl(h, uniforms, n_shots, outcomes);
 }
 
 int32_t qcb_measure_qubits(qcb_handle h, const int32_t* qubits, int32_t m, double u, int32_t* out_bits, double* out_prob) {
+  if (h && h->is_group) {
+    if (!qubits) return fail(h, QCB_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    return group_run(h, [&](qcb_sim* mb, int r) -> int {
+      std::vector<int32_t> bits(m > 0 ? m : 1); double pr = 0;
+      return qcb_measure_qubits(mb, qubits, m, u, r == 0 ? out_bits : bits.data(), r == 0 ? out_prob : &pr);
+    });
+  }
   ENTER(h);
   if (!qubits) return fail(h, QCB_ERR_INVALID, "null argument");
   return measure_qubits_impl(h, qubits, m, u, out_bits, out_prob, nullptr, true);
 }
 
 int32_t qcb_marginal_probabilities(qcb_handle h, const int32_t* qubits, int32_t m, double* out_probs) {
+  if (h && h->is_group) {
+    if (!qubits || !out_probs) return fail(h, QCB_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    return group_run(h, [&](qcb_sim* mb, int r) -> int {
+      std::vector<double> pr((size_t)1 << (m > 0 && m < 31 ? m : 0));
+      return qcb_marginal_probabilities(mb, qubits, m, r == 0 ? out_probs : pr.data());
+    });
+  }
   ENTER(h);
   if (!qubits || !out_probs) return fail(h, QCB_ERR_INVALID, "null argument");
   return measure_qubits_impl(h, qubits, m, 0.0, nullptr, nullptr, out_probs, false);
 }
 
 int32_t qcb_expect_pauli(qcb_handle h, const char* s, double* out) {
+  if (h && h->is_group) {
+    if (!s || !out) return fail(h, QCB_ERR_INVALID, "null argument");
+    std::vector<double> v(h->members.size(), 0.0);
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    int rc = group_run(h, [&](qcb_sim* m, int r) -> int { return qcb_expect_pauli(m, s, &v[r]); });
+    *out = v[0];
+    return rc;
+  }
   ENTER(h);
   if (!s || !out) return fail(h, QCB_ERR_INVALID, "null argument");
   const char* arr[1] = {s};
@@ -1159,6 +1527,16 @@ int32_t qcb_expect_pauli(qcb_handle h, const char* s, double* out) {
 
 int32_t qcb_expect_hamiltonian(qcb_handle h, const double* coeffs, const char* const* strings, uint64_t n_terms,
                                double* out_energy, double* out_terms) {
+  if (h && h->is_group) {
+    if ((n_terms && (!coeffs || !strings)) || !out_energy) return fail(h, QCB_ERR_INVALID, "null argument");
+    std::vector<double> e(h->members.size(), 0.0);
+    std::vector<std::vector<double>> t(h->members.size(), std::vector<double>(n_terms));
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    int rc = group_run(h, [&](qcb_sim* m, int r) -> int { return qcb_expect_hamiltonian(m, coeffs, strings, n_terms, &e[r], t[r].data()); });
+    *out_energy = e[0];
+    if (out_terms && n_terms) std::memcpy(out_terms, t[0].data(), n_terms * 8);
+    return rc;
+  }
   ENTER(h);
   if ((n_terms && (!coeffs || !strings)) || !out_energy) return fail(h, QCB_ERR_INVALID, "null argument");
   std::vector<double> t(n_terms);
@@ -1171,10 +1549,27 @@ int32_t qcb_expect_hamiltonian(qcb_handle h, const double* coeffs, const char* c
 }
 
 int32_t qcb_expect_1q(qcb_handle h, const double mat[8], int32_t target, double* out) {
+  if (h && h->is_group) {
+    if (!mat || !out) return fail(h, QCB_ERR_INVALID, "bad argument");
+    std::vector<double> v(h->members.size(), 0.0);
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    int rc = group_run(h, [&](qcb_sim* m, int r) -> int { return qcb_expect_1q(m, mat, target, &v[r]); });
+    *out = v[0];
+    return rc;
+  }
   ENTER(h);
   if (!mat || !out || target < 0 || target >= h->cfg.n_total) return fail(h, QCB_ERR_INVALID, "bad argument");
-  const int bit = h->perm[h->cfg.n_total - 1 - target];
-  if (bit >= h->cfg.n_local) return fail(h, QCB_ERR_UNSUPPORTED, "expect_1q on a global (rank) qubit: not supported in the sharded layout yet");
+  int bit = h->perm[h->cfg.n_total - 1 - target];
+  if (bit >= h->cfg.n_local) {
+    // the pair partner of every amplitude lives on another GPU: bring the qubit into the top local position with one qubit
+    // exchange (the layout permutation is tracked; nothing is moved back until a read needs the canonical order)
+    const int n = h->cfg.n_total, l = h->cfg.n_local - 1;
+    RET(do_exchange(h, bit, l));
+    std::vector<int> logical_of(n);
+    for (int b = 0; b < n; ++b) logical_of[h->perm[b]] = b;
+    std::swap(h->perm[logical_of[bit]], h->perm[logical_of[l]]);
+    bit = l;
+  }
   Mat2 O; std::memcpy(O.m, mat, sizeof O.m);
   const int grid = red_grid(h);
   RET(ensure_partials(h, (size_t)grid * 2));
@@ -1188,6 +1583,14 @@ int32_t qcb_expect_1q(qcb_handle h, const double mat[8], int32_t target, double*
 }
 
 int32_t qcb_fidelity(qcb_handle h, const double* host, uint64_t count, double* out) {
+  if (h && h->is_group) {
+    if (!host || !out || count != h->local_count) return fail(h, QCB_ERR_INVALID, "fidelity: count must equal 2^n_qubits");
+    std::vector<double> v(h->members.size(), 0.0);
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    int rc = group_run(h, [&](qcb_sim* m, int r) -> int { return qcb_fidelity(m, host + 2 * (uint64_t)r * m->local_count, m->local_count, &v[r]); });
+    *out = v[0];
+    return rc;
+  }
   ENTER(h);
   if (!host || !out || count != h->local_count) return fail(h, QCB_ERR_INVALID, "fidelity: count must equal the local slice size");
   RET(restore_layout(h));
@@ -1212,6 +1615,7 @@ int32_t qcb_fidelity(qcb_handle h, const double* host, uint64_t count, double* o
 }
 
 int32_t qcb_apply_kraus_1q(qcb_handle h, const double mat[8], int32_t target) {
+  GROUP_ALL(h, qcb_apply_kraus_1q(m, mat, target));
   ENTER(h);
   if (!mat || target < 0 || target >= h->cfg.n_total) return fail(h, QCB_ERR_INVALID, "bad argument");
   RET(begin_timing(h));
@@ -1221,6 +1625,21 @@ int32_t qcb_apply_kraus_1q(qcb_handle h, const double mat[8], int32_t target) {
   int rc = normalize_inplace(h);
   end_timing(h);
   return rc;
+}
+
+int32_t qcb_noisy_set_initial_state(qcb_handle h, const double* host, uint64_t count) {
+  if (h && h->is_group) return fail(h, QCB_ERR_UNSUPPORTED, "noisy trajectories run as independent replicas per GPU (use one single-GPU handle per device)");
+  ENTER(h);
+  if (!host) { if (h->noisy_init) { cudaFree(h->noisy_init); h->noisy_init = nullptr; } return QCB_OK; }
+  if (h->cfg.world > 1) return fail(h, QCB_ERR_UNSUPPORTED, "noisy trajectories run as independent replicas per GPU (world_size must be 1)");
+  if (count != h->local_count) return fail(h, QCB_ERR_INVALID, "noisy initial state: count must equal 2^n_qubits");
+  if (!h->noisy_init) {
+    cudaError_t e = cudaMalloc(&h->noisy_init, count * sizeof(double2));
+    if (e != cudaSuccess) { h->noisy_init = nullptr; return fail(h, QCB_ERR_NOMEM, "noisy initial state: cannot allocate a second state buffer"); }
+  }
+  CU(h, cudaMemcpyAsync(h->noisy_init, host, count * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return QCB_OK;
 }
 
 int32_t qcb_noisy_draws_per_shot(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb_noise_table* noise, uint64_t* out) {
@@ -1239,6 +1658,7 @@ int32_t qcb_noisy_draws_per_shot(qcb_handle h, const qcb_op* ops, uint64_t n_ops
 
 int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb_noise_table* noise, const double* uniforms,
                       uint64_t draws_per_shot, uint64_t n_shots, uint64_t* out_outcomes, double* traj_out, uint64_t max_traj) {
+  if (h && h->is_group) return fail(h, QCB_ERR_UNSUPPORTED, "noisy trajectories run as independent replicas per GPU (use one single-GPU handle per device)");
   ENTER(h);
   if ((n_ops && !ops) || (n_shots && (!uniforms || !out_outcomes))) return fail(h, QCB_ERR_INVALID, "null argument");
   if (h->cfg.world > 1) return fail(h, QCB_ERR_UNSUPPORTED, "noisy trajectories run as independent replicas per GPU (world_size must be 1)");
@@ -1295,8 +1715,13 @@ int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb
   for (const auto& grp : groups) {
     const double* u = uniforms + grp[0] * draws_per_shot;
     uint64_t di = 0;
-    CU(h, cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream));
-    CU(h, launch_set_amp(h->state, 0, 1.0, 0.0, h->stream));
+    if (h->noisy_init) {      // (or (:initial-state options) zero-state), hardware_simulator.clj:128-131
+      CU(h, cudaMemcpyAsync(h->state, h->noisy_init, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+      CU(h, cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream));
+      CU(h, launch_set_amp(h->state, 0, 1.0, 0.0, h->stream));
+    }
+    for (size_t b = 0; b < h->perm.size(); ++b) h->perm[b] = (int)b;
     std::vector<Gate> pending;
     std::string err;
     auto flush = [&]() -> int { if (pending.empty()) return QCB_OK; std::vector<Gate> g; g.swap(pending); return run_gates(h, std::move(g)); };
@@ -1357,6 +1782,16 @@ int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb
 }
 
 int32_t qcb_get_stats(qcb_handle h, qcb_stats* out) {
+  if (h && h->is_group) {      // member 0's counters; device times are the maximum over the members
+    if (!out) return fail(h, QCB_ERR_INVALID, "null argument");
+    std::vector<qcb_stats> st(h->members.size());
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    int rc = group_run(h, [&](qcb_sim* m, int r) -> int { return qcb_get_stats(m, &st[r]); });
+    if (rc != QCB_OK) return rc;
+    *out = st[0];
+    for (auto& q : st) { out->gpu_ms = std::max(out->gpu_ms, q.gpu_ms); out->exchange_ms = std::max(out->exchange_ms, q.exchange_ms); }
+    return QCB_OK;
+  }
   ENTER(h);
   if (!out) return fail(h, QCB_ERR_INVALID, "null argument");
   if (h->timing_pending) {
@@ -1366,17 +1801,27 @@ int32_t qcb_get_stats(qcb_handle h, qcb_stats* out) {
     h->stats.gpu_ms = ms;
     h->timing_pending = false;
   }
+  xtime_resolve(h);
   *out = h->stats;
   return QCB_OK;
 }
 
 int32_t qcb_timer_start(qcb_handle h) {
+  GROUP_ALL(h, qcb_timer_start(m));
   ENTER(h);
   CU(h, cudaEventRecord(h->tev0, h->stream));
   return QCB_OK;
 }
 
 int32_t qcb_timer_stop(qcb_handle h, double* out_ms) {
+  if (h && h->is_group) {
+    if (!out_ms) return fail(h, QCB_ERR_INVALID, "null argument");
+    std::vector<double> v(h->members.size(), 0.0);
+    std::lock_guard<std::recursive_mutex> _glk(h->mu);
+    int rc = group_run(h, [&](qcb_sim* m, int r) -> int { return qcb_timer_stop(m, &v[r]); });
+    *out_ms = *std::max_element(v.begin(), v.end());
+    return rc;
+  }
   ENTER(h);
   if (!out_ms) return fail(h, QCB_ERR_INVALID, "null argument");
   CU(h, cudaEventRecord(h->tev1, h->stream));
@@ -1504,6 +1949,11 @@ int32_t qcb_job_result_get(qcb_handle h, uint64_t id, qcb_job_result* r) {
   r->execution_time_ms = job->exec_ms;
   std::snprintf(r->error_message, sizeof r->error_message, "%s", job->error.c_str());
   if (r->status != QCB_JOB_COMPLETED) return QCB_OK;
+  if (job->payload_dropped) {
+    std::snprintf(r->error_message, sizeof r->error_message, "result payload released (only the 64 most recently finished jobs keep theirs)");
+    r->n_shots = 0; r->energy = job->energy; r->has_energy = job->has_energy;
+    return QCB_OK;
+  }
   if (r->outcomes) std::memcpy(r->outcomes, job->outcomes.data(), 8 * std::min<uint64_t>(r->n_shots, job->outcomes.size()));
   r->n_shots = job->outcomes.size();
   r->energy = job->energy; r->has_energy = job->has_energy;
@@ -1525,6 +1975,18 @@ int32_t qcb_cancel(qcb_handle h, uint64_t id, int32_t* out_status) {
   } else if (out_status) {
     *out_status = st;                        // :cannot-cancel: already finished
   }
+  return QCB_OK;
+}
+
+int32_t qcb_job_release(qcb_handle h, uint64_t id) {
+  if (!h) return QCB_ERR_INVALID;
+  std::unique_lock<std::mutex> lk(h->jmu);
+  auto it = h->jobs.find(id);
+  if (it == h->jobs.end()) return QCB_ERR_NOTFOUND;
+  const int st = it->second->status.load();
+  if (st == QCB_JOB_QUEUED || st == QCB_JOB_RUNNING) return fail(h, QCB_ERR_STATE, "job is still queued or running: cancel it first");
+  h->jobs.erase(it);
+  for (auto f = h->finished.begin(); f != h->finished.end(); ++f) if (*f == id) { h->finished.erase(f); break; }
   return QCB_OK;
 }
 
@@ -1565,6 +2027,7 @@ static int la_run(qcb_handle h, const std::vector<std::pair<const double*, uint6
 }
 
 int32_t qcb_la_matmul(qcb_handle h, const double* A, const double* B, uint64_t m, uint64_t k, uint64_t n, double* C) {
+  if (h && h->is_group) return qcb_la_matmul(h->members[0], A, B, m, k, n, C);
   ENTER(h);
   if (!A || !B || !C) return fail(h, QCB_ERR_INVALID, "null argument");
   return la_run(h, {{A, m * k}, {B, k * n}}, m * n, C, [&](std::vector<double2*>& d, double2* o) { return launch_la_matmul(d[0], d[1], m, k, n, o, h->stream); });
@@ -1573,22 +2036,26 @@ int32_t qcb_la_matvec(qcb_handle h, const double* A, const double* x, uint64_t r
   return qcb_la_matmul(h, A, x, rows, cols, 1, y);
 }
 int32_t qcb_la_kron(qcb_handle h, const double* A, uint64_t ar, uint64_t ac, const double* B, uint64_t br, uint64_t bc, double* C) {
+  if (h && h->is_group) return qcb_la_kron(h->members[0], A, ar, ac, B, br, bc, C);
   ENTER(h);
   if (!A || !B || !C) return fail(h, QCB_ERR_INVALID, "null argument");
   return la_run(h, {{A, ar * ac}, {B, br * bc}}, ar * ac * br * bc, C, [&](std::vector<double2*>& d, double2* o) { return launch_la_kron(d[0], ar, ac, d[1], br, bc, o, h->stream); });
 }
 int32_t qcb_la_outer(qcb_handle h, const double* x, const double* y, uint64_t n, uint64_t m, double* C) {
+  if (h && h->is_group) return qcb_la_outer(h->members[0], x, y, n, m, C);
   ENTER(h);
   if (!x || !y || !C) return fail(h, QCB_ERR_INVALID, "null argument");
   return la_run(h, {{x, n}, {y, m}}, n * m, C, [&](std::vector<double2*>& d, double2* o) { return launch_la_outer(d[0], d[1], n, m, o, h->stream); });
 }
 int32_t qcb_la_axpby(qcb_handle h, const double alpha[2], const double* x, const double beta[2], const double* y, uint64_t n, double* out) {
+  if (h && h->is_group) return qcb_la_axpby(h->members[0], alpha, x, beta, y, n, out);
   ENTER(h);
   if (!alpha || !x || !out || (y && !beta)) return fail(h, QCB_ERR_INVALID, "null argument");
   const double2 al{alpha[0], alpha[1]}, be{beta ? beta[0] : 0.0, beta ? beta[1] : 0.0};
   return la_run(h, {{x, n}, {y, n}}, n, out, [&](std::vector<double2*>& d, double2* o) { return launch_la_axpby(al, d[0], be, d[1], n, o, h->stream); });
 }
 int32_t qcb_la_inner(qcb_handle h, const double* x, const double* y, uint64_t n, double out[2]) {
+  if (h && h->is_group) return qcb_la_inner(h->members[0], x, y, n, out);
   ENTER(h);
   if (!x || !y || !out) return fail(h, QCB_ERR_INVALID, "null argument");
   const int grid = (int)std::min<uint64_t>((n + RED_THREADS - 1) / RED_THREADS, (uint64_t)red_grid(h));
@@ -1706,6 +2173,7 @@ int32_t qcb_la_condition_number(qcb_handle h, const double* A, uint64_t m, uint6
 #undef LA_ARGS
 #undef LA_LOCK
 int32_t qcb_la_trace(qcb_handle h, const double* A, uint64_t n, double out[2]) {
+  if (h && h->is_group) return qcb_la_trace(h->members[0], A, n, out);
   ENTER(h);
   if (!A || !out) return fail(h, QCB_ERR_INVALID, "null argument");
   RET(ensure_scratch(h, n * n * 16 + 256));
@@ -1745,9 +2213,25 @@ int run_job(qcb_sim* h, Job& job) {
   if (rc == QCB_OK) step(qcb_synchronize(h));
   h->active_cancel = nullptr;
   job.exec_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  // the inputs are not needed any more; the outputs of all but the 64 most recently finished jobs are dropped as well, so
+  // that a variational loop through the job API does not grow the host heap (status and timing stay queryable)
+  std::vector<qcb_op>().swap(job.ops); job.ext_d.clear(); job.ext_i.clear();
+  std::vector<double>().swap(job.initial); std::vector<double>().swap(job.uniforms);
   if (job.cancel.load()) job.status.store(QCB_JOB_CANCELLED);
   else if (rc != QCB_OK) { job.error = h->err; job.status.store(QCB_JOB_FAILED); }   // never throw out of the worker (ideal_simulator.clj:93-96)
   else job.status.store(QCB_JOB_COMPLETED);
+  {
+    std::unique_lock<std::mutex> lk(h->jmu);
+    h->finished.push_back(job.id);
+    while (h->finished.size() > 64) {
+      auto it = h->jobs.find(h->finished.front());
+      h->finished.pop_front();
+      if (it == h->jobs.end()) continue;
+      Job& old = *it->second;
+      std::vector<double>().swap(old.probs); std::vector<double>().swap(old.state); std::vector<uint64_t>().swap(old.outcomes);
+      old.payload_dropped = true;
+    }
+  }
   return rc;
 }
 

@@ -19,7 +19,7 @@ class QcbConfig(C.Structure):
                 ("strict_parity", C.c_int32), ("tile_bits", C.c_int32), ("low_bits", C.c_int32),
                 ("rank", C.c_int32), ("world_size", C.c_int32), ("nccl_unique_id", C.c_void_p),
                 ("max_stage_cost", C.c_int32), ("max_stage_rounds", C.c_int32), ("dense_mma", C.c_int32), ("tile_mover", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("n_gpus", C.c_int32), ("device_ids", C.c_int32 * 8), ("reserved", C.c_int32 * 3)]
 
 
 class QcbOp(C.Structure):
@@ -256,8 +256,12 @@ def _put_mat(o: QcbOp, mat) -> None:
 
 def make_config(n_qubits: int, *, device: int = -1, fusion: int = 1, strict_parity: int = 1, tile_bits: int = 0,
                 low_bits: int = 0, rank: int = 0, world_size: int = 1, nccl_unique_id=None,
-                max_stage_cost: int = 0, max_stage_rounds: int = 0, dense_mma: int = 0, tile_mover: int = 0) -> QcbConfig:
+                max_stage_cost: int = 0, max_stage_rounds: int = 0, dense_mma: int = 0, tile_mover: int = 0,
+                n_gpus: int = 0, device_ids=None) -> QcbConfig:
     cfg = QcbConfig()
+    cfg.n_gpus = n_gpus
+    for i in range(8):
+        cfg.device_ids[i] = device_ids[i] if device_ids is not None and i < len(device_ids) else -1
     cfg.n_qubits, cfg.device, cfg.fusion, cfg.strict_parity = n_qubits, device, fusion, strict_parity
     cfg.tile_bits, cfg.low_bits, cfg.rank, cfg.world_size = tile_bits, low_bits, rank, world_size
     cfg.nccl_unique_id = nccl_unique_id

@@ -52,6 +52,7 @@ def main():
             nrm = sv.norm2()
             energy = sv.expect_hamiltonian(H)
             energy_x = sv.expect_hamiltonian(HX)      # X / Y factors on the global qubits: localised by qubit exchanges
+            e1 = sv.expect_1q(np.array([[0, -1j], [1j, 0]]), 0)      # 1-qubit observable on the most global qubit
             shots = sv.sample(u)
             got = sv.get_state()
         lc = 1 << (n - p)
@@ -61,6 +62,8 @@ def main():
         assert abs(nrm - 1.0) <= 1e-10, f"rank {rank} n={n}: norm {nrm}"
         assert abs(energy - O.hamiltonian_expectation(H, want)) <= 1e-9, f"rank {rank} n={n}: energy"
         assert abs(energy_x - O.hamiltonian_expectation(HX, want)) <= 1e-9, f"rank {rank} n={n}: energy with X/Y on global qubits"
+        want_e1 = float(np.real(np.vdot(want, O.apply_single_qubit_gate(want, np.array([[0, -1j], [1j, 0]]), 0))))
+        assert abs(e1 - want_e1) <= 1e-10, f"rank {rank} n={n}: expect_1q on a global qubit {e1} vs {want_e1}"
         ref = O.sample_outcomes(want, u)
         dist_b = O.sample_boundary_distance(want, u)
         assert not ((shots != ref) & (dist_b > 1e-12)).any(), f"rank {rank} n={n}: shot outcomes differ"

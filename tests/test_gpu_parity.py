@@ -687,6 +687,31 @@ def test_multi_gpu_sharded_matches_oracle():
     assert out.returncode == 0 and "multi-gpu ok" in out.stdout, (out.stdout[-2000:], out.stderr[-3000:])
 
 
+def test_single_process_multi_gpu_handle():
+    """ONE handle (qcb_config.n_gpus) owning the whole sharded state, driven by one host process - the mode a JVM host uses
+    (SURVEY 8b).  tests/group_check.py in a subprocess on every GPU of the box; skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    ngpu = L.device_count()
+    world = 1 << (ngpu.bit_length() - 1)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "group_check.py"), str(world)], cwd=root, capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0 and "group ok" in out.stdout, (out.stdout[-2000:], out.stderr[-3000:])
+
+
+def test_multi_gpu_handle_rejects_bad_configs():
+    with pytest.raises(L.QcbError):
+        L.StateVector(10, n_gpus=3)
+    with pytest.raises(L.QcbError):
+        L.StateVector(10, n_gpus=2, world_size=2)
+    if L.device_count() < 8:
+        with pytest.raises(L.QcbError):
+            L.StateVector(12, n_gpus=8)
+
+
 def test_config2_grover_26q_full_size_property():
     """BASELINE.json configs[1] at its full size (26 qubits, 1 GiB state): after k oracle + diffusion operators the marked
     amplitude is sin((2k+1) theta) and every other amplitude cos((2k+1) theta) / sqrt(N-1), theta = asin(1/sqrt(N)) - a

@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for nm in names:
         assert hasattr(lib, nm), f"{nm} declared in include/qcb200.h but not exported"
     assert set(names) == set(L.EXPORTED_SYMBOLS), "ctypes prototypes out of sync with the header"
-    assert L.load().qcb_abi_version() == 1
+    assert L.load().qcb_abi_version() == 2
 
 
 def test_struct_layouts_match_header(tmp_path):
