@@ -59,6 +59,7 @@ def lib():
         _lib.orc_apply_1q_dense_kron.restype = C.c_int
         _lib.orc_apply_1q_dense_kron.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_set_num_threads.argtypes = [C.c_int]
     return _lib
 
 
@@ -146,3 +147,10 @@ def apply_1q_dense_kron(state: np.ndarray, target: int, mat: np.ndarray) -> np.n
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """Sets the OpenMP thread count of the C oracle (e.g. to os.cpu_count() under torchrun, which exports
+    OMP_NUM_THREADS=1) and returns what the runtime reports afterwards."""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()

@@ -232,6 +232,16 @@ int orc_apply_1q_dense_kron(double* state, int n, int target, const double mat[8
   return 0;
 }
 
+/* host threads the OpenMP loops use (torchrun exports OMP_NUM_THREADS=1 to its children: the bench's CPU legs reset it) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  extern void omp_set_num_threads(int);
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   extern int omp_get_max_threads(void);

@@ -317,6 +317,27 @@ __device__ __forceinline__ void k3_load_A(double (&A)[6], const double* __restri
   for (int i = 0; i < 6; ++i) A[i] = __ldg(mats + (size_t)var * K3_FRAG_DOUBLES + i * 32);
 }
 
+// Where a round's results go.  Shared tile: byte address tile_s + (lane offset ^ batch offset).  DIRECT (the last round of a
+// sweep, stage flag T_FLAG_DIRECT_STORE): straight to global memory from registers - amplitude offset (lane part ^ batch
+// part) from the tile's base; the batch parts come from gtab (built once per launch), the lane parts are per-round constants.
+struct K3Out {
+  uint32_t tile_s;            // shared tile
+  uint32_t lz, lw;            // lane byte offsets of result columns 0 / 1 in the shared tile
+  double2* gbase;             // DIRECT: tile base in global memory
+  uint64_t g0, g1;            // DIRECT: lane parts of the global amplitude offsets of result columns 0 / 1
+  const uint64_t* gtab;       // DIRECT: batch parts, indexed like btab
+};
+template <bool DIRECT>
+__device__ __forceinline__ void k3_store(const K3Out& o, uint32_t X, uint64_t G, double r0, double i0, double r1, double i1) {
+  if (DIRECT) {
+    __stcs(o.gbase + (o.g0 ^ G), double2{r0, i0});
+    __stcs(o.gbase + (o.g1 ^ G), double2{r1, i1});
+  } else {
+    sts_c128(o.tile_s + (o.lz ^ X), r0, i0);
+    sts_c128(o.tile_s + (o.lw ^ X), r1, i1);
+  }
+}
+
 // Batches btab[0..per) of one warp, all with the matrix variant held in A (P0 P1 N0 N1 R0 R1).  Software pipeline over
 // batches: in the steady state the warp issues, for batch i,   Re0(i) K0(i+1) Im0(i) K1(i+1) Re1(i) Im1(i)   - every
 // dependent pair is at least two tensor instructions apart (a DMMA.8x8x4 holds the pipe of the SM partition for 16 cycles,
@@ -329,9 +350,11 @@ struct K3State {
   double nr0, ni0, nr1, ni1;                  // batch i+1: raw loads
   double pr0, pr1, pi0, pi1;                  // batch i-1: results waiting for their stores
   uint32_t X, Xp, Xn;                         // swizzled byte offsets of batches i, i-1, i+1
+  uint64_t Gc, Gp;                            // DIRECT: global batch offsets of batches i, i-1
 };
-template <bool HAS1, bool HAS2, bool HASP>
-__device__ __forceinline__ void k3_iter(K3State& t, uint32_t tile_s, const uint4& lt, uint32_t x_next2, const double (&A)[6]) {
+template <bool HAS1, bool HAS2, bool HASP, bool DIRECT>
+__device__ __forceinline__ void k3_iter(K3State& t, uint32_t tile_s, const uint4& lt, uint32_t x_next2, const double (&A)[6],
+                                        const K3Out& out, uint64_t g_next) {
   double re0, re1, im0, im1, k0n = 0, k1n = 0, ns0 = 0, ns1 = 0, nd0 = 0, nd1 = 0;
   dmma_884_c(re0, re1, A[2], t.s0, t.K0, t.K1);
   if (HAS1) dmma_884_c(k0n, k1n, A[0], t.nr0, 0.0, 0.0);
@@ -345,18 +368,21 @@ __device__ __forceinline__ void k3_iter(K3State& t, uint32_t tile_s, const uint4
     lds_c128(tile_s + (lt.y ^ x_next2), t.nr1, t.ni1);
   }
   dmma_884_c(re0, re1, A[3], t.s1, re0, re1);
-  if (HASP) {
-    sts_c128(tile_s + (lt.z ^ t.Xp), t.pr0, t.pi0);
-    sts_c128(tile_s + (lt.w ^ t.Xp), t.pr1, t.pi1);
-  }
+  if (HASP) k3_store<DIRECT>(out, t.Xp, t.Gp, t.pr0, t.pi0, t.pr1, t.pi1);
   dmma_884_c(im0, im1, A[5], t.d1, im0, im1);
   t.pr0 = re0; t.pr1 = re1; t.pi0 = im0; t.pi1 = im1;
   t.Xp = t.X; t.X = t.Xn; t.Xn = x_next2;
+  if (DIRECT) { t.Gp = t.Gc; t.Gc = g_next; }
   t.K0 = k0n; t.K1 = k1n; t.s0 = ns0; t.s1 = ns1; t.d0 = nd0; t.d1 = nd1;
 }
-__device__ __forceinline__ void k3_batches(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[6]) {
+template <bool DIRECT>
+__device__ __forceinline__ void k3_batches(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[6],
+                                           const K3Out& out) {
   K3State t;
   t.X = btab[0] & DMMA_BATCH_OFF_MASK; t.Xp = t.X; t.Xn = t.X;
+  t.Gc = DIRECT ? out.gtab[0] : 0; t.Gp = t.Gc;
+  // g_next of iteration i = global offset of batch i+1 (it becomes Gc when the state rotates)
+  auto gn = [&](uint32_t i) -> uint64_t { return (DIRECT && i + 1u < per) ? out.gtab[i + 1u] : 0; };
   t.pr0 = t.pr1 = t.pi0 = t.pi1 = 0.0;
   {
     double r0, i0, r1, i1;
@@ -372,23 +398,22 @@ __device__ __forceinline__ void k3_batches(uint32_t tile_s, const uint4 lt, cons
     dmma_884_c(t.K0, t.K1, A[1], r1, t.K0, t.K1);
   }
   if (per >= 3u) {
-    k3_iter<true, true, false>(t, tile_s, lt, btab[2] & DMMA_BATCH_OFF_MASK, A);
+    k3_iter<true, true, false, DIRECT>(t, tile_s, lt, btab[2] & DMMA_BATCH_OFF_MASK, A, out, gn(0));
 #ifdef QCB_K3_UNROLL
 #pragma unroll 16
 #else
 #pragma unroll 1
 #endif
-    for (uint32_t i = 1; i + 2u < per; ++i) k3_iter<true, true, true>(t, tile_s, lt, btab[i + 2u] & DMMA_BATCH_OFF_MASK, A);
-    k3_iter<true, false, true>(t, tile_s, lt, 0u, A);
-    k3_iter<false, false, true>(t, tile_s, lt, 0u, A);
+    for (uint32_t i = 1; i + 2u < per; ++i) k3_iter<true, true, true, DIRECT>(t, tile_s, lt, btab[i + 2u] & DMMA_BATCH_OFF_MASK, A, out, gn(i));
+    k3_iter<true, false, true, DIRECT>(t, tile_s, lt, 0u, A, out, gn(per - 2u));
+    k3_iter<false, false, true, DIRECT>(t, tile_s, lt, 0u, A, out, 0);
   } else if (per == 2u) {
-    k3_iter<true, false, false>(t, tile_s, lt, 0u, A);
-    k3_iter<false, false, true>(t, tile_s, lt, 0u, A);
+    k3_iter<true, false, false, DIRECT>(t, tile_s, lt, 0u, A, out, gn(0));
+    k3_iter<false, false, true, DIRECT>(t, tile_s, lt, 0u, A, out, 0);
   } else {
-    k3_iter<false, false, false>(t, tile_s, lt, 0u, A);
+    k3_iter<false, false, false, DIRECT>(t, tile_s, lt, 0u, A, out, 0);
   }
-  sts_c128(tile_s + (lt.z ^ t.Xp), t.pr0, t.pi0);
-  sts_c128(tile_s + (lt.w ^ t.Xp), t.pr1, t.pi1);
+  k3_store<DIRECT>(out, t.Xp, t.Gp, t.pr0, t.pi0, t.pr1, t.pi1);
 }
 
 // ---- the same pipeline without register rotation: two operand sets that swap roles every batch (the loop body handles two
@@ -403,11 +428,17 @@ struct K3Set {
 };
 // one batch: c = its operands (K, s, d ready), n = the next batch's (raw loads in flight); HAS1 / HAS2 / HASP: a batch i+1 /
 // i+2 / i-1 exists.  pr / pi = the results (stored at the top of the NEXT call), pa0 / pa1 their shared-memory addresses.
-template <bool HAS1, bool HAS2, bool HASP>
+// DIRECT: pa0 / pa1 are unused, the results go to global memory at (lane part ^ pg), pg = the batch's global offset.
+template <bool HAS1, bool HAS2, bool HASP, bool DIRECT>
 __device__ __forceinline__ void k3_pp(K3Set& c, K3Set& n, double& pr0, double& pr1, double& pi0, double& pi1, uint32_t& pa0, uint32_t& pa1,
-                                      uint32_t tile_s, const uint4& lt, uint32_t xq, const double (&A)[6]) {
-  if (HASP) { sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1); }
-  pa0 = tile_s + (lt.z ^ c.X); pa1 = tile_s + (lt.w ^ c.X);
+                                      uint64_t& pg, uint32_t tile_s, const uint4& lt, uint32_t xq, const double (&A)[6],
+                                      const K3Out& out, uint64_t g_cur) {
+  if (HASP) {
+    if (DIRECT) { __stcs(out.gbase + (out.g0 ^ pg), double2{pr0, pi0}); __stcs(out.gbase + (out.g1 ^ pg), double2{pr1, pi1}); }
+    else { sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1); }
+  }
+  if (DIRECT) pg = g_cur;
+  else { pa0 = tile_s + (lt.z ^ c.X); pa1 = tile_s + (lt.w ^ c.X); }
   if (HAS2) {
     c.X = xq & DMMA_BATCH_OFF_MASK;
     lds_c128(tile_s + (lt.x ^ c.X), c.r0, c.i0);
@@ -425,10 +456,14 @@ __device__ __forceinline__ void k3_pp(K3Set& c, K3Set& n, double& pr0, double& p
   dmma_884_c(pi0, pi1, A[5], c.d1, pi0, pi1);
 }
 // per even and >= 4
-__device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[6]) {
+template <bool DIRECT>
+__device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[6],
+                                              const K3Out& out) {
   K3Set a, b;
   double pr0 = 0, pr1 = 0, pi0 = 0, pi1 = 0;
   uint32_t pa0 = 0, pa1 = 0;
+  uint64_t pg = 0;
+  auto gq = [&](uint32_t i) -> uint64_t { return DIRECT ? out.gtab[i] : 0; };
   a.X = btab[0] & DMMA_BATCH_OFF_MASK;
   b.X = btab[1] & DMMA_BATCH_OFF_MASK;
   lds_c128(tile_s + (lt.x ^ a.X), a.r0, a.i0);
@@ -440,33 +475,40 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
   dmma_884_c(a.K0, a.K1, A[0], a.r0, 0.0, 0.0);
   dmma_884_c(a.K0, a.K1, A[1], a.r1, a.K0, a.K1);
   // batches 0, 1
-  k3_pp<true, true, false>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  k3_pp<true, true, false, DIRECT>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(0));
   xq = btab[3];
-  k3_pp<true, true, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  k3_pp<true, true, true, DIRECT>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(1));
   // batches 2 .. per-3 (both look-aheads exist)
 #pragma unroll 1
   for (uint32_t i = 2; i + 2u < per; i += 2u) {
     xq = btab[i + 2u];
-    k3_pp<true, true, true>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+    k3_pp<true, true, true, DIRECT>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(i));
     xq = btab[i + 3u];
-    k3_pp<true, true, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+    k3_pp<true, true, true, DIRECT>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(i + 1u));
   }
-  k3_pp<true, false, true>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
-  k3_pp<false, false, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
-  sts_c128(pa0, pr0, pi0);
-  sts_c128(pa1, pr1, pi1);
+  k3_pp<true, false, true, DIRECT>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, 0u, A, out, gq(per - 2u));
+  k3_pp<false, false, true, DIRECT>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, 0u, A, out, gq(per - 1u));
+  if (DIRECT) { __stcs(out.gbase + (out.g0 ^ pg), double2{pr0, pi0}); __stcs(out.gbase + (out.g1 ^ pg), double2{pr1, pi1}); }
+  else { sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1); }
 }
 
 // One warp's share of a three-product round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
+template <bool DIRECT>
 __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
-                                             uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[6], uint32_t cur) {
+                                             uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[6], uint32_t cur,
+                                             K3Out out) {
   const uint4 lt = lane_tab_r[2u * lane];
+  out.tile_s = tile_s; out.lz = lt.z; out.lw = lt.w;
+  if (DIRECT) {   // lane parts of the global offsets: second table entry of the lane (written by the prologue for the last round)
+    const uint4 lg = lane_tab_r[2u * lane + 1u];
+    out.g0 = (uint64_t)lg.x | ((uint64_t)lg.y << 32); out.g1 = (uint64_t)lg.z | ((uint64_t)lg.w << 32);
+  }
   if ((btab[0] >> 20) == (btab[per - 1u] >> 20)) {
     // local condition bits are the top bits of the batch index: equal at both ends => one variant for the whole share
 #ifndef QCB_K3_ROTATE
-    if (per >= 4u && !(per & 1u)) { k3_batches_pp(tile_s, lt, btab, per, A); return; }
+    if (per >= 4u && !(per & 1u)) { k3_batches_pp<DIRECT>(tile_s, lt, btab, per, A, out); return; }
 #endif
-    k3_batches(tile_s, lt, btab, per, A);
+    k3_batches<DIRECT>(tile_s, lt, btab, per, A, out);
     return;
   }
   // the variant changes inside the share: runs of equal variants, each through the pipelined loop
@@ -476,7 +518,9 @@ __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_
     uint32_t e = b + 1u;
     while (e < per && (btab[e] >> 20) == (btab[b] >> 20)) ++e;
     if (v != cur) { k3_load_A(A, mats, v); cur = v; }
-    k3_batches(tile_s, lt, btab + b, e - b, A);
+    K3Out o2 = out;
+    o2.gtab = out.gtab + b;
+    k3_batches<DIRECT>(tile_s, lt, btab + b, e - b, A, o2);
     b = e;
   }
 }
@@ -493,7 +537,7 @@ __device__ unsigned g_mover_pause_ns;
 template <int KE>
 __device__ __forceinline__ void mover_fast(double2* __restrict__ state, const uint64_t* sprog, const StageCtx& sc, const uint64_t* hoff,
                                            uint32_t smem_s, uint32_t tile_bytes, uint32_t mt, uint32_t T, uint32_t nbuf,
-                                           uint64_t* full, uint64_t* done) {
+                                           uint64_t* full, uint64_t* done, bool direct) {
   const uint32_t low = mt & 15u;
   const uint32_t s_mt = swz(mt, 0u) << 4;
   const unsigned pause = g_mover_pause_ns;
@@ -502,6 +546,22 @@ __device__ __forceinline__ void mover_fast(double2* __restrict__ state, const ui
 #pragma unroll
   for (uint32_t k = 0; k < KE; ++k) roff[k] = (uint32_t)(hoff[(mt >> 4) + 8u * k] >> 4);
   PF_DECL;
+  if (direct) {
+    // the consumers write the results to global memory themselves (last round): this warpgroup only loads, as soon as the
+    // buffer's previous tile has been released
+    for (uint32_t j = 0; j < T; ++j) {
+      if (j >= nbuf) { const uint32_t s = j - nbuf; mbar_wait<true>(done + (s % nbuf), (s / nbuf) & 1u); PF_ADD(PF_M_WAIT_DONE); }
+      const uint64_t t = active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
+      const char* gb = reinterpret_cast<const char*>(state + tile_base(sprog, sc, t) + low);
+      const uint32_t bs = smem_s + (j % nbuf) * tile_bytes;
+#pragma unroll
+      for (uint32_t k = 0; k < KE; ++k) cp_async16_s(bs + (s_mt ^ (swz(128u * k, 0u) << 4)), gb + ((uint64_t)roff[k] << 8));
+      cp_async_mbar_arrive(full + (j % nbuf));
+      PF_ADD(PF_M_LOAD);
+    }
+    PF_TOTAL(PF_M_TOTAL);
+    return;
+  }
   for (uint32_t j = 0; j < T + nbuf - 1u; ++j) {
     if (j < T) {
       const uint64_t t = active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
@@ -583,6 +643,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
   uint32_t* batch_tab = reinterpret_cast<uint32_t*>(p);   p += (((size_t)4 * nbstride * sc.n_rounds) + 15u) & ~(size_t)15u;
   uint32_t* run_dst = reinterpret_cast<uint32_t*>(p);     p += ((size_t)(4u << (m - L)) + 15u) & ~(size_t)15u;
   uint2* rtab = reinterpret_cast<uint2*>(p);              p += ((size_t)8 * sc.n_rounds + 15u) & ~(size_t)15u;   // {hi_desc, matrix word offset}
+  uint64_t* gtab = reinterpret_cast<uint64_t*>(p);        p += (size_t)8 * nbstride;                             // direct store: global offset of every batch of the last round
   uint64_t* full = reinterpret_cast<uint64_t*>(p);
   uint64_t* done = full + nbuf;
 
@@ -628,12 +689,25 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
     decode_dmma(sprog, r, c);
     if (b < (1u << (c.n_grp - 3u))) batch_tab[idx] = dmma_batch_entry(c, b, m);
   }
+  // direct store (FORM 2 only): the last round writes to global memory; its batches' and lanes' global offsets
+  const bool direct = FORM == 2 && (stage_g[41] & T_FLAG_DIRECT_STORE) != 0 && !use_tma && sc.n_rounds > 0;
+  if (FORM == 2 && direct) {
+    const uint32_t rl = sc.n_rounds - 1u;
+    K3Ctx c;
+    decode_k3(sprog, rl, c);
+    auto goff = [&](uint32_t idx) -> uint64_t { return hoff[idx >> L] + (uint64_t)(idx & ((1u << L) - 1u)); };
+    for (uint32_t b = tid; b < (1u << (c.n_grp - 3u)); b += NTHREADS) gtab[b] = goff(k3_batch_base(c, b));
+    if (tid < 32u) {
+      const uint64_t a0 = goff(k3_lane_store_index(c, tid, 0u)), a1 = goff(k3_lane_store_index(c, tid, 1u));
+      lane_tab[2u * (rl * 32u + tid) + 1u] = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), (uint32_t)a1, (uint32_t)(a1 >> 32));
+    }
+  }
   __syncthreads();
 
   const uint32_t T = (uint32_t)((n_active - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
   const uint32_t lowmask = (1u << L) - 1u;
   // Register re-allocation between the warpgroups (setmaxnreg): the kernel is compiled for 168 registers per thread (384
-  // threads, one CTA per SM); the mover warpgroup hands registers to the two consumer warpgroups (104 / 200 per thread).
+  // threads, one CTA per SM); the mover warpgroup hands registers to the two consumer warpgroups (112 / 192 per thread).
 #ifndef QCB_NO_REALLOC
   constexpr bool REALLOC = (NCW == 8 && MOVER_WARPS == 4);      // measured: +6 % (5166 -> 5473 gates/s, profiles/r2a_ab.log)
 #else
@@ -641,7 +715,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
 #endif
 
   if (warp >= NCW) {
-  if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n");
+  if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;\n");
   if (use_tma) {
     // ---------------- mover (TMA): one warp, one bulk tensor copy per run
     if (warp > NCW) return;
@@ -675,8 +749,8 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
     PF_TOTAL(PF_M_TOTAL);
   } else if (L == 4u && LC == 0u && (m == 12u || m == 11u)) {
     // ---------------- mover warps, 64 KB / 32 KB tiles with 256-byte runs (the common case)
-    if (m == 12u) mover_fast<32>(state, sprog, sc, hoff, smem_u32(smem_raw), (uint32_t)tile_bytes, tid - NCT, T, nbuf, full, done);
-    else mover_fast<16>(state, sprog, sc, hoff, smem_u32(smem_raw), (uint32_t)tile_bytes, tid - NCT, T, nbuf, full, done);
+    if (m == 12u) mover_fast<32>(state, sprog, sc, hoff, smem_u32(smem_raw), (uint32_t)tile_bytes, tid - NCT, T, nbuf, full, done, direct);
+    else mover_fast<16>(state, sprog, sc, hoff, smem_u32(smem_raw), (uint32_t)tile_bytes, tid - NCT, T, nbuf, full, done, false);
   } else {
     // ---------------- mover warps (fallback: 16 bytes per thread through the LSU)
     const uint32_t mt = tid - NCT;
@@ -718,7 +792,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
   }
   } else {
     // ---------------- consumer groups
-    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;\n");
+    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;\n");
     const uint32_t grp = warp / WPG, gwarp = warp - grp * WPG, gtid = tid - grp * GT;
     const uint32_t smem_s = smem_u32(smem_raw);
     // every tensor-core round has m - 3 group bits: the batch geometry of this warp is a kernel constant
@@ -760,10 +834,18 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
           if (next_mma) prefetch(nj, nr);
           PF_ADD(PF_C_SETUP);
           if (active) {
-            if constexpr (FORM == 2)
-              k3_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                           mats, lane, Ac, curc);
-            else
+            if constexpr (FORM == 2) {
+              K3Out out;
+              out.gtab = gtab + b0; out.gbase = nullptr; out.g0 = out.g1 = 0;
+              if (direct && r + 1u == sc.n_rounds) {
+                out.gbase = state + tile_base(sprog, sc, active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x));
+                k3_round_run<true>(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
+                                   mats, lane, Ac, curc, out);
+              } else {
+                k3_round_run<false>(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
+                                    mats, lane, Ac, curc, out);
+              }
+            } else
               dmma_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
                              mats, lane, Ac, curc, dbg_bits);
           }
@@ -855,7 +937,8 @@ cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const u
   const size_t tile_n = (size_t)1 << sc.m, nbstride = tile_n >= 64 ? (tile_n >> 6) : 1;
   const size_t fixed = 8 * (size_t)((stage_words + 1u) & ~1u) + ((((size_t)8 << (sc.m - rb)) + 15) & ~(size_t)15) +
                        (size_t)1024 * sc.n_rounds + ((4 * nbstride * sc.n_rounds + 15) & ~(size_t)15) +
-                       ((((size_t)4 << (sc.m - rb)) + 15) & ~(size_t)15) + (((size_t)8 * sc.n_rounds + 15) & ~(size_t)15) + 16 * 8 + 1024;   // + run / round tables, mbarriers (nbuf <= 8), alignment slack
+                       ((((size_t)4 << (sc.m - rb)) + 15) & ~(size_t)15) + (((size_t)8 * sc.n_rounds + 15) & ~(size_t)15) + 8 * nbstride +
+                       16 * 8 + 1024;   // + run / round tables, direct-store batch offsets, mbarriers (nbuf <= 8), alignment slack
   const size_t limit = 227 * 1024;
   uint64_t grid = (uint64_t)num_sms;
   if (grid > n_active) grid = n_active;

@@ -75,6 +75,7 @@ Config config_from(const qcb_config& c) {
   k.dense_mma = (c.dense_mma == 2) ? 0 : 1;
   k.mma_form = (c.dense_mma == 3) ? 1 : 0;
   if (const char* e = std::getenv("QCB_MMA_FORM")) k.mma_form = std::atoi(e) ? 1 : 0;      // experiment knob
+  if (const char* e = std::getenv("QCB_DIRECT_STORE")) k.direct_store = std::atoi(e) ? 1 : 0;
   k.tma = (c.tile_mover == 2) ? 1 : 0;
   if (const char* e = std::getenv("QCB_THIN_DEFER")) k.thin_defer = std::atoi(e);            // experiment knob
   if (const char* e = std::getenv("QCB_WINDOW_SEARCH")) k.window_search = std::atoi(e);
@@ -1005,7 +1006,7 @@ void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const
   key.clear();
   key.reserve(16 + perm_in.size() + 6 * gates.size());
   const int c[] = {cfg.n_total, cfg.n_local, cfg.rank, cfg.world, cfg.tile_bits, cfg.low_bits, cfg.fusion, cfg.max_stage_cost,
-                   cfg.max_stage_rounds, cfg.dense_mma + 16 * cfg.mma_form, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer};
+                   cfg.max_stage_rounds, cfg.dense_mma + 16 * cfg.mma_form + 32 * cfg.direct_store, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer};
   for (int v : c) key.push_back((uint64_t)(int64_t)v);
   key.push_back(perm_in.size());
   for (int v : perm_in) key.push_back((uint64_t)v);
@@ -1177,6 +1178,32 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
     else form_rounds(cfg, st, eg, max_rounds, materialize);
     absorbed_out.swap(st.absorbed);
     st.absorbed.clear();
+    // Direct store: when the sweep ends in a three-product tensor-core round (and the tile has the default geometry the
+    // specialised mover handles), that round writes its results to global memory from registers.  Its store lanes no longer
+    // touch shared memory, so the two group bits that ride on the lane index for stores (grp_pos[1], grp_pos[2]) are
+    // re-chosen for coalescing instead of bank conflicts: the lowest free tile bits, so that the four lanes of a quad write
+    // 64 contiguous bytes.  (grp_pos[0] stays: it belongs to the loads, which still come from the shared tile.)
+    st.flags &= ~FLAG_DIRECT_STORE;
+    if (materialize && cfg.direct_store && !cfg.tma && m == 12 && L == 4 && !st.rounds.empty() && st.rounds.back().k3) {
+      bool all_mma = true;
+      for (const Round& r : st.rounds) all_mma = all_mma && r.dmma;
+      if (all_mma) {
+        Round& rd = st.rounds.back();
+        uint64_t cond = 0;
+        for (int p : rd.cond_pos) cond |= 1ULL << p;
+        std::vector<int> freeb;                                   // group bits that are not local condition bits, except grp_pos[0]
+        for (size_t i = 1; i < rd.grp_pos.size(); ++i) if (!((cond >> rd.grp_pos[i]) & 1)) freeb.push_back(rd.grp_pos[i]);
+        if (freeb.size() >= 2) {
+          std::sort(freeb.begin(), freeb.end());
+          std::vector<int> g;
+          g.push_back(rd.grp_pos[0]);
+          for (int p : freeb) g.push_back(p);                     // ascending: the two lowest become the store lane bits
+          for (size_t i = 1; i < rd.grp_pos.size(); ++i) if ((cond >> rd.grp_pos[i]) & 1) g.push_back(rd.grp_pos[i]);
+          rd.grp_pos = g;
+          st.flags |= FLAG_DIRECT_STORE;
+        }
+      }
+    }
     st.skip_mask = st.skip_val = 0; st.sweep_fraction = 1.0;
     if (eg.size() == 1 && absorbed_out.size() == 1 && !lead) {
       const Gate& e = eg[0];

@@ -80,6 +80,7 @@ enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_
 constexpr int STAGE_WORDS = 48;
 constexpr int ROUND_WORDS = 40;
 constexpr uint64_t FLAG_NEEDS_SUM = 1;     // epilogue: accumulate sum of amplitudes (for the next REFLECT)
+constexpr uint64_t FLAG_DIRECT_STORE = 2;  // the last round writes its results to global memory itself (tile_core.h: T_FLAG_DIRECT_STORE)
 
 // S_GROVER: one streaming pass a' = alpha * a + beta (the Grover diffusion, coefficients from the preceding sum) followed by
 // the sign flips of the phase oracles that come next, and - when another diffusion follows - the sum of the result, so that
@@ -134,6 +135,7 @@ struct Config {
   int max_stage_cost = 0;
   int max_stage_rounds = 0;
   int dense_mma = 1;           // rounds as dense 8x8 complex blocks on the fp64 tensor cores
+  int direct_store = 1;        // last tensor-core round of a sweep stores straight to HBM (no STS + mover read-back)
   int mma_form = 0;            // 0 = three-product form (six m8n8k4 steps per batch, 16-byte shared accesses);
                                // 1 = 16x16 real block (m16n8k16 = eight steps, 8-byte accesses), the round-1 kernel
   int round_yield_pct = 50;    // end a stage early when the next round would absorb less than this % of the stage's average round

@@ -27,6 +27,9 @@ namespace qcb {
 enum : uint32_t { TD_MAT1 = 0, TD_MAT2 = 1, TD_SWAPP = 2, TD_DMASK = 3, TD_DNEG = 4, TD_DPOP1 = 5, TD_AFFINE = 6,
                   TD_MAT1R = 7, TD_MAT1RI = 8, TD_PERMX = 9, TD_DENSE = 10 };
 constexpr int T_OP_WORDS = 16, T_STAGE_WORDS = 48, T_ROUND_WORDS = 40;
+// stage word [41] flags (plan.h): bit 1 = the last round (a three-product tensor-core round) stores its results straight to
+// global memory from registers; the mover then never writes the tile back
+constexpr uint64_t T_FLAG_DIRECT_STORE = 2;
 
 // Shared-memory layout of a tile (16-byte units), parameter c = stage word [43].
 // c = 0 (LSU mover, the default): every row bit >= 3 is XOR-folded onto the three chunk bits - any three index bits
@@ -471,6 +474,12 @@ QCB_HD void k3_lane_entry(const K3Ctx& c, uint32_t lane, uint32_t (&e)[4]) {
   for (uint32_t s = 0; s < 2; ++s) e[s] = swz(k3_group_offset(c, g) | k3_pattern_offset(c, q + 4u * s, c.kmap), c.c) << 4;
 #pragma unroll
   for (uint32_t i = 0; i < 2; ++i) e[2 + i] = swz(k3_group_offset(c, 2u * q + i) | k3_pattern_offset(c, g, c.mmap), c.c) << 4;
+}
+// tile-local (unswizzled) index of the amplitude a lane stores as result column i of a batch with base 0: where the last
+// round of a sweep writes it in global memory (direct store, stage flag T_FLAG_DIRECT_STORE)
+QCB_HD uint32_t k3_lane_store_index(const K3Ctx& c, uint32_t lane, uint32_t i) {
+  const uint32_t g = lane >> 2, q = lane & 3u;
+  return k3_group_offset(c, 2u * q + i) | k3_pattern_offset(c, g, c.mmap);
 }
 QCB_HD uint32_t k3_batch_base(const K3Ctx& c, uint32_t batch) {
   uint32_t o = 0;

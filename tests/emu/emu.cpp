@@ -84,8 +84,10 @@ int emu_stage_max_conflict(Emu* e, uint64_t si, int nthreads) {
     if (round_kind(st, r) == 2u) {
       // 16-byte accesses are served per quarter-warp (8 lanes x 16 B = 128 B): count lanes per 16-byte bank group
       K3Ctx c; decode_k3(st, r, c);
+      // the stores of a direct-store round go to global memory, not to the shared tile
+      const int n_which = ((st[41] & T_FLAG_DIRECT_STORE) && r + 1u == sc.n_rounds) ? 2 : 4;
       for (int quarter = 0; quarter < 4; ++quarter)
-        for (int which = 0; which < 4; ++which) {
+        for (int which = 0; which < n_which; ++which) {
           int cnt[8] = {0};
           for (uint32_t l = 0; l < 8; ++l) {
             uint32_t e[4];
@@ -169,8 +171,12 @@ static void emu_dmma_round(double2* tile, const uint64_t* st, uint32_t r, uint64
 
 // Software model of the three-product round (tile_core.h: K3Ctx; kernels.cu: k3_round_run), warp by warp, with the
 // mma.m8n8k4 .f64 fragment layouts: K = P Br, Re = K + N (Br + Bi), Im = K + R (Bi - Br).
-static void emu_k3_round(double2* tile, const uint64_t* st, uint32_t r, uint64_t ext_hi, uint32_t m, int nthreads) {
+// direct != nullptr: the round is the last one of a sweep with T_FLAG_DIRECT_STORE - results go to global memory at
+// direct[goff(tile-local index)] exactly like the kernel computes the address (XOR of the batch's and the lane's offsets)
+static void emu_k3_round(double2* tile, const uint64_t* st, uint32_t r, uint64_t ext_hi, uint32_t m, int nthreads,
+                         double2* direct = nullptr, const StageCtx* scp = nullptr) {
   K3Ctx c; decode_k3(st, r, c);
+  auto goff = [&](uint32_t idx) -> uint64_t { return hi_offset(st, *scp, idx >> scp->L) + (idx & ((1u << scp->L) - 1u)); };
   const uint32_t NW = nthreads / 32;
   const uint32_t nbatch = 1u << (c.n_grp - 3u);
   const uint32_t per = nbatch >= NW ? nbatch / NW : 1u;
@@ -207,7 +213,8 @@ static void emu_k3_round(double2* tile, const uint64_t* st, uint32_t r, uint64_t
       for (uint32_t lane = 0; lane < 32; ++lane)
         for (int i = 0; i < 2; ++i) {
           const double2 o{Re[lane / 4][2 * (lane % 4) + i], Im[lane / 4][2 * (lane % 4) + i]};
-          std::memcpy(tb + (X ^ lt[lane][2 + i]), &o, 16);
+          if (direct) direct[goff(k3_batch_base(c, bidx)) ^ goff(k3_lane_store_index(c, lane, (uint32_t)i))] = o;
+          else std::memcpy(tb + (X ^ lt[lane][2 + i]), &o, 16);
         }
     }
   }
@@ -235,7 +242,11 @@ int emu_run_tile_stage(Emu* e, uint64_t si, double* state, const double* dev_val
       tile[swz(i, sc.c)] = gs[base + hi_offset(st, sc, i >> sc.L) + (i & ((1u << sc.L) - 1u))];
     for (uint32_t r = 0; r < sc.n_rounds; ++r) {
       if (round_kind(st, r) == 1u) { emu_dmma_round(tile.data(), st, r, ext_hi, sc.m, nthreads); continue; }
-      if (round_kind(st, r) == 2u) { emu_k3_round(tile.data(), st, r, ext_hi, sc.m, nthreads); continue; }
+      if (round_kind(st, r) == 2u) {
+        const bool direct = (st[41] & T_FLAG_DIRECT_STORE) && r + 1u == sc.n_rounds;
+        emu_k3_round(tile.data(), st, r, ext_hi, sc.m, nthreads, direct ? gs + base : nullptr, &sc);
+        continue;
+      }
       RoundCtx rc; decode_round(st, r, rc);
       for (uint32_t tid = 0; tid < (uint32_t)nthreads; ++tid) {
         switch (rc.r) {
@@ -246,6 +257,7 @@ int emu_run_tile_stage(Emu* e, uint64_t si, double* state, const double* dev_val
         }
       }
     }
+    if (st[41] & T_FLAG_DIRECT_STORE) continue;      // the last round has written the tile itself
     for (uint32_t i = 0; i < tile_n; ++i)
       gs[base + hi_offset(st, sc, i >> sc.L) + (i & ((1u << sc.L) - 1u))] = tile[swz(i, sc.c)];
   }

@@ -537,7 +537,8 @@ def test_result_extraction_every_spec_on_device():
     sa = r["sample-results"][0]
     from qclojure_b200 import results as RS
     p_up = (1 + O.expectation_1q(psi, O.PAULI_Z, 2)) / 2
-    assert sa["sample-outcomes"] == RS.sample_eigenvalues({-1.0: 1 - p_up, 1.0: p_up}, u[:64])
+    # one draw stream per job: the :sample spec continues where the measurement shots stopped (no draw is used twice)
+    assert sa["sample-outcomes"] == RS.sample_eigenvalues({-1.0: 1 - p_up, 1.0: p_up}, u[128:192])
     # full-register dense observable through the P2 ops (result.clj:279-280)
     res = B.execute_circuit(sim, circ, {"result-specs": {"expectation": {"observables": [full]}}})
     assert abs(res["results"]["expectation-results"][0]["expectation-value"] - np.vdot(psi, full @ psi).real) <= TOL
