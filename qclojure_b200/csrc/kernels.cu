@@ -1008,8 +1008,16 @@ k_reduce(const double2* __restrict__ state, uint64_t count, int mode, double* __
   __shared__ double sm[2 * 32];
   double v[2] = {0.0, 0.0};
   const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
-  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
-    const double2 a = state[i];
+  uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  // streaming read: four independent 16-byte loads in flight per thread (one load per iteration leaves the memory
+  // system latency-bound at ~0.73 of the copy bandwidth, profiles/r1e_launches.csv)
+  for (; i + 3 * stride < count; i += 4 * stride) {
+    const double2 a0 = __ldcs(state + i), a1 = __ldcs(state + i + stride), a2 = __ldcs(state + i + 2 * stride), a3 = __ldcs(state + i + 3 * stride);
+    if (mode == 0) { v[0] += (a0.x + a1.x) + (a2.x + a3.x); v[1] += (a0.y + a1.y) + (a2.y + a3.y); }
+    else { v[0] += (a0.x * a0.x + a0.y * a0.y) + (a1.x * a1.x + a1.y * a1.y) + ((a2.x * a2.x + a2.y * a2.y) + (a3.x * a3.x + a3.y * a3.y)); }
+  }
+  for (; i < count; i += stride) {
+    const double2 a = __ldcs(state + i);
     if (mode == 0) { v[0] += a.x; v[1] += a.y; }
     else { v[0] += a.x * a.x + a.y * a.y; }
   }
@@ -1056,7 +1064,13 @@ __global__ void __launch_bounds__(RED_THREADS)
 k_scale_dev(double2* __restrict__ state, uint64_t count, const double* __restrict__ coef) {
   const double2 al{coef[0], coef[1]};
   const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
-  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) state[i] = cmul(al, state[i]);
+  uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  for (; i + 3 * stride < count; i += 4 * stride) {
+    const double2 a0 = __ldcs(state + i), a1 = __ldcs(state + i + stride), a2 = __ldcs(state + i + 2 * stride), a3 = __ldcs(state + i + 3 * stride);
+    __stcs(state + i, cmul(al, a0)); __stcs(state + i + stride, cmul(al, a1));
+    __stcs(state + i + 2 * stride, cmul(al, a2)); __stcs(state + i + 3 * stride, cmul(al, a3));
+  }
+  for (; i < count; i += stride) state[i] = cmul(al, state[i]);
 }
 cudaError_t launch_scale_dev(double2* state, uint64_t count, const double* coef, int grid, cudaStream_t s) {
   k_scale_dev<<<grid, RED_THREADS, 0, s>>>(state, count, coef);
@@ -1107,10 +1121,14 @@ cudaError_t launch_grover_step(double2* state, uint64_t count, const double* coe
 __global__ void __launch_bounds__(RED_THREADS)
 k_probabilities(const double2* __restrict__ state, uint64_t offset, uint64_t count, double* __restrict__ out) {
   const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
-  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
-    const double2 a = state[offset + i];
-    out[i] = a.x * a.x + a.y * a.y;
+  const double2* src = state + offset;
+  uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  for (; i + 3 * stride < count; i += 4 * stride) {
+    const double2 a0 = __ldcs(src + i), a1 = __ldcs(src + i + stride), a2 = __ldcs(src + i + 2 * stride), a3 = __ldcs(src + i + 3 * stride);
+    out[i] = a0.x * a0.x + a0.y * a0.y; out[i + stride] = a1.x * a1.x + a1.y * a1.y;
+    out[i + 2 * stride] = a2.x * a2.x + a2.y * a2.y; out[i + 3 * stride] = a3.x * a3.x + a3.y * a3.y;
   }
+  for (; i < count; i += stride) { const double2 a = src[i]; out[i] = a.x * a.x + a.y * a.y; }
 }
 cudaError_t launch_probabilities(const double2* state, uint64_t offset, uint64_t count, double* out, int grid, cudaStream_t s) {
   k_probabilities<<<grid, RED_THREADS, 0, s>>>(state, offset, count, out);
@@ -1132,7 +1150,13 @@ k_inner(const double2* __restrict__ phi, const double2* __restrict__ psi, uint64
   __shared__ double sm[2 * 32];
   double v[2] = {0.0, 0.0};
   const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
-  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
+  uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  for (; i + stride < count; i += 2 * stride) {
+    const double2 a0 = __ldcs(phi + i), b0 = __ldcs(psi + i), a1 = __ldcs(phi + i + stride), b1 = __ldcs(psi + i + stride);
+    v[0] += (a0.x * b0.x + a0.y * b0.y) + (a1.x * b1.x + a1.y * b1.y);
+    v[1] += (a0.x * b0.y - a0.y * b0.x) + (a1.x * b1.y - a1.y * b1.x);
+  }
+  for (; i < count; i += stride) {
     const double2 a = phi[i], b = psi[i];
     v[0] += a.x * b.x + a.y * b.y;
     v[1] += a.x * b.y - a.y * b.x;
@@ -1159,20 +1183,33 @@ k_expect_group(const double2* __restrict__ state, uint64_t count, uint64_t xmask
   for (int k = 0; k < EXPECT_TERMS; ++k) acc[k] = 0.0;
   const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
   if (xmask == 0) {
-    for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
-      const double2 a = state[i];
+    // the loads of four elements are issued before the first is consumed (streaming read, see k_reduce)
+    auto one = [&](uint64_t i, double2 a) {
       const double p = a.x * a.x + a.y * a.y;
       const uint64_t gi = i | ext_or;
 #pragma unroll
       for (int k = 0; k < EXPECT_TERMS; ++k)
         if (k < terms.n) acc[k] += (__popcll(gi & terms.zmask[k]) & 1) ? -p : p;
+    };
+    uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+    for (; i + 3 * stride < count; i += 4 * stride) {
+      const double2 a0 = __ldcs(state + i), a1 = __ldcs(state + i + stride), a2 = __ldcs(state + i + 2 * stride), a3 = __ldcs(state + i + 3 * stride);
+      one(i, a0); one(i + stride, a1); one(i + 2 * stride, a2); one(i + 3 * stride, a3);
     }
+    for (; i < count; i += stride) one(i, state[i]);
   } else {
     const uint64_t half = count >> 1;
     for (uint64_t h = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; h < half; h += stride) {
       const uint64_t i = ((h >> pivot) << (pivot + 1)) | (h & ((1ULL << pivot) - 1ULL));
       const uint64_t j = i ^ xmask;
-      const double2 ai = state[i], aj = state[j];
+      // the next pair of this thread is requested before this one is consumed
+      const uint64_t hn = h + stride;
+      if (hn < half) {
+        const uint64_t in = ((hn >> pivot) << (pivot + 1)) | (hn & ((1ULL << pivot) - 1ULL));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(state + in));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(state + (in ^ xmask)));
+      }
+      const double2 ai = __ldcs(state + i), aj = __ldcs(state + j);
       // conj(ai)*aj = (x, y);  conj(aj)*ai = (x, -y)
       const double x = ai.x * aj.x + ai.y * aj.y, y = ai.x * aj.y - ai.y * aj.x;
       const uint64_t gi = i | ext_or, gj = j | ext_or;
@@ -1205,14 +1242,20 @@ k_expect_1q(const double2* __restrict__ state, uint64_t count, int bit, Mat2 O, 
   __shared__ double sm[2 * 32];
   double v[2] = {0.0, 0.0};
   const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS, half = count >> 1;
-  for (uint64_t h = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; h < half; h += stride) {
-    const uint64_t i0 = ((h >> bit) << (bit + 1)) | (h & ((1ULL << bit) - 1ULL)), i1 = i0 | (1ULL << bit);
-    const double2 a0 = state[i0], a1 = state[i1];
+  auto one = [&](double2 a0, double2 a1) {
     const double2 b0 = cmul2(double2{O.m[0], O.m[1]}, a0, double2{O.m[2], O.m[3]}, a1);
     const double2 b1 = cmul2(double2{O.m[4], O.m[5]}, a0, double2{O.m[6], O.m[7]}, a1);
     v[0] += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y;
     v[1] += a0.x * b0.y - a0.y * b0.x + a1.x * b1.y - a1.y * b1.x;
+  };
+  auto idx0 = [&](uint64_t h) { return ((h >> bit) << (bit + 1)) | (h & ((1ULL << bit) - 1ULL)); };
+  uint64_t h = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  for (; h + stride < half; h += 2 * stride) {          // two pairs = four 16-byte loads in flight
+    const uint64_t i0 = idx0(h), j0 = idx0(h + stride);
+    const double2 a0 = __ldcs(state + i0), a1 = __ldcs(state + (i0 | (1ULL << bit))), c0 = __ldcs(state + j0), c1 = __ldcs(state + (j0 | (1ULL << bit)));
+    one(a0, a1); one(c0, c1);
   }
+  for (; h < half; h += stride) { const uint64_t i0 = idx0(h); one(state[i0], state[i0 | (1ULL << bit)]); }
   block_sum<2>(v, sm);
   if (threadIdx.x == 0) { partials[2 * blockIdx.x] = v[0]; partials[2 * blockIdx.x + 1] = v[1]; }
 }
@@ -1224,26 +1267,70 @@ cudaError_t launch_expect_1q(const double2* state, uint64_t count, int bit, cons
 // ------------------------------------------------------------------ partial measurement (domain/state.clj:946-1014)
 // key(i) = sum_k bit(i, pos[k]) << k ; histogram of |a|^2 over keys, per block in shared memory.
 // partials: [grid][2^m]
+// Deterministic (no floating-point atomics): every warp owns a private histogram in shared memory; inside a warp the lanes
+// that hold the same key are found with match.any, their values are added up in ascending lane order by the group's lowest
+// lane, which alone updates the bin - so no two lanes ever write one bin, and the order of every addition is fixed.  The
+// warps' histograms are added in warp order.  blockDim = 32 * W with W * 2^m * 8 bytes <= 64 KB (W = 8 up to m = 10,
+// 2 at m = 12).  Optional filter (fl.n > 0): only amplitudes whose bits fl.pos match fval are counted (second pass of a
+// measurement of more than 12 qubits).
 __global__ void __launch_bounds__(RED_THREADS)
-k_marginal(const double2* __restrict__ state, uint64_t count, uint64_t ext_or, BitList bl, double* __restrict__ partials) {
+k_marginal(const double2* __restrict__ state, uint64_t count, uint64_t ext_or, BitList bl, BitList fl, uint32_t fval,
+           double* __restrict__ partials) {
   extern __shared__ double hist[];
-  const uint32_t nk = 1u << bl.n;
-  for (uint32_t k = threadIdx.x; k < nk; k += RED_THREADS) hist[k] = 0.0;
+  const uint32_t nk = 1u << bl.n, nthreads = blockDim.x, nw = nthreads >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  for (uint32_t k = threadIdx.x; k < nk * nw; k += nthreads) hist[k] = 0.0;
   __syncthreads();
-  const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
-  for (uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {
-    const double2 a = state[i];
-    const uint64_t gi = i | ext_or;
-    uint32_t key = 0;
+  double* mine = hist + (size_t)wid * nk;
+  const uint64_t stride = (uint64_t)gridDim.x * nthreads;
+  const uint64_t rounds = (count + stride - 1) / stride;           // every lane runs the same number of iterations (warp collectives)
+  for (uint64_t it = 0; it < rounds; ++it) {
+    const uint64_t i = it * stride + (uint64_t)blockIdx.x * nthreads + threadIdx.x;
+    uint32_t key = 0xffffffffu;
+    double p = 0.0;
+    if (i < count) {
+      const double2 a = __ldcs(state + i);
+      const uint64_t gi = i | ext_or;
+      uint32_t f = 0;
+      for (int k = 0; k < fl.n; ++k) f |= (uint32_t)((gi >> fl.pos[k]) & 1ULL) << k;
+      if (f == fval) {
+        key = 0;
 #pragma unroll 4
-    for (int k = 0; k < bl.n; ++k) key |= (uint32_t)((gi >> bl.pos[k]) & 1ULL) << k;
-    atomicAdd(&hist[key], a.x * a.x + a.y * a.y);
+        for (int k = 0; k < bl.n; ++k) key |= (uint32_t)((gi >> bl.pos[k]) & 1ULL) << k;
+        p = a.x * a.x + a.y * a.y;
+      }
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    const uint32_t leader = __ffs(peers) - 1u;
+    double sum = 0.0;
+    for (uint32_t rest = peers; rest;) {                          // ascending lane order; every lane walks its own group
+      const uint32_t src = __ffs(rest) - 1u;
+      rest &= rest - 1u;
+      // all lanes must take part in every shuffle of the warp: iterate over the union of the groups' walks
+      sum += __shfl_sync(peers, p, src);
+    }
+    if (lane == leader && key != 0xffffffffu) mine[key] += sum;
+    __syncwarp();
   }
   __syncthreads();
-  for (uint32_t k = threadIdx.x; k < nk; k += RED_THREADS) partials[(uint64_t)blockIdx.x * nk + k] = hist[k];
+  for (uint32_t k = threadIdx.x; k < nk; k += nthreads) {
+    double t = 0.0;
+    for (uint32_t w = 0; w < nw; ++w) t += hist[(size_t)w * nk + k];
+    partials[(uint64_t)blockIdx.x * nk + k] = t;
+  }
 }
-cudaError_t launch_marginal(const double2* state, uint64_t count, uint64_t ext_or, const BitList& bl, double* partials, int grid, cudaStream_t s) {
-  k_marginal<<<grid, RED_THREADS, sizeof(double) << bl.n, s>>>(state, count, ext_or, bl, partials);
+cudaError_t launch_marginal(const double2* state, uint64_t count, uint64_t ext_or, const BitList& bl, const BitList& fl, uint32_t fval,
+                            double* partials, int grid, cudaStream_t s) {
+  int nw = (int)(8192u >> bl.n);
+  nw = nw < 1 ? 1 : (nw > 8 ? 8 : nw);
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(configured.load() & (1ULL << (dev & 63)))) {
+    cudaError_t e = cudaFuncSetAttribute(k_marginal, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    configured.fetch_or(1ULL << (dev & 63));
+  }
+  k_marginal<<<grid, 32 * nw, (sizeof(double) << bl.n) * nw, s>>>(state, count, ext_or, bl, fl, fval, partials);
   return cudaGetLastError();
 }
 
@@ -1256,9 +1343,8 @@ k_collapse(double2* __restrict__ state, uint64_t count, uint64_t ext_or, BitList
     uint32_t key = 0;
 #pragma unroll 4
     for (int k = 0; k < bl.n; ++k) key |= (uint32_t)((gi >> bl.pos[k]) & 1ULL) << k;
-    double2 a = state[i];
-    if (key == sel) { a.x *= factor; a.y *= factor; } else { a.x = 0.0; a.y = 0.0; }
-    state[i] = a;
+    if (key == sel) { double2 a = state[i]; a.x *= factor; a.y *= factor; state[i] = a; }
+    else state[i] = double2{0.0, 0.0};                       // no read needed for the amplitudes that vanish
   }
 }
 cudaError_t launch_collapse(double2* state, uint64_t count, uint64_t ext_or, const BitList& bl, uint32_t sel, double factor, int grid, cudaStream_t s) {

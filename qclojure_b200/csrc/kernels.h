@@ -11,7 +11,8 @@ constexpr int SAMPLE_THREADS = 256;
 constexpr int SAMPLE_PER_THREAD = 16;
 constexpr int SAMPLE_CHUNK = SAMPLE_THREADS * SAMPLE_PER_THREAD;   // amplitudes per sampling chunk
 constexpr int EXPECT_TERMS = 16;                                   // Pauli terms per expectation pass
-constexpr int MAX_MEASURE_BITS = 12;
+constexpr int MAX_MEASURE_BITS = 24;                               // qubits per :measure op (two histogram passes of <= 12 bits)
+constexpr int MAX_HIST_BITS = 12;                                  // bins of one marginal pass: 2^12 doubles per warp in shared memory
 
 struct ExpectTerms { int n; uint64_t zmask[EXPECT_TERMS]; double pr[EXPECT_TERMS], pi[EXPECT_TERMS]; };
 struct Mat2 { double m[8]; };
@@ -47,7 +48,8 @@ cudaError_t launch_inner(const double2* phi, const double2* psi, uint64_t count,
 cudaError_t launch_expect_group(const double2* state, uint64_t count, uint64_t xmask, int pivot, uint64_t ext_or,
                                 const ExpectTerms& terms, double* partials, int grid, cudaStream_t s);
 cudaError_t launch_expect_1q(const double2* state, uint64_t count, int bit, const Mat2& O, double* partials, int grid, cudaStream_t s);
-cudaError_t launch_marginal(const double2* state, uint64_t count, uint64_t ext_or, const BitList& bl, double* partials, int grid, cudaStream_t s);
+cudaError_t launch_marginal(const double2* state, uint64_t count, uint64_t ext_or, const BitList& bl, const BitList& filter, uint32_t filter_val,
+                            double* partials, int grid, cudaStream_t s);
 cudaError_t launch_collapse(double2* state, uint64_t count, uint64_t ext_or, const BitList& bl, uint32_t sel, double factor, int grid, cudaStream_t s);
 cudaError_t launch_chunk_sums(const double2* state, uint64_t count, double* sums, int grid, cudaStream_t s);
 cudaError_t launch_scan_inclusive(double* v, uint64_t n, cudaStream_t s);

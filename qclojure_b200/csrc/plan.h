@@ -135,7 +135,8 @@ struct Config {
   int max_stage_cost = 0;
   int max_stage_rounds = 0;
   int dense_mma = 1;           // rounds as dense 8x8 complex blocks on the fp64 tensor cores
-  int direct_store = 1;        // last tensor-core round of a sweep stores straight to HBM (no STS + mover read-back)
+  int direct_store = 0;        // last tensor-core round of a sweep stores straight to HBM (no STS + mover read-back); measured
+                               // neutral to slightly slower (profiles/r2c_ab.log: 5423 vs 5521 gates/s), hence off (QCB_DIRECT_STORE=1)
   int mma_form = 0;            // 0 = three-product form (six m8n8k4 steps per batch, 16-byte shared accesses);
                                // 1 = 16x16 real block (m16n8k16 = eight steps, 8-byte accesses), the round-1 kernel
   int round_yield_pct = 50;    // end a stage early when the next round would absorb less than this % of the stage's average round

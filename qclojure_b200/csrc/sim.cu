@@ -729,40 +729,76 @@ int norm_squared(qcb_sim* h, double* out) {
   return QCB_OK;
 }
 
-// measure-specific-qubits (domain/state.clj:946-1014)
+// measure-specific-qubits (domain/state.clj:946-1014).  Up to MAX_HIST_BITS measured qubits: one histogram pass.  Up to
+// MAX_MEASURE_BITS: two passes - the outcome enumeration (bit i of the outcome index <-> i-th listed qubit, ascending index)
+// is major in the bits above MAX_HIST_BITS, so the draw first selects those from their marginal and then the low bits from
+// the marginal restricted to that choice: the same "first outcome with cumulative >= r" as one pass over all 2^m outcomes.
 int measure_qubits_impl(qcb_sim* h, const int32_t* qubits, int m, double u, int32_t* out_bits, double* out_prob,
                         double* out_probs, bool collapse) {
   const int n = h->cfg.n_total;
   if (m <= 0 || m > MAX_MEASURE_BITS) return fail(h, QCB_ERR_UNSUPPORTED, "measure: 1.." + std::to_string(MAX_MEASURE_BITS) + " qubits per :measure op supported");
-  BitList bl; bl.n = m;
+  if (out_probs && m > MAX_HIST_BITS) return fail(h, QCB_ERR_UNSUPPORTED, "marginal distribution over more than " + std::to_string(MAX_HIST_BITS) + " qubits: not supported");
+  BitList all; all.n = m;
   for (int k = 0; k < m; ++k) {
     if (qubits[k] < 0 || qubits[k] >= n) return fail(h, QCB_ERR_INVALID, "measure: qubit out of range");
-    bl.pos[k] = h->perm[n - 1 - qubits[k]];
+    all.pos[k] = h->perm[n - 1 - qubits[k]];
   }
   const uint64_t ext_or = (uint64_t)h->cfg.rank << h->cfg.n_local;
   const int grid = std::min(red_grid(h), 296);
-  const uint32_t nk = 1u << m;
-  RET(ensure_partials(h, (size_t)grid * nk + nk));
-  CU(h, launch_marginal(h->state, h->local_count, ext_or, bl, h->d_partials, grid, h->stream));
-  double* d_out = h->d_partials + (size_t)grid * nk;
-  CU(h, launch_finalize(h->d_partials, grid, nk, 0, 0.0, d_out, h->stream));
-  RET(allreduce_sum(h, d_out, nk));
-  h->stats.n_kernel_launches += 2;
-  std::vector<double> probs(nk);
-  RET(read_back(h, d_out, nk * sizeof(double), probs.data()));
-  if (out_probs) std::memcpy(out_probs, probs.data(), nk * sizeof(double));
-  if (!collapse) return QCB_OK;
-  // select: r = total * u ; first outcome (enumeration order) with cum >= r, clamped (state.clj:979-985)
-  double total = 0;
-  std::vector<double> cum(nk);
-  for (uint32_t k = 0; k < nk; ++k) { total += probs[k]; cum[k] = total; }
-  const double r = total * u;
-  uint32_t sel = 0;
-  while (sel < nk && cum[sel] < r) ++sel;
-  if (sel >= nk) sel = nk - 1;
-  const double p = probs[sel];
+  // one histogram pass over `bits` (restricted to filter == fval): probabilities of the 2^bits.n outcomes, summed over ranks
+  auto pass = [&](const BitList& bits, const BitList& filter, uint32_t fval, std::vector<double>& probs) -> int {
+    const uint32_t nk = 1u << bits.n;
+    RET(ensure_partials(h, (size_t)grid * nk + nk));
+    CU(h, launch_marginal(h->state, h->local_count, ext_or, bits, filter, fval, h->d_partials, grid, h->stream));
+    double* d_out = h->d_partials + (size_t)grid * nk;
+    CU(h, launch_finalize(h->d_partials, grid, nk, 0, 0.0, d_out, h->stream));
+    RET(allreduce_sum(h, d_out, nk));
+    h->stats.n_kernel_launches += 2;
+    probs.resize(nk);
+    return read_back(h, d_out, nk * sizeof(double), probs.data());
+  };
+  // first outcome (enumeration order) with cumulative >= r, clamped (state.clj:979-985); returns the cumulative before it
+  auto pick = [](const std::vector<double>& probs, double r, double& before) -> uint32_t {
+    double cum = 0; uint32_t sel = 0; before = 0;
+    for (; sel < probs.size(); ++sel) { if (cum + probs[sel] >= r) break; cum += probs[sel]; }
+    if (sel >= probs.size()) { sel = (uint32_t)probs.size() - 1; cum -= probs[sel]; }
+    before = cum;
+    return sel;
+  };
+  BitList none; none.n = 0;
+  uint32_t sel = 0; double p = 0;
+  if (m <= MAX_HIST_BITS) {
+    std::vector<double> probs;
+    RET(pass(all, none, 0, probs));
+    if (out_probs) std::memcpy(out_probs, probs.data(), probs.size() * sizeof(double));
+    if (!collapse) return QCB_OK;
+    double total = 0;
+    for (double v : probs) total += v;
+    // r = total * u ; first outcome with cum >= r where cum is the running sum INCLUDING the outcome (the reference's loop)
+    const double r = total * u;
+    double cum = 0;
+    while (sel < probs.size() && (cum += probs[sel]) < r) ++sel;
+    if (sel >= probs.size()) sel = (uint32_t)probs.size() - 1;
+    p = probs[sel];
+  } else {
+    BitList lo, hi; lo.n = MAX_HIST_BITS; hi.n = m - MAX_HIST_BITS;
+    for (int k = 0; k < lo.n; ++k) lo.pos[k] = all.pos[k];
+    for (int k = 0; k < hi.n; ++k) hi.pos[k] = all.pos[MAX_HIST_BITS + k];
+    std::vector<double> ph, pl;
+    RET(pass(hi, none, 0, ph));
+    double total = 0;
+    for (double v : ph) total += v;
+    const double r = total * u;
+    double before = 0;
+    const uint32_t kh = pick(ph, r, before);
+    RET(pass(lo, hi, kh, pl));
+    double b2 = 0;
+    const uint32_t kl = pick(pl, r - before, b2);
+    sel = kl | (kh << MAX_HIST_BITS);
+    p = pl[kl];
+  }
   const double factor = p > 0 ? 1.0 / std::sqrt(p) : 1.0;
-  CU(h, launch_collapse(h->state, h->local_count, ext_or, bl, sel, factor, red_grid(h), h->stream));
+  CU(h, launch_collapse(h->state, h->local_count, ext_or, all, sel, factor, red_grid(h), h->stream));
   h->stats.n_kernel_launches += 1;
   if (out_bits) for (int k = 0; k < m; ++k) out_bits[k] = (sel >> k) & 1;
   if (out_prob) *out_prob = p;

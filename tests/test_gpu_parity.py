@@ -380,6 +380,45 @@ def test_partial_measurement_collapse():
     assert abs(got[3] - 1) <= TOL
 
 
+def test_direct_store_variant_matches_oracle(monkeypatch):
+    """The optional direct-store variant of the tile kernel (QCB_DIRECT_STORE=1: the last round of a sweep writes to HBM from
+    registers) against the C oracle."""
+    monkeypatch.setenv("QCB_DIRECT_STORE", "1")
+    for n in (14, 22):
+        circ = C.random_brickwork_circuit(n, 12)
+        want = CO.apply_circuit(circ)
+        with L.StateVector(n) as sv:
+            sv.apply_circuit(circ)
+            assert np.max(np.abs(sv.get_state() - want)) <= TOL
+
+
+def test_measure_many_qubits_two_pass_and_determinism():
+    """:measure of more than 12 qubits (two histogram passes: the bits above 12 of the outcome enumeration first, then the
+    low 12 restricted to that choice) against the oracle's single enumeration, and run-to-run bit-identity of the marginal
+    histogram (no floating-point atomics: per-warp private bins, fixed addition order)."""
+    n = 16
+    init = _rand_state(n, 45)
+    rng = np.random.default_rng(46)
+    for m, u in ((13, 0.31), (14, 0.77), (16, 0.05), (16, 0.999)):
+        qubits = [int(q) for q in rng.permutation(n)[:m]]
+        bits, col, _probs = O.measure_specific_qubits(init, qubits, u)
+        with L.StateVector(n) as sv:
+            sv.set_state(init)
+            gbits, gp = sv.measure_qubits(qubits, u)
+            assert gbits == bits, (m, u)
+            assert np.max(np.abs(sv.get_state() - col)) <= TOL
+            assert abs(sv.norm2() - 1.0) <= TOL
+    with L.StateVector(n) as sv:
+        sv.set_state(init)
+        for qubits in ([0, 5, 9], list(range(12)), [15, 3, 8, 1, 12, 7, 0]):
+            a = sv.marginal_probabilities(qubits)
+            b = sv.marginal_probabilities(qubits)
+            assert np.array_equal(a, b)                                    # bit-identical, not just close
+            assert np.max(np.abs(a - np.array(O.measure_specific_qubits(init, qubits, 0.5)[2]))) <= TOL
+        with pytest.raises(L.QcbError):
+            sv.marginal_probabilities(list(range(13)))                     # a 2^13-entry distribution is not offered
+
+
 # ------------------------------------------------------------------ expectation values
 def test_pauli_and_hamiltonian_expectations():
     n = 12

@@ -277,3 +277,29 @@ def test_tile_layout_is_linear_bijection():
                     rows = img[h:h + (1 << c)] >> 3
                     assert rows.min() == img[h] >> 3 and rows.max() - rows.min() == (1 << (c - 3)) - 1
                     assert img[h] % 8 == (img[h] >> 3) % 8          # chunk = 0 ^ (row address & 7): hardware 128B swizzle
+
+
+def test_direct_store_last_round(monkeypatch):
+    """QCB_DIRECT_STORE=1: the last three-product round of a sweep writes to global memory itself (stage flag bit 1; the
+    emulator follows the kernel's address arithmetic: batch offset XOR lane offset) - same amplitudes as the oracle."""
+    import ctypes as CT
+    from oracle import c_oracle as CO
+    monkeypatch.setenv("QCB_DIRECT_STORE", "1")
+    for n in (13, 16):
+        circ = C.random_brickwork_circuit(n, 8)
+        p = E.EmuPlan(n, circ["operations"])
+        nw = E.lib().emu_program_words(p.h, None, 0)
+        buf = (CT.c_uint64 * nw)()
+        E.lib().emu_program_words(p.h, buf, nw)
+        w = np.frombuffer(buf, dtype=np.uint64)
+        pos, flagged, tiles = 4, 0, 0
+        for _s in range(int(w[1])):
+            kind = int(w[pos]); pos += 2
+            if kind != 0:
+                continue
+            tiles += 1
+            flagged += (int(w[pos + 41]) >> 1) & 1
+            pos += int(w[pos + 40])
+        assert tiles > 0 and flagged == tiles
+        got = E.run_world(n, circ["operations"])
+        assert np.max(np.abs(got - CO.apply_circuit(circ))) <= 1e-10
