@@ -1184,12 +1184,18 @@ k_expect_group(const double2* __restrict__ state, uint64_t count, uint64_t xmask
   const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
   if (xmask == 0) {
     // the loads of four elements are issued before the first is consumed (streaming read, see k_reduce)
+    // parity(gi & z) with ONE 32-bit POPC per term: the two halves are folded first (POPC issues at a quarter of the integer
+    // rate and was what bounded this loop: 1.3 TB/s with two POPCs per term, profiles/r2d_reductions.txt)
     auto one = [&](uint64_t i, double2 a) {
       const double p = a.x * a.x + a.y * a.y;
       const uint64_t gi = i | ext_or;
+      const uint32_t lo = (uint32_t)gi, hi = (uint32_t)(gi >> 32);
 #pragma unroll
       for (int k = 0; k < EXPECT_TERMS; ++k)
-        if (k < terms.n) acc[k] += (__popcll(gi & terms.zmask[k]) & 1) ? -p : p;
+        if (k < terms.n) {
+          const uint32_t f = (lo & (uint32_t)terms.zmask[k]) ^ (hi & (uint32_t)(terms.zmask[k] >> 32));
+          acc[k] += (__popc(f) & 1) ? -p : p;
+        }
     };
     uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
     for (; i + 3 * stride < count; i += 4 * stride) {
@@ -1199,30 +1205,30 @@ k_expect_group(const double2* __restrict__ state, uint64_t count, uint64_t xmask
     for (; i < count; i += stride) one(i, state[i]);
   } else {
     const uint64_t half = count >> 1;
-    for (uint64_t h = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; h < half; h += stride) {
-      const uint64_t i = ((h >> pivot) << (pivot + 1)) | (h & ((1ULL << pivot) - 1ULL));
+    auto pair_index = [&](uint64_t h) { return ((h >> pivot) << (pivot + 1)) | (h & ((1ULL << pivot) - 1ULL)); };
+    auto one = [&](uint64_t i, double2 ai, double2 aj) {
       const uint64_t j = i ^ xmask;
-      // the next pair of this thread is requested before this one is consumed
-      const uint64_t hn = h + stride;
-      if (hn < half) {
-        const uint64_t in = ((hn >> pivot) << (pivot + 1)) | (hn & ((1ULL << pivot) - 1ULL));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(state + in));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(state + (in ^ xmask)));
-      }
-      const double2 ai = __ldcs(state + i), aj = __ldcs(state + j);
       // conj(ai)*aj = (x, y);  conj(aj)*ai = (x, -y)
       const double x = ai.x * aj.x + ai.y * aj.y, y = ai.x * aj.y - ai.y * aj.x;
       const uint64_t gi = i | ext_or, gj = j | ext_or;
 #pragma unroll
       for (int k = 0; k < EXPECT_TERMS; ++k) {
         if (k < terms.n) {
-          const double si = (__popcll(gi & terms.zmask[k]) & 1) ? -1.0 : 1.0;
-          const double sj = (__popcll(gj & terms.zmask[k]) & 1) ? -1.0 : 1.0;
+          const uint32_t zl = (uint32_t)terms.zmask[k], zh = (uint32_t)(terms.zmask[k] >> 32);
+          const double si = (__popc(((uint32_t)gi & zl) ^ ((uint32_t)(gi >> 32) & zh)) & 1) ? -1.0 : 1.0;
+          const double sj = (__popc(((uint32_t)gj & zl) ^ ((uint32_t)(gj >> 32) & zh)) & 1) ? -1.0 : 1.0;
           // phase (pr, pi): Re(ph * sj * (x + iy)) + Re(ph * si * (x - iy))
           acc[k] += sj * (terms.pr[k] * x - terms.pi[k] * y) + si * (terms.pr[k] * x + terms.pi[k] * y);
         }
       }
+    };
+    uint64_t h = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+    for (; h + stride < half; h += 2 * stride) {          // two pairs = four 16-byte loads in flight
+      const uint64_t i0 = pair_index(h), i1 = pair_index(h + stride);
+      const double2 a0 = __ldcs(state + i0), b0 = __ldcs(state + (i0 ^ xmask)), a1 = __ldcs(state + i1), b1 = __ldcs(state + (i1 ^ xmask));
+      one(i0, a0, b0); one(i1, a1, b1);
     }
+    for (; h < half; h += stride) { const uint64_t i = pair_index(h); one(i, state[i], state[i ^ xmask]); }
   }
   block_sum<EXPECT_TERMS>(acc, sm);
   if (threadIdx.x == 0) {
@@ -1267,12 +1273,13 @@ cudaError_t launch_expect_1q(const double2* state, uint64_t count, int bit, cons
 // ------------------------------------------------------------------ partial measurement (domain/state.clj:946-1014)
 // key(i) = sum_k bit(i, pos[k]) << k ; histogram of |a|^2 over keys, per block in shared memory.
 // partials: [grid][2^m]
-// Deterministic (no floating-point atomics): every warp owns a private histogram in shared memory; inside a warp the lanes
-// that hold the same key are found with match.any, their values are added up in ascending lane order by the group's lowest
-// lane, which alone updates the bin - so no two lanes ever write one bin, and the order of every addition is fixed.  The
-// warps' histograms are added in warp order.  blockDim = 32 * W with W * 2^m * 8 bytes <= 64 KB (W = 8 up to m = 10,
-// 2 at m = 12).  Optional filter (fl.n > 0): only amplitudes whose bits fl.pos match fval are counted (second pass of a
-// measurement of more than 12 qubits).
+// Deterministic (no floating-point atomics): every warp owns a private histogram in shared memory.  A lane's index is
+// (multiple of 32) + lane, so inside a warp the key varies only with the measured (or filtered) bits among index bits
+// 0..4: the lanes that share a key differ exactly in the other low bits, and their values are combined with xor-shuffles
+// over those bits (same additions in the same order in every lane of the group); the lane with zeros there alone updates
+// the bin - no two lanes ever write one bin, every addition has a fixed order, and the warps' histograms are added in warp
+// order.  blockDim = 32 * W with W * 2^m * 8 bytes <= 64 KB (W = 8 up to m = 10, 2 at m = 12).  Optional filter (fl.n > 0):
+// only amplitudes whose bits fl.pos match fval are counted (second pass of a measurement of more than 12 qubits).
 __global__ void __launch_bounds__(RED_THREADS)
 k_marginal(const double2* __restrict__ state, uint64_t count, uint64_t ext_or, BitList bl, BitList fl, uint32_t fval,
            double* __restrict__ partials) {
@@ -1281,11 +1288,17 @@ k_marginal(const double2* __restrict__ state, uint64_t count, uint64_t ext_or, B
   for (uint32_t k = threadIdx.x; k < nk * nw; k += nthreads) hist[k] = 0.0;
   __syncthreads();
   double* mine = hist + (size_t)wid * nk;
+  uint32_t fixed_low = 0;                                          // index bits 0..4 that the key or the filter depends on
+  for (int k = 0; k < bl.n; ++k) if (bl.pos[k] < 5) fixed_low |= 1u << bl.pos[k];
+  for (int k = 0; k < fl.n; ++k) if (fl.pos[k] < 5) fixed_low |= 1u << fl.pos[k];
+  const uint32_t free_low = ~fixed_low & 31u;
+  const bool leader = (lane & free_low) == 0;
   const uint64_t stride = (uint64_t)gridDim.x * nthreads;
   const uint64_t rounds = (count + stride - 1) / stride;           // every lane runs the same number of iterations (warp collectives)
   for (uint64_t it = 0; it < rounds; ++it) {
     const uint64_t i = it * stride + (uint64_t)blockIdx.x * nthreads + threadIdx.x;
-    uint32_t key = 0xffffffffu;
+    uint32_t key = 0;
+    bool valid = false;
     double p = 0.0;
     if (i < count) {
       const double2 a = __ldcs(state + i);
@@ -1293,22 +1306,18 @@ k_marginal(const double2* __restrict__ state, uint64_t count, uint64_t ext_or, B
       uint32_t f = 0;
       for (int k = 0; k < fl.n; ++k) f |= (uint32_t)((gi >> fl.pos[k]) & 1ULL) << k;
       if (f == fval) {
-        key = 0;
+        valid = true;
 #pragma unroll 4
         for (int k = 0; k < bl.n; ++k) key |= (uint32_t)((gi >> bl.pos[k]) & 1ULL) << k;
         p = a.x * a.x + a.y * a.y;
       }
     }
-    const uint32_t peers = __match_any_sync(0xffffffffu, key);
-    const uint32_t leader = __ffs(peers) - 1u;
-    double sum = 0.0;
-    for (uint32_t rest = peers; rest;) {                          // ascending lane order; every lane walks its own group
-      const uint32_t src = __ffs(rest) - 1u;
-      rest &= rest - 1u;
-      // all lanes must take part in every shuffle of the warp: iterate over the union of the groups' walks
-      sum += __shfl_sync(peers, p, src);
-    }
-    if (lane == leader && key != 0xffffffffu) mine[key] += sum;
+#pragma unroll
+    for (uint32_t b = 0; b < 5; ++b)
+      if ((free_low >> b) & 1u) p += __shfl_xor_sync(0xffffffffu, p, 1u << b);
+    // a group lies either wholly inside or wholly outside the range / the filter, except in the ragged last iteration,
+    // where the lanes beyond `count` contribute zeros
+    if (leader && valid) mine[key] += p;
     __syncwarp();
   }
   __syncthreads();

@@ -1,0 +1,54 @@
+// mbar_racecheck_probe.cu — does compute-sanitizer's racecheck model mbarrier ordering?  Warp 0 writes a shared array and
+// arrives on an mbarrier (release); warp 1 waits on the barrier's phase (acquire) and reads the array.  This is correctly
+// synchronised under the PTX memory model; if racecheck still reports a hazard here, its reports on k_tile_stage's
+// mbarrier-ordered accesses (tile ring: full[] / done[]) are the same tool limitation.  A second kernel does the same
+// hand-over with bar.sync (which racecheck does model) as the control.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void k_mbar(int* out) {
+  __shared__ int data[32];
+  __shared__ uint64_t bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+  __syncthreads();
+  for (int it = 0; it < 4; ++it) {
+    if (warp == 0) {
+      data[lane] = it * 100 + lane;
+      __syncwarp();
+      if (lane == 0) asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(&bar)) : "memory");
+    } else {
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(&bar)), "r"(it & 1) : "memory");
+      out[it * 32 + lane] = data[lane];
+    }
+    __syncthreads();      // keeps the next iteration's write behind this iteration's read (not the pair under test)
+  }
+}
+
+__global__ void k_barsync(int* out) {
+  __shared__ int data[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int it = 0; it < 4; ++it) {
+    if (warp == 0) data[lane] = it * 100 + lane;
+    __syncthreads();
+    if (warp == 1) out[it * 32 + lane] = data[lane];
+    __syncthreads();
+  }
+}
+
+int main() {
+  int* d; cudaMalloc(&d, 128 * sizeof(int));
+  k_barsync<<<1, 64>>>(d); cudaDeviceSynchronize();
+  k_mbar<<<1, 64>>>(d); cudaDeviceSynchronize();
+  int h[128]; cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+  int bad = 0;
+  for (int it = 0; it < 4; ++it) for (int l = 0; l < 32; ++l) bad += h[it * 32 + l] != it * 100 + l;
+  printf("mbar probe: %s (%d wrong)\n", bad ? "WRONG VALUES" : "values ok", bad);
+  return bad != 0;
+}

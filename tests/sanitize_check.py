@@ -37,7 +37,7 @@ def main():
     check("unfused (one gate per sweep)", 12, brick12[:40], fusion=0)
     check("TMA mover", 13, brick13, tile_mover=2)
     check("small tiles (generic mover)", 12, brick12, tile_bits=8, low_bits=3)
-    check("every gate kind", 8, _all_gates_circuit(8)["operations"])
+    check("every gate kind", 8, _all_gates_circuit(8, np.random.default_rng(8))["operations"])
     os.environ["QCB_DIRECT_STORE"] = "1"
     check("direct store", 13, brick13)
     os.environ.pop("QCB_DIRECT_STORE")
