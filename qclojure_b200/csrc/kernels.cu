@@ -1183,26 +1183,37 @@ k_expect_group(const double2* __restrict__ state, uint64_t count, uint64_t xmask
   for (int k = 0; k < EXPECT_TERMS; ++k) acc[k] = 0.0;
   const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
   if (xmask == 0) {
-    // the loads of four elements are issued before the first is consumed (streaming read, see k_reduce)
-    // parity(gi & z) with ONE 32-bit POPC per term: the two halves are folded first (POPC issues at a quarter of the integer
-    // rate and was what bounded this loop: 1.3 TB/s with two POPCs per term, profiles/r2d_reductions.txt)
-    auto one = [&](uint64_t i, double2 a) {
-      const double p = a.x * a.x + a.y * a.y;
+    // Diagonal terms: sum_i (-1)^parity(i & z) |a_i|^2.  A thread takes FOUR consecutive amplitudes (64 bytes): their
+    // parities differ from the first one's only through z's two lowest bits, which are constants of the term, so one
+    // parity evaluation (two ANDs, one XOR, ONE 32-bit POPC - POPC issues at a quarter of the integer rate and bounded the
+    // one-amplitude-per-evaluation loop at 1.3 TB/s, profiles/r2d_reductions.txt) signs one of four precomputed
+    // combinations p0 +- p1 +- p2 +- p3.
+    const uint64_t quads = count >> 2;
+    for (uint64_t q = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; q < quads; q += stride) {
+      const uint64_t i = q << 2;
+      const double2 a0 = __ldcs(state + i), a1 = __ldcs(state + i + 1), a2 = __ldcs(state + i + 2), a3 = __ldcs(state + i + 3);
+      const double p0 = a0.x * a0.x + a0.y * a0.y, p1 = a1.x * a1.x + a1.y * a1.y, p2 = a2.x * a2.x + a2.y * a2.y, p3 = a3.x * a3.x + a3.y * a3.y;
+      // combo[c]: bit 0 of c = z bit 0 set (p1, p3 flip), bit 1 = z bit 1 set (p2, p3 flip)
+      const double combo[4] = {(p0 + p1) + (p2 + p3), (p0 - p1) + (p2 - p3), (p0 + p1) - (p2 + p3), (p0 - p1) - (p2 - p3)};
       const uint64_t gi = i | ext_or;
       const uint32_t lo = (uint32_t)gi, hi = (uint32_t)(gi >> 32);
 #pragma unroll
       for (int k = 0; k < EXPECT_TERMS; ++k)
         if (k < terms.n) {
-          const uint32_t f = (lo & (uint32_t)terms.zmask[k]) ^ (hi & (uint32_t)(terms.zmask[k] >> 32));
-          acc[k] += (__popc(f) & 1) ? -p : p;
+          const uint32_t zl = (uint32_t)terms.zmask[k];
+          const uint32_t f = (lo & zl) ^ (hi & (uint32_t)(terms.zmask[k] >> 32));        // lo's bits 0, 1 are zero
+          const double v = combo[zl & 3u];
+          acc[k] += (__popc(f) & 1) ? -v : v;
         }
-    };
-    uint64_t i = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
-    for (; i + 3 * stride < count; i += 4 * stride) {
-      const double2 a0 = __ldcs(state + i), a1 = __ldcs(state + i + stride), a2 = __ldcs(state + i + 2 * stride), a3 = __ldcs(state + i + 3 * stride);
-      one(i, a0); one(i + stride, a1); one(i + 2 * stride, a2); one(i + 3 * stride, a3);
     }
-    for (; i < count; i += stride) one(i, state[i]);
+    for (uint64_t i = (quads << 2) + (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {   // count < 4
+      const double2 a = state[i];
+      const double p = a.x * a.x + a.y * a.y;
+      const uint64_t gi = i | ext_or;
+#pragma unroll
+      for (int k = 0; k < EXPECT_TERMS; ++k)
+        if (k < terms.n) acc[k] += (__popcll(gi & terms.zmask[k]) & 1) ? -p : p;
+    }
   } else {
     const uint64_t half = count >> 1;
     auto pair_index = [&](uint64_t h) { return ((h >> pivot) << (pivot + 1)) | (h & ((1ULL << pivot) - 1ULL)); };

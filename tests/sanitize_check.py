@@ -29,6 +29,14 @@ def main():
         assert err <= 1e-10, (tag, err)
         print(f"ok {tag}: n={n} err={err:.1e}", flush=True)
 
+    if "--single-tile" in sys.argv:
+        # ONE tile per CTA and sweep (12 qubits = the tile): no buffer of the ring is ever reused, so the only accesses ordered
+        # through mbarriers are mover-load -> first round and last round -> mover write-back; the round-to-round hand-over
+        # inside a consumer group goes through bar.sync alone.  racecheck models bar.sync but not mbarrier phases
+        # (tests/cuda/mbar_racecheck_probe.cu): here it must not report any store / load pair of the rounds themselves.
+        check("single tile, three-product rounds", 12, C.random_brickwork_circuit(12, 10)["operations"])
+        print("sanitize_check ok (single tile)", flush=True)
+        return
     brick13 = C.random_brickwork_circuit(13, 6)["operations"]       # tile = 12 bits: specialised mover, 2 tiles per sweep
     brick12 = C.random_brickwork_circuit(12, 6)["operations"]
     check("three-product rounds, cp.async mover", 13, brick13)
