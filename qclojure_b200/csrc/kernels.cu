@@ -479,7 +479,11 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
   xq = btab[3];
   k3_pp<true, true, true, DIRECT>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(1));
   // batches 2 .. per-3 (both look-aheads exist)
+#ifdef QCB_PP_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
   for (uint32_t i = 2; i + 2u < per; i += 2u) {
     xq = btab[i + 2u];
     k3_pp<true, true, true, DIRECT>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(i));
@@ -1565,13 +1569,21 @@ cudaError_t launch_unpack_half(double2* state, const double2* buf, uint64_t firs
 __global__ void __launch_bounds__(RED_THREADS)
 k_swap_global(double2* __restrict__ mine, SwapPeers peers, SwapBits sb, uint32_t g, uint64_t n_rest_half) {
   const uint32_t k = (uint32_t)sb.k;
-  const uint64_t per_partner = n_rest_half;                       // work items per partner
+  const uint64_t per_partner = n_rest_half;                       // work items per partner (a power of two)
   const uint64_t total = per_partner * ((1ull << k) - 1ull);
+  const uint64_t chunk = per_partner < (1ull << 13) ? per_partner : (1ull << 13);   // 128 KiB per partner visit
   const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+  // Work item -> (partner, position).  Partners are visited block-cyclically (chunks of `chunk` items) in the XOR order
+  // v = g ^ s, s = 1 .. 2^k - 1, so that at any moment the CTAs of a rank talk to all partners at once and the traffic
+  // into every rank comes from all of its partners at once.  (Walking the partners one after the other in the same order
+  // on every rank makes all ranks hit the same receiver at the same time: 342 GB/s per direction on 8 GPUs instead of the
+  // 697 GB/s of a single pair, profiles/r2e_bench_8gpu.log.)
+  const uint64_t nparts = (1ull << k) - 1ull;
   auto locate = [&](uint64_t w, uint64_t& x, uint64_t& xp, double2*& peer) {
-    const uint32_t pi = (uint32_t)(w / per_partner);              // partner ordinal 0 .. 2^k - 2
-    uint64_t rest = w - (uint64_t)pi * per_partner;
-    const uint32_t v = pi + (pi >= g ? 1u : 0u);                  // partner's value of the exchanged bits (skips g)
+    const uint64_t c = w / chunk, in = w - c * chunk;
+    const uint32_t s = 1u + (uint32_t)(c % nparts);
+    uint64_t rest = (c / nparts) * chunk + in;
+    const uint32_t v = g ^ s;                                     // partner's value of the exchanged bits
     // the pair's lower rank takes the items whose top rest bit is 0, the higher rank those with 1
     if (g > v) rest |= n_rest_half;
     uint64_t base = rest;

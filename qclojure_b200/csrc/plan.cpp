@@ -1352,10 +1352,12 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
     // physical bit (and whatever depends on them) are skipped by the stage builder, so an exchange is only paid for
     // when no gate at all can run without it
     {
-      // Experiment knob, OFF by default (thin_defer = 0): do not run a THIN stage (fewer gates than thin_defer) while gates
-      // wait for an exchange, so that its gates ride along in the fuller sweeps after the exchange.  Brickwork gains 3 %
-      // in the cost model (33 q on 8 GPUs: 23 -> 21 sweeps), but circuits without free exchange partners pay for the
-      // earlier exchanges with many more of them (QFT-26 on 8 GPUs: 7 -> 11..22 exchanges), hence off.
+      // Do not run a THIN stage (fewer gates than thin_defer, default 12) while gates wait for an exchange: its gates ride
+      // along in the fuller sweeps after the exchange.  Round 1 kept this off because every extra exchange cost a pairwise
+      // half-slice transfer; with up to three global qubits moving in ONE in-place pass a moderate threshold pays: the
+      // 33-qubit benchmark on 8 GPUs goes from 23 sweeps / 89 rounds to 21 / 86 with the same single exchange pass, QFT-26 on
+      // 8 GPUs from 23 sweeps / 5 exchange passes to 19 / 6.  Larger thresholds trade sweeps for many more exchanges
+      // (QFT-26: 10 passes at 16, 18 at 24) and are not worth it.
       const bool may_defer = cfg.world > 1 && cfg.fusion && cfg.thin_defer > 0 &&
                              !(plan.stages.size() && plan.stages.back().kind == S_EXCHANGE);
       std::vector<int> saved_pending;

@@ -141,7 +141,8 @@ struct Config {
                                // 1 = 16x16 real block (m16n8k16 = eight steps, 8-byte accesses), the round-1 kernel
   int round_yield_pct = 50;    // end a stage early when the next round would absorb less than this % of the stage's average round
   int window_search = 1;       // stage builder also tries contiguous tile windows and keeps the best yield
-  int thin_defer = 0;          // multi-GPU: a stage with fewer gates than this is not run while gates wait for an exchange
+  int thin_defer = 12;         // multi-GPU: a stage with fewer gates than this is not run while gates wait for an exchange
+                               // (its gates ride along in the fuller sweeps after the exchange)
   int tma = 0;                 // tiles move by TMA tensor copies (layout follows the hardware 128-byte swizzle)
   int threads = 256;
 };
