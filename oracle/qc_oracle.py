@@ -750,15 +750,16 @@ def execute_single_noisy_shot(circuit, noise_model, draws, initial_state=None, *
     return bitstring, state
 
 
-def run_noisy(circuit, noise_model, uniforms: np.ndarray, max_trajectories: int = 100, *, superset=False):
+def run_noisy(circuit, noise_model, uniforms: np.ndarray, max_trajectories: int = 100, *, superset=False, initial_state=None):
     """hardware_simulator.clj:120-185 — `shots` independent shots; counts keyed by bitstring; the first
-    <= max_trajectories final states are kept.  uniforms: [shots, draws_per_shot] array."""
+    <= max_trajectories final states are kept.  uniforms: [shots, draws_per_shot] array.  initial_state:
+    (or (:initial-state options) zero-state), hardware_simulator.clj:228-230."""
     counts: Dict[str, int] = {}
     trajectories = []
     last = None
     for row in np.asarray(uniforms):
         it = iter(row.tolist())
-        bs, st = execute_single_noisy_shot(circuit, noise_model, it, superset=superset)
+        bs, st = execute_single_noisy_shot(circuit, noise_model, it, initial_state, superset=superset)
         counts[bs] = counts.get(bs, 0) + 1
         if len(trajectories) < max_trajectories:
             trajectories.append(st)

@@ -479,10 +479,11 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
   xq = btab[3];
   k3_pp<true, true, true, DIRECT>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(1));
   // batches 2 .. per-3 (both look-aheads exist)
-#ifdef QCB_PP_UNROLL2
-#pragma unroll 2
-#else
+  // two loop bodies (four batches) per back edge: +2 % over one (profiles/r2g_ab.log); fully unrolled, ptxas serialises the batches
+#ifdef QCB_PP_UNROLL1
 #pragma unroll 1
+#else
+#pragma unroll 2
 #endif
   for (uint32_t i = 2; i + 2u < per; i += 2u) {
     xq = btab[i + 2u];
@@ -1310,13 +1311,12 @@ k_marginal(const double2* __restrict__ state, uint64_t count, uint64_t ext_or, B
   const bool leader = (lane & free_low) == 0;
   const uint64_t stride = (uint64_t)gridDim.x * nthreads;
   const uint64_t rounds = (count + stride - 1) / stride;           // every lane runs the same number of iterations (warp collectives)
-  for (uint64_t it = 0; it < rounds; ++it) {
-    const uint64_t i = it * stride + (uint64_t)blockIdx.x * nthreads + threadIdx.x;
+  // one element: key / validity / probability, combined over the group's lanes, added to the warp's bin by the leader
+  auto consume = [&](uint64_t i, double2 a) {
     uint32_t key = 0;
     bool valid = false;
     double p = 0.0;
     if (i < count) {
-      const double2 a = __ldcs(state + i);
       const uint64_t gi = i | ext_or;
       uint32_t f = 0;
       for (int k = 0; k < fl.n; ++k) f |= (uint32_t)((gi >> fl.pos[k]) & 1ULL) << k;
@@ -1334,6 +1334,19 @@ k_marginal(const double2* __restrict__ state, uint64_t count, uint64_t ext_or, B
     // where the lanes beyond `count` contribute zeros
     if (leader && valid) mine[key] += p;
     __syncwarp();
+  };
+  const uint64_t first = (uint64_t)blockIdx.x * nthreads + threadIdx.x;
+  uint64_t it = 0;
+  for (; it + 3 < rounds; it += 4) {                               // four independent 16-byte loads in flight per thread
+    const uint64_t i0 = it * stride + first, i1 = i0 + stride, i2 = i1 + stride, i3 = i2 + stride;
+    const double2 z{0.0, 0.0};
+    const double2 a0 = i0 < count ? __ldcs(state + i0) : z, a1 = i1 < count ? __ldcs(state + i1) : z;
+    const double2 a2 = i2 < count ? __ldcs(state + i2) : z, a3 = i3 < count ? __ldcs(state + i3) : z;
+    consume(i0, a0); consume(i1, a1); consume(i2, a2); consume(i3, a3);
+  }
+  for (; it < rounds; ++it) {
+    const uint64_t i = it * stride + first;
+    consume(i, i < count ? __ldcs(state + i) : double2{0.0, 0.0});
   }
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < nk; k += nthreads) {

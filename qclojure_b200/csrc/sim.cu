@@ -744,7 +744,7 @@ int measure_qubits_impl(qcb_sim* h, const int32_t* qubits, int m, double u, int3
     all.pos[k] = h->perm[n - 1 - qubits[k]];
   }
   const uint64_t ext_or = (uint64_t)h->cfg.rank << h->cfg.n_local;
-  const int grid = std::min(red_grid(h), 296);
+  const int grid = red_grid(h);
   // one histogram pass over `bits` (restricted to filter == fval): probabilities of the 2^bits.n outcomes, summed over ranks
   auto pass = [&](const BitList& bits, const BitList& filter, uint32_t fval, std::vector<double>& probs) -> int {
     const uint32_t nk = 1u << bits.n;
@@ -1713,6 +1713,164 @@ int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb
   }
   RET(begin_timing(h));
   h->stats.n_ops = n_ops * n_shots;
+  // ---- trajectory tree (default for states up to 1 GiB): the shots walk the circuit TOGETHER for as long as their
+  // histories agree.  At a noisy gate with several Kraus operators the shots split by the operator their draw selects
+  // (a state-independent table, channel.clj:225-233); at a mid-circuit :measure they split by the outcome their draw selects
+  // from the marginal distribution of the shared state (state.clj:946-1014).  At every split the state is checkpointed
+  // once on the device and restored for each further branch, so a gate is applied once per distinct history PREFIX instead
+  // of once per shot (the per-shot loop) or once per distinct complete history (the grouping below, which cannot handle
+  // :measure ops at all).  Same draws -> same outcomes, trajectories and final state as the shot-by-shot loop.
+  {
+    static const bool tree_off = std::getenv("QCB_NOISY_TREE") && std::atoi(std::getenv("QCB_NOISY_TREE")) == 0;
+    bool tree_ok = !tree_off && n <= 26 && n_shots > 0;
+    for (uint64_t k = 0; k < n_ops && tree_ok; ++k) if (ops[k].kind == QCB_OP_MEASURE && (ops[k].n_mask > MAX_HIST_BITS || !ops[k].ext)) tree_ok = false;
+    if (tree_ok) {
+      std::vector<double2*> ckpts;                      // pool of device checkpoints (depth of the open splits)
+      size_t ckpt_used = 0;
+      auto ckpt_get = [&](double2** out) -> int {
+        if (ckpt_used == ckpts.size()) {
+          double2* b = nullptr;
+          if (cudaMalloc(&b, h->local_count * sizeof(double2)) != cudaSuccess) { cudaGetLastError(); return fail(h, QCB_ERR_NOMEM, "noisy trajectories: out of device memory for a state checkpoint"); }
+          ckpts.push_back(b);
+        }
+        *out = ckpts[ckpt_used++];
+        return QCB_OK;
+      };
+      const uint64_t last_shot = n_shots - 1;
+      std::vector<double> us;
+      std::vector<uint64_t> outs;
+      auto flush = [&](std::vector<Gate>& pending) -> int {
+        if (pending.empty()) return QCB_OK;
+        std::vector<Gate> g; g.swap(pending);
+        return run_gates(h, std::move(g));
+      };
+      // the Kraus operator `kidx` of entry e after the gate on qubit tq: pre-scaled when proportional to a unitary, else
+      // applied and followed by the norm pass (channel.clj:162-200)
+      auto push_kraus = [&](std::vector<Gate>& pending, const qcb_noise_entry* e, int kidx, int tq) -> int {
+        double scale = 1.0;
+        if (proportional_to_unitary(e->kraus[kidx], &scale)) { pending.push_back(kraus_gate(h, e->kraus[kidx], tq, scale)); return QCB_OK; }
+        pending.push_back(kraus_gate(h, e->kraus[kidx], tq, 1.0));
+        RET(flush(pending));
+        return normalize_inplace(h);
+      };
+      // splits `shots` by key, the group that holds the run's last shot last (the handle keeps that shot's final state)
+      auto split = [&](const std::vector<uint64_t>& shots, const std::vector<uint32_t>& keys, std::vector<std::pair<uint32_t, std::vector<uint64_t>>>& groups) {
+        std::map<uint32_t, size_t> index;
+        for (size_t j = 0; j < shots.size(); ++j) {
+          auto it = index.find(keys[j]);
+          if (it == index.end()) { it = index.emplace(keys[j], groups.size()).first; groups.emplace_back(keys[j], std::vector<uint64_t>()); }
+          groups[it->second].second.push_back(shots[j]);
+        }
+        for (size_t g = 0; g + 1 < groups.size(); ++g)
+          if (std::find(groups[g].second.begin(), groups[g].second.end(), last_shot) != groups[g].second.end()) { std::swap(groups[g], groups.back()); break; }
+      };
+      std::function<int(uint64_t, uint64_t, std::vector<uint64_t>&, std::vector<Gate>&)> walk =
+          [&](uint64_t k, uint64_t di, std::vector<uint64_t>& shots, std::vector<Gate>& pending) -> int {
+        std::string err;
+        for (; k < n_ops; ++k) {
+          const qcb_op& op = ops[k];
+          if (op.kind == QCB_OP_MEASURE) {
+            RET(flush(pending));
+            const int32_t* mq = static_cast<const int32_t*>(op.ext);
+            const int m = op.n_mask;
+            std::vector<double> probs((size_t)1 << m);
+            RET(measure_qubits_impl(h, mq, m, 0.0, nullptr, nullptr, probs.data(), false));
+            double total = 0;
+            for (double v : probs) total += v;
+            std::vector<uint32_t> keys(shots.size());
+            for (size_t j = 0; j < shots.size(); ++j) {       // the selection rule of measure_qubits_impl, per shot
+              const double r = total * uniforms[shots[j] * draws_per_shot + di];
+              uint32_t sel = 0; double cum = 0;
+              while (sel < probs.size() && (cum += probs[sel]) < r) ++sel;
+              keys[j] = sel >= probs.size() ? (uint32_t)probs.size() - 1 : sel;
+            }
+            std::vector<std::pair<uint32_t, std::vector<uint64_t>>> groups;
+            split(shots, keys, groups);
+            double2* ck = nullptr;
+            if (groups.size() > 1) { RET(ckpt_get(&ck)); CU(h, cudaMemcpyAsync(ck, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream)); }
+            for (size_t g = 0; g < groups.size(); ++g) {
+              if (g) CU(h, cudaMemcpyAsync(h->state, ck, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
+              // collapse onto the group's outcome: any of its draws selects it
+              RET(measure_qubits_impl(h, mq, m, uniforms[groups[g].second[0] * draws_per_shot + di], nullptr, nullptr, nullptr, true));
+              if (groups.size() == 1) { shots.swap(groups[0].second); break; }
+              std::vector<Gate> p2;
+              RET(walk(k + 1, di + 1, groups[g].second, p2));
+            }
+            if (groups.size() > 1) { --ckpt_used; return QCB_OK; }
+            ++di;
+            continue;
+          }
+          int rc = lower_ops(h->cfg, &op, 1, pending, err);
+          if (rc != QCB_OK) return fail(h, rc, err);
+          const qcb_noise_entry* e = find_noise(noise, op.kind);
+          if (!e || e->n_kraus < 1) continue;
+          int tq = noise_target(op);
+          if (tq < 0 || tq >= n) tq = 0;
+          if (e->n_kraus == 1) { RET(push_kraus(pending, e, 0, tq)); continue; }
+          std::vector<uint32_t> keys(shots.size());
+          for (size_t j = 0; j < shots.size(); ++j) keys[j] = (uint32_t)select_kraus(e, uniforms[shots[j] * draws_per_shot + di]);
+          std::vector<std::pair<uint32_t, std::vector<uint64_t>>> groups;
+          split(shots, keys, groups);
+          if (groups.size() == 1) { RET(push_kraus(pending, e, (int)groups[0].first, tq)); ++di; continue; }
+          RET(flush(pending));
+          double2* ck = nullptr;
+          RET(ckpt_get(&ck));
+          CU(h, cudaMemcpyAsync(ck, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
+          for (size_t g = 0; g < groups.size(); ++g) {
+            if (g) CU(h, cudaMemcpyAsync(h->state, ck, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
+            std::vector<Gate> p2;
+            RET(push_kraus(p2, e, (int)groups[g].first, tq));
+            RET(walk(k + 1, di + 1, groups[g].second, p2));
+          }
+          --ckpt_used;
+          return QCB_OK;
+        }
+        // ---- leaf: every shot here shares the final state.  One measure-state draw each, then readout noise (noise.clj:193-202)
+        RET(flush(pending));
+        us.resize(shots.size());
+        outs.assign(shots.size(), 0);
+        for (size_t j = 0; j < shots.size(); ++j) us[j] = uniforms[shots[j] * draws_per_shot + di];
+        RET(sample_impl(h, us.data(), shots.size(), outs.data()));
+        for (size_t j = 0; j < shots.size(); ++j) {
+          const double* uj = uniforms + shots[j] * draws_per_shot;
+          uint64_t dj = di + 1, outcome = outs[j];
+          if (noise && noise->has_readout) {
+            std::vector<int> flipped;
+            for (int q = 0; q < n; ++q) {
+              const int bitpos = n - 1 - q;
+              const int orig = (outcome >> bitpos) & 1;
+              double factor = 1.0;
+              if (noise->correlation) for (int src : flipped) factor *= noise->correlation[(size_t)src * n + q];
+              double eff = (orig ? noise->prob_1_to_0 : noise->prob_0_to_1) * factor;
+              eff = std::min(1.0, std::max(0.0, eff));
+              if (uj[dj++] < eff) { outcome ^= 1ULL << bitpos; flipped.push_back(q); }
+            }
+          }
+          out_outcomes[shots[j]] = outcome;
+          if (traj_out && shots[j] < max_traj)
+            CU(h, cudaMemcpyAsync(traj_out + shots[j] * 2 * h->local_count, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+        }
+        return QCB_OK;
+      };
+      if (h->noisy_init) {
+        CU(h, cudaMemcpyAsync(h->state, h->noisy_init, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
+      } else {
+        CU(h, cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream));
+        CU(h, launch_set_amp(h->state, 0, 1.0, 0.0, h->stream));
+      }
+      for (size_t b = 0; b < h->perm.size(); ++b) h->perm[b] = (int)b;
+      std::vector<uint64_t> all(n_shots);
+      for (uint64_t sidx = 0; sidx < n_shots; ++sidx) all[sidx] = sidx;
+      std::vector<Gate> p0;
+      int rc = walk(0, 0, all, p0);
+      cudaStreamSynchronize(h->stream);
+      for (double2* b : ckpts) cudaFree(b);
+      if (rc != QCB_OK) return rc;
+      end_timing(h);
+      return QCB_OK;
+    }
+  }
+  // ---- fallback (QCB_NOISY_TREE=0, states above 1 GiB, :measure of more than 12 qubits)
   // The Kraus operator applied after a noisy gate is chosen by a draw and a state-independent probability table
   // (channel.clj:225-233), so without mid-circuit :measure ops the final state of a shot is a function of its sequence of
   // choices only.  Shots are grouped by that sequence: one state evolution per distinct sequence, then all of the group's

@@ -42,9 +42,24 @@ __global__ void k_barsync(int* out) {
   }
 }
 
+// Third kernel: the hand-over through a NAMED barrier that only part of the CTA takes part in (bar.sync 1, 64 inside a
+// 128-thread block) - how the consumer groups of k_tile_stage separate their rounds.
+__global__ void k_named(int* out) {
+  __shared__ int data[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= 2) return;                       // warps 2, 3 never touch barrier 1
+  for (int it = 0; it < 4; ++it) {
+    if (warp == 0) data[lane] = it * 100 + lane;
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+    if (warp == 1) out[it * 32 + lane] = data[lane];
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+  }
+}
+
 int main() {
   int* d; cudaMalloc(&d, 128 * sizeof(int));
   k_barsync<<<1, 64>>>(d); cudaDeviceSynchronize();
+  k_named<<<1, 128>>>(d); cudaDeviceSynchronize();
   k_mbar<<<1, 64>>>(d); cudaDeviceSynchronize();
   int h[128]; cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
   int bad = 0;

@@ -507,6 +507,77 @@ def test_noisy_trajectories_match_oracle(profile, n, shots):
     assert np.max(np.abs(last - want["final-state"])) <= TOL
 
 
+def test_noisy_trajectory_tree_with_mid_circuit_measure(monkeypatch):
+    """The trajectory tree (shots share every common prefix of their Kraus choices AND mid-circuit measurement outcomes;
+    device checkpoints at the splits) against the oracle's shot-by-shot loop on the same draws: counts, the first
+    trajectories, the last shot's final state - for a circuit with two :measure ops - and against the library's own per-shot
+    path (QCB_NOISY_TREE=0); plus the :initial-state option of the noisy path."""
+    from qclojure_b200 import ops as OPS
+    with open(os.path.join(GOLDEN, "device_profiles.json")) as f:
+        nm = [d for d in json.load(f)["devices"] if d["id"] == ":ibm-lagos"][0]["noise_model"]
+    n, shots = 6, 300
+    circ = C.ghz_state_circuit(n)
+    C.measure(circ, [2])
+    circ["operations"] += C.random_brickwork_circuit(n, 2, seed=5)["operations"]
+    C.measure(circ, [0, 4])
+    C.h(circ, 3); C.cnot(circ, 3, 5)
+    dps = O.draws_per_shot(circ, nm)
+    u = np.random.default_rng(17).random((shots, dps))
+    want = O.run_noisy(circ, nm, u, max_trajectories=16)
+    table, keep = _noise_table(nm, n)
+    enc = OPS.encode_ops(circ["operations"])
+
+    def run():
+        with L.StateVector(n) as sv:
+            outcomes, traj = sv.run_noisy(enc, table, u, max_trajectories=16)
+            return outcomes, traj, sv.get_state(), sv.stats()
+
+    outcomes, traj, last, st_tree = run()
+    counts = {}
+    for o in outcomes:
+        bs = O.basis_string(int(o), n)
+        counts[bs] = counts.get(bs, 0) + 1
+    assert counts == want["measurement-results"]
+    for k in range(16):
+        assert np.max(np.abs(traj[k] - want["trajectories"][k])) <= TOL
+    assert np.max(np.abs(last - want["final-state"])) <= TOL
+    monkeypatch.setenv("QCB_NOISY_TREE", "0")
+    # the environment switch is read once per process: compare through a fresh interpreter
+    import subprocess, sys, pickle, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        np.save(os.path.join(d, "u.npy"), u)
+        with open(os.path.join(d, "circ.pkl"), "wb") as f:
+            pickle.dump((circ, nm, n), f)
+        code = ("import sys, pickle, numpy as np; sys.path.insert(0, %r)\n"
+                "from qclojure_b200 import _lib as L, ops as OPS, noise as NZ\n"
+                "circ, nm, n = pickle.load(open(%r, 'rb')); u = np.load(%r)\n"
+                "table, keep = NZ.build_noise_table(nm, n); enc = OPS.encode_ops(circ['operations'])\n"
+                "sv = L.StateVector(n); o, t = sv.run_noisy(enc, table, u, max_trajectories=0); np.save(%r, o); print(sv.stats()['n_kernel_launches'])\n"
+                % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(d, "circ.pkl"), os.path.join(d, "u.npy"),
+                   os.path.join(d, "o.npy")))
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        per_shot = np.load(os.path.join(d, "o.npy"))
+        launches_per_shot = int(out.stdout.strip().splitlines()[-1])
+    assert np.array_equal(per_shot, outcomes)
+    assert st_tree["n_kernel_launches"] < launches_per_shot          # shared prefixes: fewer kernels than one plan per shot
+    # :initial-state of the noisy path (hardware_simulator.clj:228-230)
+    init = _rand_state(n, 91)
+    want_i = O.run_noisy(circ, nm, u[:40], max_trajectories=4, initial_state=init)
+    with L.StateVector(n) as sv:
+        sv.noisy_set_initial_state(init)
+        o1, t1 = sv.run_noisy(enc, table, u[:40], max_trajectories=4)
+        sv.noisy_set_initial_state(None)
+        o2, _t2 = sv.run_noisy(enc, table, u[:40], max_trajectories=0)
+    assert np.array_equal(o2, outcomes[:40])
+    for k in range(4):
+        assert np.max(np.abs(t1[k] - want_i["trajectories"][k])) <= TOL
+    cnt_i = {}
+    for o in o1:
+        cnt_i[O.basis_string(int(o), n)] = cnt_i.get(O.basis_string(int(o), n), 0) + 1
+    assert cnt_i == want_i["measurement-results"]
+
+
 # ------------------------------------------------------------------ jobs and P2
 def test_job_layer():
     from qclojure_b200 import backend as B
