@@ -97,6 +97,17 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
+// the round barrier of consumer group `grp`: barrier 1 + grp with the id as an IMMEDIATE (a barrier id held in a register
+// is legal PTX, but compute-sanitizer's racecheck does not follow it and then reports every round-to-round hand-over)
+template <uint32_t NT>
+__device__ __forceinline__ void group_bar_sync(uint32_t grp) {
+  switch (grp) {
+    case 0: asm volatile("bar.sync 1, %0;\n" ::"n"(NT) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;\n" ::"n"(NT) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;\n" ::"n"(NT) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;\n" ::"n"(NT) : "memory"); break;
+  }
+}
 
 // ------------------------------------------------------------------ TMA (cp.async.bulk.tensor) primitives
 // The state is described to the TMA unit as a 2-D tensor of doubles [rows = 2^(n_local-3)][16] (one row = 8 amplitudes =
@@ -825,7 +836,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
       mbar_wait(full + b, (j / nbuf) & 1u);
       PF_ADD(PF_C_WAIT_FULL);
       for (uint32_t r = 0; r < sc.n_rounds; ++r) {
-        if (r) named_bar_sync(1 + grp, GT);
+        if (r) group_bar_sync<GT>(grp);
         PF_ADD(PF_C_BARRIER);
         uint32_t nj = j, nr = r + 1u;
         if (nr == sc.n_rounds) { nr = 0; nj = j + NG; }

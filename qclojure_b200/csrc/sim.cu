@@ -1713,13 +1713,14 @@ int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb
   }
   RET(begin_timing(h));
   h->stats.n_ops = n_ops * n_shots;
-  // ---- trajectory tree (default for states up to 1 GiB): the shots walk the circuit TOGETHER for as long as their
-  // histories agree.  At a noisy gate with several Kraus operators the shots split by the operator their draw selects
-  // (a state-independent table, channel.clj:225-233); at a mid-circuit :measure they split by the outcome their draw selects
-  // from the marginal distribution of the shared state (state.clj:946-1014).  At every split the state is checkpointed
-  // once on the device and restored for each further branch, so a gate is applied once per distinct history PREFIX instead
-  // of once per shot (the per-shot loop) or once per distinct complete history (the grouping below, which cannot handle
-  // :measure ops at all).  Same draws -> same outcomes, trajectories and final state as the shot-by-shot loop.
+  // ---- trajectory tree (default for states up to 1 GiB): shots that share a history share the work.  The circuit is cut
+  // into segments at its mid-circuit :measure ops.  Inside a segment the Kraus operator applied after a noisy gate is chosen
+  // by a draw and a state-independent probability table (channel.clj:225-233), so the shots of a node are grouped by their
+  // choice tuple for the whole segment and every group runs the segment as one fused plan; at a :measure the group's shots
+  // split by the outcome their draw selects from the marginal of the shared state (state.clj:946-1014).  States are
+  // checkpointed on the device where a node has several children.  Without :measure ops this is exactly "one evolution per
+  // distinct Kraus sequence"; with them it replaces the shot-by-shot loop.  Same draws -> same outcomes, trajectories and
+  // final state as that loop.
   {
     static const bool tree_off = std::getenv("QCB_NOISY_TREE") && std::atoi(std::getenv("QCB_NOISY_TREE")) == 0;
     bool tree_ok = !tree_off && n <= 26 && n_shots > 0;
@@ -1764,92 +1765,112 @@ int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb
         for (size_t g = 0; g + 1 < groups.size(); ++g)
           if (std::find(groups[g].second.begin(), groups[g].second.end(), last_shot) != groups[g].second.end()) { std::swap(groups[g], groups.back()); break; }
       };
-      std::function<int(uint64_t, uint64_t, std::vector<uint64_t>&, std::vector<Gate>&)> walk =
-          [&](uint64_t k, uint64_t di, std::vector<uint64_t>& shots, std::vector<Gate>& pending) -> int {
-        std::string err;
-        for (; k < n_ops; ++k) {
-          const qcb_op& op = ops[k];
-          if (op.kind == QCB_OP_MEASURE) {
-            RET(flush(pending));
-            const int32_t* mq = static_cast<const int32_t*>(op.ext);
-            const int m = op.n_mask;
-            std::vector<double> probs((size_t)1 << m);
-            RET(measure_qubits_impl(h, mq, m, 0.0, nullptr, nullptr, probs.data(), false));
-            double total = 0;
-            for (double v : probs) total += v;
-            std::vector<uint32_t> keys(shots.size());
-            for (size_t j = 0; j < shots.size(); ++j) {       // the selection rule of measure_qubits_impl, per shot
-              const double r = total * uniforms[shots[j] * draws_per_shot + di];
-              uint32_t sel = 0; double cum = 0;
-              while (sel < probs.size() && (cum += probs[sel]) < r) ++sel;
-              keys[j] = sel >= probs.size() ? (uint32_t)probs.size() - 1 : sel;
+      // One SEGMENT = the ops up to the next :measure (or the end).  The Kraus choices inside a segment do not depend on the
+      // state, so the shots of a node are grouped by their whole choice tuple for the segment up front and each group runs
+      // the segment as ONE fused plan (a split at every noisy gate would cut the plan into one sweep per gate).  The tree
+      // branches where it must: per distinct choice tuple at a segment start, per outcome at a :measure.
+      std::function<int(uint64_t, uint64_t, std::vector<uint64_t>&)> walk =
+          [&](uint64_t k0, uint64_t di0, std::vector<uint64_t>& shots) -> int {
+        uint64_t k1 = k0;
+        while (k1 < n_ops && ops[k1].kind != QCB_OP_MEASURE) ++k1;
+        // multi-Kraus gates of the segment, in order: (op index, entry)
+        std::vector<std::pair<uint64_t, const qcb_noise_entry*>> multi;
+        for (uint64_t k = k0; k < k1; ++k) {
+          const qcb_noise_entry* e = find_noise(noise, ops[k].kind);
+          if (e && e->n_kraus > 1) multi.emplace_back(k, e);
+        }
+        const uint64_t di1 = di0 + multi.size();                 // draw index after the segment
+        // group the shots by their choice tuple
+        std::vector<std::pair<std::string, std::vector<uint64_t>>> groups;
+        {
+          std::map<std::string, size_t> index;
+          std::string sig(multi.size(), '\0');
+          for (uint64_t sh : shots) {
+            for (size_t c = 0; c < multi.size(); ++c) sig[c] = (char)select_kraus(multi[c].second, uniforms[sh * draws_per_shot + di0 + c]);
+            auto it = index.find(sig);
+            if (it == index.end()) { it = index.emplace(sig, groups.size()).first; groups.emplace_back(sig, std::vector<uint64_t>()); }
+            groups[it->second].second.push_back(sh);
+          }
+          for (size_t g = 0; g + 1 < groups.size(); ++g)
+            if (std::find(groups[g].second.begin(), groups[g].second.end(), last_shot) != groups[g].second.end()) { std::swap(groups[g], groups.back()); break; }
+        }
+        double2* ck = nullptr;
+        if (groups.size() > 1) { RET(ckpt_get(&ck)); CU(h, cudaMemcpyAsync(ck, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream)); }
+        for (size_t g = 0; g < groups.size(); ++g) {
+          if (g) CU(h, cudaMemcpyAsync(h->state, ck, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
+          std::vector<uint64_t>& gs = groups[g].second;
+          // ---- the segment with this group's choices, as one plan (cut only where a non-unitary Kraus operator needs the norm)
+          std::vector<Gate> pending;
+          std::string err;
+          size_t c = 0;
+          for (uint64_t k = k0; k < k1; ++k) {
+            const qcb_op& op = ops[k];
+            int rc = lower_ops(h->cfg, &op, 1, pending, err);
+            if (rc != QCB_OK) return fail(h, rc, err);
+            const qcb_noise_entry* e = find_noise(noise, op.kind);
+            if (!e || e->n_kraus < 1) continue;
+            int tq = noise_target(op);
+            if (tq < 0 || tq >= n) tq = 0;
+            const int kidx = (e->n_kraus == 1) ? 0 : (int)groups[g].first[c++];
+            RET(push_kraus(pending, e, kidx, tq));
+          }
+          RET(flush(pending));
+          if (k1 == n_ops) {
+            // ---- leaf: every shot of the group shares the final state.  One measure-state draw each, then readout noise
+            // (noise.clj:193-202)
+            us.resize(gs.size());
+            outs.assign(gs.size(), 0);
+            for (size_t j = 0; j < gs.size(); ++j) us[j] = uniforms[gs[j] * draws_per_shot + di1];
+            RET(sample_impl(h, us.data(), gs.size(), outs.data()));
+            for (size_t j = 0; j < gs.size(); ++j) {
+              const double* uj = uniforms + gs[j] * draws_per_shot;
+              uint64_t dj = di1 + 1, outcome = outs[j];
+              if (noise && noise->has_readout) {
+                std::vector<int> flipped;
+                for (int q = 0; q < n; ++q) {
+                  const int bitpos = n - 1 - q;
+                  const int orig = (outcome >> bitpos) & 1;
+                  double factor = 1.0;
+                  if (noise->correlation) for (int src : flipped) factor *= noise->correlation[(size_t)src * n + q];
+                  double eff = (orig ? noise->prob_1_to_0 : noise->prob_0_to_1) * factor;
+                  eff = std::min(1.0, std::max(0.0, eff));
+                  if (uj[dj++] < eff) { outcome ^= 1ULL << bitpos; flipped.push_back(q); }
+                }
+              }
+              out_outcomes[gs[j]] = outcome;
+              if (traj_out && gs[j] < max_traj)
+                CU(h, cudaMemcpyAsync(traj_out + gs[j] * 2 * h->local_count, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
             }
-            std::vector<std::pair<uint32_t, std::vector<uint64_t>>> groups;
-            split(shots, keys, groups);
-            double2* ck = nullptr;
-            if (groups.size() > 1) { RET(ckpt_get(&ck)); CU(h, cudaMemcpyAsync(ck, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream)); }
-            for (size_t g = 0; g < groups.size(); ++g) {
-              if (g) CU(h, cudaMemcpyAsync(h->state, ck, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
-              // collapse onto the group's outcome: any of its draws selects it
-              RET(measure_qubits_impl(h, mq, m, uniforms[groups[g].second[0] * draws_per_shot + di], nullptr, nullptr, nullptr, true));
-              if (groups.size() == 1) { shots.swap(groups[0].second); break; }
-              std::vector<Gate> p2;
-              RET(walk(k + 1, di + 1, groups[g].second, p2));
-            }
-            if (groups.size() > 1) { --ckpt_used; return QCB_OK; }
-            ++di;
             continue;
           }
-          int rc = lower_ops(h->cfg, &op, 1, pending, err);
-          if (rc != QCB_OK) return fail(h, rc, err);
-          const qcb_noise_entry* e = find_noise(noise, op.kind);
-          if (!e || e->n_kraus < 1) continue;
-          int tq = noise_target(op);
-          if (tq < 0 || tq >= n) tq = 0;
-          if (e->n_kraus == 1) { RET(push_kraus(pending, e, 0, tq)); continue; }
-          std::vector<uint32_t> keys(shots.size());
-          for (size_t j = 0; j < shots.size(); ++j) keys[j] = (uint32_t)select_kraus(e, uniforms[shots[j] * draws_per_shot + di]);
-          std::vector<std::pair<uint32_t, std::vector<uint64_t>>> groups;
-          split(shots, keys, groups);
-          if (groups.size() == 1) { RET(push_kraus(pending, e, (int)groups[0].first, tq)); ++di; continue; }
-          RET(flush(pending));
-          double2* ck = nullptr;
-          RET(ckpt_get(&ck));
-          CU(h, cudaMemcpyAsync(ck, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
-          for (size_t g = 0; g < groups.size(); ++g) {
-            if (g) CU(h, cudaMemcpyAsync(h->state, ck, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
-            std::vector<Gate> p2;
-            RET(push_kraus(p2, e, (int)groups[g].first, tq));
-            RET(walk(k + 1, di + 1, groups[g].second, p2));
+          // ---- :measure at k1: the group's shots split by the outcome their draw selects from the shared state's marginal
+          const qcb_op& mop = ops[k1];
+          const int32_t* mq = static_cast<const int32_t*>(mop.ext);
+          const int m = mop.n_mask;
+          std::vector<double> probs((size_t)1 << m);
+          RET(measure_qubits_impl(h, mq, m, 0.0, nullptr, nullptr, probs.data(), false));
+          double total = 0;
+          for (double v : probs) total += v;
+          std::vector<uint32_t> keys(gs.size());
+          for (size_t j = 0; j < gs.size(); ++j) {             // the selection rule of measure_qubits_impl, per shot
+            const double r = total * uniforms[gs[j] * draws_per_shot + di1];
+            uint32_t sel = 0; double cum = 0;
+            while (sel < probs.size() && (cum += probs[sel]) < r) ++sel;
+            keys[j] = sel >= probs.size() ? (uint32_t)probs.size() - 1 : sel;
           }
-          --ckpt_used;
-          return QCB_OK;
-        }
-        // ---- leaf: every shot here shares the final state.  One measure-state draw each, then readout noise (noise.clj:193-202)
-        RET(flush(pending));
-        us.resize(shots.size());
-        outs.assign(shots.size(), 0);
-        for (size_t j = 0; j < shots.size(); ++j) us[j] = uniforms[shots[j] * draws_per_shot + di];
-        RET(sample_impl(h, us.data(), shots.size(), outs.data()));
-        for (size_t j = 0; j < shots.size(); ++j) {
-          const double* uj = uniforms + shots[j] * draws_per_shot;
-          uint64_t dj = di + 1, outcome = outs[j];
-          if (noise && noise->has_readout) {
-            std::vector<int> flipped;
-            for (int q = 0; q < n; ++q) {
-              const int bitpos = n - 1 - q;
-              const int orig = (outcome >> bitpos) & 1;
-              double factor = 1.0;
-              if (noise->correlation) for (int src : flipped) factor *= noise->correlation[(size_t)src * n + q];
-              double eff = (orig ? noise->prob_1_to_0 : noise->prob_0_to_1) * factor;
-              eff = std::min(1.0, std::max(0.0, eff));
-              if (uj[dj++] < eff) { outcome ^= 1ULL << bitpos; flipped.push_back(q); }
-            }
+          std::vector<std::pair<uint32_t, std::vector<uint64_t>>> sub;
+          split(gs, keys, sub);
+          double2* ck2 = nullptr;
+          if (sub.size() > 1) { RET(ckpt_get(&ck2)); CU(h, cudaMemcpyAsync(ck2, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream)); }
+          for (size_t q = 0; q < sub.size(); ++q) {
+            if (q) CU(h, cudaMemcpyAsync(h->state, ck2, h->local_count * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
+            // collapse onto the sub-group's outcome: any of its draws selects it
+            RET(measure_qubits_impl(h, mq, m, uniforms[sub[q].second[0] * draws_per_shot + di1], nullptr, nullptr, nullptr, true));
+            RET(walk(k1 + 1, di1 + 1, sub[q].second));
           }
-          out_outcomes[shots[j]] = outcome;
-          if (traj_out && shots[j] < max_traj)
-            CU(h, cudaMemcpyAsync(traj_out + shots[j] * 2 * h->local_count, h->state, h->local_count * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+          if (sub.size() > 1) --ckpt_used;
         }
+        if (groups.size() > 1) --ckpt_used;
         return QCB_OK;
       };
       if (h->noisy_init) {
@@ -1861,8 +1882,7 @@ int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb
       for (size_t b = 0; b < h->perm.size(); ++b) h->perm[b] = (int)b;
       std::vector<uint64_t> all(n_shots);
       for (uint64_t sidx = 0; sidx < n_shots; ++sidx) all[sidx] = sidx;
-      std::vector<Gate> p0;
-      int rc = walk(0, 0, all, p0);
+      int rc = walk(0, 0, all);
       cudaStreamSynchronize(h->stream);
       for (double2* b : ckpts) cudaFree(b);
       if (rc != QCB_OK) return rc;
