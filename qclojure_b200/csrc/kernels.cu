@@ -240,6 +240,7 @@ __device__ __forceinline__ void dmma_round_run(uint32_t tile_s, const uint4* lan
   };
   auto store_D = [&](uint32_t X, const double (&D)[4]) {
     if (DBG_ON(2)) { if (D[0] + D[1] + D[2] + D[3] == 1.2345) sts_f64(tile_s, D[0]); return; }
+    __syncwarp();     // intra-warp in-place update: see k3_pp
 #pragma unroll
     for (int i = 0; i < 4; ++i) sts_f64(tile_s + (ps[i] ^ X), D[i]);
   };
@@ -269,6 +270,7 @@ __device__ __forceinline__ void dmma_round_run(uint32_t tile_s, const uint4* lan
         dmma_884_acc(D[2], D[3], A[3], Bc[1]);
         if (more) Bn[3] = lds_f64(tile_s + (pl[3] ^ Xn));
         dmma_884_acc(D[0], D[1], A[4], Bc[2]);
+        if (i) __syncwarp();
         if (i) sts_f64(tile_s + (ps[0] ^ Xp), Dp[0]);
         dmma_884_acc(D[2], D[3], A[5], Bc[2]);
         if (i) sts_f64(tile_s + (ps[1] ^ Xp), Dp[1]);
@@ -344,6 +346,7 @@ __device__ __forceinline__ void k3_store(const K3Out& o, uint32_t X, uint64_t G,
     __stcs(o.gbase + (o.g0 ^ G), double2{r0, i0});
     __stcs(o.gbase + (o.g1 ^ G), double2{r1, i1});
   } else {
+    __syncwarp();     // intra-warp in-place update: see k3_pp
     sts_c128(o.tile_s + (o.lz ^ X), r0, i0);
     sts_c128(o.tile_s + (o.lw ^ X), r1, i1);
   }
@@ -445,6 +448,10 @@ __device__ __forceinline__ void k3_pp(K3Set& c, K3Set& n, double& pr0, double& p
                                       uint64_t& pg, uint32_t tile_s, const uint4& lt, uint32_t xq, const double (&A)[6],
                                       const K3Out& out, uint64_t g_cur) {
   if (HASP) {
+    // In-place update inside a warp: the amplitudes one lane stores were loaded (as B operands) by OTHER lanes of the same
+    // warp.  Those loads fed mma.sync instructions that have completed before the results exist, so the order is given by
+    // data dependence; the __syncwarp states it in the memory model's terms as well (and is what racecheck looks for).
+    if (!DIRECT) __syncwarp();
     if (DIRECT) { __stcs(out.gbase + (out.g0 ^ pg), double2{pr0, pi0}); __stcs(out.gbase + (out.g1 ^ pg), double2{pr1, pi1}); }
     else { sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1); }
   }
@@ -505,7 +512,7 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
   k3_pp<true, false, true, DIRECT>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, 0u, A, out, gq(per - 2u));
   k3_pp<false, false, true, DIRECT>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, 0u, A, out, gq(per - 1u));
   if (DIRECT) { __stcs(out.gbase + (out.g0 ^ pg), double2{pr0, pi0}); __stcs(out.gbase + (out.g1 ^ pg), double2{pr1, pi1}); }
-  else { sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1); }
+  else { __syncwarp(); sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1); }
 }
 
 // One warp's share of a three-product round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.

@@ -158,6 +158,7 @@ struct qcb_sim {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> xtimes;   // exchange event pairs of the current call (resolved by qcb_get_stats)
   std::vector<cudaEvent_t> xev_pool;
   double2* noisy_init = nullptr;                  // qcb_noisy_set_initial_state: device copy of the trajectories' initial state
+  std::vector<double2*> ckpts;                    // state checkpoints of the noisy trajectory tree (kept between calls)
   cudaEvent_t xrecv[2] = {nullptr, nullptr}, xcopy[2] = {nullptr, nullptr}, xpack[2] = {nullptr, nullptr};
   cudaEvent_t tev0 = nullptr, tev1 = nullptr;
   std::string err;
@@ -1311,6 +1312,7 @@ int32_t qcb_destroy(qcb_handle h) {
   tile_prof_dump();
   cudaFree(h->state); cudaFree(h->d_prog); cudaFree(h->d_vals); cudaFree(h->d_partials); cudaFree(h->d_scratch); cudaFree(h->xbuf);
   cudaFree(h->noisy_init);
+  for (double2* b : h->ckpts) cudaFree(b);
   if (h->h_prog) cudaFreeHost(h->h_prog);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1726,7 +1728,7 @@ int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb
     bool tree_ok = !tree_off && n <= 26 && n_shots > 0;
     for (uint64_t k = 0; k < n_ops && tree_ok; ++k) if (ops[k].kind == QCB_OP_MEASURE && (ops[k].n_mask > MAX_HIST_BITS || !ops[k].ext)) tree_ok = false;
     if (tree_ok) {
-      std::vector<double2*> ckpts;                      // pool of device checkpoints (depth of the open splits)
+      std::vector<double2*>& ckpts = h->ckpts;          // pool of device checkpoints (depth of the open splits), kept by the handle
       size_t ckpt_used = 0;
       auto ckpt_get = [&](double2** out) -> int {
         if (ckpt_used == ckpts.size()) {
@@ -1884,7 +1886,6 @@ int32_t qcb_run_noisy(qcb_handle h, const qcb_op* ops, uint64_t n_ops, const qcb
       for (uint64_t sidx = 0; sidx < n_shots; ++sidx) all[sidx] = sidx;
       int rc = walk(0, 0, all);
       cudaStreamSynchronize(h->stream);
-      for (double2* b : ckpts) cudaFree(b);
       if (rc != QCB_OK) return rc;
       end_timing(h);
       return QCB_OK;

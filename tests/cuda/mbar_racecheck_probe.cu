@@ -56,8 +56,37 @@ __global__ void k_named(int* out) {
   }
 }
 
+// Fourth kernel: the CTA shape of k_tile_stage - 384 threads; warps 0-3 hand a shared array around through bar.sync 1, 128,
+// warps 4-7 do the same on their own array through bar.sync 2, 128 at their own pace, warps 8-11 wait on an mbarrier that
+// warp 0 completes at the end.  The hand-over under test is a rotation: in round r warp w writes its quarter, after the
+// barrier it reads the quarter of warp (w + 1) % 4 - correctly synchronised by the group's named barrier alone.
+__global__ void k_groups(int* out) {
+  __shared__ int data[2][128];
+  __shared__ uint64_t bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = warp >> 2, gw = warp & 3;
+  if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+  __syncthreads();
+  if (grp == 2) {                               // the "movers": parked on the mbarrier
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+    return;
+  }
+  int acc = 0;
+  for (int r = 0; r < 6 + 3 * grp; ++r) {       // the two groups run different numbers of rounds
+    data[grp][gw * 32 + lane] = r * 1000 + gw * 32 + lane;
+    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+    acc += data[grp][((gw + 1) & 3) * 32 + lane];
+    if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+  }
+  out[threadIdx.x] = acc;
+  if (threadIdx.x == 0) asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(&bar)) : "memory");
+}
+
 int main() {
-  int* d; cudaMalloc(&d, 128 * sizeof(int));
+  int* d; cudaMalloc(&d, 384 * sizeof(int));
+  k_groups<<<1, 384>>>(d); cudaDeviceSynchronize();
   k_barsync<<<1, 64>>>(d); cudaDeviceSynchronize();
   k_named<<<1, 128>>>(d); cudaDeviceSynchronize();
   k_mbar<<<1, 64>>>(d); cudaDeviceSynchronize();
