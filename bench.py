@@ -541,6 +541,8 @@ def run_ours(args):
 
     if rank == 0:
         step_ms = gpu_ms / args.steps
+        plan0 = L.plan_summary(n, ops, fusion=args.fusion, max_stage_cost=args.stage_cost, max_stage_rounds=args.stage_rounds,
+                               tile_bits=args.tile_bits, low_bits=args.low_bits, rank=0, world_size=world)
         roof = _roofline(stats, args.qubits, peak, peak_src, mma_flops)
         roof["traffic"], tsrc = _traffic_record(n, world, args)
         if tsrc:
@@ -560,6 +562,9 @@ def run_ours(args):
             "amplitude_updates_per_sec": n_gates * float(1 << n) * args.steps / (gpu_ms / 1000.0),
             "amplitude_updates_per_sec_per_gpu": n_gates * float(1 << args.qubits) * args.steps / (gpu_ms / 1000.0),
             "sweeps_per_step": stats["n_sweeps"], "rounds_per_step": stats["n_rounds"],
+            # passes over the shared-memory tile: a paired pass applies two dense 8x8 rounds to registers between one load
+            # and one store of the tile (rank 0's plan)
+            "passes_per_step": plan0["passes"], "paired_passes_per_step": plan0["paired_passes"],
             "gates_per_sweep": n_gates / max(1, stats["n_sweeps"]),
             "hbm_frac": roof["hbm"]["frac"], "fp64_tensor_frac": roof["fp64_tensor"]["frac"],
             "roofline": roof,

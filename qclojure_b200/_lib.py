@@ -381,5 +381,21 @@ def plan_summary(n_qubits: int, ops, **cfgkw) -> dict:
     lib.qcb_plan_summary(p, C.byref(a), C.byref(b), C.byref(c))
     nw = C.c_uint64()
     lib.qcb_plan_serialize(p, None, 0, C.byref(nw))
+    words = np.empty(int(nw.value), dtype=np.uint64)
+    lib.qcb_plan_serialize(p, words.ctypes.data_as(C.c_void_p), nw.value, C.byref(nw))
     lib.qcb_plan_destroy(p)
-    return {"stages": int(a.value), "rounds": int(b.value), "exchanges": int(c.value), "program_words": int(nw.value)}
+    # passes over the shared tile (csrc/plan.h: program layout): a paired pass (round kind 3) carries two dense rounds
+    sweeps = passes = pairs = 0
+    pos = 4
+    for _ in range(int(words[1])):
+        kind = int(words[pos]); pos += 2
+        if kind == 3:                                    # S_GROVER: marked indices follow the header
+            pos += int(words[pos - 1]) & 0xff
+        if kind != 0:
+            continue
+        nr = int(words[pos + 3])
+        sweeps += 1; passes += nr
+        pairs += sum(1 for r in range(nr) if int(words[pos + 48 + 40 * r + 17]) == 3)
+        pos += int(words[pos + 40])
+    return {"stages": int(a.value), "rounds": int(b.value), "exchanges": int(c.value), "program_words": int(nw.value),
+            "tile_sweeps": sweeps, "passes": passes, "paired_passes": pairs}

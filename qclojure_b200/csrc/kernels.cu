@@ -325,7 +325,8 @@ __device__ __forceinline__ void dmma_884_c(double& d0, double& d1, double a, dou
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
                : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
-__device__ __forceinline__ void k3_load_A(double (&A)[6], const double* __restrict__ mats, uint32_t var) {
+template <int NA>
+__device__ __forceinline__ void k3_load_A(double (&A)[NA], const double* __restrict__ mats, uint32_t var) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) A[i] = __ldg(mats + (size_t)var * K3_FRAG_DOUBLES + i * 32);
 }
@@ -367,7 +368,7 @@ struct K3State {
   uint64_t Gc, Gp;                            // DIRECT: global batch offsets of batches i, i-1
 };
 template <bool HAS1, bool HAS2, bool HASP, bool DIRECT>
-__device__ __forceinline__ void k3_iter(K3State& t, uint32_t tile_s, const uint4& lt, uint32_t x_next2, const double (&A)[6],
+__device__ __forceinline__ void k3_iter(K3State& t, uint32_t tile_s, const uint4& lt, uint32_t x_next2, const double (&A)[12],
                                         const K3Out& out, uint64_t g_next) {
   double re0, re1, im0, im1, k0n = 0, k1n = 0, ns0 = 0, ns1 = 0, nd0 = 0, nd1 = 0;
   dmma_884_c(re0, re1, A[2], t.s0, t.K0, t.K1);
@@ -390,7 +391,7 @@ __device__ __forceinline__ void k3_iter(K3State& t, uint32_t tile_s, const uint4
   t.K0 = k0n; t.K1 = k1n; t.s0 = ns0; t.s1 = ns1; t.d0 = nd0; t.d1 = nd1;
 }
 template <bool DIRECT>
-__device__ __forceinline__ void k3_batches(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[6],
+__device__ __forceinline__ void k3_batches(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12],
                                            const K3Out& out) {
   K3State t;
   t.X = btab[0] & DMMA_BATCH_OFF_MASK; t.Xp = t.X; t.Xn = t.X;
@@ -445,7 +446,7 @@ struct K3Set {
 // DIRECT: pa0 / pa1 are unused, the results go to global memory at (lane part ^ pg), pg = the batch's global offset.
 template <bool HAS1, bool HAS2, bool HASP, bool DIRECT>
 __device__ __forceinline__ void k3_pp(K3Set& c, K3Set& n, double& pr0, double& pr1, double& pi0, double& pi1, uint32_t& pa0, uint32_t& pa1,
-                                      uint64_t& pg, uint32_t tile_s, const uint4& lt, uint32_t xq, const double (&A)[6],
+                                      uint64_t& pg, uint32_t tile_s, const uint4& lt, uint32_t xq, const double (&A)[12],
                                       const K3Out& out, uint64_t g_cur) {
   if (HASP) {
     // In-place update inside a warp: the amplitudes one lane stores were loaded (as B operands) by OTHER lanes of the same
@@ -475,7 +476,7 @@ __device__ __forceinline__ void k3_pp(K3Set& c, K3Set& n, double& pr0, double& p
 }
 // per even and >= 4
 template <bool DIRECT>
-__device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[6],
+__device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12],
                                               const K3Out& out) {
   K3Set a, b;
   double pr0 = 0, pr1 = 0, pi0 = 0, pi1 = 0;
@@ -518,7 +519,7 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
 // One warp's share of a three-product round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
 template <bool DIRECT>
 __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
-                                             uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[6], uint32_t cur,
+                                             uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur,
                                              K3Out out) {
   const uint4 lt = lane_tab_r[2u * lane];
   out.tile_s = tile_s; out.lz = lt.z; out.lw = lt.w;
@@ -544,6 +545,135 @@ __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_
     K3Out o2 = out;
     o2.gtab = out.gtab + b;
     k3_batches<DIRECT>(tile_s, lt, btab + b, e - b, A, o2);
+    b = e;
+  }
+}
+
+// ------------------------------------------------------------------ paired rounds (round kind 3, tile_core.h "paired rounds")
+// Two dense 8x8 complex blocks per pass: the first block's D registers ARE the second block's B registers (the fragment
+// layouts of mma.m8n8k4 transpose lane-group bits and pattern bits for free), so a batch costs the same two 16-byte loads and
+// two 16-byte stores as a single round but carries twelve DMMA.8x8x4 - half the shared-memory traffic per tensor instruction.
+// A[0..5] = P0 P1 N0 N1 R0 R1 of the first block, A[6..11] of the second.
+__device__ __forceinline__ void k3x_load_A(double (&A)[12], const double* __restrict__ mats, uint32_t var) {
+#pragma unroll
+  for (int i = 0; i < 12; ++i) A[i] = __ldg(mats + (size_t)var * K3X_FRAG_DOUBLES + i * 32);
+}
+struct K3XSet {
+  double r0, i0, r1, i1;             // raw loads = operands of the first block
+  double s0, s1, d0, d1;             // Br + Bi, Bi - Br of the block in progress
+  double K0, K1;                     // K = P Br of the block in progress
+  double x0, x1, y0, y1;             // results of the first block (Re, Im of columns 0, 1) = operands of the second
+  uint32_t X;                        // swizzled byte offset of the batch the set currently belongs to
+};
+// first block of the batch in `n`, on its own (pipeline prologue)
+__device__ __forceinline__ void k3x_first_block(K3XSet& n, const double (&A)[12]) {
+  n.s0 = n.r0 + n.i0; n.d0 = n.i0 - n.r0; n.s1 = n.r1 + n.i1; n.d1 = n.i1 - n.r1;
+  dmma_884_c(n.K0, n.K1, A[0], n.r0, 0.0, 0.0);
+  dmma_884_c(n.K0, n.K1, A[1], n.r1, n.K0, n.K1);
+  dmma_884_c(n.x0, n.x1, A[2], n.s0, n.K0, n.K1);
+  dmma_884_c(n.y0, n.y1, A[4], n.d0, n.K0, n.K1);
+  dmma_884_c(n.x0, n.x1, A[3], n.s1, n.x0, n.x1);
+  dmma_884_c(n.y0, n.y1, A[5], n.d1, n.y0, n.y1);
+}
+// One batch of the steady state: the SECOND block of batch i (set c: x / y ready) interleaved with the FIRST block of batch
+// i+1 (set n: raw loads landed), so that dependent tensor instructions are at least two issue slots apart; the loads of batch
+// i+2 go into c's raw registers (dead since the previous call), the results of batch i-1 are stored at the top.
+template <bool HAS1, bool HAS2, bool HASP>
+__device__ __forceinline__ void k3x_pp(K3XSet& c, K3XSet& n, double& pr0, double& pr1, double& pi0, double& pi1, uint32_t& pa0, uint32_t& pa1,
+                                       uint32_t tile_s, const uint4& lt, uint32_t xq, const double (&A)[12]) {
+  if (HASP) {
+    __syncwarp();                      // in-place update inside a warp: see k3_pp
+    sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1);
+  }
+  pa0 = tile_s + (lt.z ^ c.X); pa1 = tile_s + (lt.w ^ c.X);
+  if (HAS2) {
+    c.X = xq & DMMA_BATCH_OFF_MASK;
+    lds_c128(tile_s + (lt.x ^ c.X), c.r0, c.i0);
+    lds_c128(tile_s + (lt.y ^ c.X), c.r1, c.i1);
+  }
+  dmma_884_c(c.K0, c.K1, A[6], c.x0, 0.0, 0.0);
+  if (HAS1) dmma_884_c(n.K0, n.K1, A[0], n.r0, 0.0, 0.0);
+  dmma_884_c(c.K0, c.K1, A[7], c.x1, c.K0, c.K1);
+  if (HAS1) dmma_884_c(n.K0, n.K1, A[1], n.r1, n.K0, n.K1);
+  c.s0 = c.x0 + c.y0; c.d0 = c.y0 - c.x0;
+  if (HAS1) { n.s0 = n.r0 + n.i0; n.d0 = n.i0 - n.r0; }
+  dmma_884_c(pr0, pr1, A[8], c.s0, c.K0, c.K1);
+  if (HAS1) dmma_884_c(n.x0, n.x1, A[2], n.s0, n.K0, n.K1);
+  dmma_884_c(pi0, pi1, A[10], c.d0, c.K0, c.K1);
+  if (HAS1) dmma_884_c(n.y0, n.y1, A[4], n.d0, n.K0, n.K1);
+  c.s1 = c.x1 + c.y1; c.d1 = c.y1 - c.x1;
+  if (HAS1) { n.s1 = n.r1 + n.i1; n.d1 = n.i1 - n.r1; }
+  dmma_884_c(pr0, pr1, A[9], c.s1, pr0, pr1);
+  if (HAS1) dmma_884_c(n.x0, n.x1, A[3], n.s1, n.x0, n.x1);
+  dmma_884_c(pi0, pi1, A[11], c.d1, pi0, pi1);
+  if (HAS1) dmma_884_c(n.y0, n.y1, A[5], n.d1, n.y0, n.y1);
+}
+// per even and >= 4, one matrix variant
+__device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12]) {
+  K3XSet a, b;
+  double pr0 = 0, pr1 = 0, pi0 = 0, pi1 = 0;
+  uint32_t pa0 = 0, pa1 = 0;
+  a.X = btab[0] & DMMA_BATCH_OFF_MASK;
+  b.X = btab[1] & DMMA_BATCH_OFF_MASK;
+  lds_c128(tile_s + (lt.x ^ a.X), a.r0, a.i0);
+  lds_c128(tile_s + (lt.y ^ a.X), a.r1, a.i1);
+  lds_c128(tile_s + (lt.x ^ b.X), b.r0, b.i0);
+  lds_c128(tile_s + (lt.y ^ b.X), b.r1, b.i1);
+  uint32_t xq = btab[2];
+  k3x_first_block(a, A);
+  k3x_pp<true, true, false>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  xq = btab[3];
+  k3x_pp<true, true, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+#pragma unroll 1
+  for (uint32_t i = 2; i + 2u < per; i += 2u) {
+    xq = btab[i + 2u];
+    k3x_pp<true, true, true>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+    xq = btab[i + 3u];
+    k3x_pp<true, true, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  }
+  k3x_pp<true, false, true>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
+  k3x_pp<false, false, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
+  __syncwarp();
+  sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1);
+}
+// any number of batches, one after the other (short shares, variant changes inside a share)
+__device__ __forceinline__ void k3x_batches_simple(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12]) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < per; ++i) {
+    K3XSet t;
+    t.X = btab[i] & DMMA_BATCH_OFF_MASK;
+    lds_c128(tile_s + (lt.x ^ t.X), t.r0, t.i0);
+    lds_c128(tile_s + (lt.y ^ t.X), t.r1, t.i1);
+    k3x_first_block(t, A);
+    double re0, re1, im0, im1;
+    t.s0 = t.x0 + t.y0; t.d0 = t.y0 - t.x0; t.s1 = t.x1 + t.y1; t.d1 = t.y1 - t.x1;
+    dmma_884_c(t.K0, t.K1, A[6], t.x0, 0.0, 0.0);
+    dmma_884_c(t.K0, t.K1, A[7], t.x1, t.K0, t.K1);
+    dmma_884_c(re0, re1, A[8], t.s0, t.K0, t.K1);
+    dmma_884_c(im0, im1, A[10], t.d0, t.K0, t.K1);
+    dmma_884_c(re0, re1, A[9], t.s1, re0, re1);
+    dmma_884_c(im0, im1, A[11], t.d1, im0, im1);
+    __syncwarp();
+    sts_c128(tile_s + (lt.z ^ t.X), re0, im0);
+    sts_c128(tile_s + (lt.w ^ t.X), re1, im1);
+  }
+}
+// One warp's share of a paired round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
+__device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
+                                              uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur) {
+  const uint4 lt = lane_tab_r[2u * lane];
+  if ((btab[0] >> 20) == (btab[per - 1u] >> 20)) {
+    if (per >= 4u && !(per & 1u)) k3x_batches_pp(tile_s, lt, btab, per, A);
+    else k3x_batches_simple(tile_s, lt, btab, per, A);
+    return;
+  }
+  uint32_t b = 0;
+  while (b < per) {
+    const uint32_t v = var_hi | (btab[b] >> 20);
+    uint32_t e = b + 1u;
+    while (e < per && (btab[e] >> 20) == (btab[b] >> 20)) ++e;
+    if (v != cur) { k3x_load_A(A, mats, v); cur = v; }
+    k3x_batches_simple(tile_s, lt, btab + b, e - b, A);
     b = e;
   }
 }
@@ -679,13 +809,13 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
     for (uint32_t b = 0; b < nbuf; ++b) { mbar_init(full + b, use_tma ? 1u : MOVER_THREADS); mbar_init(done + b, WPG); }
   __syncthreads();
   for (uint32_t idx = tid; idx < sc.n_rounds * 32u; idx += NTHREADS) {
-    const uint32_t r = idx >> 5;
-    if (round_kind(sprog, r) != (uint32_t)FORM) continue;
+    const uint32_t r = idx >> 5, kd = round_kind(sprog, r);
+    if (kd != (uint32_t)FORM && !(FORM == 2 && kd == 3u)) continue;
     if (FORM == 2) {
       K3Ctx c;
       decode_k3(sprog, r, c);
       uint32_t e[4];
-      k3_lane_entry(c, idx & 31u, e);
+      if (kd == 3u) k3x_lane_entry(c, idx & 31u, e); else k3_lane_entry(c, idx & 31u, e);
       lane_tab[2u * idx] = make_uint4(e[0], e[1], e[2], e[3]);
     } else {
       DmmaCtx c;
@@ -706,8 +836,8 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
     rtab[r] = make_uint2(hd, (uint32_t)w[2]);
   }
   for (uint32_t idx = tid; idx < sc.n_rounds * nbstride; idx += NTHREADS) {
-    const uint32_t r = idx / nbstride, b = idx - r * nbstride;
-    if (round_kind(sprog, r) != (uint32_t)FORM) continue;
+    const uint32_t r = idx / nbstride, b = idx - r * nbstride, kd = round_kind(sprog, r);
+    if (kd != (uint32_t)FORM && !(FORM == 2 && kd == 3u)) continue;
     DmmaCtx c;                                            // the batch geometry words are common to both forms
     decode_dmma(sprog, r, c);
     if (b < (1u << (c.n_grp - 3u))) batch_tab[idx] = dmma_batch_entry(c, b, m);
@@ -822,10 +952,15 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
     const uint32_t nbatch = tile_n >= 64u ? (tile_n >> 6) : 1u;
     const uint32_t per = nbatch >= (uint32_t)WPG ? nbatch / WPG : 1u, b0 = gwarp * per;
     const bool active = b0 < nbatch;
-    constexpr int NA = FORM == 2 ? 6 : 8;                 // A-fragment registers of one matrix variant
+    constexpr int NA = FORM == 2 ? 12 : 8;                // A-fragment registers of one matrix variant (12: a paired round)
     double A[NA];
     uint32_t cur = 0xffffffffu, var_hi = 0;
     DBG_DECL;
+    // a tensor-core round of this kernel's form (form 2: single three-product rounds and paired rounds)
+    auto is_mma = [&](uint32_t r) {
+      const uint32_t kd = round_kind(sprog, r);
+      return kd == (uint32_t)FORM || (FORM == 2 && kd == 3u);
+    };
     // operands of (tile j, round r): variant bits from the tile id, first variant of this warp, its A fragments
     auto prefetch = [&](uint32_t j, uint32_t r) {
       if (!active) return;
@@ -833,10 +968,12 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
       const uint2 rt = rtab[r];
       var_hi = dmma_var_hi(rt.x, ext_hi);
       cur = var_hi | (batch_tab[r * nbstride + b0] >> 20);
-      if constexpr (FORM == 2) k3_load_A(A, reinterpret_cast<const double*>(stage_g + rt.y) + lane, cur);
-      else dmma_load_A(A, reinterpret_cast<const double*>(stage_g + rt.y) + lane, cur);
+      if constexpr (FORM == 2) {
+        if (round_kind(sprog, r) == 3u) k3x_load_A(A, reinterpret_cast<const double*>(stage_g + rt.y) + lane, cur);
+        else k3_load_A(A, reinterpret_cast<const double*>(stage_g + rt.y) + lane, cur);
+      } else dmma_load_A(A, reinterpret_cast<const double*>(stage_g + rt.y) + lane, cur);
     };
-    if (grp < T && (MMA_ONLY || round_kind(sprog, 0) == (uint32_t)FORM)) prefetch(grp, 0);
+    if (grp < T && is_mma(0)) prefetch(grp, 0);
     PF_DECL;
     for (uint32_t j = grp; j < T; j += NG) {
       const uint32_t b = j % nbuf;
@@ -847,8 +984,8 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
         PF_ADD(PF_C_BARRIER);
         uint32_t nj = j, nr = r + 1u;
         if (nr == sc.n_rounds) { nr = 0; nj = j + NG; }
-        const bool next_mma = nj < T && (MMA_ONLY || round_kind(sprog, nr) == (uint32_t)FORM);
-        if (MMA_ONLY || round_kind(sprog, r) == (uint32_t)FORM) {
+        const bool next_mma = nj < T && (MMA_ONLY || is_mma(nr));
+        if (MMA_ONLY || is_mma(r)) {
           double Ac[NA];
 #pragma unroll
           for (int i = 0; i < NA; ++i) Ac[i] = A[i];
@@ -858,6 +995,10 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
           PF_ADD(PF_C_SETUP);
           if (active) {
             if constexpr (FORM == 2) {
+              if (round_kind(sprog, r) == 3u) {
+                k3x_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
+                              mats, lane, Ac, curc);
+              } else {
               K3Out out;
               out.gtab = gtab + b0; out.gbase = nullptr; out.g0 = out.g1 = 0;
               if (direct && r + 1u == sc.n_rounds) {
@@ -867,6 +1008,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
               } else {
                 k3_round_run<false>(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
                                     mats, lane, Ac, curc, out);
+              }
               }
             } else
               dmma_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,

@@ -77,6 +77,9 @@ Config config_from(const qcb_config& c) {
   if (const char* e = std::getenv("QCB_MMA_FORM")) k.mma_form = std::atoi(e) ? 1 : 0;      // experiment knob
   if (const char* e = std::getenv("QCB_DIRECT_STORE")) k.direct_store = std::atoi(e) ? 1 : 0;
   k.tma = (c.tile_mover == 2) ? 1 : 0;
+  if (const char* e = std::getenv("QCB_PAIR_ROUNDS")) k.pair_rounds = std::atoi(e) ? 1 : 0;   // experiment knobs
+  if (const char* e = std::getenv("QCB_PAIR_YIELD_PCT")) k.pair_yield_pct = std::atoi(e);
+  if (const char* e = std::getenv("QCB_PAIR_COST_Q")) k.pair_cost_q = std::max(4, std::atoi(e));
   if (const char* e = std::getenv("QCB_THIN_DEFER")) k.thin_defer = std::atoi(e);            // experiment knob
   if (const char* e = std::getenv("QCB_WINDOW_SEARCH")) k.window_search = std::atoi(e);
   if (const char* e = std::getenv("QCB_ROUND_YIELD_PCT")) k.round_yield_pct = std::atoi(e);   // 0 = greedy tiles / rounds only
@@ -459,7 +462,8 @@ static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& wo
     words[rb + 0] = rd.slot_pos.size();
     for (size_t j = 0; j < rd.slot_pos.size(); ++j) words[rb + 4 + j] = (uint64_t)rd.slot_pos[j];
     if (rd.dmma) {
-      words[rb + 17] = rd.k3 ? 2 : 1;
+      words[rb + 17] = rd.pair ? 3 : (rd.k3 ? 2 : 1);
+      if (rd.pair) words[rb + 36] = (uint64_t)rd.mmap2[0] | ((uint64_t)rd.mmap2[1] << 4) | ((uint64_t)rd.mmap2[2] << 8);
       words[rb + 18] = rd.grp_pos.size();
       for (size_t j = 0; j < rd.grp_pos.size() && j < 10; ++j) words[rb + 19 + j] = (uint64_t)rd.grp_pos[j];
       words[rb + 29] = rd.cond_pos.size();
@@ -854,6 +858,82 @@ static void build_k3_round(const Config& cfg, const Stage& st, Round& rd) {
   (void)cfg;
 }
 
+// Two rounds in one pass (round kind 3, tile_core.h "paired rounds"): rd.gates on the slot triple S1 = rd.slot_pos, then
+// rd.gates2 on the disjoint triple S2, which becomes the batch's three lane bits grp_pos[0..2].  form_rounds guarantees that
+// neither block has a condition bit inside the other's slots.  A-fragment registers 0..5 = first block (as build_k3_round),
+// 6..11 = second block with its columns in the order the hardware enumerates the lane-group index.
+// Bank conflicts: a load quarter varies k-index bits 0, 1 (two S1 bits) and grp_pos[0] (an S2 bit); a store quarter varies
+// column bits 1, 2 (two S1 bits, mmap[1], mmap[2]) and m-index bit 0 of the second block (an S2 bit, mmap2[0]).
+static void build_k3_pair_round(const Config& cfg, const Stage& st, Round& rd) {
+  const int m = st.m;
+  uint64_t s1 = 0, s2 = rd.slot_mask2;
+  for (int p : rd.slot_pos) s1 |= 1ULL << p;
+  uint64_t cond = 0;
+  for (const Gate& g : rd.gates) cond |= gate_bits(g) & ~s1;
+  for (const Gate& g : rd.gates2) cond |= gate_bits(g) & ~s2;
+  rd.cond_pos.clear();
+  for (int p = 0; p < 64; ++p) if ((cond >> p) & 1) rd.cond_pos.push_back(p);
+  uint64_t busy = s1 | s2 | cond;
+  for (int p = m - 1; p >= 0 && popc(s1) < 3; --p) if (!((busy >> p) & 1)) { s1 |= 1ULL << p; busy |= 1ULL << p; }
+  for (int p = m - 1; p >= 0 && popc(s2) < 3; --p) if (!((busy >> p) & 1)) { s2 |= 1ULL << p; busy |= 1ULL << p; }
+  rd.slot_pos.clear();
+  std::vector<int> t2;
+  for (int p = 0; p < m; ++p) { if ((s1 >> p) & 1) rd.slot_pos.push_back(p); if ((s2 >> p) & 1) t2.push_back(p); }
+  const int rb = st.layout_c;
+  auto distinct3 = [&](int a, int b, int d) {
+    const int ca = chunk_class(a, rb), cb = chunk_class(b, rb), cd = chunk_class(d, rb);
+    return ca >= 0 && cb >= 0 && cd >= 0 && ca != cb && cb != cd && ca != cd;
+  };
+  int bkc = 2, bg0 = 0, bmx = 0, bh = 0;
+  for (int kc = 0, best = -1; kc < 3 && best < 1; ++kc) for (int g0 = 0; g0 < 3 && best < 1; ++g0) {
+    const int sc = distinct3(rd.slot_pos[(kc + 1) % 3], rd.slot_pos[(kc + 2) % 3], t2[g0]) ? 1 : 0;
+    if (sc > best) { best = sc; bkc = kc; bg0 = g0; }
+  }
+  // group bit order of S2: the load-quarter bit first, the other two ascending
+  std::vector<int> g2 = {t2[bg0]};
+  for (int j = 0; j < 3; ++j) if (j != bg0) g2.push_back(t2[j]);
+  for (int mx = 0, best = -1; mx < 3 && best < 1; ++mx) for (int h = 0; h < 3 && best < 1; ++h) {
+    const int sc = distinct3(rd.slot_pos[(mx + 1) % 3], rd.slot_pos[(mx + 2) % 3], g2[h]) ? 1 : 0;
+    if (sc > best) { best = sc; bmx = mx; bh = h; }
+  }
+  {
+    int a = (bkc + 1) % 3, b = (bkc + 2) % 3;
+    if (a > b) std::swap(a, b);
+    rd.kmap[0] = a; rd.kmap[1] = b; rd.kmap[2] = bkc;
+    int r0 = (bmx + 1) % 3, r1 = (bmx + 2) % 3;
+    if (r0 > r1) std::swap(r0, r1);
+    rd.mmap[0] = bmx; rd.mmap[1] = r0; rd.mmap[2] = r1;
+    int h0 = (bh + 1) % 3, h1 = (bh + 2) % 3;
+    if (h0 > h1) std::swap(h0, h1);
+    rd.mmap2[0] = bh; rd.mmap2[1] = h0; rd.mmap2[2] = h1;
+  }
+  rd.grp_pos = g2;
+  for (int p = 0; p < m; ++p) if (!(((s1 | s2 | cond) >> p) & 1)) rd.grp_pos.push_back(p);
+  for (int p = 0; p < m; ++p) if ((cond >> p) & 1) rd.grp_pos.push_back(p);
+  const int k = (int)rd.cond_pos.size();
+  const size_t nvar = (size_t)1 << k, FD = 2 * K3_FRAG_DOUBLES_HOST;
+  rd.frag.assign(nvar * FD, 0.0);
+  auto pattern_of = [&](int idx, const int (&map)[3]) { return (((idx >> 0) & 1) << map[0]) | (((idx >> 1) & 1) << map[1]) | (((idx >> 2) & 1) << map[2]); };
+  for (size_t var = 0; var < nvar; ++var) {
+    uint64_t fixed = 0;
+    for (int j = 0; j < k; ++j) if ((var >> j) & 1) fixed |= 1ULL << rd.cond_pos[j];
+    cplx M1[8][8], M2[8][8];
+    for (int row = 0; row < 8; ++row) for (int col = 0; col < 8; ++col) M1[row][col] = M2[row][col] = cplx{row == col ? 1.0 : 0.0, 0.0};
+    for (const Gate& g : rd.gates) small_apply_cols(g, rd.slot_pos, M1, 8, fixed);
+    for (const Gate& g : rd.gates2) small_apply_cols(g, g2, M2, 8, fixed);
+    for (int reg = 0; reg < 6; ++reg) for (int lane = 0; lane < 32; ++lane) {
+      const int mi = lane / 4, ki = lane % 4 + 4 * (reg & 1);
+      const cplx z1 = M1[pattern_of(mi, rd.mmap)][pattern_of(ki, rd.kmap)];
+      const cplx z2 = M2[pattern_of(mi, rd.mmap2)][2 * (ki & 3) + (ki >> 2)];     // tile_core.h: k3x_hw_k_to_group
+      rd.frag[var * FD + (size_t)reg * 32 + lane] = (reg < 2) ? (z1.re + z1.im) : (reg < 4 ? -z1.im : z1.re);
+      rd.frag[var * FD + (size_t)(6 + reg) * 32 + lane] = (reg < 2) ? (z2.re + z2.im) : (reg < 4 ? -z2.im : z2.re);
+    }
+  }
+  rd.dmma = true;
+  rd.k3 = true;
+  (void)cfg;
+}
+
 static void fuse_round(Round& rd) {
   const int r = (int)rd.slot_pos.size();
   if (r == 0 || rd.gates.size() < 2) return;
@@ -893,11 +973,14 @@ struct RoundGate {
 
 // One candidate round: scan the pending gates in order and take every gate that fits slot bits inside `Rcap` (at most
 // MAX_SLOT_BITS of them).  Returns indices into the pending list (taken / rest, order preserved) - no gate is copied.
+// Partner search of a paired round (tile_core.h "paired rounds"): touched0 = condition bits of the first block (they count
+// against MAX_COND_BITS), avoid = the first block's slot bits - a gate that touches one of them cannot join the second block,
+// neither as a target nor as a condition.
 static void pick_round(const Config& cfg, const Stage& st, const std::vector<RoundGate>& pg, uint64_t Rcap, std::vector<int>& taken,
-                       std::vector<int>& rest, uint64_t& R_out) {
+                       std::vector<int>& rest, uint64_t& R_out, uint64_t touched0 = 0, uint64_t avoid = 0, bool partner = false) {
   const int rmax = std::min(MAX_SLOT_BITS, st.m);
   const bool use_mma = cfg.dense_mma && st.m >= 6;
-  uint64_t R = 0, touched = 0, bx = 0, bz = 0;          // touched = bits of accepted gates; bx / bz = Blocker state
+  uint64_t R = 0, touched = touched0, bx = 0, bz = 0;   // touched = bits of accepted gates; bx / bz = Blocker state
   taken.clear();
   rest.clear();
   auto fits = [&](uint64_t Rn) { return popc(Rn) <= rmax && (Rn & ~Rcap) == 0; };
@@ -906,6 +989,7 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
     auto block = [&]() { bx |= g.t; bz |= g.d; rest.push_back((int)gi); };
     auto accept = [&](uint64_t Rn) { R = Rn; touched |= g.bits; taken.push_back((int)gi); };
     if ((g.t & (bx | bz)) || (g.d & bx)) { block(); continue; }
+    if (partner && (g.reflect || (g.bits & avoid))) { block(); continue; }
     // prefer making the gate *pure* (every tile-local bit it touches becomes a slot bit): pure gates fold into
     // the round's dense block for free; controls / diagonal operands on tile-id or rank bits can never be slots
     if (use_mma && !g.reflect) {
@@ -931,15 +1015,26 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
 }
 
 // Form shared-memory rounds from the gates of one stage (gates already in ext space; targets < m).
+// The round budget is counted in quarter rounds: a single round costs 4, a paired pass cfg.pair_cost_q (default 6).
+static void materialize_round(const Config& cfg, const Stage& st, Round& rd) {
+  if (rd.pair) { build_k3_pair_round(cfg, st, rd); return; }
+  if (dmma_eligible(cfg, st, rd)) { if (cfg.mma_form == 0) build_k3_round(cfg, st, rd); else build_dmma_round(cfg, st, rd); }
+  else if (cfg.fusion) fuse_round(rd);
+}
+
 static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, int max_rounds, bool materialize = true) {
   std::vector<Gate> pending = gates;
   const bool search = cfg.fusion && cfg.window_search && cfg.dense_mma && st.m >= 6;
+  const bool pairing = search && cfg.pair_rounds && cfg.mma_form == 0 && !cfg.tma && !cfg.direct_store && st.m >= 10;
   const uint64_t tile_mask = (1ULL << st.m) - 1ULL;
   std::vector<RoundGate> pg;
-  std::vector<int> taken, rest, ctaken, crest;
-  while (!pending.empty() && (int)st.rounds.size() < std::max(1, max_rounds)) {
+  std::vector<int> taken, rest, ctaken, crest, ptaken, prest;
+  uint64_t targeted = 0;
+  // per-gate facts of the current pending list
+  auto prepare = [&]() {
     pg.resize(pending.size());
-    uint64_t later_targets = 0, targeted = 0;
+    uint64_t later_targets = 0;
+    targeted = 0;
     for (size_t i = pending.size(); i-- > 0;) {
       const Gate& g = pending[i];
       RoundGate& r = pg[i];
@@ -950,38 +1045,78 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
       later_targets |= r.t;
       targeted |= r.t;
     }
-    uint64_t R = 0;
-    pick_round(cfg, st, pg, ~0ULL, taken, rest, R);             // greedy: slot bits follow the first gates in line
-    if (search && pending.size() > taken.size()) {
-      // every triple of tile-local bits some pending gate targets is a candidate slot set; keep the round that absorbs
-      // most gates (a tensor-core round costs the same however many gates it folds)
+  };
+  // Best round of the current pending list: greedy (slot bits follow the first gates in line), then - with the search on -
+  // every triple of tile-local bits some pending gate targets; keep the round that absorbs most gates (a tensor-core round
+  // costs the same however many gates it folds).  partner: slots must avoid `forbid`, see pick_round.
+  auto choose = [&](bool partner, uint64_t forbid, uint64_t touched0, uint64_t avoid, std::vector<int>& btaken, std::vector<int>& brest,
+                    uint64_t& bR) {
+    pick_round(cfg, st, pg, partner ? ~forbid : ~0ULL, btaken, brest, bR, touched0, avoid, partner);
+    if (search && pending.size() > btaken.size()) {
       std::vector<int> tb;
-      for (int b = 0; b < st.m; ++b) if ((targeted >> b) & 1) tb.push_back(b);
+      for (int b = 0; b < st.m; ++b) if (((targeted & ~forbid) >> b) & 1) tb.push_back(b);
       uint64_t cR = 0;
       for (size_t i = 0; i < tb.size(); ++i) for (size_t j = i + 1; j < tb.size(); ++j) for (size_t k = j + 1; k < tb.size(); ++k) {
         const uint64_t cap = (1ULL << tb[i]) | (1ULL << tb[j]) | (1ULL << tb[k]);
-        pick_round(cfg, st, pg, cap, ctaken, crest, cR);
-        if (ctaken.size() > taken.size()) { taken.swap(ctaken); rest.swap(crest); R = cR; }
+        pick_round(cfg, st, pg, cap, ctaken, crest, cR, touched0, avoid, partner);
+        if (ctaken.size() > btaken.size()) { btaken.swap(ctaken); brest.swap(crest); bR = cR; }
       }
     }
+  };
+  const int budget_q = 4 * std::max(1, max_rounds);
+  int used_q = 4 * (int)st.rounds.size();
+  size_t members = st.rounds.size();                 // rounds formed so far, a paired pass counting two
+  bool have_pre = false;                             // the next round has been chosen already (while looking for a partner)
+  uint64_t R = 0, pR = 0;
+  while (!pending.empty() && used_q + 4 <= budget_q) {
+    if (have_pre) { taken.swap(ptaken); rest.swap(prest); R = pR; have_pre = false; }
+    else { prepare(); choose(false, 0, 0, 0, taken, rest, R); }
     if (taken.empty()) break;                              // nothing fits a round of this stage: leave the rest pending
     // a thin round costs as much as a full one: leave its gates to the next sweep, whose tile search starts afresh
-    if (search && cfg.round_yield_pct > 0 && st.rounds.size() >= 2 && !st.absorbed.empty() &&
-        taken.size() * 100 * st.rounds.size() < (size_t)cfg.round_yield_pct * st.absorbed.size()) break;
+    if (search && cfg.round_yield_pct > 0 && members >= 2 && !st.absorbed.empty() &&
+        taken.size() * 100 * members < (size_t)cfg.round_yield_pct * st.absorbed.size()) break;
     Round rd;
     for (int i : taken) { rd.gates.push_back(pending[i]); st.absorbed.push_back(pending[i].uid); rd.uids.push_back(pending[i].uid); }
     rd.slot_mask = R;
-    std::vector<Gate> next;
-    next.reserve(rest.size());
-    for (int i : rest) next.push_back(std::move(pending[i]));
+    {
+      std::vector<Gate> next;
+      next.reserve(rest.size());
+      for (int i : rest) next.push_back(std::move(pending[i]));
+      pending.swap(next);
+    }
     // unfused mode keeps exactly one gate per round anyway (one gate per stage)
     for (int b = 0; b < st.m; ++b) if ((R >> b) & 1) rd.slot_pos.push_back(b);
-    if (materialize) {
-      if (dmma_eligible(cfg, st, rd)) { if (cfg.mma_form == 0) build_k3_round(cfg, st, rd); else build_dmma_round(cfg, st, rd); }
-      else if (cfg.fusion) fuse_round(rd);
+    used_q += 4; ++members;
+    // ---- a partner for this round?  Candidates: slot triples disjoint from this round's slots and condition bits, holding
+    // only gates that do not touch this round's slots.  It is taken when it absorbs at least pair_yield_pct % of what the best
+    // unrestricted next round would (which is then kept as the next round when the partner is refused).
+    if (pairing && !pending.empty() && used_q - 4 + cfg.pair_cost_q <= budget_q && dmma_eligible(cfg, st, rd)) {
+      uint64_t condA = 0;
+      for (const Gate& g : rd.gates) condA |= gate_bits(g) & ~R;
+      const int kl = popc(condA & tile_mask);
+      prepare();
+      choose(false, 0, 0, 0, ptaken, prest, pR);
+      have_pre = true;
+      std::vector<int> qtaken, qrest;
+      uint64_t qR = 0;
+      if (popc(R) + 3 + kl <= st.m) choose(true, R | (condA & tile_mask), condA, R, qtaken, qrest, qR);
+      uint64_t condB = 0;
+      for (int i : qtaken) condB |= pg[i].bits & ~qR;
+      const bool roomy = 6 + popc((condA | condB) & tile_mask) <= st.m && popc(condA | condB) <= MAX_COND_BITS;
+      if (!qtaken.empty() && roomy && qtaken.size() * 100 >= (size_t)cfg.pair_yield_pct * ptaken.size()) {
+        rd.pair = true;
+        rd.slot_mask2 = qR;
+        for (int i : qtaken) { rd.gates2.push_back(pending[i]); st.absorbed.push_back(pending[i].uid); rd.uids2.push_back(pending[i].uid); }
+        std::vector<Gate> next;
+        next.reserve(qrest.size());
+        for (int i : qrest) next.push_back(std::move(pending[i]));
+        pending.swap(next);
+        used_q += cfg.pair_cost_q - 4; ++members;
+        have_pre = false;
+      }
     }
+    if (materialize) materialize_round(cfg, st, rd);
     st.rounds.push_back(std::move(rd));
-    pending.swap(next);
   }
 }
 
@@ -996,8 +1131,17 @@ static void replay_rounds(const Config& cfg, Stage& st, const std::vector<Gate>&
       st.absorbed.push_back(u);
     }
     for (int b = 0; b < st.m; ++b) if ((rd.slot_mask >> b) & 1) rd.slot_pos.push_back(b);
-    if (dmma_eligible(cfg, st, rd)) { if (cfg.mma_form == 0) build_k3_round(cfg, st, rd); else build_dmma_round(cfg, st, rd); }
-    else if (cfg.fusion) fuse_round(rd);
+    if (r < tr.round_pair.size() && tr.round_pair[r] && r + 1 < tr.round_uids.size()) {
+      ++r;                                                   // the next recorded round is this one's partner
+      rd.pair = true;
+      rd.uids2 = tr.round_uids[r];
+      rd.slot_mask2 = tr.round_slots[r];
+      for (int u : rd.uids2) {
+        for (const Gate& g : gates) if (g.uid == u) { rd.gates2.push_back(g); break; }
+        st.absorbed.push_back(u);
+      }
+    }
+    materialize_round(cfg, st, rd);
     st.rounds.push_back(std::move(rd));
   }
 }
@@ -1006,7 +1150,8 @@ void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const
   key.clear();
   key.reserve(16 + perm_in.size() + 6 * gates.size());
   const int c[] = {cfg.n_total, cfg.n_local, cfg.rank, cfg.world, cfg.tile_bits, cfg.low_bits, cfg.fusion, cfg.max_stage_cost,
-                   cfg.max_stage_rounds, cfg.dense_mma + 16 * cfg.mma_form + 32 * cfg.direct_store, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer};
+                   cfg.max_stage_rounds, cfg.dense_mma + 16 * cfg.mma_form + 32 * cfg.direct_store, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer,
+                   cfg.pair_rounds + 2 * cfg.pair_yield_pct + 512 * cfg.pair_cost_q};
   for (int v : c) key.push_back((uint64_t)(int64_t)v);
   key.push_back(perm_in.size());
   for (int v : perm_in) key.push_back((uint64_t)v);
@@ -1063,7 +1208,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
       Stage& s = plan.stages[si];
       plan.stage_offsets.push_back(plan.words.size());
       plan.words.push_back((uint64_t)s.kind);
-      if (s.kind == S_TILE) { plan.words.push_back(0); encode_stage(cfg, s, plan.words); plan.n_rounds += s.rounds.size(); }
+      if (s.kind == S_TILE) { plan.words.push_back(0); encode_stage(cfg, s, plan.words); for (const Round& r : s.rounds) plan.n_rounds += r.dense_rounds(); }
       else if (s.kind == S_EXCHANGE) { plan.words.push_back((uint64_t)s.gbit | ((uint64_t)s.lbit << 8)); }
       else if (s.kind == S_GROVER) {
         plan.words.push_back((uint64_t)s.marked.size() | ((uint64_t)s.needs_sum << 8));
@@ -1184,7 +1329,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
     // re-chosen for coalescing instead of bank conflicts: the lowest free tile bits, so that the four lanes of a quad write
     // 64 contiguous bytes.  (grp_pos[0] stays: it belongs to the loads, which still come from the shared tile.)
     st.flags &= ~FLAG_DIRECT_STORE;
-    if (materialize && cfg.direct_store && !cfg.tma && m == 12 && L == 4 && !st.rounds.empty() && st.rounds.back().k3) {
+    if (materialize && cfg.direct_store && !cfg.tma && m == 12 && L == 4 && !st.rounds.empty() && st.rounds.back().k3 && !st.rounds.back().pair) {
       bool all_mma = true;
       for (const Round& r : st.rounds) all_mma = all_mma && r.dmma;
       if (all_mma) {
@@ -1244,7 +1389,11 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
     for (size_t k = 0; k < taken.size(); ++k) if (absorbed[pending[taken[k]]]) st.src_gates.push_back(pending[taken[k]]);
     if (record) {
       StageTrace tr; tr.kind = S_TILE; tr.lead = lead != nullptr; tr.tile_bits = A; tr.taken = taken_uids;
-      for (size_t r = lead ? 1 : 0; r < st.rounds.size(); ++r) { tr.round_uids.push_back(st.rounds[r].uids); tr.round_slots.push_back(st.rounds[r].slot_mask); }
+      for (size_t r = lead ? 1 : 0; r < st.rounds.size(); ++r) {
+        const Round& rd = st.rounds[r];
+        tr.round_uids.push_back(rd.uids); tr.round_slots.push_back(rd.slot_mask); tr.round_pair.push_back(rd.pair ? 1 : 0);
+        if (rd.pair) { tr.round_uids.push_back(rd.uids2); tr.round_slots.push_back(rd.slot_mask2); tr.round_pair.push_back(0); }
+      }
       record->stages.push_back(std::move(tr));
     }
     plan.stages.push_back(st);

@@ -73,9 +73,11 @@ enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_
 //     [4..7)  slot_pos[3] (tile-local, ascending)   [7..10) lane_pos[3]
 //     [10] n_ins  [11..17) ins_pos[6] ascending (slot ∪ lane positions)
 //     [17] kind (0 = interpreter round, 1 = tensor-core round as a 16x16 real block, 2 = tensor-core round in the
-//          three-product form, tile_core.h: K3Ctx)   [18] n_grp_bits   [19..29) grp_pos[10]
-//     [29] k (condition bits)  [30..34) cond_pos[4] (ext positions)  [34] j_load (kind 2: kmap)  [35] j_store (kind 2: mmap)
-//     tensor-core rounds: [2] = word offset of the A-fragment matrices (2^k * 256 / 192 doubles, after all descriptors)
+//          three-product form, tile_core.h: K3Ctx, 3 = two three-product rounds on disjoint slot triples in one pass,
+//          tile_core.h "paired rounds")   [18] n_grp_bits   [19..29) grp_pos[10]
+//     [29] k (condition bits)  [30..34) cond_pos[4] (ext positions)  [34] j_load (kinds 2, 3: kmap)  [35] j_store (kinds 2, 3: mmap)
+//     [36] kind 3: mmap2
+//     tensor-core rounds: [2] = word offset of the A-fragment matrices (2^k * 256 / 192 / 384 doubles, after all descriptors)
 //   StageDesc [42] = number of leading words (descriptors + interpreter op slots) that the kernel copies to smem
 constexpr int STAGE_WORDS = 48;
 constexpr int ROUND_WORDS = 40;
@@ -105,6 +107,14 @@ struct Round {
                                     // kind 2: 2^k * 192 doubles [variant][P0 P1 N0 N1 R0 R1][lane]
   std::vector<int> uids;            // Gate::uid of the gates the scheduler put into this round, in order (plan traces)
   uint64_t slot_mask = 0;           // the slot bits the scheduler chose (before a tensor-core round pads them to 3)
+  // paired round (round kind 3, tile_core.h "paired rounds"): a second dense block, on the disjoint slot triple
+  // grp_pos[0..2], applied to the first block's results straight from registers - one pass over the tile for two rounds
+  bool pair = false;
+  std::vector<Gate> gates2;         // gates of the second block (ext space), applied after `gates`
+  std::vector<int> uids2;
+  uint64_t slot_mask2 = 0;          // slot bits the scheduler chose for the second block (tile-local, before padding)
+  int mmap2[3] = {0, 1, 2};         // index into grp_pos[0..2] of the bit carried by bit b of the second block's m-index
+  int dense_rounds() const { return pair ? 2 : 1; }
 };
 
 struct Stage {
@@ -141,6 +151,9 @@ struct Config {
                                // 1 = 16x16 real block (m16n8k16 = eight steps, 8-byte accesses), the round-1 kernel
   int round_yield_pct = 50;    // end a stage early when the next round would absorb less than this % of the stage's average round
   int window_search = 1;       // stage builder also tries contiguous tile windows and keeps the best yield
+  int pair_rounds = 1;         // consecutive tensor-core rounds on disjoint slot triples share one pass over the tile (round kind 3)
+  int pair_yield_pct = 60;     // a partner is taken when it absorbs at least this % of what the best unrestricted next round would
+  int pair_cost_q = 6;         // cost of a paired pass in quarter rounds (a single round = 4) against the stage's round budget
   int thin_defer = 12;         // multi-GPU: a stage with fewer gates than this is not run while gates wait for an exchange
                                // (its gates ride along in the fuller sweeps after the exchange)
   int tma = 0;                 // tiles move by TMA tensor copies (layout follows the hardware 128-byte swizzle)
@@ -171,6 +184,7 @@ struct StageTrace {
   std::vector<int> taken;                    // gates handed to the stage builder (uids, in order)
   std::vector<std::vector<int>> round_uids;  // per formed round
   std::vector<uint64_t> round_slots;
+  std::vector<uint8_t> round_pair;           // per formed round: 1 = this round and the next one share a pass (round kind 3)
   int gbit = -1, lbit = -1;                  // S_EXCHANGE
   bool needs_sum = false;                    // S_GROVER (taken = the diffusion and the oracles it absorbs)
 };

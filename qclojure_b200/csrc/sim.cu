@@ -514,7 +514,7 @@ int execute_stage(qcb_sim* h, Plan& plan, size_t si) {
     const uint32_t words = (uint32_t)plan.words[off + 2 + 42];      // descriptor part only (copied to smem)
     uint64_t active = 0;
     CU(h, launch_tile_stage(h->state, h->d_prog + off + 2, plan.words.data() + off + 2, words, h->d_vals, h->num_sms, h->stream, &active, &h->maps));
-    if (active) { h->stats.n_sweeps++; h->stats.n_kernel_launches++; h->stats.n_rounds += st.rounds.size(); }
+    if (active) { h->stats.n_sweeps++; h->stats.n_kernel_launches++; for (const Round& r : st.rounds) h->stats.n_rounds += r.dense_rounds(); }
   } else if (st.kind == S_SUM) {
     // Grover diffusion: sum of all amplitudes -> (alpha, beta) = (-1, 2*mean) in d_vals[0..4)
     const int grid = red_grid(h);

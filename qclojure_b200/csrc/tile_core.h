@@ -437,9 +437,11 @@ struct K3Ctx {
   uint32_t n_grp, k, c;
   uint32_t slot_pos[3], grp_pos[10], cond_pos[4];
   uint32_t kmap[3], mmap[3];
+  uint32_t mmap2[3];                         // round kind 3 only (see "paired rounds" below)
   uint64_t mat_off;
 };
 constexpr uint32_t K3_FRAG_DOUBLES = 192;   // per variant: 6 A registers x 32 lanes (P0 P1 N0 N1 R0 R1)
+constexpr uint32_t K3X_FRAG_DOUBLES = 384;  // round kind 3: the six registers of the first block, then those of the second
 
 QCB_HD void decode_k3(const uint64_t* stage, uint32_t round_idx, K3Ctx& c) {
   const uint64_t* w = stage + T_STAGE_WORDS + (uint64_t)round_idx * T_ROUND_WORDS;
@@ -449,6 +451,7 @@ QCB_HD void decode_k3(const uint64_t* stage, uint32_t round_idx, K3Ctx& c) {
     c.slot_pos[j] = (uint32_t)w[4 + j];
     c.kmap[j] = (uint32_t)(w[34] >> (4 * j)) & 15u;
     c.mmap[j] = (uint32_t)(w[35] >> (4 * j)) & 15u;
+    c.mmap2[j] = (uint32_t)(w[36] >> (4 * j)) & 15u;
   }
   for (int j = 0; j < 10; ++j) c.grp_pos[j] = (uint32_t)w[19 + j];
   for (int j = 0; j < 4; ++j) c.cond_pos[j] = (uint32_t)w[30 + j];
@@ -474,6 +477,34 @@ QCB_HD void k3_lane_entry(const K3Ctx& c, uint32_t lane, uint32_t (&e)[4]) {
   for (uint32_t s = 0; s < 2; ++s) e[s] = swz(k3_group_offset(c, g) | k3_pattern_offset(c, q + 4u * s, c.kmap), c.c) << 4;
 #pragma unroll
   for (uint32_t i = 0; i < 2; ++i) e[2 + i] = swz(k3_group_offset(c, 2u * q + i) | k3_pattern_offset(c, g, c.mmap), c.c) << 4;
+}
+// ---- paired rounds (round kind 3): TWO dense 8x8 complex blocks, on disjoint slot triples S1 and S2, in ONE pass over the
+// shared tile.  The m8n8k4 fragment layouts transpose for free: after the first block a lane holds, as D registers i = 0, 1,
+// the amplitudes (S1 pattern lane/4, group 2(lane%4) + i); handed to the next product as B registers of k-steps 0, 1 the
+// hardware reads them as (k = lane%4 + 4i, column lane/4) - i.e. the batch's three lane-group bits have become the
+// contraction index and the first block's output pattern has become the column.  So when S2 = the lane bits grp_pos[0..2] of
+// the first block, the second block needs no trip through shared memory, no shuffle and no move: its matrix columns are
+// simply stored in the order the hardware enumerates them (hardware k <-> group index 2(k & 3) + (k >> 2)).
+// Loads are those of a kind-2 round on S1 (kmap).  After the second block a lane holds (S2 pattern lane/4 via mmap2,
+// S1 pattern 2(lane%4) + i via mmap): its two stores.  Round word [36] = mmap2: index (0..2) into grp_pos[0..2] of the S2 bit
+// carried by bit b of the second block's m-index, 4 bits each.
+QCB_HD uint32_t k3x_hw_k_to_group(uint32_t k) { return 2u * (k & 3u) + (k >> 2); }
+QCB_HD uint32_t k3x_pattern2_offset(const K3Ctx& c, uint32_t idx) {
+  uint32_t o = 0;
+#pragma unroll
+  for (uint32_t b = 0; b < 3; ++b) {
+    const uint32_t j = c.mmap2[b];
+    const uint32_t pos = (j == 0) ? c.grp_pos[0] : (j == 1 ? c.grp_pos[1] : c.grp_pos[2]);
+    o |= ((idx >> b) & 1u) << pos;
+  }
+  return o;
+}
+QCB_HD void k3x_lane_entry(const K3Ctx& c, uint32_t lane, uint32_t (&e)[4]) {
+  const uint32_t g = lane >> 2, q = lane & 3u;
+#pragma unroll
+  for (uint32_t s = 0; s < 2; ++s) e[s] = swz(k3_group_offset(c, g) | k3_pattern_offset(c, q + 4u * s, c.kmap), c.c) << 4;
+#pragma unroll
+  for (uint32_t i = 0; i < 2; ++i) e[2 + i] = swz(k3x_pattern2_offset(c, g) | k3_pattern_offset(c, 2u * q + i, c.mmap), c.c) << 4;
 }
 // tile-local (unswizzled) index of the amplitude a lane stores as result column i of a batch with base 0: where the last
 // round of a sweep writes it in global memory (direct store, stage flag T_FLAG_DIRECT_STORE)

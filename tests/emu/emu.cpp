@@ -81,9 +81,10 @@ int emu_stage_max_conflict(Emu* e, uint64_t si, int nthreads) {
   StageCtx sc; decode_stage(st, sc);
   int worst = 1;
   for (uint32_t r = 0; r < sc.n_rounds; ++r) {
-    if (round_kind(st, r) == 2u) {
+    if (round_kind(st, r) == 2u || round_kind(st, r) == 3u) {
       // 16-byte accesses are served per quarter-warp (8 lanes x 16 B = 128 B): count lanes per 16-byte bank group
       K3Ctx c; decode_k3(st, r, c);
+      const bool pair = round_kind(st, r) == 3u;
       // the stores of a direct-store round go to global memory, not to the shared tile
       const int n_which = ((st[41] & T_FLAG_DIRECT_STORE) && r + 1u == sc.n_rounds) ? 2 : 4;
       for (int quarter = 0; quarter < 4; ++quarter)
@@ -91,7 +92,7 @@ int emu_stage_max_conflict(Emu* e, uint64_t si, int nthreads) {
           int cnt[8] = {0};
           for (uint32_t l = 0; l < 8; ++l) {
             uint32_t e[4];
-            k3_lane_entry(c, quarter * 8 + l, e);
+            if (pair) k3x_lane_entry(c, quarter * 8 + l, e); else k3_lane_entry(c, quarter * 8 + l, e);
             cnt[(e[which] >> 4) & 7]++;
           }
           for (int b = 0; b < 8; ++b) if (cnt[b] > worst) worst = cnt[b];
@@ -220,6 +221,68 @@ static void emu_k3_round(double2* tile, const uint64_t* st, uint32_t r, uint64_t
   }
 }
 
+// Software model of a paired round (tile_core.h "paired rounds"; kernels.cu: k3x_round_run), lane by lane: the first block's
+// D registers are handed to the second block as its B registers exactly as the kernel does it, so the free transposition the
+// m8n8k4 fragment layouts provide is what is being tested here.
+static void emu_k3x_round(double2* tile, const uint64_t* st, uint32_t r, uint64_t ext_hi, uint32_t m, int nthreads) {
+  K3Ctx c; decode_k3(st, r, c);
+  const uint32_t NW = nthreads / 32;
+  const uint32_t nbatch = 1u << (c.n_grp - 3u);
+  const uint32_t per = nbatch >= NW ? nbatch / NW : 1u;
+  unsigned char* tb = reinterpret_cast<unsigned char*>(tile);
+  const double* mats = reinterpret_cast<const double*>(st + c.mat_off);
+  uint32_t lt[32][4];
+  for (uint32_t lane = 0; lane < 32; ++lane) k3x_lane_entry(c, lane, lt[lane]);
+  const uint32_t var_hi = k3_variant_hi(c, ext_hi, m);
+  // D = A (8x8, fragment registers a0 / a1 per lane = k-steps 0 / 1) * B (8x8, registers b0 / b1 per lane) + C, all in the
+  // per-lane register layouts of mma.m8n8k4 .f64
+  auto mma = [](const double (&a0)[32], const double (&a1)[32], const double (&b0)[32], const double (&b1)[32], const double (&c0)[32],
+                const double (&c1)[32], double (&d0)[32], double (&d1)[32]) {
+    double Am[8][8], Bm[8][8];
+    for (int lane = 0; lane < 32; ++lane) {
+      Am[lane / 4][lane % 4] = a0[lane]; Am[lane / 4][lane % 4 + 4] = a1[lane];
+      Bm[lane % 4][lane / 4] = b0[lane]; Bm[lane % 4 + 4][lane / 4] = b1[lane];
+    }
+    double o0[32], o1[32];
+    for (int lane = 0; lane < 32; ++lane) {
+      const int row = lane / 4, col = 2 * (lane % 4);
+      double x = c0[lane], y = c1[lane];
+      for (int t = 0; t < 8; ++t) { x += Am[row][t] * Bm[t][col]; y += Am[row][t] * Bm[t][col + 1]; }
+      o0[lane] = x; o1[lane] = y;
+    }
+    for (int lane = 0; lane < 32; ++lane) { d0[lane] = o0[lane]; d1[lane] = o1[lane]; }
+  };
+  for (uint32_t warp = 0; warp < NW; ++warp) {
+    for (uint32_t b = 0; b < per; ++b) {
+      const uint32_t bidx = warp * per + b;
+      if (bidx >= nbatch) break;
+      const uint32_t e = k3_batch_entry(c, bidx, m);
+      const uint32_t X = e & DMMA_BATCH_OFF_MASK, var = var_hi | (e >> 20);
+      double A[12][32], r0[32], i0[32], r1[32], i1[32], zero[32] = {};
+      for (uint32_t lane = 0; lane < 32; ++lane) {
+        for (int i = 0; i < 12; ++i) A[i][lane] = mats[(size_t)var * K3X_FRAG_DOUBLES + i * 32 + lane];
+        double2 a; std::memcpy(&a, tb + (X ^ lt[lane][0]), 16); r0[lane] = a.x; i0[lane] = a.y;
+        std::memcpy(&a, tb + (X ^ lt[lane][1]), 16); r1[lane] = a.x; i1[lane] = a.y;
+      }
+      for (int blk = 0; blk < 2; ++blk) {
+        double s0[32], s1[32], d0[32], d1[32], K0[32], K1[32], x0[32], x1[32], y0[32], y1[32];
+        for (int lane = 0; lane < 32; ++lane) { s0[lane] = r0[lane] + i0[lane]; d0[lane] = i0[lane] - r0[lane]; s1[lane] = r1[lane] + i1[lane]; d1[lane] = i1[lane] - r1[lane]; }
+        const int o = 6 * blk;
+        mma(A[o + 0], A[o + 1], r0, r1, zero, zero, K0, K1);
+        mma(A[o + 2], A[o + 3], s0, s1, K0, K1, x0, x1);
+        mma(A[o + 4], A[o + 5], d0, d1, K0, K1, y0, y1);
+        // results (x = Re, y = Im) of columns 2(lane%4) + {0, 1} become the operands of k-steps 0, 1
+        for (int lane = 0; lane < 32; ++lane) { r0[lane] = x0[lane]; r1[lane] = x1[lane]; i0[lane] = y0[lane]; i1[lane] = y1[lane]; }
+      }
+      for (uint32_t lane = 0; lane < 32; ++lane) {
+        const double2 o0{r0[lane], i0[lane]}, o1{r1[lane], i1[lane]};
+        std::memcpy(tb + (X ^ lt[lane][2]), &o0, 16);
+        std::memcpy(tb + (X ^ lt[lane][3]), &o1, 16);
+      }
+    }
+  }
+}
+
 // Run one S_TILE stage on this rank's local slice.
 int emu_run_tile_stage(Emu* e, uint64_t si, double* state, const double* dev_vals, int nthreads) {
   const Stage& S = e->plan.stages[si];
@@ -247,6 +310,7 @@ int emu_run_tile_stage(Emu* e, uint64_t si, double* state, const double* dev_val
         emu_k3_round(tile.data(), st, r, ext_hi, sc.m, nthreads, direct ? gs + base : nullptr, &sc);
         continue;
       }
+      if (round_kind(st, r) == 3u) { emu_k3x_round(tile.data(), st, r, ext_hi, sc.m, nthreads); continue; }
       RoundCtx rc; decode_round(st, r, rc);
       for (uint32_t tid = 0; tid < (uint32_t)nthreads; ++tid) {
         switch (rc.r) {

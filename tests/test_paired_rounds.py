@@ -1,0 +1,129 @@
+"""Paired rounds (round kind 3; csrc/tile_core.h "paired rounds", csrc/plan.cpp: build_k3_pair_round): two dense 8x8 complex
+blocks on disjoint slot triples in one pass over the shared tile, the second block fed from the first block's D registers.
+CPU checks through the host emulator, which models the mma.m8n8k4 fragment layouts lane by lane (tests/emu/emu.cpp:
+emu_k3x_round), against the oracle; the GPU parity tests exercise the same plans on the device."""
+import ctypes as CT
+
+import numpy as np
+import pytest
+
+from oracle import qc_oracle as O
+from qclojure_b200 import circuits as C
+from tests.emu import emu as E
+from tests.test_oracle_c import _all_gates_circuit
+from tests.test_plan_trace import _fresh, _replayed, _reangle
+
+TOL = 1e-10
+
+
+def _round_kinds(plan):
+    """[(stage, [kind of every pass])] from the serialised program (csrc/plan.h: RoundDesc word [17])."""
+    nw = E.lib().emu_program_words(plan.h, None, 0)
+    buf = (CT.c_uint64 * nw)()
+    E.lib().emu_program_words(plan.h, buf, nw)
+    w = np.frombuffer(buf, dtype=np.uint64)
+    pos, out = 4, []
+    for s in range(int(w[1])):
+        kind = int(w[pos]); pos += 2
+        if kind == 3:                                   # S_GROVER: marked indices follow
+            pos += int(w[pos - 1]) & 0xff
+        if kind != 0:
+            continue
+        st = w[pos:]
+        out.append((s, [int(st[48 + 40 * r + 17]) for r in range(int(st[3]))], st))
+        pos += int(st[40])
+    return out
+
+
+def _rand_state(n, seed):
+    rng = np.random.default_rng(seed)
+    s = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    return s / np.linalg.norm(s)
+
+
+def test_benchmark_plan_pairs_rounds_and_stays_conflict_free():
+    circ = C.random_brickwork_circuit(30, 20)
+    p = E.EmuPlan(30, circ["operations"])
+    kinds = _round_kinds(p)
+    passes = sum(len(k) for _, k, _ in kinds)
+    pairs = sum(k.count(3) for _, k, _ in kinds)
+    assert pairs >= 15                                   # a third of the passes or more carry two rounds
+    assert p.num_rounds == passes + pairs                # n_rounds counts dense blocks: a paired pass counts two
+    assert max(p.max_conflict(s) for s, _, _ in kinds) == 1
+    for _, ks, st in kinds:
+        m = int(st[1])
+        for r, kd in enumerate(ks):
+            if kd != 3:
+                continue
+            rd = st[48 + 40 * r: 48 + 40 * (r + 1)]
+            s1 = {int(rd[4 + j]) for j in range(3)}
+            s2 = {int(rd[19 + j]) for j in range(3)}
+            cond = {int(rd[30 + j]) for j in range(int(rd[29]))}
+            assert len(s1) == 3 and len(s2) == 3 and not (s1 & s2) and not (cond & (s1 | s2))
+            assert int(rd[18]) == m - 3 and len(cond) <= 4
+
+
+@pytest.mark.parametrize("n,tile,low", [(10, 10, 4), (12, 12, 4), (13, 10, 4), (14, 12, 4), (15, 13, 4), (16, 11, 3)])
+def test_paired_rounds_match_oracle_all_gates(n, tile, low):
+    """Every gate kind of the vocabulary (controls / diagonal operands become condition bits of either block)."""
+    rng = np.random.default_rng(100 + n)
+    circ = _all_gates_circuit(n, rng)
+    init = _rand_state(n, n)
+    want = O.execute_circuit(circ, init)
+    got, plans = E.run_world(n, circ["operations"], init, tile_bits=tile, low_bits=low, return_plans=True)
+    assert np.max(np.abs(got - want)) <= TOL
+    assert any(3 in k for _, k, _ in _round_kinds(plans[0]))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_paired_rounds_match_oracle_random_circuits(seed):
+    """Random mixes of dense 1q / 2q gates, controlled rotations and diagonal gates at 13-14 qubits, 4 warps per group as in
+    the kernel's default layout (nthreads = 128) and 16."""
+    rng = np.random.default_rng(seed)
+    n = 13 + seed % 2
+    circ = C.create_circuit(n)
+    for _ in range(160):
+        a, b, c = (int(x) for x in rng.choice(n, 3, replace=False))
+        k = int(rng.integers(0, 8))
+        if k == 0: C.add_gate(circ, "h", target=a)
+        elif k == 1: C.rx(circ, a, rng.random() * 6)
+        elif k == 2: C.ry(circ, a, rng.random() * 6)
+        elif k == 3: C.cnot(circ, a, b)
+        elif k == 4: C.crz(circ, a, b, rng.random() * 6)
+        elif k == 5: C.cz(circ, a, b)
+        elif k == 6: C.swap(circ, a, b)
+        else: C.toffoli(circ, a, b, c)
+    init = _rand_state(n, seed)
+    want = O.execute_circuit(circ, init)
+    for nthreads in (128, 512):
+        got, plans = E.run_world(n, circ["operations"], init, return_plans=True, nthreads=nthreads)
+        assert np.max(np.abs(got - want)) <= TOL
+    assert any(3 in k for _, k, _ in _round_kinds(plans[0]))
+
+
+def test_pairing_off_gives_the_same_state(monkeypatch):
+    circ = C.random_brickwork_circuit(14, 10)
+    init = _rand_state(14, 3)
+    on, plans_on = E.run_world(14, circ["operations"], init, return_plans=True)
+    monkeypatch.setenv("QCB_PAIR_ROUNDS", "0")
+    off, plans_off = E.run_world(14, circ["operations"], init, return_plans=True)
+    assert np.max(np.abs(on - off)) <= 1e-13
+    assert any(3 in k for _, k, _ in _round_kinds(plans_on[0]))
+    assert not any(3 in k for _, k, _ in _round_kinds(plans_off[0]))
+
+
+def test_sharded_plan_with_paired_rounds_matches_oracle():
+    circ = C.random_brickwork_circuit(15, 8)
+    want = O.execute_circuit(circ)
+    got, plans = E.run_world(15, circ["operations"], world=4, tile_bits=10, return_plans=True)
+    assert np.max(np.abs(got - want)) <= TOL
+    assert any(3 in k for pl in plans for _, k, _ in _round_kinds(pl))
+
+
+def test_trace_replay_reproduces_paired_rounds():
+    """A replayed plan (variational loop) must equal the freshly scheduled one word for word, pairs included."""
+    ops = C.random_brickwork_circuit(16, 10)["operations"]
+    ops2 = _reangle(ops, 5)
+    a = _replayed(16, ops, ops2)
+    b = _fresh(16, ops2)
+    assert a.shape == b.shape and np.array_equal(a, b)
