@@ -131,7 +131,8 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // ------------------------------------------------------------------ optional cycle accounting (make PROFILE=1)
 #ifdef QCB_TILE_PROFILE
 // ablation switches of the profiling build (QCB_TILE_DBG): 1 = skip the DMMAs, 2 = skip the fragment LDS/STS,
-// 4 = skip the HBM traffic of the mover (results are then wrong on purpose: timing experiments only)
+// 4 = skip the HBM traffic of the mover, 8 = skip the round barriers, 16 = fetch the A fragments once only
+// (results are then wrong on purpose: timing experiments only)
 __device__ int g_tile_dbg;
 #ifdef QCB_TILE_ABLATE
 __device__ __forceinline__ int tile_dbg() { int v; asm volatile("ld.global.cv.s32 %0, [%1];" : "=r"(v) : "l"(&g_tile_dbg)); return v; }
@@ -331,6 +332,21 @@ __device__ __forceinline__ void k3_load_A(double (&A)[NA], const double* __restr
   for (int i = 0; i < 6; ++i) A[i] = __ldg(mats + (size_t)var * K3_FRAG_DOUBLES + i * 32);
 }
 
+// Ablation switches of the profiling build (make ABLATE=1, QCB_TILE_DBG): ABL & 1 = no tensor instructions, ABL & 2 = no
+// fragment loads / stores (results are then wrong on purpose: timing experiments only).  ABL = 0 in the product build.
+template <int ABL>
+__device__ __forceinline__ void xmma(double& d0, double& d1, double a, double b, double c0, double c1) {
+  if (ABL & 1) { d0 = c0; d1 = c1; } else dmma_884_c(d0, d1, a, b, c0, c1);
+}
+template <int ABL>
+__device__ __forceinline__ void xlds(uint32_t addr, double& x, double& y) {
+  if (ABL & 2) { x = __hiloint2double((int)addr, 1); y = x; } else lds_c128(addr, x, y);
+}
+template <int ABL>
+__device__ __forceinline__ void xsts(uint32_t addr, double x, double y) {
+  if (ABL & 2) { asm volatile("" ::"r"(addr), "d"(x), "d"(y)); } else sts_c128(addr, x, y);
+}
+
 // Where a round's results go.  Shared tile: byte address tile_s + (lane offset ^ batch offset).  DIRECT (the last round of a
 // sweep, stage flag T_FLAG_DIRECT_STORE): straight to global memory from registers - amplitude offset (lane part ^ batch
 // part) from the tile's base; the batch parts come from gtab (built once per launch), the lane parts are per-round constants.
@@ -444,7 +460,7 @@ struct K3Set {
 // one batch: c = its operands (K, s, d ready), n = the next batch's (raw loads in flight); HAS1 / HAS2 / HASP: a batch i+1 /
 // i+2 / i-1 exists.  pr / pi = the results (stored at the top of the NEXT call), pa0 / pa1 their shared-memory addresses.
 // DIRECT: pa0 / pa1 are unused, the results go to global memory at (lane part ^ pg), pg = the batch's global offset.
-template <bool HAS1, bool HAS2, bool HASP, bool DIRECT>
+template <bool HAS1, bool HAS2, bool HASP, bool DIRECT, int ABL = 0>
 __device__ __forceinline__ void k3_pp(K3Set& c, K3Set& n, double& pr0, double& pr1, double& pi0, double& pi1, uint32_t& pa0, uint32_t& pa1,
                                       uint64_t& pg, uint32_t tile_s, const uint4& lt, uint32_t xq, const double (&A)[12],
                                       const K3Out& out, uint64_t g_cur) {
@@ -454,28 +470,28 @@ __device__ __forceinline__ void k3_pp(K3Set& c, K3Set& n, double& pr0, double& p
     // data dependence; the __syncwarp states it in the memory model's terms as well (and is what racecheck looks for).
     if (!DIRECT) __syncwarp();
     if (DIRECT) { __stcs(out.gbase + (out.g0 ^ pg), double2{pr0, pi0}); __stcs(out.gbase + (out.g1 ^ pg), double2{pr1, pi1}); }
-    else { sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1); }
+    else { xsts<ABL>(pa0, pr0, pi0); xsts<ABL>(pa1, pr1, pi1); }
   }
   if (DIRECT) pg = g_cur;
   else { pa0 = tile_s + (lt.z ^ c.X); pa1 = tile_s + (lt.w ^ c.X); }
   if (HAS2) {
     c.X = xq & DMMA_BATCH_OFF_MASK;
-    lds_c128(tile_s + (lt.x ^ c.X), c.r0, c.i0);
-    lds_c128(tile_s + (lt.y ^ c.X), c.r1, c.i1);
+    xlds<ABL>(tile_s + (lt.x ^ c.X), c.r0, c.i0);
+    xlds<ABL>(tile_s + (lt.y ^ c.X), c.r1, c.i1);
   }
-  dmma_884_c(pr0, pr1, A[2], c.s0, c.K0, c.K1);
-  if (HAS1) dmma_884_c(n.K0, n.K1, A[0], n.r0, 0.0, 0.0);
-  dmma_884_c(pi0, pi1, A[4], c.d0, c.K0, c.K1);
+  xmma<ABL>(pr0, pr1, A[2], c.s0, c.K0, c.K1);
+  if (HAS1) xmma<ABL>(n.K0, n.K1, A[0], n.r0, 0.0, 0.0);
+  xmma<ABL>(pi0, pi1, A[4], c.d0, c.K0, c.K1);
   if (HAS1) {
-    dmma_884_c(n.K0, n.K1, A[1], n.r1, n.K0, n.K1);
+    xmma<ABL>(n.K0, n.K1, A[1], n.r1, n.K0, n.K1);
     n.s0 = n.r0 + n.i0; n.d0 = n.i0 - n.r0;
   }
-  dmma_884_c(pr0, pr1, A[3], c.s1, pr0, pr1);
+  xmma<ABL>(pr0, pr1, A[3], c.s1, pr0, pr1);
   if (HAS1) { n.s1 = n.r1 + n.i1; n.d1 = n.i1 - n.r1; }
-  dmma_884_c(pi0, pi1, A[5], c.d1, pi0, pi1);
+  xmma<ABL>(pi0, pi1, A[5], c.d1, pi0, pi1);
 }
 // per even and >= 4
-template <bool DIRECT>
+template <bool DIRECT, int ABL = 0>
 __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12],
                                               const K3Out& out) {
   K3Set a, b;
@@ -485,18 +501,18 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
   auto gq = [&](uint32_t i) -> uint64_t { return DIRECT ? out.gtab[i] : 0; };
   a.X = btab[0] & DMMA_BATCH_OFF_MASK;
   b.X = btab[1] & DMMA_BATCH_OFF_MASK;
-  lds_c128(tile_s + (lt.x ^ a.X), a.r0, a.i0);
-  lds_c128(tile_s + (lt.y ^ a.X), a.r1, a.i1);
-  lds_c128(tile_s + (lt.x ^ b.X), b.r0, b.i0);
-  lds_c128(tile_s + (lt.y ^ b.X), b.r1, b.i1);
+  xlds<ABL>(tile_s + (lt.x ^ a.X), a.r0, a.i0);
+  xlds<ABL>(tile_s + (lt.y ^ a.X), a.r1, a.i1);
+  xlds<ABL>(tile_s + (lt.x ^ b.X), b.r0, b.i0);
+  xlds<ABL>(tile_s + (lt.y ^ b.X), b.r1, b.i1);
   uint32_t xq = btab[2];
   a.s0 = a.r0 + a.i0; a.d0 = a.i0 - a.r0; a.s1 = a.r1 + a.i1; a.d1 = a.i1 - a.r1;
-  dmma_884_c(a.K0, a.K1, A[0], a.r0, 0.0, 0.0);
-  dmma_884_c(a.K0, a.K1, A[1], a.r1, a.K0, a.K1);
+  xmma<ABL>(a.K0, a.K1, A[0], a.r0, 0.0, 0.0);
+  xmma<ABL>(a.K0, a.K1, A[1], a.r1, a.K0, a.K1);
   // batches 0, 1
-  k3_pp<true, true, false, DIRECT>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(0));
+  k3_pp<true, true, false, DIRECT, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(0));
   xq = btab[3];
-  k3_pp<true, true, true, DIRECT>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(1));
+  k3_pp<true, true, true, DIRECT, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(1));
   // batches 2 .. per-3 (both look-aheads exist)
   // two loop bodies (four batches) per back edge: +2 % over one (profiles/r2g_ab.log); fully unrolled, ptxas serialises the batches
 #ifdef QCB_PP_UNROLL1
@@ -506,14 +522,14 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
 #endif
   for (uint32_t i = 2; i + 2u < per; i += 2u) {
     xq = btab[i + 2u];
-    k3_pp<true, true, true, DIRECT>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(i));
+    k3_pp<true, true, true, DIRECT, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(i));
     xq = btab[i + 3u];
-    k3_pp<true, true, true, DIRECT>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(i + 1u));
+    k3_pp<true, true, true, DIRECT, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(i + 1u));
   }
-  k3_pp<true, false, true, DIRECT>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, 0u, A, out, gq(per - 2u));
-  k3_pp<false, false, true, DIRECT>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, 0u, A, out, gq(per - 1u));
+  k3_pp<true, false, true, DIRECT, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, 0u, A, out, gq(per - 2u));
+  k3_pp<false, false, true, DIRECT, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, 0u, A, out, gq(per - 1u));
   if (DIRECT) { __stcs(out.gbase + (out.g0 ^ pg), double2{pr0, pi0}); __stcs(out.gbase + (out.g1 ^ pg), double2{pr1, pi1}); }
-  else { __syncwarp(); sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1); }
+  else { __syncwarp(); xsts<ABL>(pa0, pr0, pi0); xsts<ABL>(pa1, pr1, pi1); }
 }
 
 // One warp's share of a three-product round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
@@ -530,7 +546,18 @@ __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_
   if ((btab[0] >> 20) == (btab[per - 1u] >> 20)) {
     // local condition bits are the top bits of the batch index: equal at both ends => one variant for the whole share
 #ifndef QCB_K3_ROTATE
-    if (per >= 4u && !(per & 1u)) { k3_batches_pp<DIRECT>(tile_s, lt, btab, per, A, out); return; }
+    if (per >= 4u && !(per & 1u)) {
+#ifdef QCB_TILE_ABLATE
+      switch (tile_dbg() & 3) {
+        case 1: k3_batches_pp<DIRECT, 1>(tile_s, lt, btab, per, A, out); return;
+        case 2: k3_batches_pp<DIRECT, 2>(tile_s, lt, btab, per, A, out); return;
+        case 3: k3_batches_pp<DIRECT, 3>(tile_s, lt, btab, per, A, out); return;
+        default: break;
+      }
+#endif
+      k3_batches_pp<DIRECT>(tile_s, lt, btab, per, A, out);
+      return;
+    }
 #endif
     k3_batches<DIRECT>(tile_s, lt, btab, per, A, out);
     return;
@@ -544,6 +571,10 @@ __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_
     if (v != cur) { k3_load_A(A, mats, v); cur = v; }
     K3Out o2 = out;
     o2.gtab = out.gtab + b;
+#ifndef QCB_K3_ROTATE
+    if (e - b >= 4u && !((e - b) & 1u)) k3_batches_pp<DIRECT>(tile_s, lt, btab + b, e - b, A, o2);
+    else
+#endif
     k3_batches<DIRECT>(tile_s, lt, btab + b, e - b, A, o2);
     b = e;
   }
@@ -566,75 +597,77 @@ struct K3XSet {
   uint32_t X;                        // swizzled byte offset of the batch the set currently belongs to
 };
 // first block of the batch in `n`, on its own (pipeline prologue)
+template <int ABL = 0>
 __device__ __forceinline__ void k3x_first_block(K3XSet& n, const double (&A)[12]) {
   n.s0 = n.r0 + n.i0; n.d0 = n.i0 - n.r0; n.s1 = n.r1 + n.i1; n.d1 = n.i1 - n.r1;
-  dmma_884_c(n.K0, n.K1, A[0], n.r0, 0.0, 0.0);
-  dmma_884_c(n.K0, n.K1, A[1], n.r1, n.K0, n.K1);
-  dmma_884_c(n.x0, n.x1, A[2], n.s0, n.K0, n.K1);
-  dmma_884_c(n.y0, n.y1, A[4], n.d0, n.K0, n.K1);
-  dmma_884_c(n.x0, n.x1, A[3], n.s1, n.x0, n.x1);
-  dmma_884_c(n.y0, n.y1, A[5], n.d1, n.y0, n.y1);
+  xmma<ABL>(n.K0, n.K1, A[0], n.r0, 0.0, 0.0);
+  xmma<ABL>(n.K0, n.K1, A[1], n.r1, n.K0, n.K1);
+  xmma<ABL>(n.x0, n.x1, A[2], n.s0, n.K0, n.K1);
+  xmma<ABL>(n.y0, n.y1, A[4], n.d0, n.K0, n.K1);
+  xmma<ABL>(n.x0, n.x1, A[3], n.s1, n.x0, n.x1);
+  xmma<ABL>(n.y0, n.y1, A[5], n.d1, n.y0, n.y1);
 }
 // One batch of the steady state: the SECOND block of batch i (set c: x / y ready) interleaved with the FIRST block of batch
 // i+1 (set n: raw loads landed), so that dependent tensor instructions are at least two issue slots apart; the loads of batch
 // i+2 go into c's raw registers (dead since the previous call), the results of batch i-1 are stored at the top.
-template <bool HAS1, bool HAS2, bool HASP>
+template <bool HAS1, bool HAS2, bool HASP, int ABL = 0>
 __device__ __forceinline__ void k3x_pp(K3XSet& c, K3XSet& n, double& pr0, double& pr1, double& pi0, double& pi1, uint32_t& pa0, uint32_t& pa1,
                                        uint32_t tile_s, const uint4& lt, uint32_t xq, const double (&A)[12]) {
   if (HASP) {
     __syncwarp();                      // in-place update inside a warp: see k3_pp
-    sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1);
+    xsts<ABL>(pa0, pr0, pi0); xsts<ABL>(pa1, pr1, pi1);
   }
   pa0 = tile_s + (lt.z ^ c.X); pa1 = tile_s + (lt.w ^ c.X);
   if (HAS2) {
     c.X = xq & DMMA_BATCH_OFF_MASK;
-    lds_c128(tile_s + (lt.x ^ c.X), c.r0, c.i0);
-    lds_c128(tile_s + (lt.y ^ c.X), c.r1, c.i1);
+    xlds<ABL>(tile_s + (lt.x ^ c.X), c.r0, c.i0);
+    xlds<ABL>(tile_s + (lt.y ^ c.X), c.r1, c.i1);
   }
-  dmma_884_c(c.K0, c.K1, A[6], c.x0, 0.0, 0.0);
-  if (HAS1) dmma_884_c(n.K0, n.K1, A[0], n.r0, 0.0, 0.0);
-  dmma_884_c(c.K0, c.K1, A[7], c.x1, c.K0, c.K1);
-  if (HAS1) dmma_884_c(n.K0, n.K1, A[1], n.r1, n.K0, n.K1);
+  xmma<ABL>(c.K0, c.K1, A[6], c.x0, 0.0, 0.0);
+  if (HAS1) xmma<ABL>(n.K0, n.K1, A[0], n.r0, 0.0, 0.0);
+  xmma<ABL>(c.K0, c.K1, A[7], c.x1, c.K0, c.K1);
+  if (HAS1) xmma<ABL>(n.K0, n.K1, A[1], n.r1, n.K0, n.K1);
   c.s0 = c.x0 + c.y0; c.d0 = c.y0 - c.x0;
   if (HAS1) { n.s0 = n.r0 + n.i0; n.d0 = n.i0 - n.r0; }
-  dmma_884_c(pr0, pr1, A[8], c.s0, c.K0, c.K1);
-  if (HAS1) dmma_884_c(n.x0, n.x1, A[2], n.s0, n.K0, n.K1);
-  dmma_884_c(pi0, pi1, A[10], c.d0, c.K0, c.K1);
-  if (HAS1) dmma_884_c(n.y0, n.y1, A[4], n.d0, n.K0, n.K1);
+  xmma<ABL>(pr0, pr1, A[8], c.s0, c.K0, c.K1);
+  if (HAS1) xmma<ABL>(n.x0, n.x1, A[2], n.s0, n.K0, n.K1);
+  xmma<ABL>(pi0, pi1, A[10], c.d0, c.K0, c.K1);
+  if (HAS1) xmma<ABL>(n.y0, n.y1, A[4], n.d0, n.K0, n.K1);
   c.s1 = c.x1 + c.y1; c.d1 = c.y1 - c.x1;
   if (HAS1) { n.s1 = n.r1 + n.i1; n.d1 = n.i1 - n.r1; }
-  dmma_884_c(pr0, pr1, A[9], c.s1, pr0, pr1);
-  if (HAS1) dmma_884_c(n.x0, n.x1, A[3], n.s1, n.x0, n.x1);
-  dmma_884_c(pi0, pi1, A[11], c.d1, pi0, pi1);
-  if (HAS1) dmma_884_c(n.y0, n.y1, A[5], n.d1, n.y0, n.y1);
+  xmma<ABL>(pr0, pr1, A[9], c.s1, pr0, pr1);
+  if (HAS1) xmma<ABL>(n.x0, n.x1, A[3], n.s1, n.x0, n.x1);
+  xmma<ABL>(pi0, pi1, A[11], c.d1, pi0, pi1);
+  if (HAS1) xmma<ABL>(n.y0, n.y1, A[5], n.d1, n.y0, n.y1);
 }
 // per even and >= 4, one matrix variant
+template <int ABL = 0>
 __device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12]) {
   K3XSet a, b;
   double pr0 = 0, pr1 = 0, pi0 = 0, pi1 = 0;
   uint32_t pa0 = 0, pa1 = 0;
   a.X = btab[0] & DMMA_BATCH_OFF_MASK;
   b.X = btab[1] & DMMA_BATCH_OFF_MASK;
-  lds_c128(tile_s + (lt.x ^ a.X), a.r0, a.i0);
-  lds_c128(tile_s + (lt.y ^ a.X), a.r1, a.i1);
-  lds_c128(tile_s + (lt.x ^ b.X), b.r0, b.i0);
-  lds_c128(tile_s + (lt.y ^ b.X), b.r1, b.i1);
+  xlds<ABL>(tile_s + (lt.x ^ a.X), a.r0, a.i0);
+  xlds<ABL>(tile_s + (lt.y ^ a.X), a.r1, a.i1);
+  xlds<ABL>(tile_s + (lt.x ^ b.X), b.r0, b.i0);
+  xlds<ABL>(tile_s + (lt.y ^ b.X), b.r1, b.i1);
   uint32_t xq = btab[2];
-  k3x_first_block(a, A);
-  k3x_pp<true, true, false>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  k3x_first_block<ABL>(a, A);
+  k3x_pp<true, true, false, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
   xq = btab[3];
-  k3x_pp<true, true, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  k3x_pp<true, true, true, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
 #pragma unroll 1
   for (uint32_t i = 2; i + 2u < per; i += 2u) {
     xq = btab[i + 2u];
-    k3x_pp<true, true, true>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+    k3x_pp<true, true, true, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
     xq = btab[i + 3u];
-    k3x_pp<true, true, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+    k3x_pp<true, true, true, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
   }
-  k3x_pp<true, false, true>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
-  k3x_pp<false, false, true>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
+  k3x_pp<true, false, true, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
+  k3x_pp<false, false, true, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
   __syncwarp();
-  sts_c128(pa0, pr0, pi0); sts_c128(pa1, pr1, pi1);
+  xsts<ABL>(pa0, pr0, pi0); xsts<ABL>(pa1, pr1, pi1);
 }
 // any number of batches, one after the other (short shares, variant changes inside a share)
 __device__ __forceinline__ void k3x_batches_simple(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12]) {
@@ -644,7 +677,7 @@ __device__ __forceinline__ void k3x_batches_simple(uint32_t tile_s, const uint4 
     t.X = btab[i] & DMMA_BATCH_OFF_MASK;
     lds_c128(tile_s + (lt.x ^ t.X), t.r0, t.i0);
     lds_c128(tile_s + (lt.y ^ t.X), t.r1, t.i1);
-    k3x_first_block(t, A);
+    k3x_first_block<0>(t, A);
     double re0, re1, im0, im1;
     t.s0 = t.x0 + t.y0; t.d0 = t.y0 - t.x0; t.s1 = t.x1 + t.y1; t.d1 = t.y1 - t.x1;
     dmma_884_c(t.K0, t.K1, A[6], t.x0, 0.0, 0.0);
@@ -663,8 +696,17 @@ __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane
                                               uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur) {
   const uint4 lt = lane_tab_r[2u * lane];
   if ((btab[0] >> 20) == (btab[per - 1u] >> 20)) {
-    if (per >= 4u && !(per & 1u)) k3x_batches_pp(tile_s, lt, btab, per, A);
-    else k3x_batches_simple(tile_s, lt, btab, per, A);
+    if (per >= 4u && !(per & 1u)) {
+#ifdef QCB_TILE_ABLATE
+      switch (tile_dbg() & 3) {
+        case 1: k3x_batches_pp<1>(tile_s, lt, btab, per, A); return;
+        case 2: k3x_batches_pp<2>(tile_s, lt, btab, per, A); return;
+        case 3: k3x_batches_pp<3>(tile_s, lt, btab, per, A); return;
+        default: break;
+      }
+#endif
+      k3x_batches_pp<0>(tile_s, lt, btab, per, A);
+    } else k3x_batches_simple(tile_s, lt, btab, per, A);
     return;
   }
   uint32_t b = 0;
@@ -673,7 +715,8 @@ __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane
     uint32_t e = b + 1u;
     while (e < per && (btab[e] >> 20) == (btab[b] >> 20)) ++e;
     if (v != cur) { k3x_load_A(A, mats, v); cur = v; }
-    k3x_batches_simple(tile_s, lt, btab + b, e - b, A);
+    if (e - b >= 4u && !((e - b) & 1u)) k3x_batches_pp<0>(tile_s, lt, btab + b, e - b, A);
+    else k3x_batches_simple(tile_s, lt, btab + b, e - b, A);
     b = e;
   }
 }
@@ -980,7 +1023,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
       mbar_wait(full + b, (j / nbuf) & 1u);
       PF_ADD(PF_C_WAIT_FULL);
       for (uint32_t r = 0; r < sc.n_rounds; ++r) {
-        if (r) group_bar_sync<GT>(grp);
+        if (r && !DBG_ON(8)) group_bar_sync<GT>(grp);
         PF_ADD(PF_C_BARRIER);
         uint32_t nj = j, nr = r + 1u;
         if (nr == sc.n_rounds) { nr = 0; nj = j + NG; }
@@ -991,7 +1034,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
           for (int i = 0; i < NA; ++i) Ac[i] = A[i];
           const uint32_t curc = cur, var_hic = var_hi;
           const double* mats = reinterpret_cast<const double*>(stage_g + rtab[r].y) + lane;
-          if (next_mma) prefetch(nj, nr);
+          if (next_mma && !(DBG_ON(16) && cur != 0xffffffffu)) prefetch(nj, nr);
           PF_ADD(PF_C_SETUP);
           if (active) {
             if constexpr (FORM == 2) {

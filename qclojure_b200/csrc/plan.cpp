@@ -78,8 +78,9 @@ Config config_from(const qcb_config& c) {
   if (const char* e = std::getenv("QCB_DIRECT_STORE")) k.direct_store = std::atoi(e) ? 1 : 0;
   k.tma = (c.tile_mover == 2) ? 1 : 0;
   if (const char* e = std::getenv("QCB_PAIR_ROUNDS")) k.pair_rounds = std::atoi(e) ? 1 : 0;   // experiment knobs
-  if (const char* e = std::getenv("QCB_PAIR_YIELD_PCT")) k.pair_yield_pct = std::atoi(e);
   if (const char* e = std::getenv("QCB_PAIR_COST_Q")) k.pair_cost_q = std::max(4, std::atoi(e));
+  if (const char* e = std::getenv("QCB_PAIR_SEARCH")) k.pair_search = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("QCB_PAIR_EFF_PCT")) k.pair_eff_pct = std::atoi(e);
   if (const char* e = std::getenv("QCB_THIN_DEFER")) k.thin_defer = std::atoi(e);            // experiment knob
   if (const char* e = std::getenv("QCB_WINDOW_SEARCH")) k.window_search = std::atoi(e);
   if (const char* e = std::getenv("QCB_ROUND_YIELD_PCT")) k.round_yield_pct = std::atoi(e);   // 0 = greedy tiles / rounds only
@@ -1022,14 +1023,16 @@ static void materialize_round(const Config& cfg, const Stage& st, Round& rd) {
   else if (cfg.fusion) fuse_round(rd);
 }
 
+struct RoundCand { std::vector<int> taken, rest; uint64_t R = 0; };
+
 static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, int max_rounds, bool materialize = true) {
   std::vector<Gate> pending = gates;
   const bool search = cfg.fusion && cfg.window_search && cfg.dense_mma && st.m >= 6;
   const bool pairing = search && cfg.pair_rounds && cfg.mma_form == 0 && !cfg.tma && !cfg.direct_store && st.m >= 10;
   const uint64_t tile_mask = (1ULL << st.m) - 1ULL;
-  std::vector<RoundGate> pg;
-  std::vector<int> taken, rest, ctaken, crest, ptaken, prest;
-  uint64_t targeted = 0;
+  std::vector<RoundGate> pg, pg2;
+  std::vector<int> ctaken, crest;
+  uint64_t targeted = 0, targeted2 = 0;
   // per-gate facts of the current pending list
   auto prepare = [&]() {
     pg.resize(pending.size());
@@ -1046,74 +1049,116 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
       targeted |= r.t;
     }
   };
-  // Best round of the current pending list: greedy (slot bits follow the first gates in line), then - with the search on -
-  // every triple of tile-local bits some pending gate targets; keep the round that absorbs most gates (a tensor-core round
-  // costs the same however many gates it folds).  partner: slots must avoid `forbid`, see pick_round.
-  auto choose = [&](bool partner, uint64_t forbid, uint64_t touched0, uint64_t avoid, std::vector<int>& btaken, std::vector<int>& brest,
-                    uint64_t& bR) {
-    pick_round(cfg, st, pg, partner ? ~forbid : ~0ULL, btaken, brest, bR, touched0, avoid, partner);
-    if (search && pending.size() > btaken.size()) {
+  // the same facts for a sub-list of the pending gates (what is left once a candidate round has taken its gates)
+  auto subset = [&](const std::vector<int>& idx) {
+    pg2.resize(idx.size());
+    uint64_t later_targets = 0;
+    targeted2 = 0;
+    for (size_t i = idx.size(); i-- > 0;) {
+      RoundGate r = pg[idx[i]];
+      r.later = (later_targets & r.want) != 0;
+      later_targets |= r.t;
+      targeted2 |= r.t;
+      pg2[i] = r;
+    }
+  };
+  // The K best rounds of a gate list, best first: greedy (slot bits follow the first gates in line), then - with the search
+  // on - every triple of tile-local bits some gate targets; a round is the better the more gates it absorbs (a tensor-core
+  // round costs the same however many gates it folds).  partner: slots must avoid `forbid`, see pick_round.
+  auto choose = [&](const std::vector<RoundGate>& G, uint64_t targ, bool partner, uint64_t forbid, uint64_t touched0, uint64_t avoid,
+                    size_t K, std::vector<RoundCand>& out) {
+    out.clear();
+    auto offer = [&](std::vector<int>& t, std::vector<int>& r, uint64_t R) {
+      if (t.empty()) return;
+      for (const RoundCand& c : out) if (c.R == R) return;
+      size_t pos = out.size();
+      while (pos > 0 && out[pos - 1].taken.size() < t.size()) --pos;      // strictly better moves ahead: ties keep the earlier
+      if (pos >= K) return;
+      RoundCand c; c.taken = t; c.rest = r; c.R = R;
+      out.insert(out.begin() + pos, std::move(c));
+      if (out.size() > K) out.pop_back();
+    };
+    uint64_t cR = 0;
+    pick_round(cfg, st, G, partner ? ~forbid : ~0ULL, ctaken, crest, cR, touched0, avoid, partner);
+    const size_t greedy_n = ctaken.size();
+    offer(ctaken, crest, cR);
+    if (search && G.size() > greedy_n) {
       std::vector<int> tb;
-      for (int b = 0; b < st.m; ++b) if (((targeted & ~forbid) >> b) & 1) tb.push_back(b);
-      uint64_t cR = 0;
+      for (int b = 0; b < st.m; ++b) if (((targ & ~forbid) >> b) & 1) tb.push_back(b);
       for (size_t i = 0; i < tb.size(); ++i) for (size_t j = i + 1; j < tb.size(); ++j) for (size_t k = j + 1; k < tb.size(); ++k) {
         const uint64_t cap = (1ULL << tb[i]) | (1ULL << tb[j]) | (1ULL << tb[k]);
-        pick_round(cfg, st, pg, cap, ctaken, crest, cR, touched0, avoid, partner);
-        if (ctaken.size() > btaken.size()) { btaken.swap(ctaken); brest.swap(crest); bR = cR; }
+        pick_round(cfg, st, G, cap, ctaken, crest, cR, touched0, avoid, partner);
+        if (!out.empty() && out.size() >= K && ctaken.size() <= out.back().taken.size()) continue;
+        offer(ctaken, crest, cR);
       }
     }
   };
   const int budget_q = 4 * std::max(1, max_rounds);
   int used_q = 4 * (int)st.rounds.size();
   size_t members = st.rounds.size();                 // rounds formed so far, a paired pass counting two
-  bool have_pre = false;                             // the next round has been chosen already (while looking for a partner)
-  uint64_t R = 0, pR = 0;
+  const size_t K = pairing ? (size_t)std::max(1, cfg.pair_search) : 1;
+  const double pair_eff = std::max(100, cfg.pair_eff_pct) / 100.0;   // cost of a paired pass in single rounds (measured: 1.7)
+  std::vector<RoundCand> cands, pc;
   while (!pending.empty() && used_q + 4 <= budget_q) {
-    if (have_pre) { taken.swap(ptaken); rest.swap(prest); R = pR; have_pre = false; }
-    else { prepare(); choose(false, 0, 0, 0, taken, rest, R); }
-    if (taken.empty()) break;                              // nothing fits a round of this stage: leave the rest pending
+    prepare();
+    choose(pg, targeted, false, 0, 0, 0, K, cands);
+    if (cands.empty()) break;                              // nothing fits a round of this stage: leave the rest pending
+    // ---- options: the best single round, or one of the K best rounds together with ITS best partner (a round on a disjoint
+    // slot triple whose gates touch neither the first round's slots nor - as slots - its condition bits: the two then share
+    // one pass over the tile, round kind 3).  The option that absorbs most gates per unit of cost wins.
+    size_t best_k = 0;
+    bool best_pair = false;
+    RoundCand best_b;
+    double best_eff = (double)cands[0].taken.size();
+    if (pairing && used_q + cfg.pair_cost_q <= budget_q) {
+      // the alternative to a pair is two single rounds: the best round and the best round after it, at twice the cost
+      if (!cands[0].rest.empty() && used_q + 8 <= budget_q) {
+        subset(cands[0].rest);
+        choose(pg2, targeted2, false, 0, 0, 0, 1, pc);
+        if (!pc.empty()) best_eff = 0.5 * (double)(cands[0].taken.size() + pc[0].taken.size());
+      }
+      for (size_t k = 0; k < cands.size(); ++k) {
+        const RoundCand& a = cands[k];
+        if (a.rest.empty()) continue;
+        uint64_t condA = 0;
+        bool ok = true;
+        for (int i : a.taken) { condA |= pg[i].bits & ~a.R; ok = ok && !pg[i].reflect; }
+        const int kl = popc(condA & tile_mask);
+        if (!ok || popc(condA) > MAX_COND_BITS || popc(a.R) > 3 || 6 + kl > st.m) continue;
+        subset(a.rest);
+        choose(pg2, targeted2, true, a.R | (condA & tile_mask), condA, a.R, 1, pc);
+        if (pc.empty()) continue;
+        uint64_t condB = 0;
+        for (int i : pc[0].taken) condB |= pg2[i].bits & ~pc[0].R;
+        if (6 + popc((condA | condB) & tile_mask) > st.m || popc(condA | condB) > MAX_COND_BITS) continue;
+        const double eff = (double)(a.taken.size() + pc[0].taken.size()) / pair_eff;
+        if (eff > best_eff || (!best_pair && eff == best_eff)) { best_eff = eff; best_k = k; best_pair = true; best_b = pc[0]; }
+      }
+    }
+    const RoundCand& A = cands[best_k];
     // a thin round costs as much as a full one: leave its gates to the next sweep, whose tile search starts afresh
     if (search && cfg.round_yield_pct > 0 && members >= 2 && !st.absorbed.empty() &&
-        taken.size() * 100 * members < (size_t)cfg.round_yield_pct * st.absorbed.size()) break;
+        (best_pair ? best_eff : (double)A.taken.size()) * 100 * members < (double)cfg.round_yield_pct * st.absorbed.size()) break;
     Round rd;
-    for (int i : taken) { rd.gates.push_back(pending[i]); st.absorbed.push_back(pending[i].uid); rd.uids.push_back(pending[i].uid); }
-    rd.slot_mask = R;
+    for (int i : A.taken) { rd.gates.push_back(pending[i]); st.absorbed.push_back(pending[i].uid); rd.uids.push_back(pending[i].uid); }
+    rd.slot_mask = A.R;
+    // unfused mode keeps exactly one gate per round anyway (one gate per stage)
+    for (int b = 0; b < st.m; ++b) if ((A.R >> b) & 1) rd.slot_pos.push_back(b);
+    std::vector<int> left = A.rest;
+    used_q += 4; ++members;
+    if (best_pair) {
+      rd.pair = true;
+      rd.slot_mask2 = best_b.R;
+      for (int j : best_b.taken) { const Gate& g = pending[A.rest[j]]; rd.gates2.push_back(g); st.absorbed.push_back(g.uid); rd.uids2.push_back(g.uid); }
+      left.clear();
+      for (int j : best_b.rest) left.push_back(A.rest[j]);
+      used_q += cfg.pair_cost_q - 4; ++members;
+    }
     {
       std::vector<Gate> next;
-      next.reserve(rest.size());
-      for (int i : rest) next.push_back(std::move(pending[i]));
+      next.reserve(left.size());
+      for (int i : left) next.push_back(std::move(pending[i]));
       pending.swap(next);
-    }
-    // unfused mode keeps exactly one gate per round anyway (one gate per stage)
-    for (int b = 0; b < st.m; ++b) if ((R >> b) & 1) rd.slot_pos.push_back(b);
-    used_q += 4; ++members;
-    // ---- a partner for this round?  Candidates: slot triples disjoint from this round's slots and condition bits, holding
-    // only gates that do not touch this round's slots.  It is taken when it absorbs at least pair_yield_pct % of what the best
-    // unrestricted next round would (which is then kept as the next round when the partner is refused).
-    if (pairing && !pending.empty() && used_q - 4 + cfg.pair_cost_q <= budget_q && dmma_eligible(cfg, st, rd)) {
-      uint64_t condA = 0;
-      for (const Gate& g : rd.gates) condA |= gate_bits(g) & ~R;
-      const int kl = popc(condA & tile_mask);
-      prepare();
-      choose(false, 0, 0, 0, ptaken, prest, pR);
-      have_pre = true;
-      std::vector<int> qtaken, qrest;
-      uint64_t qR = 0;
-      if (popc(R) + 3 + kl <= st.m) choose(true, R | (condA & tile_mask), condA, R, qtaken, qrest, qR);
-      uint64_t condB = 0;
-      for (int i : qtaken) condB |= pg[i].bits & ~qR;
-      const bool roomy = 6 + popc((condA | condB) & tile_mask) <= st.m && popc(condA | condB) <= MAX_COND_BITS;
-      if (!qtaken.empty() && roomy && qtaken.size() * 100 >= (size_t)cfg.pair_yield_pct * ptaken.size()) {
-        rd.pair = true;
-        rd.slot_mask2 = qR;
-        for (int i : qtaken) { rd.gates2.push_back(pending[i]); st.absorbed.push_back(pending[i].uid); rd.uids2.push_back(pending[i].uid); }
-        std::vector<Gate> next;
-        next.reserve(qrest.size());
-        for (int i : qrest) next.push_back(std::move(pending[i]));
-        pending.swap(next);
-        used_q += cfg.pair_cost_q - 4; ++members;
-        have_pre = false;
-      }
     }
     if (materialize) materialize_round(cfg, st, rd);
     st.rounds.push_back(std::move(rd));
@@ -1151,7 +1196,7 @@ void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const
   key.reserve(16 + perm_in.size() + 6 * gates.size());
   const int c[] = {cfg.n_total, cfg.n_local, cfg.rank, cfg.world, cfg.tile_bits, cfg.low_bits, cfg.fusion, cfg.max_stage_cost,
                    cfg.max_stage_rounds, cfg.dense_mma + 16 * cfg.mma_form + 32 * cfg.direct_store, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer,
-                   cfg.pair_rounds + 2 * cfg.pair_yield_pct + 512 * cfg.pair_cost_q};
+                   cfg.pair_rounds + 2 * cfg.pair_eff_pct + 2048 * cfg.pair_cost_q + 65536 * cfg.pair_search};
   for (int v : c) key.push_back((uint64_t)(int64_t)v);
   key.push_back(perm_in.size());
   for (int v : perm_in) key.push_back((uint64_t)v);
@@ -1177,7 +1222,9 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
   // (round_yield_pct); the next sweep's tile search then starts afresh on the leftovers: 72 rounds in 16 sweeps
   // instead of 88 in 10 for the benchmark circuit.
   const int max_cost = cfg.max_stage_cost > 0 ? cfg.max_stage_cost : 800;
-  const int max_rounds = cfg.max_stage_rounds > 0 ? cfg.max_stage_rounds : 5;
+  // With paired rounds (two rounds per pass over the tile at ~1.7 x the cost of one) the budget is 7 rounds' worth.
+  const bool pairs_on = cfg.fusion && cfg.window_search && cfg.dense_mma && cfg.pair_rounds && cfg.mma_form == 0 && !cfg.tma && !cfg.direct_store;
+  const int max_rounds = cfg.max_stage_rounds > 0 ? cfg.max_stage_rounds : (pairs_on ? 7 : 5);
   const double sweep_bytes = 32.0 * std::ldexp(1.0, nl);
   const uint64_t local_mask = (nl >= 64) ? ~0ULL : ((1ULL << nl) - 1);
   const uint64_t tileid_mask = ((nl - m) >= 64) ? ~0ULL : ((1ULL << (nl - m)) - 1);

@@ -152,8 +152,10 @@ struct Config {
   int round_yield_pct = 50;    // end a stage early when the next round would absorb less than this % of the stage's average round
   int window_search = 1;       // stage builder also tries contiguous tile windows and keeps the best yield
   int pair_rounds = 1;         // consecutive tensor-core rounds on disjoint slot triples share one pass over the tile (round kind 3)
-  int pair_yield_pct = 60;     // a partner is taken when it absorbs at least this % of what the best unrestricted next round would
-  int pair_cost_q = 6;         // cost of a paired pass in quarter rounds (a single round = 4) against the stage's round budget
+  int pair_search = 1;         // the partner search is run for this many of the best candidate rounds
+  int pair_eff_pct = 170;      // cost of a paired pass in % of a single round (measured on B200: 3.39 ms vs 2.0 ms at 30 qubits):
+                               // a pair is formed when its gates per unit of cost beat the best single round's
+  int pair_cost_q = 7;         // cost of a paired pass in quarter rounds (a single round = 4) against the stage's round budget
   int thin_defer = 12;         // multi-GPU: a stage with fewer gates than this is not run while gates wait for an exchange
                                // (its gates ride along in the fuller sweeps after the exchange)
   int tma = 0;                 // tiles move by TMA tensor copies (layout follows the hardware 128-byte swizzle)

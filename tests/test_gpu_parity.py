@@ -770,7 +770,8 @@ print("mover ok")
 
 
 @pytest.mark.parametrize("env", [{"QCB_TILE_MOVER": "2"}, {"QCB_TILE_MOVER": "2", "QCB_NO_TMA": "1"}, {"QCB_CONSUMERS": "2x8"},
-                                 {"QCB_CONSUMERS": "1x8", "QCB_TILE_BUFFERS": "2"}])
+                                 {"QCB_CONSUMERS": "1x8", "QCB_TILE_BUFFERS": "2"}, {"QCB_PAIR_ROUNDS": "0"},
+                                 {"QCB_PAIR_EFF_PCT": "100", "QCB_CONSUMERS": "2x8"}])
 def test_tile_kernel_variants_match_oracle(env):
     """The TMA mover (tensor copies + hardware swizzle layout), the same layout moved by the LSU mover, the other consumer
     layouts and a shorter buffer ring give the same amplitudes (the knobs are read once per process, hence the subprocess)."""
@@ -780,6 +781,45 @@ def test_tile_kernel_variants_match_oracle(env):
     out = subprocess.run([sys.executable, "-c", _MOVER_SCRIPT], cwd=root, env={**os.environ, **env}, capture_output=True,
                          text=True, timeout=600)
     assert out.returncode == 0 and "mover ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_paired_rounds_on_device_match_oracle():
+    """Paired passes (round kind 3: the second dense block consumes the first block's D registers) against the oracle, with
+    controls / diagonal operands as condition bits of either block, at sizes with one tile (12 q), many tiles (18 q) and
+    tiles whose id bits are condition bits (22 q vs the C oracle)."""
+    from tests.test_oracle_c import _all_gates_circuit
+    for n in (12, 15, 18):
+        rng = np.random.default_rng(40 + n)
+        circ = _all_gates_circuit(n, rng)
+        init = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+        init /= np.linalg.norm(init)
+        want = O.execute_circuit(circ, init)
+        ps = L.plan_summary(n, circ["operations"])
+        assert ps["paired_passes"] > 0
+        with L.StateVector(n) as sv:
+            sv.set_state(init)
+            sv.apply_circuit(circ)
+            assert float(np.max(np.abs(sv.get_state() - want))) <= 1e-10
+    n = 22
+    circ = C.random_brickwork_circuit(n, 12)
+    ps = L.plan_summary(n, circ["operations"])
+    assert ps["paired_passes"] > 0 and ps["rounds"] == ps["passes"] + ps["paired_passes"]
+    want = CO.apply_circuit(circ)
+    with L.StateVector(n) as sv:
+        sv.apply_circuit(circ)
+        assert float(np.max(np.abs(sv.get_state() - want))) <= 1e-10
+
+
+def test_swap_kernel_unit_all_partner_schedules():
+    """k_swap_global (the in-place multi-qubit exchange over peer memory) for worlds of 2, 4, 8 ranks emulated as slices on
+    ONE device, k = 1..3 exchanged qubits at arbitrary positions: tests/cuda/swap_kernel_test.cu (54 cases)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cuda", "swap_kernel_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "tests", "cuda"), "-s", "swap_kernel_test"], timeout=600)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "swap kernel ok" in out.stdout, (out.stdout[-1000:], out.stderr[-1000:])
 
 
 def test_multi_gpu_sharded_matches_oracle():
