@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <type_traits>
 
 #include "kernels.h"
 #include "tile_core.h"
@@ -340,11 +341,11 @@ __device__ __forceinline__ void xmma(double& d0, double& d1, double a, double b,
 }
 template <int ABL>
 __device__ __forceinline__ void xlds(uint32_t addr, double& x, double& y) {
-  if (ABL & 2) { x = __hiloint2double((int)addr, 1); y = x; } else lds_c128(addr, x, y);
+  if (ABL & 2) { x = __hiloint2double(0x3ff00000 | (int)(addr & 0xfffffu), (int)addr); y = __hiloint2double(0x3fe00000 | (int)(addr & 0xfffffu), 7); } else lds_c128(addr, x, y);
 }
 template <int ABL>
 __device__ __forceinline__ void xsts(uint32_t addr, double x, double y) {
-  if (ABL & 2) { asm volatile("" ::"r"(addr), "d"(x), "d"(y)); } else sts_c128(addr, x, y);
+  if (ABL & 2) { if (addr == 0xffffffffu) sts_c128(addr, x, y); } else sts_c128(addr, x, y);     // never taken, keeps the results alive
 }
 
 // Where a round's results go.  Shared tile: byte address tile_s + (lane offset ^ batch offset).  DIRECT (the last round of a
@@ -491,9 +492,11 @@ __device__ __forceinline__ void k3_pp(K3Set& c, K3Set& n, double& pr0, double& p
   xmma<ABL>(pi0, pi1, A[5], c.d1, pi0, pi1);
 }
 // per even and >= 4
-template <bool DIRECT, int ABL = 0>
+// mid(): work for the NEXT pass (operand prefetch) placed between the peeled calls, where its latency chain (table lookups,
+// address arithmetic, fragment loads) hides behind this pass's tensor instructions instead of sitting between two passes
+template <bool DIRECT, int ABL = 0, class F>
 __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12],
-                                              const K3Out& out) {
+                                              const K3Out& out, F&& mid) {
   K3Set a, b;
   double pr0 = 0, pr1 = 0, pi0 = 0, pi1 = 0;
   uint32_t pa0 = 0, pa1 = 0;
@@ -513,6 +516,7 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
   k3_pp<true, true, false, DIRECT, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(0));
   xq = btab[3];
   k3_pp<true, true, true, DIRECT, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(1));
+  mid();
   // batches 2 .. per-3 (both look-aheads exist)
   // two loop bodies (four batches) per back edge: +2 % over one (profiles/r2g_ab.log); fully unrolled, ptxas serialises the batches
 #ifdef QCB_PP_UNROLL1
@@ -533,10 +537,10 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
 }
 
 // One warp's share of a three-product round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
-template <bool DIRECT>
+template <bool DIRECT, class F>
 __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
                                              uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur,
-                                             K3Out out) {
+                                             K3Out out, F&& mid) {
   const uint4 lt = lane_tab_r[2u * lane];
   out.tile_s = tile_s; out.lz = lt.z; out.lw = lt.w;
   if (DIRECT) {   // lane parts of the global offsets: second table entry of the lane (written by the prologue for the last round)
@@ -549,19 +553,21 @@ __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_
     if (per >= 4u && !(per & 1u)) {
 #ifdef QCB_TILE_ABLATE
       switch (tile_dbg() & 3) {
-        case 1: k3_batches_pp<DIRECT, 1>(tile_s, lt, btab, per, A, out); return;
-        case 2: k3_batches_pp<DIRECT, 2>(tile_s, lt, btab, per, A, out); return;
-        case 3: k3_batches_pp<DIRECT, 3>(tile_s, lt, btab, per, A, out); return;
+        case 1: k3_batches_pp<DIRECT, 1>(tile_s, lt, btab, per, A, out, mid); return;
+        case 2: k3_batches_pp<DIRECT, 2>(tile_s, lt, btab, per, A, out, mid); return;
+        case 3: k3_batches_pp<DIRECT, 3>(tile_s, lt, btab, per, A, out, mid); return;
         default: break;
       }
 #endif
-      k3_batches_pp<DIRECT>(tile_s, lt, btab, per, A, out);
+      k3_batches_pp<DIRECT>(tile_s, lt, btab, per, A, out, mid);
       return;
     }
 #endif
+    mid();
     k3_batches<DIRECT>(tile_s, lt, btab, per, A, out);
     return;
   }
+  mid();
   // the variant changes inside the share: runs of equal variants, each through the pipelined loop
   uint32_t b = 0;
   while (b < per) {
@@ -572,7 +578,7 @@ __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_
     K3Out o2 = out;
     o2.gtab = out.gtab + b;
 #ifndef QCB_K3_ROTATE
-    if (e - b >= 4u && !((e - b) & 1u)) k3_batches_pp<DIRECT>(tile_s, lt, btab + b, e - b, A, o2);
+    if (e - b >= 4u && !((e - b) & 1u)) k3_batches_pp<DIRECT>(tile_s, lt, btab + b, e - b, A, o2, [] {});
     else
 #endif
     k3_batches<DIRECT>(tile_s, lt, btab + b, e - b, A, o2);
@@ -641,8 +647,8 @@ __device__ __forceinline__ void k3x_pp(K3XSet& c, K3XSet& n, double& pr0, double
   if (HAS1) xmma<ABL>(n.y0, n.y1, A[5], n.d1, n.y0, n.y1);
 }
 // per even and >= 4, one matrix variant
-template <int ABL = 0>
-__device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12]) {
+template <int ABL = 0, class F>
+__device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12], F&& mid) {
   K3XSet a, b;
   double pr0 = 0, pr1 = 0, pi0 = 0, pi1 = 0;
   uint32_t pa0 = 0, pa1 = 0;
@@ -657,6 +663,7 @@ __device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, 
   k3x_pp<true, true, false, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
   xq = btab[3];
   k3x_pp<true, true, true, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  mid();
 #pragma unroll 1
   for (uint32_t i = 2; i + 2u < per; i += 2u) {
     xq = btab[i + 2u];
@@ -669,6 +676,78 @@ __device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, 
   __syncwarp();
   xsts<ABL>(pa0, pr0, pi0); xsts<ABL>(pa1, pr1, pi1);
 }
+// Lockstep variant of the same pipeline (per even, >= 2): TWO batches advance through the first block together, then through
+// the second block together.  Dependent tensor instructions are still two issue slots apart, but a pass neither starts nor
+// ends with a block that runs on its own at half rate (k3x_first_block / the last call of k3x_batches_pp); the loads of the
+// next two batches are issued between the blocks, the results of the previous two are stored inside the first block.
+template <int ABL = 0, class F>
+__device__ __forceinline__ void k3x_batches_lock(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12], F&& mid) {
+  K3XSet a, b;
+  double ar0 = 0, ar1 = 0, ai0 = 0, ai1 = 0, br0 = 0, br1 = 0, bi0 = 0, bi1 = 0;   // results of the previous two batches
+  uint32_t pa0 = 0, pa1 = 0, pb0 = 0, pb1 = 0;                                       // and where they go
+  a.X = btab[0] & DMMA_BATCH_OFF_MASK;
+  b.X = btab[1] & DMMA_BATCH_OFF_MASK;
+  xlds<ABL>(tile_s + (lt.x ^ a.X), a.r0, a.i0);
+  xlds<ABL>(tile_s + (lt.y ^ a.X), a.r1, a.i1);
+  xlds<ABL>(tile_s + (lt.x ^ b.X), b.r0, b.i0);
+  xlds<ABL>(tile_s + (lt.y ^ b.X), b.r1, b.i1);
+  auto body = [&](uint32_t xa, uint32_t xb, auto hasp, auto has2) {
+    constexpr bool HASP = decltype(hasp)::value, HAS2 = decltype(has2)::value;
+    a.s0 = a.r0 + a.i0; a.d0 = a.i0 - a.r0; b.s0 = b.r0 + b.i0; b.d0 = b.i0 - b.r0;
+    xmma<ABL>(a.K0, a.K1, A[0], a.r0, 0.0, 0.0);
+    xmma<ABL>(b.K0, b.K1, A[0], b.r0, 0.0, 0.0);
+    xmma<ABL>(a.K0, a.K1, A[1], a.r1, a.K0, a.K1);
+    xmma<ABL>(b.K0, b.K1, A[1], b.r1, b.K0, b.K1);
+    a.s1 = a.r1 + a.i1; a.d1 = a.i1 - a.r1; b.s1 = b.r1 + b.i1; b.d1 = b.i1 - b.r1;
+    if (HASP) {
+      __syncwarp();                    // in-place update inside a warp: see k3_pp
+      xsts<ABL>(pa0, ar0, ai0); xsts<ABL>(pa1, ar1, ai1); xsts<ABL>(pb0, br0, bi0); xsts<ABL>(pb1, br1, bi1);
+    }
+    xmma<ABL>(a.x0, a.x1, A[2], a.s0, a.K0, a.K1);
+    xmma<ABL>(b.x0, b.x1, A[2], b.s0, b.K0, b.K1);
+    xmma<ABL>(a.y0, a.y1, A[4], a.d0, a.K0, a.K1);
+    xmma<ABL>(b.y0, b.y1, A[4], b.d0, b.K0, b.K1);
+    xmma<ABL>(a.x0, a.x1, A[3], a.s1, a.x0, a.x1);
+    xmma<ABL>(b.x0, b.x1, A[3], b.s1, b.x0, b.x1);
+    xmma<ABL>(a.y0, a.y1, A[5], a.d1, a.y0, a.y1);
+    xmma<ABL>(b.y0, b.y1, A[5], b.d1, b.y0, b.y1);
+    pa0 = tile_s + (lt.z ^ a.X); pa1 = tile_s + (lt.w ^ a.X); pb0 = tile_s + (lt.z ^ b.X); pb1 = tile_s + (lt.w ^ b.X);
+    if (HAS2) {
+      a.X = xa & DMMA_BATCH_OFF_MASK; b.X = xb & DMMA_BATCH_OFF_MASK;
+      xlds<ABL>(tile_s + (lt.x ^ a.X), a.r0, a.i0);
+      xlds<ABL>(tile_s + (lt.y ^ a.X), a.r1, a.i1);
+      xlds<ABL>(tile_s + (lt.x ^ b.X), b.r0, b.i0);
+      xlds<ABL>(tile_s + (lt.y ^ b.X), b.r1, b.i1);
+    }
+    xmma<ABL>(a.K0, a.K1, A[6], a.x0, 0.0, 0.0);
+    xmma<ABL>(b.K0, b.K1, A[6], b.x0, 0.0, 0.0);
+    xmma<ABL>(a.K0, a.K1, A[7], a.x1, a.K0, a.K1);
+    xmma<ABL>(b.K0, b.K1, A[7], b.x1, b.K0, b.K1);
+    a.s0 = a.x0 + a.y0; a.d0 = a.y0 - a.x0; b.s0 = b.x0 + b.y0; b.d0 = b.y0 - b.x0;
+    xmma<ABL>(ar0, ar1, A[8], a.s0, a.K0, a.K1);
+    xmma<ABL>(br0, br1, A[8], b.s0, b.K0, b.K1);
+    xmma<ABL>(ai0, ai1, A[10], a.d0, a.K0, a.K1);
+    xmma<ABL>(bi0, bi1, A[10], b.d0, b.K0, b.K1);
+    a.s1 = a.x1 + a.y1; a.d1 = a.y1 - a.x1; b.s1 = b.x1 + b.y1; b.d1 = b.y1 - b.x1;
+    xmma<ABL>(ar0, ar1, A[9], a.s1, ar0, ar1);
+    xmma<ABL>(br0, br1, A[9], b.s1, br0, br1);
+    xmma<ABL>(ai0, ai1, A[11], a.d1, ai0, ai1);
+    xmma<ABL>(bi0, bi1, A[11], b.d1, bi0, bi1);
+  };
+  using T = std::true_type;
+  using N = std::false_type;
+  if (per == 2u) { mid(); body(0u, 0u, N{}, N{}); }
+  else {
+    body(btab[2], btab[3], N{}, T{});
+    mid();
+#pragma unroll 1
+    for (uint32_t i = 2; i + 2u < per; i += 2u) body(btab[i + 2u], btab[i + 3u], T{}, T{});
+    body(0u, 0u, T{}, N{});
+  }
+  __syncwarp();
+  xsts<ABL>(pa0, ar0, ai0); xsts<ABL>(pa1, ar1, ai1); xsts<ABL>(pb0, br0, bi0); xsts<ABL>(pb1, br1, bi1);
+}
+
 // any number of batches, one after the other (short shares, variant changes inside a share)
 __device__ __forceinline__ void k3x_batches_simple(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12]) {
 #pragma unroll 1
@@ -692,30 +771,41 @@ __device__ __forceinline__ void k3x_batches_simple(uint32_t tile_s, const uint4 
   }
 }
 // One warp's share of a paired round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
+template <class F>
 __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
-                                              uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur) {
+                                              uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur,
+                                              F&& mid) {
   const uint4 lt = lane_tab_r[2u * lane];
   if ((btab[0] >> 20) == (btab[per - 1u] >> 20)) {
     if (per >= 4u && !(per & 1u)) {
 #ifdef QCB_TILE_ABLATE
       switch (tile_dbg() & 3) {
-        case 1: k3x_batches_pp<1>(tile_s, lt, btab, per, A); return;
-        case 2: k3x_batches_pp<2>(tile_s, lt, btab, per, A); return;
-        case 3: k3x_batches_pp<3>(tile_s, lt, btab, per, A); return;
+        case 1: k3x_batches_pp<1>(tile_s, lt, btab, per, A, mid); return;
+        case 2: k3x_batches_pp<2>(tile_s, lt, btab, per, A, mid); return;
+        case 3: k3x_batches_pp<3>(tile_s, lt, btab, per, A, mid); return;
         default: break;
       }
 #endif
-      k3x_batches_pp<0>(tile_s, lt, btab, per, A);
-    } else k3x_batches_simple(tile_s, lt, btab, per, A);
+#ifdef QCB_K3X_LOCK
+      k3x_batches_lock<0>(tile_s, lt, btab, per, A, mid);
+#else
+      k3x_batches_pp<0>(tile_s, lt, btab, per, A, mid);
+#endif
+    } else { mid(); k3x_batches_simple(tile_s, lt, btab, per, A); }
     return;
   }
+  mid();
   uint32_t b = 0;
   while (b < per) {
     const uint32_t v = var_hi | (btab[b] >> 20);
     uint32_t e = b + 1u;
     while (e < per && (btab[e] >> 20) == (btab[b] >> 20)) ++e;
     if (v != cur) { k3x_load_A(A, mats, v); cur = v; }
-    if (e - b >= 4u && !((e - b) & 1u)) k3x_batches_pp<0>(tile_s, lt, btab + b, e - b, A);
+#ifdef QCB_K3X_LOCK
+    if (e - b >= 2u && !((e - b) & 1u)) k3x_batches_lock<0>(tile_s, lt, btab + b, e - b, A, [] {});
+#else
+    if (e - b >= 4u && !((e - b) & 1u)) k3x_batches_pp<0>(tile_s, lt, btab + b, e - b, A, [] {});
+#endif
     else k3x_batches_simple(tile_s, lt, btab + b, e - b, A);
     b = e;
   }
@@ -1034,23 +1124,30 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
           for (int i = 0; i < NA; ++i) Ac[i] = A[i];
           const uint32_t curc = cur, var_hic = var_hi;
           const double* mats = reinterpret_cast<const double*>(stage_g + rtab[r].y) + lane;
-          if (next_mma && !(DBG_ON(16) && cur != 0xffffffffu)) prefetch(nj, nr);
+          const bool do_pf = next_mma && !(DBG_ON(16) && cur != 0xffffffffu);
+#ifdef QCB_PREFETCH_EARLY
+          if (do_pf) prefetch(nj, nr);
+          auto mid = [] {};
+#else
+          auto mid = [&] { if (do_pf) prefetch(nj, nr); };
+          if ((FORM != 2 || !active) && do_pf) prefetch(nj, nr);      // the 16x16 form keeps the prefetch between the passes
+#endif
           PF_ADD(PF_C_SETUP);
           if (active) {
             if constexpr (FORM == 2) {
               if (round_kind(sprog, r) == 3u) {
                 k3x_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                              mats, lane, Ac, curc);
+                              mats, lane, Ac, curc, mid);
               } else {
               K3Out out;
               out.gtab = gtab + b0; out.gbase = nullptr; out.g0 = out.g1 = 0;
               if (direct && r + 1u == sc.n_rounds) {
                 out.gbase = state + tile_base(sprog, sc, active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x));
                 k3_round_run<true>(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                                   mats, lane, Ac, curc, out);
+                                   mats, lane, Ac, curc, out, mid);
               } else {
                 k3_round_run<false>(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                                    mats, lane, Ac, curc, out);
+                                    mats, lane, Ac, curc, out, mid);
               }
               }
             } else
