@@ -646,7 +646,9 @@ __device__ __forceinline__ void k3x_pp(K3XSet& c, K3XSet& n, double& pr0, double
   xmma<ABL>(pi0, pi1, A[11], c.d1, pi0, pi1);
   if (HAS1) xmma<ABL>(n.y0, n.y1, A[5], n.d1, n.y0, n.y1);
 }
-// per even and >= 4, one matrix variant
+// per even and >= 4, one matrix variant.  (A lockstep variant - two batches through the first block together, then through the
+// second - measured the same: 5485 vs 5511 gates/s, profiles/r2n_ab.log; on registers alone it loses 9 % to the drain between
+// the blocks, scripts/dmma_mix.cu.)
 template <int ABL = 0, class F>
 __device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12], F&& mid) {
   K3XSet a, b;
@@ -676,78 +678,6 @@ __device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, 
   __syncwarp();
   xsts<ABL>(pa0, pr0, pi0); xsts<ABL>(pa1, pr1, pi1);
 }
-// Lockstep variant of the same pipeline (per even, >= 2): TWO batches advance through the first block together, then through
-// the second block together.  Dependent tensor instructions are still two issue slots apart, but a pass neither starts nor
-// ends with a block that runs on its own at half rate (k3x_first_block / the last call of k3x_batches_pp); the loads of the
-// next two batches are issued between the blocks, the results of the previous two are stored inside the first block.
-template <int ABL = 0, class F>
-__device__ __forceinline__ void k3x_batches_lock(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12], F&& mid) {
-  K3XSet a, b;
-  double ar0 = 0, ar1 = 0, ai0 = 0, ai1 = 0, br0 = 0, br1 = 0, bi0 = 0, bi1 = 0;   // results of the previous two batches
-  uint32_t pa0 = 0, pa1 = 0, pb0 = 0, pb1 = 0;                                       // and where they go
-  a.X = btab[0] & DMMA_BATCH_OFF_MASK;
-  b.X = btab[1] & DMMA_BATCH_OFF_MASK;
-  xlds<ABL>(tile_s + (lt.x ^ a.X), a.r0, a.i0);
-  xlds<ABL>(tile_s + (lt.y ^ a.X), a.r1, a.i1);
-  xlds<ABL>(tile_s + (lt.x ^ b.X), b.r0, b.i0);
-  xlds<ABL>(tile_s + (lt.y ^ b.X), b.r1, b.i1);
-  auto body = [&](uint32_t xa, uint32_t xb, auto hasp, auto has2) {
-    constexpr bool HASP = decltype(hasp)::value, HAS2 = decltype(has2)::value;
-    a.s0 = a.r0 + a.i0; a.d0 = a.i0 - a.r0; b.s0 = b.r0 + b.i0; b.d0 = b.i0 - b.r0;
-    xmma<ABL>(a.K0, a.K1, A[0], a.r0, 0.0, 0.0);
-    xmma<ABL>(b.K0, b.K1, A[0], b.r0, 0.0, 0.0);
-    xmma<ABL>(a.K0, a.K1, A[1], a.r1, a.K0, a.K1);
-    xmma<ABL>(b.K0, b.K1, A[1], b.r1, b.K0, b.K1);
-    a.s1 = a.r1 + a.i1; a.d1 = a.i1 - a.r1; b.s1 = b.r1 + b.i1; b.d1 = b.i1 - b.r1;
-    if (HASP) {
-      __syncwarp();                    // in-place update inside a warp: see k3_pp
-      xsts<ABL>(pa0, ar0, ai0); xsts<ABL>(pa1, ar1, ai1); xsts<ABL>(pb0, br0, bi0); xsts<ABL>(pb1, br1, bi1);
-    }
-    xmma<ABL>(a.x0, a.x1, A[2], a.s0, a.K0, a.K1);
-    xmma<ABL>(b.x0, b.x1, A[2], b.s0, b.K0, b.K1);
-    xmma<ABL>(a.y0, a.y1, A[4], a.d0, a.K0, a.K1);
-    xmma<ABL>(b.y0, b.y1, A[4], b.d0, b.K0, b.K1);
-    xmma<ABL>(a.x0, a.x1, A[3], a.s1, a.x0, a.x1);
-    xmma<ABL>(b.x0, b.x1, A[3], b.s1, b.x0, b.x1);
-    xmma<ABL>(a.y0, a.y1, A[5], a.d1, a.y0, a.y1);
-    xmma<ABL>(b.y0, b.y1, A[5], b.d1, b.y0, b.y1);
-    pa0 = tile_s + (lt.z ^ a.X); pa1 = tile_s + (lt.w ^ a.X); pb0 = tile_s + (lt.z ^ b.X); pb1 = tile_s + (lt.w ^ b.X);
-    if (HAS2) {
-      a.X = xa & DMMA_BATCH_OFF_MASK; b.X = xb & DMMA_BATCH_OFF_MASK;
-      xlds<ABL>(tile_s + (lt.x ^ a.X), a.r0, a.i0);
-      xlds<ABL>(tile_s + (lt.y ^ a.X), a.r1, a.i1);
-      xlds<ABL>(tile_s + (lt.x ^ b.X), b.r0, b.i0);
-      xlds<ABL>(tile_s + (lt.y ^ b.X), b.r1, b.i1);
-    }
-    xmma<ABL>(a.K0, a.K1, A[6], a.x0, 0.0, 0.0);
-    xmma<ABL>(b.K0, b.K1, A[6], b.x0, 0.0, 0.0);
-    xmma<ABL>(a.K0, a.K1, A[7], a.x1, a.K0, a.K1);
-    xmma<ABL>(b.K0, b.K1, A[7], b.x1, b.K0, b.K1);
-    a.s0 = a.x0 + a.y0; a.d0 = a.y0 - a.x0; b.s0 = b.x0 + b.y0; b.d0 = b.y0 - b.x0;
-    xmma<ABL>(ar0, ar1, A[8], a.s0, a.K0, a.K1);
-    xmma<ABL>(br0, br1, A[8], b.s0, b.K0, b.K1);
-    xmma<ABL>(ai0, ai1, A[10], a.d0, a.K0, a.K1);
-    xmma<ABL>(bi0, bi1, A[10], b.d0, b.K0, b.K1);
-    a.s1 = a.x1 + a.y1; a.d1 = a.y1 - a.x1; b.s1 = b.x1 + b.y1; b.d1 = b.y1 - b.x1;
-    xmma<ABL>(ar0, ar1, A[9], a.s1, ar0, ar1);
-    xmma<ABL>(br0, br1, A[9], b.s1, br0, br1);
-    xmma<ABL>(ai0, ai1, A[11], a.d1, ai0, ai1);
-    xmma<ABL>(bi0, bi1, A[11], b.d1, bi0, bi1);
-  };
-  using T = std::true_type;
-  using N = std::false_type;
-  if (per == 2u) { mid(); body(0u, 0u, N{}, N{}); }
-  else {
-    body(btab[2], btab[3], N{}, T{});
-    mid();
-#pragma unroll 1
-    for (uint32_t i = 2; i + 2u < per; i += 2u) body(btab[i + 2u], btab[i + 3u], T{}, T{});
-    body(0u, 0u, T{}, N{});
-  }
-  __syncwarp();
-  xsts<ABL>(pa0, ar0, ai0); xsts<ABL>(pa1, ar1, ai1); xsts<ABL>(pb0, br0, bi0); xsts<ABL>(pb1, br1, bi1);
-}
-
 // any number of batches, one after the other (short shares, variant changes inside a share)
 __device__ __forceinline__ void k3x_batches_simple(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12]) {
 #pragma unroll 1
@@ -786,11 +716,7 @@ __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane
         default: break;
       }
 #endif
-#ifdef QCB_K3X_LOCK
-      k3x_batches_lock<0>(tile_s, lt, btab, per, A, mid);
-#else
       k3x_batches_pp<0>(tile_s, lt, btab, per, A, mid);
-#endif
     } else { mid(); k3x_batches_simple(tile_s, lt, btab, per, A); }
     return;
   }
@@ -801,11 +727,7 @@ __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane
     uint32_t e = b + 1u;
     while (e < per && (btab[e] >> 20) == (btab[b] >> 20)) ++e;
     if (v != cur) { k3x_load_A(A, mats, v); cur = v; }
-#ifdef QCB_K3X_LOCK
-    if (e - b >= 2u && !((e - b) & 1u)) k3x_batches_lock<0>(tile_s, lt, btab + b, e - b, A, [] {});
-#else
     if (e - b >= 4u && !((e - b) & 1u)) k3x_batches_pp<0>(tile_s, lt, btab + b, e - b, A, [] {});
-#endif
     else k3x_batches_simple(tile_s, lt, btab + b, e - b, A);
     b = e;
   }
