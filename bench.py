@@ -222,7 +222,12 @@ def _roofline(stats, n_local, peak, peak_src, mma_form_flops):
          "fp64_tensor": {"achieved": tf, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / DMMA_PEAK_TFLOPS,
                          "peak_source": "DMMA microbenchmark on this pool (profiles/r1c_dmma_microbench.log; 296 TF / 8 GPUs in the HGX spec)",
                          "flops_per_launch": flops_exec / sweeps, "flops_per_amplitude_per_round": mma_form_flops,
-                         "algorithmic_tflops": flops_alg / tile_s / 1e12, "ideal_ms_per_step": 1e3 * t_mma},
+                         "algorithmic_tflops": flops_alg / tile_s / 1e12, "ideal_ms_per_step": 1e3 * t_mma,
+                         # what the instruction mix of a three-product round allows on the fp64 pipe: 6 DMMA.8x8x4 (16.1 cycles each)
+                         # + 4 DADD (3 cycles each, same pipe) = 108 cycles per batch against 96 for the DMMAs alone
+                         "instruction_mix_bound": {"cycles_per_batch": 108, "dmma_cycles_per_batch": 96, "frac_of_peak": 96.0 / 108.0,
+                                                   "frac_of_mix_bound": (tf / DMMA_PEAK_TFLOPS) * 108.0 / 96.0,
+                                                   "source": "scripts/dmma_mix.cu on this pool (profiles/r2o_dmma_mix.log)"}},
          "avg_launch_ms": 1e3 * tile_s / sweeps, "launches_per_step": stats["n_sweeps"]}
     return r
 

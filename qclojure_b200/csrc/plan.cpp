@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace qcb {
 
@@ -77,10 +78,12 @@ Config config_from(const qcb_config& c) {
   if (const char* e = std::getenv("QCB_MMA_FORM")) k.mma_form = std::atoi(e) ? 1 : 0;      // experiment knob
   if (const char* e = std::getenv("QCB_DIRECT_STORE")) k.direct_store = std::atoi(e) ? 1 : 0;
   k.tma = (c.tile_mover == 2) ? 1 : 0;
-  if (const char* e = std::getenv("QCB_PAIR_ROUNDS")) k.pair_rounds = std::atoi(e) ? 1 : 0;   // experiment knobs
-  if (const char* e = std::getenv("QCB_PAIR_COST_Q")) k.pair_cost_q = std::max(4, std::atoi(e));
-  if (const char* e = std::getenv("QCB_PAIR_SEARCH")) k.pair_search = std::max(1, std::atoi(e));
-  if (const char* e = std::getenv("QCB_PAIR_EFF_PCT")) k.pair_eff_pct = std::atoi(e);
+  // experiment knobs; setting any of the pair knobs pins the scheduler to that setting (no plan portfolio)
+  if (const char* e = std::getenv("QCB_PAIR_ROUNDS")) { k.pair_rounds = std::atoi(e) ? 1 : 0; k.plan_portfolio = 0; }
+  if (const char* e = std::getenv("QCB_PAIR_COST_Q")) { k.pair_cost_q = std::max(4, std::atoi(e)); k.plan_portfolio = 0; }
+  if (const char* e = std::getenv("QCB_PAIR_SEARCH")) { k.pair_search = std::max(1, std::atoi(e)); k.plan_portfolio = 0; }
+  if (const char* e = std::getenv("QCB_PAIR_EFF_PCT")) { k.pair_eff_pct = std::atoi(e); k.plan_portfolio = 0; }
+  if (const char* e = std::getenv("QCB_PLAN_PORTFOLIO")) k.plan_portfolio = std::atoi(e) ? 1 : 0;
   if (const char* e = std::getenv("QCB_THIN_DEFER")) k.thin_defer = std::atoi(e);            // experiment knob
   if (const char* e = std::getenv("QCB_WINDOW_SEARCH")) k.window_search = std::atoi(e);
   if (const char* e = std::getenv("QCB_ROUND_YIELD_PCT")) k.round_yield_pct = std::atoi(e);   // 0 = greedy tiles / rounds only
@@ -1196,7 +1199,7 @@ void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const
   key.reserve(16 + perm_in.size() + 6 * gates.size());
   const int c[] = {cfg.n_total, cfg.n_local, cfg.rank, cfg.world, cfg.tile_bits, cfg.low_bits, cfg.fusion, cfg.max_stage_cost,
                    cfg.max_stage_rounds, cfg.dense_mma + 16 * cfg.mma_form + 32 * cfg.direct_store, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer,
-                   cfg.pair_rounds + 2 * cfg.pair_eff_pct + 2048 * cfg.pair_cost_q + 65536 * cfg.pair_search};
+                   cfg.pair_rounds + 2 * cfg.pair_eff_pct + 2048 * cfg.pair_cost_q + 65536 * cfg.pair_search + 1048576 * cfg.plan_portfolio};
   for (int v : c) key.push_back((uint64_t)(int64_t)v);
   key.push_back(perm_in.size());
   for (int v : perm_in) key.push_back((uint64_t)v);
@@ -1211,7 +1214,8 @@ void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const
   }
 }
 
-int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanTrace* record, const PlanTrace* replay) {
+// dry: decisions only - no matrices, no encoding, no sink (what the plan portfolio scores its candidates with)
+static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanTrace* record, const PlanTrace* replay, bool dry) {
   const Config& cfg = plan.cfg;
   const int n = cfg.n_total, nl = cfg.n_local, m = std::min(cfg.tile_bits, nl), L = std::min(cfg.low_bits, m);
   std::vector<int> perm(n);
@@ -1250,6 +1254,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
   plan.n_rounds = 0;
   int sink_rc = QCB_OK;
   auto emit_new_stages = [&]() {
+    if (dry) return;
     while (plan.stage_offsets.size() < plan.stages.size() && sink_rc == QCB_OK) {
       const size_t si = plan.stage_offsets.size();
       Stage& s = plan.stages[si];
@@ -1429,7 +1434,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
     if (taken.empty() && !lead) return 0;          // nothing executable in the current layout (multi-GPU: exchange first)
     Stage st; std::vector<int> abs_uids, taken_uids(taken.size());
     for (size_t k = 0; k < taken.size(); ++k) taken_uids[k] = pending[taken[k]];
-    make_stage(lead, A, taken_uids, true, st, abs_uids, nullptr);
+    make_stage(lead, A, taken_uids, !dry, st, abs_uids, nullptr);
     std::vector<char> absorbed(plan.gates.size(), 0);
     size_t keep = 0;
     for (int u : abs_uids) if (u >= 0 && !absorbed[u]) { absorbed[u] = 1; ++keep; }
@@ -1633,6 +1638,74 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
   emit_new_stages();
   if (sink_rc != QCB_OK) { plan.error = "stage sink failed"; return sink_rc; }
   return QCB_OK;
+}
+
+// Estimated device time of a plan in milliseconds at 2^30 amplitudes per GPU, from the cost model fitted to the B200
+// measurements of round 2 (profiles/r2l_ab.log: 13 plans of the same circuit, residual <= 2 %): a sweep costs 1.52 ms on top
+// of its passes (mover traffic, fill / drain), a single tensor-core round 2.0 ms, a paired pass 3.39 ms; an interpreter round
+// is charged like a paired pass, a qubit exchange like 8 ms (2-GPU measurement, 12.4 ms for one qubit, less per qubit when
+// several move in one pass).  Only the RATIOS matter: the portfolio compares plans of one circuit on one machine.
+static double plan_cost_ms(const Plan& plan) {
+  double c = 0.0;
+  for (const Stage& st : plan.stages) {
+    if (st.kind == S_EXCHANGE) { c += 8.0; continue; }
+    if (st.kind == S_SUM) { c += 2.6; continue; }
+    if (st.kind == S_GROVER) { c += 5.3; continue; }
+    double t = 1.52;
+    for (const Round& rd : st.rounds) t += rd.pair ? 3.39 : 2.0;
+    c += t * st.sweep_fraction;
+  }
+  return c;
+}
+
+// Plan portfolio: the greedy stage / round builders are sensitive to their budgets (how many rounds a sweep may hold, when a
+// partner round is worth a paired pass), and which setting wins depends on the circuit (+-4 % on the brickwork circuits of 26
+// to 33 qubits).  For large circuits the scheduler therefore makes its decisions under a handful of settings - decisions only,
+// no matrices, a few milliseconds each - keeps the plan the cost model likes best and replays that one through the normal path.
+int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanTrace* record, const PlanTrace* replay) {
+  const Config base = plan.cfg;
+  const bool pairs_on = base.fusion && base.window_search && base.dense_mma && base.pair_rounds && base.mma_form == 0 && !base.tma && !base.direct_store;
+  if (replay || !base.plan_portfolio || !pairs_on || base.max_stage_rounds > 0 || base.n_local < 24 || plan.gates.size() < 128)
+    return schedule_impl(plan, perm_in, sink, record, replay, false);
+  struct Knobs { int rounds, cost_q, eff_pct, search, pairs; };
+  static const Knobs kn[] = {{7, 7, 170, 1, 1}, {7, 7, 150, 4, 1}, {6, 6, 170, 1, 1}, {8, 7, 160, 4, 1}, {5, 6, 170, 1, 0}};
+  auto with = [&](const Knobs& k) {
+    Config c = base;
+    c.max_stage_rounds = k.rounds; c.pair_cost_q = k.cost_q; c.pair_eff_pct = k.eff_pct; c.pair_search = k.search; c.pair_rounds = k.pairs;
+    return c;
+  };
+  // the candidates are independent: one host thread each (the scheduler keeps no global state)
+  constexpr int NK = (int)(sizeof kn / sizeof kn[0]);
+  PlanTrace traces[NK];
+  double costs[NK];
+  int rcs[NK];
+  {
+    std::vector<std::thread> th;
+    for (int i = 0; i < NK; ++i)
+      th.emplace_back([&, i] {
+        Plan t;
+        t.cfg = with(kn[i]);
+        t.gates = plan.gates;
+        rcs[i] = schedule_impl(t, perm_in, nullptr, &traces[i], nullptr, true);
+        costs[i] = rcs[i] == QCB_OK ? plan_cost_ms(t) : 0.0;
+      });
+    for (auto& t : th) t.join();
+  }
+  int best = -1;
+  double best_cost = 0.0;
+  for (int i = 0; i < NK; ++i)
+    if (rcs[i] == QCB_OK && (best < 0 || costs[i] < best_cost)) { best = i; best_cost = costs[i]; }
+  PlanTrace best_trace;
+  if (best >= 0) best_trace = std::move(traces[best]);
+  if (best < 0) return schedule_impl(plan, perm_in, sink, record, nullptr, false);
+  plan.cfg = with(kn[best]);
+  const int rc = schedule_impl(plan, perm_in, sink, nullptr, &best_trace, false);
+  plan.cfg = base;
+  if (record) {
+    *record = std::move(best_trace);
+    plan_structure_key(base, plan.gates, perm_in, record->key);
+  }
+  return rc;
 }
 
 }  // namespace qcb

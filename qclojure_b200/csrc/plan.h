@@ -156,6 +156,7 @@ struct Config {
   int pair_eff_pct = 170;      // cost of a paired pass in % of a single round (measured on B200: 3.39 ms vs 2.0 ms at 30 qubits):
                                // a pair is formed when its gates per unit of cost beat the best single round's
   int pair_cost_q = 7;         // cost of a paired pass in quarter rounds (a single round = 4) against the stage's round budget
+  int plan_portfolio = 1;      // large circuits: schedule under a handful of budget settings, keep the plan the cost model prefers
   int thin_defer = 12;         // multi-GPU: a stage with fewer gates than this is not run while gates wait for an exchange
                                // (its gates ride along in the fuller sweeps after the exchange)
   int tma = 0;                 // tiles move by TMA tensor copies (layout follows the hardware 128-byte swizzle)

@@ -29,7 +29,7 @@ def build():
         return LIB
     cuda_inc = "/usr/local/cuda/include"
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                           "-I" + cuda_inc, *SRCS, "-o", LIB])
+                           "-I" + cuda_inc, *SRCS, "-o", LIB, "-pthread"])
     return LIB
 
 
