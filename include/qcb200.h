@@ -210,7 +210,7 @@ typedef struct qcb_stats {
   uint64_t n_ops;             /* ops submitted                                                  */
   uint64_t n_gates_lowered;   /* after expanding global-* gates                                 */
   uint64_t n_sweeps;          /* fused tile sweeps (kernel launches of the gate executor)       */
-  uint64_t n_rounds;          /* shared-memory rounds inside those sweeps                       */
+  uint64_t n_rounds;          /* dense-block rounds inside those sweeps (a paired pass counts two)  */
   uint64_t n_kernel_launches; /* every kernel this library launched for the call                */
   uint64_t n_exchanges;       /* global<->local qubit swaps (multi-GPU)                         */
   uint64_t bytes_exchanged;   /* bytes this rank sent over NVLink                               */

@@ -127,3 +127,34 @@ def test_trace_replay_reproduces_paired_rounds():
     a = _replayed(16, ops, ops2)
     b = _fresh(16, ops2)
     assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def _cost(ps):
+    """csrc/plan.cpp: plan_cost_ms for plans of tensor-core rounds only."""
+    return 1.52 * ps["tile_sweeps"] + 2.0 * (ps["passes"] - ps["paired_passes"]) + 3.39 * ps["paired_passes"]
+
+
+def test_plan_portfolio_picks_the_cheapest_member_and_replays_word_for_word(monkeypatch):
+    """Large circuits (>= 24 local qubits, >= 128 gates) are scheduled under five budget settings; the plan the cost model
+    prefers is the one that is built (csrc/plan.cpp: schedule).  It can never be worse than any member, a pinned knob switches
+    the portfolio off, and a replayed plan of the same structure equals the fresh one word for word."""
+    from qclojure_b200 import _lib as L
+    n = 24
+    ops = C.random_brickwork_circuit(n, 20)["operations"]
+    chosen = L.plan_summary(n, ops)
+    members = []
+    for rounds, cost_q, eff, search, pairs in [(7, 7, 170, 1, 1), (7, 7, 150, 4, 1), (6, 6, 170, 1, 1), (8, 7, 160, 4, 1), (5, 6, 170, 1, 0)]:
+        for k, v in (("QCB_PAIR_COST_Q", cost_q), ("QCB_PAIR_EFF_PCT", eff), ("QCB_PAIR_SEARCH", search), ("QCB_PAIR_ROUNDS", pairs)):
+            monkeypatch.setenv(k, str(v))
+        members.append(_cost(L.plan_summary(n, ops, max_stage_rounds=rounds)))
+    for k in ("QCB_PAIR_COST_Q", "QCB_PAIR_EFF_PCT", "QCB_PAIR_SEARCH", "QCB_PAIR_ROUNDS"):
+        monkeypatch.delenv(k)
+    assert abs(_cost(chosen) - min(members)) < 1e-9
+    assert len(set(round(m, 6) for m in members)) > 1            # the settings really differ on this circuit
+    ops2 = _reangle(ops, 9)
+    a = _replayed(n, ops, ops2)
+    b = _fresh(n, ops2)
+    assert a.shape == b.shape and np.array_equal(a, b)
+    monkeypatch.setenv("QCB_PLAN_PORTFOLIO", "0")
+    fixed = L.plan_summary(n, ops)
+    assert abs(_cost(fixed) - members[0]) < 1e-9                  # portfolio off = the first (default) setting
