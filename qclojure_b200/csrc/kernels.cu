@@ -1409,20 +1409,69 @@ k_expect_group(const double2* __restrict__ state, uint64_t count, uint64_t xmask
 #pragma unroll
   for (int k = 0; k < EXPECT_TERMS; ++k) acc[k] = 0.0;
   const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
-  if (xmask == 0) {
+  if (xmask == 0 && count >= 2048 && (count & 2047) == 0) {
+    // Diagonal terms, large states: sum_i (-1)^parity(i & z) |a_i|^2 without a POPC per term and amplitude (POPC issues at a
+    // quarter of the integer rate and bounded this loop at 0.58 - 0.63 of the HBM peak).  A warp walks blocks of 2^11
+    // amplitudes; in step t lane l takes the four amplitudes t << 7 | j << 5 | l, j = 0..3 (every load instruction of the warp
+    // reads 512 contiguous bytes), so parity(index & z) = parity(base & z) ^ parity(t << 7 & z) ^ parity(l & z) ^ (z's bits 5
+    // and 6 against j, folded into the choice of p0 +- p1 +- p2 +- p3).  The 16 terms' parities travel as the bits of one
+    // word: base part once per block, lane part once per kernel, step part from a 16-entry table.
+    __shared__ uint32_t steppar[16];
+    if (threadIdx.x < 16) {
+      uint32_t w = 0;
+      for (int k = 0; k < EXPECT_TERMS; ++k) w |= (uint32_t)(__popcll(((uint64_t)threadIdx.x << 7) & terms.zmask[k]) & 1) << k;
+      steppar[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t lanepar = 0;
+    for (int k = 0; k < EXPECT_TERMS; ++k) lanepar |= (uint32_t)(__popcll((uint64_t)lane & terms.zmask[k]) & 1) << k;
+    const uint64_t nblk = count >> 11, wstride = (uint64_t)gridDim.x * (RED_THREADS / 32);
+    for (uint64_t blk = (uint64_t)blockIdx.x * (RED_THREADS / 32) + (threadIdx.x >> 5); blk < nblk; blk += wstride) {
+      const uint64_t base = blk << 11;
+      uint32_t par0 = lanepar;
+#pragma unroll
+      for (int k = 0; k < EXPECT_TERMS; ++k) par0 ^= (uint32_t)(__popcll((base | ext_or) & terms.zmask[k]) & 1) << k;
+      const double2* p = state + base + lane;
+      double2 a0 = __ldcs(p), a1 = __ldcs(p + 32), a2 = __ldcs(p + 64), a3 = __ldcs(p + 96);
+#pragma unroll 4
+      for (uint32_t t = 0; t < 16; ++t) {
+        double2 b0 = a0, b1 = a1, b2 = a2, b3 = a3;
+        if (t + 1 < 16) { const double2* pn = p + ((uint64_t)(t + 1) << 7); b0 = __ldcs(pn); b1 = __ldcs(pn + 32); b2 = __ldcs(pn + 64); b3 = __ldcs(pn + 96); }
+        const double p0 = a0.x * a0.x + a0.y * a0.y, p1 = a1.x * a1.x + a1.y * a1.y, p2 = a2.x * a2.x + a2.y * a2.y, p3 = a3.x * a3.x + a3.y * a3.y;
+        // combo[c]: bit 0 of c = z bit 5 set (p1, p3 flip), bit 1 = z bit 6 set (p2, p3 flip)
+        const double combo[4] = {(p0 + p1) + (p2 + p3), (p0 - p1) + (p2 - p3), (p0 + p1) - (p2 + p3), (p0 - p1) - (p2 - p3)};
+        const uint32_t w = par0 ^ steppar[t];
+#pragma unroll
+        for (int k = 0; k < EXPECT_TERMS; ++k)
+          if (k < terms.n) {
+            const double v = combo[((uint32_t)terms.zmask[k] >> 5) & 3u];
+            const int vh = __double2hiint(v) ^ (int)((w << (31 - k)) & 0x80000000u);
+            acc[k] += __hiloint2double(vh, __double2loint(v));
+          }
+        a0 = b0; a1 = b1; a2 = b2; a3 = b3;
+      }
+    }
+  } else if (xmask == 0) {
     // Diagonal terms: sum_i (-1)^parity(i & z) |a_i|^2.  A thread takes FOUR consecutive amplitudes (64 bytes): their
     // parities differ from the first one's only through z's two lowest bits, which are constants of the term, so one
     // parity evaluation (two ANDs, one XOR, ONE 32-bit POPC - POPC issues at a quarter of the integer rate and bounded the
     // one-amplitude-per-evaluation loop at 1.3 TB/s, profiles/r2d_reductions.txt) signs one of four precomputed
-    // combinations p0 +- p1 +- p2 +- p3.
+    // combinations p0 +- p1 +- p2 +- p3.  The four loads of the NEXT quad are issued before the arithmetic of the current
+    // one.  (Choosing the combination with selects and signing it with integer instructions instead of the indexed local
+    // array + negate was measured slower: 4.87 vs 4.56 ms at 30 qubits, profiles/r2r_expect_*.log.)
     const uint64_t quads = count >> 2;
-    for (uint64_t q = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; q < quads; q += stride) {
-      const uint64_t i = q << 2;
-      const double2 a0 = __ldcs(state + i), a1 = __ldcs(state + i + 1), a2 = __ldcs(state + i + 2), a3 = __ldcs(state + i + 3);
+    uint64_t q = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
+    double2 a0, a1, a2, a3;
+    if (q < quads) { const double2* p = state + (q << 2); a0 = __ldcs(p); a1 = __ldcs(p + 1); a2 = __ldcs(p + 2); a3 = __ldcs(p + 3); }
+    while (q < quads) {
+      const uint64_t qn = q + stride;
+      double2 b0 = a0, b1 = a1, b2 = a2, b3 = a3;
+      if (qn < quads) { const double2* p = state + (qn << 2); b0 = __ldcs(p); b1 = __ldcs(p + 1); b2 = __ldcs(p + 2); b3 = __ldcs(p + 3); }
       const double p0 = a0.x * a0.x + a0.y * a0.y, p1 = a1.x * a1.x + a1.y * a1.y, p2 = a2.x * a2.x + a2.y * a2.y, p3 = a3.x * a3.x + a3.y * a3.y;
       // combo[c]: bit 0 of c = z bit 0 set (p1, p3 flip), bit 1 = z bit 1 set (p2, p3 flip)
       const double combo[4] = {(p0 + p1) + (p2 + p3), (p0 - p1) + (p2 - p3), (p0 + p1) - (p2 + p3), (p0 - p1) - (p2 - p3)};
-      const uint64_t gi = i | ext_or;
+      const uint64_t gi = (q << 2) | ext_or;
       const uint32_t lo = (uint32_t)gi, hi = (uint32_t)(gi >> 32);
 #pragma unroll
       for (int k = 0; k < EXPECT_TERMS; ++k)
@@ -1432,6 +1481,8 @@ k_expect_group(const double2* __restrict__ state, uint64_t count, uint64_t xmask
           const double v = combo[zl & 3u];
           acc[k] += (__popc(f) & 1) ? -v : v;
         }
+      a0 = b0; a1 = b1; a2 = b2; a3 = b3;
+      q = qn;
     }
     for (uint64_t i = (quads << 2) + (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x; i < count; i += stride) {   // count < 4
       const double2 a = state[i];
@@ -1453,18 +1504,32 @@ k_expect_group(const double2* __restrict__ state, uint64_t count, uint64_t xmask
       for (int k = 0; k < EXPECT_TERMS; ++k) {
         if (k < terms.n) {
           const uint32_t zl = (uint32_t)terms.zmask[k], zh = (uint32_t)(terms.zmask[k] >> 32);
-          const double si = (__popc(((uint32_t)gi & zl) ^ ((uint32_t)(gi >> 32) & zh)) & 1) ? -1.0 : 1.0;
-          const double sj = (__popc(((uint32_t)gj & zl) ^ ((uint32_t)(gj >> 32) & zh)) & 1) ? -1.0 : 1.0;
-          // phase (pr, pi): Re(ph * sj * (x + iy)) + Re(ph * si * (x - iy))
-          acc[k] += sj * (terms.pr[k] * x - terms.pi[k] * y) + si * (terms.pr[k] * x + terms.pi[k] * y);
+          const uint32_t fi = __popc(((uint32_t)gi & zl) ^ ((uint32_t)(gi >> 32) & zh)) & 1u;
+          const uint32_t fj = __popc(((uint32_t)gj & zl) ^ ((uint32_t)(gj >> 32) & zh)) & 1u;
+          // Re(ph * sj * (x + iy)) + Re(ph * si * (x - iy)) with ph = (pr, pi), si / sj = +-1:
+          //   = (sj + si) pr x - (sj - si) pi y: equal signs leave the x part, opposite signs the y part
+          const double u = terms.pr[k] * x, w = terms.pi[k] * y;
+          const double v = (fi == fj) ? 2.0 * u : -2.0 * w;
+          const int vh = __double2hiint(v) ^ (int)(fj << 31);
+          acc[k] += __hiloint2double(vh, __double2loint(v));
         }
       }
     };
+    // two pairs = four 16-byte loads per step; the loads of the next step are issued before the arithmetic of this one
     uint64_t h = (uint64_t)blockIdx.x * RED_THREADS + threadIdx.x;
-    for (; h + stride < half; h += 2 * stride) {          // two pairs = four 16-byte loads in flight
-      const uint64_t i0 = pair_index(h), i1 = pair_index(h + stride);
-      const double2 a0 = __ldcs(state + i0), b0 = __ldcs(state + (i0 ^ xmask)), a1 = __ldcs(state + i1), b1 = __ldcs(state + (i1 ^ xmask));
+    double2 a0, b0, a1, b1;
+    uint64_t i0 = 0, i1 = 0;
+    bool have = h + stride < half;
+    if (have) { i0 = pair_index(h); i1 = pair_index(h + stride); a0 = __ldcs(state + i0); b0 = __ldcs(state + (i0 ^ xmask)); a1 = __ldcs(state + i1); b1 = __ldcs(state + (i1 ^ xmask)); }
+    while (have) {
+      const uint64_t hn = h + 2 * stride;
+      const bool have_n = hn + stride < half;
+      double2 na0 = a0, nb0 = b0, na1 = a1, nb1 = b1;
+      uint64_t ni0 = 0, ni1 = 0;
+      if (have_n) { ni0 = pair_index(hn); ni1 = pair_index(hn + stride); na0 = __ldcs(state + ni0); nb0 = __ldcs(state + (ni0 ^ xmask)); na1 = __ldcs(state + ni1); nb1 = __ldcs(state + (ni1 ^ xmask)); }
       one(i0, a0, b0); one(i1, a1, b1);
+      a0 = na0; b0 = nb0; a1 = na1; b1 = nb1; i0 = ni0; i1 = ni1;
+      h = hn; have = have_n;
     }
     for (; h < half; h += stride) { const uint64_t i = pair_index(h); one(i, state[i], state[i ^ xmask]); }
   }
