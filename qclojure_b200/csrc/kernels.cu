@@ -1642,10 +1642,98 @@ k_marginal(const double2* __restrict__ state, uint64_t count, uint64_t ext_or, B
     partials[(uint64_t)blockIdx.x * nk + k] = t;
   }
 }
+// The same histogram for large states, block-wise: six index bits >= 5 that neither the key nor the filter depends on (freeb)
+// become a lane's private loop, so a lane adds up its 64 amplitudes in a register and the warp combines and bins ONCE per block
+// of 2^11 amplitudes instead of once per amplitude (the generic kernel spends ten SHFL per 16 bytes when no measured bit lies
+// in the lane bits).  Every load instruction of a warp reads 512 contiguous bytes; blocks the filter rejects are not read.
+// base_pos: the positions of the remaining index bits (block number -> base address).  Deterministic like k_marginal.
+struct BasePos { int n; int pos[40]; };
+__global__ void __launch_bounds__(RED_THREADS)
+k_marginal_blocks(const double2* __restrict__ state, uint64_t nblk, uint64_t ext_or, BitList bl, BitList fl, uint32_t fval, BitList freeb,
+                  BasePos bp, double* __restrict__ partials) {
+  extern __shared__ double hist[];
+  __shared__ uint64_t offs[64];
+  const uint32_t nk = 1u << bl.n, nthreads = blockDim.x, nw = nthreads >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  for (uint32_t k = threadIdx.x; k < nk * nw; k += nthreads) hist[k] = 0.0;
+  for (uint32_t i = threadIdx.x; i < 64; i += nthreads) {
+    uint64_t o = 0;
+    for (int b = 0; b < 6; ++b) o |= (uint64_t)((i >> b) & 1u) << freeb.pos[b];
+    offs[i] = o;
+  }
+  __syncthreads();
+  double* mine = hist + (size_t)wid * nk;
+  uint32_t fixed_low = 0;                                          // lane bits that the key or the filter depends on
+  for (int k = 0; k < bl.n; ++k) if (bl.pos[k] < 5) fixed_low |= 1u << bl.pos[k];
+  for (int k = 0; k < fl.n; ++k) if (fl.pos[k] < 5) fixed_low |= 1u << fl.pos[k];
+  const uint32_t free_low = ~fixed_low & 31u;
+  const bool leader = (lane & free_low) == 0;
+  const uint64_t wstride = (uint64_t)gridDim.x * nw;
+  for (uint64_t blk = (uint64_t)blockIdx.x * nw + wid; blk < nblk; blk += wstride) {
+    uint64_t base = 0;
+    for (int b = 0; b < bp.n; ++b) base |= ((blk >> b) & 1ULL) << bp.pos[b];
+    const uint64_t gi = base | lane | ext_or;
+    uint32_t f = 0, key = 0;
+    for (int k = 0; k < fl.n; ++k) f |= (uint32_t)((gi >> fl.pos[k]) & 1ULL) << k;
+    const bool valid = f == fval;
+    if (!__any_sync(0xffffffffu, valid)) continue;                 // the whole block fails the filter: not read at all
+#pragma unroll 4
+    for (int k = 0; k < bl.n; ++k) key |= (uint32_t)((gi >> bl.pos[k]) & 1ULL) << k;
+    const double2* p = state + base + lane;
+    double sum = 0.0;
+    double2 a0 = __ldcs(p + offs[0]), a1 = __ldcs(p + offs[1]), a2 = __ldcs(p + offs[2]), a3 = __ldcs(p + offs[3]);
+#pragma unroll 2
+    for (uint32_t t = 0; t < 64; t += 4) {
+      double2 b0 = a0, b1 = a1, b2 = a2, b3 = a3;
+      if (t + 4 < 64) { b0 = __ldcs(p + offs[t + 4]); b1 = __ldcs(p + offs[t + 5]); b2 = __ldcs(p + offs[t + 6]); b3 = __ldcs(p + offs[t + 7]); }
+      sum += (a0.x * a0.x + a0.y * a0.y) + (a1.x * a1.x + a1.y * a1.y);
+      sum += (a2.x * a2.x + a2.y * a2.y) + (a3.x * a3.x + a3.y * a3.y);
+      a0 = b0; a1 = b1; a2 = b2; a3 = b3;
+    }
+    if (!valid) sum = 0.0;
+#pragma unroll
+    for (uint32_t b = 0; b < 5; ++b)
+      if ((free_low >> b) & 1u) sum += __shfl_xor_sync(0xffffffffu, sum, 1u << b);
+    if (leader && valid) mine[key] += sum;
+    __syncwarp();
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < nk; k += nthreads) {
+    double t = 0.0;
+    for (uint32_t w = 0; w < nw; ++w) t += hist[(size_t)w * nk + k];
+    partials[(uint64_t)blockIdx.x * nk + k] = t;
+  }
+}
+
 cudaError_t launch_marginal(const double2* state, uint64_t count, uint64_t ext_or, const BitList& bl, const BitList& fl, uint32_t fval,
                             double* partials, int grid, cudaStream_t s) {
   int nw = (int)(8192u >> bl.n);
   nw = nw < 1 ? 1 : (nw > 8 ? 8 : nw);
+  // block-wise kernel: power-of-two slice of >= 2^11 amplitudes with six free index bits >= 5
+  if (count >= 2048 && (count & (count - 1)) == 0) {
+    int nl = 0;
+    while ((1ULL << nl) < count) ++nl;
+    uint64_t used = 31;                                           // lane bits
+    for (int k = 0; k < bl.n; ++k) if (bl.pos[k] < nl) used |= 1ULL << bl.pos[k];
+    for (int k = 0; k < fl.n; ++k) if (fl.pos[k] < nl) used |= 1ULL << fl.pos[k];
+    BitList freeb; freeb.n = 0;
+    for (int p = 5; p < nl && freeb.n < 6; ++p) if (!((used >> p) & 1)) { freeb.pos[freeb.n++] = p; used |= 1ULL << p; }
+    if (freeb.n == 6) {
+      BasePos bp; bp.n = 0;
+      uint64_t taken = 31;
+      for (int k = 0; k < 6; ++k) taken |= 1ULL << freeb.pos[k];
+      for (int p = 5; p < nl; ++p) if (!((taken >> p) & 1)) bp.pos[bp.n++] = p;
+      static std::atomic<uint64_t> configured_b{0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!(configured_b.load() & (1ULL << (dev & 63)))) {
+        cudaError_t e = cudaFuncSetAttribute(k_marginal_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return e;
+        configured_b.fetch_or(1ULL << (dev & 63));
+      }
+      k_marginal_blocks<<<grid, 32 * nw, (sizeof(double) << bl.n) * nw, s>>>(state, count >> 11, ext_or, bl, fl, fval, freeb, bp, partials);
+      return cudaGetLastError();
+    }
+  }
   static std::atomic<uint64_t> configured{0};
   int dev = 0;
   cudaGetDevice(&dev);
