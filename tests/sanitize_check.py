@@ -68,6 +68,17 @@ def main():
         assert sv.measure_qubits([1, 7, 3], 0.4)[0] == bits
         assert np.max(np.abs(sv.get_state() - col)) <= 1e-10
         sv.normalize()
+    # block-wise reduction kernels (slices of >= 2^11 amplitudes with six free index bits): marginal histogram, diagonal terms
+    n2 = 14
+    init2 = np.random.default_rng(6).standard_normal(1 << n2) + 1j * np.random.default_rng(7).standard_normal(1 << n2)
+    init2 /= np.linalg.norm(init2)
+    H2 = C.max_cut_hamiltonian(C.random_regular_graph(n2, 3, seed=11), n2)
+    with L.StateVector(n2) as sv:
+        sv.set_state(init2)
+        assert abs(sv.expect_hamiltonian(H2) - O.hamiltonian_expectation(H2, init2)) <= 1e-10
+        for qs in ([0, 13], [2], [13, 12, 11, 0]):
+            _bits, _col, probs2 = O.measure_specific_qubits(init2, qs, 0.4)
+            assert np.max(np.abs(sv.marginal_probabilities(qs) - np.array(probs2))) <= 1e-10
     ops = [{"operation-type": "global-h", "operation-params": {}}]
     for _ in range(3):
         ops += [{"operation-type": "phase-oracle", "operation-params": {"index": 77}}, {"operation-type": "grover-diffusion", "operation-params": {}}]
