@@ -170,6 +170,45 @@ void tile_prof_dump() {
 void tile_prof_dump() {}
 #endif
 
+// ------------------------------------------------------------------ optional timeline trace (-DQCB_TILE_TRACE)
+// Time stamps of one CTA's warps at the hand-over points of the tile pipeline (tile arrived, pass started, first operands in
+// flight, steady-state loop entered / left, results stored, tile released; mover: loads issued, tile written back), for a few
+// tiles of every launch.  Dumped as text when the handle is destroyed; scripts/trace_summary.py turns it into per-segment
+// cycle counts.  Timing experiments only.
+#ifdef QCB_TILE_TRACE
+__device__ unsigned long long g_tile_trace[1 << 16];
+__device__ unsigned g_tile_trace_n;
+struct TileTrace {
+  uint32_t warp, j, r;
+  bool on;
+  __device__ __forceinline__ void operator()(uint32_t id) const {
+    if (!on) return;
+    const unsigned k = atomicAdd(&g_tile_trace_n, 1u);
+    if (k < (1u << 16))
+      g_tile_trace[k] = ((unsigned long long)id << 56) | ((unsigned long long)warp << 52) | ((unsigned long long)(j & 0xffu) << 44) |
+                        ((unsigned long long)(r & 0xfu) << 40) | ((unsigned long long)clock64() & 0xffffffffffULL);
+  }
+};
+#define TRACE_MAKE(w, jj, rr) TileTrace{(w), (jj), (rr), blockIdx.x == 3u && (threadIdx.x & 31u) == 0u && (jj) >= 40u && (jj) < 44u}
+void tile_trace_dump() {
+  unsigned n = 0;
+  if (cudaMemcpyFromSymbol(&n, g_tile_trace_n, sizeof n) != cudaSuccess || n == 0) return;
+  if (n > (1u << 16)) n = 1u << 16;
+  unsigned long long* h = (unsigned long long*)malloc(sizeof(unsigned long long) * n);
+  if (cudaMemcpyFromSymbol(h, g_tile_trace, sizeof(unsigned long long) * n) == cudaSuccess)
+    for (unsigned i = 0; i < n; ++i)
+      fprintf(stderr, "[tile-trace] %u %u %u %u %llu\n", (unsigned)(h[i] >> 56), (unsigned)(h[i] >> 52) & 15u, (unsigned)(h[i] >> 44) & 255u,
+              (unsigned)(h[i] >> 40) & 15u, h[i] & 0xffffffffffULL);
+  free(h);
+  unsigned z = 0;
+  cudaMemcpyToSymbol(g_tile_trace_n, &z, sizeof z);
+}
+#else
+struct TileTrace { __device__ __forceinline__ void operator()(uint32_t) const {} };
+#define TRACE_MAKE(w, jj, rr) TileTrace{}
+void tile_trace_dump() {}
+#endif
+
 // ------------------------------------------------------------------ tensor-core round
 // One warp applies the round's dense 16x16 real matrix to 8 groups at a time:
 //   D(16x8) = A(16x16) * B(16x8),  A = matrix variant (fragments from global through L1, reloaded only when the
@@ -492,11 +531,13 @@ __device__ __forceinline__ void k3_pp(K3Set& c, K3Set& n, double& pr0, double& p
   xmma<ABL>(pi0, pi1, A[5], c.d1, pi0, pi1);
 }
 // per even and >= 4
+// (Also fetching the NEXT pass's lane entry and first batch entries here, so that a pass starts with its operand loads instead
+// of dependent table look-ups, was measured slower: 5604 - 5639 vs 5716 - 5723 gates/s, profiles/r2u_ab.log.)
 // mid(): work for the NEXT pass (operand prefetch) placed between the peeled calls, where its latency chain (table lookups,
 // address arithmetic, fragment loads) hides behind this pass's tensor instructions instead of sitting between two passes
 template <bool DIRECT, int ABL = 0, class F>
 __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12],
-                                              const K3Out& out, F&& mid) {
+                                              const K3Out& out, F&& mid, const TileTrace tr = TileTrace{}) {
   K3Set a, b;
   double pr0 = 0, pr1 = 0, pi0 = 0, pi1 = 0;
   uint32_t pa0 = 0, pa1 = 0;
@@ -509,6 +550,7 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
   xlds<ABL>(tile_s + (lt.x ^ b.X), b.r0, b.i0);
   xlds<ABL>(tile_s + (lt.y ^ b.X), b.r1, b.i1);
   uint32_t xq = btab[2];
+  tr(4);
   a.s0 = a.r0 + a.i0; a.d0 = a.i0 - a.r0; a.s1 = a.r1 + a.i1; a.d1 = a.i1 - a.r1;
   xmma<ABL>(a.K0, a.K1, A[0], a.r0, 0.0, 0.0);
   xmma<ABL>(a.K0, a.K1, A[1], a.r1, a.K0, a.K1);
@@ -516,7 +558,9 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
   k3_pp<true, true, false, DIRECT, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(0));
   xq = btab[3];
   k3_pp<true, true, true, DIRECT, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(1));
+  tr(5);
   mid();
+  tr(6);
   // batches 2 .. per-3 (both look-aheads exist)
   // two loop bodies (four batches) per back edge: +2 % over one (profiles/r2g_ab.log); fully unrolled, ptxas serialises the batches
 #ifdef QCB_PP_UNROLL1
@@ -530,17 +574,19 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
     xq = btab[i + 3u];
     k3_pp<true, true, true, DIRECT, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, xq, A, out, gq(i + 1u));
   }
+  tr(7);
   k3_pp<true, false, true, DIRECT, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, 0u, A, out, gq(per - 2u));
   k3_pp<false, false, true, DIRECT, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, pg, tile_s, lt, 0u, A, out, gq(per - 1u));
   if (DIRECT) { __stcs(out.gbase + (out.g0 ^ pg), double2{pr0, pi0}); __stcs(out.gbase + (out.g1 ^ pg), double2{pr1, pi1}); }
   else { __syncwarp(); xsts<ABL>(pa0, pr0, pi0); xsts<ABL>(pa1, pr1, pi1); }
+  tr(8);
 }
 
 // One warp's share of a three-product round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
 template <bool DIRECT, class F>
 __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
                                              uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur,
-                                             K3Out out, F&& mid) {
+                                             K3Out out, F&& mid, const TileTrace tr = TileTrace{}) {
   const uint4 lt = lane_tab_r[2u * lane];
   out.tile_s = tile_s; out.lz = lt.z; out.lw = lt.w;
   if (DIRECT) {   // lane parts of the global offsets: second table entry of the lane (written by the prologue for the last round)
@@ -559,7 +605,7 @@ __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_
         default: break;
       }
 #endif
-      k3_batches_pp<DIRECT>(tile_s, lt, btab, per, A, out, mid);
+      k3_batches_pp<DIRECT>(tile_s, lt, btab, per, A, out, mid, tr);
       return;
     }
 #endif
@@ -650,7 +696,8 @@ __device__ __forceinline__ void k3x_pp(K3XSet& c, K3XSet& n, double& pr0, double
 // second - measured the same: 5485 vs 5511 gates/s, profiles/r2n_ab.log; on registers alone it loses 9 % to the drain between
 // the blocks, scripts/dmma_mix.cu.)
 template <int ABL = 0, class F>
-__device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12], F&& mid) {
+__device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12], F&& mid,
+                                               const TileTrace tr = TileTrace{}) {
   K3XSet a, b;
   double pr0 = 0, pr1 = 0, pi0 = 0, pi1 = 0;
   uint32_t pa0 = 0, pa1 = 0;
@@ -661,11 +708,14 @@ __device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, 
   xlds<ABL>(tile_s + (lt.x ^ b.X), b.r0, b.i0);
   xlds<ABL>(tile_s + (lt.y ^ b.X), b.r1, b.i1);
   uint32_t xq = btab[2];
+  tr(4);
   k3x_first_block<ABL>(a, A);
   k3x_pp<true, true, false, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
   xq = btab[3];
   k3x_pp<true, true, true, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
+  tr(5);
   mid();
+  tr(6);
 #pragma unroll 1
   for (uint32_t i = 2; i + 2u < per; i += 2u) {
     xq = btab[i + 2u];
@@ -673,10 +723,12 @@ __device__ __forceinline__ void k3x_batches_pp(uint32_t tile_s, const uint4 lt, 
     xq = btab[i + 3u];
     k3x_pp<true, true, true, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, xq, A);
   }
+  tr(7);
   k3x_pp<true, false, true, ABL>(a, b, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
   k3x_pp<false, false, true, ABL>(b, a, pr0, pr1, pi0, pi1, pa0, pa1, tile_s, lt, 0u, A);
   __syncwarp();
   xsts<ABL>(pa0, pr0, pi0); xsts<ABL>(pa1, pr1, pi1);
+  tr(8);
 }
 // any number of batches, one after the other (short shares, variant changes inside a share)
 __device__ __forceinline__ void k3x_batches_simple(uint32_t tile_s, const uint4 lt, const uint32_t* btab, uint32_t per, const double (&A)[12]) {
@@ -704,7 +756,7 @@ __device__ __forceinline__ void k3x_batches_simple(uint32_t tile_s, const uint4 
 template <class F>
 __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
                                               uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur,
-                                              F&& mid) {
+                                              F&& mid, const TileTrace tr = TileTrace{}) {
   const uint4 lt = lane_tab_r[2u * lane];
   if ((btab[0] >> 20) == (btab[per - 1u] >> 20)) {
     if (per >= 4u && !(per & 1u)) {
@@ -716,7 +768,7 @@ __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane
         default: break;
       }
 #endif
-      k3x_batches_pp<0>(tile_s, lt, btab, per, A, mid);
+      k3x_batches_pp<0>(tile_s, lt, btab, per, A, mid, tr);
     } else { mid(); k3x_batches_simple(tile_s, lt, btab, per, A); }
     return;
   }
@@ -783,11 +835,13 @@ __device__ __forceinline__ void mover_fast(double2* __restrict__ state, const ui
         }
       }
       cp_async_mbar_arrive(full + (j % nbuf));
+      TRACE_MAKE(8u + (mt >> 5), j, 0u)(20);
       PF_ADD(PF_M_LOAD);
     }
     if (j + 1u >= nbuf) {
       const uint32_t s = j + 1u - nbuf;                        // tile to write back (s < T by the loop bound)
       mbar_wait<true>(done + (s % nbuf), (s / nbuf) & 1u);
+      TRACE_MAKE(8u + (mt >> 5), s, 0u)(21);
       PF_ADD(PF_M_WAIT_DONE);
       const uint64_t t = active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x);
       char* gb = reinterpret_cast<char*>(state + tile_base(sprog, sc, t) + low);
@@ -801,6 +855,7 @@ __device__ __forceinline__ void mover_fast(double2* __restrict__ state, const ui
         for (uint32_t u = 0; u < 8; ++u) __stcs(reinterpret_cast<double2*>(gb + ((uint64_t)roff[k0 + u] << 8)), v[u]);
         if (pause) __nanosleep(pause);
       }
+      TRACE_MAKE(8u + (mt >> 5), s, 0u)(22);
       PF_ADD(PF_M_STORE);
     }
   }
@@ -1032,10 +1087,15 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
     PF_DECL;
     for (uint32_t j = grp; j < T; j += NG) {
       const uint32_t b = j % nbuf;
+      TRACE_MAKE(warp, j, 0u)(0);
       mbar_wait(full + b, (j / nbuf) & 1u);
+      TRACE_MAKE(warp, j, 0u)(1);
       PF_ADD(PF_C_WAIT_FULL);
       for (uint32_t r = 0; r < sc.n_rounds; ++r) {
+        const TileTrace tr = TRACE_MAKE(warp, j, r);
+        tr(9);
         if (r && !DBG_ON(8)) group_bar_sync<GT>(grp);
+        tr(2);
         PF_ADD(PF_C_BARRIER);
         uint32_t nj = j, nr = r + 1u;
         if (nr == sc.n_rounds) { nr = 0; nj = j + NG; }
@@ -1055,11 +1115,12 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
           if ((FORM != 2 || !active) && do_pf) prefetch(nj, nr);      // the 16x16 form keeps the prefetch between the passes
 #endif
           PF_ADD(PF_C_SETUP);
+          tr(3);
           if (active) {
             if constexpr (FORM == 2) {
               if (round_kind(sprog, r) == 3u) {
                 k3x_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                              mats, lane, Ac, curc, mid);
+                              mats, lane, Ac, curc, mid, tr);
               } else {
               K3Out out;
               out.gtab = gtab + b0; out.gbase = nullptr; out.g0 = out.g1 = 0;
@@ -1069,7 +1130,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
                                    mats, lane, Ac, curc, out, mid);
               } else {
                 k3_round_run<false>(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                                    mats, lane, Ac, curc, out, mid);
+                                    mats, lane, Ac, curc, out, mid, tr);
               }
               }
             } else
@@ -1094,6 +1155,7 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
       if (use_tma) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(done + b);
+      TRACE_MAKE(warp, j, 15u)(10);
     }
     PF_TOTAL(PF_C_TOTAL);
   }

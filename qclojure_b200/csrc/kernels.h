@@ -36,6 +36,7 @@ cudaError_t build_tile_maps(double2* state, int n_local, TileMaps* out);
 cudaError_t launch_tile_stage(double2* state, const uint64_t* stage_dev, const uint64_t* stage_host, uint32_t stage_words,
                               const double* dev_vals, int num_sms, cudaStream_t stream, uint64_t* out_active, const TileMaps* maps);
 void tile_prof_dump();   // prints the cycle accounting of k_tile_stage (only in a PROFILE=1 build)
+void tile_trace_dump();  // prints the timeline trace of k_tile_stage (only in a -DQCB_TILE_TRACE build)
 cudaError_t launch_set_amp(double2* state, uint64_t idx, double re, double im, cudaStream_t s);
 cudaError_t launch_reduce(const double2* state, uint64_t count, int mode, double* partials, int grid, cudaStream_t s);
 cudaError_t launch_finalize(const double* partials, uint32_t nparts, uint32_t K, int post, double param, double* out, cudaStream_t s);

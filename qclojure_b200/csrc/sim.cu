@@ -1310,6 +1310,7 @@ int32_t qcb_destroy(qcb_handle h) {
   for (auto& p : h->peer_state) if (p) { if (h->peers_ipc) cudaIpcCloseMemHandle(p); p = nullptr; }
   if (h->comm) g_nccl.CommDestroy(h->comm);
   tile_prof_dump();
+  tile_trace_dump();
   cudaFree(h->state); cudaFree(h->d_prog); cudaFree(h->d_vals); cudaFree(h->d_partials); cudaFree(h->d_scratch); cudaFree(h->xbuf);
   cudaFree(h->noisy_init);
   for (double2* b : h->ckpts) cudaFree(b);
