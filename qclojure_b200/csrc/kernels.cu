@@ -387,6 +387,30 @@ __device__ __forceinline__ void xsts(uint32_t addr, double x, double y) {
   if (ABL & 2) { if (addr == 0xffffffffu) sts_c128(addr, x, y); } else sts_c128(addr, x, y);     // never taken, keeps the results alive
 }
 
+// Far phases of a pass (tile_core.h "far phases"): the row factors d = dr + i di of this lane's row (lane / 4) for the first and
+// the second block, computed once per tile and pass; apply() scales a freshly loaded set of A fragments.
+struct FarD {
+  double dr1, di1, dr2, di2;
+  bool on1, on2;
+  __device__ __forceinline__ void apply(double (&A)[12]) const {
+    if (on1) { far_scale(A[0], A[2], A[4], dr1, di1); far_scale(A[1], A[3], A[5], dr1, di1); }
+    if (on2) { far_scale(A[6], A[8], A[10], dr2, di2); far_scale(A[7], A[9], A[11], dr2, di2); }
+  }
+};
+// the four sums of a far table for the tile ext_hi: lane e takes entry e (at most 32 entries), xor-shuffle reduction
+__device__ __forceinline__ void far_sums_warp(const uint64_t* __restrict__ tab, uint32_t n, uint64_t ext_hi, uint32_t lane, double (&s)[4]) {
+  s[0] = s[1] = s[2] = s[3] = 0.0;
+  if (lane < n) {
+    const uint64_t* e = tab + 5u * lane;
+    if ((ext_hi >> __ldg(e)) & 1ULL) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] = __longlong_as_double((long long)__ldg(e + 1 + k));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s[k] = warp_sum(s[k]);
+}
+
 // Where a round's results go.  Shared tile: byte address tile_s + (lane offset ^ batch offset).  DIRECT (the last round of a
 // sweep, stage flag T_FLAG_DIRECT_STORE): straight to global memory from registers - amplitude offset (lane part ^ batch
 // part) from the tile's base; the batch parts come from gtab (built once per launch), the lane parts are per-round constants.
@@ -586,7 +610,7 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
 template <bool DIRECT, class F>
 __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
                                              uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur,
-                                             K3Out out, F&& mid, const TileTrace tr = TileTrace{}) {
+                                             K3Out out, F&& mid, const FarD& far, const TileTrace tr = TileTrace{}) {
   const uint4 lt = lane_tab_r[2u * lane];
   out.tile_s = tile_s; out.lz = lt.z; out.lw = lt.w;
   if (DIRECT) {   // lane parts of the global offsets: second table entry of the lane (written by the prologue for the last round)
@@ -620,7 +644,7 @@ __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_
     const uint32_t v = var_hi | (btab[b] >> 20);
     uint32_t e = b + 1u;
     while (e < per && (btab[e] >> 20) == (btab[b] >> 20)) ++e;
-    if (v != cur) { k3_load_A(A, mats, v); cur = v; }
+    if (v != cur) { k3_load_A(A, mats, v); far.apply(A); cur = v; }
     K3Out o2 = out;
     o2.gtab = out.gtab + b;
 #ifndef QCB_K3_ROTATE
@@ -756,7 +780,7 @@ __device__ __forceinline__ void k3x_batches_simple(uint32_t tile_s, const uint4 
 template <class F>
 __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
                                               uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur,
-                                              F&& mid, const TileTrace tr = TileTrace{}) {
+                                              F&& mid, const FarD& far, const TileTrace tr = TileTrace{}) {
   const uint4 lt = lane_tab_r[2u * lane];
   if ((btab[0] >> 20) == (btab[per - 1u] >> 20)) {
     if (per >= 4u && !(per & 1u)) {
@@ -778,7 +802,7 @@ __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane
     const uint32_t v = var_hi | (btab[b] >> 20);
     uint32_t e = b + 1u;
     while (e < per && (btab[e] >> 20) == (btab[b] >> 20)) ++e;
-    if (v != cur) { k3x_load_A(A, mats, v); cur = v; }
+    if (v != cur) { k3x_load_A(A, mats, v); far.apply(A); cur = v; }
     if (e - b >= 4u && !((e - b) & 1u)) k3x_batches_pp<0>(tile_s, lt, btab + b, e - b, A, [] {});
     else k3x_batches_simple(tile_s, lt, btab + b, e - b, A);
     b = e;
@@ -1106,6 +1130,30 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
           for (int i = 0; i < NA; ++i) Ac[i] = A[i];
           const uint32_t curc = cur, var_hic = var_hi;
           const double* mats = reinterpret_cast<const double*>(stage_g + rtab[r].y) + lane;
+          FarD far;
+          far.on1 = far.on2 = false;
+          if constexpr (FORM == 2) {
+            // far phases: diagonal gates with an operand outside the tile scale the rows of the block by a constant of the tile
+            const uint64_t* w = sprog + T_STAGE_WORDS + (uint64_t)r * T_ROUND_WORDS;
+            const uint32_t fn = (uint32_t)w[39];
+            if (fn != 0u && active) {
+              const uint64_t ext_hi = sc.ext_hi_base | active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
+              double fs[4];
+              if (fn & 0xffffu) {
+                far_sums_warp(stage_g + w[37], fn & 0xffffu, ext_hi, lane, fs);
+                const uint32_t mm[3] = {(uint32_t)w[35] & 15u, (uint32_t)(w[35] >> 4) & 15u, (uint32_t)(w[35] >> 8) & 15u};
+                sincos(far_angle(fs, k3_pattern_index(lane >> 2, mm)), &far.di1, &far.dr1);
+                far.on1 = true;
+              }
+              if (fn >> 16) {
+                far_sums_warp(stage_g + w[38], fn >> 16, ext_hi, lane, fs);
+                const uint32_t mm[3] = {(uint32_t)w[36] & 15u, (uint32_t)(w[36] >> 4) & 15u, (uint32_t)(w[36] >> 8) & 15u};
+                sincos(far_angle(fs, k3_pattern_index(lane >> 2, mm)), &far.di2, &far.dr2);
+                far.on2 = true;
+              }
+              far.apply(Ac);
+            }
+          }
           const bool do_pf = next_mma && !(DBG_ON(16) && cur != 0xffffffffu);
 #ifdef QCB_PREFETCH_EARLY
           if (do_pf) prefetch(nj, nr);
@@ -1120,17 +1168,17 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
             if constexpr (FORM == 2) {
               if (round_kind(sprog, r) == 3u) {
                 k3x_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                              mats, lane, Ac, curc, mid, tr);
+                              mats, lane, Ac, curc, mid, far, tr);
               } else {
               K3Out out;
               out.gtab = gtab + b0; out.gbase = nullptr; out.g0 = out.g1 = 0;
               if (direct && r + 1u == sc.n_rounds) {
                 out.gbase = state + tile_base(sprog, sc, active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x));
                 k3_round_run<true>(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                                   mats, lane, Ac, curc, out, mid);
+                                   mats, lane, Ac, curc, out, mid, far);
               } else {
                 k3_round_run<false>(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                                    mats, lane, Ac, curc, out, mid, tr);
+                                    mats, lane, Ac, curc, out, mid, far, tr);
               }
               }
             } else

@@ -84,6 +84,7 @@ Config config_from(const qcb_config& c) {
   if (const char* e = std::getenv("QCB_PAIR_SEARCH")) { k.pair_search = std::max(1, std::atoi(e)); k.plan_portfolio = 0; }
   if (const char* e = std::getenv("QCB_PAIR_EFF_PCT")) { k.pair_eff_pct = std::atoi(e); k.plan_portfolio = 0; }
   if (const char* e = std::getenv("QCB_PLAN_PORTFOLIO")) k.plan_portfolio = std::atoi(e) ? 1 : 0;
+  if (const char* e = std::getenv("QCB_FAR_PHASE")) k.far_phase = std::atoi(e) ? 1 : 0;
   if (const char* e = std::getenv("QCB_THIN_DEFER")) k.thin_defer = std::atoi(e);            // experiment knob
   if (const char* e = std::getenv("QCB_WINDOW_SEARCH")) k.window_search = std::atoi(e);
   if (const char* e = std::getenv("QCB_ROUND_YIELD_PCT")) k.round_yield_pct = std::atoi(e);   // 0 = greedy tiles / rounds only
@@ -498,6 +499,9 @@ static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& wo
     size_t rb = rbase + r * ROUND_WORDS;
     words[rb + 2] = words.size() - base;
     for (double d : rd.frag) words.push_back(dbl_bits(d));
+    if (!rd.far.empty()) { words[rb + 37] = words.size() - base; for (uint64_t w : rd.far) words.push_back(w); }
+    if (!rd.far2.empty()) { words[rb + 38] = words.size() - base; for (uint64_t w : rd.far2) words.push_back(w); }
+    words[rb + 39] = (uint64_t)(rd.far.size() / 5) | ((uint64_t)(rd.far2.size() / 5) << 16);
   }
   words[base + 40] = words.size() - base;
 }
@@ -679,15 +683,81 @@ static uint64_t gate_bits(const Gate& g) {
   return b;
 }
 
+// ---- far phases.  A diagonal gate on exactly two bits (CRZ, CZ, controlled phase after lowering) one of which is a slot of the
+// round and the other lies OUTSIDE the tile (a tile-id or rank bit) needs no condition bit: for a given tile the far bit is a
+// constant, so the gate is a diagonal on one slot whose angle is a constant of the tile.  The product of all such gates of a
+// round is  D(tile) = e^{i gamma} prod_j diag(e^{-i phi_j}, e^{+i phi_j})_slot j,  gamma / phi_j = (constants, folded into the
+// matrices here) + sums over the far bits that are set - a ROW scaling of the round's 8x8 block as long as no later gate of the
+// round acts non-diagonally on that slot.  The kernel applies it per tile and pass to the A fragments (kernels.cu: far_factor).
+static bool far_kind(const Gate& g) {
+  if (g.kind == G_DTAB1) return popc(g.cmask) == 1 && g.t0 >= 0 && !((g.cmask >> g.t0) & 1);
+  if (g.kind == G_DMASK) return popc(g.dmask) == 2;
+  return false;
+}
+// flags[i] = gate i of `gates` rides as a far phase of a round with the CHOSEN slot bits slot_mask (tile of m bits)
+static void classify_far(const Config& cfg, const std::vector<Gate>& gates, uint64_t slot_mask, int m, std::vector<char>& flags) {
+  flags.assign(gates.size(), 0);
+  if (!cfg.far_phase || cfg.mma_form != 0) return;
+  const uint64_t tile_mask = (1ULL << m) - 1ULL;
+  uint64_t later_targets = 0;
+  for (size_t i = gates.size(); i-- > 0;) {
+    const Gate& g = gates[i];
+    if (far_kind(g)) {
+      const uint64_t b = gate_bits(g), l = b & slot_mask, h = b & ~tile_mask;
+      if (popc(b) == 2 && popc(l) == 1 && popc(h) == 1 && !(later_targets & l)) flags[i] = 1;
+    }
+    later_targets |= g.target_mask();
+  }
+}
+// condition bits of a round: every bit a gate touches that is not a slot, far phases excepted
+static uint64_t round_cond_bits(const std::vector<Gate>& gates, const std::vector<char>& far, uint64_t slot_mask) {
+  uint64_t cond = 0;
+  for (size_t i = 0; i < gates.size(); ++i) if (!far[i]) cond |= gate_bits(gates[i]) & ~slot_mask;
+  return cond;
+}
+// Far-phase table of one block: slots = final slot positions (pattern bit j <-> slots[j]).  Entry = {far position - m, gamma,
+// phi_0, phi_1, phi_2}.  With D0 / D1 the gate's diagonal on its slot for the far bit = 0 / 1: D0 goes into the matrices
+// (far bit forced to 0 by the caller), D1 / D0 = e^{i g} diag(e^{-i f}, e^{+i f}) into the table.
+static void build_far_table(const std::vector<Gate>& gates, const std::vector<char>& far, const std::vector<int>& slots, int m,
+                            std::vector<uint64_t>& out) {
+  out.clear();
+  std::vector<int> pos;
+  std::vector<double> val;                       // 4 per entry
+  const uint64_t tile_mask = (1ULL << m) - 1ULL;
+  for (size_t i = 0; i < gates.size(); ++i) {
+    if (!far[i]) continue;
+    const Gate& g = gates[i];
+    const uint64_t b = gate_bits(g), hm = b & ~tile_mask;
+    const int h = 63 - __builtin_clzll(hm);
+    int j = -1, lp = -1;
+    for (size_t k = 0; k < slots.size(); ++k) if ((b >> slots[k]) & 1) { j = (int)k; lp = slots[k]; }
+    std::vector<int> one = {lp};
+    std::vector<cplx> v0 = {cplx{1, 0}, cplx{1, 0}}, v1 = v0;
+    small_apply(g, one, v0, 0);
+    small_apply(g, one, v1, hm);
+    auto ratio_arg = [](cplx a1, cplx a0) { return std::atan2(a1.im * a0.re - a1.re * a0.im, a1.re * a0.re + a1.im * a0.im); };   // arg(a1 / a0)
+    const double ra = ratio_arg(v1[0], v0[0]), rb = ratio_arg(v1[1], v0[1]);
+    size_t e = 0;
+    while (e < pos.size() && pos[e] != h - m) ++e;
+    if (e == pos.size()) { pos.push_back(h - m); val.insert(val.end(), 4, 0.0); }
+    val[4 * e] += 0.5 * (ra + rb);
+    val[4 * e + 1 + j] += 0.5 * (rb - ra);
+  }
+  for (size_t e = 0; e < pos.size(); ++e) {
+    out.push_back((uint64_t)pos[e]);
+    for (int k = 0; k < 4; ++k) out.push_back(dbl_bits(val[4 * e + k]));
+  }
+}
+
 // ---- tensor-core round: the whole round as 2^k dense 16x16 real matrices in mma.m16n8k16 A-fragment order
 static bool dmma_eligible(const Config& cfg, const Stage& st, const Round& rd) {
   if (!cfg.dense_mma || st.m < 6 || rd.slot_pos.size() > 3) return false;
-  uint64_t slot_mask = 0, cond = 0;
+  uint64_t slot_mask = 0;
   for (int p : rd.slot_pos) slot_mask |= 1ULL << p;
-  for (const Gate& g : rd.gates) {
-    if (g.kind == G_REFLECT || g.kind == G_DENSE) return false;
-    cond |= gate_bits(g) & ~slot_mask;
-  }
+  for (const Gate& g : rd.gates) if (g.kind == G_REFLECT || g.kind == G_DENSE) return false;
+  std::vector<char> far;
+  classify_far(cfg, rd.gates, slot_mask, st.m, far);
+  const uint64_t cond = round_cond_bits(rd.gates, far, slot_mask);
   // padding the slot set to 3 needs free tile-local bits; lanes need 3 more
   const int free_bits = st.m - (int)rd.slot_pos.size() - popc(cond & ((1ULL << st.m) - 1ULL));
   if (free_bits < (3 - (int)rd.slot_pos.size()) + 3) return false;
@@ -798,8 +868,10 @@ static void build_k3_round(const Config& cfg, const Stage& st, Round& rd) {
   const int m = st.m;
   uint64_t slot_mask = 0;
   for (int p : rd.slot_pos) slot_mask |= 1ULL << p;
-  uint64_t cond = 0;
-  for (const Gate& g : rd.gates) cond |= gate_bits(g) & ~slot_mask;
+  std::vector<char> far;
+  classify_far(cfg, rd.gates, slot_mask, m, far);
+  const uint64_t cond = round_cond_bits(rd.gates, far, slot_mask);
+  const uint64_t not_tile = ~((1ULL << m) - 1ULL);
   rd.cond_pos.clear();
   for (int p = 0; p < 64; ++p) if ((cond >> p) & 1) rd.cond_pos.push_back(p);
   const uint64_t tile_mask = (1ULL << m) - 1ULL;
@@ -849,7 +921,11 @@ static void build_k3_round(const Config& cfg, const Stage& st, Round& rd) {
     for (int j = 0; j < k; ++j) if ((var >> j) & 1) fixed |= 1ULL << rd.cond_pos[j];
     cplx M[8][8];
     for (int row = 0; row < 8; ++row) for (int col = 0; col < 8; ++col) M[row][col] = cplx{row == col ? 1.0 : 0.0, 0.0};
-    for (const Gate& g : rd.gates) small_apply_cols(g, rd.slot_pos, M, 8, fixed);
+    for (size_t gi = 0; gi < rd.gates.size(); ++gi) {
+      const Gate& g = rd.gates[gi];
+      // a far phase enters with its far bit = 0; what the bit adds when it is set is in the far table
+      small_apply_cols(g, rd.slot_pos, M, 8, far[gi] ? (fixed & ~(gate_bits(g) & not_tile)) : fixed);
+    }
     for (int reg = 0; reg < 6; ++reg) for (int lane = 0; lane < 32; ++lane) {
       const int mi = lane / 4, ki = lane % 4 + 4 * (reg & 1);
       const cplx z = M[pattern_of(mi, rd.mmap)][pattern_of(ki, rd.kmap)];
@@ -857,9 +933,9 @@ static void build_k3_round(const Config& cfg, const Stage& st, Round& rd) {
       rd.frag[var * K3_FRAG_DOUBLES_HOST + (size_t)reg * 32 + lane] = v;
     }
   }
+  build_far_table(rd.gates, far, rd.slot_pos, m, rd.far);
   rd.dmma = true;
   rd.k3 = true;
-  (void)cfg;
 }
 
 // Two rounds in one pass (round kind 3, tile_core.h "paired rounds"): rd.gates on the slot triple S1 = rd.slot_pos, then
@@ -872,9 +948,11 @@ static void build_k3_pair_round(const Config& cfg, const Stage& st, Round& rd) {
   const int m = st.m;
   uint64_t s1 = 0, s2 = rd.slot_mask2;
   for (int p : rd.slot_pos) s1 |= 1ULL << p;
-  uint64_t cond = 0;
-  for (const Gate& g : rd.gates) cond |= gate_bits(g) & ~s1;
-  for (const Gate& g : rd.gates2) cond |= gate_bits(g) & ~s2;
+  std::vector<char> far1, far2;
+  classify_far(cfg, rd.gates, s1, m, far1);
+  classify_far(cfg, rd.gates2, s2, m, far2);
+  const uint64_t cond = round_cond_bits(rd.gates, far1, s1) | round_cond_bits(rd.gates2, far2, s2);
+  const uint64_t not_tile = ~((1ULL << m) - 1ULL);
   rd.cond_pos.clear();
   for (int p = 0; p < 64; ++p) if ((cond >> p) & 1) rd.cond_pos.push_back(p);
   uint64_t busy = s1 | s2 | cond;
@@ -923,8 +1001,14 @@ static void build_k3_pair_round(const Config& cfg, const Stage& st, Round& rd) {
     for (int j = 0; j < k; ++j) if ((var >> j) & 1) fixed |= 1ULL << rd.cond_pos[j];
     cplx M1[8][8], M2[8][8];
     for (int row = 0; row < 8; ++row) for (int col = 0; col < 8; ++col) M1[row][col] = M2[row][col] = cplx{row == col ? 1.0 : 0.0, 0.0};
-    for (const Gate& g : rd.gates) small_apply_cols(g, rd.slot_pos, M1, 8, fixed);
-    for (const Gate& g : rd.gates2) small_apply_cols(g, g2, M2, 8, fixed);
+    for (size_t gi = 0; gi < rd.gates.size(); ++gi) {
+      const Gate& g = rd.gates[gi];
+      small_apply_cols(g, rd.slot_pos, M1, 8, far1[gi] ? (fixed & ~(gate_bits(g) & not_tile)) : fixed);
+    }
+    for (size_t gi = 0; gi < rd.gates2.size(); ++gi) {
+      const Gate& g = rd.gates2[gi];
+      small_apply_cols(g, g2, M2, 8, far2[gi] ? (fixed & ~(gate_bits(g) & not_tile)) : fixed);
+    }
     for (int reg = 0; reg < 6; ++reg) for (int lane = 0; lane < 32; ++lane) {
       const int mi = lane / 4, ki = lane % 4 + 4 * (reg & 1);
       const cplx z1 = M1[pattern_of(mi, rd.mmap)][pattern_of(ki, rd.kmap)];
@@ -933,9 +1017,10 @@ static void build_k3_pair_round(const Config& cfg, const Stage& st, Round& rd) {
       rd.frag[var * FD + (size_t)(6 + reg) * 32 + lane] = (reg < 2) ? (z2.re + z2.im) : (reg < 4 ? -z2.im : z2.re);
     }
   }
+  build_far_table(rd.gates, far1, rd.slot_pos, m, rd.far);
+  build_far_table(rd.gates2, far2, g2, m, rd.far2);
   rd.dmma = true;
   rd.k3 = true;
-  (void)cfg;
 }
 
 static void fuse_round(Round& rd) {
@@ -973,6 +1058,7 @@ static void fuse_round(Round& rd) {
 struct RoundGate {
   uint64_t t, d, bits, want;   // non-diagonal targets, diagonal operands, all bits touched, tile-local part of them
   bool can_be_pure, later, reflect;
+  bool far_ok;                 // diagonal two-bit gate with exactly one tile-local operand: may ride as a far phase (classify_far)
 };
 
 // One candidate round: scan the pending gates in order and take every gate that fits slot bits inside `Rcap` (at most
@@ -985,6 +1071,7 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
   const int rmax = std::min(MAX_SLOT_BITS, st.m);
   const bool use_mma = cfg.dense_mma && st.m >= 6;
   uint64_t R = 0, touched = touched0, bx = 0, bz = 0;   // touched = bits of accepted gates; bx / bz = Blocker state
+  uint64_t closed = 0;                                  // slots carrying a far phase: no non-diagonal gate may follow on them
   taken.clear();
   rest.clear();
   auto fits = [&](uint64_t Rn) { return popc(Rn) <= rmax && (Rn & ~Rcap) == 0; };
@@ -994,6 +1081,12 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
     auto accept = [&](uint64_t Rn) { R = Rn; touched |= g.bits; taken.push_back((int)gi); };
     if ((g.t & (bx | bz)) || (g.d & bx)) { block(); continue; }
     if (partner && (g.reflect || (g.bits & avoid))) { block(); continue; }
+    if (g.t & closed) { block(); continue; }
+    if (use_mma && g.far_ok) {
+      // far phase: the tile-local operand becomes (or is) a slot, the far operand costs no condition bit
+      const uint64_t l = g.want, Rn = R | l;
+      if (fits(Rn) && popc(touched & ~Rn) <= MAX_COND_BITS) { R = Rn; touched |= l; closed |= l; taken.push_back((int)gi); continue; }
+    }
     // prefer making the gate *pure* (every tile-local bit it touches becomes a slot bit): pure gates fold into
     // the round's dense block for free; controls / diagonal operands on tile-id or rank bits can never be slots
     if (use_mma && !g.reflect) {
@@ -1048,9 +1141,21 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
       r.reflect = g.kind == G_REFLECT;
       r.can_be_pure = cfg.fusion && (r.bits & ~tile_mask) == 0 && g.kind != G_DPOP1 && g.kind != G_REFLECT;
       r.later = (later_targets & r.want) != 0;       // some later gate targets one of its bits
+      r.far_ok = cfg.far_phase && cfg.mma_form == 0 && far_kind(g) && popc(r.bits) == 2 && popc(r.want) == 1;
       later_targets |= r.t;
       targeted |= r.t;
     }
+  };
+  // condition bits a candidate round would have: every non-slot bit its gates touch, far phases excepted (classify_far's rule)
+  auto cond_of = [&](const std::vector<RoundGate>& G, const std::vector<int>& tk, uint64_t Rs) {
+    uint64_t cond = 0, later = 0;
+    for (size_t k = tk.size(); k-- > 0;) {
+      const RoundGate& g = G[tk[k]];
+      const uint64_t l = g.bits & Rs;
+      if (!(g.far_ok && popc(l) == 1 && !(later & l))) cond |= g.bits & ~Rs;
+      later |= g.t;
+    }
+    return cond;
   };
   // the same facts for a sub-list of the pending gates (what is left once a candidate round has taken its gates)
   auto subset = [&](const std::vector<int>& idx) {
@@ -1123,16 +1228,15 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
       for (size_t k = 0; k < cands.size(); ++k) {
         const RoundCand& a = cands[k];
         if (a.rest.empty()) continue;
-        uint64_t condA = 0;
         bool ok = true;
-        for (int i : a.taken) { condA |= pg[i].bits & ~a.R; ok = ok && !pg[i].reflect; }
+        for (int i : a.taken) ok = ok && !pg[i].reflect;
+        const uint64_t condA = cond_of(pg, a.taken, a.R);
         const int kl = popc(condA & tile_mask);
         if (!ok || popc(condA) > MAX_COND_BITS || popc(a.R) > 3 || 6 + kl > st.m) continue;
         subset(a.rest);
         choose(pg2, targeted2, true, a.R | (condA & tile_mask), condA, a.R, 1, pc);
         if (pc.empty()) continue;
-        uint64_t condB = 0;
-        for (int i : pc[0].taken) condB |= pg2[i].bits & ~pc[0].R;
+        const uint64_t condB = cond_of(pg2, pc[0].taken, pc[0].R);
         if (6 + popc((condA | condB) & tile_mask) > st.m || popc(condA | condB) > MAX_COND_BITS) continue;
         const double eff = (double)(a.taken.size() + pc[0].taken.size()) / pair_eff;
         if (eff > best_eff || (!best_pair && eff == best_eff)) { best_eff = eff; best_k = k; best_pair = true; best_b = pc[0]; }
@@ -1199,7 +1303,7 @@ void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const
   key.reserve(16 + perm_in.size() + 6 * gates.size());
   const int c[] = {cfg.n_total, cfg.n_local, cfg.rank, cfg.world, cfg.tile_bits, cfg.low_bits, cfg.fusion, cfg.max_stage_cost,
                    cfg.max_stage_rounds, cfg.dense_mma + 16 * cfg.mma_form + 32 * cfg.direct_store, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer,
-                   cfg.pair_rounds + 2 * cfg.pair_eff_pct + 2048 * cfg.pair_cost_q + 65536 * cfg.pair_search + 1048576 * cfg.plan_portfolio};
+                   cfg.pair_rounds + 2 * cfg.pair_eff_pct + 2048 * cfg.pair_cost_q + 65536 * cfg.pair_search + 1048576 * cfg.plan_portfolio + 2097152 * cfg.far_phase};
   for (int v : c) key.push_back((uint64_t)(int64_t)v);
   key.push_back(perm_in.size());
   for (int v : perm_in) key.push_back((uint64_t)v);

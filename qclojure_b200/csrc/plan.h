@@ -76,7 +76,8 @@ enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_
 //          three-product form, tile_core.h: K3Ctx, 3 = two three-product rounds on disjoint slot triples in one pass,
 //          tile_core.h "paired rounds")   [18] n_grp_bits   [19..29) grp_pos[10]
 //     [29] k (condition bits)  [30..34) cond_pos[4] (ext positions)  [34] j_load (kinds 2, 3: kmap)  [35] j_store (kinds 2, 3: mmap)
-//     [36] kind 3: mmap2
+//     [36] kind 3: mmap2   [37] / [38] word offset of the far-phase table of the first / second block (0 = none)
+//     [39] entries of the first table | entries of the second << 16
 //     tensor-core rounds: [2] = word offset of the A-fragment matrices (2^k * 256 / 192 / 384 doubles, after all descriptors)
 //   StageDesc [42] = number of leading words (descriptors + interpreter op slots) that the kernel copies to smem
 constexpr int STAGE_WORDS = 48;
@@ -115,6 +116,10 @@ struct Round {
   uint64_t slot_mask2 = 0;          // slot bits the scheduler chose for the second block (tile-local, before padding)
   int mmap2[3] = {0, 1, 2};         // index into grp_pos[0..2] of the bit carried by bit b of the second block's m-index
   int dense_rounds() const { return pair ? 2 : 1; }
+  // far phases (tile_core.h "far phases"): diagonal two-bit gates with one operand on a slot and the other OUTSIDE the tile are
+  // not condition bits - the product of their phases is a constant of the tile, applied by every lane to its A fragments.
+  // Per entry five words: ext position of the far bit minus m, then gamma, phi_0, phi_1, phi_2 (doubles) - see build_far_table.
+  std::vector<uint64_t> far, far2;  // first / second block
 };
 
 struct Stage {
@@ -156,6 +161,7 @@ struct Config {
   int pair_eff_pct = 170;      // cost of a paired pass in % of a single round (measured on B200: 3.39 ms vs 2.0 ms at 30 qubits):
                                // a pair is formed when its gates per unit of cost beat the best single round's
   int pair_cost_q = 7;         // cost of a paired pass in quarter rounds (a single round = 4) against the stage's round budget
+  int far_phase = 1;           // diagonal two-bit gates with a far operand (outside the tile) ride as tile-constant phases
   int plan_portfolio = 1;      // large circuits: schedule under a handful of budget settings, keep the plan the cost model prefers
   int thin_defer = 12;         // multi-GPU: a stage with fewer gates than this is not run while gates wait for an exchange
                                // (its gates ride along in the fuller sweeps after the exchange)

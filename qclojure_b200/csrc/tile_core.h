@@ -439,6 +439,7 @@ struct K3Ctx {
   uint32_t kmap[3], mmap[3];
   uint32_t mmap2[3];                         // round kind 3 only (see "paired rounds" below)
   uint64_t mat_off;
+  uint32_t far_off[2], far_n[2];             // far-phase tables of the first / second block (word offset from the stage, entries)
 };
 constexpr uint32_t K3_FRAG_DOUBLES = 192;   // per variant: 6 A registers x 32 lanes (P0 P1 N0 N1 R0 R1)
 constexpr uint32_t K3X_FRAG_DOUBLES = 384;  // round kind 3: the six registers of the first block, then those of the second
@@ -455,6 +456,31 @@ QCB_HD void decode_k3(const uint64_t* stage, uint32_t round_idx, K3Ctx& c) {
   }
   for (int j = 0; j < 10; ++j) c.grp_pos[j] = (uint32_t)w[19 + j];
   for (int j = 0; j < 4; ++j) c.cond_pos[j] = (uint32_t)w[30 + j];
+  c.far_off[0] = (uint32_t)w[37]; c.far_off[1] = (uint32_t)w[38];
+  c.far_n[0] = (uint32_t)w[39] & 0xffffu; c.far_n[1] = (uint32_t)(w[39] >> 16) & 0xffffu;
+}
+// ---- far phases (plan.cpp: classify_far / build_far_table).  A table entry is five words: position of a far bit (relative to
+// the tile bits, i.e. a bit of ext_hi), gamma, phi_0, phi_1, phi_2.  For the tile ext_hi the block's rows are scaled by
+//   d(pattern) = exp(i (G + sum_j (pattern bit j ? +F_j : -F_j))),   G / F_j = sums of gamma / phi_j over the entries whose bit is set.
+// far_sums: the four sums (sequential - the kernel does the same with a warp reduction over the entries).
+QCB_HD void far_sums(const uint64_t* tab, uint32_t n, uint64_t ext_hi, double (&s)[4]) {
+  s[0] = s[1] = s[2] = s[3] = 0.0;
+  for (uint32_t e = 0; e < n; ++e) {
+    if (!((ext_hi >> tab[5 * e]) & 1ULL)) continue;
+    for (int k = 0; k < 4; ++k) s[k] += as_double(tab[5 * e + 1 + k]);
+  }
+}
+QCB_HD double far_angle(const double (&s)[4], uint32_t pattern) {
+  return s[0] + ((pattern & 1u) ? s[1] : -s[1]) + ((pattern & 2u) ? s[2] : -s[2]) + ((pattern & 4u) ? s[3] : -s[3]);
+}
+// slot pattern (slot-order bits) of a hardware m-index under a map (mmap / mmap2)
+QCB_HD uint32_t k3_pattern_index(uint32_t idx, const uint32_t (&map)[3]) {
+  return (((idx >> 0) & 1u) << map[0]) | (((idx >> 1) & 1u) << map[1]) | (((idx >> 2) & 1u) << map[2]);
+}
+// row scaling of the fragments of one lane: (P, N, R) = (Mr + Mi, -Mi, Mr) of a row multiplied by d = dr + i di
+QCB_HD void far_scale(double& P, double& N, double& R, double dr, double di) {
+  const double r2 = dr * R + di * N, n2 = dr * N - di * R;
+  R = r2; N = n2; P = r2 - n2;
 }
 // tile-local offset of the slot pattern selected by a k-index / m-index
 QCB_HD uint32_t k3_pattern_offset(const K3Ctx& c, uint32_t idx, const uint32_t (&map)[3]) {

@@ -203,6 +203,15 @@ static void emu_k3_round(double2* tile, const uint64_t* st, uint32_t r, uint64_t
           Br[lane % 4 + 4 * s][lane / 4] = a.x; Bi[lane % 4 + 4 * s][lane / 4] = a.y;
         }
       }
+      if (c.far_n[0]) {      // far phases: every row of the block scaled by the tile's phase for that output pattern
+        double fs[4];
+        far_sums(st + c.far_off[0], c.far_n[0], ext_hi, fs);
+        for (int row = 0; row < 8; ++row) {
+          const double ang = far_angle(fs, k3_pattern_index((uint32_t)row, c.mmap));
+          const double dr = std::cos(ang), di = std::sin(ang);
+          for (int col = 0; col < 8; ++col) far_scale(Pm[row][col], Nm[row][col], Rm[row][col], dr, di);
+        }
+      }
       double Re[8][8], Im[8][8];
       for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) {
         double k = 0, re = 0, im = 0;
@@ -259,8 +268,20 @@ static void emu_k3x_round(double2* tile, const uint64_t* st, uint32_t r, uint64_
       const uint32_t e = k3_batch_entry(c, bidx, m);
       const uint32_t X = e & DMMA_BATCH_OFF_MASK, var = var_hi | (e >> 20);
       double A[12][32], r0[32], i0[32], r1[32], i1[32], zero[32] = {};
+      double fs1[4] = {0, 0, 0, 0}, fs2[4] = {0, 0, 0, 0};
+      if (c.far_n[0]) far_sums(st + c.far_off[0], c.far_n[0], ext_hi, fs1);
+      if (c.far_n[1]) far_sums(st + c.far_off[1], c.far_n[1], ext_hi, fs2);
       for (uint32_t lane = 0; lane < 32; ++lane) {
         for (int i = 0; i < 12; ++i) A[i][lane] = mats[(size_t)var * K3X_FRAG_DOUBLES + i * 32 + lane];
+        // far phases: a lane's fragments all belong to the row lane / 4 of their block
+        if (c.far_n[0]) {
+          const double ang = far_angle(fs1, k3_pattern_index(lane / 4, c.mmap));
+          for (int s2 = 0; s2 < 2; ++s2) far_scale(A[0 + s2][lane], A[2 + s2][lane], A[4 + s2][lane], std::cos(ang), std::sin(ang));
+        }
+        if (c.far_n[1]) {
+          const double ang = far_angle(fs2, k3_pattern_index(lane / 4, c.mmap2));
+          for (int s2 = 0; s2 < 2; ++s2) far_scale(A[6 + s2][lane], A[8 + s2][lane], A[10 + s2][lane], std::cos(ang), std::sin(ang));
+        }
         double2 a; std::memcpy(&a, tb + (X ^ lt[lane][0]), 16); r0[lane] = a.x; i0[lane] = a.y;
         std::memcpy(&a, tb + (X ^ lt[lane][1]), 16); r1[lane] = a.x; i1[lane] = a.y;
       }

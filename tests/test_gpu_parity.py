@@ -810,6 +810,38 @@ def test_paired_rounds_on_device_match_oracle():
         assert float(np.max(np.abs(sv.get_state() - want))) <= 1e-10
 
 
+def test_far_phases_qft_on_device():
+    """QFT ladders with controls outside the tile ride as tile-constant row scalings of the A fragments (far phases): amplitudes
+    against the oracle at 14 - 22 qubits (2 - 10 far bits), with far phases off for comparison, and the plan really uses them."""
+    for n in (14, 18, 22):
+        circ = C.quantum_fourier_transform_circuit(n)
+        init = _rand_state(n, 70 + n)
+        want = O.execute_circuit(circ, init)
+        with L.StateVector(n) as sv:
+            sv.set_state(init)
+            sv.apply_circuit(circ)
+            assert float(np.max(np.abs(sv.get_state() - want))) <= TOL
+    # a mix of CRZ (both orientations), CZ and non-diagonal gates on the same qubits
+    n = 20
+    rng = np.random.default_rng(5)
+    circ = C.create_circuit(n)
+    for _ in range(300):
+        a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+        k = int(rng.integers(0, 6))
+        if k == 0: C.add_gate(circ, "h", target=a)
+        elif k == 1: C.rx(circ, a, rng.random() * 6)
+        elif k == 2: C.crz(circ, a, b, rng.random() * 6)
+        elif k == 3: C.cz(circ, a, b)
+        elif k == 4: C.cnot(circ, a, b)
+        else: C.rz(circ, a, rng.random() * 6)
+    init = _rand_state(n, 6)
+    want = O.execute_circuit(circ, init)
+    with L.StateVector(n) as sv:
+        sv.set_state(init)
+        sv.apply_circuit(circ)
+        assert float(np.max(np.abs(sv.get_state() - want))) <= TOL
+
+
 def test_swap_kernel_unit_all_partner_schedules():
     """k_swap_global (the in-place multi-qubit exchange over peer memory) for worlds of 2, 4, 8 ranks emulated as slices on
     ONE device, k = 1..3 exchanged qubits at arbitrary positions: tests/cuda/swap_kernel_test.cu (54 cases)."""
