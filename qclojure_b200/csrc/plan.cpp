@@ -1082,11 +1082,6 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
     if ((g.t & (bx | bz)) || (g.d & bx)) { block(); continue; }
     if (partner && (g.reflect || (g.bits & avoid))) { block(); continue; }
     if (g.t & closed) { block(); continue; }
-    if (use_mma && g.far_ok) {
-      // far phase: the tile-local operand becomes (or is) a slot, the far operand costs no condition bit
-      const uint64_t l = g.want, Rn = R | l;
-      if (fits(Rn) && popc(touched & ~Rn) <= MAX_COND_BITS) { R = Rn; touched |= l; closed |= l; taken.push_back((int)gi); continue; }
-    }
     // prefer making the gate *pure* (every tile-local bit it touches becomes a slot bit): pure gates fold into
     // the round's dense block for free; controls / diagonal operands on tile-id or rank bits can never be slots
     if (use_mma && !g.reflect) {
@@ -1099,6 +1094,11 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
       // along as condition bits
       if (g.can_be_pure && g.t == 0 && g.later && popc(g.want) <= rmax) { block(); continue; }
       if (fits(R | g.t) && conds_after(R | g.t) <= MAX_COND_BITS) accept(R | g.t);
+      else if (g.far_ok && fits(R | g.want) && popc((touched | g.want) & ~(R | g.want)) <= MAX_COND_BITS) {
+        // out of condition bits: a diagonal two-bit gate with one far operand can still ride as a far phase - its tile-local
+        // operand becomes (or is) a slot, the far operand costs nothing; no non-diagonal gate may follow on that slot in this round
+        R |= g.want; touched |= g.want; closed |= g.want; taken.push_back((int)gi);
+      }
       else if (taken.empty() && Rcap == ~0ULL) accept(R | g.t);     // always make progress (falls back to the interpreter if needed)
       else block();
       continue;
