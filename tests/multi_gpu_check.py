@@ -70,6 +70,24 @@ def main():
         if rank == 0:
             print(f"n={n} world={world}: max|err|={err:.2e} exchanges={stats['n_exchanges']} sweeps={stats['n_sweeps']} "
                   f"exchange_ms={stats['exchange_ms']:.3f}", flush=True)
+    # QFT across the ranks: the ladder's controls on rank bits and tile-id bits ride as far phases (no exchange, no condition bits)
+    for nl in (13, 17):
+        n = nl + p
+        circ = C.quantum_fourier_transform_circuit(n)
+        init = np.random.default_rng(n).standard_normal(1 << n) + 1j * np.random.default_rng(n + 1).standard_normal(1 << n)
+        init /= np.linalg.norm(init)
+        want = O.execute_circuit(circ, init)
+        lc = 1 << nl
+        with L.StateVector(n, device=local_rank, rank=rank, world_size=world, nccl_id=new_nccl_id()) as sv:
+            sv.set_state(init[rank * lc:(rank + 1) * lc])
+            sv.apply_circuit(circ)
+            stats = sv.stats()
+            got = sv.get_state()
+        err = float(np.max(np.abs(got - want[rank * lc:(rank + 1) * lc])))
+        worst = max(worst, err)
+        assert err <= 1e-10, f"rank {rank} QFT n={n}: amplitude mismatch {err}"
+        if rank == 0:
+            print(f"QFT n={n} world={world}: max|err|={err:.2e} exchanges={stats['n_exchanges']} sweeps={stats['n_sweeps']}", flush=True)
     t = torch.tensor([worst], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
