@@ -387,16 +387,6 @@ __device__ __forceinline__ void xsts(uint32_t addr, double x, double y) {
   if (ABL & 2) { if (addr == 0xffffffffu) sts_c128(addr, x, y); } else sts_c128(addr, x, y);     // never taken, keeps the results alive
 }
 
-// Far phases of a pass (tile_core.h "far phases"): the row factors d = dr + i di of this lane's row (lane / 4) for the first and
-// the second block, computed once per tile and pass; apply() scales a freshly loaded set of A fragments.
-struct FarD {
-  double dr1, di1, dr2, di2;
-  bool on1, on2;
-  __device__ __forceinline__ void apply(double (&A)[12]) const {
-    if (on1) { far_scale(A[0], A[2], A[4], dr1, di1); far_scale(A[1], A[3], A[5], dr1, di1); }
-    if (on2) { far_scale(A[6], A[8], A[10], dr2, di2); far_scale(A[7], A[9], A[11], dr2, di2); }
-  }
-};
 // the four sums of a far table for the tile ext_hi: lane e takes entry e (at most 32 entries), xor-shuffle reduction
 __device__ __forceinline__ void far_sums_warp(const uint64_t* __restrict__ tab, uint32_t n, uint64_t ext_hi, uint32_t lane, double (&s)[4]) {
   s[0] = s[1] = s[2] = s[3] = 0.0;
@@ -607,10 +597,10 @@ __device__ __forceinline__ void k3_batches_pp(uint32_t tile_s, const uint4 lt, c
 }
 
 // One warp's share of a three-product round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
-template <bool DIRECT, class F>
+template <bool DIRECT, class F, class FF>
 __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
                                              uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur,
-                                             K3Out out, F&& mid, const FarD& far, const TileTrace tr = TileTrace{}) {
+                                             K3Out out, F&& mid, FF&& far_fix, const TileTrace tr = TileTrace{}) {
   const uint4 lt = lane_tab_r[2u * lane];
   out.tile_s = tile_s; out.lz = lt.z; out.lw = lt.w;
   if (DIRECT) {   // lane parts of the global offsets: second table entry of the lane (written by the prologue for the last round)
@@ -644,7 +634,7 @@ __device__ __forceinline__ void k3_round_run(uint32_t tile_s, const uint4* lane_
     const uint32_t v = var_hi | (btab[b] >> 20);
     uint32_t e = b + 1u;
     while (e < per && (btab[e] >> 20) == (btab[b] >> 20)) ++e;
-    if (v != cur) { k3_load_A(A, mats, v); far.apply(A); cur = v; }
+    if (v != cur) { k3_load_A(A, mats, v); far_fix(A); cur = v; }
     K3Out o2 = out;
     o2.gtab = out.gtab + b;
 #ifndef QCB_K3_ROTATE
@@ -777,10 +767,10 @@ __device__ __forceinline__ void k3x_batches_simple(uint32_t tile_s, const uint4 
   }
 }
 // One warp's share of a paired round on the tile at shared address `tile_s`.  A holds variant `cur` on entry.
-template <class F>
+template <class F, class FF>
 __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane_tab_r, const uint32_t* btab, uint32_t per,
                                               uint32_t var_hi, const double* __restrict__ mats, uint32_t lane, double (&A)[12], uint32_t cur,
-                                              F&& mid, const FarD& far, const TileTrace tr = TileTrace{}) {
+                                              F&& mid, FF&& far_fix, const TileTrace tr = TileTrace{}) {
   const uint4 lt = lane_tab_r[2u * lane];
   if ((btab[0] >> 20) == (btab[per - 1u] >> 20)) {
     if (per >= 4u && !(per & 1u)) {
@@ -802,7 +792,7 @@ __device__ __forceinline__ void k3x_round_run(uint32_t tile_s, const uint4* lane
     const uint32_t v = var_hi | (btab[b] >> 20);
     uint32_t e = b + 1u;
     while (e < per && (btab[e] >> 20) == (btab[b] >> 20)) ++e;
-    if (v != cur) { k3x_load_A(A, mats, v); far.apply(A); cur = v; }
+    if (v != cur) { k3x_load_A(A, mats, v); far_fix(A); cur = v; }
     if (e - b >= 4u && !((e - b) & 1u)) k3x_batches_pp<0>(tile_s, lt, btab + b, e - b, A, [] {});
     else k3x_batches_simple(tile_s, lt, btab + b, e - b, A);
     b = e;
@@ -1130,30 +1120,41 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
           for (int i = 0; i < NA; ++i) Ac[i] = A[i];
           const uint32_t curc = cur, var_hic = var_hi;
           const double* mats = reinterpret_cast<const double*>(stage_g + rtab[r].y) + lane;
-          FarD far;
-          far.on1 = far.on2 = false;
-          if constexpr (FORM == 2) {
-            // far phases: diagonal gates with an operand outside the tile scale the rows of the block by a constant of the tile
-            const uint64_t* w = sprog + T_STAGE_WORDS + (uint64_t)r * T_ROUND_WORDS;
-            const uint32_t fn = (uint32_t)w[39];
-            if (fn != 0u && active) {
+          // far phases (tile_core.h): diagonal gates with an operand outside the tile scale the rows (gates after the block) or
+          // the columns (gates before it) of the block by constants of the tile - applied to a freshly loaded set of fragments
+          auto far_fix = [&](double (&X)[12]) {
+            if constexpr (FORM == 2) {
+              const uint64_t* w = sprog + T_STAGE_WORDS + (uint64_t)r * T_ROUND_WORDS;
+              const uint32_t fn = (uint32_t)w[39];
+              if (fn == 0u) return;
               const uint64_t ext_hi = sc.ext_hi_base | active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x);
-              double fs[4];
-              if (fn & 0xffffu) {
-                far_sums_warp(stage_g + w[37], fn & 0xffffu, ext_hi, lane, fs);
-                const uint32_t mm[3] = {(uint32_t)w[35] & 15u, (uint32_t)(w[35] >> 4) & 15u, (uint32_t)(w[35] >> 8) & 15u};
-                sincos(far_angle(fs, k3_pattern_index(lane >> 2, mm)), &far.di1, &far.dr1);
-                far.on1 = true;
+              const uint32_t mm1[3] = {(uint32_t)w[35] & 15u, (uint32_t)(w[35] >> 4) & 15u, (uint32_t)(w[35] >> 8) & 15u};
+              const uint32_t km1[3] = {(uint32_t)w[34] & 15u, (uint32_t)(w[34] >> 4) & 15u, (uint32_t)(w[34] >> 8) & 15u};
+              const uint32_t mm2[3] = {(uint32_t)w[36] & 15u, (uint32_t)(w[36] >> 4) & 15u, (uint32_t)(w[36] >> 8) & 15u};
+              double fs[4], dr, di;
+#pragma unroll
+              for (int blk = 0; blk < 2; ++blk) {
+                const uint32_t n_post = (fn >> (8 * blk)) & 0xffu, n_pre = (fn >> (16 + 8 * blk)) & 0xffu;
+                const uint64_t offs = w[37 + blk];
+                if (n_post) {
+                  far_sums_warp(stage_g + (uint32_t)offs, n_post, ext_hi, lane, fs);
+                  sincos(far_angle(fs, k3_pattern_index(lane >> 2, blk ? mm2 : mm1)), &di, &dr);
+                  far_scale(X[6 * blk + 0], X[6 * blk + 2], X[6 * blk + 4], dr, di);
+                  far_scale(X[6 * blk + 1], X[6 * blk + 3], X[6 * blk + 5], dr, di);
+                }
+                if (n_pre) {
+                  far_sums_warp(stage_g + (uint32_t)(offs >> 32), n_pre, ext_hi, lane, fs);
+#pragma unroll
+                  for (uint32_t s2 = 0; s2 < 2; ++s2) {
+                    const uint32_t kcol = (lane & 3u) + 4u * s2;
+                    sincos(far_angle(fs, blk ? k3x_hw_k_to_group(kcol) : k3_pattern_index(kcol, km1)), &di, &dr);
+                    far_scale(X[6 * blk + s2], X[6 * blk + 2 + s2], X[6 * blk + 4 + s2], dr, di);
+                  }
+                }
               }
-              if (fn >> 16) {
-                far_sums_warp(stage_g + w[38], fn >> 16, ext_hi, lane, fs);
-                const uint32_t mm[3] = {(uint32_t)w[36] & 15u, (uint32_t)(w[36] >> 4) & 15u, (uint32_t)(w[36] >> 8) & 15u};
-                sincos(far_angle(fs, k3_pattern_index(lane >> 2, mm)), &far.di2, &far.dr2);
-                far.on2 = true;
-              }
-              far.apply(Ac);
             }
-          }
+          };
+          if constexpr (FORM == 2) { if (active) far_fix(Ac); }
           const bool do_pf = next_mma && !(DBG_ON(16) && cur != 0xffffffffu);
 #ifdef QCB_PREFETCH_EARLY
           if (do_pf) prefetch(nj, nr);
@@ -1168,17 +1169,17 @@ k_tile_stage(double2* __restrict__ state, const uint64_t* __restrict__ stage_g, 
             if constexpr (FORM == 2) {
               if (round_kind(sprog, r) == 3u) {
                 k3x_round_run(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                              mats, lane, Ac, curc, mid, far, tr);
+                              mats, lane, Ac, curc, mid, far_fix, tr);
               } else {
               K3Out out;
               out.gtab = gtab + b0; out.gbase = nullptr; out.g0 = out.g1 = 0;
               if (direct && r + 1u == sc.n_rounds) {
                 out.gbase = state + tile_base(sprog, sc, active_to_tile(sc, (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x));
                 k3_round_run<true>(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                                   mats, lane, Ac, curc, out, mid, far);
+                                   mats, lane, Ac, curc, out, mid, far_fix);
               } else {
                 k3_round_run<false>(smem_s + b * (uint32_t)tile_bytes, lane_tab + (size_t)r * 64u, batch_tab + r * nbstride + b0, per, var_hic,
-                                    mats, lane, Ac, curc, out, mid, far, tr);
+                                    mats, lane, Ac, curc, out, mid, far_fix, tr);
               }
               }
             } else

@@ -499,9 +499,13 @@ static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& wo
     size_t rb = rbase + r * ROUND_WORDS;
     words[rb + 2] = words.size() - base;
     for (double d : rd.frag) words.push_back(dbl_bits(d));
-    if (!rd.far.empty()) { words[rb + 37] = words.size() - base; for (uint64_t w : rd.far) words.push_back(w); }
-    if (!rd.far2.empty()) { words[rb + 38] = words.size() - base; for (uint64_t w : rd.far2) words.push_back(w); }
-    words[rb + 39] = (uint64_t)(rd.far.size() / 5) | ((uint64_t)(rd.far2.size() / 5) << 16);
+    uint64_t off[4] = {0, 0, 0, 0};
+    const std::vector<uint64_t>* tabs[4] = {&rd.far, &rd.far2, &rd.farpre, &rd.farpre2};
+    for (int t = 0; t < 4; ++t) if (!tabs[t]->empty()) { off[t] = words.size() - base; for (uint64_t w : *tabs[t]) words.push_back(w); }
+    words[rb + 37] = off[0] | (off[2] << 32);              // first block: after (row) | before (column) << 32
+    words[rb + 38] = off[1] | (off[3] << 32);              // second block
+    words[rb + 39] = (uint64_t)(rd.far.size() / 5) | ((uint64_t)(rd.far2.size() / 5) << 8) | ((uint64_t)(rd.farpre.size() / 5) << 16) |
+                     ((uint64_t)(rd.farpre2.size() / 5) << 24);
   }
   words[base + 40] = words.size() - base;
 }
@@ -704,9 +708,19 @@ static void classify_far(const Config& cfg, const std::vector<Gate>& gates, uint
     const Gate& g = gates[i];
     if (far_kind(g)) {
       const uint64_t b = gate_bits(g), l = b & slot_mask, h = b & ~tile_mask;
-      if (popc(b) == 2 && popc(l) == 1 && popc(h) == 1 && !(later_targets & l)) flags[i] = 1;
+      if (popc(b) == 2 && popc(l) == 1 && popc(h) == 1 && !(later_targets & l)) flags[i] = 1;      // after the block: row scaling
     }
     later_targets |= g.target_mask();
+  }
+  // the same BEFORE the block (column scaling) when no earlier gate of the round acts non-diagonally on the slot
+  uint64_t earlier_targets = 0;
+  for (size_t i = 0; i < gates.size(); ++i) {
+    const Gate& g = gates[i];
+    if (!flags[i] && far_kind(g)) {
+      const uint64_t b = gate_bits(g), l = b & slot_mask, h = b & ~tile_mask;
+      if (popc(b) == 2 && popc(l) == 1 && popc(h) == 1 && !(earlier_targets & l)) flags[i] = 2;
+    }
+    earlier_targets |= g.target_mask();
   }
 }
 // condition bits of a round: every bit a gate touches that is not a slot, far phases excepted
@@ -719,13 +733,13 @@ static uint64_t round_cond_bits(const std::vector<Gate>& gates, const std::vecto
 // phi_0, phi_1, phi_2}.  With D0 / D1 the gate's diagonal on its slot for the far bit = 0 / 1: D0 goes into the matrices
 // (far bit forced to 0 by the caller), D1 / D0 = e^{i g} diag(e^{-i f}, e^{+i f}) into the table.
 static void build_far_table(const std::vector<Gate>& gates, const std::vector<char>& far, const std::vector<int>& slots, int m,
-                            std::vector<uint64_t>& out) {
+                            std::vector<uint64_t>& out, char which = 1) {
   out.clear();
   std::vector<int> pos;
   std::vector<double> val;                       // 4 per entry
   const uint64_t tile_mask = (1ULL << m) - 1ULL;
   for (size_t i = 0; i < gates.size(); ++i) {
-    if (!far[i]) continue;
+    if (far[i] != which) continue;
     const Gate& g = gates[i];
     const uint64_t b = gate_bits(g), hm = b & ~tile_mask;
     const int h = 63 - __builtin_clzll(hm);
@@ -933,7 +947,8 @@ static void build_k3_round(const Config& cfg, const Stage& st, Round& rd) {
       rd.frag[var * K3_FRAG_DOUBLES_HOST + (size_t)reg * 32 + lane] = v;
     }
   }
-  build_far_table(rd.gates, far, rd.slot_pos, m, rd.far);
+  build_far_table(rd.gates, far, rd.slot_pos, m, rd.far, 1);
+  build_far_table(rd.gates, far, rd.slot_pos, m, rd.farpre, 2);
   rd.dmma = true;
   rd.k3 = true;
 }
@@ -1017,8 +1032,10 @@ static void build_k3_pair_round(const Config& cfg, const Stage& st, Round& rd) {
       rd.frag[var * FD + (size_t)(6 + reg) * 32 + lane] = (reg < 2) ? (z2.re + z2.im) : (reg < 4 ? -z2.im : z2.re);
     }
   }
-  build_far_table(rd.gates, far1, rd.slot_pos, m, rd.far);
-  build_far_table(rd.gates2, far2, g2, m, rd.far2);
+  build_far_table(rd.gates, far1, rd.slot_pos, m, rd.far, 1);
+  build_far_table(rd.gates2, far2, g2, m, rd.far2, 1);
+  build_far_table(rd.gates, far1, rd.slot_pos, m, rd.farpre, 2);
+  build_far_table(rd.gates2, far2, g2, m, rd.farpre2, 2);
   rd.dmma = true;
   rd.k3 = true;
 }
@@ -1072,13 +1089,14 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
   const bool use_mma = cfg.dense_mma && st.m >= 6;
   uint64_t R = 0, touched = touched0, bx = 0, bz = 0;   // touched = bits of accepted gates; bx / bz = Blocker state
   uint64_t closed = 0;                                  // slots carrying a far phase: no non-diagonal gate may follow on them
+  uint64_t opened = 0;                                  // bits some accepted gate acts on non-diagonally
   taken.clear();
   rest.clear();
   auto fits = [&](uint64_t Rn) { return popc(Rn) <= rmax && (Rn & ~Rcap) == 0; };
   for (size_t gi = 0; gi < pg.size(); ++gi) {
     const RoundGate& g = pg[gi];
     auto block = [&]() { bx |= g.t; bz |= g.d; rest.push_back((int)gi); };
-    auto accept = [&](uint64_t Rn) { R = Rn; touched |= g.bits; taken.push_back((int)gi); };
+    auto accept = [&](uint64_t Rn) { R = Rn; touched |= g.bits; opened |= g.t; taken.push_back((int)gi); };
     if ((g.t & (bx | bz)) || (g.d & bx)) { block(); continue; }
     if (partner && (g.reflect || (g.bits & avoid))) { block(); continue; }
     if (g.t & closed) { block(); continue; }
@@ -1094,6 +1112,10 @@ static void pick_round(const Config& cfg, const Stage& st, const std::vector<Rou
       // along as condition bits
       if (g.can_be_pure && g.t == 0 && g.later && popc(g.want) <= rmax) { block(); continue; }
       if (fits(R | g.t) && conds_after(R | g.t) <= MAX_COND_BITS) accept(R | g.t);
+      else if (g.far_ok && !(opened & g.want) && fits(R | g.want) && popc((touched | g.want) & ~(R | g.want)) <= MAX_COND_BITS) {
+        // the same BEFORE the block (nothing non-diagonal has touched the slot yet in this round): the slot stays open
+        R |= g.want; touched |= g.want; taken.push_back((int)gi);
+      }
       else if (g.far_ok && fits(R | g.want) && popc((touched | g.want) & ~(R | g.want)) <= MAX_COND_BITS) {
         // out of condition bits: a diagonal two-bit gate with one far operand can still ride as a far phase - its tile-local
         // operand becomes (or is) a slot, the far operand costs nothing; no non-diagonal gate may follow on that slot in this round
@@ -1148,12 +1170,20 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
   };
   // condition bits a candidate round would have: every non-slot bit its gates touch, far phases excepted (classify_far's rule)
   auto cond_of = [&](const std::vector<RoundGate>& G, const std::vector<int>& tk, uint64_t Rs) {
-    uint64_t cond = 0, later = 0;
+    uint64_t cond = 0, later = 0, earlier = 0;
+    std::vector<char> fl(tk.size(), 0);
     for (size_t k = tk.size(); k-- > 0;) {
       const RoundGate& g = G[tk[k]];
       const uint64_t l = g.bits & Rs;
-      if (!(g.far_ok && popc(l) == 1 && !(later & l))) cond |= g.bits & ~Rs;
+      if (g.far_ok && popc(l) == 1 && !(later & l)) fl[k] = 1;
       later |= g.t;
+    }
+    for (size_t k = 0; k < tk.size(); ++k) {
+      const RoundGate& g = G[tk[k]];
+      const uint64_t l = g.bits & Rs;
+      if (!fl[k] && g.far_ok && popc(l) == 1 && !(earlier & l)) fl[k] = 2;
+      earlier |= g.t;
+      if (!fl[k]) cond |= g.bits & ~Rs;
     }
     return cond;
   };

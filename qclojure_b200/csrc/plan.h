@@ -76,8 +76,9 @@ enum DevOpKind : uint32_t { D_MAT1 = 0, D_MAT2 = 1, D_SWAPP = 2, D_DMASK = 3, D_
 //          three-product form, tile_core.h: K3Ctx, 3 = two three-product rounds on disjoint slot triples in one pass,
 //          tile_core.h "paired rounds")   [18] n_grp_bits   [19..29) grp_pos[10]
 //     [29] k (condition bits)  [30..34) cond_pos[4] (ext positions)  [34] j_load (kinds 2, 3: kmap)  [35] j_store (kinds 2, 3: mmap)
-//     [36] kind 3: mmap2   [37] / [38] word offset of the far-phase table of the first / second block (0 = none)
-//     [39] entries of the first table | entries of the second << 16
+//     [36] kind 3: mmap2   [37] / [38] far-phase tables of the first / second block: word offset of the table applied AFTER the
+//     block (row scaling) | offset of the one applied BEFORE it (column scaling) << 32, 0 = none
+//     [39] entries: after-1 | after-2 << 8 | before-1 << 16 | before-2 << 24
 //     tensor-core rounds: [2] = word offset of the A-fragment matrices (2^k * 256 / 192 / 384 doubles, after all descriptors)
 //   StageDesc [42] = number of leading words (descriptors + interpreter op slots) that the kernel copies to smem
 constexpr int STAGE_WORDS = 48;
@@ -119,7 +120,8 @@ struct Round {
   // far phases (tile_core.h "far phases"): diagonal two-bit gates with one operand on a slot and the other OUTSIDE the tile are
   // not condition bits - the product of their phases is a constant of the tile, applied by every lane to its A fragments.
   // Per entry five words: ext position of the far bit minus m, then gamma, phi_0, phi_1, phi_2 (doubles) - see build_far_table.
-  std::vector<uint64_t> far, far2;  // first / second block
+  std::vector<uint64_t> far, far2;        // after the first / second block: row scaling
+  std::vector<uint64_t> farpre, farpre2;  // before the first / second block (no earlier non-diagonal gate on the slot): column scaling
 };
 
 struct Stage {

@@ -439,7 +439,8 @@ struct K3Ctx {
   uint32_t kmap[3], mmap[3];
   uint32_t mmap2[3];                         // round kind 3 only (see "paired rounds" below)
   uint64_t mat_off;
-  uint32_t far_off[2], far_n[2];             // far-phase tables of the first / second block (word offset from the stage, entries)
+  uint32_t far_off[4], far_n[4];             // far-phase tables (word offset from the stage, entries): after block 1, after block 2,
+                                             // before block 1, before block 2
 };
 constexpr uint32_t K3_FRAG_DOUBLES = 192;   // per variant: 6 A registers x 32 lanes (P0 P1 N0 N1 R0 R1)
 constexpr uint32_t K3X_FRAG_DOUBLES = 384;  // round kind 3: the six registers of the first block, then those of the second
@@ -456,12 +457,14 @@ QCB_HD void decode_k3(const uint64_t* stage, uint32_t round_idx, K3Ctx& c) {
   }
   for (int j = 0; j < 10; ++j) c.grp_pos[j] = (uint32_t)w[19 + j];
   for (int j = 0; j < 4; ++j) c.cond_pos[j] = (uint32_t)w[30 + j];
-  c.far_off[0] = (uint32_t)w[37]; c.far_off[1] = (uint32_t)w[38];
-  c.far_n[0] = (uint32_t)w[39] & 0xffffu; c.far_n[1] = (uint32_t)(w[39] >> 16) & 0xffffu;
+  c.far_off[0] = (uint32_t)w[37]; c.far_off[1] = (uint32_t)w[38]; c.far_off[2] = (uint32_t)(w[37] >> 32); c.far_off[3] = (uint32_t)(w[38] >> 32);
+  for (int t = 0; t < 4; ++t) c.far_n[t] = (uint32_t)(w[39] >> (8 * t)) & 0xffu;
 }
 // ---- far phases (plan.cpp: classify_far / build_far_table).  A table entry is five words: position of a far bit (relative to
 // the tile bits, i.e. a bit of ext_hi), gamma, phi_0, phi_1, phi_2.  For the tile ext_hi the block's rows are scaled by
 //   d(pattern) = exp(i (G + sum_j (pattern bit j ? +F_j : -F_j))),   G / F_j = sums of gamma / phi_j over the entries whose bit is set.
+// A table applied BEFORE the block scales the COLUMNS instead (input pattern; hardware k-index through kmap, or - second block of a
+// pair - the lane-group index itself).
 // far_sums: the four sums (sequential - the kernel does the same with a warp reduction over the entries).
 QCB_HD void far_sums(const uint64_t* tab, uint32_t n, uint64_t ext_hi, double (&s)[4]) {
   s[0] = s[1] = s[2] = s[3] = 0.0;

@@ -212,6 +212,15 @@ static void emu_k3_round(double2* tile, const uint64_t* st, uint32_t r, uint64_t
           for (int col = 0; col < 8; ++col) far_scale(Pm[row][col], Nm[row][col], Rm[row][col], dr, di);
         }
       }
+      if (c.far_n[2]) {      // ... and, for phases that precede the block, every column (input pattern)
+        double fs[4];
+        far_sums(st + c.far_off[2], c.far_n[2], ext_hi, fs);
+        for (int col = 0; col < 8; ++col) {
+          const double ang = far_angle(fs, k3_pattern_index((uint32_t)col, c.kmap));
+          const double dr = std::cos(ang), di = std::sin(ang);
+          for (int row = 0; row < 8; ++row) far_scale(Pm[row][col], Nm[row][col], Rm[row][col], dr, di);
+        }
+      }
       double Re[8][8], Im[8][8];
       for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) {
         double k = 0, re = 0, im = 0;
@@ -271,6 +280,9 @@ static void emu_k3x_round(double2* tile, const uint64_t* st, uint32_t r, uint64_
       double fs1[4] = {0, 0, 0, 0}, fs2[4] = {0, 0, 0, 0};
       if (c.far_n[0]) far_sums(st + c.far_off[0], c.far_n[0], ext_hi, fs1);
       if (c.far_n[1]) far_sums(st + c.far_off[1], c.far_n[1], ext_hi, fs2);
+      double fp1[4] = {0, 0, 0, 0}, fp2[4] = {0, 0, 0, 0};
+      if (c.far_n[2]) far_sums(st + c.far_off[2], c.far_n[2], ext_hi, fp1);
+      if (c.far_n[3]) far_sums(st + c.far_off[3], c.far_n[3], ext_hi, fp2);
       for (uint32_t lane = 0; lane < 32; ++lane) {
         for (int i = 0; i < 12; ++i) A[i][lane] = mats[(size_t)var * K3X_FRAG_DOUBLES + i * 32 + lane];
         // far phases: a lane's fragments all belong to the row lane / 4 of their block
@@ -281,6 +293,18 @@ static void emu_k3x_round(double2* tile, const uint64_t* st, uint32_t r, uint64_
         if (c.far_n[1]) {
           const double ang = far_angle(fs2, k3_pattern_index(lane / 4, c.mmap2));
           for (int s2 = 0; s2 < 2; ++s2) far_scale(A[6 + s2][lane], A[8 + s2][lane], A[10 + s2][lane], std::cos(ang), std::sin(ang));
+        }
+        // phases that precede a block: column scaling, a lane's fragment register s belongs to column lane % 4 + 4 s
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const uint32_t kcol = lane % 4 + 4 * s2;
+          if (c.far_n[2]) {
+            const double ang = far_angle(fp1, k3_pattern_index(kcol, c.kmap));
+            far_scale(A[0 + s2][lane], A[2 + s2][lane], A[4 + s2][lane], std::cos(ang), std::sin(ang));
+          }
+          if (c.far_n[3]) {
+            const double ang = far_angle(fp2, k3x_hw_k_to_group(kcol));
+            far_scale(A[6 + s2][lane], A[8 + s2][lane], A[10 + s2][lane], std::cos(ang), std::sin(ang));
+          }
         }
         double2 a; std::memcpy(&a, tb + (X ^ lt[lane][0]), 16); r0[lane] = a.x; i0[lane] = a.y;
         std::memcpy(&a, tb + (X ^ lt[lane][1]), 16); r1[lane] = a.x; i1[lane] = a.y;

@@ -32,7 +32,7 @@ def _far_entries(plan):
         st = w[pos:]
         for r in range(int(st[3])):
             v = int(st[48 + 40 * r + 39])
-            total += (v & 0xffff) + (v >> 16)
+            total += sum((v >> (8 * t)) & 0xff for t in range(4))
         pos += int(st[40])
     return total
 
