@@ -42,6 +42,26 @@ def run(device: int = 0, quick: bool = False) -> dict:
         dt = timed(lambda: B.execute_circuit(sim, circ, opt, poll_s=0.0005, max_polls=100000))
         out[f"config1_{name}_1024shots_ms"] = 1e3 * dt
     sim.close()
+    # the same circuit family at scale: QFT on 30 qubits (480 gates, every rotation controlled by a later qubit), device time of
+    # set_zero + apply_ops on a resident state
+    try:
+        n30 = 30
+        enc30 = OPS.encode_ops(C.quantum_fourier_transform_circuit(n30)["operations"])
+        with L.StateVector(n30, device=device) as sv:
+            for _ in range(2):
+                sv.set_zero(); sv.apply_ops(enc30)
+            sv.synchronize()
+            sv.timer_start()
+            for _ in range(3):
+                sv.set_zero(); sv.apply_ops(enc30)
+            ms30 = sv.timer_stop() / 3
+            st30 = sv.stats()
+            a0 = sv.get_amplitudes([0, (1 << n30) - 1])
+        out["config1_qft30_device_ms"] = ms30
+        out["config1_qft30_sweeps_rounds"] = [int(st30["n_sweeps"]), int(st30["n_rounds"])]
+        out["config1_qft30_uniform_amp_err"] = float(np.max(np.abs(a0 - 2.0 ** (-n30 / 2))))
+    except Exception as ex:      # noqa: BLE001
+        out["config1_qft30_device_ms"] = f"skipped: {ex}"
     # ---- config 2: Grover 26 q, 64 iterations of oracle + diffusion
     n = 26
     ops = [{"operation-type": "global-h", "operation-params": {}}]
