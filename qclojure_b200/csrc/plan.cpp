@@ -433,6 +433,11 @@ static Gate to_ext(const Gate& g, const std::vector<int>& ext_of_phys) {
 }
 
 static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& words) {
+  {
+    size_t need = STAGE_WORDS + st.rounds.size() * ROUND_WORDS;
+    for (const Round& rd : st.rounds) need += rd.frag.size() + rd.far.size() + rd.far2.size() + rd.farpre.size() + rd.farpre2.size() + 64 * OP_WORDS;
+    if (words.capacity() < words.size() + need) words.reserve(std::max(words.capacity() * 2, words.size() + need));
+  }
   size_t base = words.size();
   words.resize(base + STAGE_WORDS, 0);
   const int m = st.m;
@@ -498,7 +503,11 @@ static void encode_stage(const Config& cfg, Stage& st, std::vector<uint64_t>& wo
     if (!rd.dmma) continue;
     size_t rb = rbase + r * ROUND_WORDS;
     words[rb + 2] = words.size() - base;
-    for (double d : rd.frag) words.push_back(dbl_bits(d));
+    {
+      const size_t at = words.size();
+      words.resize(at + rd.frag.size());
+      std::memcpy(words.data() + at, rd.frag.data(), rd.frag.size() * sizeof(double));      // a double's bits are the word
+    }
     uint64_t off[4] = {0, 0, 0, 0};
     const std::vector<uint64_t>* tabs[4] = {&rd.far, &rd.far2, &rd.farpre, &rd.farpre2};
     for (int t = 0; t < 4; ++t) if (!tabs[t]->empty()) { off[t] = words.size() - base; for (uint64_t w : *tabs[t]) words.push_back(w); }
@@ -904,6 +913,12 @@ static void build_k3_round(const Config& cfg, const Stage& st, Round& rd) {
   int best = -1, bkc = 2, bmx = 0;
   std::vector<int> lanes = {cand[0], cand[1], cand[2]};
   const int nc = (int)cand.size();
+  if (rd.layout_hint) {                                    // replayed plan: the roles were found when the trace was recorded
+    const RoundLayout& h = *rd.layout_hint;
+    lanes = {h.lanes[0], h.lanes[1], h.lanes[2]};
+    bkc = h.kmap[2]; bmx = h.mmap[0];
+    best = 2;
+  }
   for (int kc = 0; kc < 3 && best < 2; ++kc) for (int mx = 0; mx < 3 && best < 2; ++mx) {
     const int ka = (kc + 1) % 3, kb = (kc + 2) % 3;
     for (int i0 = 0; i0 < nc && best < 2; ++i0) for (int i1 = 0; i1 < nc && best < 2; ++i1) for (int i2 = i1 + 1; i2 < nc; ++i2) {
@@ -930,6 +945,8 @@ static void build_k3_round(const Config& cfg, const Stage& st, Round& rd) {
   const size_t nvar = (size_t)1 << k;
   rd.frag.assign(nvar * K3_FRAG_DOUBLES_HOST, 0.0);
   auto pattern_of = [&](int idx, const int (&map)[3]) { return (((idx >> 0) & 1) << map[0]) | (((idx >> 1) & 1) << map[1]) | (((idx >> 2) & 1) << map[2]); };
+  int rowp[8], colp[8];                                    // hardware m- / k-index -> slot pattern
+  for (int i = 0; i < 8; ++i) { rowp[i] = pattern_of(i, rd.mmap); colp[i] = pattern_of(i, rd.kmap); }
   for (size_t var = 0; var < nvar; ++var) {
     uint64_t fixed = 0;
     for (int j = 0; j < k; ++j) if ((var >> j) & 1) fixed |= 1ULL << rd.cond_pos[j];
@@ -940,11 +957,12 @@ static void build_k3_round(const Config& cfg, const Stage& st, Round& rd) {
       // a far phase enters with its far bit = 0; what the bit adds when it is set is in the far table
       small_apply_cols(g, rd.slot_pos, M, 8, far[gi] ? (fixed & ~(gate_bits(g) & not_tile)) : fixed);
     }
-    for (int reg = 0; reg < 6; ++reg) for (int lane = 0; lane < 32; ++lane) {
-      const int mi = lane / 4, ki = lane % 4 + 4 * (reg & 1);
-      const cplx z = M[pattern_of(mi, rd.mmap)][pattern_of(ki, rd.kmap)];
-      const double v = (reg < 2) ? (z.re + z.im) : (reg < 4 ? -z.im : z.re);
-      rd.frag[var * K3_FRAG_DOUBLES_HOST + (size_t)reg * 32 + lane] = v;
+    for (int reg = 0; reg < 6; ++reg) {
+      double* out = &rd.frag[var * K3_FRAG_DOUBLES_HOST + (size_t)reg * 32];
+      for (int lane = 0; lane < 32; ++lane) {
+        const cplx z = M[rowp[lane / 4]][colp[lane % 4 + 4 * (reg & 1)]];
+        out[lane] = (reg < 2) ? (z.re + z.im) : (reg < 4 ? -z.im : z.re);
+      }
     }
   }
   build_far_table(rd.gates, far, rd.slot_pos, m, rd.far, 1);
@@ -982,14 +1000,20 @@ static void build_k3_pair_round(const Config& cfg, const Stage& st, Round& rd) {
     return ca >= 0 && cb >= 0 && cd >= 0 && ca != cb && cb != cd && ca != cd;
   };
   int bkc = 2, bg0 = 0, bmx = 0, bh = 0;
-  for (int kc = 0, best = -1; kc < 3 && best < 1; ++kc) for (int g0 = 0; g0 < 3 && best < 1; ++g0) {
+  const bool hinted = rd.layout_hint != nullptr;
+  if (hinted) {
+    const RoundLayout& h = *rd.layout_hint;
+    bkc = h.kmap[2]; bmx = h.mmap[0]; bh = h.mmap2[0];
+    for (int j = 0; j < 3; ++j) if (t2[j] == h.lanes[0]) bg0 = j;
+  }
+  for (int kc = 0, best = hinted ? 1 : -1; kc < 3 && best < 1; ++kc) for (int g0 = 0; g0 < 3 && best < 1; ++g0) {
     const int sc = distinct3(rd.slot_pos[(kc + 1) % 3], rd.slot_pos[(kc + 2) % 3], t2[g0]) ? 1 : 0;
     if (sc > best) { best = sc; bkc = kc; bg0 = g0; }
   }
   // group bit order of S2: the load-quarter bit first, the other two ascending
   std::vector<int> g2 = {t2[bg0]};
   for (int j = 0; j < 3; ++j) if (j != bg0) g2.push_back(t2[j]);
-  for (int mx = 0, best = -1; mx < 3 && best < 1; ++mx) for (int h = 0; h < 3 && best < 1; ++h) {
+  for (int mx = 0, best = hinted ? 1 : -1; mx < 3 && best < 1; ++mx) for (int h = 0; h < 3 && best < 1; ++h) {
     const int sc = distinct3(rd.slot_pos[(mx + 1) % 3], rd.slot_pos[(mx + 2) % 3], g2[h]) ? 1 : 0;
     if (sc > best) { best = sc; bmx = mx; bh = h; }
   }
@@ -1011,25 +1035,50 @@ static void build_k3_pair_round(const Config& cfg, const Stage& st, Round& rd) {
   const size_t nvar = (size_t)1 << k, FD = 2 * K3_FRAG_DOUBLES_HOST;
   rd.frag.assign(nvar * FD, 0.0);
   auto pattern_of = [&](int idx, const int (&map)[3]) { return (((idx >> 0) & 1) << map[0]) | (((idx >> 1) & 1) << map[1]) | (((idx >> 2) & 1) << map[2]); };
+  // A block's matrix depends only on ITS condition bits: of the 2^k variants of the pass only those that differ in them are
+  // built, the others copy the fragments of their representative (the variant with the other block's bits cleared).
+  const uint64_t condA = round_cond_bits(rd.gates, far1, s1), condB = round_cond_bits(rd.gates2, far2, s2);
+  size_t selA = 0, selB = 0;                               // variant-index bits that matter to the first / second block
+  for (int j = 0; j < k; ++j) {
+    if ((condA >> rd.cond_pos[j]) & 1) selA |= (size_t)1 << j;
+    if ((condB >> rd.cond_pos[j]) & 1) selB |= (size_t)1 << j;
+  }
+  int row1[8], row2[8], col1[8], col2[8];                  // hardware m- / k-index -> pattern of the block
+  for (int i = 0; i < 8; ++i) { row1[i] = pattern_of(i, rd.mmap); row2[i] = pattern_of(i, rd.mmap2); col1[i] = pattern_of(i, rd.kmap); col2[i] = 2 * (i & 3) + (i >> 2); }
+  auto fill = [&](size_t var, int base_reg, const cplx (*M)[8], const int* rowp, const int* colp) {
+    for (int reg = 0; reg < 6; ++reg) {
+      double* out = &rd.frag[var * FD + (size_t)(base_reg + reg) * 32];
+      for (int lane = 0; lane < 32; ++lane) {
+        const cplx z = M[rowp[lane / 4]][colp[lane % 4 + 4 * (reg & 1)]];
+        out[lane] = (reg < 2) ? (z.re + z.im) : (reg < 4 ? -z.im : z.re);
+      }
+    }
+  };
   for (size_t var = 0; var < nvar; ++var) {
     uint64_t fixed = 0;
     for (int j = 0; j < k; ++j) if ((var >> j) & 1) fixed |= 1ULL << rd.cond_pos[j];
-    cplx M1[8][8], M2[8][8];
-    for (int row = 0; row < 8; ++row) for (int col = 0; col < 8; ++col) M1[row][col] = M2[row][col] = cplx{row == col ? 1.0 : 0.0, 0.0};
-    for (size_t gi = 0; gi < rd.gates.size(); ++gi) {
-      const Gate& g = rd.gates[gi];
-      small_apply_cols(g, rd.slot_pos, M1, 8, far1[gi] ? (fixed & ~(gate_bits(g) & not_tile)) : fixed);
+    const size_t repA = var & selA, repB = var & selB;
+    if (repA == var) {
+      cplx M1[8][8];
+      for (int row = 0; row < 8; ++row) for (int col = 0; col < 8; ++col) M1[row][col] = cplx{row == col ? 1.0 : 0.0, 0.0};
+      for (size_t gi = 0; gi < rd.gates.size(); ++gi) {
+        const Gate& g = rd.gates[gi];
+        small_apply_cols(g, rd.slot_pos, M1, 8, far1[gi] ? (fixed & ~(gate_bits(g) & not_tile)) : fixed);
+      }
+      fill(var, 0, M1, row1, col1);
+    } else {
+      std::memcpy(&rd.frag[var * FD], &rd.frag[repA * FD], 6 * 32 * sizeof(double));
     }
-    for (size_t gi = 0; gi < rd.gates2.size(); ++gi) {
-      const Gate& g = rd.gates2[gi];
-      small_apply_cols(g, g2, M2, 8, far2[gi] ? (fixed & ~(gate_bits(g) & not_tile)) : fixed);
-    }
-    for (int reg = 0; reg < 6; ++reg) for (int lane = 0; lane < 32; ++lane) {
-      const int mi = lane / 4, ki = lane % 4 + 4 * (reg & 1);
-      const cplx z1 = M1[pattern_of(mi, rd.mmap)][pattern_of(ki, rd.kmap)];
-      const cplx z2 = M2[pattern_of(mi, rd.mmap2)][2 * (ki & 3) + (ki >> 2)];     // tile_core.h: k3x_hw_k_to_group
-      rd.frag[var * FD + (size_t)reg * 32 + lane] = (reg < 2) ? (z1.re + z1.im) : (reg < 4 ? -z1.im : z1.re);
-      rd.frag[var * FD + (size_t)(6 + reg) * 32 + lane] = (reg < 2) ? (z2.re + z2.im) : (reg < 4 ? -z2.im : z2.re);
+    if (repB == var) {
+      cplx M2[8][8];
+      for (int row = 0; row < 8; ++row) for (int col = 0; col < 8; ++col) M2[row][col] = cplx{row == col ? 1.0 : 0.0, 0.0};
+      for (size_t gi = 0; gi < rd.gates2.size(); ++gi) {
+        const Gate& g = rd.gates2[gi];
+        small_apply_cols(g, g2, M2, 8, far2[gi] ? (fixed & ~(gate_bits(g) & not_tile)) : fixed);
+      }
+      fill(var, 6, M2, row2, col2);
+    } else {
+      std::memcpy(&rd.frag[var * FD + 6 * 32], &rd.frag[repB * FD + 6 * 32], 6 * 32 * sizeof(double));
     }
   }
   build_far_table(rd.gates, far1, rd.slot_pos, m, rd.far, 1);
@@ -1304,8 +1353,10 @@ static void form_rounds(const Config& cfg, Stage& st, std::vector<Gate>& gates, 
 
 // Rounds of one stage rebuilt from a recorded trace: same gates per round, same slot bits, fresh matrices.
 static void replay_rounds(const Config& cfg, Stage& st, const std::vector<Gate>& gates, const StageTrace& tr) {
-  for (size_t r = 0; r < tr.round_uids.size(); ++r) {
+  size_t pass = 0;
+  for (size_t r = 0; r < tr.round_uids.size(); ++r, ++pass) {
     Round rd;
+    if (pass < tr.layouts.size() && tr.layouts[pass].lanes[0] >= 0) rd.layout_hint = &tr.layouts[pass];
     rd.uids = tr.round_uids[r];
     rd.slot_mask = tr.round_slots[r];
     for (int u : rd.uids) {
@@ -1324,6 +1375,7 @@ static void replay_rounds(const Config& cfg, Stage& st, const std::vector<Gate>&
       }
     }
     materialize_round(cfg, st, rd);
+    rd.layout_hint = nullptr;
     st.rounds.push_back(std::move(rd));
   }
 }
@@ -1381,6 +1433,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
   // the program is encoded stage by stage as the plan grows (header word [1] = number of stages, patched at the end)
   plan.words.clear();
   plan.stage_offsets.clear();
+  if (replay && replay->words_hint) plan.words.reserve(replay->words_hint + 1024);
   plan.words.push_back(0x51434232ULL);                 // magic "QCB2"
   plan.words.push_back(0);
   plan.words.push_back((uint64_t)n);
@@ -1579,6 +1632,10 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
         const Round& rd = st.rounds[r];
         tr.round_uids.push_back(rd.uids); tr.round_slots.push_back(rd.slot_mask); tr.round_pair.push_back(rd.pair ? 1 : 0);
         if (rd.pair) { tr.round_uids.push_back(rd.uids2); tr.round_slots.push_back(rd.slot_mask2); tr.round_pair.push_back(0); }
+        RoundLayout lay;
+        for (int j = 0; j < 3; ++j) { lay.kmap[j] = rd.kmap[j]; lay.mmap[j] = rd.mmap[j]; lay.mmap2[j] = rd.mmap2[j]; lay.lanes[j] = -1; }
+        if (rd.k3 && rd.grp_pos.size() >= 3) for (int j = 0; j < 3; ++j) lay.lanes[j] = rd.grp_pos[j];
+        tr.layouts.push_back(lay);
       }
       record->stages.push_back(std::move(tr));
     }
@@ -1771,6 +1828,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
   plan.perm_out = perm;
   emit_new_stages();
   if (sink_rc != QCB_OK) { plan.error = "stage sink failed"; return sink_rc; }
+  if (record) record->words_hint = plan.words.size();
   return QCB_OK;
 }
 
@@ -1838,6 +1896,22 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
   if (record) {
     *record = std::move(best_trace);
     plan_structure_key(base, plan.gates, perm_in, record->key);
+    record->words_hint = plan.words.size();
+    // the candidates were scored without matrices, so their traces carry no lane roles: take them from the plan just built
+    size_t si = 0;
+    for (StageTrace& tr : record->stages) {
+      if (tr.kind != S_TILE) { if (tr.kind == S_EXCHANGE || tr.kind == S_SUM || tr.kind == S_GROVER) ++si; continue; }
+      if (si >= plan.stages.size()) break;
+      const Stage& st = plan.stages[si++];
+      tr.layouts.clear();
+      for (size_t r = tr.lead ? 1 : 0; r < st.rounds.size(); ++r) {
+        const Round& rd = st.rounds[r];
+        RoundLayout lay;
+        for (int j = 0; j < 3; ++j) { lay.kmap[j] = rd.kmap[j]; lay.mmap[j] = rd.mmap[j]; lay.mmap2[j] = rd.mmap2[j]; lay.lanes[j] = -1; }
+        if (rd.k3 && rd.grp_pos.size() >= 3) for (int j = 0; j < 3; ++j) lay.lanes[j] = rd.grp_pos[j];
+        tr.layouts.push_back(lay);
+      }
+    }
   }
   return rc;
 }

@@ -94,7 +94,12 @@ constexpr int MAX_GROVER_MARKED = 8;
 
 constexpr int MAX_COND_BITS = 4;          // outside-condition bits of a tensor-core round (2^k matrix variants)
 
+// roles the lane-assignment search of a tensor-core round chose (plan.cpp: build_k3_round / build_k3_pair_round); a plan trace
+// keeps them so that a replay skips the search
+struct RoundLayout { int kmap[3], mmap[3], mmap2[3], lanes[3]; };
+
 struct Round {
+  const RoundLayout* layout_hint = nullptr;   // replay: take the roles from here instead of searching
   std::vector<int> slot_pos;        // tile-local positions held in registers
   std::vector<Gate> gates;          // gates with bits already translated to ext space (see Stage)
   // tensor-core ("dmma") round: the whole round is one of 2^k dense 16x16 real matrices, selected per group
@@ -196,10 +201,12 @@ struct StageTrace {
   std::vector<std::vector<int>> round_uids;  // per formed round
   std::vector<uint64_t> round_slots;
   std::vector<uint8_t> round_pair;           // per formed round: 1 = this round and the next one share a pass (round kind 3)
+  std::vector<RoundLayout> layouts;          // per PASS of three-product rounds: the lane roles (empty entries for other kinds)
   int gbit = -1, lbit = -1;                  // S_EXCHANGE
   bool needs_sum = false;                    // S_GROVER (taken = the diffusion and the oracles it absorbs)
 };
 struct PlanTrace {
+  size_t words_hint = 0;                     // size of the encoded program (reserve on replay)
   std::vector<uint64_t> key;
   std::vector<StageTrace> stages;
 };
