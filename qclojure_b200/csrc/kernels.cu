@@ -1934,20 +1934,32 @@ k_chunk_sums(const double2* __restrict__ state, uint64_t count, double* __restri
   }
 }
 
-// in-place inclusive scan of `n` doubles by one block (sequential over tiles of RED_THREADS with carry)
+// in-place inclusive scan of `n` doubles by one block: tiles of RED_THREADS x SCAN_ITEMS elements, each thread scans its
+// SCAN_ITEMS consecutive elements in registers, the thread totals are combined with warp shuffles, a carry links the tiles
+// (2^30 amplitudes = 262 144 chunk sums = 64 tiles; one element per thread and tile made this 1024 serial steps)
+constexpr int SCAN_ITEMS = 16;
 __global__ void __launch_bounds__(RED_THREADS)
 k_scan_inclusive(double* __restrict__ v, uint64_t n) {
   __shared__ double sm[64];
-  __shared__ double carry_s;
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0.0;
-  __syncthreads();
-  for (uint64_t base = 0; base < n; base += RED_THREADS) {
-    const uint64_t i = base + tid;
-    double x = (i < n) ? v[i] : 0.0;
+  double carry = 0.0;                                        // inclusive prefix of everything before this tile (same in every thread)
+  for (uint64_t base = 0; base < n; base += (uint64_t)RED_THREADS * SCAN_ITEMS) {
+    const uint64_t i0 = base + (uint64_t)tid * SCAN_ITEMS;
+    double x[SCAN_ITEMS];
+    if (i0 + SCAN_ITEMS <= n) {
+      const double2* src = reinterpret_cast<const double2*>(v + i0);   // v is 256-byte aligned, i0 a multiple of 16
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
-    if (lane == 31) sm[wid] = x;
+      for (int k = 0; k < SCAN_ITEMS / 2; ++k) { const double2 t = src[k]; x[2 * k] = t.x; x[2 * k + 1] = t.y; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k) x[k] = (i0 + k < n) ? v[i0 + k] : 0.0;
+    }
+#pragma unroll
+    for (int k = 1; k < SCAN_ITEMS; ++k) x[k] += x[k - 1];
+    double incl = x[SCAN_ITEMS - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) sm[wid] = incl;
     __syncthreads();
     if (wid == 0) {
       double w = (lane < RED_THREADS / 32) ? sm[lane] : 0.0;
@@ -1956,12 +1968,17 @@ k_scan_inclusive(double* __restrict__ v, uint64_t n) {
       sm[32 + lane] = w;
     }
     __syncthreads();
-    const double carry = carry_s;
-    const double incl = carry + ((wid == 0) ? 0.0 : sm[32 + wid - 1]) + x;
-    if (i < n) v[i] = incl;
-    __syncthreads();
-    if (tid == RED_THREADS - 1) carry_s = incl;
-    __syncthreads();
+    const double excl = carry + ((wid == 0) ? 0.0 : sm[32 + wid - 1]) + (incl - x[SCAN_ITEMS - 1]);
+    carry += sm[32 + RED_THREADS / 32 - 1];
+    if (i0 + SCAN_ITEMS <= n) {
+      double2* dst = reinterpret_cast<double2*>(v + i0);
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS / 2; ++k) dst[k] = double2{excl + x[2 * k], excl + x[2 * k + 1]};
+    } else {
+#pragma unroll
+      for (int k = 0; k < SCAN_ITEMS; ++k) if (i0 + k < n) v[i0 + k] = excl + x[k];
+    }
+    __syncthreads();                                         // sm[] is rewritten by the next tile
   }
 }
 
