@@ -342,7 +342,7 @@ def test_probabilities_norm_amplitudes():
         assert np.max(np.abs(sv.get_state() - init)) <= TOL
 
 
-@pytest.mark.parametrize("n", [1, 3, 11, 13, 18])
+@pytest.mark.parametrize("n", [1, 3, 11, 13, 18, 25])      # 25: 8192 chunk sums = two tiles of the chunk-sum scan (carry)
 def test_sampling_rule(n):
     init = _rand_state(n, 30 + n)
     u = np.concatenate([[0.0, 0.999999999999], np.random.default_rng(n).random(2000)])
