@@ -386,6 +386,7 @@ def plan_summary(n_qubits: int, ops, **cfgkw) -> dict:
     lib.qcb_plan_destroy(p)
     # passes over the shared tile (csrc/plan.h: program layout): a paired pass (round kind 3) carries two dense rounds
     sweeps = passes = pairs = 0
+    per_sweep = []                                       # (passes, paired passes) of every tile sweep
     pos = 4
     for _ in range(int(words[1])):
         kind = int(words[pos]); pos += 2
@@ -395,7 +396,9 @@ def plan_summary(n_qubits: int, ops, **cfgkw) -> dict:
             continue
         nr = int(words[pos + 3])
         sweeps += 1; passes += nr
-        pairs += sum(1 for r in range(nr) if int(words[pos + 48 + 40 * r + 17]) == 3)
+        np_ = sum(1 for r in range(nr) if int(words[pos + 48 + 40 * r + 17]) == 3)
+        pairs += np_
+        per_sweep.append((nr, np_))
         pos += int(words[pos + 40])
     return {"stages": int(a.value), "rounds": int(b.value), "exchanges": int(c.value), "program_words": int(nw.value),
-            "tile_sweeps": sweeps, "passes": passes, "paired_passes": pairs}
+            "tile_sweeps": sweeps, "passes": passes, "paired_passes": pairs, "per_sweep": per_sweep}

@@ -1846,6 +1846,9 @@ static double plan_cost_ms(const Plan& plan) {
     if (st.kind == S_GROVER) { c += 5.3; continue; }
     double t = 1.52;
     for (const Round& rd : st.rounds) t += rd.pair ? 3.39 : 2.0;
+    // a sweep cannot beat its HBM traffic: 32 B per amplitude at the 0.9 of the copy peak that two-round sweeps reach
+    // (bench.py: roofline.hbm_bound_config, 37 sweeps in 216.6 ms) - thin tail sweeps are not as cheap as their rounds
+    t = std::max(t, 5.8);
     c += t * st.sweep_fraction;
   }
   return c;

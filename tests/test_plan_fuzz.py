@@ -181,7 +181,7 @@ def test_trace_replay_equals_fresh_schedule_on_random_circuits(block):
 def test_empty_and_single_gate_programs():
     from qclojure_b200 import _lib as L
     assert L.plan_summary(5, []) == {"stages": 0, "rounds": 0, "exchanges": 0, "program_words": 4, "tile_sweeps": 0, "passes": 0,
-                                     "paired_passes": 0}
+                                     "paired_passes": 0, "per_sweep": []}
     st = E.run_world(5, [])
     assert st[0] == 1.0 and np.count_nonzero(st) == 1
     for n in (1, 2, 13):
