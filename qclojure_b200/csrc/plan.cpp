@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <system_error>
 #include <thread>
 
 namespace qcb {
@@ -1887,15 +1888,19 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
   double costs[NKMAX];
   int rcs[NKMAX];
   {
+    auto work = [&](int i) {
+      Plan t;
+      t.cfg = with(kn[i]);
+      t.gates = plan.gates;
+      rcs[i] = schedule_impl(t, perm_in, nullptr, &traces[i], nullptr, true);
+      costs[i] = rcs[i] == QCB_OK ? plan_cost_ms(t) : 0.0;
+    };
     std::vector<std::thread> th;
-    for (int i = 0; i < NK; ++i)
-      th.emplace_back([&, i] {
-        Plan t;
-        t.cfg = with(kn[i]);
-        t.gates = plan.gates;
-        rcs[i] = schedule_impl(t, perm_in, nullptr, &traces[i], nullptr, true);
-        costs[i] = rcs[i] == QCB_OK ? plan_cost_ms(t) : 0.0;
-      });
+    th.reserve(NK);
+    for (int i = 0; i < NK; ++i) {
+      try { th.emplace_back(work, i); }
+      catch (const std::system_error&) { work(i); }        // no thread to be had (pid limit of a container): score it here
+    }
     for (auto& t : th) t.join();
   }
   int best = -1;
