@@ -1382,13 +1382,15 @@ static void replay_rounds(const Config& cfg, Stage& st, const std::vector<Gate>&
   }
 }
 
-void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const std::vector<int>& perm_in, std::vector<uint64_t>& key) {
+void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const std::vector<int>& perm_in, std::vector<uint64_t>& key,
+                        uint64_t support_in) {
   key.clear();
   key.reserve(16 + perm_in.size() + 6 * gates.size());
   const int c[] = {cfg.n_total, cfg.n_local, cfg.rank, cfg.world, cfg.tile_bits, cfg.low_bits, cfg.fusion, cfg.max_stage_cost,
                    cfg.max_stage_rounds, cfg.dense_mma + 16 * cfg.mma_form + 32 * cfg.direct_store, cfg.round_yield_pct, cfg.window_search, cfg.tma, cfg.thin_defer,
                    cfg.pair_rounds + 2 * cfg.pair_eff_pct + 2048 * cfg.pair_cost_q + 65536 * cfg.pair_search + 1048576 * cfg.plan_portfolio + 2097152 * cfg.far_phase};
   for (int v : c) key.push_back((uint64_t)(int64_t)v);
+  key.push_back(support_in);
   key.push_back(perm_in.size());
   for (int v : perm_in) key.push_back((uint64_t)v);
   key.push_back(gates.size());
@@ -1420,6 +1422,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
   const double sweep_bytes = 32.0 * std::ldexp(1.0, nl);
   const uint64_t local_mask = (nl >= 64) ? ~0ULL : ((1ULL << nl) - 1);
   const uint64_t tileid_mask = ((nl - m) >= 64) ? ~0ULL : ((1ULL << (nl - m)) - 1);
+  uint64_t support = plan.support_in;                    // logical bits that can be 1 where the state is non-zero (plan.h)
 
   // logical bit space -> physical bit space under the current permutation
   auto to_phys = [&](const Gate& g) {
@@ -1599,6 +1602,26 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
       st.skip_mask = cm >> m; st.skip_val = cv >> m;
       st.sweep_fraction = std::ldexp(1.0, -popc(st.skip_mask & tileid_mask));
     }
+    if (support != ~0ULL && !lead) {
+      // known support: an amplitude is zero unless every bit outside the support is 0, so only the tiles whose id has 0 in
+      // those bits hold anything (a bit an existing condition already fixes keeps that condition)
+      uint64_t zext = 0;
+      for (int lb = 0; lb < n; ++lb) {
+        if ((support >> lb) & 1) continue;
+        const int pb = perm[lb];
+        if (pb < nl && ((A >> pb) & 1)) continue;            // a tile bit
+        zext |= 1ULL << ext_of_phys[pb];
+      }
+      zext &= ~(st.skip_mask << m);
+      st.skip_mask |= zext >> m;
+      st.sweep_fraction = std::ldexp(1.0, -popc(st.skip_mask & tileid_mask));
+    }
+  };
+  // the support after a tile stage: its gates' non-diagonal targets join (the affine pass of a diffusion fills everything)
+  auto grow_support = [&](bool lead, const std::vector<int>& uids) {
+    if (support == ~0ULL) return;
+    if (lead) { support = ~0ULL; return; }
+    for (int u : uids) if (u >= 0) support |= plan.gates[u].target_mask();
   };
 
   auto build_tile_stage = [&](const Gate* lead) -> size_t {
@@ -1643,6 +1666,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
     }
     plan.stages.push_back(st);
     plan.algorithmic_bytes += sweep_bytes * st.sweep_fraction;
+    grow_support(lead != nullptr, abs_uids);
     std::vector<int> rest;
     for (size_t i = 0; i < pending.size(); ++i) if (!absorbed[pending[i]]) rest.push_back(pending[i]);
     pending.swap(rest);
@@ -1663,7 +1687,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
     }
     return s;
   };
-  if (record) { record->stages.clear(); plan_structure_key(cfg, plan.gates, perm_in, record->key); }
+  if (record) { record->stages.clear(); plan_structure_key(cfg, plan.gates, perm_in, record->key, plan.support_in); }
   if (replay) {
     // ---- the decisions come from a trace of a structurally identical circuit: no searching
     Gate lead_gate;
@@ -1677,6 +1701,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
       } else if (tr.kind == S_GROVER) {
         plan.stages.push_back(make_grover_stage(tr.taken, tr.needs_sum));
         plan.algorithmic_bytes += sweep_bytes;
+        support = ~0ULL;
       } else if (tr.kind == S_EXCHANGE) {
         std::vector<int> logical_of(n);
         for (int b = 0; b < n; ++b) logical_of[perm[b]] = b;
@@ -1694,6 +1719,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
         for (int u : tr.taken) if (absorbed[u]) st.src_gates.push_back(u);
         plan.stages.push_back(st);
         plan.algorithmic_bytes += sweep_bytes * st.sweep_fraction;
+        grow_support(lead != nullptr, abs_uids);
       }
     }
     pending.clear();
@@ -1719,6 +1745,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
         std::vector<int> uids(pending.begin(), pending.begin() + k);
         plan.stages.push_back(make_grover_stage(uids, next_reflect));
         plan.algorithmic_bytes += sweep_bytes;
+        support = ~0ULL;
         if (record) { StageTrace tr; tr.kind = S_GROVER; tr.taken = uids; tr.needs_sum = next_reflect; record->stages.push_back(tr); }
         pending.erase(pending.begin(), pending.begin() + k);
         continue;
@@ -1758,6 +1785,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
       double saved_bytes = plan.algorithmic_bytes;
       const size_t saved_traces = record ? record->stages.size() : 0;
       if (may_defer) saved_pending = pending;
+      const uint64_t saved_support = support;
       const size_t got = build_tile_stage(nullptr);
       if (got && may_defer && (int)got < cfg.thin_defer && got < pending.size() + got) {
         // is anything blocked on a global bit?
@@ -1767,6 +1795,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
         if (blocked) {
           plan.stages.pop_back();
           plan.algorithmic_bytes = saved_bytes;
+          support = saved_support;
           if (record) record->stages.resize(saved_traces);
           pending.swap(saved_pending);
         } else continue;
@@ -1828,6 +1857,7 @@ static int schedule_impl(Plan& plan, const std::vector<int>& perm_in, StageSink*
   }
 
   plan.perm_out = perm;
+  plan.support_out = support;
   emit_new_stages();
   if (sink_rc != QCB_OK) { plan.error = "stage sink failed"; return sink_rc; }
   if (record) record->words_hint = plan.words.size();
@@ -1892,6 +1922,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
       Plan t;
       t.cfg = with(kn[i]);
       t.gates = plan.gates;
+      t.support_in = plan.support_in;
       rcs[i] = schedule_impl(t, perm_in, nullptr, &traces[i], nullptr, true);
       costs[i] = rcs[i] == QCB_OK ? plan_cost_ms(t) : 0.0;
     };
@@ -1927,7 +1958,7 @@ int schedule(Plan& plan, const std::vector<int>& perm_in, StageSink* sink, PlanT
   plan.cfg = base;
   if (record) {
     *record = std::move(best_trace);
-    plan_structure_key(base, plan.gates, perm_in, record->key);
+    plan_structure_key(base, plan.gates, perm_in, record->key, plan.support_in);
     record->words_hint = plan.words.size();
     // the candidates were scored without matrices, so their traces carry no lane roles: take them from the plan just built
     size_t si = 0;

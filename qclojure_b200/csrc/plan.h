@@ -186,6 +186,11 @@ struct Plan {
   uint64_t n_rounds = 0, n_exchanges = 0;
   double algorithmic_bytes = 0, unfused_bytes = 0;
   std::string error;
+  // Support of the state: LOGICAL bits that can be 1 in the index of a non-zero amplitude (~0 = nothing known).  A state
+  // straight after qcb_set_zero has support 0; every non-diagonal target of an executed gate joins it.  A tile sweep over a state
+  // with known support visits only the tiles whose id bits outside the support are 0 (Stage::skip_mask).  EXPERIMENTAL: the
+  // handle passes anything but ~0 only with QCB_ZERO_SKIP=1 (sim.cu); verified on the host emulator, not yet on hardware.
+  uint64_t support_in = ~0ULL, support_out = ~0ULL;
 };
 
 // ---- plan traces: the scheduler's decisions for one circuit STRUCTURE (which gates share a sweep / a round, tile and slot
@@ -212,7 +217,8 @@ struct PlanTrace {
 };
 // Everything the scheduler's decisions depend on: configuration, incoming bit permutation, and per gate its kind, bits,
 // cost class and sign-flip flag (never the angles themselves).
-void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const std::vector<int>& perm_in, std::vector<uint64_t>& key);
+void plan_structure_key(const Config& cfg, const std::vector<Gate>& gates, const std::vector<int>& perm_in, std::vector<uint64_t>& key,
+                        uint64_t support_in = ~0ULL);
 
 // qcb_op[] -> Gate[] ; returns QCB_OK or an error code with `err` set.
 int lower_ops(const Config& cfg, const qcb_op* ops, uint64_t n_ops, std::vector<Gate>& out, std::string& err);

@@ -123,6 +123,9 @@ struct GroupShared {
 
 // ------------------------------------------------------------------ the handle
 struct qcb_sim {
+  // logical bits that can be 1 where the state is non-zero (plan.h: Plan::support_in); ~0 = nothing known.  0 only straight after
+  // qcb_set_zero with QCB_ZERO_SKIP=1 on a single-GPU handle; every API entry except qcb_apply_ops forgets it (ENTER).
+  uint64_t support = ~0ULL;
   // group handle (n_gpus > 1): no device state of its own, every entry point fans out to `members`
   bool is_group = false;
   std::vector<qcb_sim*> members;
@@ -585,6 +588,8 @@ int run_gates(qcb_sim* h, std::vector<Gate>&& gates) {
   Plan plan;
   plan.cfg = h->cfg;
   plan.gates = std::move(gates);
+  plan.support_in = (h->cfg.world == 1) ? h->support : ~0ULL;
+  h->support = ~0ULL;                                   // until the plan has run to its end
   // program size bound: a tensor-core round holds at most 2^MAX_COND_BITS matrices of 256 doubles, and there are at most
   // as many rounds as gates; typical programs are ~80 words per gate
   RET(ensure_prog(h, std::max<size_t>(1 << 17, plan.gates.size() * 512)));
@@ -597,7 +602,7 @@ int run_gates(qcb_sim* h, std::vector<Gate>&& gates) {
   uint64_t hash = 1469598103934665603ULL;
   if (cacheable) {
     rec = std::make_shared<PlanTrace>();
-    plan_structure_key(plan.cfg, plan.gates, h->perm, rec->key);
+    plan_structure_key(plan.cfg, plan.gates, h->perm, rec->key, plan.support_in);
     for (uint64_t w : rec->key) { hash ^= w; hash *= 1099511628211ULL; hash ^= hash >> 29; }
     auto it = h->traces.find(hash);
     if (it != h->traces.end())
@@ -625,6 +630,7 @@ int run_gates(qcb_sim* h, std::vector<Gate>&& gates) {
   h->stats.algorithmic_bytes += plan.algorithmic_bytes;
   h->stats.unfused_bytes += plan.unfused_bytes;
   h->perm = plan.perm_out;
+  if (h->cfg.world == 1) h->support = plan.support_out;
   return QCB_OK;
 }
 
@@ -1335,10 +1341,14 @@ int32_t qcb_destroy(qcb_handle h) {
 // arguments, outputs taken from member 0 where the SPMD path already returns the same result on every rank).
 #define GROUP_ALL(h, call_on_m)                                                              \
   if ((h) && (h)->is_group) { std::lock_guard<std::recursive_mutex> _glk((h)->mu); return group_run((h), [&](qcb_sim* m, int r) -> int { (void)r; return (call_on_m); }); }
-#define ENTER(h)                                               \
+#define ENTER_KEEP(h)                                          \
   if (!(h)) return QCB_ERR_INVALID;                            \
   std::lock_guard<std::recursive_mutex> _lk((h)->mu);          \
   CU(h, cudaSetDevice((h)->device));
+// every entry point but qcb_apply_ops forgets what is known about the support of the state (qcb_sim::support)
+#define ENTER(h)                                               \
+  ENTER_KEEP(h)                                                \
+  (h)->support = ~0ULL;
 
 int32_t qcb_synchronize(qcb_handle h) {
   GROUP_ALL(h, qcb_synchronize(m));
@@ -1353,6 +1363,10 @@ int32_t qcb_set_zero(qcb_handle h) {
   CU(h, cudaMemsetAsync(h->state, 0, h->local_count * sizeof(double2), h->stream));
   if (h->cfg.rank == 0) CU(h, launch_set_amp(h->state, 0, 1.0, 0.0, h->stream));
   for (size_t b = 0; b < h->perm.size(); ++b) h->perm[b] = (int)b;
+  // EXPERIMENTAL (off by default, verified on the host emulator only): the sweeps that follow visit only the tiles that can hold
+  // non-zero amplitudes (plan.h: Plan::support_in)
+  static const bool zero_skip = std::getenv("QCB_ZERO_SKIP") && std::atoi(std::getenv("QCB_ZERO_SKIP")) != 0;
+  if (zero_skip && h->cfg.world == 1 && !h->is_group) h->support = 0;
   return QCB_OK;
 }
 
@@ -1456,7 +1470,7 @@ int32_t qcb_state_dev_ptr(qcb_handle h, void** dev_ptr, uint64_t* local_count) {
 
 int32_t qcb_apply_ops(qcb_handle h, const qcb_op* ops, uint64_t n_ops) {
   GROUP_ALL(h, qcb_apply_ops(m, ops, n_ops));
-  ENTER(h);
+  ENTER_KEEP(h);                                        // the one entry point that may use a known support (after qcb_set_zero)
   if (!ops && n_ops) return fail(h, QCB_ERR_INVALID, "null ops");
   RET(begin_timing(h));
   h->stats.n_ops = n_ops;

@@ -24,9 +24,14 @@ struct Emu {
 
 extern "C" {
 
+static uint64_t g_next_support = ~0ULL;
+// support of the input state for the plans created from now on (plan.h: Plan::support_in; ~0 = unknown, 0 = |0...0>)
+void emu_set_support(uint64_t s) { g_next_support = s; }
+
 int emu_create(const qcb_config* cfg, const qcb_op* ops, uint64_t n_ops, const int32_t* perm_in, Emu** out) {
   Emu* e = new Emu();
   e->plan.cfg = config_from(*cfg);
+  e->plan.support_in = g_next_support;
   int rc = lower_ops(e->plan.cfg, ops, n_ops, e->plan.gates, e->err);
   if (rc == QCB_OK) {
     std::vector<int> perm;

@@ -43,6 +43,8 @@ def lib():
         L = C.CDLL(LIB)
         L.emu_create.restype = C.c_int
         L.emu_create.argtypes = [C.POINTER(OPS.QcbConfig), C.POINTER(OPS.QcbOp), C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
+        L.emu_set_support.argtypes = [C.c_uint64]
+        L.emu_set_support.restype = None
         L.emu_error.restype = C.c_char_p
         L.emu_error.argtypes = [C.c_void_p]
         L.emu_destroy.argtypes = [C.c_void_p]
@@ -87,8 +89,10 @@ class EmuError(RuntimeError):
 class EmuPlan:
     """The plan of ONE rank."""
 
-    def __init__(self, n, ops, *, rank=0, world=1, perm_in=None, **cfgkw):
+    def __init__(self, n, ops, *, rank=0, world=1, perm_in=None, support=None, **cfgkw):
+        """support: what is known about the input state (plan.h: Plan::support_in) - None = nothing, 0 = it is |0...0>."""
         self.n, self.rank, self.world = n, rank, world
+        lib().emu_set_support(C.c_uint64(0xFFFFFFFFFFFFFFFF if support is None else support))
         cfg = OPS.make_config(n, rank=rank, world_size=world, **cfgkw)
         arr, cnt, self._keep = OPS.encode_ops(ops)
         h = C.c_void_p()

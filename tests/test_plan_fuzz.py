@@ -212,3 +212,36 @@ def test_wire_formats_round_trip_random_circuits(seed):
     back = Q.qasm_to_circuit(Q.circuit_to_qasm(plain))
     b, nb, _k2 = OPS.encode_ops(back["operations"])
     assert na == nb and bytes(a) == bytes(b)
+
+
+def test_known_zero_state_support_skips_tiles_and_keeps_results():
+    """EXPERIMENTAL path (csrc/plan.h: Plan::support_in, off unless QCB_ZERO_SKIP=1): a plan that is told its input is |0...0>
+    visits only the tiles that can hold non-zero amplitudes - same results as the oracle on random circuits over the whole
+    vocabulary (Grover operators, fusion off, sharded worlds), the first sweeps shrink, and the claim matters (a dense state
+    run under it comes out wrong: the tiles really are skipped)."""
+    for seed in range(9000, 9120):
+        rng = np.random.default_rng(seed)
+        world = int(rng.choice([1, 1, 2, 4]))
+        p = world.bit_length() - 1
+        n = int(rng.integers(max(4, p + 3), 13))
+        nl = n - p
+        tile = int(rng.integers(min(3, nl), min(nl, 9) + 1))
+        low = int(rng.integers(1, max(2, min(tile, 4)) + 1))
+        circ = random_circuit(n, rng, int(rng.integers(5, 70)), grover=(seed % 3 == 0))
+        init = np.zeros(1 << n, dtype=complex); init[0] = 1.0
+        got = E.run_world(n, circ["operations"], init, world=world, tile_bits=tile, low_bits=low, fusion=int(seed % 5 != 0), support=0)
+        err = float(np.max(np.abs(got - _reference(circ, init))))
+        assert err <= TOL, f"seed {seed}: n={n} world={world} tile={tile} low={low} err={err}"
+    n = 14
+    circ = C.random_brickwork_circuit(n, 8)
+    known = E.EmuPlan(n, circ["operations"], tile_bits=6, low_bits=2, support=0)
+    plain = E.EmuPlan(n, circ["operations"], tile_bits=6, low_bits=2)
+    fk = [known.stage_info(i)["fraction"] for i in range(known.num_stages)]
+    fp = [plain.stage_info(i)["fraction"] for i in range(plain.num_stages)]
+    assert fk[0] == 2.0 ** -(n - 6) and fk[0] < fk[1] < fk[2] <= 1.0 and fp[0] == 1.0
+    assert all(a <= b for a, b in zip(fk, fp))
+    rng = np.random.default_rng(1)
+    dense = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    dense /= np.linalg.norm(dense)
+    wrong = E.run_world(n, circ["operations"], dense, tile_bits=6, low_bits=2, support=0)
+    assert np.max(np.abs(wrong - _reference(circ, dense))) > 1e-3
